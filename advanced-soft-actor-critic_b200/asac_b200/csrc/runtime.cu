@@ -1,0 +1,24 @@
+// Error string, version and launch accounting of libasac_b200.so.
+#include <atomic>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace asac {
+static thread_local char g_error[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace asac
+
+extern "C" const char *asac_last_error(void) { return asac::g_error; }
+extern "C" int asac_version(void) { return 100; }
+extern "C" int64_t asac_launch_count(void) { return asac::g_launches.load(std::memory_order_relaxed); }
+extern "C" void asac_reset_launch_count(void) { asac::g_launches.store(0, std::memory_order_relaxed); }

@@ -1,0 +1,1059 @@
+// Fused SAC update kernels (sm_100a): value pass (_get_y / get_l_probs / _get_td_error /
+// alpha loss), critic forward+loss+backward, policy forward+backward, gradient reduction,
+// Adam and the Polyak target update.
+//
+// Replaces the torch op graph of SAC_Base._train and friends for the continuous-action,
+// stock-network case (algorithm/sac_base.py:745-764, 1159-1189, 1244-1466, 1468-1605,
+// 1841-1949, 2027-2126, 2182-2245).  Exact formulas and the reference quirks that are
+// reproduced on purpose are listed in DESIGN.md §5.
+#include <math.h>
+
+#include "common.cuh"
+#include "mlp_tile.cuh"
+
+namespace asac {
+
+struct SacArgs {
+    AsacSacConfig cfg;
+    AsacSacParams prm;
+    AsacSacBatch bat;
+    AsacSacWork wrk;
+    int tile_batch;  // batch elements per CTA
+    int mode;        // value pass: 0 = train (_get_y), 1 = post (alpha loss, l_probs, td error)
+};
+
+__host__ __device__ __forceinline__ NetShape q_shape(const AsacSacConfig &c) {
+    return NetShape{c.state_size + c.action_size, c.q_hidden, c.q_depth, 1};
+}
+__host__ __device__ __forceinline__ NetShape pi_shape(const AsacSacConfig &c) {
+    return NetShape{c.state_size, c.pi_hidden, c.pi_depth, 2 * c.action_size};
+}
+__host__ __device__ __forceinline__ int sac_lda(const AsacSacConfig &c) {
+    const int a = tile_lda(c.q_hidden, c.state_size + c.action_size), b = tile_lda(c.pi_hidden, c.state_size);
+    return a > b ? a : b;
+}
+__host__ __device__ __forceinline__ int sac_wsz(const AsacSacConfig &c) {
+    const int a = tile_wsz(c.q_hidden, c.state_size + c.action_size), b = tile_wsz(c.pi_hidden, c.state_size);
+    return round_up(a > b ? a : b, 4);
+}
+
+constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
+
+// torch.distributions.Normal.log_prob: -((x - loc)^2) / (2 var) - log(scale) - log(sqrt(2 pi))
+__device__ __forceinline__ float normal_log_prob(float x, float loc, float scale) {
+    const float var = scale * scale;
+    const float d = x - loc;
+    return -(d * d) / (2.f * var) - logf(scale) - LOG_SQRT_2PI;
+}
+// max(1 - tanh(x)^2, 1e-2)   (utils/operators.py:14,19)
+__device__ __forceinline__ float squash_floor(float x) {
+    const float t = tanhf(x);
+    return fmaxf(1.f - t * t, 1e-2f);
+}
+// policy.py:169
+__device__ __forceinline__ float policy_loc(float m) { return tanhf(m / 5.f) * 5.f; }
+__device__ __forceinline__ float policy_scale(float s) { return expf(fminf(fmaxf(s, -20.f), 0.5f)); }
+
+__device__ __forceinline__ float block_sum(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < NT / 32; ++w) s += red[w];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------ smem plans
+struct ValuePlan {
+    int lda, wsz, rows_max;  // rows_max: multiple of 16
+    int off_xin, off_a, off_b, off_w0, off_w1, off_ho, off_xs, off_logp, off_qmin, off_ratio, off_qs, off_red;
+    int total;  // floats
+};
+__host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c, int TB, int mode) {
+    ValuePlan p;
+    const int L = c.seq_len, n = c.n_step, A = c.action_size;
+    const int t0 = (mode == 1 && c.use_n_step_is) ? 0 : c.burn_in;
+    const int Lp = L - t0;
+    const int rp = round_up(TB * Lp, PASS_ROWS);
+    const int rq = round_up(TB * (n + 1), PASS_ROWS) + round_up(TB, PASS_ROWS);
+    p.rows_max = rp > rq ? rp : rq;
+    p.lda = sac_lda(c);
+    p.wsz = sac_wsz(c);
+    int o = 0;
+    p.off_xin = o; o += p.rows_max * p.lda;
+    p.off_a = o; o += p.rows_max * p.lda;
+    p.off_b = o; o += p.rows_max * p.lda;
+    p.off_w0 = o; o += p.wsz;
+    p.off_w1 = o; o += p.wsz;
+    p.off_ho = o; o += round_up(rp * 2 * A, 4);
+    p.off_xs = o; o += round_up(TB * (n + 1) * A, 4);
+    p.off_logp = o; o += round_up(TB * (n + 1), 4);
+    p.off_qmin = o; o += round_up(p.rows_max, 4);
+    p.off_ratio = o; o += round_up(TB * (n > 0 ? n : 1), 4);
+    p.off_qs = o; o += round_up(c.ensemble * TB, 4);
+    p.off_red = o; o += 8;
+    p.total = o;
+    return p;
+}
+
+struct GradPlan {
+    int lda, wsz;
+    int off_px, off_pz, off_qz, off_qin, off_g0, off_g1, off_g2, off_w0, off_w1, off_small, off_red;
+    int total;
+};
+// critic: px/pz hold the critic's activations, qz unused.  policy: px/pz policy, qz critics' z.
+__host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, bool policy) {
+    GradPlan p;
+    p.lda = sac_lda(c);
+    p.wsz = sac_wsz(c);
+    const int rows = PASS_ROWS;
+    const int d = policy ? c.pi_depth : c.q_depth;
+    int o = 0;
+    p.off_px = o; o += (d + 1) * rows * p.lda;
+    p.off_pz = o; o += d * rows * p.lda;
+    p.off_qz = o; o += policy ? c.ensemble * c.q_depth * rows * p.lda : 0;
+    p.off_qin = o; o += policy ? rows * p.lda : 0;
+    p.off_g0 = o; o += rows * p.lda;
+    p.off_g1 = o; o += rows * p.lda;
+    p.off_g2 = o; o += rows * p.lda;
+    p.off_w0 = o; o += p.wsz;
+    p.off_w1 = o; o += p.wsz;
+    p.off_small = o; o += round_up(rows * (6 * c.action_size + c.ensemble + 4), 4);
+    p.off_red = o; o += 8;
+    p.total = o;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------ value pass
+// mode 0: y = _get_y(...) on the online policy / target critics (sac_base.py:1297-1466) and
+//         tq_i = target-Q_i(s_b, a_b) (sac_base.py:1541).
+// mode 1: after the three Adam steps — alpha-loss terms (:1930-1945), pi_probs = get_l_probs
+//         (:1159-1189), y' = _get_y with mu := pi_probs and td = mean_i |Q_i(s_b,a_b) - y'|
+//         (:2182-2245).
+__global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacArgs a) {
+    extern __shared__ float4 smem4[];
+    float *sm = reinterpret_cast<float *>(smem4);
+    const AsacSacConfig &c = a.cfg;
+    const int tid = threadIdx.x;
+    const int B = c.batch, L = c.seq_len, b = c.burn_in, n = c.n_step, S = c.state_size, A = c.action_size;
+    const int E = c.ensemble, TB = a.tile_batch;
+    const bool post = a.mode == 1;
+    const bool use_is = c.use_n_step_is != 0;
+    const int e0 = blockIdx.x * TB;
+    const int TBa = min(TB, B - e0);
+    const int t0 = (post && use_is) ? 0 : b;
+    const int Lp = L - t0;
+    const int RP = TBa * Lp, RV = TBa * (n + 1), RS = TBa;
+    const bool need_tq = !post && c.clip_epsilon > 0.f;
+    const ValuePlan pl = value_plan(c, TB, a.mode);
+    const int lda = pl.lda;
+    float *xin = sm + pl.off_xin, *bufA = sm + pl.off_a, *bufB = sm + pl.off_b;
+    float *ho = sm + pl.off_ho, *xs = sm + pl.off_xs, *logp = sm + pl.off_logp, *qmin = sm + pl.off_qmin;
+    float *ratio = sm + pl.off_ratio, *qs = sm + pl.off_qs, *red = sm + pl.off_red;
+    TileSmem ts;
+    ts.w[0] = sm + pl.off_w0; ts.w[1] = sm + pl.off_w1;
+
+    const NetShape ps = pi_shape(c), qsh = q_shape(c);
+    const int64_t q_stride = net_stride(qsh);
+
+    // ---- policy over the P rows
+    {
+        const int S4 = round_up(S, 4);
+        const int RPp = round_up(RP, PASS_ROWS);
+        for (int i = tid; i < RPp * S4; i += NT) {
+            const int r = i / S4, col = i - r * S4;
+            float v = 0.f;
+            if (r < RP && col < S) {
+                const int e = r / Lp, tt = r - e * Lp;
+                v = a.bat.states[((int64_t)(e0 + e) * L + t0 + tt) * S + col];
+            }
+            xin[r * lda + col] = v;
+        }
+        ts.bias[0] = ts.w[0] + ps.hidden * tile_lda(ps.hidden, ps.in_dim);
+        ts.bias[1] = ts.w[1] + ps.hidden * tile_lda(ps.hidden, ps.in_dim);
+        float *h = net_trunk_forward(ps, a.prm.pi, ts, xin, bufA, bufB, nullptr, nullptr, lda, RPp);
+        head_forward(h, lda, ps.hidden, a.prm.pi + net_w_off(ps, ps.depth), a.prm.pi + net_b_off(ps, ps.depth),
+                     2 * A, RP, ho);
+        __syncthreads();
+    }
+
+    // ---- per P row: distribution, sampled action, log-probs, IS ratio, pi_probs, alpha terms
+    float alpha_term = 0.f, alpha_loss = 0.f;
+    const float log_alpha = a.prm.log_alpha[0];
+    for (int r = tid; r < RP; r += NT) {
+        const int e = r / Lp, tt = r - e * Lp, t = t0 + tt, eg = e0 + e;
+        float *hr = ho + r * 2 * A;
+        for (int j = 0; j < A; ++j) {
+            const float m = hr[j], s = hr[A + j];
+            hr[j] = policy_loc(m);
+            hr[A + j] = policy_scale(s);
+        }
+        if (t >= b) {  // value row k = t - b
+            const int k = t - b, rv = e * (n + 1) + k;
+            const float *eps = (post ? a.bat.eps_td : a.bat.eps_y) + ((int64_t)eg * (n + 1) + k) * A;
+            float corr = 0.f;
+            for (int j = 0; j < A; ++j) {
+                const float x = hr[j] + eps[j] * hr[A + j];  // Normal.rsample: loc + eps * scale
+                xs[rv * A + j] = x;
+                corr += logf(squash_floor(x));
+            }
+            float lp_sum = 0.f;
+            for (int j = 0; j < A; ++j) {
+                float lp = normal_log_prob(xs[rv * A + j], hr[j], hr[A + j]) - corr;  // operators.py:12-14
+                if (lp == INFINITY) lp = 0.f;                                         // operators.py:23
+                lp_sum += lp;
+            }
+            logp[rv] = lp_sum;
+        }
+        if (use_is && t < L - 1) {  // pi / mu of the stored action (sac_base.py:1450-1455, 1159-1189)
+            const float *act = a.bat.actions + ((int64_t)eg * c.bn_stride + t) * A;
+            float fl = 1.f;
+            for (int j = 0; j < A; ++j) fl *= squash_floor(atanhf(fminf(fmaxf(act[j], -0.999f), 0.999f)));
+            float pi_prod = 1.f, mu_prod = 1.f;
+            for (int j = 0; j < A; ++j) {
+                const float xa = atanhf(fminf(fmaxf(act[j], -0.999f), 0.999f));
+                float pj = expf(normal_log_prob(xa, hr[j], hr[A + j])) / fl;  // operators.py:17-19
+                float mj;
+                if (post) {
+                    a.wrk.pi_probs[((int64_t)eg * (L - 1) + t) * A + j] = pj;
+                    mj = pj;
+                } else {
+                    mj = a.bat.mu_probs[((int64_t)eg * c.bn_stride + t) * A + j];
+                }
+                if (isinf(pj)) pj = 1.f;  // prod_prob, operators.py:27-31
+                if (isinf(mj)) mj = 1.f;
+                pi_prod *= pj;
+                mu_prod *= mj;
+            }
+            if (isinf(pi_prod) || isnan(pi_prod)) pi_prod = 1.f;
+            if (isinf(mu_prod) || isnan(mu_prod)) mu_prod = 1.f;
+            if (t >= b) ratio[e * n + (t - b)] = pi_prod / fmaxf(mu_prod, 1e-8f);  // sac_base.py:1275
+        }
+        if (post && c.use_auto_alpha && t == b) {  // sac_base.py:1931-1939
+            const float *eps = a.bat.eps_alpha + (int64_t)eg * A;
+            float corr = 0.f;
+            for (int j = 0; j < A; ++j) corr += logf(squash_floor(hr[j] + eps[j] * hr[A + j]));
+            float lp_sum = 0.f;
+            int valid = 0;
+            for (int j = 0; j < A; ++j) {
+                const float x = hr[j] + eps[j] * hr[A + j];  // Normal.sample == torch.normal(loc, scale)
+                float lp = normal_log_prob(x, hr[j], hr[A + j]) - corr;
+                if (lp != INFINITY) ++valid; else lp = 0.f;
+                lp_sum += lp;
+            }
+            const float target = c.target_c_alpha * (float)(-valid);
+            const float term = -lp_sum - target;
+            alpha_term += term;
+            alpha_loss += log_alpha * term;
+        }
+    }
+    __syncthreads();
+
+    // ---- critic inputs: V rows [state(e, b+k), tanh(x)], then S rows [state(e, b), stored action]
+    const int K0 = S + A, K04 = round_up(K0, 4);
+    const int RVp = round_up(RV, PASS_ROWS);
+    const int s_row0 = post ? RVp : RV;  // post: S rows go through the online critics separately
+    const int rows_all = round_up(s_row0 + RS, PASS_ROWS);
+    for (int i = tid; i < rows_all * K04; i += NT) {
+        const int r = i / K04, col = i - r * K04;
+        float v = 0.f;
+        if (r < RV) {
+            const int e = r / (n + 1), k = r - e * (n + 1);
+            if (col < S) v = a.bat.states[((int64_t)(e0 + e) * L + b + k) * S + col];
+            else if (col < K0) v = tanhf(xs[r * A + (col - S)]);
+        } else if (r >= s_row0 && r < s_row0 + RS) {
+            const int e = r - s_row0;
+            if (col < S) v = a.bat.states[((int64_t)(e0 + e) * L + b) * S + col];
+            else if (col < K0) v = a.bat.actions[((int64_t)(e0 + e) * c.bn_stride + b) * A + (col - S)];
+        }
+        xin[r * lda + col] = v;
+    }
+    ts.bias[0] = ts.w[0] + qsh.hidden * tile_lda(qsh.hidden, qsh.in_dim);
+    ts.bias[1] = ts.w[1] + qsh.hidden * tile_lda(qsh.hidden, qsh.in_dim);
+    __syncthreads();
+
+    // ---- target critics over the V rows (+ S rows for the clipped loss)
+    {
+        const int rq = need_tq ? RV + RS : RV;
+        const int rqp = round_up(rq, PASS_ROWS);
+        for (int i = 0; i < E; ++i) {
+            const float *prm = a.prm.q_target + i * q_stride;
+            float *h = net_trunk_forward(qsh, prm, ts, xin, bufA, bufB, nullptr, nullptr, lda, rqp);
+            float *qo = (h == bufA ? bufB : bufA);  // free buffer: head outputs [rq]
+            head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, rq,
+                         qo);
+            __syncthreads();
+            for (int r = tid; r < rq; r += NT) {
+                if (r < RV) qmin[r] = (i == 0) ? qo[r] : fminf(qmin[r], qo[r]);  // sac_base.py:1439-1442
+                else a.wrk.tq[(int64_t)i * B + e0 + (r - RV)] = qo[r];
+            }
+            __syncthreads();
+        }
+    }
+    // ---- post: online critics over the S rows (sac_base.py:2211-2216)
+    if (post) {
+        for (int i = 0; i < E; ++i) {
+            const float *prm = a.prm.q + i * q_stride;
+            float *h = net_trunk_forward(qsh, prm, ts, xin + s_row0 * lda, bufA, bufB, nullptr, nullptr, lda,
+                                         round_up(RS, PASS_ROWS));
+            head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, RS,
+                         qs + i * TB);
+            __syncthreads();
+        }
+    }
+
+    // ---- per batch element: V, v-trace, y (sac_base.py:1244-1295, 1444-1464)
+    if (tid < TBa) {
+        const int e = tid, eg = e0 + e;
+        const float alpha = expf(log_alpha);
+        float v_prev = qmin[e * (n + 1)] - alpha * logp[e * (n + 1)];
+        const float v0 = v_prev;
+        float sum = 0.f, cprod = 1.f;
+        for (int k = 0; k < n; ++k) {
+            const float v_next = qmin[e * (n + 1) + k + 1] - alpha * logp[e * (n + 1) + k + 1];
+            const int64_t idx = (int64_t)eg * c.bn_stride + b + k;
+            const float nd = a.bat.dones[idx] ? 0.f : 1.f;
+            float td = a.bat.rewards[idx] + (c.gamma * nd) * v_next - v_prev;
+            td = c.gamma_ratio[k] * td;
+            if (use_is) {
+                td = c.lambda_ratio[k] * td;
+                const float is = ratio[e * n + k];
+                const float rho = fminf(is, c.v_rho);
+                td = (cprod * rho) * td;
+                cprod = cprod * fminf(is, c.v_c);
+            }
+            const float keep = (a.bat.last_masks[idx] | a.bat.padding_masks[idx]) ? 0.f : 1.f;
+            sum += td * keep;
+            v_prev = v_next;
+        }
+        const float y = v0 + sum;
+        if (!post) {
+            a.wrk.y[eg] = y;
+        } else {
+            a.wrk.y_td[eg] = y;
+            float acc = 0.f;
+            for (int i = 0; i < E; ++i) acc += fabsf(qs[i * TB + e] - y);
+            a.wrk.td_error[eg] = acc / (float)E;
+        }
+    }
+    if (post && c.use_auto_alpha) {
+        const float s0 = block_sum(alpha_term, red);
+        const float s1 = block_sum(alpha_loss, red);
+        if (tid == 0) {
+            a.wrk.grad_alpha_part[blockIdx.x * 2 + 0] = s0;
+            a.wrk.grad_alpha_part[blockIdx.x * 2 + 1] = s1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ critic
+// grid (n_tiles, E): forward of Q_i on (s_b, a_b), clipped double loss, backward
+// (sac_base.py:1516, 1539-1570).  Partial gradients are sums over the tile's rows of
+// d(sum_i mean_B loss_i)/d theta_i.
+__global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacArgs a) {
+    extern __shared__ float4 smem4[];
+    float *sm = reinterpret_cast<float *>(smem4);
+    const AsacSacConfig &c = a.cfg;
+    const int tid = threadIdx.x;
+    const int B = c.batch, L = c.seq_len, b = c.burn_in, S = c.state_size, A = c.action_size, E = c.ensemble;
+    const int TB = a.tile_batch, e0 = blockIdx.x * TB, TBa = min(TB, B - e0), net = blockIdx.y;
+    const GradPlan pl = grad_plan(c, false);
+    const int lda = pl.lda, R = PASS_ROWS;
+    const NetShape qsh = q_shape(c);
+    const int d = qsh.depth, H = qsh.hidden;
+    const int64_t q_stride = net_stride(qsh);
+    const float *prm = a.prm.q + net * q_stride;
+    float *gout = a.wrk.grad_q_part + ((int64_t)blockIdx.x * E + net) * q_stride;
+
+    float *px[ASAC_MAX_DEPTH + 1], *pz[ASAC_MAX_DEPTH];
+    for (int l = 0; l <= d; ++l) px[l] = sm + pl.off_px + l * R * lda;
+    for (int l = 0; l < d; ++l) pz[l] = sm + pl.off_pz + l * R * lda;
+    float *g[3] = {sm + pl.off_g0, sm + pl.off_g1, sm + pl.off_g2};
+    float *qout = sm + pl.off_small, *dq = qout + R, *red = sm + pl.off_red;
+    TileSmem ts;
+    ts.w[0] = sm + pl.off_w0; ts.w[1] = sm + pl.off_w1;
+    ts.bias[0] = ts.w[0] + H * tile_lda(H, qsh.in_dim);
+    ts.bias[1] = ts.w[1] + H * tile_lda(H, qsh.in_dim);
+
+    const int K0 = S + A, K04 = round_up(K0, 4);
+    for (int i = tid; i < R * K04; i += NT) {
+        const int r = i / K04, col = i - r * K04;
+        float v = 0.f;
+        if (r < TBa) {
+            if (col < S) v = a.bat.states[((int64_t)(e0 + r) * L + b) * S + col];
+            else if (col < K0) v = a.bat.actions[((int64_t)(e0 + r) * c.bn_stride + b) * A + (col - S)];
+        }
+        px[0][r * lda + col] = v;
+    }
+    net_trunk_forward(qsh, prm, ts, px[0], nullptr, nullptr, px, pz, lda, R);
+    head_forward(px[d], lda, H, prm + net_w_off(qsh, d), prm + net_b_off(qsh, d), 1, TBa, qout);
+    __syncthreads();
+
+    float loss = 0.f;
+    if (tid < R) {
+        float gq = 0.f;
+        if (tid < TBa) {
+            const int eg = e0 + tid;
+            const float q = qout[tid], y = a.wrk.y[eg];
+            const float w = (c.use_priority && a.bat.priority_is) ? a.bat.priority_is[eg] : 1.f;
+            float l, gl;
+            if (c.clip_epsilon > 0.f) {
+                const float tq = a.wrk.tq[(int64_t)net * B + eg];
+                const float diff = q - tq;
+                const float cl = fminf(fmaxf(diff, -c.clip_epsilon), c.clip_epsilon);
+                const float cq = tq + cl;
+                const float la = (cq - y) * (cq - y), lb = (q - y) * (q - y);
+                const float ga = (diff >= -c.clip_epsilon && diff <= c.clip_epsilon) ? 2.f * (cq - y) : 0.f;
+                const float gb = 2.f * (q - y);
+                l = fmaxf(la, lb);
+                gl = la > lb ? ga : (la < lb ? gb : 0.5f * (ga + gb));  // torch.maximum splits ties
+            } else {
+                l = (q - y) * (q - y);
+                gl = 2.f * (q - y);
+            }
+            loss = l * w;
+            gq = (gl * w) / (float)B;
+            a.wrk.q_val[(int64_t)net * B + eg] = q;
+        }
+        dq[tid] = gq;
+    }
+    loss = block_sum(loss, red);  // contains the barrier that publishes dq
+    if (tid == 0) a.wrk.loss_q[blockIdx.x * E + net] = loss;
+
+    // head backward, then the ResBlocks in reverse
+    head_backward(dq, 1, px[d], lda, H, prm + net_w_off(qsh, d), R, gout + net_w_off(qsh, d),
+                  gout + net_b_off(qsh, d), g[0], lda);
+    int cur = 0;
+    for (int l = d - 1; l >= 0; --l) {
+        const int K = net_k(qsh, l);
+        if (l > 0) {
+            stage_weights(ts.w[l & 1], nullptr, prm + net_w_off(qsh, l), nullptr, H, H, true);
+            cp_async_commit();
+        }
+        __syncthreads();
+        float *dY = g[cur], *dZ = g[(cur + 1) % 3], *dX = g[(cur + 2) % 3];
+        for (int i = tid; i < R * H; i += NT) {
+            const int r = i / H, j = i - r * H;
+            dZ[r * lda + j] = r < TBa ? dY[r * lda + j] * gelu_erf_grad(pz[l][r * lda + j]) : 0.f;
+        }
+        __syncthreads();
+        layer_weight_grad(dZ, lda, px[l], lda, H, K, TBa, gout + net_w_off(qsh, l), gout + net_b_off(qsh, l));
+        if (l > 0) {
+            cp_async_wait<0>();
+            __syncthreads();
+            layer_input_grad(H, dZ, lda, ts.w[l & 1], dY, dX, R, true);
+            cur = (cur + 2) % 3;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ policy
+// grid (n_tiles): policy forward on s_b, rsample, critics on (s_b, tanh x), min, backward
+// through the critics to the action and through the policy (sac_base.py:1882-1908).
+__global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ SacArgs a) {
+    extern __shared__ float4 smem4[];
+    float *sm = reinterpret_cast<float *>(smem4);
+    const AsacSacConfig &c = a.cfg;
+    const int tid = threadIdx.x;
+    const int B = c.batch, L = c.seq_len, b = c.burn_in, S = c.state_size, A = c.action_size, E = c.ensemble;
+    const int TB = a.tile_batch, e0 = blockIdx.x * TB, TBa = min(TB, B - e0);
+    const GradPlan pl = grad_plan(c, true);
+    const int lda = pl.lda, R = PASS_ROWS;
+    const NetShape ps = pi_shape(c), qsh = q_shape(c);
+    const int dp = ps.depth, Hp = ps.hidden, dqn = qsh.depth, Hq = qsh.hidden;
+    const int64_t q_stride = net_stride(qsh), pi_stride = net_stride(ps);
+    float *gout = a.wrk.grad_pi_part + (int64_t)blockIdx.x * pi_stride;
+
+    float *px[ASAC_MAX_DEPTH + 1], *pz[ASAC_MAX_DEPTH];
+    for (int l = 0; l <= dp; ++l) px[l] = sm + pl.off_px + l * R * lda;
+    for (int l = 0; l < dp; ++l) pz[l] = sm + pl.off_pz + l * R * lda;
+    float *qin = sm + pl.off_qin;
+    float *g[3] = {sm + pl.off_g0, sm + pl.off_g1, sm + pl.off_g2};
+    // small: ho[R][2A] (m,s -> mu,sigma), xs[R][A], da[R][A], qv[E][R], dq[R], amin[R]
+    float *ho = sm + pl.off_small, *xs = ho + R * 2 * A, *da = xs + R * A, *qv = da + R * A, *dq = qv + E * R;
+    float *amin = dq + R, *dO = amin + R;  // dO aliases nothing: sized below
+    float *red = sm + pl.off_red;
+    TileSmem ts;
+    ts.w[0] = sm + pl.off_w0; ts.w[1] = sm + pl.off_w1;
+
+    // ---- policy forward (saved)
+    const int S4 = round_up(S, 4);
+    for (int i = tid; i < R * S4; i += NT) {
+        const int r = i / S4, col = i - r * S4;
+        px[0][r * lda + col] = (r < TBa && col < S) ? a.bat.states[((int64_t)(e0 + r) * L + b) * S + col] : 0.f;
+    }
+    ts.bias[0] = ts.w[0] + Hp * tile_lda(Hp, ps.in_dim);
+    ts.bias[1] = ts.w[1] + Hp * tile_lda(Hp, ps.in_dim);
+    net_trunk_forward(ps, a.prm.pi, ts, px[0], nullptr, nullptr, px, pz, lda, R);
+    head_forward(px[dp], lda, Hp, a.prm.pi + net_w_off(ps, dp), a.prm.pi + net_b_off(ps, dp), 2 * A, TBa, ho);
+    __syncthreads();
+
+    // ---- sample, critic input
+    const int K0 = S + A, K04 = round_up(K0, 4);
+    for (int i = tid; i < R * K04; i += NT) {
+        const int r = i / K04, col = i - r * K04;
+        float v = 0.f;
+        if (r < TBa) {
+            if (col < S) {
+                v = px[0][r * lda + col];
+            } else if (col < K0) {
+                const int j = col - S;
+                const float mu = policy_loc(ho[r * 2 * A + j]), sg = policy_scale(ho[r * 2 * A + A + j]);
+                const float x = mu + a.bat.eps_pi[(int64_t)(e0 + r) * A + j] * sg;
+                xs[r * A + j] = x;
+                v = tanhf(x);
+            }
+        }
+        qin[r * lda + col] = v;
+    }
+    for (int i = tid; i < R * A; i += NT) da[i] = 0.f;
+    ts.bias[0] = ts.w[0] + Hq * tile_lda(Hq, qsh.in_dim);
+    ts.bias[1] = ts.w[1] + Hq * tile_lda(Hq, qsh.in_dim);
+    __syncthreads();
+
+    // ---- critics forward (z saved)
+    for (int i = 0; i < E; ++i) {
+        const float *prm = a.prm.q + i * q_stride;
+        float *qz[ASAC_MAX_DEPTH];
+        for (int l = 0; l < dqn; ++l) qz[l] = sm + pl.off_qz + (i * dqn + l) * R * lda;
+        float *h = net_trunk_forward(qsh, prm, ts, qin, g[0], g[1], nullptr, qz, lda, R);
+        head_forward(h, lda, Hq, prm + net_w_off(qsh, dqn), prm + net_b_off(qsh, dqn), 1, TBa, qv + i * R);
+        __syncthreads();
+    }
+    if (tid < R) {
+        int best = 0;
+        if (tid < TBa) {
+            float m = qv[tid];
+            for (int i = 1; i < E; ++i)
+                if (qv[i * R + tid] < m) { m = qv[i * R + tid]; best = i; }
+        }
+        amin[tid] = (float)best;
+    }
+    __syncthreads();
+
+    // ---- backward through each critic to its action input; d loss / d q_min = -1/B
+    for (int i = 0; i < E; ++i) {
+        const float *prm = a.prm.q + i * q_stride;
+        if (tid < R) dq[tid] = (tid < TBa && (int)amin[tid] == i) ? -1.f / (float)B : 0.f;
+        __syncthreads();
+        head_backward(dq, 1, nullptr, lda, Hq, prm + net_w_off(qsh, dqn), R, nullptr, nullptr, g[0], lda);
+        int cur = 0;
+        for (int l = dqn - 1; l >= 0; --l) {
+            if (l > 0) {
+                stage_weights(ts.w[l & 1], nullptr, prm + net_w_off(qsh, l), nullptr, Hq, Hq, true);
+                cp_async_commit();
+            }
+            __syncthreads();
+            float *dY = g[cur], *dZ = g[(cur + 1) % 3], *dX = g[(cur + 2) % 3];
+            const float *z = sm + pl.off_qz + (i * dqn + l) * R * lda;
+            for (int t = tid; t < R * Hq; t += NT) {
+                const int r = t / Hq, j = t - r * Hq;
+                dZ[r * lda + j] = r < TBa ? dY[r * lda + j] * gelu_erf_grad(z[r * lda + j]) : 0.f;
+            }
+            __syncthreads();
+            if (l > 0) {
+                cp_async_wait<0>();
+                __syncthreads();
+                layer_input_grad(Hq, dZ, lda, ts.w[l & 1], dY, dX, R, true);
+                cur = (cur + 2) % 3;
+            } else {
+                // first layer: only the action columns of the input gradient are needed
+                const float *W0 = prm + net_w_off(qsh, 0);
+                for (int t = tid; t < TBa * A; t += NT) {
+                    const int r = t / A, j = t - r * A;
+                    float s = 0.f;
+                    for (int h = 0; h < Hq; ++h) s = fmaf(dZ[r * lda + h], __ldg(W0 + (int64_t)h * K0 + S + j), s);
+                    if (K0 == Hq) s += dY[r * lda + S + j];  // residual first block
+                    da[r * A + j] += s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- d loss / d (mean, logstd) pre-activations; loss and entropy sums
+    float loss = 0.f, ent = 0.f;
+    const float alpha = expf(a.prm.log_alpha[0]);
+    for (int i = tid; i < R * 2 * A; i += NT) dO[i] = 0.f;
+    __syncthreads();
+    if (tid < TBa) {
+        const int r = tid;
+        float corr = 0.f, qm = qv[(int)amin[r] * R + r];
+        for (int j = 0; j < A; ++j) corr += logf(squash_floor(xs[r * A + j]));
+        float lp_sum = 0.f;
+        for (int j = 0; j < A; ++j) {
+            const float m = ho[r * 2 * A + j], s = ho[r * 2 * A + A + j];
+            const float mu = policy_loc(m), sg = policy_scale(s);
+            const float x = xs[r * A + j], eps = a.bat.eps_pi[(int64_t)(e0 + r) * A + j];
+            float lp = normal_log_prob(x, mu, sg) - corr;
+            const bool lp_inf = (lp == INFINITY);
+            if (lp_inf) lp = 0.f;
+            lp_sum += lp;
+            const float e1 = 0.5f + LOG_SQRT_2PI + logf(sg);  // Normal.entropy
+            ent += (e1 == INFINITY) ? 0.f : e1;
+            // d/dx of alpha * (-A * log max(1 - tanh^2 x, 1e-2)): every action dim carries the summed
+            // Jacobian term (operators.py:12-14), hence the factor A
+            const float t = tanhf(x), one_m = 1.f - t * t;
+            const float dcorr = one_m > 1e-2f ? 2.f * t : (one_m == 1e-2f ? t : 0.f);
+            const float dx = (alpha * (float)A * dcorr) / (float)B + da[r * A + j] * one_m;
+            // the Normal.log_prob(rsample) terms cancel analytically except -log(scale)
+            const float dsig = dx * eps - alpha / ((float)B * sg);
+            const float th = tanhf(m / 5.f);
+            dO[r * 2 * A + j] = dx * (1.f - th * th);
+            dO[r * 2 * A + A + j] = (s >= -20.f && s <= 0.5f) ? dsig * sg : 0.f;
+        }
+        loss = alpha * lp_sum - qm;
+    }
+    loss = block_sum(loss, red);
+    ent = block_sum(ent, red);
+    if (tid == 0) {
+        a.wrk.stats_pi[blockIdx.x * 2 + 0] = loss;
+        a.wrk.stats_pi[blockIdx.x * 2 + 1] = ent;
+    }
+
+    // ---- policy backward
+    head_backward(dO, 2 * A, px[dp], lda, Hp, a.prm.pi + net_w_off(ps, dp), R, gout + net_w_off(ps, dp),
+                  gout + net_b_off(ps, dp), g[0], lda);
+    int cur = 0;
+    for (int l = dp - 1; l >= 0; --l) {
+        const int K = net_k(ps, l);
+        if (l > 0) {
+            stage_weights(ts.w[l & 1], nullptr, a.prm.pi + net_w_off(ps, l), nullptr, Hp, Hp, true);
+            cp_async_commit();
+        }
+        __syncthreads();
+        float *dY = g[cur], *dZ = g[(cur + 1) % 3], *dX = g[(cur + 2) % 3];
+        for (int t = tid; t < R * Hp; t += NT) {
+            const int r = t / Hp, j = t - r * Hp;
+            dZ[r * lda + j] = r < TBa ? dY[r * lda + j] * gelu_erf_grad(pz[l][r * lda + j]) : 0.f;
+        }
+        __syncthreads();
+        layer_weight_grad(dZ, lda, px[l], lda, Hp, K, TBa, gout + net_w_off(ps, l), gout + net_b_off(ps, l));
+        if (l > 0) {
+            cp_async_wait<0>();
+            __syncthreads();
+            layer_input_grad(Hp, dZ, lda, ts.w[l & 1], dY, dX, R, true);
+            cur = (cur + 2) % 3;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ optimiser
+// sums the per-tile partials in tile order: out[p] = sum_t part[t * tile_stride + p]
+__device__ __forceinline__ float reduce_partials(const float *part, int n_tiles, int64_t tile_stride, int64_t p) {
+    float s = 0.f;
+    for (int t = 0; t < n_tiles; ++t) s += part[t * tile_stride + p];
+    return s;
+}
+
+struct AdamArgs {
+    float *param, *m, *v;
+    const float *part;      // partial gradients (or nullptr: read `grad`)
+    float *grad;            // reduced gradient (written when part != nullptr and write_grad)
+    const int64_t *step;    // optimizer step counter (value BEFORE this step)
+    int64_t count;          // number of floats
+    int64_t tile_stride;    // stride between tiles in `part`
+    int n_tiles;
+    int write_grad, do_adam;
+    float grad_scale;       // applied to the reduced gradient (1/B folded elsewhere; 1/world for DDP)
+    double lr;
+};
+
+// torch.optim.Adam single-tensor path (betas 0.9/0.999, eps 1e-8, no weight decay / amsgrad)
+__global__ void __launch_bounds__(256) k_reduce_adam(const AdamArgs a) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.count) return;
+    float gr;
+    if (a.part) {
+        gr = reduce_partials(a.part, a.n_tiles, a.tile_stride, p);
+        if (a.write_grad) a.grad[p] = gr;
+    } else {
+        gr = a.grad[p];
+    }
+    if (!a.do_adam) return;
+    gr = gr * a.grad_scale;
+    const double t = (double)(a.step[0] + 1);
+    const double bc1 = 1.0 - pow(0.9, t), bc2 = 1.0 - pow(0.999, t);
+    const float step_size = (float)(-(a.lr / bc1));
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float w1 = (float)(1.0 - 0.9), w2 = (float)(1.0 - 0.999);
+    float m = a.m[p], v = a.v[p];
+    m = m + w1 * (gr - m);                      // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * 0.999f + (w2 * gr) * gr;            // mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
+    a.m[p] = m;
+    a.v[p] = v;
+    a.param[p] = a.param[p] + (step_size * m) / denom;  // addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+// alpha: a single scalar, gradient = (sum over tiles of the alpha terms) / B  (sac_base.py:1941-1948)
+__global__ void k_alpha_adam(const AsacSacParams prm, const AsacSacWork wrk, int n_tiles, int batch, int do_reduce,
+                             int do_adam, float grad_scale, double lr) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float gr;
+    if (do_reduce) {
+        float s = 0.f;
+        for (int t = 0; t < n_tiles; ++t) s += wrk.grad_alpha_part[t * 2];
+        gr = s / (float)batch;
+        wrk.grad_alpha[0] = gr;
+    } else {
+        gr = wrk.grad_alpha[0];
+    }
+    if (!do_adam) return;
+    gr = gr * grad_scale;
+    const double t = (double)(prm.counters[3] + 1);
+    const double bc1 = 1.0 - pow(0.9, t), bc2 = 1.0 - pow(0.999, t);
+    const float step_size = (float)(-(lr / bc1));
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float w1 = (float)(1.0 - 0.9), w2 = (float)(1.0 - 0.999);
+    float m = prm.alpha_m[0], v = prm.alpha_v[0];
+    m = m + w1 * (gr - m);
+    v = v * 0.999f + (w2 * gr) * gr;
+    const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
+    prm.alpha_m[0] = m;
+    prm.alpha_v[0] = v;
+    prm.log_alpha[0] = prm.log_alpha[0] + (step_size * m) / denom;
+}
+
+__global__ void k_bump(int64_t *counters, int mask) {
+    if (threadIdx.x < 4 && ((mask >> threadIdx.x) & 1)) counters[threadIdx.x] += 1;
+}
+
+// sac_base.py:745-764: target = target * (1 - tau) + source * tau, gated on the global step
+__global__ void __launch_bounds__(256) k_polyak(float *target, const float *source, int64_t count,
+                                                const int64_t *counters, int per_step, float tau, float one_m,
+                                                int force) {
+    if (!force && (counters[0] % per_step) != 0) return;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= count) return;
+    target[p] = target[p] * one_m + source[p] * tau;
+}
+
+__global__ void __launch_bounds__(256) k_fill_normal(float *out, int64_t n, uint64_t seed, const int64_t *counter,
+                                                     int stream_id) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 4 outputs per thread
+    if (q * 4 >= n) return;
+    uint32_t r[4];
+    philox4(seed ^ ((uint64_t)stream_id << 56), (uint64_t)counter[0], (uint64_t)q, r);
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float u1 = ((float)(r[2 * h] >> 8) + 1.f) * (1.f / 16777216.f);  // (0, 1]
+        const float u2 = (float)(r[2 * h + 1] >> 8) * (1.f / 16777216.f);      // [0, 1)
+        const float rad = sqrtf(-2.f * logf(u1));
+        float sn, cs;
+        sincospif(2.f * u2, &sn, &cs);
+        z[2 * h] = rad * cs;
+        z[2 * h + 1] = rad * sn;
+    }
+    for (int i = 0; i < 4; ++i)
+        if (q * 4 + i < n) out[q * 4 + i] = z[i];
+}
+
+// standalone stock-net forward (actor side / tests)
+struct MlpArgs {
+    const float *params, *x;
+    float *out;
+    NetShape s;
+    int64_t rows;
+    int rows_per_cta;
+};
+__global__ void __launch_bounds__(NT) k_mlp_forward(const MlpArgs a) {
+    extern __shared__ float4 smem4[];
+    float *sm = reinterpret_cast<float *>(smem4);
+    const int tid = threadIdx.x;
+    const NetShape s = a.s;
+    const int lda = tile_lda(s.hidden, s.in_dim), wsz = round_up(tile_wsz(s.hidden, s.in_dim), 4);
+    const int RC = a.rows_per_cta;
+    const int64_t r0 = (int64_t)blockIdx.x * RC;
+    const int rows = (int)min((int64_t)RC, a.rows - r0);
+    float *xin = sm, *bufA = xin + RC * lda, *bufB = bufA + RC * lda;
+    TileSmem ts;
+    ts.w[0] = bufB + RC * lda; ts.w[1] = ts.w[0] + wsz;
+    ts.bias[0] = ts.w[0] + s.hidden * lda; ts.bias[1] = ts.w[1] + s.hidden * lda;
+    float *ho = ts.w[1] + wsz;
+    const int K4 = round_up(s.in_dim, 4);
+    const int rp = round_up(rows, PASS_ROWS);
+    for (int i = tid; i < rp * K4; i += NT) {
+        const int r = i / K4, col = i - r * K4;
+        xin[r * lda + col] = (r < rows && col < s.in_dim) ? a.x[(r0 + r) * s.in_dim + col] : 0.f;
+    }
+    float *h = net_trunk_forward(s, a.params, ts, xin, bufA, bufB, nullptr, nullptr, lda, rp);
+    head_forward(h, lda, s.hidden, a.params + net_w_off(s, s.depth), a.params + net_b_off(s, s.depth), s.out_dim, rows,
+                 ho);
+    __syncthreads();
+    for (int i = tid; i < rows * s.out_dim; i += NT) a.out[r0 * s.out_dim + i] = ho[i];
+}
+
+}  // namespace asac
+
+using namespace asac;
+
+// ------------------------------------------------------------------------------------ host side
+static int validate(const AsacSacConfig *c) {
+    ASAC_REQUIRE(c != nullptr, "null config");
+    ASAC_REQUIRE(c->batch > 0 && c->seq_len == c->burn_in + c->n_step + 1 && c->n_step >= 1 && c->burn_in >= 0,
+                 "bad batch/sequence sizes (B=%d L=%d b=%d n=%d)", c->batch, c->seq_len, c->burn_in, c->n_step);
+    ASAC_UNSUPPORTED(c->n_step > ASAC_MAX_NSTEP, "n_step %d > %d", c->n_step, ASAC_MAX_NSTEP);
+    ASAC_UNSUPPORTED(c->ensemble < 1 || c->ensemble > ASAC_MAX_ENSEMBLE, "ensemble_q_num %d outside [1, %d]",
+                     c->ensemble, ASAC_MAX_ENSEMBLE);
+    ASAC_UNSUPPORTED(c->q_depth < 1 || c->q_depth > ASAC_MAX_DEPTH || c->pi_depth < 1 || c->pi_depth > ASAC_MAX_DEPTH,
+                     "dense depth outside [1, %d]", ASAC_MAX_DEPTH);
+    const int hs[2] = {c->q_hidden, c->pi_hidden};
+    for (int h : hs)
+        ASAC_UNSUPPORTED(!(h == 16 || h == 32 || h == 64 || h == 128), "hidden width %d not in {16, 32, 64, 128}", h);
+    ASAC_REQUIRE(c->state_size > 0 && c->action_size > 0, "state/action size must be positive");
+    ASAC_UNSUPPORTED(c->action_size > 64, "action_size %d > 64", c->action_size);
+    ASAC_REQUIRE(c->bn_stride >= c->seq_len - 1, "bn_stride %d < L-1", c->bn_stride);
+    ASAC_REQUIRE(c->update_target_per_step >= 1, "update_target_per_step < 1");
+    return ASAC_OK;
+}
+
+static const int kSmemLimit = 227 * 1024;
+
+extern "C" int asac_sac_tile_batch(const AsacSacConfig *c) {
+    if (validate(c) != ASAC_OK) return ASAC_EINVAL;
+    // largest tile <= 16 whose value-pass plan fits in shared memory
+    for (int tb = PASS_ROWS; tb >= 1; tb >>= 1) {
+        const int need0 = value_plan(*c, tb, 0).total * 4, need1 = value_plan(*c, tb, 1).total * 4;
+        if (need0 <= kSmemLimit && need1 <= kSmemLimit) return tb;
+    }
+    set_error("asac_sac_tile_batch: sequence too long for the fused value pass");
+    return ASAC_EUNSUPPORTED;
+}
+
+extern "C" int64_t asac_mlp_param_count(int in_dim, int hidden, int depth, int out_dim) {
+    return net_count(NetShape{in_dim, hidden, depth, out_dim});
+}
+extern "C" int64_t asac_mlp_param_stride(int in_dim, int hidden, int depth, int out_dim) {
+    return net_stride(NetShape{in_dim, hidden, depth, out_dim});
+}
+
+static int make_args(SacArgs &a, const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
+                     const AsacSacWork *wrk) {
+    int rc = validate(cfg);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(prm && wrk, "null params/work");
+    a.cfg = *cfg;
+    a.prm = *prm;
+    if (bat) a.bat = *bat; else memset(&a.bat, 0, sizeof(a.bat));
+    a.wrk = *wrk;
+    a.tile_batch = asac_sac_tile_batch(cfg);
+    if (a.tile_batch < 1) return a.tile_batch;
+    a.mode = 0;
+    const int tiles = (cfg->batch + a.tile_batch - 1) / a.tile_batch;
+    ASAC_REQUIRE(wrk->n_tiles == tiles, "work.n_tiles %d != ceil(B / tile_batch) = %d", wrk->n_tiles, tiles);
+    return ASAC_OK;
+}
+
+// raises the kernel's dynamic shared-memory limit once per (device, kernel); repeated calls with
+// a size already granted do nothing, so CUDA-graph capture never sees an attribute call
+template <typename K>
+static int set_smem(K kernel, int bytes, const char *name) {
+    ASAC_UNSUPPORTED(bytes > kSmemLimit, "%s needs %d bytes of shared memory (> %d)", name, bytes, kSmemLimit);
+    if (bytes <= 48 * 1024) return ASAC_OK;
+    static thread_local int granted[4][16];  // [kernel slot][device]
+    static thread_local const void *slots[4] = {nullptr, nullptr, nullptr, nullptr};
+    int dev = 0;
+    ASAC_CUDA(cudaGetDevice(&dev));
+    int slot = 0;
+    while (slot < 4 && slots[slot] != nullptr && slots[slot] != (const void *)kernel) ++slot;
+    if (slot == 4 || dev >= 16) {
+        ASAC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        return ASAC_OK;
+    }
+    slots[slot] = (const void *)kernel;
+    if (granted[slot][dev] < bytes) {
+        ASAC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        granted[slot][dev] = bytes;
+    }
+    return ASAC_OK;
+}
+
+extern "C" int asac_sac_polyak(const AsacSacConfig *cfg, const AsacSacParams *prm, float force_tau, void *stream) {
+    int rc = validate(cfg);
+    if (rc != ASAC_OK) return rc;
+    const int64_t count = net_stride(q_shape(*cfg)) * cfg->ensemble;
+    const int force = force_tau >= 0.f;
+    k_polyak<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        prm->q_target, prm->q, count, prm->counters, cfg->update_target_per_step, force ? force_tau : cfg->tau,
+        force ? (float)(1.0 - (double)force_tau) : cfg->one_minus_tau, force);
+    ASAC_LAUNCHED("k_polyak");
+    return ASAC_OK;
+}
+
+static int launch_value_pass(SacArgs &a, int mode, void *stream) {
+    a.mode = mode;
+    const int bytes = value_plan(a.cfg, a.tile_batch, mode).total * 4;
+    int rc = set_smem(k_value_pass, bytes, "k_value_pass");
+    if (rc != ASAC_OK) return rc;
+    k_value_pass<<<a.wrk.n_tiles, NT, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_value_pass");
+    return ASAC_OK;
+}
+
+extern "C" int asac_sac_target_y(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
+                                 const AsacSacWork *wrk, void *stream) {
+    SacArgs a;
+    int rc = make_args(a, cfg, prm, bat, wrk);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(bat && bat->states && bat->eps_y, "asac_sac_target_y: missing batch tensors");
+    return launch_value_pass(a, 0, stream);
+}
+
+extern "C" int asac_sac_post(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
+                             const AsacSacWork *wrk, void *stream) {
+    SacArgs a;
+    int rc = make_args(a, cfg, prm, bat, wrk);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(bat && bat->states && bat->eps_td && bat->eps_alpha, "asac_sac_post: missing batch tensors");
+    return launch_value_pass(a, 1, stream);
+}
+
+extern "C" int asac_sac_q_backward(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
+                                   const AsacSacWork *wrk, void *stream) {
+    SacArgs a;
+    int rc = make_args(a, cfg, prm, bat, wrk);
+    if (rc != ASAC_OK) return rc;
+    const int bytes = grad_plan(a.cfg, false).total * 4;
+    rc = set_smem(k_q_backward, bytes, "k_q_backward");
+    if (rc != ASAC_OK) return rc;
+    k_q_backward<<<dim3(a.wrk.n_tiles, cfg->ensemble), NT, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_q_backward");
+    return ASAC_OK;
+}
+
+extern "C" int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
+                                        const AsacSacWork *wrk, void *stream) {
+    SacArgs a;
+    int rc = make_args(a, cfg, prm, bat, wrk);
+    if (rc != ASAC_OK) return rc;
+    const int bytes = grad_plan(a.cfg, true).total * 4;
+    rc = set_smem(k_policy_backward, bytes, "k_policy_backward");
+    if (rc != ASAC_OK) return rc;
+    k_policy_backward<<<a.wrk.n_tiles, NT, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_policy_backward");
+    return ASAC_OK;
+}
+
+static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk, int which,
+                              int do_reduce, int do_adam, float grad_scale, void *stream) {
+    int rc = validate(cfg);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(which >= 0 && which <= 2, "which must be 0 (critics), 1 (policy) or 2 (alpha)");
+    if (which == 2) {
+        k_alpha_adam<<<1, 32, 0, (cudaStream_t)stream>>>(*prm, *wrk, wrk->n_tiles, cfg->batch, do_reduce, do_adam,
+                                                        grad_scale, cfg->learning_rate);
+        ASAC_LAUNCHED("k_alpha_adam");
+        return ASAC_OK;
+    }
+    AdamArgs a;
+    if (which == 0) {
+        const int64_t stride = net_stride(q_shape(*cfg));
+        a.param = prm->q; a.m = prm->q_m; a.v = prm->q_v;
+        a.part = do_reduce ? wrk->grad_q_part : nullptr;
+        a.grad = wrk->grad_q;
+        a.step = prm->counters + 1;
+        a.count = stride * cfg->ensemble;
+        a.tile_stride = a.count;
+    } else {
+        const int64_t stride = net_stride(pi_shape(*cfg));
+        a.param = prm->pi; a.m = prm->pi_m; a.v = prm->pi_v;
+        a.part = do_reduce ? wrk->grad_pi_part : nullptr;
+        a.grad = wrk->grad_pi;
+        a.step = prm->counters + 2;
+        a.count = stride;
+        a.tile_stride = stride;
+    }
+    a.n_tiles = wrk->n_tiles;
+    a.write_grad = 1;
+    a.do_adam = do_adam;
+    a.grad_scale = grad_scale;
+    a.lr = cfg->learning_rate;
+    k_reduce_adam<<<(unsigned)((a.count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_reduce_adam");
+    return ASAC_OK;
+}
+
+static int bump(const AsacSacParams *prm, int mask, void *stream) {
+    k_bump<<<1, 32, 0, (cudaStream_t)stream>>>(prm->counters, mask);
+    ASAC_LAUNCHED("k_bump");
+    return ASAC_OK;
+}
+
+extern "C" int asac_sac_reduce_grads(const AsacSacConfig *cfg, const AsacSacWork *wrk, int which, void *stream) {
+    AsacSacParams none;
+    memset(&none, 0, sizeof(none));
+    return launch_reduce_adam(cfg, &none, wrk, which, 1, 0, 1.f, stream);
+}
+
+extern "C" int asac_sac_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk, int which,
+                             float grad_scale, void *stream) {
+    int rc = launch_reduce_adam(cfg, prm, wrk, which, 0, 1, grad_scale, stream);
+    if (rc != ASAC_OK) return rc;
+    return bump(prm, 1 << (which + 1), stream);
+}
+
+extern "C" int asac_sac_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk,
+                                    int which, void *stream) {
+    int rc = launch_reduce_adam(cfg, prm, wrk, which, 1, 1, 1.f, stream);
+    if (rc != ASAC_OK) return rc;
+    return bump(prm, 1 << (which + 1), stream);
+}
+
+extern "C" int asac_sac_advance_step(const AsacSacParams *prm, void *stream) { return bump(prm, 1, stream); }
+
+extern "C" int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
+                             const AsacSacWork *wrk, void *stream) {
+    SacArgs a;
+    int rc = make_args(a, cfg, prm, bat, wrk);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(bat && bat->states && bat->eps_y && bat->eps_pi, "asac_sac_step: missing batch tensors");
+    if ((rc = asac_sac_polyak(cfg, prm, -1.f, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_value_pass(a, 0, stream)) != ASAC_OK) return rc;
+    if ((rc = asac_sac_q_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_reduce_adam(cfg, prm, wrk, 0, 1, 1, 1.f, stream)) != ASAC_OK) return rc;
+    if ((rc = asac_sac_policy_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, 1.f, stream)) != ASAC_OK) return rc;
+    int mask = 1 | 2 | 4;
+    const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
+    if (need_post) {
+        ASAC_REQUIRE(bat->eps_td && bat->eps_alpha, "asac_sac_step: missing eps_td / eps_alpha");
+        if ((rc = launch_value_pass(a, 1, stream)) != ASAC_OK) return rc;
+    }
+    if (cfg->use_auto_alpha) {
+        if ((rc = launch_reduce_adam(cfg, prm, wrk, 2, 1, 1, 1.f, stream)) != ASAC_OK) return rc;
+        mask |= 8;
+    }
+    return bump(prm, mask, stream);
+}
+
+extern "C" int asac_fill_normal(float *out, int64_t n, uint64_t seed, const int64_t *counter, int stream_id,
+                                void *stream) {
+    if (n <= 0) return ASAC_OK;
+    const int64_t quads = (n + 3) / 4;
+    k_fill_normal<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, counter, stream_id);
+    ASAC_LAUNCHED("k_fill_normal");
+    return ASAC_OK;
+}
+
+extern "C" int asac_mlp_forward(const float *params, int in_dim, int hidden, int depth, int out_dim, const float *x,
+                                int64_t rows, float *out, void *stream) {
+    ASAC_UNSUPPORTED(!(hidden == 16 || hidden == 32 || hidden == 64 || hidden == 128), "hidden width %d", hidden);
+    ASAC_UNSUPPORTED(depth < 1 || depth > ASAC_MAX_DEPTH, "depth %d", depth);
+    ASAC_REQUIRE(in_dim > 0 && out_dim > 0 && rows > 0, "asac_mlp_forward: bad sizes");
+    MlpArgs a;
+    a.params = params; a.x = x; a.out = out;
+    a.s = NetShape{in_dim, hidden, depth, out_dim};
+    a.rows = rows;
+    a.rows_per_cta = 32;
+    const int lda = tile_lda(hidden, in_dim), wsz = round_up(tile_wsz(hidden, in_dim), 4);
+    const int bytes = (3 * a.rows_per_cta * lda + 2 * wsz + round_up(a.rows_per_cta * out_dim, 4)) * 4;
+    int rc = set_smem(k_mlp_forward, bytes, "k_mlp_forward");
+    if (rc != ASAC_OK) return rc;
+    k_mlp_forward<<<(unsigned)((rows + a.rows_per_cta - 1) / a.rows_per_cta), NT, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_mlp_forward");
+    return ASAC_OK;
+}

@@ -1,0 +1,185 @@
+"""Lowering of stock plugin networks onto the flat parameter layout of the CUDA kernels.
+
+A plugin ``ModelQ`` / ``ModelPolicy`` is *stock* when it is the reference's default topology
+(algorithm/nn_models/q.py:34-91, policy.py:116-174): identity ``dense`` / ``c_state_dense`` /
+``c_action_dense`` and a ``c_dense`` made of equal-width ``ResBlock(Linear + GELU)`` blocks.
+Every ``ModelQ`` / ``ModelPolicy`` under the reference's ``envs/`` is of that form (SURVEY.md §2
+row 4).  For such nets the learner keeps ONE flat fp32 buffer per net family and re-points the
+``nn.Parameter`` storage of the modules at views of it, so the torch modules (actor side,
+``state_dict`` / checkpoints) and the kernels (learner side) share the same HBM bytes.
+
+Flat layout per net (include/asac_b200.h):
+    W0[H, in] b0[H]  W1[H, H] b1[H] ...  Whead[O, H] bhead[O]
+For the policy the head is [mean rows; logstd rows].
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+from torch import nn
+
+from . import nn_models as m
+
+
+class NotStockNetwork(NotImplementedError):
+    """Raised when a plugin network cannot be lowered onto the fused kernels."""
+
+
+@dataclass(frozen=True)
+class NetShape:
+    in_dim: int
+    hidden: int
+    depth: int
+    out_dim: int
+
+    @property
+    def count(self) -> int:
+        n, k = 0, self.in_dim
+        for _ in range(self.depth):
+            n += self.hidden * k + self.hidden
+            k = self.hidden
+        return n + self.out_dim * self.hidden + self.out_dim
+
+    @property
+    def stride(self) -> int:
+        return (self.count + 3) // 4 * 4
+
+
+def _no_params(mod: nn.Module) -> bool:
+    return sum(p.numel() for p in mod.parameters()) == 0
+
+
+def _trunk_blocks(layers: m.LinearLayers, what: str) -> tuple[list[m.ResBlock], nn.Linear | None]:
+    blocks, head = [], None
+    for mod in layers.dense:
+        if isinstance(mod, m.ResBlock):
+            if head is not None:
+                raise NotStockNetwork(f'{what}: block after the output layer')
+            act = mod.act
+            if not isinstance(act, nn.GELU) or getattr(act, 'approximate', 'none') != 'none':
+                raise NotStockNetwork(f'{what}: activation {type(act).__name__} is not exact GELU')
+            lin = mod.linear
+            if mod.residual != (lin.in_features == lin.out_features):
+                raise NotStockNetwork(f'{what}: residual flag does not follow in == out')
+            blocks.append(mod)
+        elif isinstance(mod, nn.Dropout):
+            if mod.p != 0:
+                raise NotStockNetwork(f'{what}: dropout p={mod.p} != 0')
+        elif isinstance(mod, nn.Linear):
+            head = mod
+        else:
+            raise NotStockNetwork(f'{what}: unexpected module {type(mod).__name__}')
+    if not blocks:
+        raise NotStockNetwork(f'{what}: needs at least one dense block')
+    widths = {b.linear.out_features for b in blocks}
+    if len(widths) != 1:
+        raise NotStockNetwork(f'{what}: unequal block widths {sorted(widths)}')
+    return blocks, head
+
+
+def analyze_q(q: nn.Module) -> tuple[NetShape, list[nn.Parameter]]:
+    """-> (shape, parameters in flat order).  Raises NotStockNetwork otherwise."""
+    if not isinstance(q, m.ModelQ) or type(q).forward is not m.ModelQ.forward:
+        raise NotStockNetwork('ModelQ overrides forward')
+    if q.d_action_sizes or not q.c_action_size:
+        raise NotStockNetwork('only continuous-action critics are lowered')
+    if not (_no_params(q.dense) and _no_params(q.c_state_dense) and _no_params(q.c_action_dense)):
+        raise NotStockNetwork('ModelQ with dense / c_state_dense / c_action_dense layers')
+    blocks, head = _trunk_blocks(q.c_dense, 'ModelQ.c_dense')
+    if head is None or head.out_features != 1:
+        raise NotStockNetwork('ModelQ.c_dense has no scalar output layer')
+    shape = NetShape(blocks[0].linear.in_features, blocks[0].linear.out_features, len(blocks), 1)
+    params = [p for b in blocks for p in (b.linear.weight, b.linear.bias)] + [head.weight, head.bias]
+    if sum(p.numel() for p in q.parameters()) != shape.count:
+        raise NotStockNetwork('ModelQ has parameters outside c_dense')
+    return shape, params
+
+
+def analyze_policy(pi: nn.Module) -> tuple[NetShape, list[nn.Parameter]]:
+    if not isinstance(pi, m.ModelPolicy) or type(pi).forward is not m.ModelPolicy.forward:
+        raise NotStockNetwork('ModelPolicy overrides forward')
+    if pi.d_action_sizes or not pi.c_action_size:
+        raise NotStockNetwork('only continuous-action policies are lowered')
+    if not _no_params(pi.dense):
+        raise NotStockNetwork('ModelPolicy with a shared dense trunk')
+    blocks, head = _trunk_blocks(pi.c_dense, 'ModelPolicy.c_dense')
+    if head is not None:
+        raise NotStockNetwork('ModelPolicy.c_dense has an output layer')
+    heads = []
+    for name in ('mean_dense', 'logstd_dense'):
+        mods = list(getattr(pi, name).dense)
+        if len(mods) != 1 or not isinstance(mods[0], nn.Linear):
+            raise NotStockNetwork(f'ModelPolicy.{name} is not a single Linear')
+        heads.append(mods[0])
+    A = pi.c_action_size
+    shape = NetShape(blocks[0].linear.in_features, blocks[0].linear.out_features, len(blocks), 2 * A)
+    # flat order: trunk, then head weight rows [mean; logstd], then head bias [mean; logstd]
+    params = [p for b in blocks for p in (b.linear.weight, b.linear.bias)]
+    params += [heads[0].weight, heads[1].weight, heads[0].bias, heads[1].bias]
+    if sum(p.numel() for p in pi.parameters()) != shape.count:
+        raise NotStockNetwork('ModelPolicy has parameters outside c_dense / mean_dense / logstd_dense')
+    return shape, params
+
+
+def bind_parameters(params: list[nn.Parameter], flat: torch.Tensor) -> None:
+    """Copies each parameter into consecutive slices of ``flat`` and makes the parameter a view
+    of that slice (shared storage from then on)."""
+    off = 0
+    with torch.no_grad():
+        for p in params:
+            n = p.numel()
+            view = flat[off:off + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            off += n
+    if off > flat.numel():
+        raise AssertionError('flat buffer too small')
+
+
+def flat_from_state_dict(shape: NetShape, state: dict, policy: bool, prefix: str = '') -> torch.Tensor:
+    """Builds the flat fp32 vector of one stock net from a reference-format ``state_dict``
+    (keys ``c_dense.dense.{2l}.linear.{weight,bias}``, ...).  CPU helper for tests / import."""
+    parts = []
+    for layer in range(shape.depth):
+        parts += [state[f'{prefix}c_dense.dense.{2 * layer}.linear.weight'],
+                  state[f'{prefix}c_dense.dense.{2 * layer}.linear.bias']]
+    if policy:
+        parts += [state[f'{prefix}mean_dense.dense.0.weight'], state[f'{prefix}logstd_dense.dense.0.weight'],
+                  state[f'{prefix}mean_dense.dense.0.bias'], state[f'{prefix}logstd_dense.dense.0.bias']]
+    else:
+        parts += [state[f'{prefix}c_dense.dense.{2 * shape.depth}.weight'],
+                  state[f'{prefix}c_dense.dense.{2 * shape.depth}.bias']]
+    flat = torch.cat([torch.as_tensor(p, dtype=torch.float32).reshape(-1) for p in parts])
+    if flat.numel() != shape.count:
+        raise ValueError(f'state_dict holds {flat.numel()} values, the shape needs {shape.count}')
+    out = torch.zeros(shape.stride, dtype=torch.float32)
+    out[:shape.count] = flat
+    return out
+
+
+def state_dict_from_flat(shape: NetShape, flat: torch.Tensor, policy: bool) -> dict[str, torch.Tensor]:
+    """Inverse of :func:`flat_from_state_dict` (returns views on ``flat``'s device)."""
+    out, off, k = {}, 0, shape.in_dim
+    H = shape.hidden
+
+    def take(n, *view):
+        nonlocal off
+        t = flat[off:off + n].view(*view)
+        off += n
+        return t
+
+    for layer in range(shape.depth):
+        out[f'c_dense.dense.{2 * layer}.linear.weight'] = take(H * k, H, k)
+        out[f'c_dense.dense.{2 * layer}.linear.bias'] = take(H, H)
+        k = H
+    if policy:
+        A = shape.out_dim // 2
+        out['mean_dense.dense.0.weight'] = take(A * H, A, H)
+        out['logstd_dense.dense.0.weight'] = take(A * H, A, H)
+        out['mean_dense.dense.0.bias'] = take(A, A)
+        out['logstd_dense.dense.0.bias'] = take(A, A)
+    else:
+        out[f'c_dense.dense.{2 * shape.depth}.weight'] = take(H, 1, H)
+        out[f'c_dense.dense.{2 * shape.depth}.bias'] = take(1, 1)
+    return out

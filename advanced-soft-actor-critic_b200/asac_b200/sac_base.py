@@ -1,0 +1,678 @@
+"""B200-native SAC learner with the reference's ``SAC_Base`` API.
+
+Mirrors ``algorithm/sac_base.py`` of the reference for the hot path named in BASELINE.json:
+same constructor keywords (sac_base.py:22-93), ``train() -> int`` (:2496-2609),
+``put_episode`` (:2303-2349), ``choose_action`` (:968-1019), checkpoint key names (:493-566).
+The per-batch update is NOT a torch op graph: sampling, window gather + padding, noise,
+Polyak, ``_get_y``, critic / policy / alpha losses with hand-derived backward passes, Adam,
+``get_l_probs``, ``_get_td_error``, the priority update and the mu-prob write-back are kernels of
+``libasac_b200.so`` enqueued on one stream and (by default) replayed as a single CUDA graph.
+
+Scope: continuous actions, vector observations through ``ModelSimpleRep`` and
+stock ``ModelQ`` / ``ModelPolicy`` topologies.  Anything else raises ``NotImplementedError`` at
+construction — there is no silent torch or CPU fallback for the update path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import random
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import _lib, lowering
+from . import nn_models as m
+from ._lib import check, ptr
+from .replay_buffer import PrioritizedReplayBuffer
+
+
+class _FlatAdam:
+    """``torch.optim.Adam``-shaped view (``state_dict`` / ``load_state_dict``) of flat moment
+    buffers that the CUDA Adam kernel updates (sac_base.py:296-300)."""
+
+    def __init__(self, params: list[torch.nn.Parameter], flat_param: torch.Tensor, m_flat: torch.Tensor,
+                 v_flat: torch.Tensor, counters: torch.Tensor, counter_index: int, lr: float):
+        self._params, self._lr = params, lr
+        self._counters, self._ci = counters, counter_index
+        base = flat_param.data_ptr()
+        self._views = []
+        for p in params:
+            off = (p.data_ptr() - base) // 4
+            self._views.append((m_flat[off:off + p.numel()].view(p.shape), v_flat[off:off + p.numel()].view(p.shape)))
+
+    def state_dict(self) -> dict:
+        step = float(self._counters[self._ci].item())
+        state = {}
+        if step > 0:
+            for i, (mm, vv) in enumerate(self._views):
+                state[i] = {'step': torch.tensor(step), 'exp_avg': mm.clone(), 'exp_avg_sq': vv.clone()}
+        group = dict(lr=self._lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, maximize=False,
+                     foreach=None, capturable=False, differentiable=False, fused=None,
+                     params=list(range(len(self._views))))
+        return {'state': state, 'param_groups': [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        steps = set()
+        for i, (mm, vv) in enumerate(self._views):
+            st = sd['state'].get(i)
+            if st is None:
+                mm.zero_(); vv.zero_()
+                continue
+            mm.copy_(st['exp_avg']); vv.copy_(st['exp_avg_sq'])
+            steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise RuntimeError('per-parameter Adam step counts differ; not representable')
+        self._counters[self._ci] = steps.pop() if steps else 0
+
+
+class SAC_Base:
+    _closed = False
+
+    def __init__(self,
+                 obs_names: list[str],
+                 obs_shapes: list[tuple[int]],
+                 d_action_sizes: list[int],
+                 c_action_size: int,
+                 model_abs_dir: Path | None,
+                 nn,
+
+                 device: str | None = None,
+                 ma_name: str | None = None,
+                 summary_path: str | None = 'log',
+                 train_mode: bool = True,
+                 last_ckpt: str | None = None,
+
+                 nn_config: dict | None = None,
+
+                 seed: float | None = None,
+                 write_summary_per_step: float = 1e3,
+                 save_model_per_step: float = 1e5,
+
+                 use_replay_buffer: bool = True,
+                 use_priority: bool = True,
+
+                 ensemble_q_num: int = 2,
+                 ensemble_q_sample: int = 2,
+
+                 burn_in_step: int = 0,
+                 n_step: int = 1,
+                 seq_encoder=None,
+
+                 batch_size: int = 256,
+                 tau: float = 0.005,
+                 update_target_per_step: int = 1,
+                 init_log_alpha: float = -2.3,
+                 use_auto_alpha: bool = True,
+                 target_d_alpha: float = 0.98,
+                 target_c_alpha: float = 1.,
+                 d_policy_entropy_penalty: float = 0.5,
+
+                 learning_rate: float = 3e-4,
+
+                 gamma: float = 0.99,
+                 v_lambda: float = 1.,
+                 v_rho: float = 1.,
+                 v_c: float = 1.,
+                 clip_epsilon: float = 0.2,
+
+                 discrete_dqn_like: bool = False,
+                 discrete_dqn_epsilon: float = 0.2,
+                 use_n_step_is: bool = True,
+
+                 siamese=None,
+                 siamese_use_q: bool = False,
+                 siamese_use_adaptive: bool = False,
+
+                 use_prediction: bool = False,
+                 transition_kl: float = 0.8,
+                 use_extra_data: bool = True,
+
+                 curiosity=None,
+                 curiosity_strength: float = 1.,
+                 use_rnd: bool = False,
+                 rnd_n_sample: int = 10,
+
+                 use_normalization: bool = False,
+
+                 offline_enabled: bool = False,
+                 offline_loss: bool = False,
+
+                 action_noise: list[float] | None = None,
+
+                 replay_config: dict | None = None,
+
+                 use_cuda_graph: bool = True):
+        self._lib = _lib.load()  # fails loudly when libasac_b200.so is missing
+        if not torch.cuda.is_available():
+            raise _lib.AsacError('asac_b200.SAC_Base needs a CUDA device: the update path has no CPU fallback')
+
+        self.obs_names = obs_names
+        self.obs_shapes = obs_shapes
+        self.d_action_sizes = d_action_sizes
+        self.d_action_summed_size = sum(d_action_sizes)
+        self.d_action_branch_size = len(d_action_sizes)
+        self.c_action_size = c_action_size
+        self.model_abs_dir = model_abs_dir
+        self.ma_name = ma_name
+        self.train_mode = train_mode
+
+        self.use_replay_buffer = use_replay_buffer
+        self.use_priority = use_priority
+        self.ensemble_q_num = ensemble_q_num
+        self.ensemble_q_sample = ensemble_q_sample
+        self.burn_in_step = burn_in_step
+        self.n_step = n_step
+        self.seq_encoder = seq_encoder
+
+        self.write_summary_per_step = int(write_summary_per_step)
+        self.save_model_per_step = int(save_model_per_step)
+        self.batch_size = batch_size
+        self.tau = tau
+        self.update_target_per_step = update_target_per_step
+        self.use_auto_alpha = use_auto_alpha
+        self.target_d_alpha = target_d_alpha
+        self.target_c_alpha = target_c_alpha
+        self.d_policy_entropy_penalty = d_policy_entropy_penalty
+        self.learning_rate = learning_rate
+        self.gamma = gamma
+        self.v_lambda = v_lambda
+        self.v_rho = v_rho
+        self.v_c = v_c
+        self.clip_epsilon = clip_epsilon
+        self.use_n_step_is = use_n_step_is
+        self.action_noise = action_noise
+        self.use_cuda_graph = use_cuda_graph
+
+        unsupported = {
+            'discrete action branches (d_action_sizes)': bool(d_action_sizes),
+            'c_action_size == 0': not c_action_size,
+            'seq_encoder': seq_encoder is not None,
+            'siamese': siamese is not None,
+            'use_prediction': use_prediction,
+            'curiosity': curiosity is not None,
+            'use_rnd': use_rnd,
+            'use_normalization': use_normalization,
+            'offline_enabled': offline_enabled,
+            'use_replay_buffer=False (on-policy BatchBuffer)': not use_replay_buffer,
+            'ensemble_q_sample != ensemble_q_num': ensemble_q_sample != ensemble_q_num,
+            'action_noise': action_noise is not None,
+        }
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError('outside the B200 hot path (SURVEY.md §8): ' + ', '.join(bad))
+
+        if device is None:
+            device = f'cuda:{torch.cuda.current_device()}'
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.AsacError(f"device '{device}': the B200 learner runs on CUDA only")
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+
+        self._logger = logging.getLogger('sac.base' if ma_name is None else f'sac.base.{ma_name}')
+        self._seed = seed
+        if seed is not None:
+            torch.manual_seed(int(seed))  # sac_base.py:246-248 seeds torch only
+        torch.distributions.Distribution.set_default_validate_args(False)
+
+        self.summary_writer = None
+        if model_abs_dir is not None and summary_path is not None:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                path = Path(model_abs_dir).joinpath(summary_path)
+                self.summary_writer = SummaryWriter(str(path if ma_name is None else path.joinpath(ma_name)))
+            except Exception as e:  # tensorboard is optional
+                self._logger.warning(f'no summary writer: {e}')
+        self.summary_available = False
+
+        with torch.cuda.device(self.device):
+            self._build_model(nn, nn_config, init_log_alpha)
+            self._build_ckpt()
+            self._init_replay_buffer(replay_config)
+            self._build_step_buffers()
+            self._init_or_restore(int(last_ckpt) if last_ckpt is not None else None)
+        self._graph = None
+        self._graph_columns_key = None
+
+    # ------------------------------------------------------------------ construction
+    def _build_model(self, nn, nn_config: dict | None, init_log_alpha: float) -> None:
+        nn_config = {} if nn_config is None else nn_config
+        nn_config = {k: ({} if nn_config.get(k) is None else nn_config[k]) for k in ('rep', 'policy')}
+        dev = self.device
+        A = self.c_action_size
+
+        self._gamma_ratio = torch.logspace(0, self.n_step - 1, self.n_step, self.gamma)      # sac_base.py:285
+        self._lambda_ratio = torch.logspace(0, self.n_step - 1, self.n_step, self.v_lambda)  # sac_base.py:286
+        self._padding_action = torch.zeros(A, dtype=torch.float32, device=dev)               # sac_base.py:291-294
+        self._np_padding_action = np.zeros(A, dtype=np.float32)
+
+        self.model_rep = nn.ModelRep(self.obs_names, self.obs_shapes, self.d_action_sizes, A, False,
+                                     self.model_abs_dir, **nn_config['rep']).to(dev)
+        self.model_target_rep = nn.ModelRep(self.obs_names, self.obs_shapes, self.d_action_sizes, A, True,
+                                            self.model_abs_dir, **nn_config['rep']).to(dev)
+        if type(self.model_rep).forward is not m.ModelSimpleRep.forward or \
+                sum(p.numel() for p in self.model_rep.parameters()) != 0:
+            raise NotImplementedError('only ModelSimpleRep (vector observations) is on the B200 hot path; '
+                                      'encoder representations are the next scope row (SURVEY.md §8f)')
+        self.optimizer_rep = None
+        self._vector_obs = [(name, shape) for name, shape in zip(self.obs_names, self.obs_shapes) if len(shape) == 1]
+        self.state_size = sum(shape[0] for _, shape in self._vector_obs)
+        if self.state_size == 0:
+            raise NotImplementedError('ModelSimpleRep needs at least one vector observation')
+        self.seq_hidden_state_shape = (0,)
+
+        E = self.ensemble_q_num
+        self.model_q_list = [nn.ModelQ(self.state_size, self.d_action_sizes, A, False, self.model_abs_dir).to(dev)
+                             for _ in range(E)]
+        self.model_target_q_list = [nn.ModelQ(self.state_size, self.d_action_sizes, A, True,
+                                              self.model_abs_dir).to(dev) for _ in range(E)]
+        self.model_policy = nn.ModelPolicy(self.state_size, self.d_action_sizes, A, self.model_abs_dir,
+                                           **nn_config['policy']).to(dev)
+        for q in self.model_target_q_list:
+            for p in q.parameters():
+                p.requires_grad = False
+
+        # ---- lower the stock nets onto flat buffers shared with the kernels
+        q_shapes = [lowering.analyze_q(q) for q in self.model_q_list + self.model_target_q_list]
+        self._q_shape = q_shapes[0][0]
+        if any(s != self._q_shape for s, _ in q_shapes):
+            raise lowering.NotStockNetwork('ensemble members differ in shape')
+        self._pi_shape, pi_params = lowering.analyze_policy(self.model_policy)
+        Pq, Ppi = self._q_shape.stride, self._pi_shape.stride
+        f32 = dict(dtype=torch.float32, device=dev)
+        self._q_flat = torch.zeros(E, Pq, **f32)
+        self._qt_flat = torch.zeros(E, Pq, **f32)
+        self._pi_flat = torch.zeros(Ppi, **f32)
+        for i in range(E):
+            lowering.bind_parameters(q_shapes[i][1], self._q_flat[i])
+            lowering.bind_parameters(q_shapes[E + i][1], self._qt_flat[i])
+        lowering.bind_parameters(pi_params, self._pi_flat)
+        self._q_m, self._q_v = torch.zeros_like(self._q_flat), torch.zeros_like(self._q_flat)
+        self._pi_m, self._pi_v = torch.zeros_like(self._pi_flat), torch.zeros_like(self._pi_flat)
+
+        self.log_d_alpha = torch.tensor(init_log_alpha, dtype=torch.float32, device=dev)
+        self.log_c_alpha = torch.full((1,), init_log_alpha, **f32)[0]  # 0-dim view of a 1-element buffer
+        self._log_alpha_buf = self.log_c_alpha.view(1)
+        self._alpha_m, self._alpha_v = torch.zeros(1, **f32), torch.zeros(1, **f32)
+        # counters: global_step, adam steps of critics / policy / alpha
+        self._counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.global_step = torch.tensor(0, dtype=torch.int64)
+        self._host_step = 0
+
+        lr = self.learning_rate
+        self.optimizer_q_list = [_FlatAdam(list(q.parameters()), self._q_flat[i], self._q_m[i], self._q_v[i],
+                                           self._counters, 1, lr) for i, q in enumerate(self.model_q_list)]
+        self.optimizer_policy = _FlatAdam(list(self.model_policy.parameters()), self._pi_flat, self._pi_m, self._pi_v,
+                                          self._counters, 2, lr)
+        self.optimizer_alpha = None
+        if self.use_auto_alpha:
+            self.optimizer_alpha = _AlphaAdam(self._alpha_m, self._alpha_v, self._counters, lr)
+
+        # ---- C structs
+        cfg = _lib.AsacSacConfig()
+        cfg.learning_rate = float(lr)
+        cfg.batch, cfg.burn_in, cfg.n_step = self.batch_size, self.burn_in_step, self.n_step
+        cfg.seq_len = self.burn_in_step + self.n_step + 1
+        cfg.state_size, cfg.action_size, cfg.ensemble = self.state_size, A, E
+        cfg.q_hidden, cfg.q_depth = self._q_shape.hidden, self._q_shape.depth
+        cfg.pi_hidden, cfg.pi_depth = self._pi_shape.hidden, self._pi_shape.depth
+        cfg.use_n_step_is, cfg.use_priority = int(self.use_n_step_is), int(self.use_priority)
+        cfg.use_auto_alpha = int(self.use_auto_alpha)
+        cfg.update_target_per_step = int(self.update_target_per_step)
+        cfg.bn_stride = cfg.seq_len
+        cfg.tau, cfg.one_minus_tau = float(self.tau), float(np.float32(1. - self.tau))
+        cfg.gamma, cfg.v_rho, cfg.v_c = float(self.gamma), float(self.v_rho), float(self.v_c)
+        cfg.clip_epsilon, cfg.target_c_alpha = float(self.clip_epsilon), float(self.target_c_alpha)
+        if self.n_step > _lib.MAX_NSTEP:
+            raise NotImplementedError(f'n_step > {_lib.MAX_NSTEP}')
+        for k in range(self.n_step):
+            cfg.gamma_ratio[k] = float(self._gamma_ratio[k])
+            cfg.lambda_ratio[k] = float(self._lambda_ratio[k])
+        self._cfg = cfg
+        tile = self._lib.asac_sac_tile_batch(C.byref(cfg))
+        if tile < 1:
+            check(tile, 'asac_sac_tile_batch')
+        self._n_tiles = (self.batch_size + tile - 1) // tile
+
+        prm = _lib.AsacSacParams()
+        prm.q, prm.q_target, prm.pi = ptr(self._q_flat), ptr(self._qt_flat), ptr(self._pi_flat)
+        prm.log_alpha = ptr(self._log_alpha_buf)
+        prm.q_m, prm.q_v, prm.pi_m, prm.pi_v = ptr(self._q_m), ptr(self._q_v), ptr(self._pi_m), ptr(self._pi_v)
+        prm.alpha_m, prm.alpha_v = ptr(self._alpha_m), ptr(self._alpha_v)
+        prm.counters = ptr(self._counters)
+        self._prm = prm
+
+    def _build_ckpt(self) -> None:
+        """Same key names as sac_base.py:493-566 so .pth files interchange."""
+        ck = {'global_step': self.global_step}
+        for i in range(self.ensemble_q_num):
+            ck[f'model_q_{i}'] = self.model_q_list[i]
+            ck[f'model_target_q_{i}'] = self.model_target_q_list[i]
+            ck[f'optimizer_q_{i}'] = self.optimizer_q_list[i]
+        ck['model_policy'] = self.model_policy
+        ck['optimizer_policy'] = self.optimizer_policy
+        ck['log_d_alpha'] = self.log_d_alpha
+        ck['log_c_alpha'] = self.log_c_alpha
+        if self.use_auto_alpha:
+            ck['optimizer_alpha'] = self.optimizer_alpha
+        self.ckpt_dict = ck
+
+    def _init_replay_buffer(self, replay_config: dict | None) -> None:
+        if not self.train_mode:
+            return
+        replay_config = {} if replay_config is None else dict(replay_config)
+        if self._seed is not None:
+            replay_config.setdefault('seed', int(self._seed))
+        self.replay_buffer = PrioritizedReplayBuffer(batch_size=self.batch_size, sample_prev_n=self.burn_in_step,
+                                                     sample_post_n=self.n_step, device=self.device,
+                                                     logger_parent_name=self._logger.name, **replay_config)
+        self._cfg.td_error_min = float(self.replay_buffer.td_error_min)
+        self._cfg.td_error_max = float(self.replay_buffer.td_error_max)
+        self._cfg.per_alpha = float(self.replay_buffer.alpha)
+
+    def _build_step_buffers(self) -> None:
+        """Persistent device buffers of one train() call (static addresses -> CUDA graph)."""
+        B, L, S, A, E = self.batch_size, self._cfg.seq_len, self.state_size, self.c_action_size, self.ensemble_q_num
+        n, T = self.n_step, self._n_tiles
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        bt = self._bt = {
+            'index': torch.zeros(B, L, dtype=torch.int32, device=dev),
+            'states': torch.zeros(B, L, S, **f32), 'actions': torch.zeros(B, L, A, **f32),
+            'rewards': torch.zeros(B, L, **f32), 'dones': torch.zeros(B, L, **u8),
+            'last_masks': torch.zeros(B, L, **u8), 'padding_masks': torch.zeros(B, L, **u8),
+            'mu_probs': torch.zeros(B, L, A, **f32),
+        }
+        # one noise buffer, four views: eps_y, eps_pi, eps_alpha, eps_td
+        sizes = [B * (n + 1) * A, B * A, B * A, B * (n + 1) * A]
+        self._noise = torch.zeros(sum(sizes), **f32)
+        offs = np.cumsum([0] + sizes)
+        self._eps = [self._noise[offs[i]:offs[i + 1]] for i in range(4)]
+        Pq, Ppi = self._q_shape.stride, self._pi_shape.stride
+        wk = self._wk = {
+            'y': torch.zeros(B, **f32), 'tq': torch.zeros(E, B, **f32), 'q_val': torch.zeros(E, B, **f32),
+            'loss_q': torch.zeros(T, E, **f32), 'grad_q_part': torch.zeros(T, E, Pq, **f32),
+            'grad_q': torch.zeros(E, Pq, **f32), 'grad_pi_part': torch.zeros(T, Ppi, **f32),
+            'grad_pi': torch.zeros(Ppi, **f32), 'stats_pi': torch.zeros(T, 2, **f32),
+            'grad_alpha_part': torch.zeros(T, 2, **f32), 'grad_alpha': torch.zeros(1, **f32),
+            'pi_probs': torch.zeros(B, L - 1, A, **f32), 'y_td': torch.zeros(B, **f32),
+            'td_error': torch.zeros(B, **f32),
+        }
+        work = _lib.AsacSacWork()
+        work.n_tiles = T
+        for k, t in wk.items():
+            setattr(work, k, ptr(t))
+        self._work = work
+        self._smp = {'slots': torch.zeros(B, dtype=torch.int32, device=dev),
+                     'ids': torch.zeros(B, dtype=torch.int64, device=dev),
+                     'p': torch.zeros(B, **f32), 'w': torch.zeros(B, **f32)}
+        batch = _lib.AsacSacBatch()
+        batch.states, batch.actions, batch.rewards = ptr(bt['states']), ptr(bt['actions']), ptr(bt['rewards'])
+        batch.dones, batch.last_masks = ptr(bt['dones']), ptr(bt['last_masks'])
+        batch.padding_masks, batch.mu_probs = ptr(bt['padding_masks']), ptr(bt['mu_probs'])
+        batch.priority_is = ptr(self._smp['w']) if self.use_priority else None
+        batch.eps_y, batch.eps_pi, batch.eps_alpha, batch.eps_td = [ptr(e) for e in self._eps]
+        self._batch = batch
+        self._noise_seed = (int(self._seed) if self._seed is not None else random.getrandbits(62)) ^ 0x5AC5AC
+
+    def _init_or_restore(self, last_ckpt: int | None) -> None:
+        """sac_base.py:568-629."""
+        self.ckpt_dir = None
+        fresh = True
+        if self.model_abs_dir:
+            self.ckpt_dir = ckpt_dir = Path(self.model_abs_dir).joinpath('model')
+            ckpts = sorted(int(p.stem) for p in ckpt_dir.glob('*.pth')) if ckpt_dir.exists() else []
+            ckpt_dir.mkdir(parents=True, exist_ok=True)
+            if ckpts:
+                fresh = False
+                if last_ckpt is None or last_ckpt not in ckpts:
+                    if last_ckpt is not None:
+                        self._logger.warning(f'{last_ckpt} NOT IN {ckpts}, using {ckpts[-1]}')
+                    last_ckpt = ckpts[-1]
+                path = ckpt_dir.joinpath(f'{last_ckpt}.pth')
+                restored = torch.load(path, map_location=self.device, weights_only=True)
+                failed = False
+                for name, obj in self.ckpt_dict.items():
+                    if name not in restored:
+                        self._logger.warning(f'{name} not in {last_ckpt}.pth')
+                        continue
+                    if isinstance(obj, torch.Tensor):
+                        obj.copy_(restored[name].to(obj.device))  # in place: the kernels hold the address
+                    else:
+                        if failed and name.startswith('optimizer'):
+                            continue
+                        try:
+                            obj.load_state_dict(restored[name])
+                        except RuntimeError as e:
+                            failed = True
+                            self._logger.error(e)
+                self._host_step = int(self.global_step.item())
+                self._counters[0] = self._host_step
+                self._logger.info(f'Restored from {path}')
+                if self.train_mode:
+                    self.replay_buffer.load(ckpt_dir, last_ckpt)
+        if fresh:
+            self._logger.info('Initializing from scratch')
+            self._update_target_variables()
+        self.set_train_mode(self.train_mode)
+
+    # ------------------------------------------------------------------ small API
+    def _update_target_variables(self, tau=1.) -> None:
+        """sac_base.py:745-764 (hard copy by default)."""
+        with torch.cuda.device(self.device):
+            check(self._lib.asac_sac_polyak(C.byref(self._cfg), C.byref(self._prm), float(tau),
+                                            _lib.current_stream()), 'sac_polyak')
+
+    def set_train_mode(self, train_mode=True):
+        self.train_mode = train_mode
+        for mod in self.ckpt_dict.values():
+            if isinstance(mod, torch.nn.Module):
+                mod.train(mode=train_mode)
+
+    def get_global_step(self) -> int:
+        return self._host_step
+
+    def increase_global_step(self) -> int:
+        self._host_step += 1
+        self.global_step.fill_(self._host_step)
+        return self._host_step
+
+    def get_initial_action(self, batch_size, get_numpy=True):
+        if get_numpy:
+            return np.repeat(self._np_padding_action[np.newaxis, :], batch_size, axis=0)
+        return self._padding_action.repeat(batch_size, 1)
+
+    def get_initial_seq_hidden_state(self, batch_size, get_numpy=True):
+        if get_numpy:
+            return np.zeros([batch_size, *self.seq_hidden_state_shape], dtype=np.float32)
+        return torch.zeros([batch_size, *self.seq_hidden_state_shape], device=self.device)
+
+    def save_model(self, save_replay_buffer=False) -> None:
+        if self.ckpt_dir is None:
+            return
+        step = self.get_global_step()
+        path = self.ckpt_dir.joinpath(f'{step}.pth')
+        torch.save({k: (v.detach().clone() if isinstance(v, torch.Tensor) else v.state_dict())
+                    for k, v in self.ckpt_dict.items()}, path)
+        self._logger.info(f'Model saved at {path}')
+        if save_replay_buffer:
+            self.replay_buffer.save(self.ckpt_dir, step)
+
+    def write_constant_summaries(self, constant_summaries: list[dict], iteration=None) -> None:
+        if self.summary_writer is None:
+            return
+        for s in constant_summaries:
+            self.summary_writer.add_scalar(s['tag'], s['simple_value'],
+                                           self.get_global_step() if iteration is None else iteration)
+        self.summary_writer.flush()
+
+    # ------------------------------------------------------------------ actor side
+    @torch.no_grad()
+    def choose_action(self, obs_list, pre_action, pre_seq_hidden_state, offline_action=None,
+                      disable_sample: bool = False, force_rnd_if_available: bool = False):
+        """sac_base.py:968-1019 (continuous branch of _choose_action :882-966); torch modules on the
+        same parameter storage the kernels train."""
+        obs = [torch.from_numpy(np.asarray(o)).to(self.device) for o in obs_list]
+        for i, o in enumerate(obs):
+            if o.dtype == torch.uint8:
+                obs[i] = o.float() / 255.
+            elif o.dtype == torch.bool:
+                obs[i] = o.float()
+        state, hidden = self.model_rep([o.unsqueeze(1) for o in obs], None, None)
+        state, hidden = state.squeeze(1), hidden.squeeze(1)
+        _, c_policy = self.model_policy(state, obs)
+        if offline_action is not None:
+            c_action = torch.from_numpy(offline_action).to(self.device)
+        elif disable_sample:
+            c_action = torch.tanh(c_policy.mean)
+        else:
+            c_action = torch.tanh(c_policy.sample())
+        x = torch.atanh(torch.clamp(c_action, -0.999, 0.999))
+        floor = torch.clamp_min(1 - torch.tanh(x) ** 2, 1e-2)
+        prob = torch.exp(c_policy.log_prob(x)) / floor.prod(-1, keepdim=True)  # operators.py:17-19
+        return c_action.cpu().numpy(), prob.cpu().numpy(), hidden.cpu().numpy()
+
+    # ------------------------------------------------------------------ ingest
+    def put_episode(self, ep_indexes, ep_obses_list, ep_actions, ep_rewards, ep_dones, ep_probs,
+                    ep_pre_seq_hidden_states) -> None:
+        """sac_base.py:2303-2396."""
+        if ep_indexes.shape[1] < self.n_step:
+            return
+        assert ep_indexes.dtype == np.int32
+        last = np.zeros_like(ep_indexes, dtype=bool)
+        last[:, -1] = True
+        last[ep_indexes == -1] = True
+        storage = {'index': ep_indexes.squeeze(0), 'last_mask': last.squeeze(0)}
+        for name, o in zip(self.obs_names, ep_obses_list):
+            storage[f'obs_{name}'] = o.squeeze(0)
+        storage.update(action=ep_actions.squeeze(0), reward=ep_rewards.squeeze(0), done=ep_dones.squeeze(0),
+                       mu_prob=ep_probs.squeeze(0), pre_seq_hidden_state=ep_pre_seq_hidden_states.squeeze(0))
+        self.replay_buffer.add(storage, ignore_size=1)
+
+    # ------------------------------------------------------------------ the step
+    def _gather_specs(self):
+        rb, bt = self.replay_buffer, self._bt
+        S, A = self.state_size, self.c_action_size
+        specs = [('index', bt['index'], 4, 0, _lib.ROLE_INDEX),
+                 ('last_mask', bt['last_masks'], 1, 0, _lib.ROLE_COPY),
+                 ('action', bt['actions'], 4 * A, 0, _lib.ROLE_ACTION),
+                 ('reward', bt['rewards'], 4, 0, _lib.ROLE_REWARD),
+                 ('done', bt['dones'], 1, 0, _lib.ROLE_DONE),
+                 ('mu_prob', bt['mu_probs'], 4 * A, 0, _lib.ROLE_MU_PROB)]
+        off = 0
+        for name, shape in self._vector_obs:
+            col = rb._columns[f'obs_{name}']
+            if col.dtype != torch.float32:
+                raise NotImplementedError(f'vector observation {name} is stored as {col.dtype}; float32 expected')
+            specs.append((f'obs_{name}', bt['states'], 4 * S, 4 * off, _lib.ROLE_COPY))
+            off += shape[0]
+        for key, _, nbytes, _, _ in specs[:6]:
+            if rb._row_bytes(key) != nbytes:
+                raise ValueError(f'stored column {key} has {rb._row_bytes(key)} bytes per row, expected {nbytes}')
+        return specs
+
+    def _enqueue_step(self) -> None:
+        """Everything one train() does on the device, in stream order (graph-capturable)."""
+        lib, rb, stream = self._lib, self.replay_buffer, _lib.current_stream()
+        smp, cfg, prm, batch, work = self._smp, self._cfg, self._prm, self._batch, self._work
+        B = self.batch_size
+        # 1. prioritized sample + IS weights (replay_buffer.py:347-354)
+        check(lib.asac_per_sample(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), B, None, rb._seed,
+                                  ptr(rb._draw_counter), ptr(rb._per_state), ptr(smp['slots']), ptr(smp['ids']),
+                                  ptr(smp['p']), ptr(smp['w']), stream), 'per_sample')
+        # 2. window gather fused with the padding rule (replay_buffer.py:356-362, sac_base.py:2435-2453)
+        rb._gather(smp['ids'], self._specs, self._padding_action, self._bt['padding_masks'])
+        # 3. the four Gaussian draws of the step
+        check(lib.asac_fill_normal(ptr(self._noise), self._noise.numel(), self._noise_seed, ptr(self._counters), 0,
+                                   stream), 'fill_normal')
+        # 4. _train + get_l_probs + _get_td_error
+        check(lib.asac_sac_step(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), stream), 'sac_step')
+        # 5. priority update and mu-prob write-back (sac_base.py:2584, 2598-2605)
+        if self.use_priority:
+            check(lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), ptr(smp['ids']),
+                                      ptr(self._wk['td_error']), B, float(rb.td_error_min), float(rb.td_error_max),
+                                      float(rb.alpha), 0, ptr(rb._per_state), stream), 'per_update')
+        if self.use_n_step_is:
+            rb.write_back(smp['ids'], 'mu_prob', self._wk['pi_probs'], -self.burn_in_step, self._bt['padding_masks'])
+
+    def train(self) -> int:
+        step = self.get_global_step()
+        rb = self.replay_buffer
+        if not rb.is_lg_batch_size:
+            return step
+        with torch.cuda.device(self.device):
+            key = tuple((k, v.data_ptr()) for k, v in rb._columns.items())
+            if self._graph_columns_key != key:  # first step, or the storage was re-allocated (load / clear)
+                self._specs = self._gather_specs()
+                self._graph, self._graph_columns_key = None, key
+                self._enqueue_step()  # eager warm-up (also sets the kernels' shared-memory attributes)
+            elif not self.use_cuda_graph:
+                self._enqueue_step()
+            else:
+                if self._graph is None:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._enqueue_step()
+                    self._graph = graph
+                self._graph.replay()
+        if self.save_model_per_step and step % self.save_model_per_step == 0:
+            self.save_model()
+        if self.summary_writer is not None and step % self.write_summary_per_step == 0:
+            self._write_summaries(step)
+        return self.increase_global_step()
+
+    def _write_summaries(self, step: int) -> None:
+        wk, B = self._wk, self.batch_size
+        w = self.summary_writer
+        w.add_scalar('loss/q', float(wk['loss_q'][:, 0].sum().item()) / B, step)
+        w.add_scalar('loss/c_entropy', float(wk['stats_pi'][:, 1].sum().item()) / B, step)
+        w.add_scalar('loss/c_alpha', float(torch.exp(self.log_c_alpha).item()), step)
+        w.add_scalar('metric/replay_id', self.replay_buffer.get_curr_id(), step)
+        w.flush()
+        self.summary_available = True
+
+    def last_step_stats(self) -> dict[str, float]:
+        """Scalars of the most recent step (synchronises): what sac_base.py:2128-2178 logs."""
+        wk, B = self._wk, self.batch_size
+        return {'loss_q': float(wk['loss_q'][:, 0].sum().item()) / B,
+                'loss_policy': float(wk['stats_pi'][:, 0].sum().item()) / B,
+                'c_entropy': float(wk['stats_pi'][:, 1].sum().item()) / B,
+                'c_alpha': float(torch.exp(self.log_c_alpha).item()),
+                'td_error_mean': float(wk['td_error'].mean().item())}
+
+    def close(self):
+        self._closed = True
+        self._graph = None
+        if hasattr(self, 'replay_buffer'):
+            self.replay_buffer.check_nan()
+            self.replay_buffer.close()
+        if self.summary_writer is not None:
+            self.summary_writer.close()
+
+
+class _AlphaAdam:
+    """Adam state of ``[log_d_alpha, log_c_alpha]`` (sac_base.py:472); only log_c_alpha ever gets a
+    gradient in continuous-only runs, so the torch state dict holds entry 1 alone."""
+
+    def __init__(self, m_buf, v_buf, counters, lr):
+        self._m, self._v, self._counters, self._lr = m_buf, v_buf, counters, lr
+
+    def state_dict(self) -> dict:
+        step = float(self._counters[3].item())
+        state = {}
+        if step > 0:
+            state[1] = {'step': torch.tensor(step), 'exp_avg': self._m[0].clone(), 'exp_avg_sq': self._v[0].clone()}
+        group = dict(lr=self._lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, maximize=False,
+                     foreach=None, capturable=False, differentiable=False, fused=None, params=[0, 1])
+        return {'state': state, 'param_groups': [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        st = sd['state'].get(1)
+        if st is None:
+            self._m.zero_(); self._v.zero_(); self._counters[3] = 0
+            return
+        self._m[0] = st['exp_avg']; self._v[0] = st['exp_avg_sq']
+        self._counters[3] = int(float(st['step']))

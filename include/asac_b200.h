@@ -1,0 +1,301 @@
+/*
+ * asac_b200.h — C ABI of libasac_b200.so (sm_100a).
+ *
+ * The reference (BlueFisher/Advanced-Soft-Actor-Critic) is 100 % Python and has no FFI;
+ * every entry point below replaces a Python function of the reference's hot path and is
+ * what a ctypes binding inside the reference would call.  File:line
+ * citations are relative to the reference checkout.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (a torch tensor's data_ptr())
+ *     unless the parameter name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued, nothing synchronises
+ *     unless stated;
+ *   - the return value is 0 on success, otherwise a negative ASAC_E* code or a positive
+ *     cudaError_t; asac_last_error() returns a static description;
+ *   - no entry point falls back to the CPU.
+ */
+#ifndef ASAC_B200_H
+#define ASAC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASAC_OK 0
+#define ASAC_EINVAL (-1)       /* bad argument (shape, alignment, unsupported size) */
+#define ASAC_EUNSUPPORTED (-2) /* configuration outside the fused path              */
+
+#define ASAC_MAX_COLUMNS 16
+#define ASAC_MAX_NSTEP 16
+#define ASAC_MAX_DEPTH 4
+#define ASAC_MAX_ENSEMBLE 8
+
+const char *asac_last_error(void);
+int asac_version(void);
+/* number of kernels this library has launched since load / since the last reset
+ * (bench.py's gpu_launches) */
+int64_t asac_launch_count(void);
+void asac_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Sum tree  — replaces SumTree (algorithm/replay_buffer.py:145-242).
+ *
+ * HBM layout: float32[2*capacity], 1-based heap: node 1 is the root, the children of
+ * node i are 2i and 2i+1 (one aligned float2), leaf of data slot j is node capacity+j.
+ * nodes[1:] is element-for-element the reference's `_tree` array (root at 0, children
+ * 2i+1/2i+2), so `<ckpt>-rb_tree.npy` files interchange by an offset of one.
+ * Every parent holds fp32 (left + right), exactly as replay_buffer.py:181.
+ * ---------------------------------------------------------------------------------- */
+
+/* SumTree.update (replay_buffer.py:172-183): nodes[capacity+slot[i]] = p[i] (duplicates:
+ * the last one wins, like NumPy fancy assignment), then every ancestor is recomputed.
+ * k may be any size; it is processed in sequential chunks of <= 1024. */
+int asac_tree_update(float *nodes, int64_t capacity, const int64_t *slots, const float *p,
+                     int64_t k, void *stream);
+
+/* Full bottom-up recomputation of the internal nodes from the leaves (used after
+ * SumTree.load, replay_buffer.py:225-227). */
+int asac_tree_rebuild(float *nodes, int64_t capacity, void *stream);
+
+/* SumTree.max (replay_buffer.py:237-239): max over the leaves -> out[0]. */
+int asac_tree_leaf_max(const float *nodes, int64_t capacity, float *out, void *stream);
+
+/* SumTree.sample (replay_buffer.py:185-205) with the uniforms injected:
+ * seg = total/B in fp32; v_i = i*seg + ((i+1)*seg - i*seg) * u[i] in float64; descent
+ * "left iff v <= left || right == 0" comparing in float64.  When `unit_uniform` is NULL the
+ * uniforms come from Philox4x32-10 keyed by (seed, draw_counter[0]).
+ * out_slot[i] = leaf - capacity (int32), out_p[i] = the leaf's priority. */
+int asac_tree_sample(const float *nodes, int64_t capacity, int batch, const double *unit_uniform,
+                     uint64_t seed, const int64_t *draw_counter, int32_t *out_slot, float *out_p,
+                     void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Prioritized replay — replaces PrioritizedReplayBuffer (replay_buffer.py:245-477).
+ * `store_ids` is DataStorage's `_id` column, int64[capacity] (replay_buffer.py:36).
+ * `per_state` is double[4] on the device: {beta, beta_increment, unused, nan_flag}.
+ * ---------------------------------------------------------------------------------- */
+
+/* One iteration of _prefetch_loop's sampling block (replay_buffer.py:347-354): tree
+ * sample, data ids, beta += increment (capped at 1), IS weights (w/min w)^-beta computed in
+ * float64 and rounded to fp32.  batch <= 1024.  draw_counter[0] is advanced by one when the
+ * uniforms are generated on the device. */
+int asac_per_sample(const float *nodes, int64_t capacity, const int64_t *store_ids, int batch,
+                    const double *unit_uniform, uint64_t seed, int64_t *draw_counter,
+                    double *per_state, int32_t *out_slot, int64_t *out_data_id, float *out_p,
+                    float *out_is_weight, void *stream);
+
+/* PrioritizedReplayBuffer.update (replay_buffer.py:412-427): p = clip(|td|, min, max)^alpha in
+ * fp32, skipped where store_ids[id % capacity] != id, then SumTree.update.  A NaN td sets
+ * per_state[3] = 1 and leaves the tree untouched (the reference raises).  k <= 1024.
+ * When `precomputed_p` is non-zero `td` already holds priorities (add() path). */
+int asac_per_update(float *nodes, int64_t capacity, const int64_t *store_ids,
+                    const int64_t *data_ids, const float *td, int k, float td_min, float td_max,
+                    float alpha, int precomputed_p, double *per_state, void *stream);
+
+/* PrioritizedReplayBuffer.add's bookkeeping (replay_buffer.py:293-307 + DataStorage.add
+ * :43-54): writes store_ids for T new rows starting at `first_id`, gives them priority
+ * max_p (device scalar; td_error_max when the buffer was empty), zero for the last
+ * `ignore_size` rows and for rows landing in the last `ignore_size` ring slots, and updates
+ * the tree.  The row payload itself is written by asac_storage_write_rows. */
+int asac_per_add(float *nodes, int64_t capacity, int64_t *store_ids, int64_t first_id, int64_t T,
+                 const float *max_p, int ignore_size, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Transition storage — replaces DataStorage (replay_buffer.py:21-142) and the learner-side
+ * padding of SAC_Base._sample_from_replay_buffer (sac_base.py:2435-2453).
+ * ---------------------------------------------------------------------------------- */
+
+/* DataStorage.add payload (replay_buffer.py:45-50): ring[(first_id+i) % (10*capacity) %
+ * capacity] = rows[i] for one column of `row_bytes` bytes per row. */
+int asac_storage_write_rows(void *ring, int64_t capacity, int64_t first_id, const void *rows,
+                            int64_t T, int64_t row_bytes, void *stream);
+
+enum {
+    ASAC_ROLE_COPY = 0,      /* obs, last_mask: copied as stored                           */
+    ASAC_ROLE_INDEX = 1,     /* int32 episode index: -1 on padded rows (sac_base.py:2445)  */
+    ASAC_ROLE_ACTION = 2,    /* float32[A]: padding_action on padded rows (:2449)          */
+    ASAC_ROLE_REWARD = 3,    /* float32: 0 on padded rows (:2450)                          */
+    ASAC_ROLE_DONE = 4,      /* bool: true on padded rows (:2451)                          */
+    ASAC_ROLE_MU_PROB = 5,   /* float32[A]: 1 on padded rows (:2452)                       */
+    ASAC_ROLE_HIDDEN = 6     /* float32[*]: 0 on padded rows (:2453)                       */
+};
+
+typedef struct {
+    const void *ring;      /* [capacity, row_bytes] */
+    void *out;             /* destination base                                              */
+    int32_t row_bytes;     /* bytes per stored row                                          */
+    int32_t out_stride;    /* bytes between consecutive (b, t) rows in `out`                */
+    int32_t out_offset;    /* byte offset inside the destination row (state concatenation)  */
+    int32_t role;          /* ASAC_ROLE_*                                                    */
+} AsacColumn;
+
+typedef struct {
+    int32_t n_columns;
+    int32_t index_column;  /* which column holds the int32 episode index */
+    AsacColumn col[ASAC_MAX_COLUMNS];
+} AsacColumnTable;
+
+/* get_storage_data over the windows data_id + [-prev_n, post_n] (replay_buffer.py:356-362)
+ * fused with the padding rule: a row is padding when stored_index(b,t) -
+ * stored_index(b,prev_n) != t - prev_n.  out_padding_mask is uint8[batch, L].
+ * padding_action is float32[A] (sac_base.py:291-294). */
+int asac_storage_gather(const AsacColumnTable *table_host, int64_t capacity,
+                        const int64_t *data_ids, int batch, int prev_n, int post_n,
+                        const float *padding_action, uint8_t *out_padding_mask, void *stream);
+
+/* update_transitions (replay_buffer.py:429-434) for the write-backs of sac_base.py:2586-2605:
+ * ring[(data_id[b] + first_offset + t) % capacity] = rows[b, t] for t < n_rows, skipped on
+ * padded rows and where store_ids no longer holds that id. */
+int asac_storage_scatter(void *ring, int64_t capacity, const int64_t *store_ids,
+                         const int64_t *data_ids, int batch, int first_offset, int n_rows,
+                         const void *rows, int64_t row_bytes, int64_t rows_b_stride,
+                         const uint8_t *padding_mask, int64_t mask_b_stride, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * SAC update — replaces SAC_Base._train / get_l_probs / _get_td_error for the continuous,
+ * stock-network case (sac_base.py:2027-2245; nets: nn_models/q.py:34-91,
+ * nn_models/policy.py:116-174, nn_models/layers/linear_layers.py:24-119).
+ *
+ * A stock net is `depth` ResBlocks (Linear + exact-erf GELU, + input when in == out)
+ * followed by a Linear head.  Flat parameter layout per net, all fp32:
+ *     W0[H, in] b0[H]  W1[H, H] b1[H] ... W(d-1)[H, H] b(d-1)[H]  Whead[O, H] bhead[O]
+ * with O = 1 for a Q net and O = 2A for the policy (rows 0..A-1 mean, A..2A-1 logstd).
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    double learning_rate;   /* Adam lr (kept in float64 like the Python float)  */
+    int32_t batch;          /* B                                             */
+    int32_t seq_len;        /* L = burn_in + n_step + 1                      */
+    int32_t burn_in;        /* b                                             */
+    int32_t n_step;         /* n  (<= ASAC_MAX_NSTEP)                        */
+    int32_t state_size;     /* S                                             */
+    int32_t action_size;    /* A  (continuous)                               */
+    int32_t ensemble;       /* E  (== ensemble_q_sample)                     */
+    int32_t q_hidden, q_depth;
+    int32_t pi_hidden, pi_depth;
+    int32_t use_n_step_is, use_priority, use_auto_alpha;
+    int32_t update_target_per_step;
+    int32_t bn_stride;      /* rows per batch element in the action/reward/... arrays (L or L-1) */
+    float tau, one_minus_tau /* float32(1. - tau) */, gamma, v_rho, v_c, clip_epsilon, target_c_alpha;
+    float td_error_min, td_error_max, per_alpha;
+    float gamma_ratio[ASAC_MAX_NSTEP];   /* torch.logspace(0, n-1, n, gamma)    (sac_base.py:285) */
+    float lambda_ratio[ASAC_MAX_NSTEP];  /* torch.logspace(0, n-1, n, v_lambda) (sac_base.py:286) */
+} AsacSacConfig;
+
+typedef struct {
+    /* parameters (flat, see layout above) */
+    float *q;            /* [E, Pq]  online critics  (Pq = asac_mlp_param_stride) */
+    float *q_target;     /* [E, Pq]  target critics       */
+    float *pi;           /* [Ppi]    policy               */
+    float *log_alpha;    /* [1]      log_c_alpha          */
+    /* Adam moments (torch.optim.Adam defaults, sac_base.py:296-300) */
+    float *q_m, *q_v;    /* [E, Pq]  */
+    float *pi_m, *pi_v;  /* [Ppi]    */
+    float *alpha_m, *alpha_v; /* [1] */
+    /* counters: int64[4] = {global_step, adam_step_q, adam_step_pi, adam_step_alpha} */
+    int64_t *counters;
+} AsacSacParams;
+
+typedef struct {
+    const float *states;          /* [B, L, S]  encoded states (ModelSimpleRep: concat of vector obs) */
+    const float *actions;         /* [B, bn_stride, A] */
+    const float *rewards;         /* [B, bn_stride]    */
+    const uint8_t *dones;         /* [B, bn_stride]    */
+    const uint8_t *last_masks;    /* [B, bn_stride]    */
+    const uint8_t *padding_masks; /* [B, bn_stride]    */
+    const float *mu_probs;        /* [B, bn_stride, A] */
+    const float *priority_is;     /* [B] or NULL       */
+    /* injected N(0,1) draws (Normal.rsample / Normal.sample, sac_base.py:1346,1883,1932,2223) */
+    const float *eps_y;           /* [B, n+1, A] */
+    const float *eps_pi;          /* [B, A]      */
+    const float *eps_alpha;       /* [B, A]      */
+    const float *eps_td;          /* [B, n+1, A] */
+} AsacSacBatch;
+
+typedef struct {
+    int32_t n_tiles;      /* ceil(B / asac_sac_tile_batch())                            */
+    float *y;             /* [B]       _get_y output of the train pass                  */
+    float *tq;            /* [E, B]    target-Q(s0, a0) for the clipped loss            */
+    float *q_val;         /* [E, B]    online Q(s0, a0) seen by the loss                */
+    float *loss_q;        /* [n_tiles, E] per-tile sums of the weighted loss (÷B = mean) */
+    float *grad_q_part;   /* [n_tiles, E, Pq]                                           */
+    float *grad_q;        /* [E, Pq]   reduced gradient (also the all-reduce buffer)    */
+    float *grad_pi_part;  /* [n_tiles, Ppi]                                             */
+    float *grad_pi;       /* [Ppi]                                                      */
+    float *stats_pi;      /* [n_tiles, 2] per-tile sums: policy loss, entropy           */
+    float *grad_alpha_part; /* [n_tiles, 2] per-tile sums: d loss/d log_alpha, alpha loss */
+    float *grad_alpha;    /* [1]                                                        */
+    float *pi_probs;      /* [B, L-1, A] get_l_probs output                             */
+    float *y_td;          /* [B]       _get_y inside _get_td_error                      */
+    float *td_error;      /* [B]                                                        */
+} AsacSacWork;
+
+/* batch elements handled by one CTA of the row-tiled kernels for this configuration
+ * (work.n_tiles = ceil(B / asac_sac_tile_batch(cfg))) */
+int asac_sac_tile_batch(const AsacSacConfig *cfg);
+/* float stride between consecutive flat nets = asac_mlp_param_count rounded up to 4 */
+int64_t asac_mlp_param_stride(int in_dim, int hidden, int depth, int out_dim);
+/* float count of one flat net: in -> (H x depth) -> out */
+int64_t asac_mlp_param_count(int in_dim, int hidden, int depth, int out_dim);
+
+/* _update_target_variables (sac_base.py:745-764) when counters[0] % update_target_per_step == 0
+ * (sac_base.py:2057-2058); `force_tau` >= 0 applies that tau unconditionally (hard copy at
+ * start-up, sac_base.py:629). */
+int asac_sac_polyak(const AsacSacConfig *cfg, const AsacSacParams *prm, float force_tau, void *stream);
+
+/* _get_y (sac_base.py:1297-1466, continuous branch) + target-Q(s0,a0) (:1541) -> work.y, work.tq */
+int asac_sac_target_y(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
+                      const AsacSacWork *work, void *stream);
+
+/* _train_rep_q's critic part (sac_base.py:1516,1539-1570): forward, clipped loss, backward ->
+ * work.q_val, work.loss_q, work.grad_q_part */
+int asac_sac_q_backward(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
+                        const AsacSacWork *work, void *stream);
+
+/* _train_policy (sac_base.py:1882-1908) forward + backward -> work.grad_pi_part, work.stats_pi */
+int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacParams *prm,
+                             const AsacSacBatch *batch, const AsacSacWork *work, void *stream);
+
+/* _train_alpha's loss (sac_base.py:1930-1945), get_l_probs (:1159-1189) and _get_td_error
+ * (:2182-2245) in one pass over the updated nets -> work.grad_alpha_part, work.pi_probs,
+ * work.y_td, work.td_error */
+int asac_sac_post(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
+                  const AsacSacWork *work, void *stream);
+
+/* which = 0 critics, 1 policy, 2 alpha.  Sums the per-tile partial gradients in tile order
+ * into work.grad_*.  (Between this and asac_sac_adam a multi-GPU learner all-reduces
+ * work.grad_* and passes grad_scale = 1/world_size.) */
+int asac_sac_reduce_grads(const AsacSacConfig *cfg, const AsacSacWork *work, int which, void *stream);
+
+/* torch.optim.Adam.step (betas 0.9/0.999, eps 1e-8) on work.grad_* * grad_scale; advances
+ * the optimizer's step counter. */
+int asac_sac_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *work,
+                  int which, float grad_scale, void *stream);
+
+/* fused single-GPU variant: reduce + Adam in one kernel */
+int asac_sac_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *work,
+                         int which, void *stream);
+
+/* increase_global_step (sac_base.py:2607): counters[0] += 1 */
+int asac_sac_advance_step(const AsacSacParams *prm, void *stream);
+
+/* One whole SAC_Base._train + get_l_probs + _get_td_error (sac_base.py:2027-2245,2558-2583):
+ * polyak, target_y, q_backward, reduce_adam(q), policy_backward, reduce_adam(pi), post,
+ * reduce_adam(alpha), advance_step — the sequence a CUDA graph captures. */
+int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
+                  const AsacSacWork *work, void *stream);
+
+/* N(0,1) draws for eps_* (Philox4x32-10 + Box-Muller), keyed by (seed, counter[0], stream_id) */
+int asac_fill_normal(float *out, int64_t n, uint64_t seed, const int64_t *counter, int stream_id,
+                     void *stream);
+
+/* Stock-net forward for the actor side / tests: out[rows, O] = net(x[rows, in]). */
+int asac_mlp_forward(const float *params, int in_dim, int hidden, int depth, int out_dim,
+                     const float *x, int64_t rows, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASAC_B200_H */

@@ -1,0 +1,205 @@
+"""Drives the SAC kernels of libasac_b200.so through the C ABI on explicit tensors, stage by
+stage, so that every intermediate can be compared with the CPU oracle (tests only)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from asac_b200 import _lib, lowering
+from asac_b200._lib import check, ptr
+
+
+class SacCuda:
+    """Holds the flat parameters / Adam state / work buffers for one SacHyper and exposes the
+    staged entry points of include/asac_b200.h."""
+
+    def __init__(self, hp, batch_size: int, device='cuda:0'):
+        self.lib = _lib.load()
+        self.hp, self.B = hp, batch_size
+        self.dev = torch.device(device)
+        S, A, E = hp.state_size, hp.action_size, hp.ensemble_q_num
+        self.q_shape = lowering.NetShape(S + A, hp.hidden, hp.q_depth, 1)
+        self.pi_shape = lowering.NetShape(S, hp.hidden, hp.policy_depth, 2 * A)
+        assert self.q_shape.count == self.lib.asac_mlp_param_count(S + A, hp.hidden, hp.q_depth, 1)
+        assert self.q_shape.stride == self.lib.asac_mlp_param_stride(S + A, hp.hidden, hp.q_depth, 1)
+        assert self.pi_shape.count == self.lib.asac_mlp_param_count(S, hp.hidden, hp.policy_depth, 2 * A)
+        n, L = hp.n_step, hp.burn_in_step + hp.n_step + 1
+        self.L = L
+        cfg = _lib.AsacSacConfig()
+        cfg.learning_rate = float(hp.learning_rate)
+        cfg.batch, cfg.seq_len, cfg.burn_in, cfg.n_step = batch_size, L, hp.burn_in_step, n
+        cfg.state_size, cfg.action_size, cfg.ensemble = S, A, E
+        cfg.q_hidden, cfg.q_depth, cfg.pi_hidden, cfg.pi_depth = hp.hidden, hp.q_depth, hp.hidden, hp.policy_depth
+        cfg.use_n_step_is, cfg.use_priority = int(hp.use_n_step_is), int(hp.use_priority)
+        cfg.use_auto_alpha = int(hp.use_auto_alpha)
+        cfg.update_target_per_step = int(hp.update_target_per_step)
+        cfg.bn_stride = L - 1  # golden batches carry [B, L-1, ...] arrays
+        cfg.tau, cfg.one_minus_tau = float(hp.tau), float(np.float32(1. - hp.tau))
+        cfg.gamma, cfg.v_rho, cfg.v_c = float(hp.gamma), float(hp.v_rho), float(hp.v_c)
+        cfg.clip_epsilon, cfg.target_c_alpha = float(hp.clip_epsilon), float(hp.target_c_alpha)
+        cfg.td_error_min, cfg.td_error_max, cfg.per_alpha = 0.01, 1.0, 0.9
+        gr = torch.logspace(0, n - 1, n, hp.gamma)
+        lr = torch.logspace(0, n - 1, n, hp.v_lambda)
+        for k in range(n):
+            cfg.gamma_ratio[k], cfg.lambda_ratio[k] = float(gr[k]), float(lr[k])
+        self.cfg = cfg
+        tile = self.lib.asac_sac_tile_batch(C.byref(cfg))
+        assert tile >= 1, self.lib.asac_last_error()
+        self.tile = tile
+        T = self.n_tiles = (batch_size + tile - 1) // tile
+
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        Pq, Ppi = self.q_shape.stride, self.pi_shape.stride
+        self.q = torch.zeros(E, Pq, **f32)
+        self.qt = torch.zeros(E, Pq, **f32)
+        self.pi = torch.zeros(Ppi, **f32)
+        self.log_alpha = torch.zeros(1, **f32)
+        self.q_m, self.q_v = torch.zeros_like(self.q), torch.zeros_like(self.q)
+        self.pi_m, self.pi_v = torch.zeros_like(self.pi), torch.zeros_like(self.pi)
+        self.alpha_m, self.alpha_v = torch.zeros(1, **f32), torch.zeros(1, **f32)
+        self.counters = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        prm = _lib.AsacSacParams()
+        prm.q, prm.q_target, prm.pi, prm.log_alpha = ptr(self.q), ptr(self.qt), ptr(self.pi), ptr(self.log_alpha)
+        prm.q_m, prm.q_v, prm.pi_m, prm.pi_v = ptr(self.q_m), ptr(self.q_v), ptr(self.pi_m), ptr(self.pi_v)
+        prm.alpha_m, prm.alpha_v, prm.counters = ptr(self.alpha_m), ptr(self.alpha_v), ptr(self.counters)
+        self.prm = prm
+
+        self.wk = {
+            'y': torch.zeros(batch_size, **f32), 'tq': torch.zeros(E, batch_size, **f32),
+            'q_val': torch.zeros(E, batch_size, **f32), 'loss_q': torch.zeros(T, E, **f32),
+            'grad_q_part': torch.zeros(T, E, Pq, **f32), 'grad_q': torch.zeros(E, Pq, **f32),
+            'grad_pi_part': torch.zeros(T, Ppi, **f32), 'grad_pi': torch.zeros(Ppi, **f32),
+            'stats_pi': torch.zeros(T, 2, **f32), 'grad_alpha_part': torch.zeros(T, 2, **f32),
+            'grad_alpha': torch.zeros(1, **f32), 'pi_probs': torch.zeros(batch_size, L - 1, A, **f32),
+            'y_td': torch.zeros(batch_size, **f32), 'td_error': torch.zeros(batch_size, **f32),
+        }
+        work = _lib.AsacSacWork()
+        work.n_tiles = T
+        for k, t in self.wk.items():
+            setattr(work, k, ptr(t))
+        self.work = work
+        self._keep = []
+
+    # ---- parameters
+    def load_params(self, q, q_target, policy, log_c_alpha):
+        for i, sd in enumerate(q):
+            self.q[i].copy_(lowering.flat_from_state_dict(self.q_shape, sd, policy=False))
+        for i, sd in enumerate(q_target):
+            self.qt[i].copy_(lowering.flat_from_state_dict(self.q_shape, sd, policy=False))
+        self.pi.copy_(lowering.flat_from_state_dict(self.pi_shape, policy, policy=True))
+        self.log_alpha.fill_(float(log_c_alpha))
+
+    def snapshot(self) -> dict:
+        d = {}
+        for i in range(self.hp.ensemble_q_num):
+            for k, t in lowering.state_dict_from_flat(self.q_shape, self.q[i], False).items():
+                d[f'q{i}.{k}'] = t.cpu().numpy()
+            for k, t in lowering.state_dict_from_flat(self.q_shape, self.qt[i], False).items():
+                d[f'qt{i}.{k}'] = t.cpu().numpy()
+        for k, t in lowering.state_dict_from_flat(self.pi_shape, self.pi, True).items():
+            d[f'pi.{k}'] = t.cpu().numpy()
+        d['log_c_alpha'] = self.log_alpha[0].cpu().numpy()
+        return d
+
+    def grad_q_dict(self, i: int) -> dict:
+        return {k: t.cpu().numpy() for k, t in
+                lowering.state_dict_from_flat(self.q_shape, self.wk['grad_q'][i], False).items()}
+
+    def grad_pi_dict(self) -> dict:
+        return {k: t.cpu().numpy() for k, t in
+                lowering.state_dict_from_flat(self.pi_shape, self.wk['grad_pi'], True).items()}
+
+    # ---- batch
+    def make_batch(self, b, noise) -> _lib.AsacSacBatch:
+        """b: oracle SacBatch (CPU tensors, [B, L-1, ...] layout), noise: SacNoise."""
+        dev = self.dev
+        t = {
+            'states': b.states.float(), 'actions': b.actions.float(), 'rewards': b.rewards.float(),
+            'dones': b.dones.to(torch.uint8), 'last_masks': b.last_masks.to(torch.uint8),
+            'padding_masks': b.padding_masks.to(torch.uint8), 'mu_probs': b.mu_probs.float(),
+            'eps_y': noise.eps_y.float(), 'eps_pi': noise.eps_pi.float(), 'eps_alpha': noise.eps_alpha.float(),
+            'eps_td': noise.eps_td.float(),
+        }
+        t = {k: v.contiguous().to(dev) for k, v in t.items()}
+        if b.priority_is is not None:
+            t['priority_is'] = b.priority_is.float().contiguous().view(-1).to(dev)
+        self._keep = [t]
+        batch = _lib.AsacSacBatch()
+        for k, v in t.items():
+            setattr(batch, k, ptr(v))
+        return batch
+
+    # ---- staged calls
+    def _s(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def polyak(self, force_tau=-1.0):
+        check(self.lib.asac_sac_polyak(C.byref(self.cfg), C.byref(self.prm), float(force_tau), self._s()), 'polyak')
+
+    def target_y(self, batch):
+        check(self.lib.asac_sac_target_y(C.byref(self.cfg), C.byref(self.prm), C.byref(batch), C.byref(self.work),
+                                         self._s()), 'target_y')
+
+    def q_backward(self, batch):
+        check(self.lib.asac_sac_q_backward(C.byref(self.cfg), C.byref(self.prm), C.byref(batch), C.byref(self.work),
+                                           self._s()), 'q_backward')
+
+    def policy_backward(self, batch):
+        check(self.lib.asac_sac_policy_backward(C.byref(self.cfg), C.byref(self.prm), C.byref(batch),
+                                                C.byref(self.work), self._s()), 'policy_backward')
+
+    def post(self, batch):
+        check(self.lib.asac_sac_post(C.byref(self.cfg), C.byref(self.prm), C.byref(batch), C.byref(self.work),
+                                     self._s()), 'post')
+
+    def reduce_grads(self, which):
+        check(self.lib.asac_sac_reduce_grads(C.byref(self.cfg), C.byref(self.work), which, self._s()), 'reduce')
+
+    def adam(self, which, scale=1.0):
+        check(self.lib.asac_sac_adam(C.byref(self.cfg), C.byref(self.prm), C.byref(self.work), which, float(scale),
+                                     self._s()), 'adam')
+
+    def reduce_adam(self, which):
+        check(self.lib.asac_sac_reduce_adam(C.byref(self.cfg), C.byref(self.prm), C.byref(self.work), which,
+                                            self._s()), 'reduce_adam')
+
+    def advance(self):
+        check(self.lib.asac_sac_advance_step(C.byref(self.prm), self._s()), 'advance')
+
+    def step(self, batch):
+        check(self.lib.asac_sac_step(C.byref(self.cfg), C.byref(self.prm), C.byref(batch), C.byref(self.work),
+                                     self._s()), 'sac_step')
+
+    def staged_step(self, batch) -> dict:
+        """The sequence of asac_sac_step, one entry point at a time, returning every intermediate."""
+        hp, out = self.hp, {}
+        self.polyak()
+        self.target_y(batch)
+        out['y'] = self.wk['y'].cpu().numpy()
+        self.q_backward(batch)
+        self.reduce_grads(0)
+        out['q'] = self.wk['q_val'].cpu().numpy()
+        out['loss_q'] = (self.wk['loss_q'].sum(0) / self.B).cpu().numpy()
+        out['grad_q'] = [self.grad_q_dict(i) for i in range(hp.ensemble_q_num)]
+        self.adam(0)
+        self.policy_backward(batch)
+        self.reduce_grads(1)
+        out['grad_policy'] = self.grad_pi_dict()
+        out['loss_policy'] = float(self.wk['stats_pi'][:, 0].sum().item()) / self.B
+        out['entropy'] = float(self.wk['stats_pi'][:, 1].sum().item()) / self.B
+        self.adam(1)
+        if hp.use_auto_alpha or hp.use_n_step_is or hp.use_priority:
+            self.post(batch)
+            if hp.use_n_step_is:
+                out['pi_probs'] = self.wk['pi_probs'].cpu().numpy()
+            if hp.use_priority:
+                out['td_error'] = self.wk['td_error'].cpu().numpy()
+                out['y_td'] = self.wk['y_td'].cpu().numpy()
+        if hp.use_auto_alpha:
+            self.reduce_grads(2)
+            out['grad_log_alpha'] = self.wk['grad_alpha'].cpu().numpy()
+            self.adam(2)
+        self.advance()
+        return out

@@ -1,0 +1,169 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/asac_b200.h declares, the
+ctypes mirror of its structs has the C layout, the host-side lowering is consistent with the
+oracle's parameter naming, and the product path refuses to run without CUDA (no fallback)."""
+import ctypes as C
+import importlib.util
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / 'include' / 'asac_b200.h'
+
+
+def _declared_symbols():
+    text = re.sub(r'/\*.*?\*/', '', HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r'\b(asac_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from asac_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), f'{name} declared in {HEADER.name} but not exported'
+        assert name in _lib.PROTOTYPES, f'{name} has no ctypes prototype'
+    assert set(_lib.PROTOTYPES) == set(names)
+    assert lib.asac_version() >= 100
+
+
+def test_struct_layout_matches_c(tmp_path):
+    """sizeof/offsetof from a C translation unit vs the ctypes mirror."""
+    from asac_b200 import _lib
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "asac_b200.h"\nint main(void){\n'
+                   'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(AsacSacConfig), sizeof(AsacSacParams), '
+                   'sizeof(AsacSacBatch), sizeof(AsacSacWork), sizeof(AsacColumnTable), sizeof(AsacColumn));\n'
+                   'printf("%zu %zu %zu %zu %zu\\n", offsetof(AsacSacConfig, tau), offsetof(AsacSacConfig, gamma_ratio), '
+                   'offsetof(AsacSacConfig, lambda_ratio), offsetof(AsacSacWork, y), offsetof(AsacColumnTable, col));\n'
+                   'return 0;}\n')
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', str(ROOT / 'include'), str(src), '-o', str(exe)])
+    sizes, offs = [list(map(int, line.split())) for line in subprocess.check_output([str(exe)]).decode().splitlines()]
+    assert sizes == [C.sizeof(_lib.AsacSacConfig), C.sizeof(_lib.AsacSacParams), C.sizeof(_lib.AsacSacBatch),
+                     C.sizeof(_lib.AsacSacWork), C.sizeof(_lib.AsacColumnTable), C.sizeof(_lib.AsacColumn)]
+    assert offs == [_lib.AsacSacConfig.tau.offset, _lib.AsacSacConfig.gamma_ratio.offset,
+                    _lib.AsacSacConfig.lambda_ratio.offset, _lib.AsacSacWork.y.offset,
+                    _lib.AsacColumnTable.col.offset]
+
+
+def test_host_only_entry_points():
+    from asac_b200 import _lib, lowering
+    lib = _lib.load()
+    for (i, h, d, o) in [(8, 64, 3, 1), (6, 64, 3, 4), (4, 64, 2, 1), (5, 32, 1, 6)]:
+        shape = lowering.NetShape(i, h, d, o)
+        assert lib.asac_mlp_param_count(i, h, d, o) == shape.count
+        assert lib.asac_mlp_param_stride(i, h, d, o) == shape.stride
+    assert lowering.NetShape(8, 64, 3, 1).count == 8961
+    assert lowering.NetShape(6, 64, 3, 4).count == 9028
+    cfg = _lib.AsacSacConfig()
+    cfg.batch, cfg.seq_len, cfg.burn_in, cfg.n_step = 256, 2, 0, 1
+    cfg.state_size, cfg.action_size, cfg.ensemble = 6, 2, 2
+    cfg.q_hidden = cfg.pi_hidden = 64
+    cfg.q_depth = cfg.pi_depth = 3
+    cfg.bn_stride, cfg.update_target_per_step = 2, 1
+    assert lib.asac_sac_tile_batch(C.byref(cfg)) == 16
+    cfg.q_hidden = 48  # not a supported width -> error code + message, no crash
+    assert lib.asac_sac_tile_batch(C.byref(cfg)) < 0
+    assert b'hidden width' in lib.asac_last_error()
+    # long R2D2-style windows shrink the tile instead of overflowing shared memory
+    cfg.q_hidden, cfg.burn_in, cfg.n_step, cfg.seq_len, cfg.bn_stride = 64, 40, 5, 46, 46
+    cfg.use_n_step_is = 1
+    assert 1 <= lib.asac_sac_tile_batch(C.byref(cfg)) < 16
+
+
+def _load_plugin(tmp_path, text):
+    path = tmp_path / 'nn_plugin_cpu.py'
+    path.write_text(text)
+    spec = importlib.util.spec_from_file_location('nn_plugin_cpu', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_plugin_file_loads_unchanged_and_matches_oracle_forward(tmp_path):
+    """envs/gym/pendulum/nn.py's text, imported through the `algorithm` alias package."""
+    from asac_b200 import lowering
+    from oracle.sac_oracle import policy_forward, q_forward
+    nn = _load_plugin(tmp_path, 'import algorithm.nn_models as m\n\nModelRep = m.ModelSimpleRep\n\n\n'
+                                'class ModelQ(m.ModelQ):\n    def _build_model(self):\n'
+                                '        super()._build_model(c_dense_n=64, c_dense_depth=2)\n\n\n'
+                                'class ModelPolicy(m.ModelPolicy):\n    def _build_model(self):\n'
+                                '        super()._build_model(c_dense_n=64, c_dense_depth=2)\n')
+    torch.manual_seed(0)
+    q = nn.ModelQ(3, [], 1, False, None)
+    pi = nn.ModelPolicy(3, [], 1, None)
+    q_shape, q_params = lowering.analyze_q(q)
+    pi_shape, pi_params = lowering.analyze_policy(pi)
+    assert (q_shape.in_dim, q_shape.hidden, q_shape.depth, q_shape.out_dim) == (4, 64, 2, 1)
+    assert (pi_shape.in_dim, pi_shape.hidden, pi_shape.depth, pi_shape.out_dim) == (3, 64, 2, 2)
+    assert list(q.state_dict()) == ['c_dense.dense.0.linear.weight', 'c_dense.dense.0.linear.bias',
+                                    'c_dense.dense.2.linear.weight', 'c_dense.dense.2.linear.bias',
+                                    'c_dense.dense.4.weight', 'c_dense.dense.4.bias']
+    with torch.no_grad():
+        for p in list(q.parameters()) + list(pi.parameters()):
+            p.add_(torch.randn_like(p) * 0.1)
+    s, a = torch.randn(9, 3), torch.rand(9, 1)
+    assert torch.allclose(q(s, a, [s])[1], q_forward(dict(q.state_dict()), 2, s, a), atol=1e-6)
+    dist = pi(s, [s])[1]
+    loc, scale = policy_forward(dict(pi.state_dict()), 2, s)
+    assert torch.allclose(dist.loc, loc, atol=1e-6) and torch.allclose(dist.scale, scale, atol=1e-6)
+    # binding: parameters become views of the flat buffer, in the kernel's layout
+    flat_q = torch.zeros(q_shape.stride)
+    expect = lowering.flat_from_state_dict(q_shape, q.state_dict(), policy=False)
+    lowering.bind_parameters(q_params, flat_q)
+    assert torch.equal(flat_q, expect)
+    flat_pi = torch.zeros(pi_shape.stride)
+    expect = lowering.flat_from_state_dict(pi_shape, pi.state_dict(), policy=True)
+    lowering.bind_parameters(pi_params, flat_pi)
+    assert torch.equal(flat_pi, expect)
+    flat_q[0] = 42.
+    assert float(q.c_dense.dense[0].linear.weight[0, 0]) == 42.
+    back = lowering.state_dict_from_flat(pi_shape, flat_pi, policy=True)
+    for k, v in pi.state_dict().items():
+        assert torch.equal(back[k], v), k
+    assert torch.allclose(q(s, a, [s])[1], q_forward(dict(q.state_dict()), 2, s, a), atol=1e-6)
+
+
+def test_non_stock_networks_are_rejected(tmp_path):
+    from asac_b200 import lowering
+    import asac_b200.nn_models as m
+
+    class QWithState(m.ModelQ):
+        def _build_model(self):
+            super()._build_model(c_state_depth=1)
+
+    class QOverride(m.ModelQ):
+        def forward(self, state, c_action, obs_list):
+            return super().forward(state[..., :-1], c_action, obs_list)
+
+    with pytest.raises(lowering.NotStockNetwork):
+        lowering.analyze_q(QWithState(6, [], 2, False))
+    with pytest.raises(lowering.NotStockNetwork):
+        lowering.analyze_q(QOverride(6, [], 2, False))
+    with pytest.raises(lowering.NotStockNetwork):
+        lowering.analyze_q(m.ModelQ(6, [3], 2, False))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_product_path_fails_loudly_without_cuda(tmp_path):
+    from asac_b200 import PrioritizedReplayBuffer, SAC_Base, _lib
+    with pytest.raises(_lib.AsacError, match='no CPU fallback'):
+        PrioritizedReplayBuffer(batch_size=4, capacity=16)
+    nn = _load_plugin(tmp_path, 'import algorithm.nn_models as m\nModelRep = m.ModelSimpleRep\n'
+                                'ModelQ = m.ModelQ\nModelPolicy = m.ModelPolicy\n')
+    with pytest.raises(_lib.AsacError, match='no CPU fallback'):
+        SAC_Base(obs_names=['v'], obs_shapes=[(6,)], d_action_sizes=[], c_action_size=2, model_abs_dir=None, nn=nn)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = ROOT / 'advanced-soft-actor-critic_b200'
+    for path in pkg.rglob('*.py'):
+        text = path.read_text()
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), path

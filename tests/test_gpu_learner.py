@@ -1,0 +1,164 @@
+"""GPU: the SAC_Base drop-in end to end — plugin files load unchanged, train() advances, the CUDA
+graph replays the eager sequence bit-for-bit, checkpoints round-trip."""
+import importlib.util
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PLUGIN_TEST = '''import algorithm.nn_models as m
+
+ModelRep = m.ModelSimpleRep
+ModelQ = m.ModelQ
+ModelPolicy = m.ModelPolicy
+'''
+
+PLUGIN_PENDULUM = '''import algorithm.nn_models as m
+
+ModelRep = m.ModelSimpleRep
+
+
+class ModelQ(m.ModelQ):
+    def _build_model(self):
+        super()._build_model(c_dense_n=64, c_dense_depth=2)
+
+
+class ModelPolicy(m.ModelPolicy):
+    def _build_model(self):
+        super()._build_model(c_dense_n=64, c_dense_depth=2)
+'''
+
+
+def _plugin(tmp_path: Path, text: str, name: str):
+    path = tmp_path / f'{name}.py'
+    path.write_text(text)  # same text as the reference's envs/test/nn.py / envs/gym/pendulum/nn.py
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _episode(rng, obs_shapes, A, T):
+    return dict(ep_indexes=np.arange(T, dtype=np.int32)[None],
+                ep_obses_list=[rng.randn(1, T, *s).astype(np.float32) for s in obs_shapes],
+                ep_actions=rng.rand(1, T, A).astype(np.float32), ep_rewards=rng.randn(1, T).astype(np.float32),
+                ep_dones=rng.randint(0, 2, size=(1, T)).astype(bool), ep_probs=rng.rand(1, T, A).astype(np.float32),
+                ep_pre_seq_hidden_states=np.zeros((1, T, 0), dtype=np.float32))
+
+
+def _make(nn, graph, obs_shapes=((6,),), A=2, **kw):
+    from algorithm.sac_base import SAC_Base  # the alias package: reference-style import
+    kw.setdefault('batch_size', 64)
+    kw.setdefault('replay_config', {'capacity': 4096})
+    sac = SAC_Base(obs_names=[f'o{i}' for i in range(len(obs_shapes))], obs_shapes=list(obs_shapes),
+                   d_action_sizes=[], c_action_size=A, model_abs_dir=None, nn=nn, seed=7, use_cuda_graph=graph, **kw)
+    rng = np.random.RandomState(0)
+    for _ in range(12):
+        sac.put_episode(**_episode(rng, obs_shapes, A, 50))
+    return sac
+
+
+@pytest.mark.parametrize('plugin,kw', [(PLUGIN_TEST, dict()),
+                                       (PLUGIN_PENDULUM, dict(n_step=5, v_lambda=1.0, use_n_step_is=True)),
+                                       (PLUGIN_TEST, dict(burn_in_step=2, n_step=3, use_priority=False))])
+def test_graph_replay_equals_eager(tmp_path, plugin, kw):
+    nn = _plugin(tmp_path, plugin, 'nn_plugin')
+    a = _make(nn, graph=False, **kw)
+    b = _make(nn, graph=True, **kw)
+    for i in range(6):
+        assert a.train() == i + 1
+        assert b.train() == i + 1
+    torch.cuda.synchronize()
+    assert b._graph is not None and a._graph is None
+    for pa, pb in zip(a.model_policy.parameters(), b.model_policy.parameters()):
+        assert torch.equal(pa, pb)
+    for qa, qb in zip(a.model_q_list + a.model_target_q_list, b.model_q_list + b.model_target_q_list):
+        for pa, pb in zip(qa.parameters(), qb.parameters()):
+            assert torch.equal(pa, pb)
+    assert torch.equal(a.replay_buffer._nodes, b.replay_buffer._nodes)
+    assert torch.equal(a.replay_buffer._columns['mu_prob'], b.replay_buffer._columns['mu_prob'])
+    assert torch.equal(a.log_c_alpha, b.log_c_alpha)
+    stats = b.last_step_stats()
+    assert all(np.isfinite(v) for v in stats.values()), stats
+    assert float(a.log_c_alpha) != pytest.approx(-2.3, abs=1e-9)  # alpha moved
+    a.close(); b.close()
+
+
+def test_train_returns_step_until_buffer_exceeds_batch(tmp_path):
+    from algorithm.sac_base import SAC_Base
+    nn = _plugin(tmp_path, PLUGIN_TEST, 'nn_plugin2')
+    sac = SAC_Base(obs_names=['v'], obs_shapes=[(6,)], d_action_sizes=[], c_action_size=2, model_abs_dir=None, nn=nn,
+                   batch_size=32, replay_config={'capacity': 256})
+    assert sac.train() == 0  # sac_base.py:2503-2506
+    rng = np.random.RandomState(0)
+    sac.put_episode(**_episode(rng, [(6,)], 2, 20))
+    assert sac.train() == 0
+    sac.put_episode(**_episode(rng, [(6,)], 2, 20))
+    assert sac.train() == 1
+    action, prob, hidden = sac.choose_action([rng.randn(5, 6).astype(np.float32)],
+                                             np.zeros((5, 2), np.float32), np.zeros((5, 0), np.float32))
+    assert action.shape == (5, 2) and prob.shape == (5, 2) and hidden.shape == (5, 0)
+    assert np.all(np.abs(action) <= 1)
+    sac.close()
+
+
+def test_module_parameters_alias_kernel_storage(tmp_path):
+    """The nn.Module parameters are views of the flat buffers the kernels update."""
+    nn = _plugin(tmp_path, PLUGIN_TEST, 'nn_plugin3')
+    sac = _make(nn, graph=False)
+    w = sac.model_q_list[1].c_dense.dense[0].linear.weight
+    before = w.detach().clone()
+    sac.train()
+    torch.cuda.synchronize()
+    assert not torch.equal(before, w)
+    flat = sac._q_flat[1, :w.numel()].view_as(w)
+    assert flat.data_ptr() == w.data_ptr() and torch.equal(flat, w)
+    # hard-copied targets at start, polyak afterwards: target != online after a step
+    assert not torch.equal(sac._q_flat, sac._qt_flat)
+    sac.close()
+
+
+def test_checkpoint_roundtrip_and_reference_key_names(tmp_path):
+    nn = _plugin(tmp_path, PLUGIN_TEST, 'nn_plugin4')
+    from algorithm.sac_base import SAC_Base
+    mk = lambda: SAC_Base(obs_names=['v'], obs_shapes=[(6,)], d_action_sizes=[], c_action_size=2,
+                          model_abs_dir=tmp_path / 'run', nn=nn, batch_size=32, summary_path=None,
+                          replay_config={'capacity': 256}, seed=1)
+    sac = mk()
+    rng = np.random.RandomState(0)
+    for _ in range(3):
+        sac.put_episode(**_episode(rng, [(6,)], 2, 30))
+    for _ in range(3):
+        sac.train()
+    sac.save_model(save_replay_buffer=True)
+    saved = torch.load(tmp_path / 'run' / 'model' / '3.pth', weights_only=True)
+    assert set(saved) == {'global_step', 'model_q_0', 'model_target_q_0', 'optimizer_q_0', 'model_q_1',
+                          'model_target_q_1', 'optimizer_q_1', 'model_policy', 'optimizer_policy', 'log_d_alpha',
+                          'log_c_alpha', 'optimizer_alpha'}
+    assert 'c_dense.dense.0.linear.weight' in saved['model_q_0']
+    assert 'mean_dense.dense.0.weight' in saved['model_policy']
+    assert float(saved['optimizer_q_0']['state'][0]['step']) == 3
+    other = mk()
+    assert other.get_global_step() == 3
+    assert torch.equal(other._q_flat, sac._q_flat) and torch.equal(other._pi_m, sac._pi_m)
+    assert torch.equal(other._counters, sac._counters)
+    assert torch.equal(other.replay_buffer._nodes, sac.replay_buffer._nodes)
+    assert other.replay_buffer.size == sac.replay_buffer.size
+    assert other.train() == 4
+    sac.close(); other.close()
+
+
+def test_unsupported_configurations_fail_loudly(tmp_path):
+    from algorithm.sac_base import SAC_Base
+    nn = _plugin(tmp_path, PLUGIN_TEST, 'nn_plugin5')
+    base = dict(obs_names=['v'], obs_shapes=[(6,)], c_action_size=2, model_abs_dir=None, nn=nn)
+    with pytest.raises(NotImplementedError):
+        SAC_Base(d_action_sizes=[3], **base)
+    with pytest.raises(NotImplementedError):
+        SAC_Base(d_action_sizes=[], use_rnd=True, **base)
+    with pytest.raises(Exception):
+        SAC_Base(d_action_sizes=[], device='cpu', **base)

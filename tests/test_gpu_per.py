@@ -1,0 +1,191 @@
+"""GPU parity: the HBM segment tree / storage kernels and the PrioritizedReplayBuffer host class
+against the golden traces minted from the reference and against the NumPy oracle.
+Integer / index results and fp32 tree nodes are compared bit-exactly."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+EP_KEYS = ['index', 'last_mask', 'obs_vector', 'obs_image', 'action', 'reward', 'done', 'mu_prob',
+           'pre_seq_hidden_state']
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize('name', ['per_small.npz', 'per_zeros.npz'])
+def test_replay_trace_bit_exact(name):
+    """Same trace as tests/test_oracle_golden.py::test_per_trace_bit_exact, on the GPU buffer."""
+    from asac_b200 import PrioritizedReplayBuffer
+    g = load_golden(name)
+    capacity, batch_size, prev_n, post_n, n_rounds, n_eps = [int(x) for x in g['meta']]
+    rb = PrioritizedReplayBuffer(batch_size=batch_size, sample_prev_n=prev_n, sample_post_n=post_n,
+                                 device='cuda:0', capacity=capacity, alpha=float(g['alpha']))
+    for e in range(n_eps):
+        rb.add({k: g[f'add{e}.{k}'] for k in EP_KEYS}, ignore_size=1)
+        assert np.array_equal(_np(rb.tree_nodes()), g[f'add{e}.tree']), f'tree after add {e}'
+        assert np.array_equal(_np(rb._store_ids), g[f'add{e}.ids'])
+    lib = rb._lib
+    for r in range(n_rounds):
+        if r == 0 and 'zeroed.idx' in g:
+            idx = torch.from_numpy(g['zeroed.idx']).cuda()
+            zeros = torch.zeros(len(idx), device='cuda')
+            assert lib.asac_tree_update(rb._nodes.data_ptr(), capacity, idx.data_ptr(), zeros.data_ptr(), len(idx),
+                                        torch.cuda.current_stream().cuda_stream) == 0
+            assert np.array_equal(_np(rb.tree_nodes()), g['zeroed.tree'])
+        assert rb.beta == pytest.approx(float(g[f'r{r}.beta_before']))
+        data_ids, batch, weights = rb.sample(unit_uniform=g[f'r{r}.u'])
+        assert np.array_equal(_np(data_ids), g[f'r{r}.data_ids'])
+        w, w_ref = _np(weights)[:, 0], g[f'r{r}.is_weights']
+        assert np.max(np.abs(w.view(np.int32) - w_ref.view(np.int32))) <= 1, 'IS weights differ by more than 1 ulp'
+        for k in EP_KEYS:
+            assert np.array_equal(_np(batch[k]), g[f'r{r}.batch.{k}']), k
+        rb.update(g[f'r{r}.upd_ids'], g[f'r{r}.td'])
+        tree, ref = _np(rb.tree_nodes()), g[f'r{r}.tree_after_update']
+        assert np.array_equal(tree, ref), f'round {r}: {np.sum(tree != ref)} nodes differ after update'
+        rb.update_transitions(g[f'r{r}.upd_ids'], 'mu_prob', g[f'r{r}.new_mu'])
+        assert np.array_equal(_np(rb._columns['mu_prob']), g[f'r{r}.mu_after'])
+        rb.add({k: g[f'r{r}.ep.{k}'] for k in EP_KEYS}, ignore_size=1)
+        assert np.array_equal(_np(rb.tree_nodes()), g[f'r{r}.tree_after_add'])
+    assert np.array_equal(_np(rb._store_ids), g['final.ids'])
+    assert rb.size == int(g['final.size'])
+    assert rb._next_id == int(g['final.next_id'])
+    rb.check_nan()
+    rb.close()
+
+
+def test_tree_full_capacity_against_oracle():
+    """BASELINE capacity (524288): random updates with duplicates, rebuild, max, 4096 samples."""
+    from asac_b200 import _lib
+    from oracle.replay_oracle import SumTreeOracle
+    lib = _lib.load()
+    C = 524288
+    rng = np.random.RandomState(0)
+    s = torch.cuda.current_stream().cuda_stream
+    nodes = torch.zeros(2 * C, device='cuda')
+    oracle = SumTreeOracle(C)
+    # bulk leaves + rebuild
+    leaves = np.power(np.clip(np.abs(rng.randn(C)).astype(np.float32), 0.01, 1.0), np.float32(0.9))
+    leaves[rng.rand(C) < 0.2] = 0
+    nodes[C:] = torch.from_numpy(leaves).cuda()
+    assert lib.asac_tree_rebuild(nodes.data_ptr(), C, s) == 0
+    oracle.nodes[C - 1:] = leaves
+    oracle.rebuild()
+    assert np.array_equal(_np(nodes[1:]), oracle.nodes)
+    # incremental updates (k = 256 with duplicates, then k = 3000 > one chunk)
+    for k in (256, 3000):
+        idx = rng.randint(0, C, size=k).astype(np.int64)
+        idx[5] = idx[3]
+        p = rng.rand(k).astype(np.float32)
+        ti, tp = torch.from_numpy(idx).cuda(), torch.from_numpy(p).cuda()
+        assert lib.asac_tree_update(nodes.data_ptr(), C, ti.data_ptr(), tp.data_ptr(), k, s) == 0
+        oracle.update(idx, p)
+        got = _np(nodes[1:])
+        assert np.array_equal(got, oracle.nodes), f'k={k}: {np.sum(got != oracle.nodes)} nodes differ'
+    out = torch.zeros(1, device='cuda')
+    assert lib.asac_tree_leaf_max(nodes.data_ptr(), C, out.data_ptr(), s) == 0
+    assert float(out.item()) == float(oracle.leaf_max)
+    # sampling: injected uniforms, bit-exact leaves
+    B = 4096
+    u = rng.random_sample(B)
+    tu = torch.from_numpy(u).cuda()
+    slot = torch.zeros(B, dtype=torch.int32, device='cuda')
+    pr = torch.zeros(B, device='cuda')
+    assert lib.asac_tree_sample(nodes.data_ptr(), C, B, tu.data_ptr(), 0, None, slot.data_ptr(), pr.data_ptr(),
+                                s) == 0
+    leaf, p_ref = oracle.descend(oracle.draw(B, u))
+    assert np.array_equal(_np(slot), leaf - (C - 1))
+    assert np.array_equal(_np(pr), p_ref)
+    # device-generated uniforms: every sample lands in its stratum and on a non-zero leaf
+    counter = torch.zeros(1, dtype=torch.int64, device='cuda')
+    assert lib.asac_tree_sample(nodes.data_ptr(), C, B, None, 77, counter.data_ptr(), slot.data_ptr(),
+                                pr.data_ptr(), s) == 0
+    sl = _np(slot).astype(np.int64)
+    assert (_np(pr) > 0).all() and np.array_equal(_np(pr), leaves[sl])
+    cum = np.cumsum(leaves.astype(np.float64))
+    seg = float(oracle.total) / B
+    lo = np.concatenate([[0.], cum[:-1]])[sl]
+    assert (cum[sl] >= np.arange(B) * seg * (1 - 1e-5)).all() and (lo <= (np.arange(B) + 1) * seg * (1 + 1e-5)).all()
+
+
+def test_nan_td_error_raises_and_leaves_tree():
+    from asac_b200 import PrioritizedReplayBuffer
+    rb = PrioritizedReplayBuffer(batch_size=4, device='cuda:0', capacity=64)
+    rb.add({'index': np.arange(20, dtype=np.int32), 'x': np.random.randn(20, 3).astype(np.float32)})
+    before = rb.tree_nodes().clone()
+    ids = np.arange(4, dtype=np.int64)
+    rb.update(ids, np.array([0.5, np.nan, 0.1, 0.2], dtype=np.float32))
+    with pytest.raises(Exception, match='td_error has nan'):
+        rb.check_nan()
+    assert torch.equal(before, rb.tree_nodes())
+    assert rb.sample() is not None  # still usable
+
+
+@pytest.mark.parametrize('name', ['pad_b2n3.npz', 'pad_b0n1.npz'])
+def test_fused_gather_padding_matches_reference(name):
+    """The gather kernel with role substitution == reference sample + _sample_from_replay_buffer
+    padding (sac_base.py:2435-2453)."""
+    from asac_b200 import PrioritizedReplayBuffer, _lib
+    g = load_golden(name)
+    b, n, B, capacity = [int(x) for x in g['meta']]
+    L = b + n + 1
+    raw = {k[4:]: v for k, v in g.items() if k.startswith('raw.')}
+    # rebuild a ring whose rows at the sampled windows equal the raw gathered rows
+    rb = PrioritizedReplayBuffer(batch_size=B, sample_prev_n=b, sample_post_n=n, device='cuda:0', capacity=capacity)
+    ids = g['data_ids'].astype(np.int64)
+    window = (ids[:, None] + np.arange(-b, n + 1)[None, :]).reshape(-1)
+    slots = window % capacity
+    cols = {}
+    for k, v in raw.items():
+        flat = v.reshape(B * L, *v.shape[2:])
+        ring = np.zeros((capacity, *flat.shape[1:]), dtype=flat.dtype)
+        ring[slots] = flat
+        cols[k] = torch.from_numpy(ring).cuda()
+    rb._columns = cols
+    dev = 'cuda:0'
+    A, S = raw['action'].shape[-1], raw['obs_vector'].shape[-1]
+    out = {'index': torch.zeros(B, L, dtype=torch.int32, device=dev),
+           'last_mask': torch.zeros(B, L, dtype=torch.uint8, device=dev),
+           'action': torch.zeros(B, L, A, device=dev), 'reward': torch.zeros(B, L, device=dev),
+           'done': torch.zeros(B, L, dtype=torch.uint8, device=dev), 'mu_prob': torch.zeros(B, L, A, device=dev),
+           'states': torch.zeros(B, L, S, device=dev)}
+    specs = [('index', out['index'], 4, 0, _lib.ROLE_INDEX), ('last_mask', out['last_mask'], 1, 0, _lib.ROLE_COPY),
+             ('action', out['action'], 4 * A, 0, _lib.ROLE_ACTION), ('reward', out['reward'], 4, 0, _lib.ROLE_REWARD),
+             ('done', out['done'], 1, 0, _lib.ROLE_DONE), ('mu_prob', out['mu_prob'], 4 * A, 0, _lib.ROLE_MU_PROB),
+             ('obs_vector', out['states'], 4 * S, 0, _lib.ROLE_COPY)]
+    mask = torch.zeros(B, L, dtype=torch.uint8, device=dev)
+    rb._gather(torch.from_numpy(ids).cuda(), specs, torch.zeros(A, device=dev), mask)
+    assert np.array_equal(_np(out['index'])[:, :-1], g['padded.bn_indexes'])
+    assert np.array_equal(_np(mask)[:, :-1].astype(bool), g['padded.bn_padding_masks'])
+    assert np.array_equal(_np(out['last_mask'])[:, :-1].astype(bool), g['padded.bn_last_masks'])
+    assert np.array_equal(_np(out['action'])[:, :-1], g['padded.bn_actions'])
+    assert np.array_equal(_np(out['reward'])[:, :-1], g['padded.bn_rewards'])
+    assert np.array_equal(_np(out['done'])[:, :-1].astype(bool), g['padded.bn_dones'])
+    assert np.array_equal(_np(out['mu_prob'])[:, :-1], g['padded.bn_mu_probs'])
+    assert np.array_equal(_np(out['states']), g['padded.bnx_obs'])
+
+
+def test_write_back_skips_padding_and_stale_ids():
+    from asac_b200 import PrioritizedReplayBuffer
+    rng = np.random.RandomState(1)
+    C, B, b, n, A = 64, 8, 1, 2, 3
+    rb = PrioritizedReplayBuffer(batch_size=B, sample_prev_n=b, sample_post_n=n, device='cuda:0', capacity=C)
+    T = 90  # wraps the ring: ids 0..25 are overwritten
+    rb.add({'index': np.arange(T, dtype=np.int32), 'mu_prob': rng.rand(T, A).astype(np.float32)})
+    ref = _np(rb._columns['mu_prob']).copy()
+    store = _np(rb._store_ids)
+    ids = np.array([30, 40, 89, 10, 88, 27, 63, 64], dtype=np.int64)
+    rows = rng.rand(B, b + n, A).astype(np.float32)
+    pad = rng.rand(B, b + n + 1) < 0.3
+    rb.write_back(torch.from_numpy(ids).cuda(), 'mu_prob', torch.from_numpy(rows).cuda(), -b,
+                  torch.from_numpy(pad.astype(np.uint8)).cuda())
+    for i in range(B):
+        for t in range(b + n):
+            wid = ids[i] - b + t
+            if not pad[i, t] and store[wid % C] == wid:
+                ref[wid % C] = rows[i, t]
+    assert np.array_equal(_np(rb._columns['mu_prob']), ref)
