@@ -61,7 +61,7 @@ class AsacSacWork(C.Structure):
     _fields_ = [('n_tiles', C.c_int32),
                 ('y', vp), ('tq', vp), ('q_val', vp), ('loss_q', vp), ('grad_q_part', vp), ('grad_q', vp),
                 ('grad_pi_part', vp), ('grad_pi', vp), ('stats_pi', vp), ('grad_alpha_part', vp),
-                ('grad_alpha', vp), ('pi_probs', vp), ('y_td', vp), ('td_error', vp)]
+                ('grad_alpha', vp), ('pi_probs', vp), ('post_parts', vp), ('y_td', vp), ('td_error', vp)]
 
 
 i32, i64, u64, f32 = C.c_int, C.c_int64, C.c_uint64, C.c_float
@@ -94,6 +94,7 @@ PROTOTYPES = {
     'asac_sac_reduce_grads': (i32, [P(AsacSacConfig), P(AsacSacWork), i32, vp]),
     'asac_sac_adam': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), i32, f32, vp]),
     'asac_sac_reduce_adam': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), i32, vp]),
+    'asac_sac_td_error': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp]),
     'asac_sac_advance_step': (i32, [P(AsacSacParams), vp]),
     'asac_sac_step': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork), vp]),
     'asac_fill_normal': (i32, [vp, i64, u64, vp, i32, vp]),

@@ -305,37 +305,53 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     }
 
     // ---- per batch element: V, v-trace, y (sac_base.py:1244-1295, 1444-1464)
+    // y is linear in alpha: V_k = qmin_k - alpha * logp_k.  The train pass knows alpha and writes y;
+    // the post pass runs BEFORE the alpha Adam step of the same train() call but _get_td_error uses
+    // the UPDATED alpha (sac_base.py:2115-2116 precede :2571), so it writes the two functionals
+    // (critic part with rewards, log-prob part) and k_alpha_td combines them after the alpha step.
     if (tid < TBa) {
         const int e = tid, eg = e0 + e;
         const float alpha = expf(log_alpha);
-        float v_prev = qmin[e * (n + 1)] - alpha * logp[e * (n + 1)];
-        const float v0 = v_prev;
-        float sum = 0.f, cprod = 1.f;
+        float q_prev = qmin[e * (n + 1)], l_prev = logp[e * (n + 1)];
+        float v_prev = q_prev - alpha * l_prev;
+        const float v0 = v_prev, q0 = q_prev, l0 = l_prev;
+        float sum = 0.f, sum_q = 0.f, sum_l = 0.f, cprod = 1.f;
         for (int k = 0; k < n; ++k) {
-            const float v_next = qmin[e * (n + 1) + k + 1] - alpha * logp[e * (n + 1) + k + 1];
+            const float q_next = qmin[e * (n + 1) + k + 1], l_next = logp[e * (n + 1) + k + 1];
+            const float v_next = q_next - alpha * l_next;
             const int64_t idx = (int64_t)eg * c.bn_stride + b + k;
             const float nd = a.bat.dones[idx] ? 0.f : 1.f;
-            float td = a.bat.rewards[idx] + (c.gamma * nd) * v_next - v_prev;
+            const float rew = a.bat.rewards[idx];
+            float td = rew + (c.gamma * nd) * v_next - v_prev;
+            float td_q = rew + (c.gamma * nd) * q_next - q_prev;
+            float td_l = (c.gamma * nd) * l_next - l_prev;
             td = c.gamma_ratio[k] * td;
+            td_q = c.gamma_ratio[k] * td_q;
+            td_l = c.gamma_ratio[k] * td_l;
             if (use_is) {
                 td = c.lambda_ratio[k] * td;
+                td_q = c.lambda_ratio[k] * td_q;
+                td_l = c.lambda_ratio[k] * td_l;
                 const float is = ratio[e * n + k];
                 const float rho = fminf(is, c.v_rho);
                 td = (cprod * rho) * td;
+                td_q = (cprod * rho) * td_q;
+                td_l = (cprod * rho) * td_l;
                 cprod = cprod * fminf(is, c.v_c);
             }
             const float keep = (a.bat.last_masks[idx] | a.bat.padding_masks[idx]) ? 0.f : 1.f;
             sum += td * keep;
-            v_prev = v_next;
+            sum_q += td_q * keep;
+            sum_l += td_l * keep;
+            v_prev = v_next; q_prev = q_next; l_prev = l_next;
         }
-        const float y = v0 + sum;
         if (!post) {
-            a.wrk.y[eg] = y;
+            a.wrk.y[eg] = v0 + sum;
         } else {
-            a.wrk.y_td[eg] = y;
-            float acc = 0.f;
-            for (int i = 0; i < E; ++i) acc += fabsf(qs[i * TB + e] - y);
-            a.wrk.td_error[eg] = acc / (float)E;
+            float *parts = a.wrk.post_parts + (int64_t)eg * (2 + E);
+            parts[0] = q0 + sum_q;
+            parts[1] = l0 + sum_l;
+            for (int i = 0; i < E; ++i) parts[2 + i] = qs[i * TB + e];
         }
     }
     if (post && c.use_auto_alpha) {
@@ -688,33 +704,48 @@ __global__ void __launch_bounds__(256) k_reduce_adam(const AdamArgs a) {
     a.param[p] = a.param[p] + (step_size * m) / denom;  // addcdiv_(exp_avg, denom, value=-step_size)
 }
 
-// alpha: a single scalar, gradient = (sum over tiles of the alpha terms) / B  (sac_base.py:1941-1948)
-__global__ void k_alpha_adam(const AsacSacParams prm, const AsacSacWork wrk, int n_tiles, int batch, int do_reduce,
-                             int do_adam, float grad_scale, double lr) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float gr;
-    if (do_reduce) {
-        float s = 0.f;
-        for (int t = 0; t < n_tiles; ++t) s += wrk.grad_alpha_part[t * 2];
-        gr = s / (float)batch;
-        wrk.grad_alpha[0] = gr;
-    } else {
-        gr = wrk.grad_alpha[0];
+// alpha: a single scalar, gradient = (sum over tiles of the alpha terms) / B  (sac_base.py:1941-1948),
+// then y' = yq - alpha_new * yl and td = mean_i |Q_i(s_b, a_b) - y'|  (sac_base.py:2223-2245).  One CTA.
+__global__ void __launch_bounds__(1024) k_alpha_td(const AsacSacParams prm, const AsacSacWork wrk, int n_tiles,
+                                                   int batch, int ensemble, int do_reduce, int do_adam, int do_td,
+                                                   float grad_scale, double lr) {
+    if (threadIdx.x == 0 && (do_reduce || do_adam)) {
+        float gr;
+        if (do_reduce) {
+            float s = 0.f;
+            for (int t = 0; t < n_tiles; ++t) s += wrk.grad_alpha_part[t * 2];
+            gr = s / (float)batch;
+            wrk.grad_alpha[0] = gr;
+        } else {
+            gr = wrk.grad_alpha[0];
+        }
+        if (do_adam) {
+            gr = gr * grad_scale;
+            const double t = (double)(prm.counters[3] + 1);
+            const double bc1 = 1.0 - pow(0.9, t), bc2 = 1.0 - pow(0.999, t);
+            const float step_size = (float)(-(lr / bc1));
+            const float bc2_sqrt = (float)sqrt(bc2);
+            const float w1 = (float)(1.0 - 0.9), w2 = (float)(1.0 - 0.999);
+            float m = prm.alpha_m[0], v = prm.alpha_v[0];
+            m = m + w1 * (gr - m);
+            v = v * 0.999f + (w2 * gr) * gr;
+            const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
+            prm.alpha_m[0] = m;
+            prm.alpha_v[0] = v;
+            prm.log_alpha[0] = prm.log_alpha[0] + (step_size * m) / denom;
+        }
     }
-    if (!do_adam) return;
-    gr = gr * grad_scale;
-    const double t = (double)(prm.counters[3] + 1);
-    const double bc1 = 1.0 - pow(0.9, t), bc2 = 1.0 - pow(0.999, t);
-    const float step_size = (float)(-(lr / bc1));
-    const float bc2_sqrt = (float)sqrt(bc2);
-    const float w1 = (float)(1.0 - 0.9), w2 = (float)(1.0 - 0.999);
-    float m = prm.alpha_m[0], v = prm.alpha_v[0];
-    m = m + w1 * (gr - m);
-    v = v * 0.999f + (w2 * gr) * gr;
-    const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
-    prm.alpha_m[0] = m;
-    prm.alpha_v[0] = v;
-    prm.log_alpha[0] = prm.log_alpha[0] + (step_size * m) / denom;
+    if (!do_td) return;
+    __syncthreads();
+    const float alpha = expf(__ldcg(prm.log_alpha));
+    for (int e = threadIdx.x; e < batch; e += blockDim.x) {
+        const float *parts = wrk.post_parts + (int64_t)e * (2 + ensemble);
+        const float y = parts[0] - alpha * parts[1];
+        float acc = 0.f;
+        for (int i = 0; i < ensemble; ++i) acc += fabsf(parts[2 + i] - y);
+        wrk.y_td[e] = y;
+        wrk.td_error[e] = acc / (float)ensemble;
+    }
 }
 
 __global__ void k_bump(int64_t *counters, int mask) {
@@ -939,14 +970,16 @@ extern "C" int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacP
 }
 
 static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk, int which,
-                              int do_reduce, int do_adam, float grad_scale, void *stream) {
+                              int do_reduce, int do_adam, float grad_scale, void *stream, int do_td = 0) {
     int rc = validate(cfg);
     if (rc != ASAC_OK) return rc;
     ASAC_REQUIRE(which >= 0 && which <= 2, "which must be 0 (critics), 1 (policy) or 2 (alpha)");
     if (which == 2) {
-        k_alpha_adam<<<1, 32, 0, (cudaStream_t)stream>>>(*prm, *wrk, wrk->n_tiles, cfg->batch, do_reduce, do_adam,
-                                                        grad_scale, cfg->learning_rate);
-        ASAC_LAUNCHED("k_alpha_adam");
+        const int threads = cfg->batch >= 1024 ? 1024 : ((cfg->batch + 31) / 32) * 32;
+        k_alpha_td<<<1, threads, 0, (cudaStream_t)stream>>>(*prm, *wrk, wrk->n_tiles, cfg->batch, cfg->ensemble,
+                                                            do_reduce, do_adam, do_td, grad_scale,
+                                                            cfg->learning_rate);
+        ASAC_LAUNCHED("k_alpha_td");
         return ASAC_OK;
     }
     AdamArgs a;
@@ -998,12 +1031,17 @@ extern "C" int asac_sac_adam(const AsacSacConfig *cfg, const AsacSacParams *prm,
 
 extern "C" int asac_sac_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk,
                                     int which, void *stream) {
-    int rc = launch_reduce_adam(cfg, prm, wrk, which, 1, 1, 1.f, stream);
+    int rc = launch_reduce_adam(cfg, prm, wrk, which, 1, 1, 1.f, stream, which == 2 ? 1 : 0);
     if (rc != ASAC_OK) return rc;
     return bump(prm, 1 << (which + 1), stream);
 }
 
 extern "C" int asac_sac_advance_step(const AsacSacParams *prm, void *stream) { return bump(prm, 1, stream); }
+
+extern "C" int asac_sac_td_error(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk,
+                                 void *stream) {
+    return launch_reduce_adam(cfg, prm, wrk, 2, 0, 0, 1.f, stream, 1);
+}
 
 extern "C" int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
                              const AsacSacWork *wrk, void *stream) {
@@ -1023,9 +1061,10 @@ extern "C" int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm,
         ASAC_REQUIRE(bat->eps_td && bat->eps_alpha, "asac_sac_step: missing eps_td / eps_alpha");
         if ((rc = launch_value_pass(a, 1, stream)) != ASAC_OK) return rc;
     }
-    if (cfg->use_auto_alpha) {
-        if ((rc = launch_reduce_adam(cfg, prm, wrk, 2, 1, 1, 1.f, stream)) != ASAC_OK) return rc;
-        mask |= 8;
+    if (cfg->use_auto_alpha || need_post) {
+        const int aa = cfg->use_auto_alpha ? 1 : 0;
+        if ((rc = launch_reduce_adam(cfg, prm, wrk, 2, aa, aa, 1.f, stream, need_post ? 1 : 0)) != ASAC_OK) return rc;
+        if (aa) mask |= 8;
     }
     return bump(prm, mask, stream);
 }

@@ -227,21 +227,24 @@ __global__ void __launch_bounds__(1024) k_per_update(float *nodes, int64_t capac
 __global__ void __launch_bounds__(1024) k_per_add(float *nodes, int64_t capacity, int levels,
                                                   int64_t *store_ids, int64_t first_id, int64_t T,
                                                   int64_t chunk_begin, int chunk_len, const float *max_p,
-                                                  int ignore_size, int check_dups) {
-    __shared__ int s_slot[1024];
+                                                  int ignore_size) {
+    __shared__ int s_slot[1];
     const int t = threadIdx.x;
-    const bool active = t < chunk_len;
+    bool active = t < chunk_len;
     int slot = 0;
     float value = 0.f;
     if (active) {
         const int64_t i = chunk_begin + t;
+        // consecutive ids: row i is overwritten by row i + capacity of the same call (NumPy keeps the
+        // last write), so only the last `capacity` rows of a longer episode survive
+        active = (i + capacity >= T);
         const int64_t id = (first_id + i) % (10 * capacity);
         slot = (int)(id & (capacity - 1));
-        store_ids[slot] = id;
+        if (active) store_ids[slot] = id;
         value = max_p[0];
         if (ignore_size > 0 && (slot >= capacity - ignore_size || i >= T - ignore_size)) value = 0.f;
     }
-    block_tree_apply(nodes, capacity, levels, slot, value, active, check_dups != 0, s_slot);
+    block_tree_apply(nodes, capacity, levels, slot, value, active, false, s_slot);
 }
 
 }  // namespace asac
@@ -330,12 +333,11 @@ extern "C" int asac_per_add(float *nodes, int64_t capacity, int64_t *store_ids, 
     ASAC_REQUIRE(is_pow2(capacity), "asac_per_add: capacity is not a power of two");
     ASAC_REQUIRE(T > 0, "asac_per_add: T <= 0");
     const int levels = tree_levels(capacity);
-    const int check_dups = T > capacity ? 1 : 0;  // an episode longer than the ring overwrites itself
     for (int64_t off = 0; off < T; off += 1024) {
         const int n = (int)((T - off) < 1024 ? (T - off) : 1024);
         const int threads = ((n + 31) / 32) * 32;
         k_per_add<<<1, threads, 0, (cudaStream_t)stream>>>(nodes, capacity, levels, store_ids, first_id, T, off, n,
-                                                           max_p, ignore_size, check_dups);
+                                                           max_p, ignore_size);
         ASAC_LAUNCHED("k_per_add");
     }
     return ASAC_OK;

@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing of the learner (new capability; the reference picks ONE GPU,
+algorithm/sac_base.py:237-243).  One process per GPU, ``torch.distributed`` over NCCL.
+
+* replay: sharded by capacity — rank r owns ``capacity // world`` ring slots with its own
+  segment tree; whole episodes go to one shard (round-robin) so sampled windows never cross
+  shards.  No data-path collective: sampling, gather, priority update and write-back are local.
+* learner: data parallel over the batch with replicated weights.  The only exchange is the
+  gradient: after each of the three backward passes the reduced flat gradient buffer
+  (critics / policy / log-alpha) is all-reduced (SUM) and the Adam kernel applies 1/world.
+
+These helpers are pure host logic and run unchanged on the gloo backend (CPU tests).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_capacity(capacity: int, world_size: int) -> int:
+    """Per-rank ring size: the global capacity rounded down to a power of two
+    (replay_buffer.py:264), split evenly, each shard again a power of two."""
+    total = int(2 ** math.floor(math.log2(capacity)))
+    per = max(total // world_size, 2)
+    return int(2 ** math.floor(math.log2(per)))
+
+
+def episode_owner(episode_counter: int, world_size: int) -> int:
+    """Round-robin shard of the episode_counter-th episode."""
+    return episode_counter % world_size
+
+
+def all_reduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place SUM all-reduce of a flat gradient buffer (a no-op without a process group)."""
+    if world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def broadcast_(tensors: list[torch.Tensor], src: int = 0, group=None) -> None:
+    """Makes every rank start from rank ``src``'s weights / optimizer state."""
+    if world()[1] > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)

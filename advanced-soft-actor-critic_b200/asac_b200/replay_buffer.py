@@ -122,14 +122,18 @@ class PrioritizedReplayBuffer:
         if self._columns is None:
             self._allocate(transitions)
         first_id = self._next_id
+        # an episode longer than the ring overwrites its own head: only the last `capacity` rows
+        # survive (NumPy fancy assignment keeps the last write, replay_buffer.py:48-50)
+        skip = max(0, T - self.capacity)
         for k, v in transitions.items():
-            src = _to_device(v, self.device)
+            src = _to_device(v[skip:] if skip else v, self.device)
             col = self._columns[k]
             if src.dtype != col.dtype or tuple(src.shape[1:]) != tuple(col.shape[1:]):
                 raise ValueError(f'column {k}: got {src.dtype}{tuple(src.shape[1:])}, '
                                  f'stored {col.dtype}{tuple(col.shape[1:])}')
-            check(self._lib.asac_storage_write_rows(ptr(col), self.capacity, first_id, ptr(src), T,
-                                                    self._row_bytes(k), self._stream), 'storage_write_rows')
+            check(self._lib.asac_storage_write_rows(ptr(col), self.capacity, (first_id + skip) % self.max_id,
+                                                    ptr(src), T - skip, self._row_bytes(k), self._stream),
+                  'storage_write_rows')
         return first_id, T
 
     def _advance(self, first_id: int, T: int) -> None:

@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib, lowering
+from . import dist as adist
 from . import nn_models as m
 from ._lib import check, ptr
 from .replay_buffer import PrioritizedReplayBuffer
@@ -235,6 +236,13 @@ class SAC_Base:
             self._init_or_restore(int(last_ckpt) if last_ckpt is not None else None)
         self._graph = None
         self._graph_columns_key = None
+        self._rank, self._world = adist.world()
+        if self._world > 1:
+            # replicated weights: every rank starts from rank 0's networks and optimizer state
+            adist.broadcast_([self._q_flat, self._qt_flat, self._pi_flat, self._log_alpha_buf, self._q_m, self._q_v,
+                              self._pi_m, self._pi_v, self._alpha_m, self._alpha_v, self._counters])
+            self._noise_seed ^= 0x9E3779B97F4A7C15 * (self._rank + 1) & 0x3FFFFFFFFFFFFFFF
+            self.replay_buffer._seed ^= 0xD1B54A32D192ED03 * (self._rank + 1) & 0x3FFFFFFFFFFFFFFF
 
     # ------------------------------------------------------------------ construction
     def _build_model(self, nn, nn_config: dict | None, init_log_alpha: float) -> None:
@@ -398,7 +406,7 @@ class SAC_Base:
             'grad_q': torch.zeros(E, Pq, **f32), 'grad_pi_part': torch.zeros(T, Ppi, **f32),
             'grad_pi': torch.zeros(Ppi, **f32), 'stats_pi': torch.zeros(T, 2, **f32),
             'grad_alpha_part': torch.zeros(T, 2, **f32), 'grad_alpha': torch.zeros(1, **f32),
-            'pi_probs': torch.zeros(B, L - 1, A, **f32), 'y_td': torch.zeros(B, **f32),
+            'pi_probs': torch.zeros(B, L - 1, A, **f32), 'post_parts': torch.zeros(B, 2 + E, **f32), 'y_td': torch.zeros(B, **f32),
             'td_error': torch.zeros(B, **f32),
         }
         work = _lib.AsacSacWork()
@@ -589,7 +597,10 @@ class SAC_Base:
         check(lib.asac_fill_normal(ptr(self._noise), self._noise.numel(), self._noise_seed, ptr(self._counters), 0,
                                    stream), 'fill_normal')
         # 4. _train + get_l_probs + _get_td_error
-        check(lib.asac_sac_step(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), stream), 'sac_step')
+        if self._world == 1:
+            check(lib.asac_sac_step(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), stream), 'sac_step')
+        else:
+            self._enqueue_sac_step_data_parallel(stream)
         # 5. priority update and mu-prob write-back (sac_base.py:2584, 2598-2605)
         if self.use_priority:
             check(lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), ptr(smp['ids']),
@@ -597,6 +608,32 @@ class SAC_Base:
                                       float(rb.alpha), 0, ptr(rb._per_state), stream), 'per_update')
         if self.use_n_step_is:
             rb.write_back(smp['ids'], 'mu_prob', self._wk['pi_probs'], -self.burn_in_step, self._bt['padding_masks'])
+
+    def _enqueue_sac_step_data_parallel(self, stream) -> None:
+        """asac_sac_step with a SUM all-reduce of each reduced gradient buffer between the backward
+        pass and its Adam kernel (grad_scale = 1/world): the only collective of the step."""
+        lib, cfg, prm, batch, work = self._lib, C.byref(self._cfg), C.byref(self._prm), C.byref(self._batch), \
+            C.byref(self._work)
+        scale = 1.0 / self._world
+        check(lib.asac_sac_polyak(cfg, prm, -1.0, stream), 'polyak')
+        check(lib.asac_sac_target_y(cfg, prm, batch, work, stream), 'target_y')
+        check(lib.asac_sac_q_backward(cfg, prm, batch, work, stream), 'q_backward')
+        check(lib.asac_sac_reduce_grads(cfg, work, 0, stream), 'reduce_grads')
+        adist.all_reduce_sum_(self._wk['grad_q'])
+        check(lib.asac_sac_adam(cfg, prm, work, 0, scale, stream), 'adam')
+        check(lib.asac_sac_policy_backward(cfg, prm, batch, work, stream), 'policy_backward')
+        check(lib.asac_sac_reduce_grads(cfg, work, 1, stream), 'reduce_grads')
+        adist.all_reduce_sum_(self._wk['grad_pi'])
+        check(lib.asac_sac_adam(cfg, prm, work, 1, scale, stream), 'adam')
+        if self.use_auto_alpha or self.use_n_step_is or self.use_priority:
+            check(lib.asac_sac_post(cfg, prm, batch, work, stream), 'post')
+        if self.use_auto_alpha:
+            check(lib.asac_sac_reduce_grads(cfg, work, 2, stream), 'reduce_grads')
+            adist.all_reduce_sum_(self._wk['grad_alpha'])
+            check(lib.asac_sac_adam(cfg, prm, work, 2, scale, stream), 'adam')
+        if self.use_auto_alpha or self.use_n_step_is or self.use_priority:
+            check(lib.asac_sac_td_error(cfg, prm, work, stream), 'td_error')
+        check(lib.asac_sac_advance_step(prm, stream), 'advance_step')
 
     def train(self) -> int:
         step = self.get_global_step()
@@ -609,7 +646,7 @@ class SAC_Base:
                 self._specs = self._gather_specs()
                 self._graph, self._graph_columns_key = None, key
                 self._enqueue_step()  # eager warm-up (also sets the kernels' shared-memory attributes)
-            elif not self.use_cuda_graph:
+            elif not self.use_cuda_graph or self._world > 1:  # NCCL collectives stay outside graphs for now
                 self._enqueue_step()
             else:
                 if self._graph is None:

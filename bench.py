@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""Benchmark of the SAC learner step + prioritized replay (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (configs[1] of BASELINE.json): env_type=TEST vector obs (6,), continuous A=2, stock
+envs/test/nn.py nets, SAC + PER (alpha=0.9, capacity=524288, full), batch_size=256,
+ensemble_q_num=2, n_step=1.  One step = one SAC_Base.train(): prioritized sample, window gather,
+the whole update (critics, policy, alpha), td-error, priority update, mu-prob write-back.
+
+Prints ONE JSON line (see the keys in main()).  `value` is train() steps/s with the replay
+resident in HBM, each timed step bracketed by CUDA events with an L2 flush in between;
+`e2e` adds, per step, a put_episode() of host transitions (pinned memory -> H2D) and a D2H
+read of the step's td-errors through the public API.  `--impl reference` times the CPU port of
+the reference's own path (oracle/, NumPy sumtree + torch-CPU update) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / 'advanced-soft-actor-critic_b200')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CFG = dict(obs_shape=(6,), A=2, B=256, n_step=1, burn_in=0, E=2, hidden=64, depth=3, capacity=524288,
+           per_alpha=0.9, episode_len=100)
+METRIC = 'sac_grad_steps_per_sec_batch256'
+UNIT = 'steps/s'
+
+
+# --------------------------------------------------------------------------- synthetic data
+def synth_episode(rng, T, S, A):
+    """tests/get_synthesis_data.py:114-126 of the reference: obs randn, action rand, reward randn,
+    done randint, probs rand (float32), empty hidden state."""
+    return dict(ep_indexes=np.arange(T, dtype=np.int32)[None],
+                ep_obses_list=[rng.randn(1, T, S).astype(np.float32)],
+                ep_actions=rng.rand(1, T, A).astype(np.float32),
+                ep_rewards=rng.randn(1, T).astype(np.float32),
+                ep_dones=rng.randint(0, 2, size=(1, T)).astype(bool),
+                ep_probs=rng.rand(1, T, A).astype(np.float32),
+                ep_pre_seq_hidden_states=np.zeros((1, T, 0), dtype=np.float32))
+
+
+def pin_episode(ep):
+    out = {}
+    for k, v in ep.items():
+        if isinstance(v, list):
+            out[k] = [torch.from_numpy(x).pin_memory().numpy() for x in v]
+        else:
+            out[k] = torch.from_numpy(v).pin_memory().numpy()
+    return out
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v == 'Active'})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------- algorithmic work
+def flops_per_row(S, A, H, d):
+    q = 2 * ((S + A) * H + (d - 1) * H * H + H)
+    pi = 2 * (S * H + (d - 1) * H * H + 2 * H * A)
+    return q, pi
+
+
+def stage_work(cfg):
+    """ALGORITHMIC flops / bytes per launch of each kernel."""
+    S, A, B, n, E, H, d = cfg['obs_shape'][0], cfg['A'], cfg['B'], cfg['n_step'], cfg['E'], cfg['hidden'], cfg['depth']
+    b = cfg['burn_in']
+    L = b + n + 1
+    D = int(np.log2(cfg['capacity']))
+    q, pi = flops_per_row(S, A, H, d)
+    Pq = (S + A) * H + H + (d - 1) * (H * H + H) + H + 1
+    Ppi = S * H + H + (d - 1) * (H * H + H) + 2 * A * H + 2 * A
+    row = 4 + 1 + 4 * S + 4 * A + 4 + 1 + 4 * A
+    return {
+        'per_sample': dict(bound='hbm', bytes=B * (8 * D + 28)),
+        'gather': dict(bound='hbm', bytes=2 * B * L * row),
+        'fill_normal': dict(bound='hbm', bytes=4 * (2 * B * (n + 1) * A + 2 * B * A)),
+        'polyak': dict(bound='hbm', bytes=3 * 4 * E * Pq),
+        'value_pass_train': dict(bound='tensor', flops=pi * B * (n + 1) + E * q * (B * (n + 1) + B)),
+        'q_backward': dict(bound='tensor', flops=3 * E * q * B),
+        'adam_q': dict(bound='hbm', bytes=E * Pq * 4 * 7),
+        'policy_backward': dict(bound='tensor', flops=(3 * pi + 2 * E * q) * B),
+        'adam_pi': dict(bound='hbm', bytes=Ppi * 4 * 7),
+        'value_pass_post': dict(bound='tensor', flops=pi * B * L + E * q * (B * (n + 1) + B)),
+        'adam_alpha': dict(bound='hbm', bytes=64),
+        'per_update': dict(bound='hbm', bytes=B * (12 * D + 16)),
+        'write_back': dict(bound='hbm', bytes=B * (L - 1) * (A * 4 + 8)),
+    }
+
+
+# --------------------------------------------------------------------------- GPU arm
+def build_learner(device, seed, capacity, fill):
+    import types
+    import asac_b200.nn_models as m
+    from asac_b200 import SAC_Base
+    nn = types.SimpleNamespace(ModelRep=m.ModelSimpleRep, ModelQ=m.ModelQ, ModelPolicy=m.ModelPolicy)
+    sac = SAC_Base(obs_names=['vector'], obs_shapes=[CFG['obs_shape']], d_action_sizes=[], c_action_size=CFG['A'],
+                   model_abs_dir=None, nn=nn, device=device, seed=seed, batch_size=CFG['B'], n_step=CFG['n_step'],
+                   burn_in_step=CFG['burn_in'], ensemble_q_num=CFG['E'], ensemble_q_sample=CFG['E'],
+                   use_priority=True, replay_config={'capacity': capacity, 'alpha': CFG['per_alpha']})
+    rng = np.random.RandomState(seed)
+    S, A, T = CFG['obs_shape'][0], CFG['A'], CFG['episode_len']
+    while sac.replay_buffer.size < fill:
+        sac.put_episode(**synth_episode(rng, T, S, A))
+    torch.cuda.synchronize()
+    return sac, rng
+
+
+def profile_stages(sac, steps):
+    """Average device time of every kernel of the step: eager launches, one CUDA-event pair around
+    each C-ABI call on the launching stream."""
+    import ctypes as C
+    from asac_b200 import _lib
+    from asac_b200._lib import check, ptr
+    lib, rb = sac._lib, sac.replay_buffer
+    cfg, prm, batch, work = C.byref(sac._cfg), C.byref(sac._prm), C.byref(sac._batch), C.byref(sac._work)
+    smp, B = sac._smp, sac.batch_size
+    s = lambda: _lib.current_stream()
+    stages = [
+        ('per_sample', lambda: check(lib.asac_per_sample(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), B, None,
+                                                         rb._seed, ptr(rb._draw_counter), ptr(rb._per_state),
+                                                         ptr(smp['slots']), ptr(smp['ids']), ptr(smp['p']),
+                                                         ptr(smp['w']), s()))),
+        ('gather', lambda: rb._gather(smp['ids'], sac._specs, sac._padding_action, sac._bt['padding_masks'])),
+        ('fill_normal', lambda: check(lib.asac_fill_normal(ptr(sac._noise), sac._noise.numel(), sac._noise_seed,
+                                                           ptr(sac._counters), 0, s()))),
+        ('polyak', lambda: check(lib.asac_sac_polyak(cfg, prm, -1.0, s()))),
+        ('value_pass_train', lambda: check(lib.asac_sac_target_y(cfg, prm, batch, work, s()))),
+        ('q_backward', lambda: check(lib.asac_sac_q_backward(cfg, prm, batch, work, s()))),
+        ('adam_q', lambda: check(lib.asac_sac_reduce_adam(cfg, prm, work, 0, s()))),
+        ('policy_backward', lambda: check(lib.asac_sac_policy_backward(cfg, prm, batch, work, s()))),
+        ('adam_pi', lambda: check(lib.asac_sac_reduce_adam(cfg, prm, work, 1, s()))),
+        ('value_pass_post', lambda: check(lib.asac_sac_post(cfg, prm, batch, work, s()))),
+        ('adam_alpha', lambda: check(lib.asac_sac_reduce_adam(cfg, prm, work, 2, s()))),
+        ('per_update', lambda: check(lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids),
+                                                         ptr(smp['ids']), ptr(sac._wk['td_error']), B,
+                                                         float(rb.td_error_min), float(rb.td_error_max),
+                                                         float(rb.alpha), 0, ptr(rb._per_state), s()))),
+        ('write_back', lambda: rb.write_back(smp['ids'], 'mu_prob', sac._wk['pi_probs'], -sac.burn_in_step,
+                                             sac._bt['padding_masks'])),
+    ]
+    total = {name: 0.0 for name, _ in stages}
+    for it in range(steps + 3):
+        evs = []
+        for name, fn in stages:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((name, e0, e1))
+        check(lib.asac_sac_advance_step(C.byref(sac._prm), s()))
+        torch.cuda.synchronize()
+        if it >= 3:
+            for name, e0, e1 in evs:
+                total[name] += e0.elapsed_time(e1) * 1e3  # us
+    return {k: v / steps for k, v in total.items()}
+
+
+def run_gpu(args):
+    from asac_b200 import _lib
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    torch.cuda.set_device(local_rank)
+    device = f'cuda:{local_rank}'
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=torch.device(device))
+    from asac_b200 import dist as adist
+    capacity = adist.shard_capacity(CFG['capacity'], world) if world > 1 else CFG['capacity']
+    lib = _lib.load()
+
+    t_fill = time.perf_counter()
+    sac, rng = build_learner(device, seed=1 + rank, capacity=capacity, fill=capacity)
+    t_fill = time.perf_counter() - t_fill
+    S, A = CFG['obs_shape'][0], CFG['A']
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    # ---- warm-up (first call eager, second captures the CUDA graph)
+    for _ in range(max(args.warmup, 3)):
+        sac.train()
+    barrier()
+
+    lib.asac_reset_launch_count()
+    sac._enqueue_step() if world == 1 else None
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.asac_launch_count()) if world == 1 else 0
+    if world == 1:
+        sac.increase_global_step()
+
+    # ---- timed: K steps, one CUDA-event pair per step, L2 flushed between steps
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    events = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sac.train()
+        e1.record()
+        events.append((e0, e1))
+    barrier()
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in events]
+    total_ms = float(np.sum(step_ms))
+
+    # ---- the same K steps back to back with a warm L2 (steady state of a running learner)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sac.train()
+    e1.record()
+    barrier()
+    warm_ms = e0.elapsed_time(e1)
+    clock_info = clocks.stop()
+
+    # ---- end to end through the public API: host transitions in, td-errors out, every step
+    T_in = 8
+    eps = [pin_episode(synth_episode(rng, T_in, S, A)) for _ in range(32)]
+    h2d = sum(v.nbytes for k, v in eps[0].items() if not isinstance(v, list)) + sum(x.nbytes for x in eps[0]['ep_obses_list'])
+    h2d += T_in  # the derived last_mask column
+    td_host = torch.empty(CFG['B'], dtype=torch.float32).pin_memory()
+    for i in range(5):
+        sac.put_episode(**eps[i % 32]); sac.train(); td_host.copy_(sac._wk['td_error']); torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        sac.put_episode(**eps[i % 32])
+        sac.train()
+        td_host.copy_(sac._wk['td_error'], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        _ = float(td_host[0])
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, warm_ms, e2e_ms], device=device, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        total_ms, warm_ms, e2e_ms = [float(x) for x in t.tolist()]
+
+    units_per_step = world  # each rank processes one batch-256 update per step (weak scaling)
+    value = units_per_step * args.steps / (total_ms * 1e-3)
+    out = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'TEST vector-obs(6,) A=2 SAC+PER alpha=0.9 capacity=524288 (full) batch=256 '
+                               'ensemble_q=2 n_step=1, stock envs/test/nn.py nets (H=64, depth 3)',
+                   'global_batch': CFG['B'] * world, 'replay_capacity_per_gpu': capacity,
+                   'parallelism': f'dp{world}' if world > 1 else 'single',
+                   'l2': 'flushed between timed steps (256 MiB memset, outside the event pairs)',
+                   'cuda_graph': bool(sac._graph is not None),
+                   'value_definition': 'batch-256 gradient steps per second summed over ranks'},
+        'value_warm_l2': units_per_step * args.steps / (warm_ms * 1e-3),
+        'e2e': {'value': units_per_step * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(td_host.numel() * 4),
+                'what': f'put_episode({T_in} host transitions, pinned) + train() + D2H of td_error[256], per step'},
+        'gpu_launches': launches_per_step * args.steps,
+        'launches_per_step': launches_per_step,
+        'clocks': clock_info,
+        'fill_seconds': round(t_fill, 2),
+    }
+
+    if rank == 0 and world == 1:
+        prof = profile_stages(sac, steps=200)
+        work = stage_work(CFG)
+        peaks = {}
+        pk = ROOT / 'MEASURED_PEAKS.json'
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        tf_peak = float(peaks.get('bf16_tflops', 1590.0))
+        src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
+        kernels = {}
+        for name, us in prof.items():
+            w = work[name]
+            if w['bound'] == 'hbm':
+                ach = w['bytes'] / (us * 1e-6) / 1e9
+                kernels[name] = {'us': round(us, 3), 'bound': 'hbm', 'algorithmic_bytes': w['bytes'],
+                                 'achieved_GBps': round(ach, 3), 'frac': ach / hbm_peak}
+            else:
+                ach = w['flops'] / (us * 1e-6) / 1e12
+                kernels[name] = {'us': round(us, 3), 'bound': 'tensor', 'algorithmic_flops': w['flops'],
+                                 'achieved_TFLOPs': round(ach, 5), 'frac': ach / tf_peak}
+        top = max(prof, key=prof.get)
+        k = kernels[top]
+        out['roofline'] = {'kernel': top, 'bound': k['bound'],
+                           'achieved': k.get('achieved_GBps', k.get('achieved_TFLOPs')),
+                           'peak': hbm_peak if k['bound'] == 'hbm' else tf_peak,
+                           'unit': 'GB/s' if k['bound'] == 'hbm' else 'TFLOP/s', 'frac': k['frac'], 'traffic': None,
+                           'peak_source': src, 'share_of_step': prof[top] / sum(prof.values()),
+                           'note': 'fp32 FFMA row-tile kernel, latency-bound at B=256 (DESIGN.md §6)'}
+        per_us = prof['per_sample'] + prof['per_update']
+        per_bytes = work['per_sample']['bytes'] + work['per_update']['bytes']
+        out['per_sample_update'] = {'us': round(per_us, 3), 'algorithmic_bytes': per_bytes,
+                                    'achieved_GBps': per_bytes / (per_us * 1e-6) / 1e9,
+                                    'frac_of_hbm_peak': per_bytes / (per_us * 1e-6) / 1e9 / hbm_peak,
+                                    'dependent_levels': int(np.log2(capacity))}
+        out['kernels'] = kernels
+        out['cpu_baseline'] = cpu_port_baseline(budget_s=args.cpu_seconds)
+    sac.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_port_setup(seed=0):
+    from oracle.replay_oracle import PerOracle
+    from oracle.sac_oracle import SacHyper, SacOracle
+    S, A, B = CFG['obs_shape'][0], CFG['A'], CFG['B']
+    rng = np.random.RandomState(seed)
+    per = PerOracle(batch_size=B, sample_prev_n=CFG['burn_in'], sample_post_n=CFG['n_step'],
+                    capacity=CFG['capacity'], alpha=CFG['per_alpha'])
+    per.vectorized = True
+    C = per.capacity
+    T = CFG['episode_len']
+    # bulk fill (equivalent to C/T add() calls followed by priority updates): full ring, priorities from
+    # |N(0,1)| td errors, episode tails at zero priority (replay_buffer.py:303-306)
+    index = (np.arange(C) % T).astype(np.int32)
+    per.store.columns = {
+        '_id': np.arange(C, dtype=np.int64), 'index': index, 'last_mask': index == T - 1,
+        'obs_vector': rng.randn(C, S).astype(np.float32), 'action': rng.rand(C, A).astype(np.float32),
+        'reward': rng.randn(C).astype(np.float32), 'done': rng.randint(0, 2, size=C).astype(bool),
+        'mu_prob': rng.rand(C, A).astype(np.float32),
+        'pre_seq_hidden_state': np.zeros((C, 0), dtype=np.float32)}
+    per.store.size, per.store.next_id = C, C
+    leaves = np.power(np.clip(np.abs(rng.randn(C)).astype(np.float32), 0.01, 1.0), np.float32(CFG['per_alpha']))
+    leaves[index == T - 1] = 0
+    per.tree.nodes[C - 1:] = leaves
+    per.tree.rebuild()
+    hp = SacHyper(state_size=S, action_size=A, ensemble_q_num=CFG['E'], hidden=CFG['hidden'], q_depth=CFG['depth'],
+                  policy_depth=CFG['depth'], burn_in_step=CFG['burn_in'], n_step=CFG['n_step'])
+    return per, SacOracle(hp, seed=seed), rng
+
+
+def cpu_port_step(per, sac, rng):
+    """One SAC_Base.train() of the reference restated on the CPU (sac_base.py:2496-2609)."""
+    from oracle.replay_oracle import pad_sampled_batch
+    from oracle.sac_oracle import SacBatch, SacNoise
+    B, A, n, b = CFG['B'], CFG['A'], CFG['n_step'], CFG['burn_in']
+    data_ids, batch, weights, _ = per.sample(rng.random_sample(B))
+    batch = pad_sampled_batch(batch, b, np.zeros(A, dtype=np.float32))
+    t = torch.from_numpy
+    sb = SacBatch(states=t(batch['obs_vector']), actions=t(batch['action'][:, :-1]), rewards=t(batch['reward'][:, :-1]),
+                  dones=t(batch['done'][:, :-1]), mu_probs=t(batch['mu_prob'][:, :-1]),
+                  last_masks=t(batch['last_mask'][:, :-1]), padding_masks=t(batch['padding_mask'][:, :-1]),
+                  priority_is=t(weights))
+    noise = SacNoise(eps_y=torch.randn(B, n + 1, A), eps_pi=torch.randn(B, A), eps_alpha=torch.randn(B, A),
+                     eps_td=torch.randn(B, n + 1, A))
+    out = sac.step(sb, noise)
+    per.update(data_ids, out['td_error'].numpy())
+    pad = batch['padding_mask'][:, :-1].reshape(-1)
+    ptrs = (data_ids[:, None] + np.arange(-b, n)[None, :]).reshape(-1)
+    per.update_transitions(ptrs[~pad], 'mu_prob', out['pi_probs'].numpy().reshape(-1, A)[~pad])
+
+
+def cpu_port_baseline(budget_s=12.0, steps=None, warmup=5):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    per, sac, rng = cpu_port_setup()
+    for _ in range(warmup):
+        cpu_port_step(per, sac, rng)
+    t0, done = time.perf_counter(), 0
+    while True:
+        cpu_port_step(per, sac, rng)
+        done += 1
+        if (steps is not None and done >= steps) or (steps is None and time.perf_counter() - t0 >= budget_s):
+            break
+    dt = time.perf_counter() - t0
+    return {'value': done / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': f'{done} train() steps of the same workload (B=256, capacity 524288 full) in {dt:.1f} s: '
+                      f'NumPy sumtree + torch-CPU fp32 update (oracle/), {threads} torch threads',
+            'ms_per_step': dt / done * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    base = cpu_port_baseline(steps=args.steps, warmup=max(args.warmup, 3))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    out = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': world,
+           'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': base['ms_per_step'], 'higher_is_better': True,
+           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': 'TEST vector-obs(6,) A=2 SAC+PER alpha=0.9 capacity=524288 (full) batch=256 '
+                                  'ensemble_q=2 n_step=1, stock envs/test/nn.py nets (H=64, depth 3)',
+                      'note': 'CPU port of the reference path (oracle/); the Python reference itself cannot travel '
+                              'to the GPU box'},
+           'cpu_baseline': base,
+           'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        args.steps = 300 if args.steps is None else min(args.steps, 2000)
+        args.warmup = 5 if args.warmup is None else args.warmup
+        run_reference(args)
+    else:
+        args.steps = 2000 if args.steps is None else args.steps
+        args.warmup = 20 if args.warmup is None else args.warmup
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -228,6 +228,7 @@ typedef struct {
     float *grad_alpha_part; /* [n_tiles, 2] per-tile sums: d loss/d log_alpha, alpha loss */
     float *grad_alpha;    /* [1]                                                        */
     float *pi_probs;      /* [B, L-1, A] get_l_probs output                             */
+    float *post_parts;    /* [B, 2+E]  post pass: y' critic part, y' log-prob part, Q_i(s_b,a_b) */
     float *y_td;          /* [B]       _get_y inside _get_td_error                      */
     float *td_error;      /* [B]                                                        */
 } AsacSacWork;
@@ -258,9 +259,11 @@ int asac_sac_q_backward(const AsacSacConfig *cfg, const AsacSacParams *prm, cons
 int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacParams *prm,
                              const AsacSacBatch *batch, const AsacSacWork *work, void *stream);
 
-/* _train_alpha's loss (sac_base.py:1930-1945), get_l_probs (:1159-1189) and _get_td_error
- * (:2182-2245) in one pass over the updated nets -> work.grad_alpha_part, work.pi_probs,
- * work.y_td, work.td_error */
+/* _train_alpha's loss (sac_base.py:1930-1945), get_l_probs (:1159-1189) and the network part of
+ * _get_td_error (:2182-2245) in one pass over the updated critics / policy ->
+ * work.grad_alpha_part, work.pi_probs, work.post_parts.  y' = _get_y is linear in alpha; because
+ * the reference evaluates it AFTER the alpha step (:2115-2116 precede :2571) the two linear
+ * parts are stored and asac_sac_td_error combines them. */
 int asac_sac_post(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
                   const AsacSacWork *work, void *stream);
 
@@ -277,6 +280,12 @@ int asac_sac_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const Asac
 /* fused single-GPU variant: reduce + Adam in one kernel */
 int asac_sac_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *work,
                          int which, void *stream);
+
+/* _get_td_error's tail (sac_base.py:2223-2245) with the current log_alpha:
+ * work.y_td = parts[0] - alpha * parts[1], work.td_error = mean_i |Q_i - y_td|.  (asac_sac_step and
+ * asac_sac_reduce_adam(which=2) run it in the same kernel as the alpha Adam step.) */
+int asac_sac_td_error(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *work,
+                      void *stream);
 
 /* increase_global_step (sac_base.py:2607): counters[0] += 1 */
 int asac_sac_advance_step(const AsacSacParams *prm, void *stream);

@@ -182,6 +182,10 @@ class SacBatch:
     padding_masks: torch.Tensor   # [B, L-1] bool
     priority_is: torch.Tensor | None = None  # [B, 1]
 
+    def to(self, dtype: torch.dtype) -> 'SacBatch':
+        f = lambda t: None if t is None else (t.to(dtype) if t.is_floating_point() else t)
+        return SacBatch(**{k: f(getattr(self, k)) for k in self.__dataclass_fields__})
+
 
 @dataclass
 class SacNoise:
@@ -190,10 +194,17 @@ class SacNoise:
     eps_alpha: torch.Tensor   # [B, A]       sample  in _train_alpha      (:1932)
     eps_td: torch.Tensor      # [B, n+1, A]  rsample in _get_td_error's _get_y (:2223)
 
+    def to(self, dtype: torch.dtype) -> 'SacNoise':
+        return SacNoise(**{k: getattr(self, k).to(dtype) for k in self.__dataclass_fields__})
+
 
 class SacOracle:
-    def __init__(self, hp: SacHyper, seed: int = 0):
+    def __init__(self, hp: SacHyper, seed: int = 0, dtype: torch.dtype = torch.float32):
+        """dtype=float64 evaluates the same formulas in double precision: used by the GPU tests to
+        measure how much of a difference is the REFERENCE's own fp32 rounding (ill-conditioned rows,
+        e.g. Normal.log_prob(rsample) with a tiny scale) rather than an error of the kernels."""
         self.hp = hp
+        self.dtype = dtype
         gen = torch.Generator().manual_seed(seed)
         S, A, H = hp.state_size, hp.action_size, hp.hidden
         self.q = [init_q(S, A, H, hp.q_depth, gen) for _ in range(hp.ensemble_q_num)]
@@ -201,6 +212,10 @@ class SacOracle:
         self.policy = init_policy(S, A, H, hp.policy_depth, gen)
         self.log_c_alpha = torch.tensor(hp.init_log_alpha, dtype=torch.float32)
         self.global_step = 0
+        if dtype != torch.float32:
+            cast = lambda d: {k: v.to(dtype) for k, v in d.items()}
+            self.q, self.q_target = [cast(x) for x in self.q], [cast(x) for x in self.q_target]
+            self.policy, self.log_c_alpha = cast(self.policy), self.log_c_alpha.to(dtype)
         self._wire()
         self.polyak(1.)  # fresh start: hard copy (sac_base.py:629)
 
@@ -216,16 +231,21 @@ class SacOracle:
         # receives a grad in continuous-only runs, so Adam skips it (sac_base.py:472,1946-1948)
         self.opt_alpha = torch.optim.Adam([self.log_c_alpha], lr=hp.learning_rate)
         n = hp.n_step
-        self.gamma_ratio = torch.logspace(0, n - 1, n, hp.gamma)      # sac_base.py:285
-        self.lambda_ratio = torch.logspace(0, n - 1, n, hp.v_lambda)  # :286
+        self.gamma_ratio = torch.logspace(0, n - 1, n, hp.gamma).to(self.dtype)      # sac_base.py:285
+        self.lambda_ratio = torch.logspace(0, n - 1, n, hp.v_lambda).to(self.dtype)  # :286
 
     def load_params(self, q, q_target, policy, log_c_alpha):
-        to_t = lambda d: {k: torch.as_tensor(v, dtype=torch.float32).clone() for k, v in d.items()}
+        to_t = lambda d: {k: torch.as_tensor(v).detach().to(self.dtype).clone() for k, v in d.items()}
         self.q = [to_t(x) for x in q]
         self.q_target = [to_t(x) for x in q_target]
         self.policy = to_t(policy)
-        self.log_c_alpha = torch.tensor(float(log_c_alpha), dtype=torch.float32)
+        self.log_c_alpha = torch.as_tensor(log_c_alpha).detach().to(self.dtype).reshape(()).clone()
         self._wire()
+
+    def copy_state_from(self, other: 'SacOracle') -> None:
+        """Parameters and step counter of ``other`` (cast to this oracle's dtype); fresh Adam state."""
+        self.load_params(other.q, other.q_target, other.policy, other.log_c_alpha)
+        self.global_step = other.global_step
 
     # ---- sac_base.py:745-764
     @torch.no_grad()
@@ -245,7 +265,7 @@ class SacOracle:
             ratio = pi_probs / mu_probs.clamp(min=1e-8)
             rho = torch.minimum(ratio, torch.tensor(hp.v_rho))
             c = torch.minimum(ratio, torch.tensor(hp.v_c))
-            c = torch.cat([torch.ones((ratio.shape[0], 1)), c[..., :-1]], dim=-1)
+            c = torch.cat([torch.ones((ratio.shape[0], 1), dtype=ratio.dtype), c[..., :-1]], dim=-1)
             c = torch.cumprod(c, dim=1)
             td = c * rho * td
         td = td * ~(torch.logical_or(last_masks, padding_masks))

@@ -73,6 +73,7 @@ class SacCuda:
             'grad_pi_part': torch.zeros(T, Ppi, **f32), 'grad_pi': torch.zeros(Ppi, **f32),
             'stats_pi': torch.zeros(T, 2, **f32), 'grad_alpha_part': torch.zeros(T, 2, **f32),
             'grad_alpha': torch.zeros(1, **f32), 'pi_probs': torch.zeros(batch_size, L - 1, A, **f32),
+            'post_parts': torch.zeros(batch_size, 2 + E, **f32),
             'y_td': torch.zeros(batch_size, **f32), 'td_error': torch.zeros(batch_size, **f32),
         }
         work = _lib.AsacSacWork()
@@ -90,6 +91,50 @@ class SacCuda:
             self.qt[i].copy_(lowering.flat_from_state_dict(self.q_shape, sd, policy=False))
         self.pi.copy_(lowering.flat_from_state_dict(self.pi_shape, policy, policy=True))
         self.log_alpha.fill_(float(log_c_alpha))
+
+    def sync_from_oracle(self, oracle, what=('q', 'qt', 'pi', 'alpha')) -> None:
+        """Copies the oracle's parameters AND torch.optim.Adam state (exp_avg, exp_avg_sq, step) into
+        the CUDA buffers, so that a stage can be compared from an identical starting point."""
+        def moments(opt, params: dict, key: str):
+            out = {}
+            for name, p in params.items():
+                st = opt.state.get(p, {})
+                out[name] = st[key].detach() if key in st else torch.zeros_like(p)
+            return out
+
+        def steps(opt, params: dict) -> int:
+            vals = {int(float(opt.state[p]['step'])) for p in params.values() if p in opt.state}
+            assert len(vals) <= 1
+            return vals.pop() if vals else 0
+
+        E = self.hp.ensemble_q_num
+        if 'q' in what:
+            for i in range(E):
+                det = {k: v.detach() for k, v in oracle.q[i].items()}
+                self.q[i].copy_(lowering.flat_from_state_dict(self.q_shape, det, False))
+                self.q_m[i].copy_(lowering.flat_from_state_dict(self.q_shape, moments(oracle.opt_q[i], oracle.q[i], 'exp_avg'), False))
+                self.q_v[i].copy_(lowering.flat_from_state_dict(self.q_shape, moments(oracle.opt_q[i], oracle.q[i], 'exp_avg_sq'), False))
+            self.counters[1] = steps(oracle.opt_q[0], oracle.q[0])
+        if 'qt' in what:
+            for i in range(E):
+                self.qt[i].copy_(lowering.flat_from_state_dict(self.q_shape, oracle.q_target[i], False))
+        if 'pi' in what:
+            det = {k: v.detach() for k, v in oracle.policy.items()}
+            self.pi.copy_(lowering.flat_from_state_dict(self.pi_shape, det, True))
+            self.pi_m.copy_(lowering.flat_from_state_dict(self.pi_shape, moments(oracle.opt_policy, oracle.policy, 'exp_avg'), True))
+            self.pi_v.copy_(lowering.flat_from_state_dict(self.pi_shape, moments(oracle.opt_policy, oracle.policy, 'exp_avg_sq'), True))
+            self.counters[2] = steps(oracle.opt_policy, oracle.policy)
+        if 'alpha' in what:
+            self.log_alpha.fill_(float(oracle.log_c_alpha.detach()))
+            st = oracle.opt_alpha.state.get(oracle.log_c_alpha, {})
+            self.alpha_m.fill_(float(st['exp_avg']) if 'exp_avg' in st else 0.)
+            self.alpha_v.fill_(float(st['exp_avg_sq']) if 'exp_avg_sq' in st else 0.)
+            self.counters[3] = int(float(st['step'])) if 'step' in st else 0
+        self.counters[0] = oracle.global_step
+
+    def td_error(self):
+        check(self.lib.asac_sac_td_error(C.byref(self.cfg), C.byref(self.prm), C.byref(self.work), self._s()),
+              'td_error')
 
     def snapshot(self) -> dict:
         d = {}
@@ -190,16 +235,19 @@ class SacCuda:
         out['loss_policy'] = float(self.wk['stats_pi'][:, 0].sum().item()) / self.B
         out['entropy'] = float(self.wk['stats_pi'][:, 1].sum().item()) / self.B
         self.adam(1)
-        if hp.use_auto_alpha or hp.use_n_step_is or hp.use_priority:
+        need_post = hp.use_auto_alpha or hp.use_n_step_is or hp.use_priority
+        if need_post:
             self.post(batch)
             if hp.use_n_step_is:
                 out['pi_probs'] = self.wk['pi_probs'].cpu().numpy()
-            if hp.use_priority:
-                out['td_error'] = self.wk['td_error'].cpu().numpy()
-                out['y_td'] = self.wk['y_td'].cpu().numpy()
         if hp.use_auto_alpha:
             self.reduce_grads(2)
             out['grad_log_alpha'] = self.wk['grad_alpha'].cpu().numpy()
             self.adam(2)
+        if need_post:  # _get_td_error sees the updated alpha (sac_base.py:2115-2116 precede :2571)
+            check(self.lib.asac_sac_td_error(C.byref(self.cfg), C.byref(self.prm), C.byref(self.work), self._s()),
+                  'td_error')
+            out['td_error'] = self.wk['td_error'].cpu().numpy()
+            out['y_td'] = self.wk['y_td'].cpu().numpy()
         self.advance()
         return out

@@ -44,9 +44,32 @@ def test_replay_trace_bit_exact(name):
         assert np.max(np.abs(w.view(np.int32) - w_ref.view(np.int32))) <= 1, 'IS weights differ by more than 1 ulp'
         for k in EP_KEYS:
             assert np.array_equal(_np(batch[k]), g[f'r{r}.batch.{k}']), k
+        # priority update.  NumPy evaluates clip(td)^alpha with a SIMD fp32 powf whose results are not
+        # correctly rounded; the kernel evaluates in float64 and rounds once.  Priorities therefore
+        # agree to an fp32 ulp or two (north star: priorities within 1e-5), not bit-for-bit:
+        # (1) with the reference's own priorities injected the whole tree is bit-exact,
+        # (2) with td errors the leaves agree within 4 ulp and every parent is exactly fp32(l + r).
+        ref = g[f'r{r}.tree_after_update']
+        saved = rb._nodes.clone()
+        upd = g[f'r{r}.upd_ids'].astype(np.int64)
+        p_ref = torch.from_numpy(ref[capacity - 1:][upd % capacity].copy()).cuda()
+        t_ids = torch.from_numpy(upd).cuda()
+        assert lib.asac_per_update(rb._nodes.data_ptr(), capacity, rb._store_ids.data_ptr(), t_ids.data_ptr(),
+                                   p_ref.data_ptr(), len(upd), 0.01, 1.0, float(g['alpha']), 1,
+                                   rb._per_state.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+        tree = _np(rb.tree_nodes())
+        assert np.array_equal(tree, ref), f'round {r}: {np.sum(tree != ref)} nodes differ (injected priorities)'
+        rb._nodes.copy_(saved)
         rb.update(g[f'r{r}.upd_ids'], g[f'r{r}.td'])
-        tree, ref = _np(rb.tree_nodes()), g[f'r{r}.tree_after_update']
-        assert np.array_equal(tree, ref), f'round {r}: {np.sum(tree != ref)} nodes differ after update'
+        tree = _np(rb.tree_nodes())
+        leaves, leaves_ref = tree[capacity - 1:], ref[capacity - 1:]
+        ulps = np.abs(leaves.view(np.int32).astype(np.int64) - leaves_ref.view(np.int32).astype(np.int64))
+        assert ulps.max() <= 4, f'round {r}: priorities differ by {ulps.max()} ulp'
+        assert np.max(np.abs(leaves - leaves_ref)) <= 1e-5
+        heap = np.concatenate([[0.], tree]).astype(np.float32)  # 1-based
+        parents = np.arange(1, capacity)
+        assert np.array_equal(heap[parents], heap[2 * parents] + heap[2 * parents + 1]), 'parent != fp32(l + r)'
+        rb._nodes[1:].copy_(torch.from_numpy(ref).cuda())  # continue from the reference's exact state
         rb.update_transitions(g[f'r{r}.upd_ids'], 'mu_prob', g[f'r{r}.new_mu'])
         assert np.array_equal(_np(rb._columns['mu_prob']), g[f'r{r}.mu_after'])
         rb.add({k: g[f'r{r}.ep.{k}'] for k in EP_KEYS}, ignore_size=1)
@@ -105,6 +128,7 @@ def test_tree_full_capacity_against_oracle():
     assert lib.asac_tree_sample(nodes.data_ptr(), C, B, None, 77, counter.data_ptr(), slot.data_ptr(),
                                 pr.data_ptr(), s) == 0
     sl = _np(slot).astype(np.int64)
+    leaves = oracle.leaves().copy()
     assert (_np(pr) > 0).all() and np.array_equal(_np(pr), leaves[sl])
     cum = np.cumsum(leaves.astype(np.float64))
     seg = float(oracle.total) / B
@@ -179,8 +203,11 @@ def test_write_back_skips_padding_and_stale_ids():
     ref = _np(rb._columns['mu_prob']).copy()
     store = _np(rb._store_ids)
     ids = np.array([30, 40, 89, 10, 88, 27, 63, 64], dtype=np.int64)
-    rows = rng.rand(B, b + n, A).astype(np.float32)
+    # overlapping windows write the same value to the same row (as pi_probs of one stored action do)
+    wids = ids[:, None] - b + np.arange(b + n)[None, :]
+    rows = (np.sin(wids[..., None] * 0.37 + np.arange(A)[None, None, :]) * 0.5 + 0.5).astype(np.float32)
     pad = rng.rand(B, b + n + 1) < 0.3
+    pad[ids == 63] = False; pad[ids == 64] = False  # make the overlap observable
     rb.write_back(torch.from_numpy(ids).cuda(), 'mu_prob', torch.from_numpy(rows).cuda(), -b,
                   torch.from_numpy(pad.astype(np.uint8)).cuda())
     for i in range(B):

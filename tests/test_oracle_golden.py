@@ -103,3 +103,16 @@ def test_sac_oracle_matches_reference(name):
         snap = oracle.snapshot()
         for k, v in snap.items():
             assert rel_err(v, g[f'{pre}after.{k}']) < 1e-5, (s, k)
+
+
+def test_vectorized_descent_equals_scalar():
+    rng = np.random.RandomState(5)
+    t = SumTreeOracle(1024)
+    leaves = rng.rand(1024).astype(np.float32)
+    leaves[rng.rand(1024) < 0.3] = 0
+    t.nodes[1023:] = leaves
+    t.rebuild()
+    v = t.draw(512, rng.random_sample(512))
+    a, pa = t.descend(v)
+    b, pb = t.descend_vectorized(v)
+    assert np.array_equal(a, b) and np.array_equal(pa, pb)
