@@ -103,6 +103,18 @@ __global__ void k_storage_scatter(uint8_t *ring, int64_t capacity, const int64_t
     const int64_t id = data_ids[b] + first_offset + t;
     const int64_t slot = id & (capacity - 1);
     if (store_ids[slot] != id) return;  // replay_buffer.py:431-434
+    // Duplicate targets: NumPy's fancy assignment keeps the LAST write in flat (b, t) order
+    // (pointers are stacked on axis 1 and flattened, sac_base.py:2590-2591, 2600-2601).  A row
+    // yields when a later, unpadded (b', t') aims at the same id: data_ids[b'] + t' == data_ids[b] + t.
+    bool loses = false;
+    for (int b2 = b + lane; b2 < batch; b2 += 32) {
+        const int64_t t2 = data_ids[b] + t - data_ids[b2];
+        if (t2 < 0 || t2 >= n_rows) continue;
+        if (b2 == b && t2 <= t) continue;
+        if (padding_mask && padding_mask[b2 * mask_b_stride + t2]) continue;
+        loses = true;
+    }
+    if (__any_sync(0xffffffffu, loses)) return;
     lane_copy(ring + slot * row_bytes, rows + (b * rows_b_stride + t) * row_bytes, row_bytes, lane, 32);
 }
 

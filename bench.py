@@ -243,6 +243,7 @@ def run_gpu(args):
     clocks = ClockSampler(local_rank)
     clocks.start()
     barrier()
+    torch.cuda.profiler.start()  # `ncu --profile-from-start off` captures exactly the timed steps
     events = []
     for _ in range(args.steps):
         flush.zero_()
@@ -252,6 +253,7 @@ def run_gpu(args):
         e1.record()
         events.append((e0, e1))
     barrier()
+    torch.cuda.profiler.stop()
     step_ms = [e0.elapsed_time(e1) for e0, e1 in events]
     total_ms = float(np.sum(step_ms))
 
