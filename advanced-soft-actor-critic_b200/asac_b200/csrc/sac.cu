@@ -6,10 +6,13 @@
 // stock-network case (algorithm/sac_base.py:745-764, 1159-1189, 1244-1466, 1468-1605,
 // 1841-1949, 2027-2126, 2182-2245).  Exact formulas and the reference quirks that are
 // reproduced on purpose are listed in DESIGN.md §5.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
 #include "mlp_tile.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace asac {
 
@@ -113,7 +116,7 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
     int o = 0;
     p.off_px = o; o += (d + 1) * rows * p.lda;
     p.off_pz = o; o += d * rows * p.lda;
-    p.off_qz = o; o += policy ? c.ensemble * c.q_depth * rows * p.lda : 0;
+    p.off_qz = o; o += policy ? c.q_depth * rows * p.lda : 0;  // this CTA's critic only (cluster of E CTAs)
     p.off_qin = o; o += policy ? rows * p.lda : 0;
     p.off_g0 = o; o += rows * p.lda;
     p.off_g1 = o; o += rows * p.lda;
@@ -132,7 +135,12 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
 // mode 1: after the three Adam steps — alpha-loss terms (:1930-1945), pi_probs = get_l_probs
 //         (:1159-1189), y' = _get_y with mu := pi_probs and td = mean_i |Q_i(s_b,a_b) - y'|
 //         (:2182-2245).
+// grid (n_tiles, E), thread-block cluster (1, E, 1): the E CTAs of a batch tile each run the
+// policy (duplicated, it is the cheap part) and ONE ensemble member; the member outputs are
+// combined by cluster rank 0 through distributed shared memory (min over i, sac_base.py:1439-1442).
 __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int net = (int)cluster.block_rank();
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
     const AsacSacConfig &c = a.cfg;
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
                 float pj = expf(normal_log_prob(xa, hr[j], hr[A + j])) / fl;  // operators.py:17-19
                 float mj;
                 if (post) {
-                    a.wrk.pi_probs[((int64_t)eg * (L - 1) + t) * A + j] = pj;
+                    if (net == 0) a.wrk.pi_probs[((int64_t)eg * (L - 1) + t) * A + j] = pj;
                     mj = pj;
                 } else {
                     mj = a.bat.mu_probs[((int64_t)eg * c.bn_stride + t) * A + j];
@@ -274,35 +282,43 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     ts.bias[1] = ts.w[1] + qsh.hidden * tile_lda(qsh.hidden, qsh.in_dim);
     __syncthreads();
 
-    // ---- target critics over the V rows (+ S rows for the clipped loss)
+    // ---- target critic `net` over the V rows (+ S rows for the clipped loss)
     {
         const int rq = need_tq ? RV + RS : RV;
         const int rqp = round_up(rq, PASS_ROWS);
-        for (int i = 0; i < E; ++i) {
-            const float *prm = a.prm.q_target + i * q_stride;
-            float *h = net_trunk_forward(qsh, prm, ts, xin, bufA, bufB, nullptr, nullptr, lda, rqp);
-            float *qo = (h == bufA ? bufB : bufA);  // free buffer: head outputs [rq]
-            head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, rq,
-                         qo);
-            __syncthreads();
-            for (int r = tid; r < rq; r += NT) {
-                if (r < RV) qmin[r] = (i == 0) ? qo[r] : fminf(qmin[r], qo[r]);  // sac_base.py:1439-1442
-                else a.wrk.tq[(int64_t)i * B + e0 + (r - RV)] = qo[r];
-            }
-            __syncthreads();
+        const float *prm = a.prm.q_target + net * q_stride;
+        float *h = net_trunk_forward(qsh, prm, ts, xin, bufA, bufB, nullptr, nullptr, lda, rqp);
+        float *qo = (h == bufA ? bufB : bufA);  // free buffer: head outputs [rq]
+        head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, rq, qo);
+        __syncthreads();
+        for (int r = tid; r < rq; r += NT) {
+            if (r < RV) qmin[r] = qo[r];
+            else a.wrk.tq[(int64_t)net * B + e0 + (r - RV)] = qo[r];
         }
+        __syncthreads();
     }
-    // ---- post: online critics over the S rows (sac_base.py:2211-2216)
+    // ---- post: online critic `net` over the S rows (sac_base.py:2211-2216)
     if (post) {
-        for (int i = 0; i < E; ++i) {
-            const float *prm = a.prm.q + i * q_stride;
-            float *h = net_trunk_forward(qsh, prm, ts, xin + s_row0 * lda, bufA, bufB, nullptr, nullptr, lda,
-                                         round_up(RS, PASS_ROWS));
-            head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, RS,
-                         qs + i * TB);
-            __syncthreads();
+        const float *prm = a.prm.q + net * q_stride;
+        float *h = net_trunk_forward(qsh, prm, ts, xin + s_row0 * lda, bufA, bufB, nullptr, nullptr, lda,
+                                     round_up(RS, PASS_ROWS));
+        head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, RS, qs);
+        __syncthreads();
+    }
+    // ---- ensemble combine on rank 0 over distributed shared memory, in member order
+    cluster.sync();
+    if (net == 0) {
+        for (int i = 1; i < E; ++i) {
+            const float *rmin = cluster.map_shared_rank(qmin, i);
+            for (int r = tid; r < RV; r += NT) qmin[r] = fminf(qmin[r], rmin[r]);  // sac_base.py:1439-1442
+            if (post) {
+                const float *rqs = cluster.map_shared_rank(qs, i);
+                for (int e = tid; e < TBa; e += NT) qs[i * TB + e] = rqs[e];
+            }
         }
     }
+    cluster.sync();  // remote shared memory stays alive until rank 0 has read it
+    if (net != 0) return;
 
     // ---- per batch element: V, v-trace, y (sac_base.py:1244-1295, 1444-1464)
     // y is linear in alpha: V_k = qmin_k - alpha * logp_k.  The train pass knows alpha and writes y;
@@ -466,9 +482,12 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
 }
 
 // ------------------------------------------------------------------------------------ policy
-// grid (n_tiles): policy forward on s_b, rsample, critics on (s_b, tanh x), min, backward
-// through the critics to the action and through the policy (sac_base.py:1882-1908).
+// grid (n_tiles, E), cluster (1, E, 1): policy forward on s_b, rsample, critic `rank` on
+// (s_b, tanh x), min over the cluster, backward through the own critic to the action, sum of
+// the action gradients on rank 0, which then runs the policy backward (sac_base.py:1882-1908).
 __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ SacArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int net = (int)cluster.block_rank();
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
     const AsacSacConfig &c = a.cfg;
@@ -529,15 +548,22 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     ts.bias[1] = ts.w[1] + Hq * tile_lda(Hq, qsh.in_dim);
     __syncthreads();
 
-    // ---- critics forward (z saved)
-    for (int i = 0; i < E; ++i) {
-        const float *prm = a.prm.q + i * q_stride;
+    // ---- own critic forward (z saved), then the other members' values over DSMEM
+    {
+        const float *prm = a.prm.q + net * q_stride;
         float *qz[ASAC_MAX_DEPTH];
-        for (int l = 0; l < dqn; ++l) qz[l] = sm + pl.off_qz + (i * dqn + l) * R * lda;
+        for (int l = 0; l < dqn; ++l) qz[l] = sm + pl.off_qz + l * R * lda;
         float *h = net_trunk_forward(qsh, prm, ts, qin, g[0], g[1], nullptr, qz, lda, R);
-        head_forward(h, lda, Hq, prm + net_w_off(qsh, dqn), prm + net_b_off(qsh, dqn), 1, TBa, qv + i * R);
+        head_forward(h, lda, Hq, prm + net_w_off(qsh, dqn), prm + net_b_off(qsh, dqn), 1, TBa, qv + net * R);
         __syncthreads();
     }
+    cluster.sync();
+    for (int i = 0; i < E; ++i) {
+        if (i == net) continue;
+        const float *rv = cluster.map_shared_rank(qv, i);
+        if (tid < TBa) qv[i * R + tid] = rv[i * R + tid];
+    }
+    __syncthreads();
     if (tid < R) {
         int best = 0;
         if (tid < TBa) {
@@ -549,8 +575,9 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     }
     __syncthreads();
 
-    // ---- backward through each critic to its action input; d loss / d q_min = -1/B
-    for (int i = 0; i < E; ++i) {
+    // ---- backward through the own critic to its action input; d loss / d q_min = -1/B
+    {
+        const int i = net;
         const float *prm = a.prm.q + i * q_stride;
         if (tid < R) dq[tid] = (tid < TBa && (int)amin[tid] == i) ? -1.f / (float)B : 0.f;
         __syncthreads();
@@ -563,7 +590,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
             }
             __syncthreads();
             float *dY = g[cur], *dZ = g[(cur + 1) % 3], *dX = g[(cur + 2) % 3];
-            const float *z = sm + pl.off_qz + (i * dqn + l) * R * lda;
+            const float *z = sm + pl.off_qz + l * R * lda;
             for (int t = tid; t < R * Hq; t += NT) {
                 const int r = t / Hq, j = t - r * Hq;
                 dZ[r * lda + j] = r < TBa ? dY[r * lda + j] * gelu_erf_grad(z[r * lda + j]) : 0.f;
@@ -588,6 +615,16 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         }
         __syncthreads();
     }
+    // ---- sum of the members' action gradients on rank 0, in member order
+    cluster.sync();
+    if (net == 0) {
+        for (int i = 1; i < E; ++i) {
+            const float *rda = cluster.map_shared_rank(da, i);
+            for (int t = tid; t < TBa * A; t += NT) da[t] += rda[t];
+        }
+    }
+    cluster.sync();
+    if (net != 0) return;
 
     // ---- d loss / d (mean, logstd) pre-activations; loss and entropy sums
     float loss = 0.f, ent = 0.f;
@@ -660,7 +697,8 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
 // sums the per-tile partials in tile order: out[p] = sum_t part[t * tile_stride + p]
 __device__ __forceinline__ float reduce_partials(const float *part, int n_tiles, int64_t tile_stride, int64_t p) {
     float s = 0.f;
-    for (int t = 0; t < n_tiles; ++t) s += part[t * tile_stride + p];
+#pragma unroll 8
+    for (int t = 0; t < n_tiles; ++t) s += __ldcg(part + t * tile_stride + p);
     return s;
 }
 
@@ -846,8 +884,11 @@ static const int kSmemLimit = 227 * 1024;
 
 extern "C" int asac_sac_tile_batch(const AsacSacConfig *c) {
     if (validate(c) != ASAC_OK) return ASAC_EINVAL;
-    // largest tile <= 16 whose value-pass plan fits in shared memory
-    for (int tb = PASS_ROWS; tb >= 1; tb >>= 1) {
+    // The step is latency-bound at replay batch sizes: prefer >= 64 batch tiles (x E cluster ranks
+    // >= 128 CTAs on the 148 SMs) over full 16-row tiles, then the largest tile that fits.
+    int want = PASS_ROWS;
+    while (want > 1 && c->batch / want < 64) want >>= 1;
+    for (int tb = want; tb >= 1; tb >>= 1) {
         const int need0 = value_plan(*c, tb, 0).total * 4, need1 = value_plan(*c, tb, 1).total * 4;
         if (need0 <= kSmemLimit && need1 <= kSmemLimit) return tb;
     }
@@ -903,6 +944,25 @@ static int set_smem(K kernel, int bytes, const char *name) {
     return ASAC_OK;
 }
 
+// launch with the E CTAs of a batch tile (grid.y) as one thread-block cluster
+static cudaError_t launch_cluster(void (*kernel)(const SacArgs), dim3 grid, int smem_bytes, cudaStream_t stream,
+                                  int cluster_y, const SacArgs &a) {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = grid;
+    lc.blockDim = dim3(NT);
+    lc.dynamicSmemBytes = (size_t)smem_bytes;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = (unsigned)cluster_y;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, kernel, a);
+}
+
 extern "C" int asac_sac_polyak(const AsacSacConfig *cfg, const AsacSacParams *prm, float force_tau, void *stream) {
     int rc = validate(cfg);
     if (rc != ASAC_OK) return rc;
@@ -920,7 +980,8 @@ static int launch_value_pass(SacArgs &a, int mode, void *stream) {
     const int bytes = value_plan(a.cfg, a.tile_batch, mode).total * 4;
     int rc = set_smem(k_value_pass, bytes, "k_value_pass");
     if (rc != ASAC_OK) return rc;
-    k_value_pass<<<a.wrk.n_tiles, NT, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_CUDA(launch_cluster(k_value_pass, dim3(a.wrk.n_tiles, a.cfg.ensemble), bytes, (cudaStream_t)stream,
+                             a.cfg.ensemble, a));
     ASAC_LAUNCHED("k_value_pass");
     return ASAC_OK;
 }
@@ -964,7 +1025,8 @@ extern "C" int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacP
     const int bytes = grad_plan(a.cfg, true).total * 4;
     rc = set_smem(k_policy_backward, bytes, "k_policy_backward");
     if (rc != ASAC_OK) return rc;
-    k_policy_backward<<<a.wrk.n_tiles, NT, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_CUDA(launch_cluster(k_policy_backward, dim3(a.wrk.n_tiles, cfg->ensemble), bytes, (cudaStream_t)stream,
+                             cfg->ensemble, a));
     ASAC_LAUNCHED("k_policy_backward");
     return ASAC_OK;
 }

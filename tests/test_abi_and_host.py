@@ -68,7 +68,10 @@ def test_host_only_entry_points():
     cfg.q_hidden = cfg.pi_hidden = 64
     cfg.q_depth = cfg.pi_depth = 3
     cfg.bn_stride, cfg.update_target_per_step = 2, 1
-    assert lib.asac_sac_tile_batch(C.byref(cfg)) == 16
+    assert lib.asac_sac_tile_batch(C.byref(cfg)) == 4      # 64 batch tiles x E cluster ranks at B = 256
+    cfg.batch = 4096
+    assert lib.asac_sac_tile_batch(C.byref(cfg)) == 16     # full 16-row tiles once the batch allows
+    cfg.batch = 256
     cfg.q_hidden = 48  # not a supported width -> error code + message, no crash
     assert lib.asac_sac_tile_batch(C.byref(cfg)) < 0
     assert b'hidden width' in lib.asac_last_error()
