@@ -38,6 +38,14 @@ __host__ __device__ __forceinline__ int64_t net_count(const NetShape &s) {
 }
 __host__ __device__ __forceinline__ int64_t net_stride(const NetShape &s) { return (net_count(s) + 3) & ~(int64_t)3; }
 
+// The layer routines below are deliberately NOT inlined: a tile kernel walks ~10 layers through
+// three or four call sites, and with everything inlined (x4 width instantiations) k_value_pass
+// grew to 18 K SASS instructions (290 KB) — the ncu source page showed > 50 % of the warp stall
+// samples in `no_instruction` (instruction-cache misses) with only 4 warps per SM to hide them.
+// One copy per width keeps the hot loop resident.  Pointer arguments that live in shared memory
+// are declared to the compiler with ASAC_SMEM so the out-of-line code still uses LDS/STS.
+#define ASAC_SMEM(p) __builtin_assume(__isShared(p))
+
 // ---------------------------------------------------------------- cp.async helpers
 __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -56,8 +64,9 @@ __device__ __forceinline__ void cp_async_wait() {
 // Stage W[N][K] (row-major, global) into Ws and b[N] into bs.
 //   transpose == false : Ws[n * ldw + k], ldw = round_up(K,4) + 4, pad columns zeroed
 //   transpose == true  : Ws[k * ldw + n], ldw = N + 4   (for dX = dZ . W)
-__device__ __forceinline__ void stage_weights(float *Ws, float *bs, const float *W, const float *b, int N, int K,
-                                              bool transpose) {
+__device__ __noinline__ void stage_weights(float *Ws, float *bs, const float *W, const float *b, int N, int K,
+                                           bool transpose) {
+    ASAC_SMEM(Ws);
     const int tid = threadIdx.x;
     if (!transpose) {
         const int K4 = round_up(K, 4), ldw = K4 + 4;
@@ -129,8 +138,10 @@ __device__ __forceinline__ void gemm_core(const float *__restrict__ A, int lda, 
 // ResBlock forward over `nrows` (multiple of 16) rows:
 //   Z = X . W^T + b ;  Y = gelu(Z) (+ X when residual)        Zs may be null (no backward)
 template <int CM>
-__device__ __forceinline__ void layer_forward_t(const float *X, int ldx, int K4, const float *Ws, const float *bs,
-                                                float *Zs, float *Ys, int ldy, int nrows, bool residual) {
+__device__ __noinline__ void layer_forward_t(const float *X, int ldx, int K4, const float *Ws, const float *bs,
+                                             float *Zs, float *Ys, int ldy, int nrows, bool residual) {
+    ASAC_SMEM(X); ASAC_SMEM(Ws); ASAC_SMEM(bs); ASAC_SMEM(Ys);
+    if (Zs) ASAC_SMEM(Zs);
     const int tid = threadIdx.x, cg = tid & 15, rg = tid >> 4;
     const int ldw = K4 + 4;
     for (int r0 = 0; r0 < nrows; r0 += PASS_ROWS) {
@@ -168,8 +179,9 @@ __device__ __forceinline__ void layer_forward(int hidden, const float *X, int ld
 // dX = dZ . W (+ dY when the block was residual), W staged transposed: Wt[k * ldw + j], ldw = H + 4.
 // Output columns k < H (hidden -> hidden layers only).
 template <int CM>
-__device__ __forceinline__ void layer_input_grad_t(const float *dZ, int ld, int H, const float *Wt, const float *dY,
-                                                   float *dX, int nrows, bool residual) {
+__device__ __noinline__ void layer_input_grad_t(const float *dZ, int ld, int H, const float *Wt, const float *dY,
+                                                float *dX, int nrows, bool residual) {
+    ASAC_SMEM(dZ); ASAC_SMEM(Wt); ASAC_SMEM(dY); ASAC_SMEM(dX);
     const int tid = threadIdx.x, cg = tid & 15, rg = tid >> 4;
     const int ldw = H + 4;
     for (int r0 = 0; r0 < nrows; r0 += PASS_ROWS) {
@@ -213,8 +225,9 @@ __device__ __forceinline__ void gelu_backward(float *dY, const float *Z, int ld,
 // Partial weight / bias gradient of one layer over the tile's rows:
 //   gW[j * K + k] = sum_r dZ[r][j] * X[r][k],  gb[j] = sum_r dZ[r][j]
 // 4x4 output blocks, one float4 of dZ and one of X per row.
-__device__ __forceinline__ void layer_weight_grad(const float *dZ, int ldz, const float *X, int ldx, int H, int K,
-                                                  int nrows, float *gW, float *gb) {
+__device__ __noinline__ void layer_weight_grad(const float *dZ, int ldz, const float *X, int ldx, int H, int K,
+                                               int nrows, float *gW, float *gb) {
+    ASAC_SMEM(dZ); ASAC_SMEM(X);
     const int tid = threadIdx.x;
     const int K4 = round_up(K, 4);
     const int nJB = H >> 2, nKB = K4 >> 2;
@@ -256,8 +269,9 @@ __device__ __forceinline__ void layer_weight_grad(const float *dZ, int ldz, cons
 }
 
 // Linear head: out[r * O + o] = X[r] . Wh[o] + bh[o]   (Wh, bh in global memory, 8 lanes per dot)
-__device__ __forceinline__ void head_forward(const float *X, int ldx, int H, const float *Wh, const float *bh,
-                                             int O, int nrows, float *out) {
+__device__ __noinline__ void head_forward(const float *X, int ldx, int H, const float *Wh, const float *bh,
+                                          int O, int nrows, float *out) {
+    ASAC_SMEM(X); ASAC_SMEM(out);
     const int tid = threadIdx.x, grp = tid >> 3, sub = tid & 7;
     const int total = nrows * O;
     for (int d0 = 0; d0 < total; d0 += NT / 8) {
@@ -278,9 +292,11 @@ __device__ __forceinline__ void head_forward(const float *X, int ldx, int H, con
 
 // Head backward.  dO[r * O + o] (rows >= valid rows must be zero):
 //   gWh[o * H + j] = sum_r dO[r][o] X[r][j];  gbh[o] = sum_r dO[r][o];  dH[r][j] = sum_o dO[r][o] Wh[o][j]
-__device__ __forceinline__ void head_backward(const float *dO, int O, const float *X, int ldx, int H,
-                                              const float *Wh, int nrows, float *gWh, float *gbh, float *dH,
-                                              int ldh) {
+__device__ __noinline__ void head_backward(const float *dO, int O, const float *X, int ldx, int H,
+                                           const float *Wh, int nrows, float *gWh, float *gbh, float *dH,
+                                           int ldh) {
+    ASAC_SMEM(dO); ASAC_SMEM(dH);
+    if (X) ASAC_SMEM(X);
     const int tid = threadIdx.x;
     if (gWh) {
         for (int i = tid; i < O * H; i += NT) {

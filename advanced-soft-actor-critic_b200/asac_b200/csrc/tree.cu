@@ -20,42 +20,143 @@ static inline bool is_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
 // ------------------------------------------------------------------------------------
 // Block-cooperative leaf write + ancestor recompute.  One thread per updated leaf, one CTA.
 // Duplicate slots: the highest thread index wins (NumPy fancy-assignment order).
-// Every parent is recomputed as fp32 (left + right) from L2 (.cg loads/stores), level by
-// level behind a CTA barrier, so the result is independent of thread scheduling and
-// bit-identical to replay_buffer.py:176-183.
+//
+// Every touched parent becomes fp32 (left + right) exactly as replay_buffer.py:176-183, but the
+// D dependent global round trips of a level-by-level walk are replaced by ONE: the siblings of
+// every node on a leaf's path are prefetched at once (they are only used where the sibling
+// subtree holds no updated leaf), and the level-by-level recomputation runs on the union of
+// the paths in shared memory.  The updated leaves are kept as a sorted, doubly linked list of
+// "alive" entries; on each level two alive siblings merge (the left one survives and adds the
+// right one's value), a lone child adds its prefetched sibling.  Results go back with
+// fire-and-forget stores.  Stratified samples arrive sorted by leaf, so the bitonic sort below
+// only runs for caller-supplied id lists.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_tree_apply(float *nodes, int64_t capacity, int levels, int slot,
-                                                 float value, bool active, bool check_dups, int *s_slot) {
-    const int t = threadIdx.x;
-    bool winner = active;
-    if (check_dups) {
-        s_slot[t] = active ? slot : -1;
+constexpr int TREE_CHUNK = 8;  // levels per register set of prefetched siblings
+
+struct TreeApplySmem {
+    unsigned long long key[1024];
+    int node[1024];
+    float val[1024];
+    short next[1024], prev[1024];
+    int warp_sum[32];
+};
+
+__device__ __forceinline__ void block_tree_apply(float *nodes, int64_t capacity, int levels, int slot, float value,
+                                                 bool active, TreeApplySmem &sm) {
+    const int t = threadIdx.x, nthr = blockDim.x, lane = t & 31, warp = t >> 5;
+    // ---- sort key (slot, thread): inactive entries sort to the end
+    const unsigned long long mykey =
+        active ? (((unsigned long long)(unsigned)slot << 32) | (unsigned)t) : 0xFFFFFFFFFFFFFFFFull;
+    sm.key[t] = mykey;
+    sm.val[t] = value;
+    __syncthreads();
+    const bool unsorted = t > 0 && sm.key[t - 1] > mykey;
+    if (__syncthreads_or(unsorted)) {
+        int n2 = 32;
+        while (n2 < nthr) n2 <<= 1;
+        for (int i = nthr + t; i < n2; i += nthr) sm.key[i] = 0xFFFFFFFFFFFFFFFFull;
         __syncthreads();
-        if (active) {
-            for (int u = t + 1; u < (int)blockDim.x; ++u) {
-                if (s_slot[u] == slot) {
-                    winner = false;
-                    break;
+        for (int k = 2; k <= n2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = t; i < n2; i += nthr) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = sm.key[i], b = sm.key[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { sm.key[i] = b; sm.key[ixj] = a; }
+                    }
                 }
+                __syncthreads();
             }
         }
     }
-    int64_t node = capacity + slot;
-    if (winner) __stcg(&nodes[node], value);
-    const float2 *pairs = reinterpret_cast<const float2 *>(nodes);
-    for (int l = 0; l < levels; ++l) {
-        __syncthreads();
-        node >>= 1;
-        if (winner) {
-            float2 ch = __ldcg(pairs + node);  // children 2*node, 2*node+1
-            __stcg(&nodes[node], __fadd_rn(ch.x, ch.y));
+    // ---- winners: the last entry of each run of equal slots (= the highest thread index)
+    const unsigned long long k0 = sm.key[t];
+    const bool valid = k0 != 0xFFFFFFFFFFFFFFFFull;
+    const unsigned long long k1 = (t + 1 < nthr) ? sm.key[t + 1] : 0xFFFFFFFFFFFFFFFFull;
+    const bool winner = valid && (k1 == 0xFFFFFFFFFFFFFFFFull || (k1 >> 32) != (k0 >> 32));
+    const float wval = valid ? sm.val[(int)(k0 & 0xFFFFFFFFu)] : 0.f;
+    // ---- dense rank of the winners (block exclusive scan)
+    const unsigned ballot = __ballot_sync(0xffffffffu, winner);
+    if (lane == 0) sm.warp_sum[warp] = __popc(ballot);
+    __syncthreads();  // also: every thread has read its key / value before the arrays are reused
+    int base = 0, total = 0;
+    for (int w = 0; w < (nthr >> 5); ++w) {
+        const int c = sm.warp_sum[w];
+        if (w < warp) base += c;
+        total += c;
+    }
+    const int d = base + __popc(ballot & ((1u << lane) - 1u));
+    __syncthreads();
+    if (winner) {
+        sm.node[d] = (int)(capacity + (int64_t)(k0 >> 32));
+        sm.val[d] = wval;
+        sm.next[d] = (short)(d + 1 < total ? d + 1 : -1);
+        sm.prev[d] = (short)(d - 1);
+    }
+    __syncthreads();
+    // ---- entry t (< total) walks its leaf's path, TREE_CHUNK levels per register set; the next
+    // chunk's siblings are requested before the current chunk is consumed (one exposed round trip)
+    bool alive = t < total;
+    const int leaf_node = alive ? sm.node[t] : 1;
+    int node = leaf_node;
+    if (alive) __stcg(nodes + node, sm.val[t]);
+    float cur[TREE_CHUNK], nxt[TREE_CHUNK];
+#pragma unroll
+    for (int j = 0; j < TREE_CHUNK; ++j) cur[j] = (alive && j < levels) ? __ldcg(nodes + ((leaf_node >> j) ^ 1)) : 0.f;
+#pragma unroll 1
+    for (int l0 = 0; l0 < levels; l0 += TREE_CHUNK) {
+#pragma unroll
+        for (int j = 0; j < TREE_CHUNK; ++j) {
+            const int l = l0 + TREE_CHUNK + j;
+            nxt[j] = (alive && l < levels) ? __ldcg(nodes + ((leaf_node >> l) ^ 1)) : 0.f;
         }
+#pragma unroll
+        for (int j = 0; j < TREE_CHUNK; ++j) {
+            if (l0 + j < levels) {  // block-uniform
+                float nv = 0.f;
+                int merged = -1;
+                bool dies = false;
+                if (alive) {
+                    const float mine = sm.val[t];
+                    if ((node & 1) == 0) {
+                        const int u = sm.next[t];
+                        if (u >= 0 && sm.node[u] == node + 1) {
+                            merged = u;
+                            nv = __fadd_rn(mine, sm.val[u]);
+                        } else {
+                            nv = __fadd_rn(mine, cur[j]);
+                        }
+                    } else {
+                        const int q = sm.prev[t];
+                        if (q >= 0 && sm.node[q] == node - 1) dies = true;
+                        else nv = __fadd_rn(cur[j], mine);
+                    }
+                }
+                __syncthreads();
+                if (alive && !dies) {
+                    node >>= 1;
+                    sm.node[t] = node;
+                    sm.val[t] = nv;
+                    __stcg(nodes + node, nv);
+                    if (merged >= 0) {
+                        const int w = sm.next[merged];
+                        sm.next[t] = (short)w;
+                        if (w >= 0) sm.prev[w] = (short)t;
+                    }
+                }
+                if (dies) alive = false;
+                __syncthreads();
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < TREE_CHUNK; ++j) cur[j] = nxt[j];
     }
 }
 
 __global__ void __launch_bounds__(1024) k_tree_update(float *nodes, int64_t capacity, int levels,
                                                       const int64_t *slots, const float *p, int k) {
-    __shared__ int s_slot[1024];
+    __shared__ TreeApplySmem s_apply;
     const int t = threadIdx.x;
     const bool active = t < k;
     int slot = 0;
@@ -64,7 +165,7 @@ __global__ void __launch_bounds__(1024) k_tree_update(float *nodes, int64_t capa
         slot = (int)slots[t];
         value = p[t];
     }
-    block_tree_apply(nodes, capacity, levels, slot, value, active, true, s_slot);
+    block_tree_apply(nodes, capacity, levels, slot, value, active, s_apply);
 }
 
 __global__ void k_tree_level(float *nodes, int64_t first, int64_t count) {
@@ -100,21 +201,86 @@ __global__ void __launch_bounds__(256) k_leaf_max(const float *leaves, int64_t n
     }
 }
 
-// replay_buffer.py:195-205 for one sample; returns the data slot, *p_out = leaf priority
-__device__ __forceinline__ int tree_descend(const float *nodes, int64_t capacity, int levels, double v,
-                                            float *p_out) {
-    const float2 *pairs = reinterpret_cast<const float2 *>(nodes);
-    int64_t node = 1;
-    float leaf = nodes[1];
-    for (int l = 0; l < levels; ++l) {
-        float2 ch = __ldg(pairs + node);
-        const bool left = (v <= (double)ch.x) || (ch.y == 0.f);
-        if (!left) v -= (double)ch.x;
-        node = 2 * node + (left ? 0 : 1);
-        leaf = left ? ch.x : ch.y;
+// One decision of replay_buffer.py:195-205: go left iff v <= left || right == 0, else v -= left
+// (float64 compare / subtract against fp32 nodes, NumPy promotion).
+__device__ __forceinline__ int descend_step(float left, float right, double &v, float &leaf) {
+    const bool go_left = (v <= (double)left) || (right == 0.f);
+    if (!go_left) v -= (double)left;
+    leaf = go_left ? left : right;
+    return go_left ? 0 : 1;
+}
+
+// K levels below `node` with ONE memory round trip: the 2^j descendants of `node` on sub-level j
+// are the contiguous, aligned run nodes[node << j .. (node << j) + 2^j), so all K sub-levels are
+// requested before the first comparison (speculative loads: 2^(K+1) - 2 floats, one is used per
+// level).  The decisions themselves are replay_buffer.py:195-205 unchanged.
+template <int K>
+__device__ __forceinline__ int64_t descend_block(const float *__restrict__ nodes, int64_t node, double &v,
+                                                 float &leaf) {
+    float sub[(2 << K) - 2];  // sub-level j (1..K) at offset 2^j - 2
+    {
+        const float2 c = __ldg(reinterpret_cast<const float2 *>(nodes + (node << 1)));
+        sub[0] = c.x; sub[1] = c.y;
     }
+#pragma unroll
+    for (int j = 2; j <= K; ++j) {
+#pragma unroll
+        for (int q = 0; q < (1 << j) / 4; ++q) {
+            const int o = (1 << j) - 2 + 4 * q;
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(nodes + (node << j)) + q);
+            sub[o] = c.x; sub[o + 1] = c.y; sub[o + 2] = c.z; sub[o + 3] = c.w;
+        }
+    }
+    int path = 0;  // decisions so far, oldest in the most significant bit
+#pragma unroll
+    for (int j = 1; j <= K; ++j) {
+        // the pair under `path` on sub-level j: halve the candidate run once per earlier decision
+        float cand[1 << K];
+#pragma unroll
+        for (int i = 0; i < (1 << j); ++i) cand[i] = sub[(1 << j) - 2 + i];
+#pragma unroll
+        for (int b = 0; b < j - 1; ++b) {
+            const bool bit = (path >> (j - 2 - b)) & 1;
+            const int half = (1 << j) >> (b + 1);
+#pragma unroll
+            for (int i = 0; i < half; ++i) cand[i] = bit ? cand[i + half] : cand[i];
+        }
+        path = (path << 1) | descend_step(cand[0], cand[1], v, leaf);
+    }
+    return (node << K) + path;
+}
+
+// replay_buffer.py:195-205 for one sample; returns the data slot, *p_out = leaf priority.
+// `top` (shared memory, may be null) mirrors nodes[0 .. 2^(top_levels+1)), i.e. levels 0..top_levels.
+__device__ __forceinline__ int tree_descend(const float *__restrict__ nodes, int64_t capacity, int levels, double v,
+                                            float *p_out, const float *top = nullptr, int top_levels = 0) {
+    int64_t node = 1;
+    float leaf = top ? top[1] : nodes[1];
+    int l = 0;
+    for (; l < top_levels; ++l) node = 2 * node + descend_step(top[2 * node], top[2 * node + 1], v, leaf);
+    // K = 3 (one 8-byte and three 16-byte requests): ptxas keeps exactly this group ahead of the
+    // first decision; with K = 4 it sinks the 64-byte sub-level below it, i.e. a second round trip
+    for (; l + 3 <= levels; l += 3) node = descend_block<3>(nodes, node, v, leaf);
+    const int rest = levels - l;
+    if (rest == 2) node = descend_block<2>(nodes, node, v, leaf);
+    else if (rest == 1) node = descend_block<1>(nodes, node, v, leaf);
     *p_out = leaf;
     return (int)(node - capacity);
+}
+
+// levels of the tree mirrored in shared memory by the sampling kernels (nodes[0 .. 2^(n+1)))
+constexpr int TREE_TOP_LEVELS = 10;
+__device__ __forceinline__ int stage_tree_top(const float *__restrict__ nodes, int levels, float *top) {
+    const int n = levels < TREE_TOP_LEVELS ? levels : TREE_TOP_LEVELS;
+    const float4 *src = reinterpret_cast<const float4 *>(nodes);
+    float4 *dst = reinterpret_cast<float4 *>(top);
+    if (n >= 1) {
+        for (int i = threadIdx.x; i < ((2 << n) >> 2); i += blockDim.x) dst[i] = __ldg(src + i);
+    } else {
+        if (threadIdx.x < 2) top[threadIdx.x] = __ldg(nodes + threadIdx.x);
+    }
+    __syncthreads();
+    return n;
 }
 
 __device__ __forceinline__ double stratum_draw(float total, int batch, int i, double u) {
@@ -127,6 +293,8 @@ __device__ __forceinline__ double stratum_draw(float total, int batch, int i, do
 __global__ void k_tree_sample(const float *nodes, int64_t capacity, int levels, int batch,
                               const double *unit_uniform, uint64_t seed, const int64_t *draw_counter,
                               int32_t *out_slot, float *out_p) {
+    __shared__ __align__(16) float s_top[2 << TREE_TOP_LEVELS];
+    const int top_levels = stage_tree_top(nodes, levels, s_top);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
     double u;
@@ -137,9 +305,9 @@ __global__ void k_tree_sample(const float *nodes, int64_t capacity, int levels, 
         philox4(seed, (uint64_t)draw_counter[0], (uint64_t)i, r);
         u = u01_double(r[0], r[1]);
     }
-    const float total = nodes[1];
+    const float total = s_top[1];
     float p;
-    out_slot[i] = tree_descend(nodes, capacity, levels, stratum_draw(total, batch, i, u), &p);
+    out_slot[i] = tree_descend(nodes, capacity, levels, stratum_draw(total, batch, i, u), &p, s_top, top_levels);
     out_p[i] = p;
 }
 
@@ -151,9 +319,11 @@ __global__ void __launch_bounds__(1024) k_per_sample(const float *nodes, int64_t
                                                      int32_t *out_slot, int64_t *out_data_id, float *out_p,
                                                      float *out_w) {
     __shared__ float s_min[32];
+    __shared__ __align__(16) float s_top[2 << TREE_TOP_LEVELS];
+    const int top_levels = stage_tree_top(nodes, levels, s_top);
     const int t = threadIdx.x;
     const bool active = t < batch;
-    const float total = nodes[1];
+    const float total = s_top[1];
     float p = 0.f, w = INFINITY;
     if (active) {
         double u;
@@ -164,7 +334,8 @@ __global__ void __launch_bounds__(1024) k_per_sample(const float *nodes, int64_t
             philox4(seed, (uint64_t)draw_counter[0], (uint64_t)t, r);
             u = u01_double(r[0], r[1]);
         }
-        const int slot = tree_descend(nodes, capacity, levels, stratum_draw(total, batch, t, u), &p);
+        const int slot = tree_descend(nodes, capacity, levels, stratum_draw(total, batch, t, u), &p, s_top,
+                                      top_levels);
         out_slot[t] = slot;
         out_data_id[t] = store_ids[slot];
         out_p[t] = p;
@@ -195,7 +366,7 @@ __global__ void __launch_bounds__(1024) k_per_update(float *nodes, int64_t capac
                                                      const int64_t *store_ids, const int64_t *data_ids,
                                                      const float *td, int k, float td_min, float td_max,
                                                      float alpha, int precomputed_p, double *per_state) {
-    __shared__ int s_slot[1024];
+    __shared__ TreeApplySmem s_apply;
     const int t = threadIdx.x;
     bool active = t < k;
     int slot = 0;
@@ -220,7 +391,7 @@ __global__ void __launch_bounds__(1024) k_per_update(float *nodes, int64_t capac
         if (t == 0) per_state[3] = 1.0;  // the reference raises 'td_error has nan'
         return;
     }
-    block_tree_apply(nodes, capacity, levels, slot, value, active, true, s_slot);
+    block_tree_apply(nodes, capacity, levels, slot, value, active, s_apply);
 }
 
 // replay_buffer.py:293-307 + :43-54 — one CTA per chunk of <= 1024 new rows
@@ -228,7 +399,7 @@ __global__ void __launch_bounds__(1024) k_per_add(float *nodes, int64_t capacity
                                                   int64_t *store_ids, int64_t first_id, int64_t T,
                                                   int64_t chunk_begin, int chunk_len, const float *max_p,
                                                   int ignore_size) {
-    __shared__ int s_slot[1];
+    __shared__ TreeApplySmem s_apply;
     const int t = threadIdx.x;
     bool active = t < chunk_len;
     int slot = 0;
@@ -244,7 +415,7 @@ __global__ void __launch_bounds__(1024) k_per_add(float *nodes, int64_t capacity
         value = max_p[0];
         if (ignore_size > 0 && (slot >= capacity - ignore_size || i >= T - ignore_size)) value = 0.f;
     }
-    block_tree_apply(nodes, capacity, levels, slot, value, active, false, s_slot);
+    block_tree_apply(nodes, capacity, levels, slot, value, active, s_apply);
 }
 
 }  // namespace asac
