@@ -97,6 +97,8 @@ PROTOTYPES = {
     'asac_sac_td_error': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp]),
     'asac_sac_advance_step': (i32, [P(AsacSacParams), vp]),
     'asac_sac_step': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork), vp]),
+    'asac_sac_step_networks': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork), i32, vp]),
+    'asac_sac_finish_step': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp, i64, vp, vp, vp, vp]),
     'asac_fill_normal': (i32, [vp, i64, u64, vp, i32, vp]),
     'asac_mlp_forward': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp]),
 }

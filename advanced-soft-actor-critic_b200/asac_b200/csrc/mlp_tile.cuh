@@ -24,9 +24,9 @@ struct NetShape {
     int in_dim, hidden, depth, out_dim;
 };
 __host__ __device__ __forceinline__ int64_t net_w_off(const NetShape &s, int l) {  // l == depth -> head
-    int64_t off = 0;
-    for (int i = 0; i < l; ++i) off += (int64_t)s.hidden * (i == 0 ? s.in_dim : s.hidden) + s.hidden;
-    return off;
+    // closed form (a loop here was unrolled at every call site: 31 % of k_value_pass's instructions)
+    if (l == 0) return 0;
+    return (int64_t)s.hidden * (s.in_dim + 1) + (int64_t)(l - 1) * s.hidden * (s.hidden + 1);
 }
 __host__ __device__ __forceinline__ int net_k(const NetShape &s, int l) { return l == 0 ? s.in_dim : s.hidden; }
 __host__ __device__ __forceinline__ int net_n(const NetShape &s, int l) { return l == s.depth ? s.out_dim : s.hidden; }

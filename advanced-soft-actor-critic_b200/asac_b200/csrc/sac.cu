@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "mlp_tile.cuh"
+#include "tree_apply.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -43,19 +44,19 @@ __host__ __device__ __forceinline__ int sac_wsz(const AsacSacConfig &c) {
 constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
 
 // torch.distributions.Normal.log_prob: -((x - loc)^2) / (2 var) - log(scale) - log(sqrt(2 pi))
-__device__ __forceinline__ float normal_log_prob(float x, float loc, float scale) {
+__device__ __noinline__ float normal_log_prob(float x, float loc, float scale) {
     const float var = scale * scale;
     const float d = x - loc;
     return -(d * d) / (2.f * var) - logf(scale) - LOG_SQRT_2PI;
 }
 // max(1 - tanh(x)^2, 1e-2)   (utils/operators.py:14,19)
-__device__ __forceinline__ float squash_floor(float x) {
+__device__ __noinline__ float squash_floor(float x) {
     const float t = tanhf(x);
     return fmaxf(1.f - t * t, 1e-2f);
 }
 // policy.py:169
-__device__ __forceinline__ float policy_loc(float m) { return tanhf(m / 5.f) * 5.f; }
-__device__ __forceinline__ float policy_scale(float s) { return expf(fminf(fmaxf(s, -20.f), 0.5f)); }
+__device__ __noinline__ float policy_loc(float m) { return tanhf(m / 5.f) * 5.f; }
+__device__ __noinline__ float policy_scale(float s) { return expf(fminf(fmaxf(s, -20.f), 0.5f)); }
 
 __device__ __forceinline__ float block_sum(float v, float *red) {
 #pragma unroll
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         float v_prev = q_prev - alpha * l_prev;
         const float v0 = v_prev, q0 = q_prev, l0 = l_prev;
         float sum = 0.f, sum_q = 0.f, sum_l = 0.f, cprod = 1.f;
+#pragma unroll 1
         for (int k = 0; k < n; ++k) {
             const float q_next = qmin[e * (n + 1) + k + 1], l_next = logp[e * (n + 1) + k + 1];
             const float v_next = q_next - alpha * l_next;
@@ -744,10 +746,10 @@ __global__ void __launch_bounds__(256) k_reduce_adam(const AdamArgs a) {
 
 // alpha: a single scalar, gradient = (sum over tiles of the alpha terms) / B  (sac_base.py:1941-1948),
 // then y' = yq - alpha_new * yl and td = mean_i |Q_i(s_b, a_b) - y'|  (sac_base.py:2223-2245).  One CTA.
-__global__ void __launch_bounds__(1024) k_alpha_td(const AsacSacParams prm, const AsacSacWork wrk, int n_tiles,
-                                                   int batch, int ensemble, int do_reduce, int do_adam, int do_td,
-                                                   float grad_scale, double lr) {
-    if (threadIdx.x == 0 && (do_reduce || do_adam)) {
+__device__ __forceinline__ void alpha_reduce_adam(const AsacSacParams &prm, const AsacSacWork &wrk, int n_tiles,
+                                                  int batch, int do_reduce, int do_adam, float grad_scale,
+                                                  double lr) {
+    {
         float gr;
         if (do_reduce) {
             float s = 0.f;
@@ -773,6 +775,13 @@ __global__ void __launch_bounds__(1024) k_alpha_td(const AsacSacParams prm, cons
             prm.log_alpha[0] = prm.log_alpha[0] + (step_size * m) / denom;
         }
     }
+}
+
+__global__ void __launch_bounds__(1024) k_alpha_td(const AsacSacParams prm, const AsacSacWork wrk, int n_tiles,
+                                                   int batch, int ensemble, int do_reduce, int do_adam, int do_td,
+                                                   float grad_scale, double lr) {
+    if (threadIdx.x == 0 && (do_reduce || do_adam))
+        alpha_reduce_adam(prm, wrk, n_tiles, batch, do_reduce, do_adam, grad_scale, lr);
     if (!do_td) return;
     __syncthreads();
     const float alpha = expf(__ldcg(prm.log_alpha));
@@ -784,6 +793,51 @@ __global__ void __launch_bounds__(1024) k_alpha_td(const AsacSacParams prm, cons
         wrk.y_td[e] = y;
         wrk.td_error[e] = acc / (float)ensemble;
     }
+}
+
+// The tail of one train() in ONE CTA (batch <= 1024): alpha reduce + Adam (sac_base.py:1941-1948),
+// y' and td error with the updated alpha (:2223-2245), PrioritizedReplayBuffer.update
+// (replay_buffer.py:412-427) and the step / optimizer counters (sac_base.py:2607).
+struct EpilogueArgs {
+    AsacSacParams prm;
+    AsacSacWork wrk;
+    int n_tiles, batch, ensemble, use_auto_alpha, counter_mask;
+    double lr;
+    float *nodes;
+    int64_t capacity;
+    int levels;
+    const int64_t *store_ids, *data_ids;
+    float td_min, td_max, per_alpha;
+    double *per_state;
+};
+__global__ void __launch_bounds__(1024) k_step_epilogue(const __grid_constant__ EpilogueArgs a) {
+    __shared__ TreeApplySmem s_apply;
+    const int t = threadIdx.x;
+    if (t == 0 && a.use_auto_alpha) alpha_reduce_adam(a.prm, a.wrk, a.n_tiles, a.batch, 1, 1, 1.f, a.lr);
+    __syncthreads();
+    const float alpha = expf(__ldcg(a.prm.log_alpha));
+    bool active = t < a.batch;
+    int slot = 0, bad = 0;
+    float value = 0.f;
+    if (active) {
+        const float *parts = a.wrk.post_parts + (int64_t)t * (2 + a.ensemble);
+        const float y = parts[0] - alpha * parts[1];
+        float acc = 0.f;
+        for (int i = 0; i < a.ensemble; ++i) acc += fabsf(parts[2 + i] - y);
+        const float td = acc / (float)a.ensemble;
+        a.wrk.y_td[t] = y;
+        a.wrk.td_error[t] = td;
+        const int64_t id = a.data_ids[t];
+        slot = (int)(id & (a.capacity - 1));
+        value = td_to_priority(td, a.td_min, a.td_max, a.per_alpha, &bad);
+        active = (a.store_ids[slot] == id);
+    }
+    if (t < 4 && ((a.counter_mask >> t) & 1)) a.prm.counters[t] += 1;  // after the Adam step read counters[3]
+    if (__syncthreads_or(bad)) {
+        if (t == 0) a.per_state[3] = 1.0;  // the reference raises 'td_error has nan'
+        return;
+    }
+    block_tree_apply(a.nodes, a.capacity, a.levels, slot, value, active, s_apply);
 }
 
 __global__ void k_bump(int64_t *counters, int mask) {
@@ -1105,30 +1159,62 @@ extern "C" int asac_sac_td_error(const AsacSacConfig *cfg, const AsacSacParams *
     return launch_reduce_adam(cfg, prm, wrk, 2, 0, 0, 1.f, stream, 1);
 }
 
-extern "C" int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
-                             const AsacSacWork *wrk, void *stream) {
+extern "C" int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
+                                      const AsacSacWork *wrk, int with_polyak, void *stream) {
     SacArgs a;
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
     ASAC_REQUIRE(bat && bat->states && bat->eps_y && bat->eps_pi, "asac_sac_step: missing batch tensors");
-    if ((rc = asac_sac_polyak(cfg, prm, -1.f, stream)) != ASAC_OK) return rc;
+    if (with_polyak && (rc = asac_sac_polyak(cfg, prm, -1.f, stream)) != ASAC_OK) return rc;
     if ((rc = launch_value_pass(a, 0, stream)) != ASAC_OK) return rc;
     if ((rc = asac_sac_q_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
     if ((rc = launch_reduce_adam(cfg, prm, wrk, 0, 1, 1, 1.f, stream)) != ASAC_OK) return rc;
     if ((rc = asac_sac_policy_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
     if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, 1.f, stream)) != ASAC_OK) return rc;
-    int mask = 1 | 2 | 4;
     const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
     if (need_post) {
         ASAC_REQUIRE(bat->eps_td && bat->eps_alpha, "asac_sac_step: missing eps_td / eps_alpha");
         if ((rc = launch_value_pass(a, 1, stream)) != ASAC_OK) return rc;
     }
+    return ASAC_OK;
+}
+
+extern "C" int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
+                             const AsacSacWork *wrk, void *stream) {
+    int rc = asac_sac_step_networks(cfg, prm, bat, wrk, 1, stream);
+    if (rc != ASAC_OK) return rc;
+    int mask = 1 | 2 | 4;
+    const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
     if (cfg->use_auto_alpha || need_post) {
         const int aa = cfg->use_auto_alpha ? 1 : 0;
         if ((rc = launch_reduce_adam(cfg, prm, wrk, 2, aa, aa, 1.f, stream, need_post ? 1 : 0)) != ASAC_OK) return rc;
         if (aa) mask |= 8;
     }
     return bump(prm, mask, stream);
+}
+
+extern "C" int asac_sac_finish_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk,
+                                    float *nodes, int64_t capacity, const int64_t *store_ids,
+                                    const int64_t *data_ids, double *per_state, void *stream) {
+    int rc = validate(cfg);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(is_pow2(capacity), "asac_sac_finish_step: capacity is not a power of two");
+    ASAC_REQUIRE(cfg->batch <= 1024, "asac_sac_finish_step: batch %d > 1024", cfg->batch);
+    ASAC_REQUIRE(prm && wrk && nodes && store_ids && data_ids && per_state, "asac_sac_finish_step: null pointer");
+    EpilogueArgs a;
+    a.prm = *prm; a.wrk = *wrk;
+    a.n_tiles = wrk->n_tiles; a.batch = cfg->batch; a.ensemble = cfg->ensemble;
+    a.use_auto_alpha = cfg->use_auto_alpha ? 1 : 0;
+    a.counter_mask = 1 | 2 | 4 | (cfg->use_auto_alpha ? 8 : 0);
+    a.lr = cfg->learning_rate;
+    a.nodes = nodes; a.capacity = capacity; a.levels = tree_levels(capacity);
+    a.store_ids = store_ids; a.data_ids = data_ids;
+    a.td_min = cfg->td_error_min; a.td_max = cfg->td_error_max; a.per_alpha = cfg->per_alpha;
+    a.per_state = per_state;
+    const int threads = ((cfg->batch + 31) / 32) * 32;
+    k_step_epilogue<<<1, threads, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_step_epilogue");
+    return ASAC_OK;
 }
 
 extern "C" int asac_fill_normal(float *out, int64_t n, uint64_t seed, const int64_t *counter, int stream_id,

@@ -425,6 +425,7 @@ class SAC_Base:
         batch.eps_y, batch.eps_pi, batch.eps_alpha, batch.eps_td = [ptr(e) for e in self._eps]
         self._batch = batch
         self._noise_seed = (int(self._seed) if self._seed is not None else random.getrandbits(62)) ^ 0x5AC5AC
+        self._side_stream = torch.cuda.Stream(device=dev)
 
     def _init_or_restore(self, last_ckpt: int | None) -> None:
         """sac_base.py:568-629."""
@@ -583,31 +584,60 @@ class SAC_Base:
         return specs
 
     def _enqueue_step(self) -> None:
-        """Everything one train() does on the device, in stream order (graph-capturable)."""
-        lib, rb, stream = self._lib, self.replay_buffer, _lib.current_stream()
+        """Everything one train() does on the device (graph-capturable).  Critical path: sample ->
+        gather -> value pass -> critics -> Adam -> policy -> Adam -> post pass -> fused tail; the
+        Polyak update and the Gaussian draws (independent of the sample) and the mu-prob write-back
+        (independent of the tail) run on a forked stream, i.e. as parallel branches of the graph."""
+        lib, rb = self._lib, self.replay_buffer
         smp, cfg, prm, batch, work = self._smp, self._cfg, self._prm, self._batch, self._work
         B = self.batch_size
+        main = torch.cuda.current_stream(self.device)
+        side = self._side_stream
+        fused = self._world == 1
+        fast_tail = fused and self.use_priority and B <= 1024
+        # side branch: _update_target_variables (sac_base.py:2057-2058) + the four Gaussian draws
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            s2 = side.cuda_stream
+            if fast_tail:
+                check(lib.asac_sac_polyak(C.byref(cfg), C.byref(prm), -1.0, s2), 'sac_polyak')
+            check(lib.asac_fill_normal(ptr(self._noise), self._noise.numel(), self._noise_seed, ptr(self._counters),
+                                       0, s2), 'fill_normal')
+        stream = main.cuda_stream
         # 1. prioritized sample + IS weights (replay_buffer.py:347-354)
         check(lib.asac_per_sample(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), B, None, rb._seed,
                                   ptr(rb._draw_counter), ptr(rb._per_state), ptr(smp['slots']), ptr(smp['ids']),
                                   ptr(smp['p']), ptr(smp['w']), stream), 'per_sample')
         # 2. window gather fused with the padding rule (replay_buffer.py:356-362, sac_base.py:2435-2453)
         rb._gather(smp['ids'], self._specs, self._padding_action, self._bt['padding_masks'])
-        # 3. the four Gaussian draws of the step
-        check(lib.asac_fill_normal(ptr(self._noise), self._noise.numel(), self._noise_seed, ptr(self._counters), 0,
-                                   stream), 'fill_normal')
-        # 4. _train + get_l_probs + _get_td_error
-        if self._world == 1:
-            check(lib.asac_sac_step(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), stream), 'sac_step')
-        else:
+        main.wait_stream(side)
+        # 3. _train + get_l_probs + _get_td_error
+        if not fused:
             self._enqueue_sac_step_data_parallel(stream)
-        # 5. priority update and mu-prob write-back (sac_base.py:2584, 2598-2605)
-        if self.use_priority:
-            check(lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), ptr(smp['ids']),
-                                      ptr(self._wk['td_error']), B, float(rb.td_error_min), float(rb.td_error_max),
-                                      float(rb.alpha), 0, ptr(rb._per_state), stream), 'per_update')
+        elif fast_tail:
+            check(lib.asac_sac_step_networks(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), 0, stream),
+                  'sac_step_networks')
+        else:
+            check(lib.asac_sac_step(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), stream), 'sac_step')
+        # 4. mu-prob write-back (sac_base.py:2598-2605): needs the post pass only -> side branch
         if self.use_n_step_is:
-            rb.write_back(smp['ids'], 'mu_prob', self._wk['pi_probs'], -self.burn_in_step, self._bt['padding_masks'])
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                rb.write_back(smp['ids'], 'mu_prob', self._wk['pi_probs'], -self.burn_in_step,
+                              self._bt['padding_masks'])
+        # 5. alpha step, td error, priority update (sac_base.py:2115-2116, 2571-2584), step counters
+        if self.use_priority:
+            if fast_tail:
+                check(lib.asac_sac_finish_step(C.byref(cfg), C.byref(prm), C.byref(work), ptr(rb._nodes), rb.capacity,
+                                               ptr(rb._store_ids), ptr(smp['ids']), ptr(rb._per_state), stream),
+                      'sac_finish_step')
+            else:
+                check(lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), ptr(smp['ids']),
+                                          ptr(self._wk['td_error']), B, float(rb.td_error_min),
+                                          float(rb.td_error_max), float(rb.alpha), 0, ptr(rb._per_state), stream),
+                      'per_update')
+        if self.use_n_step_is:
+            main.wait_stream(side)
 
     def _enqueue_sac_step_data_parallel(self, stream) -> None:
         """asac_sac_step with a SUM all-reduce of each reduced gradient buffer between the backward

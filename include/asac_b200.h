@@ -296,6 +296,21 @@ int asac_sac_advance_step(const AsacSacParams *prm, void *stream);
 int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
                   const AsacSacWork *work, void *stream);
 
+/* asac_sac_step without its tail: [polyak,] target_y, q_backward, reduce_adam(q), policy_backward,
+ * reduce_adam(pi), post.  `with_polyak` = 0 when the caller has enqueued asac_sac_polyak itself
+ * (e.g. on a parallel graph branch). */
+int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
+                           const AsacSacWork *work, int with_polyak, void *stream);
+
+/* The tail of SAC_Base.train() for a prioritized run in one single-CTA kernel (batch <= 1024):
+ * alpha reduce + Adam (sac_base.py:1941-1948), _get_td_error's tail with the updated alpha
+ * (:2223-2245) -> work.y_td / work.td_error, PrioritizedReplayBuffer.update on those td errors
+ * (replay_buffer.py:412-427; cfg->td_error_min/max/per_alpha), and the global-step / optimizer
+ * counters (sac_base.py:2607).  Equals asac_sac_step's tail followed by asac_per_update. */
+int asac_sac_finish_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *work,
+                         float *nodes, int64_t capacity, const int64_t *store_ids,
+                         const int64_t *data_ids, double *per_state, void *stream);
+
 /* N(0,1) draws for eps_* (Philox4x32-10 + Box-Muller), keyed by (seed, counter[0], stream_id) */
 int asac_fill_normal(float *out, int64_t n, uint64_t seed, const int64_t *counter, int stream_id,
                      void *stream);

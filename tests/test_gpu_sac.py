@@ -331,6 +331,50 @@ def test_fused_step_equals_staged(name):
     assert torch.equal(staged.wk['y_td'], fused.wk['y_td'])
 
 
+@pytest.mark.parametrize('name', ['sac_c2.npz', 'sac_c3.npz'])
+def test_fused_tail_equals_step_plus_per_update(name):
+    """asac_sac_polyak + asac_sac_step_networks + asac_sac_finish_step (what SAC_Base.train() enqueues for
+    a prioritized run) is bit-identical to asac_sac_step followed by asac_per_update."""
+    g, m, hp, _, ref = _setup(name)
+    _, _, _, _, fused = _setup(name)
+    B, capacity = m['B'], 1024
+    rng = np.random.RandomState(3)
+    leaves = rng.rand(capacity).astype(np.float32)
+    trees, ids, states = [], [], []
+    slots = np.sort(rng.randint(0, capacity, size=B))
+    slots[1] = slots[0]  # duplicate leaf: the later sample wins
+    store = np.arange(capacity, dtype=np.int64) + 3 * capacity
+    data_ids = store[slots].copy()
+    data_ids[2] += capacity  # overwritten since it was sampled: skipped
+    for _ in range(2):
+        nodes = torch.zeros(2 * capacity, device='cuda')
+        nodes[capacity:] = torch.from_numpy(leaves).cuda()
+        assert ref.lib.asac_tree_rebuild(nodes.data_ptr(), capacity, torch.cuda.current_stream().cuda_stream) == 0
+        trees.append(nodes)
+        ids.append((torch.from_numpy(store).cuda(), torch.from_numpy(data_ids).cuda()))
+        states.append(torch.tensor([0.4, 0.001, 0., 0.], dtype=torch.float64, device='cuda'))
+    s = torch.cuda.current_stream().cuda_stream
+    for step in range(m['steps']):
+        batch, noise = golden_batch(g, step)
+        ref.step(ref.make_batch(batch, noise))
+        assert ref.lib.asac_per_update(trees[0].data_ptr(), capacity, ids[0][0].data_ptr(), ids[0][1].data_ptr(),
+                                       ref.wk['td_error'].data_ptr(), B, 0.01, 1.0, 0.9, 0, states[0].data_ptr(),
+                                       s) == 0
+        cb = fused.make_batch(batch, noise)
+        fused.polyak()
+        fused.step_networks(cb, with_polyak=0)
+        fused.finish_step(trees[1], capacity, ids[1][0], ids[1][1], states[1])
+    torch.cuda.synchronize()
+    a, b = ref.snapshot(), fused.snapshot()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert torch.equal(ref.counters, fused.counters)
+    assert torch.equal(ref.wk['td_error'], fused.wk['td_error'])
+    assert torch.equal(ref.wk['y_td'], fused.wk['y_td'])
+    assert torch.equal(trees[0], trees[1])
+    assert float(states[1][3].item()) == 0.0
+
+
 def test_large_batch_against_oracle():
     """BASELINE config-2 size (B=256, n=1) and config-3 size (B=1024, n=5) on random inputs."""
     from oracle.sac_oracle import SacBatch, SacHyper, SacNoise, SacOracle
