@@ -57,6 +57,14 @@ class AsacSacBatch(C.Structure):
                 ('eps_y', vp), ('eps_pi', vp), ('eps_alpha', vp), ('eps_td', vp)]
 
 
+class AsacWriteColumn(C.Structure):
+    _fields_ = [('ring', vp), ('rows', vp), ('row_bytes', C.c_int64)]
+
+
+class AsacWriteTable(C.Structure):
+    _fields_ = [('n_columns', C.c_int32), ('col', AsacWriteColumn * MAX_COLUMNS)]
+
+
 class AsacSacWork(C.Structure):
     _fields_ = [('n_tiles', C.c_int32),
                 ('y', vp), ('tq', vp), ('q_val', vp), ('loss_q', vp), ('grad_q_part', vp), ('grad_q', vp),
@@ -81,6 +89,7 @@ PROTOTYPES = {
     'asac_per_update': (i32, [vp, i64, vp, vp, vp, i32, f32, f32, f32, i32, vp, vp]),
     'asac_per_add': (i32, [vp, i64, vp, i64, i64, vp, i32, vp]),
     'asac_storage_write_rows': (i32, [vp, i64, i64, vp, i64, i64, vp]),
+    'asac_storage_write_table': (i32, [P(AsacWriteTable), i64, i64, i64, vp]),
     'asac_storage_gather': (i32, [P(AsacColumnTable), i64, vp, i32, i32, i32, vp, vp, vp]),
     'asac_storage_scatter': (i32, [vp, i64, vp, vp, i32, i32, i32, vp, i64, i64, vp, i64, vp]),
     'asac_sac_tile_batch': (i32, [P(AsacSacConfig)]),

@@ -45,6 +45,21 @@ __global__ void k_storage_write_rows(uint8_t *ring, int64_t capacity, int64_t fi
     lane_copy(ring + slot * row_bytes, rows + w * row_bytes, row_bytes, lane, 32);
 }
 
+// one warp per new row, all columns of the episode in one launch (rows staged column after column
+// in one device buffer by a single H2D copy)
+__global__ void k_storage_write_table(AsacWriteTable table, int64_t capacity, int64_t first_id, int64_t T) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= T) return;
+    const int64_t id = (first_id + w) % (10 * capacity);
+    const int64_t slot = id & (capacity - 1);
+    for (int c = 0; c < table.n_columns; ++c) {
+        const int64_t rb = table.col[c].row_bytes;
+        lane_copy(reinterpret_cast<uint8_t *>(table.col[c].ring) + slot * rb,
+                  reinterpret_cast<const uint8_t *>(table.col[c].rows) + w * rb, rb, lane, 32);
+    }
+}
+
 // one warp per (batch element, time step) window row
 __global__ void k_storage_gather(AsacColumnTable table, int64_t capacity, const int64_t *data_ids, int batch,
                                  int prev_n, int L, const float *padding_action, uint8_t *out_padding_mask) {
@@ -133,6 +148,19 @@ extern "C" int asac_storage_write_rows(void *ring, int64_t capacity, int64_t fir
     k_storage_write_rows<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<uint8_t *>(ring), capacity, first_id, reinterpret_cast<const uint8_t *>(rows), T, row_bytes);
     ASAC_LAUNCHED("k_storage_write_rows");
+    return ASAC_OK;
+}
+
+extern "C" int asac_storage_write_table(const AsacWriteTable *table_host, int64_t capacity, int64_t first_id,
+                                        int64_t T, void *stream) {
+    ASAC_REQUIRE(pow2(capacity), "asac_storage_write_table: capacity is not a power of two");
+    ASAC_REQUIRE(table_host && table_host->n_columns > 0 && table_host->n_columns <= ASAC_MAX_COLUMNS,
+                 "asac_storage_write_table: bad column table");
+    if (T <= 0) return ASAC_OK;
+    const int threads = 256;
+    const int64_t blocks = (T * 32 + threads - 1) / threads;
+    k_storage_write_table<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*table_host, capacity, first_id, T);
+    ASAC_LAUNCHED("k_storage_write_table");
     return ASAC_OK;
 }
 

@@ -34,6 +34,10 @@ _NP_TO_TORCH = {np.dtype('float32'): torch.float32, np.dtype('float64'): torch.f
                 np.dtype('float16'): torch.float16}
 
 
+def _align16(n: int) -> int:
+    return (n + 15) & ~15
+
+
 def _to_device(v, device) -> torch.Tensor:
     t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
     return t.to(device, non_blocking=True).contiguous()
@@ -92,6 +96,9 @@ class PrioritizedReplayBuffer:
         self._next_id = 0
         self._seed = int(np.random.SeedSequence().entropy & 0x7FFFFFFFFFFFFFFF) if seed is None else int(seed)
         self._updates = 0
+        self._stage = [None, None, None, None]  # pinned host + device staging buffers, round robin
+        self._stage_next = 0
+        self._stage_limit = 64 << 20
         self._nan_check_every = nan_check_every
         self._closed = False
 
@@ -117,7 +124,11 @@ class PrioritizedReplayBuffer:
 
     # ------------------------------------------------------------------ add
     def _store(self, transitions: dict) -> tuple[int, int]:
-        """DataStorage.add (replay_buffer.py:30-56) without the priority part -> (first_id, T)."""
+        """DataStorage.add (replay_buffer.py:30-56) without the priority part -> (first_id, T).
+
+        Host arrays take the staged path: every column of the episode is packed into one pinned
+        host buffer, crosses PCIe in ONE async copy and is written into the rings by ONE kernel
+        (asac_storage_write_table).  Device tensors are written column by column."""
         T = int(next(iter(transitions.values())).shape[0])
         if self._columns is None:
             self._allocate(transitions)
@@ -126,15 +137,52 @@ class PrioritizedReplayBuffer:
         # survive (NumPy fancy assignment keeps the last write, replay_buffer.py:48-50)
         skip = max(0, T - self.capacity)
         for k, v in transitions.items():
+            col = self._columns[k]
+            dtype = v.dtype if isinstance(v, torch.Tensor) else _NP_TO_TORCH[np.asarray(v).dtype]
+            if dtype != col.dtype or tuple(v.shape[1:]) != tuple(col.shape[1:]):
+                raise ValueError(f'column {k}: got {dtype}{tuple(v.shape[1:])}, '
+                                 f'stored {col.dtype}{tuple(col.shape[1:])}')
+        n = T - skip
+        total = sum(_align16(n * self._row_bytes(k)) for k in transitions)
+        if all(not isinstance(v, torch.Tensor) for v in transitions.values()) and \
+                len(transitions) <= _lib.MAX_COLUMNS and total <= self._stage_limit:
+            self._store_staged(transitions, first_id, skip, n, total)
+            return first_id, T
+        for k, v in transitions.items():
             src = _to_device(v[skip:] if skip else v, self.device)
             col = self._columns[k]
-            if src.dtype != col.dtype or tuple(src.shape[1:]) != tuple(col.shape[1:]):
-                raise ValueError(f'column {k}: got {src.dtype}{tuple(src.shape[1:])}, '
-                                 f'stored {col.dtype}{tuple(col.shape[1:])}')
             check(self._lib.asac_storage_write_rows(ptr(col), self.capacity, (first_id + skip) % self.max_id,
-                                                    ptr(src), T - skip, self._row_bytes(k), self._stream),
+                                                    ptr(src), n, self._row_bytes(k), self._stream),
                   'storage_write_rows')
         return first_id, T
+
+    def _store_staged(self, transitions: dict, first_id: int, skip: int, n: int, total: int) -> None:
+        slot = self._stage_next
+        self._stage_next = (slot + 1) % len(self._stage)
+        st = self._stage[slot]
+        if st is None or st['host'].numel() < total:
+            size = max(total, 1 << 16)
+            host = torch.empty(size, dtype=torch.uint8).pin_memory()
+            st = self._stage[slot] = {'host': host, 'np': host.numpy(),
+                                      'dev': torch.empty(size, dtype=torch.uint8, device=self.device),
+                                      'event': torch.cuda.Event()}
+        else:
+            st['event'].synchronize()  # the copy that last read this pinned buffer has finished
+        table = _lib.AsacWriteTable()
+        table.n_columns = len(transitions)
+        off, base = 0, st['dev'].data_ptr()
+        for i, (k, v) in enumerate(transitions.items()):
+            rb = self._row_bytes(k)
+            a = np.ascontiguousarray(v[skip:] if skip else v)
+            st['np'][off:off + n * rb] = a.reshape(-1).view(np.uint8)
+            table.col[i].ring = ptr(self._columns[k])
+            table.col[i].rows = base + off
+            table.col[i].row_bytes = rb
+            off += _align16(n * rb)
+        st['dev'][:off].copy_(st['host'][:off], non_blocking=True)
+        st['event'].record(torch.cuda.current_stream(self.device))
+        check(self._lib.asac_storage_write_table(C.byref(table), self.capacity, (first_id + skip) % self.max_id, n,
+                                                 self._stream), 'storage_write_table')
 
     def _advance(self, first_id: int, T: int) -> None:
         self._size = min(self._size + T, self.capacity)

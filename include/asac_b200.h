@@ -113,6 +113,21 @@ int asac_per_add(float *nodes, int64_t capacity, int64_t *store_ids, int64_t fir
 int asac_storage_write_rows(void *ring, int64_t capacity, int64_t first_id, const void *rows,
                             int64_t T, int64_t row_bytes, void *stream);
 
+/* DataStorage.add for every key of one episode in a single launch: the caller stages the
+ * episode's columns one after the other in ONE device buffer (one H2D copy from pinned host
+ * memory); col[c].rows points at column c's [T, row_bytes] block inside it. */
+typedef struct {
+    int32_t n_columns;
+    struct {
+        void *ring;        /* [capacity, row_bytes] */
+        const void *rows;  /* [T, row_bytes]        */
+        int64_t row_bytes;
+    } col[ASAC_MAX_COLUMNS];
+} AsacWriteTable;
+
+int asac_storage_write_table(const AsacWriteTable *table_host, int64_t capacity, int64_t first_id,
+                             int64_t T, void *stream);
+
 enum {
     ASAC_ROLE_COPY = 0,      /* obs, last_mask: copied as stored                           */
     ASAC_ROLE_INDEX = 1,     /* int32 episode index: -1 on padded rows (sac_base.py:2445)  */

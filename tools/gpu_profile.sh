@@ -10,6 +10,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 3 --warmup 3 --cpu-seconds 0.5 \
     > gpurun_out/launches_${TAG}.log 2>&1
 echo "launch list rc=$?"
+# same list without ncu's cache flush between launches (warm L2 / instruction cache)
+ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --profile-from-start off --csv \
+    --log-file gpurun_out/launches_warm_${TAG}.csv python bench.py --steps 3 --warmup 3 --cpu-seconds 0.5 \
+    > gpurun_out/launches_warm_${TAG}.log 2>&1
+echo "warm launch list rc=$?"
+if [ "${SKIP_FULL:-0}" = "1" ]; then exit 0; fi
 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:${KRE}" -c 8 \
     -f -o gpurun_out/prof_${TAG} python bench.py --steps 2 --warmup 3 --cpu-seconds 0.5 \
     > gpurun_out/prof_${TAG}.log 2>&1
