@@ -1,10 +1,20 @@
 // Row-tile MLP building blocks for the SAC update kernels (sm_100a, fp32 FFMA path).
 //
-// A CTA of NT = 128 threads owns a tile of rows whose activations live in shared memory;
-// layer weights are streamed L2 -> shared memory with cp.async (double buffered) and the
-// CTA walks the net layer by layer.  Thread mapping of the GEMM core: lane group
-// cg = tid & 15 owns columns {cg, cg+16, ...} (CM of them), row group rg = tid >> 4 owns
-// rows {2rg, 2rg+1} of each 16-row pass; operands are read as float4 along K.
+// A CTA of NT = 512 threads (16 warps, 4 per SM sub-partition) owns a tile of <= 16 rows whose
+// activations live in shared memory and walks the net layer by layer.
+//
+//   * Weights: every layer the kernel will need is a "job" of a WeightPipe.  All threads stage
+//     jobs ahead of their use with 16-byte cp.async copies into padded, bank-conflict-free rows;
+//     each thread posts a deferred arrival on the slot's mbarrier and consumers wait on the
+//     barrier's phase, so the staging of later layers overlaps the math of the current one and
+//     nobody counts cp.async groups.  Slots are recycled round robin when shared memory cannot
+//     hold all jobs.
+//   * GEMM core: thread (cg, rg, ks) = (tid & 15, (tid >> 4) & 7, tid >> 7) accumulates rows
+//     {2rg, 2rg+1} x CM columns over the ks-th quarter of K with float4 operand loads; the four
+//     K-partials meet in shared memory and the epilogue (bias, exact-erf GELU, residual) runs on
+//     all 512 threads, two outputs each.  At replay batch sizes the step is latency-bound (one
+//     16-row tile per SM): 4 warps per scheduler hide the LDS->FFMA latency that a 128-thread
+//     CTA exposed (ncu: 'short_scoreboard' on the first FFMA after the loads).
 //
 // Numerics follow the reference's torch fp32 ops: nn.Linear + exact-erf GELU + residual
 // (algorithm/nn_models/layers/linear_layers.py:46-56).  The library is compiled with
@@ -14,10 +24,19 @@
 
 namespace asac {
 
-constexpr int NT = 128;        // threads per CTA in every tiled kernel
+constexpr int NT = 512;        // threads per CTA in every tiled kernel
+constexpr int KSPLIT = 4;      // K is split over tid >> 7
 constexpr int PASS_ROWS = 16;  // rows per GEMM pass
 
 __host__ __device__ __forceinline__ int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// The layer routines below are deliberately NOT inlined: a tile kernel walks ~10 layers through
+// three or four call sites, and with everything inlined (x4 width instantiations) k_value_pass
+// grew to 18 K SASS instructions (290 KB) — the ncu source page showed > 50 % of the warp stall
+// samples in `no_instruction` (instruction-cache misses).  One copy per width keeps the hot loop
+// resident.  Pointer arguments that live in shared memory are declared to the compiler with
+// ASAC_SMEM so the out-of-line code still uses LDS/STS.
+#define ASAC_SMEM(p) __builtin_assume(__isShared(p))
 
 // ---------------------------------------------------------------- flat parameter layout
 struct NetShape {
@@ -38,63 +57,150 @@ __host__ __device__ __forceinline__ int64_t net_count(const NetShape &s) {
 }
 __host__ __device__ __forceinline__ int64_t net_stride(const NetShape &s) { return (net_count(s) + 3) & ~(int64_t)3; }
 
-// The layer routines below are deliberately NOT inlined: a tile kernel walks ~10 layers through
-// three or four call sites, and with everything inlined (x4 width instantiations) k_value_pass
-// grew to 18 K SASS instructions (290 KB) — the ncu source page showed > 50 % of the warp stall
-// samples in `no_instruction` (instruction-cache misses) with only 4 warps per SM to hide them.
-// One copy per width keeps the hot loop resident.  Pointer arguments that live in shared memory
-// are declared to the compiler with ASAC_SMEM so the out-of-line code still uses LDS/STS.
-#define ASAC_SMEM(p) __builtin_assume(__isShared(p))
-
-// ---------------------------------------------------------------- cp.async helpers
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+// ---------------------------------------------------------------- mbarrier / TMA primitives
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem)), "l"(gmem));
+}
+// the mbarrier receives one arrival when all prior cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Stage W[N][K] (row-major, global) into Ws and b[N] into bs.
-//   transpose == false : Ws[n * ldw + k], ldw = round_up(K,4) + 4, pad columns zeroed
-//   transpose == true  : Ws[k * ldw + n], ldw = N + 4   (for dX = dZ . W)
-__device__ __noinline__ void stage_weights(float *Ws, float *bs, const float *W, const float *b, int N, int K,
-                                           bool transpose) {
-    ASAC_SMEM(Ws);
+// ---------------------------------------------------------------- weight pipe
+struct WeightJob {
+    const float *W;  // [N, K] row-major (global)
+    const float *b;  // [N] or null
+    int N, K;
+};
+constexpr int MAX_WEIGHT_JOBS = 20;
+constexpr int MAX_WEIGHT_SLOTS = 16;
+
+// shared-memory row stride of a staged [N, K] matrix: K rounded to 4 plus 4 floats, so that the
+// 16-byte operand loads of 8 consecutive rows fall into distinct banks (stride = 4 mod 32 for K = 64)
+__host__ __device__ __forceinline__ int weight_ld(int K) { return round_up(K, 4) + 4; }
+__host__ __device__ __forceinline__ int weight_slot_floats(int N, int K) { return round_up(N * weight_ld(K) + N, 4); }
+
+struct WeightPipe {
+    float *slots;      // n_slots x slot_floats
+    uint64_t *bars;    // n_slots mbarriers (NT deferred arrivals each, one per thread)
+    WeightJob *jobs;   // shared-memory job table
+    int n_slots, slot_floats, n_jobs, issued, consumed;
+};
+
+// Issues every job whose slot is free; returns the new `issued`.  Executed by ALL threads at
+// CTA-uniform points, after a __syncthreads() that follows the last read of any slot being
+// recycled.  Each thread copies its share with 16-byte cp.async (LDGSTS) into the padded rows and
+// then posts one deferred arrival on the slot's mbarrier (`cp.async.mbarrier.arrive.noinc`: it
+// fires when this thread's copies have landed), so a slot is complete after NT arrivals.
+// (A first version let warp 0 issue one cp.async.bulk per weight row — 65 TMA operations per
+// layer, ~600 per kernel from a single warp — and the consumers' mbarrier wait became the largest
+// stall of k_value_pass: per-row bulk copies are too fine-grained for the TMA unit.)
+__device__ __noinline__ int pipe_fill_impl(float *slots, uint64_t *bars, const WeightJob *jobs, int n_slots,
+                                           int slot_floats, int n_jobs, int issued, int consumed) {
+    ASAC_SMEM(slots); ASAC_SMEM(jobs);
     const int tid = threadIdx.x;
-    if (!transpose) {
-        const int K4 = round_up(K, 4), ldw = K4 + 4;
-        if ((K & 3) == 0 && (((uintptr_t)W) & 15) == 0) {
-            const int per_row = K >> 2;
-            for (int i = tid; i < N * per_row; i += NT) {
+#pragma unroll 1
+    while (issued < n_jobs && issued - consumed < n_slots) {
+        const WeightJob j = jobs[issued];
+        const int slot = issued % n_slots;
+        float *Ws = slots + (int64_t)slot * slot_floats;
+        const int ldw = weight_ld(j.K);
+        float *bs = Ws + j.N * ldw;
+        if (((j.K & 3) == 0) && ((((uintptr_t)j.W) & 15) == 0)) {
+            const int per_row = j.K >> 2, total = j.N * per_row;
+#pragma unroll 1
+            for (int i = tid; i < total; i += NT) {
                 const int n = i / per_row, c = i - n * per_row;
-                cp_async16(Ws + n * ldw + 4 * c, W + (int64_t)n * K + 4 * c);
+                cp_async16(Ws + n * ldw + 4 * c, j.W + (int64_t)n * j.K + 4 * c);
             }
         } else {
-            for (int i = tid; i < N * K; i += NT) {
-                const int n = i / K, k = i - n * K;
-                cp_async4(Ws + n * ldw + k, W + i);
+            // rows that are not 16-byte multiples (e.g. K = 6): 4-byte copies, zeroed pad columns
+            const int K4 = round_up(j.K, 4), pad = K4 - j.K;
+#pragma unroll 1
+            for (int i = tid; i < j.N * j.K; i += NT) {
+                const int n = i / j.K, k = i - n * j.K;
+                cp_async4(Ws + n * ldw + k, j.W + i);
             }
-            if (K4 != K) {
-                const int padc = K4 - K;
-                for (int i = tid; i < N * padc; i += NT) Ws[(i / padc) * ldw + K + (i % padc)] = 0.f;
+#pragma unroll 1
+            for (int i = tid; i < j.N * pad; i += NT) {
+                const int n = i / pad;
+                Ws[n * ldw + j.K + (i - n * pad)] = 0.f;
             }
         }
-    } else {
-        const int ldw = N + 4;
-        for (int i = tid; i < N * K; i += NT) {
-            const int n = i / K, k = i - n * K;
-            cp_async4(Ws + k * ldw + n, W + i);
+        if (j.b) {
+#pragma unroll 1
+            for (int n = tid; n < j.N; n += NT) cp_async4(bs + n, j.b + n);
         }
+        cp_async_mbar_arrive(bars + slot);
+        ++issued;
     }
-    if (bs && b)
-        for (int i = tid; i < N; i += NT) cp_async4(bs + i, b + i);
+    return issued;
+}
+
+// all threads; `jobs` must already be written (any thread) and published by a CTA barrier
+__device__ __forceinline__ void pipe_init(WeightPipe &p, float *slots, uint64_t *bars, WeightJob *jobs, int n_slots,
+                                          int slot_floats, int n_jobs) {
+    p.slots = slots; p.bars = bars; p.jobs = jobs;
+    p.n_slots = n_slots < MAX_WEIGHT_SLOTS ? n_slots : MAX_WEIGHT_SLOTS;
+    p.slot_floats = slot_floats; p.n_jobs = n_jobs; p.issued = 0; p.consumed = 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.n_slots; ++i) mbar_init(bars + i, NT);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    p.issued = pipe_fill_impl(p.slots, p.bars, p.jobs, p.n_slots, p.slot_floats, p.n_jobs, p.issued, p.consumed);
+}
+
+// waits for the oldest unconsumed job; returns its staged weights / bias
+__device__ __forceinline__ void pipe_acquire(const WeightPipe &p, const float *&Ws, const float *&bs) {
+    const int slot = p.consumed % p.n_slots;
+    const unsigned parity = (unsigned)((p.consumed / p.n_slots) & 1);
+    mbar_wait(p.bars + slot, parity);
+    const WeightJob &j = p.jobs[p.consumed];
+    Ws = p.slots + (int64_t)slot * p.slot_floats;
+    bs = Ws + j.N * weight_ld(j.K);
+}
+// the CTA has finished reading the oldest job (a __syncthreads() must separate the reads from this
+// call); refills the freed slot
+__device__ __forceinline__ void pipe_release(WeightPipe &p) {
+    ++p.consumed;
+    if (p.issued < p.n_jobs)
+        p.issued = pipe_fill_impl(p.slots, p.bars, p.jobs, p.n_slots, p.slot_floats, p.n_jobs, p.issued, p.consumed);
 }
 
 // ---------------------------------------------------------------- activation
@@ -107,151 +213,192 @@ __device__ __forceinline__ float gelu_erf_grad(float z) {
     return cdf + z * pdf;
 }
 
-// ---------------------------------------------------------------- GEMM core
-// acc[i][c] += sum_k A[(r + i) * lda + k] * Ws[(cg + 16 c) * ldw + k],  k < K4 (multiple of 4)
-template <int CM>
-__device__ __forceinline__ void gemm_core(const float *__restrict__ A, int lda, int K4,
-                                          const float *__restrict__ Ws, int ldw, int r, int cg,
-                                          float (&acc)[2][CM]) {
-    const float *a0p = A + r * lda;
-    const float *a1p = a0p + lda;
-    const float *wp = Ws + cg * ldw;
-#pragma unroll 2
-    for (int k = 0; k < K4; k += 4) {
-        const float4 a0 = *reinterpret_cast<const float4 *>(a0p + k);
-        const float4 a1 = *reinterpret_cast<const float4 *>(a1p + k);
-#pragma unroll
-        for (int c = 0; c < CM; ++c) {
-            const float4 w = *reinterpret_cast<const float4 *>(wp + 16 * c * ldw + k);
-            acc[0][c] = fmaf(a0.x, w.x, acc[0][c]);
-            acc[1][c] = fmaf(a1.x, w.x, acc[1][c]);
-            acc[0][c] = fmaf(a0.y, w.y, acc[0][c]);
-            acc[1][c] = fmaf(a1.y, w.y, acc[1][c]);
-            acc[0][c] = fmaf(a0.z, w.z, acc[0][c]);
-            acc[1][c] = fmaf(a1.z, w.z, acc[1][c]);
-            acc[0][c] = fmaf(a0.w, w.w, acc[0][c]);
-            acc[1][c] = fmaf(a1.w, w.w, acc[1][c]);
-        }
-    }
-}
-
+// ---------------------------------------------------------------- forward layer
 // ResBlock forward over `nrows` (multiple of 16) rows:
 //   Z = X . W^T + b ;  Y = gelu(Z) (+ X when residual)        Zs may be null (no backward)
+// Ws: [H rows][ldw = K4 + 4] staged weights, `part`: KSPLIT x 16 x H floats of scratch.
 template <int CM>
 __device__ __noinline__ void layer_forward_t(const float *X, int ldx, int K4, const float *Ws, const float *bs,
-                                             float *Zs, float *Ys, int ldy, int nrows, bool residual) {
-    ASAC_SMEM(X); ASAC_SMEM(Ws); ASAC_SMEM(bs); ASAC_SMEM(Ys);
-    if (Zs) ASAC_SMEM(Zs);
-    const int tid = threadIdx.x, cg = tid & 15, rg = tid >> 4;
+                                             float *Zs, float *Ys, int ldy, int nrows, bool residual, float *part) {
+    ASAC_SMEM(X); ASAC_SMEM(Ws); ASAC_SMEM(bs); ASAC_SMEM(Ys); ASAC_SMEM(part);
+    constexpr int H = 16 * CM;
+    const int tid = threadIdx.x, cg = tid & 15, rg = (tid >> 4) & 7, ks = tid >> 7;
     const int ldw = K4 + 4;
-    for (int r0 = 0; r0 < nrows; r0 += PASS_ROWS) {
-        const int r = r0 + 2 * rg;
-        float acc[2][CM];
-#pragma unroll
-        for (int c = 0; c < CM; ++c) acc[0][c] = acc[1][c] = bs[cg + 16 * c];
-        gemm_core<CM>(X, ldx, K4, Ws, ldw, r, cg, acc);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-#pragma unroll
-            for (int c = 0; c < CM; ++c) {
-                const int j = cg + 16 * c;
-                const float z = acc[i][c];
-                if (Zs) Zs[(r + i) * ldy + j] = z;
-                float y = gelu_erf(z);
-                if (residual) y = y + X[(r + i) * ldx + j];
-                Ys[(r + i) * ldy + j] = y;
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void layer_forward(int hidden, const float *X, int ldx, int K4, const float *Ws,
-                                              const float *bs, float *Zs, float *Ys, int ldy, int nrows,
-                                              bool residual) {
-    switch (hidden >> 4) {
-        case 1: layer_forward_t<1>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual); break;
-        case 2: layer_forward_t<2>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual); break;
-        case 4: layer_forward_t<4>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual); break;
-        default: layer_forward_t<8>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual); break;
-    }
-}
-
-// dX = dZ . W (+ dY when the block was residual), W staged transposed: Wt[k * ldw + j], ldw = H + 4.
-// Output columns k < H (hidden -> hidden layers only).
-template <int CM>
-__device__ __noinline__ void layer_input_grad_t(const float *dZ, int ld, int H, const float *Wt, const float *dY,
-                                                float *dX, int nrows, bool residual) {
-    ASAC_SMEM(dZ); ASAC_SMEM(Wt); ASAC_SMEM(dY); ASAC_SMEM(dX);
-    const int tid = threadIdx.x, cg = tid & 15, rg = tid >> 4;
-    const int ldw = H + 4;
+    const int kchunk = round_up((K4 + KSPLIT - 1) / KSPLIT, 4);
+    const int kb = ks * kchunk, ke = min(K4, kb + kchunk);
+#pragma unroll 1
     for (int r0 = 0; r0 < nrows; r0 += PASS_ROWS) {
         const int r = r0 + 2 * rg;
         float acc[2][CM];
 #pragma unroll
         for (int c = 0; c < CM; ++c) acc[0][c] = acc[1][c] = 0.f;
-        gemm_core<CM>(dZ, ld, H, Wt, ldw, r, cg, acc);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        const float *a0p = X + r * ldx, *a1p = a0p + ldx, *wp = Ws + cg * ldw;
+#pragma unroll 4
+        for (int k = kb; k < ke; k += 4) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(a0p + k);
+            const float4 a1 = *reinterpret_cast<const float4 *>(a1p + k);
 #pragma unroll
             for (int c = 0; c < CM; ++c) {
-                const int k = cg + 16 * c;
-                float v = acc[i][c];
-                if (residual) v = v + dY[(r + i) * ld + k];
-                dX[(r + i) * ld + k] = v;
+                const float4 w = *reinterpret_cast<const float4 *>(wp + 16 * c * ldw + k);
+                acc[0][c] = fmaf(a0.x, w.x, acc[0][c]);
+                acc[1][c] = fmaf(a1.x, w.x, acc[1][c]);
+                acc[0][c] = fmaf(a0.y, w.y, acc[0][c]);
+                acc[1][c] = fmaf(a1.y, w.y, acc[1][c]);
+                acc[0][c] = fmaf(a0.z, w.z, acc[0][c]);
+                acc[1][c] = fmaf(a1.z, w.z, acc[1][c]);
+                acc[0][c] = fmaf(a0.w, w.w, acc[0][c]);
+                acc[1][c] = fmaf(a1.w, w.w, acc[1][c]);
             }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int c = 0; c < CM; ++c) part[(ks * PASS_ROWS + 2 * rg + i) * H + cg + 16 * c] = acc[i][c];
+        __syncthreads();
+#pragma unroll 1
+        for (int o = tid; o < PASS_ROWS * H; o += NT) {
+            const int row = o / H, j = o - row * H;
+            float z = bs[j];
+#pragma unroll
+            for (int s = 0; s < KSPLIT; ++s) z += part[s * PASS_ROWS * H + o];
+            if (Zs) Zs[(r0 + row) * ldy + j] = z;
+            float y = gelu_erf(z);
+            if (residual) y = y + X[(r0 + row) * ldx + j];
+            Ys[(r0 + row) * ldy + j] = y;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void layer_forward(int hidden, const float *X, int ldx, int K4, const float *Ws,
+                                              const float *bs, float *Zs, float *Ys, int ldy, int nrows,
+                                              bool residual, float *part) {
+    switch (hidden >> 4) {
+        case 1: layer_forward_t<1>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+        case 2: layer_forward_t<2>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+        case 4: layer_forward_t<4>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+        default: layer_forward_t<8>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+    }
+}
+
+// ---------------------------------------------------------------- input gradient
+template <int CM>
+__device__ __forceinline__ void load_cm(const float *p, float (&w)[CM]) {
+    if constexpr (CM == 1) {
+        w[0] = p[0];
+    } else if constexpr (CM == 2) {
+        const float2 v = *reinterpret_cast<const float2 *>(p);
+        w[0] = v.x; w[1] = v.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < CM / 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(p + 4 * q);
+            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
         }
     }
 }
 
-__device__ __forceinline__ void layer_input_grad(int hidden, const float *dZ, int ld, const float *Wt,
-                                                 const float *dY, float *dX, int nrows, bool residual) {
+// dX = dZ . W (+ dY when the block was residual) for a hidden -> hidden layer, 16 rows.
+// W is the forward staging (Ws[j * ldw + k], ldw = H + 4): thread (cg, rg, ks) owns the CM
+// consecutive columns k = CM*cg.. of rows {2rg, 2rg+1} over the ks-th quarter of j.
+template <int CM>
+__device__ __noinline__ void layer_input_grad_t(const float *dZ, int ld, const float *Ws, const float *dY, float *dX,
+                                                bool residual, float *part) {
+    ASAC_SMEM(dZ); ASAC_SMEM(Ws); ASAC_SMEM(dY); ASAC_SMEM(dX); ASAC_SMEM(part);
+    constexpr int H = 16 * CM;
+    const int tid = threadIdx.x, cg = tid & 15, rg = (tid >> 4) & 7, ks = tid >> 7;
+    const int ldw = H + 4;
+    const int jb = ks * (H / KSPLIT), je = jb + H / KSPLIT;
+    const int r = 2 * rg;
+    float acc[2][CM];
+#pragma unroll
+    for (int c = 0; c < CM; ++c) acc[0][c] = acc[1][c] = 0.f;
+#pragma unroll
+    for (int j = jb; j < je; j += 4) {
+        const float4 d0 = *reinterpret_cast<const float4 *>(dZ + r * ld + j);
+        const float4 d1 = *reinterpret_cast<const float4 *>(dZ + (r + 1) * ld + j);
+        const float d0v[4] = {d0.x, d0.y, d0.z, d0.w}, d1v[4] = {d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            float w[CM];
+            load_cm<CM>(Ws + (j + jj) * ldw + CM * cg, w);
+#pragma unroll
+            for (int c = 0; c < CM; ++c) {
+                acc[0][c] = fmaf(d0v[jj], w[c], acc[0][c]);
+                acc[1][c] = fmaf(d1v[jj], w[c], acc[1][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < CM; ++c) part[(ks * PASS_ROWS + r + i) * H + CM * cg + c] = acc[i][c];
+    __syncthreads();
+#pragma unroll 1
+    for (int o = tid; o < PASS_ROWS * H; o += NT) {
+        const int row = o / H, k = o - row * H;
+        float v = part[o];
+#pragma unroll
+        for (int s = 1; s < KSPLIT; ++s) v += part[s * PASS_ROWS * H + o];
+        if (residual) v = v + dY[row * ld + k];
+        dX[row * ld + k] = v;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void layer_input_grad(int hidden, const float *dZ, int ld, const float *Ws,
+                                                 const float *dY, float *dX, bool residual, float *part) {
     switch (hidden >> 4) {
-        case 1: layer_input_grad_t<1>(dZ, ld, hidden, Wt, dY, dX, nrows, residual); break;
-        case 2: layer_input_grad_t<2>(dZ, ld, hidden, Wt, dY, dX, nrows, residual); break;
-        case 4: layer_input_grad_t<4>(dZ, ld, hidden, Wt, dY, dX, nrows, residual); break;
-        default: layer_input_grad_t<8>(dZ, ld, hidden, Wt, dY, dX, nrows, residual); break;
+        case 1: layer_input_grad_t<1>(dZ, ld, Ws, dY, dX, residual, part); break;
+        case 2: layer_input_grad_t<2>(dZ, ld, Ws, dY, dX, residual, part); break;
+        case 4: layer_input_grad_t<4>(dZ, ld, Ws, dY, dX, residual, part); break;
+        default: layer_input_grad_t<8>(dZ, ld, Ws, dY, dX, residual, part); break;
     }
 }
 
-// dZ = dY * gelu'(Z)   (in place over dY), rows beyond `valid_rows` are zeroed
-__device__ __forceinline__ void gelu_backward(float *dY, const float *Z, int ld, int H, int nrows, int valid_rows) {
-    for (int i = threadIdx.x; i < nrows * H; i += NT) {
-        const int r = i / H, j = i - r * H;
-        const float g = dY[r * ld + j];
-        dY[r * ld + j] = r < valid_rows ? g * gelu_erf_grad(Z[r * ld + j]) : 0.f;
+// dZ = dY * gelu'(Z) over 16 rows (H a power of two); rows >= valid_rows are zeroed
+__device__ __noinline__ void gelu_backward(const float *dY, const float *Z, float *dZ, int ld, int H, int valid_rows) {
+    ASAC_SMEM(dY); ASAC_SMEM(Z); ASAC_SMEM(dZ);
+    const int sh = 31 - __clz(H);
+#pragma unroll 1
+    for (int i = threadIdx.x; i < PASS_ROWS * H; i += NT) {
+        const int r = i >> sh, j = i & (H - 1);
+        dZ[r * ld + j] = r < valid_rows ? dY[r * ld + j] * gelu_erf_grad(Z[r * ld + j]) : 0.f;
     }
 }
 
 // Partial weight / bias gradient of one layer over the tile's rows:
 //   gW[j * K + k] = sum_r dZ[r][j] * X[r][k],  gb[j] = sum_r dZ[r][j]
-// 4x4 output blocks, one float4 of dZ and one of X per row.
+// 2 x 4 output blocks, consecutive threads along k (coalesced 16-byte stores).
 __device__ __noinline__ void layer_weight_grad(const float *dZ, int ldz, const float *X, int ldx, int H, int K,
                                                int nrows, float *gW, float *gb) {
     ASAC_SMEM(dZ); ASAC_SMEM(X);
     const int tid = threadIdx.x;
     const int K4 = round_up(K, 4);
-    const int nJB = H >> 2, nKB = K4 >> 2;
+    const int nJB = H >> 1, nKB = K4 >> 2;
     const bool vec = ((K & 3) == 0) && ((((uintptr_t)gW) & 15) == 0);
+#pragma unroll 1
     for (int blk = tid; blk < nJB * nKB; blk += NT) {
-        const int jb = blk % nJB, kb = blk / nJB;
-        float acc[4][4];
+        const int jb = blk / nKB, kb = blk - jb * nKB;
+        float acc[2][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
         for (int r = 0; r < nrows; ++r) {
-            const float4 dz = *reinterpret_cast<const float4 *>(dZ + r * ldz + 4 * jb);
+            const float2 dz = *reinterpret_cast<const float2 *>(dZ + r * ldz + 2 * jb);
             const float4 x = *reinterpret_cast<const float4 *>(X + r * ldx + 4 * kb);
-            const float dzv[4] = {dz.x, dz.y, dz.z, dz.w};
+            const float dzv[2] = {dz.x, dz.y};
             const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dzv[a], xv[b], acc[a][b]);
         }
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            float *dst = gW + (int64_t)(4 * jb + a) * K + 4 * kb;
+        for (int a = 0; a < 2; ++a) {
+            float *dst = gW + (int64_t)(2 * jb + a) * K + 4 * kb;
             if (vec) {
                 *reinterpret_cast<float4 *>(dst) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
             } else {
@@ -269,11 +416,12 @@ __device__ __noinline__ void layer_weight_grad(const float *dZ, int ldz, const f
 }
 
 // Linear head: out[r * O + o] = X[r] . Wh[o] + bh[o]   (Wh, bh in global memory, 8 lanes per dot)
-__device__ __noinline__ void head_forward(const float *X, int ldx, int H, const float *Wh, const float *bh,
-                                          int O, int nrows, float *out) {
+__device__ __noinline__ void head_forward(const float *X, int ldx, int H, const float *Wh, const float *bh, int O,
+                                          int nrows, float *out) {
     ASAC_SMEM(X); ASAC_SMEM(out);
     const int tid = threadIdx.x, grp = tid >> 3, sub = tid & 7;
     const int total = nrows * O;
+#pragma unroll 1
     for (int d0 = 0; d0 < total; d0 += NT / 8) {
         const int d = d0 + grp;
         float s = 0.f;
@@ -292,13 +440,13 @@ __device__ __noinline__ void head_forward(const float *X, int ldx, int H, const 
 
 // Head backward.  dO[r * O + o] (rows >= valid rows must be zero):
 //   gWh[o * H + j] = sum_r dO[r][o] X[r][j];  gbh[o] = sum_r dO[r][o];  dH[r][j] = sum_o dO[r][o] Wh[o][j]
-__device__ __noinline__ void head_backward(const float *dO, int O, const float *X, int ldx, int H,
-                                           const float *Wh, int nrows, float *gWh, float *gbh, float *dH,
-                                           int ldh) {
+__device__ __noinline__ void head_backward(const float *dO, int O, const float *X, int ldx, int H, const float *Wh,
+                                           int nrows, float *gWh, float *gbh, float *dH, int ldh) {
     ASAC_SMEM(dO); ASAC_SMEM(dH);
     if (X) ASAC_SMEM(X);
     const int tid = threadIdx.x;
     if (gWh) {
+#pragma unroll 1
         for (int i = tid; i < O * H; i += NT) {
             const int o = i / H, j = i - o * H;
             float s = 0.f;
@@ -311,6 +459,7 @@ __device__ __noinline__ void head_backward(const float *dO, int O, const float *
             gbh[o] = s;
         }
     }
+#pragma unroll 1
     for (int i = tid; i < nrows * H; i += NT) {
         const int r = i / H, j = i - r * H;
         float s = 0.f;
@@ -320,49 +469,47 @@ __device__ __noinline__ void head_backward(const float *dO, int O, const float *
 }
 
 // ---------------------------------------------------------------- whole-net forward
-// Shared-memory plan of a tile kernel (all sizes in floats):
-//   act buffers : nrows * lda each, lda = max(H, round_up(in,4)) + 4
-//   weight ring : 2 x wsz, wsz = H * (max(H, round_up(in,4)) + 4) + H
-struct TileSmem {
-    float *w[2];   // weight ring
-    float *bias[2];
-};
-
 __host__ __device__ __forceinline__ int tile_lda(int hidden, int in_dim) {
     const int k4 = round_up(in_dim, 4);
     return (hidden > k4 ? hidden : k4) + 4;
 }
 __host__ __device__ __forceinline__ int tile_wsz(int hidden, int in_dim) {
-    return hidden * tile_lda(hidden, in_dim) + hidden;
+    const int a = weight_slot_floats(hidden, in_dim), b = weight_slot_floats(hidden, hidden);
+    return a > b ? a : b;
+}
+__host__ __device__ __forceinline__ int tile_part_floats(int hidden) { return KSPLIT * PASS_ROWS * hidden; }
+
+// appends the `depth` trunk layers of a stock net to a job table (forward order)
+__device__ __forceinline__ int push_trunk_jobs(WeightJob *jobs, int n, const NetShape &s, const float *params) {
+    for (int l = 0; l < s.depth; ++l)
+        jobs[n++] = WeightJob{params + net_w_off(s, l), params + net_b_off(s, l), s.hidden, net_k(s, l)};
+    return n;
+}
+// appends layers depth-1 .. 1 (the input-gradient passes of a backward walk; no bias needed)
+__device__ __forceinline__ int push_trunk_jobs_reverse(WeightJob *jobs, int n, const NetShape &s, const float *params) {
+    for (int l = s.depth - 1; l >= 1; --l)
+        jobs[n++] = WeightJob{params + net_w_off(s, l), nullptr, s.hidden, s.hidden};
+    return n;
 }
 
 // Runs the `depth` ResBlocks of a stock net over rows held in `x0` (nrows x lda, input columns
-// [0, in_dim) valid, pad columns up to round_up(in,4) zero).
+// [0, in_dim) valid, pad columns up to round_up(in,4) zero); the pipe's next `depth` jobs must be
+// this net's trunk layers in forward order.
 //   save == nullptr : ping-pongs between bufA and bufB, returns the buffer holding the output
 //   save != nullptr : layer l reads save_x[l] and writes z to save_z[l], y to save_x[l+1]
-// The caller must have issued no outstanding cp.async groups.
-__device__ __forceinline__ float *net_trunk_forward(const NetShape &s, const float *params, const TileSmem &sm,
-                                                    float *x0, float *bufA, float *bufB, float **save_x,
-                                                    float **save_z, int lda, int nrows) {
+__device__ __forceinline__ float *net_trunk_forward(const NetShape &s, WeightPipe &pipe, float *x0, float *bufA,
+                                                    float *bufB, float **save_x, float **save_z, int lda, int nrows,
+                                                    float *part) {
     const int H = s.hidden;
-    stage_weights(sm.w[0], sm.bias[0], params + net_w_off(s, 0), params + net_b_off(s, 0), H, s.in_dim, false);
-    cp_async_commit();
     float *x = x0;
+#pragma unroll 1
     for (int l = 0; l < s.depth; ++l) {
-        if (l + 1 < s.depth) {
-            stage_weights(sm.w[(l + 1) & 1], sm.bias[(l + 1) & 1], params + net_w_off(s, l + 1),
-                          params + net_b_off(s, l + 1), H, H, false);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
+        const float *Ws, *bs;
+        pipe_acquire(pipe, Ws, bs);
         const int K = net_k(s, l);
         float *y = save_x ? save_x[l + 1] : (x == bufA ? bufB : bufA);
-        layer_forward(H, x, lda, round_up(K, 4), sm.w[l & 1], sm.bias[l & 1], save_z ? save_z[l] : nullptr, y, lda,
-                      nrows, K == H);
-        __syncthreads();
+        layer_forward(H, x, lda, round_up(K, 4), Ws, bs, save_z ? save_z[l] : nullptr, y, lda, nrows, K == H, part);
+        pipe_release(pipe);  // layer_forward ends with a CTA barrier
         x = y;
     }
     return x;

@@ -40,6 +40,19 @@ __host__ __device__ __forceinline__ int sac_wsz(const AsacSacConfig &c) {
     const int a = tile_wsz(c.q_hidden, c.state_size + c.action_size), b = tile_wsz(c.pi_hidden, c.state_size);
     return round_up(a > b ? a : b, 4);
 }
+__host__ __device__ __forceinline__ int sac_part(const AsacSacConfig &c) {
+    return tile_part_floats(c.q_hidden > c.pi_hidden ? c.q_hidden : c.pi_hidden);
+}
+// floats reserved in front of the weight slots for the job table and the slot mbarriers
+constexpr int PIPE_HEADER_FLOATS = (MAX_WEIGHT_JOBS * (int)sizeof(WeightJob) + MAX_WEIGHT_SLOTS * 8 + 15) / 16 * 4;
+constexpr int kSmemBudgetFloats = 227 * 1024 / 4;
+// weight slots that fit behind `fixed` floats of other shared memory (at least 2, at most n_jobs)
+__host__ __device__ __forceinline__ int slots_that_fit(int fixed, int slot_floats, int n_jobs) {
+    int n = (kSmemBudgetFloats - fixed) / slot_floats;
+    if (n > n_jobs) n = n_jobs;
+    if (n > MAX_WEIGHT_SLOTS) n = MAX_WEIGHT_SLOTS;
+    return n < 2 ? 2 : n;
+}
 
 constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
 
@@ -65,6 +78,7 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     float s = 0.f;
+#pragma unroll
     for (int w = 0; w < NT / 32; ++w) s += red[w];
     return s;
 }
@@ -72,7 +86,9 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
 // ------------------------------------------------------------------------------------ smem plans
 struct ValuePlan {
     int lda, wsz, rows_max;  // rows_max: multiple of 16
-    int off_xin, off_a, off_b, off_w0, off_w1, off_ho, off_xs, off_logp, off_qmin, off_ratio, off_qs, off_red;
+    int off_xin, off_a, off_b, off_ho, off_xs, off_logp, off_qmin, off_ratio, off_qs, off_red, off_part, off_pipe,
+        off_slots;
+    int n_jobs, n_slots;
     int total;  // floats
 };
 __host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c, int TB, int mode) {
@@ -89,22 +105,27 @@ __host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c,
     p.off_xin = o; o += p.rows_max * p.lda;
     p.off_a = o; o += p.rows_max * p.lda;
     p.off_b = o; o += p.rows_max * p.lda;
-    p.off_w0 = o; o += p.wsz;
-    p.off_w1 = o; o += p.wsz;
     p.off_ho = o; o += round_up(rp * 2 * A, 4);
     p.off_xs = o; o += round_up(TB * (n + 1) * A, 4);
     p.off_logp = o; o += round_up(TB * (n + 1), 4);
     p.off_qmin = o; o += round_up(p.rows_max, 4);
     p.off_ratio = o; o += round_up(TB * (n > 0 ? n : 1), 4);
     p.off_qs = o; o += round_up(c.ensemble * TB, 4);
-    p.off_red = o; o += 8;
+    p.off_red = o; o += 32;
+    p.off_part = o; o += sac_part(c);
+    p.off_pipe = o; o += PIPE_HEADER_FLOATS;
+    p.off_slots = o;
+    p.n_jobs = c.pi_depth + c.q_depth + (mode == 1 ? c.q_depth : 0);
+    p.n_slots = slots_that_fit(o, p.wsz, p.n_jobs);
+    o += p.n_slots * p.wsz;
     p.total = o;
     return p;
 }
 
 struct GradPlan {
     int lda, wsz;
-    int off_px, off_pz, off_qz, off_qin, off_g0, off_g1, off_g2, off_w0, off_w1, off_small, off_red;
+    int off_px, off_pz, off_qz, off_qin, off_g0, off_g1, off_g2, off_small, off_red, off_part, off_pipe, off_slots;
+    int n_jobs, n_slots;
     int total;
 };
 // critic: px/pz hold the critic's activations, qz unused.  policy: px/pz policy, qz critics' z.
@@ -122,10 +143,16 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
     p.off_g0 = o; o += rows * p.lda;
     p.off_g1 = o; o += rows * p.lda;
     p.off_g2 = o; o += rows * p.lda;
-    p.off_w0 = o; o += p.wsz;
-    p.off_w1 = o; o += p.wsz;
     p.off_small = o; o += round_up(rows * (6 * c.action_size + c.ensemble + 4), 4);
-    p.off_red = o; o += 8;
+    p.off_red = o; o += 32;
+    p.off_part = o; o += sac_part(c);
+    p.off_pipe = o; o += PIPE_HEADER_FLOATS;
+    p.off_slots = o;
+    // critic kernel: forward + reverse walk of one critic; policy kernel: policy forward, critic forward,
+    // critic reverse, policy reverse (the last only on cluster rank 0, the plan reserves for it anyway)
+    p.n_jobs = policy ? (c.pi_depth + c.q_depth + (c.q_depth - 1) + (c.pi_depth - 1)) : (c.q_depth + c.q_depth - 1);
+    p.n_slots = slots_that_fit(o, p.wsz, p.n_jobs);
+    o += p.n_slots * p.wsz;
     p.total = o;
     return p;
 }
@@ -160,12 +187,22 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     const int lda = pl.lda;
     float *xin = sm + pl.off_xin, *bufA = sm + pl.off_a, *bufB = sm + pl.off_b;
     float *ho = sm + pl.off_ho, *xs = sm + pl.off_xs, *logp = sm + pl.off_logp, *qmin = sm + pl.off_qmin;
-    float *ratio = sm + pl.off_ratio, *qs = sm + pl.off_qs, *red = sm + pl.off_red;
-    TileSmem ts;
-    ts.w[0] = sm + pl.off_w0; ts.w[1] = sm + pl.off_w1;
+    float *ratio = sm + pl.off_ratio, *qs = sm + pl.off_qs, *red = sm + pl.off_red, *part = sm + pl.off_part;
 
     const NetShape ps = pi_shape(c), qsh = q_shape(c);
     const int64_t q_stride = net_stride(qsh);
+
+    // ---- weight pipe: policy trunk, target critic `net`, (post) online critic `net`
+    WeightJob *jobs = reinterpret_cast<WeightJob *>(sm + pl.off_pipe);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(jobs + MAX_WEIGHT_JOBS);
+    if (tid == 0) {
+        int nj = push_trunk_jobs(jobs, 0, ps, a.prm.pi);
+        nj = push_trunk_jobs(jobs, nj, qsh, a.prm.q_target + net * q_stride);
+        if (post) nj = push_trunk_jobs(jobs, nj, qsh, a.prm.q + net * q_stride);
+    }
+    __syncthreads();
+    WeightPipe pipe;
+    pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
 
     // ---- policy over the P rows
     {
@@ -180,9 +217,8 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
             }
             xin[r * lda + col] = v;
         }
-        ts.bias[0] = ts.w[0] + ps.hidden * tile_lda(ps.hidden, ps.in_dim);
-        ts.bias[1] = ts.w[1] + ps.hidden * tile_lda(ps.hidden, ps.in_dim);
-        float *h = net_trunk_forward(ps, a.prm.pi, ts, xin, bufA, bufB, nullptr, nullptr, lda, RPp);
+        __syncthreads();
+        float *h = net_trunk_forward(ps, pipe, xin, bufA, bufB, nullptr, nullptr, lda, RPp, part);
         head_forward(h, lda, ps.hidden, a.prm.pi + net_w_off(ps, ps.depth), a.prm.pi + net_b_off(ps, ps.depth),
                      2 * A, RP, ho);
         __syncthreads();
@@ -279,8 +315,6 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         }
         xin[r * lda + col] = v;
     }
-    ts.bias[0] = ts.w[0] + qsh.hidden * tile_lda(qsh.hidden, qsh.in_dim);
-    ts.bias[1] = ts.w[1] + qsh.hidden * tile_lda(qsh.hidden, qsh.in_dim);
     __syncthreads();
 
     // ---- target critic `net` over the V rows (+ S rows for the clipped loss)
@@ -288,7 +322,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         const int rq = need_tq ? RV + RS : RV;
         const int rqp = round_up(rq, PASS_ROWS);
         const float *prm = a.prm.q_target + net * q_stride;
-        float *h = net_trunk_forward(qsh, prm, ts, xin, bufA, bufB, nullptr, nullptr, lda, rqp);
+        float *h = net_trunk_forward(qsh, pipe, xin, bufA, bufB, nullptr, nullptr, lda, rqp, part);
         float *qo = (h == bufA ? bufB : bufA);  // free buffer: head outputs [rq]
         head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, rq, qo);
         __syncthreads();
@@ -301,8 +335,8 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     // ---- post: online critic `net` over the S rows (sac_base.py:2211-2216)
     if (post) {
         const float *prm = a.prm.q + net * q_stride;
-        float *h = net_trunk_forward(qsh, prm, ts, xin + s_row0 * lda, bufA, bufB, nullptr, nullptr, lda,
-                                     round_up(RS, PASS_ROWS));
+        float *h = net_trunk_forward(qsh, pipe, xin + s_row0 * lda, bufA, bufB, nullptr, nullptr, lda,
+                                     round_up(RS, PASS_ROWS), part);
         head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, RS, qs);
         __syncthreads();
     }
@@ -405,11 +439,16 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
     for (int l = 0; l <= d; ++l) px[l] = sm + pl.off_px + l * R * lda;
     for (int l = 0; l < d; ++l) pz[l] = sm + pl.off_pz + l * R * lda;
     float *g[3] = {sm + pl.off_g0, sm + pl.off_g1, sm + pl.off_g2};
-    float *qout = sm + pl.off_small, *dq = qout + R, *red = sm + pl.off_red;
-    TileSmem ts;
-    ts.w[0] = sm + pl.off_w0; ts.w[1] = sm + pl.off_w1;
-    ts.bias[0] = ts.w[0] + H * tile_lda(H, qsh.in_dim);
-    ts.bias[1] = ts.w[1] + H * tile_lda(H, qsh.in_dim);
+    float *qout = sm + pl.off_small, *dq = qout + R, *red = sm + pl.off_red, *part = sm + pl.off_part;
+    WeightJob *jobs = reinterpret_cast<WeightJob *>(sm + pl.off_pipe);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(jobs + MAX_WEIGHT_JOBS);
+    if (tid == 0) {
+        const int nj = push_trunk_jobs(jobs, 0, qsh, prm);
+        push_trunk_jobs_reverse(jobs, nj, qsh, prm);
+    }
+    __syncthreads();
+    WeightPipe pipe;
+    pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
 
     const int K0 = S + A, K04 = round_up(K0, 4);
     for (int i = tid; i < R * K04; i += NT) {
@@ -421,7 +460,8 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
         }
         px[0][r * lda + col] = v;
     }
-    net_trunk_forward(qsh, prm, ts, px[0], nullptr, nullptr, px, pz, lda, R);
+    __syncthreads();
+    net_trunk_forward(qsh, pipe, px[0], nullptr, nullptr, px, pz, lda, R, part);
     head_forward(px[d], lda, H, prm + net_w_off(qsh, d), prm + net_b_off(qsh, d), 1, TBa, qout);
     __syncthreads();
 
@@ -460,24 +500,19 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
     head_backward(dq, 1, px[d], lda, H, prm + net_w_off(qsh, d), R, gout + net_w_off(qsh, d),
                   gout + net_b_off(qsh, d), g[0], lda);
     int cur = 0;
+#pragma unroll 1
     for (int l = d - 1; l >= 0; --l) {
         const int K = net_k(qsh, l);
-        if (l > 0) {
-            stage_weights(ts.w[l & 1], nullptr, prm + net_w_off(qsh, l), nullptr, H, H, true);
-            cp_async_commit();
-        }
         __syncthreads();
         float *dY = g[cur], *dZ = g[(cur + 1) % 3], *dX = g[(cur + 2) % 3];
-        for (int i = tid; i < R * H; i += NT) {
-            const int r = i / H, j = i - r * H;
-            dZ[r * lda + j] = r < TBa ? dY[r * lda + j] * gelu_erf_grad(pz[l][r * lda + j]) : 0.f;
-        }
+        gelu_backward(dY, pz[l], dZ, lda, H, TBa);
         __syncthreads();
         layer_weight_grad(dZ, lda, px[l], lda, H, K, TBa, gout + net_w_off(qsh, l), gout + net_b_off(qsh, l));
         if (l > 0) {
-            cp_async_wait<0>();
-            __syncthreads();
-            layer_input_grad(H, dZ, lda, ts.w[l & 1], dY, dX, R, true);
+            const float *Ws, *bs;
+            pipe_acquire(pipe, Ws, bs);
+            layer_input_grad(H, dZ, lda, Ws, dY, dX, true, part);  // ends with a CTA barrier
+            pipe_release(pipe);
             cur = (cur + 2) % 3;
         }
     }
@@ -511,9 +546,21 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     // small: ho[R][2A] (m,s -> mu,sigma), xs[R][A], da[R][A], qv[E][R], dq[R], amin[R]
     float *ho = sm + pl.off_small, *xs = ho + R * 2 * A, *da = xs + R * A, *qv = da + R * A, *dq = qv + E * R;
     float *amin = dq + R, *dO = amin + R;  // dO aliases nothing: sized below
-    float *red = sm + pl.off_red;
-    TileSmem ts;
-    ts.w[0] = sm + pl.off_w0; ts.w[1] = sm + pl.off_w1;
+    float *red = sm + pl.off_red, *part = sm + pl.off_part;
+    WeightJob *jobs = reinterpret_cast<WeightJob *>(sm + pl.off_pipe);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(jobs + MAX_WEIGHT_JOBS);
+    const float *q_prm = a.prm.q + net * q_stride;
+    // ranks != 0 leave before the policy backward: they must not have its weights in flight at exit
+    const int n_jobs = pl.n_jobs - (net == 0 ? 0 : dp - 1);
+    if (tid == 0) {
+        int nj = push_trunk_jobs(jobs, 0, ps, a.prm.pi);
+        nj = push_trunk_jobs(jobs, nj, qsh, q_prm);
+        nj = push_trunk_jobs_reverse(jobs, nj, qsh, q_prm);
+        if (net == 0) nj = push_trunk_jobs_reverse(jobs, nj, ps, a.prm.pi);
+    }
+    __syncthreads();
+    WeightPipe pipe;
+    pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, n_jobs);
 
     // ---- policy forward (saved)
     const int S4 = round_up(S, 4);
@@ -521,9 +568,8 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         const int r = i / S4, col = i - r * S4;
         px[0][r * lda + col] = (r < TBa && col < S) ? a.bat.states[((int64_t)(e0 + r) * L + b) * S + col] : 0.f;
     }
-    ts.bias[0] = ts.w[0] + Hp * tile_lda(Hp, ps.in_dim);
-    ts.bias[1] = ts.w[1] + Hp * tile_lda(Hp, ps.in_dim);
-    net_trunk_forward(ps, a.prm.pi, ts, px[0], nullptr, nullptr, px, pz, lda, R);
+    __syncthreads();
+    net_trunk_forward(ps, pipe, px[0], nullptr, nullptr, px, pz, lda, R, part);
     head_forward(px[dp], lda, Hp, a.prm.pi + net_w_off(ps, dp), a.prm.pi + net_b_off(ps, dp), 2 * A, TBa, ho);
     __syncthreads();
 
@@ -546,8 +592,6 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         qin[r * lda + col] = v;
     }
     for (int i = tid; i < R * A; i += NT) da[i] = 0.f;
-    ts.bias[0] = ts.w[0] + Hq * tile_lda(Hq, qsh.in_dim);
-    ts.bias[1] = ts.w[1] + Hq * tile_lda(Hq, qsh.in_dim);
     __syncthreads();
 
     // ---- own critic forward (z saved), then the other members' values over DSMEM
@@ -555,7 +599,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         const float *prm = a.prm.q + net * q_stride;
         float *qz[ASAC_MAX_DEPTH];
         for (int l = 0; l < dqn; ++l) qz[l] = sm + pl.off_qz + l * R * lda;
-        float *h = net_trunk_forward(qsh, prm, ts, qin, g[0], g[1], nullptr, qz, lda, R);
+        float *h = net_trunk_forward(qsh, pipe, qin, g[0], g[1], nullptr, qz, lda, R, part);
         head_forward(h, lda, Hq, prm + net_w_off(qsh, dqn), prm + net_b_off(qsh, dqn), 1, TBa, qv + net * R);
         __syncthreads();
     }
@@ -585,23 +629,17 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         __syncthreads();
         head_backward(dq, 1, nullptr, lda, Hq, prm + net_w_off(qsh, dqn), R, nullptr, nullptr, g[0], lda);
         int cur = 0;
+#pragma unroll 1
         for (int l = dqn - 1; l >= 0; --l) {
-            if (l > 0) {
-                stage_weights(ts.w[l & 1], nullptr, prm + net_w_off(qsh, l), nullptr, Hq, Hq, true);
-                cp_async_commit();
-            }
             __syncthreads();
             float *dY = g[cur], *dZ = g[(cur + 1) % 3], *dX = g[(cur + 2) % 3];
-            const float *z = sm + pl.off_qz + l * R * lda;
-            for (int t = tid; t < R * Hq; t += NT) {
-                const int r = t / Hq, j = t - r * Hq;
-                dZ[r * lda + j] = r < TBa ? dY[r * lda + j] * gelu_erf_grad(z[r * lda + j]) : 0.f;
-            }
+            gelu_backward(dY, sm + pl.off_qz + l * R * lda, dZ, lda, Hq, TBa);
             __syncthreads();
             if (l > 0) {
-                cp_async_wait<0>();
-                __syncthreads();
-                layer_input_grad(Hq, dZ, lda, ts.w[l & 1], dY, dX, R, true);
+                const float *Ws, *bs;
+                pipe_acquire(pipe, Ws, bs);
+                layer_input_grad(Hq, dZ, lda, Ws, dY, dX, true, part);  // ends with a CTA barrier
+                pipe_release(pipe);
                 cur = (cur + 2) % 3;
             } else {
                 // first layer: only the action columns of the input gradient are needed
@@ -672,24 +710,19 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     head_backward(dO, 2 * A, px[dp], lda, Hp, a.prm.pi + net_w_off(ps, dp), R, gout + net_w_off(ps, dp),
                   gout + net_b_off(ps, dp), g[0], lda);
     int cur = 0;
+#pragma unroll 1
     for (int l = dp - 1; l >= 0; --l) {
         const int K = net_k(ps, l);
-        if (l > 0) {
-            stage_weights(ts.w[l & 1], nullptr, a.prm.pi + net_w_off(ps, l), nullptr, Hp, Hp, true);
-            cp_async_commit();
-        }
         __syncthreads();
         float *dY = g[cur], *dZ = g[(cur + 1) % 3], *dX = g[(cur + 2) % 3];
-        for (int t = tid; t < R * Hp; t += NT) {
-            const int r = t / Hp, j = t - r * Hp;
-            dZ[r * lda + j] = r < TBa ? dY[r * lda + j] * gelu_erf_grad(pz[l][r * lda + j]) : 0.f;
-        }
+        gelu_backward(dY, pz[l], dZ, lda, Hp, TBa);
         __syncthreads();
         layer_weight_grad(dZ, lda, px[l], lda, Hp, K, TBa, gout + net_w_off(ps, l), gout + net_b_off(ps, l));
         if (l > 0) {
-            cp_async_wait<0>();
-            __syncthreads();
-            layer_input_grad(Hp, dZ, lda, ts.w[l & 1], dY, dX, R, true);
+            const float *Ws, *bs;
+            pipe_acquire(pipe, Ws, bs);
+            layer_input_grad(Hp, dZ, lda, Ws, dY, dX, true, part);  // ends with a CTA barrier
+            pipe_release(pipe);
             cur = (cur + 2) % 3;
         }
     }
@@ -883,27 +916,50 @@ struct MlpArgs {
     int64_t rows;
     int rows_per_cta;
 };
+// shared-memory plan of k_mlp_forward (floats)
+struct MlpPlan {
+    int lda, wsz, off_a, off_b, off_ho, off_part, off_pipe, off_slots, n_slots, total;
+};
+__host__ __device__ __forceinline__ MlpPlan mlp_plan(const NetShape &s, int rows_per_cta) {
+    MlpPlan p;
+    p.lda = tile_lda(s.hidden, s.in_dim);
+    p.wsz = round_up(tile_wsz(s.hidden, s.in_dim), 4);
+    int o = rows_per_cta * p.lda;  // xin at 0
+    p.off_a = o; o += rows_per_cta * p.lda;
+    p.off_b = o; o += rows_per_cta * p.lda;
+    p.off_ho = o; o += round_up(rows_per_cta * s.out_dim, 4);
+    p.off_part = o; o += tile_part_floats(s.hidden);
+    p.off_pipe = o; o += PIPE_HEADER_FLOATS;
+    p.off_slots = o;
+    p.n_slots = slots_that_fit(o, p.wsz, s.depth);
+    p.total = o + p.n_slots * p.wsz;
+    return p;
+}
 __global__ void __launch_bounds__(NT) k_mlp_forward(const MlpArgs a) {
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
     const int tid = threadIdx.x;
     const NetShape s = a.s;
-    const int lda = tile_lda(s.hidden, s.in_dim), wsz = round_up(tile_wsz(s.hidden, s.in_dim), 4);
     const int RC = a.rows_per_cta;
+    const MlpPlan pl = mlp_plan(s, RC);
+    const int lda = pl.lda;
     const int64_t r0 = (int64_t)blockIdx.x * RC;
     const int rows = (int)min((int64_t)RC, a.rows - r0);
-    float *xin = sm, *bufA = xin + RC * lda, *bufB = bufA + RC * lda;
-    TileSmem ts;
-    ts.w[0] = bufB + RC * lda; ts.w[1] = ts.w[0] + wsz;
-    ts.bias[0] = ts.w[0] + s.hidden * lda; ts.bias[1] = ts.w[1] + s.hidden * lda;
-    float *ho = ts.w[1] + wsz;
+    float *xin = sm, *bufA = sm + pl.off_a, *bufB = sm + pl.off_b, *ho = sm + pl.off_ho, *part = sm + pl.off_part;
+    WeightJob *jobs = reinterpret_cast<WeightJob *>(sm + pl.off_pipe);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(jobs + MAX_WEIGHT_JOBS);
+    if (tid == 0) push_trunk_jobs(jobs, 0, s, a.params);
+    __syncthreads();
+    WeightPipe pipe;
+    pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, s.depth);
     const int K4 = round_up(s.in_dim, 4);
     const int rp = round_up(rows, PASS_ROWS);
     for (int i = tid; i < rp * K4; i += NT) {
         const int r = i / K4, col = i - r * K4;
         xin[r * lda + col] = (r < rows && col < s.in_dim) ? a.x[(r0 + r) * s.in_dim + col] : 0.f;
     }
-    float *h = net_trunk_forward(s, a.params, ts, xin, bufA, bufB, nullptr, nullptr, lda, rp);
+    __syncthreads();
+    float *h = net_trunk_forward(s, pipe, xin, bufA, bufB, nullptr, nullptr, lda, rp, part);
     head_forward(h, lda, s.hidden, a.params + net_w_off(s, s.depth), a.params + net_b_off(s, s.depth), s.out_dim, rows,
                  ho);
     __syncthreads();
@@ -1236,8 +1292,7 @@ extern "C" int asac_mlp_forward(const float *params, int in_dim, int hidden, int
     a.s = NetShape{in_dim, hidden, depth, out_dim};
     a.rows = rows;
     a.rows_per_cta = 32;
-    const int lda = tile_lda(hidden, in_dim), wsz = round_up(tile_wsz(hidden, in_dim), 4);
-    const int bytes = (3 * a.rows_per_cta * lda + 2 * wsz + round_up(a.rows_per_cta * out_dim, 4)) * 4;
+    const int bytes = mlp_plan(a.s, a.rows_per_cta).total * 4;
     int rc = set_smem(k_mlp_forward, bytes, "k_mlp_forward");
     if (rc != ASAC_OK) return rc;
     k_mlp_forward<<<(unsigned)((rows + a.rows_per_cta - 1) / a.rows_per_cta), NT, bytes, (cudaStream_t)stream>>>(a);
