@@ -729,14 +729,6 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------ optimiser
-// sums the per-tile partials in tile order: out[p] = sum_t part[t * tile_stride + p]
-__device__ __forceinline__ float reduce_partials(const float *part, int n_tiles, int64_t tile_stride, int64_t p) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int t = 0; t < n_tiles; ++t) s += __ldcg(part + t * tile_stride + p);
-    return s;
-}
-
 struct AdamArgs {
     float *param, *m, *v;
     const float *part;      // partial gradients (or nullptr: read `grad`)
@@ -750,23 +742,47 @@ struct AdamArgs {
     double lr;
 };
 
-// torch.optim.Adam single-tensor path (betas 0.9/0.999, eps 1e-8, no weight decay / amsgrad)
-__global__ void __launch_bounds__(256) k_reduce_adam(const AdamArgs a) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.count) return;
-    float gr;
+constexpr int ADAM_PARAMS_PER_CTA = 64, ADAM_TILE_GROUPS = 4;
+
+// Deterministic reduction of the per-tile partial gradients fused with torch.optim.Adam's
+// single-tensor update (betas 0.9/0.999, eps 1e-8, no weight decay / amsgrad).  A CTA owns 64
+// consecutive parameters; its 4 thread groups each sum a quarter of the tiles (coalesced 256-byte
+// rows, loads of different tiles in flight together), the quarters are added in group order.
+// The float64 bias corrections are computed once per CTA while the loads are in flight.
+__global__ void __launch_bounds__(ADAM_PARAMS_PER_CTA *ADAM_TILE_GROUPS) k_reduce_adam(const AdamArgs a) {
+    __shared__ float s_part[ADAM_TILE_GROUPS][ADAM_PARAMS_PER_CTA];
+    __shared__ float s_bc[2];
+    const int tid = threadIdx.x, pl = tid & (ADAM_PARAMS_PER_CTA - 1), tg = tid / ADAM_PARAMS_PER_CTA;
+    const int64_t p = (int64_t)blockIdx.x * ADAM_PARAMS_PER_CTA + pl;
+    float gr = 0.f;
     if (a.part) {
-        gr = reduce_partials(a.part, a.n_tiles, a.tile_stride, p);
+        if (p < a.count) {
+            const int per = (a.n_tiles + ADAM_TILE_GROUPS - 1) / ADAM_TILE_GROUPS;
+            const int t0 = tg * per, t1 = min(a.n_tiles, t0 + per);
+#pragma unroll 8
+            for (int t = t0; t < t1; ++t) gr += __ldcg(a.part + t * a.tile_stride + p);
+        }
+        s_part[tg][pl] = gr;
+    }
+    if (tid == ADAM_PARAMS_PER_CTA * ADAM_TILE_GROUPS - 1 && a.do_adam) {  // a thread of the last warp
+        const double t = (double)(a.step[0] + 1);
+        const double bc1 = 1.0 - pow(0.9, t), bc2 = 1.0 - pow(0.999, t);
+        s_bc[0] = (float)(-(a.lr / bc1));
+        s_bc[1] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    if (tg != 0 || p >= a.count) return;
+    if (a.part) {
+        gr = s_part[0][pl];
+#pragma unroll
+        for (int g = 1; g < ADAM_TILE_GROUPS; ++g) gr += s_part[g][pl];
         if (a.write_grad) a.grad[p] = gr;
     } else {
         gr = a.grad[p];
     }
     if (!a.do_adam) return;
     gr = gr * a.grad_scale;
-    const double t = (double)(a.step[0] + 1);
-    const double bc1 = 1.0 - pow(0.9, t), bc2 = 1.0 - pow(0.999, t);
-    const float step_size = (float)(-(a.lr / bc1));
-    const float bc2_sqrt = (float)sqrt(bc2);
+    const float step_size = s_bc[0], bc2_sqrt = s_bc[1];
     const float w1 = (float)(1.0 - 0.9), w2 = (float)(1.0 - 0.999);
     float m = a.m[p], v = a.v[p];
     m = m + w1 * (gr - m);                      // exp_avg.lerp_(grad, 1 - beta1)
@@ -779,14 +795,16 @@ __global__ void __launch_bounds__(256) k_reduce_adam(const AdamArgs a) {
 
 // alpha: a single scalar, gradient = (sum over tiles of the alpha terms) / B  (sac_base.py:1941-1948),
 // then y' = yq - alpha_new * yl and td = mean_i |Q_i(s_b, a_b) - y'|  (sac_base.py:2223-2245).  One CTA.
+// `staged` (shared memory, n_tiles floats) holds wrk.grad_alpha_part[t * 2], loaded by the whole CTA:
+// one thread summing the tiles straight from global memory serialised n_tiles L2 round trips
 __device__ __forceinline__ void alpha_reduce_adam(const AsacSacParams &prm, const AsacSacWork &wrk, int n_tiles,
                                                   int batch, int do_reduce, int do_adam, float grad_scale,
-                                                  double lr) {
+                                                  double lr, const float *staged) {
     {
         float gr;
         if (do_reduce) {
             float s = 0.f;
-            for (int t = 0; t < n_tiles; ++t) s += wrk.grad_alpha_part[t * 2];
+            for (int t = 0; t < n_tiles; ++t) s += staged[t];
             gr = s / (float)batch;
             wrk.grad_alpha[0] = gr;
         } else {
@@ -813,8 +831,13 @@ __device__ __forceinline__ void alpha_reduce_adam(const AsacSacParams &prm, cons
 __global__ void __launch_bounds__(1024) k_alpha_td(const AsacSacParams prm, const AsacSacWork wrk, int n_tiles,
                                                    int batch, int ensemble, int do_reduce, int do_adam, int do_td,
                                                    float grad_scale, double lr) {
+    __shared__ float s_alpha[1024];
+    if (do_reduce) {
+        for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) s_alpha[t] = __ldcg(wrk.grad_alpha_part + t * 2);
+        __syncthreads();
+    }
     if (threadIdx.x == 0 && (do_reduce || do_adam))
-        alpha_reduce_adam(prm, wrk, n_tiles, batch, do_reduce, do_adam, grad_scale, lr);
+        alpha_reduce_adam(prm, wrk, n_tiles, batch, do_reduce, do_adam, grad_scale, lr, s_alpha);
     if (!do_td) return;
     __syncthreads();
     const float alpha = expf(__ldcg(prm.log_alpha));
@@ -845,8 +868,13 @@ struct EpilogueArgs {
 };
 __global__ void __launch_bounds__(1024) k_step_epilogue(const __grid_constant__ EpilogueArgs a) {
     __shared__ TreeApplySmem s_apply;
+    __shared__ float s_alpha[1024];
     const int t = threadIdx.x;
-    if (t == 0 && a.use_auto_alpha) alpha_reduce_adam(a.prm, a.wrk, a.n_tiles, a.batch, 1, 1, 1.f, a.lr);
+    if (a.use_auto_alpha) {
+        for (int i = t; i < a.n_tiles; i += blockDim.x) s_alpha[i] = __ldcg(a.wrk.grad_alpha_part + i * 2);
+        __syncthreads();
+        if (t == 0) alpha_reduce_adam(a.prm, a.wrk, a.n_tiles, a.batch, 1, 1, 1.f, a.lr, s_alpha);
+    }
     __syncthreads();
     const float alpha = expf(__ldcg(a.prm.log_alpha));
     bool active = t < a.batch;
@@ -1027,6 +1055,7 @@ static int make_args(SacArgs &a, const AsacSacConfig *cfg, const AsacSacParams *
     a.mode = 0;
     const int tiles = (cfg->batch + a.tile_batch - 1) / a.tile_batch;
     ASAC_REQUIRE(wrk->n_tiles == tiles, "work.n_tiles %d != ceil(B / tile_batch) = %d", wrk->n_tiles, tiles);
+    ASAC_UNSUPPORTED(tiles > 1024, "batch %d needs %d tiles (> 1024)", cfg->batch, tiles);
     return ASAC_OK;
 }
 
@@ -1147,6 +1176,7 @@ static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm
     if (rc != ASAC_OK) return rc;
     ASAC_REQUIRE(which >= 0 && which <= 2, "which must be 0 (critics), 1 (policy) or 2 (alpha)");
     if (which == 2) {
+        ASAC_UNSUPPORTED(wrk->n_tiles > 1024, "n_tiles %d > 1024", wrk->n_tiles);
         const int threads = cfg->batch >= 1024 ? 1024 : ((cfg->batch + 31) / 32) * 32;
         k_alpha_td<<<1, threads, 0, (cudaStream_t)stream>>>(*prm, *wrk, wrk->n_tiles, cfg->batch, cfg->ensemble,
                                                             do_reduce, do_adam, do_td, grad_scale,
@@ -1177,7 +1207,8 @@ static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm
     a.do_adam = do_adam;
     a.grad_scale = grad_scale;
     a.lr = cfg->learning_rate;
-    k_reduce_adam<<<(unsigned)((a.count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    k_reduce_adam<<<(unsigned)((a.count + ADAM_PARAMS_PER_CTA - 1) / ADAM_PARAMS_PER_CTA),
+                    ADAM_PARAMS_PER_CTA * ADAM_TILE_GROUPS, 0, (cudaStream_t)stream>>>(a);
     ASAC_LAUNCHED("k_reduce_adam");
     return ASAC_OK;
 }
