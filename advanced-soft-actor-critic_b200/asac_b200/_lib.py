@@ -110,6 +110,7 @@ PROTOTYPES = {
     'asac_sac_finish_step': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp, i64, vp, vp, vp, vp]),
     'asac_fill_normal': (i32, [vp, i64, u64, vp, i32, vp]),
     'asac_mlp_forward': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp]),
+    'asac_mlp_forward_tc': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp]),
 }
 
 

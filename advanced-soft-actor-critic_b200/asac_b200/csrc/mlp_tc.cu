@@ -1,0 +1,322 @@
+// Stock-net forward on the 5th-generation tensor cores (sm_100a): tcgen05.mma kind::tf32 with
+// the accumulator in tensor memory, 3xTF32 split operands for fp32-level accuracy.
+//
+// Replaces, for large row counts, the chain of nn.Linear + exact-erf GELU + residual launches
+// of LinearLayers (algorithm/nn_models/layers/linear_layers.py:24-119) behind ModelQ / ModelPolicy
+// forwards (nn_models/q.py:74-91, nn_models/policy.py:150-170) — the evaluation the actor side
+// and the large-batch value passes spend their time in.
+//
+// One persistent CTA per SM walks 128-row tiles:
+//   * operands live in shared memory in the UMMA K-major, no-swizzle "core matrix" layout
+//     (8 rows x 16 bytes contiguous; consecutive K chunks 128 B apart, 8-row groups SBO apart),
+//     each as a (hi, lo) pair: hi = x with the 13 low mantissa bits cleared (exact in tf32),
+//     lo = x - hi.  D = A_hi.B_lo + A_lo.B_hi + A_hi.B_hi accumulates in fp32 in TMEM, which
+//     restores ~21 mantissa bits per product (plain kind::tf32 keeps 10 and cannot meet the
+//     1e-5 parity bound of the north star);
+//   * the weights of every layer are split and laid out once per CTA;
+//   * one elected thread issues the 3 x K/8 MMAs of a layer and commits them to an mbarrier;
+//   * the epilogue maps TMEM lane = row to one thread (two warps per 32-lane quarter, 32
+//     accumulator columns each): tcgen05.ld -> bias + exact-erf GELU + residual -> split ->
+//     16-byte stores straight into the next layer's A operand; the head is one more MMA
+//     (N = 16, zero padded) whose epilogue writes the rows of the result.
+#include <math.h>
+
+#include "common.cuh"
+#include "mlp_tile.cuh"
+
+namespace asac {
+
+constexpr int TC_ROWS = 128;     // UMMA_M
+constexpr int TC_THREADS = 256;  // 8 warps: 2 per TMEM lane quarter
+constexpr int TC_HEAD_N = 16;    // padded head width (UMMA_N % 16 == 0 for M = 128)
+
+// ---------------------------------------------------------------- tcgen05 primitives
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, cta_group::1
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor): start address,
+// leading (K-chunk) byte offset and stride (8-row group) byte offset, all in 16-byte units; version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// cute::UMMA::InstrDescriptor: D fp32, A/B tf32, both K-major, dense
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// float offset of element (row, k) of an operand with Kp (multiple of 8) columns in the core-matrix layout
+__host__ __device__ __forceinline__ int umma_off(int row, int k, int Kp) {
+    return (row >> 3) * (Kp * 8) + (k >> 2) * 32 + (row & 7) * 4 + (k & 3);
+}
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = x - hi;
+}
+
+// ---------------------------------------------------------------- shared-memory plan
+struct TcPlan {
+    int K0p;                  // first-layer K padded to 8
+    int off_a_hi, off_a_lo;   // [128, max(K0p, H)] activations
+    int off_w[ASAC_MAX_DEPTH + 1][2];  // per layer (head last): hi, lo
+    int off_bias;             // depth * H + TC_HEAD_N
+    int off_misc;             // mbarrier, tmem address
+    int total;                // floats
+};
+__host__ __device__ __forceinline__ TcPlan tc_plan(const NetShape &s) {
+    TcPlan p;
+    const int H = s.hidden;
+    p.K0p = round_up(s.in_dim, 8);
+    const int ka = p.K0p > H ? p.K0p : H;
+    int o = 0;
+    p.off_a_hi = o; o += TC_ROWS * ka;
+    p.off_a_lo = o; o += TC_ROWS * ka;
+    for (int l = 0; l < s.depth; ++l) {
+        const int K = l == 0 ? p.K0p : H;
+        p.off_w[l][0] = o; o += H * K;
+        p.off_w[l][1] = o; o += H * K;
+    }
+    p.off_w[s.depth][0] = o; o += TC_HEAD_N * H;
+    p.off_w[s.depth][1] = o; o += TC_HEAD_N * H;
+    p.off_bias = o; o += s.depth * H + TC_HEAD_N;
+    p.off_misc = o; o += 8;
+    p.total = o;
+    return p;
+}
+
+struct TcArgs {
+    const float *params, *x;
+    float *out;
+    NetShape s;
+    int64_t rows;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_forward_tc(const TcArgs a) {
+    extern __shared__ __align__(128) float smem_tc[];
+    float *sm = smem_tc;
+    const NetShape s = a.s;
+    const int H = s.hidden, d = s.depth, O = s.out_dim;
+    const TcPlan pl = tc_plan(s);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *a_hi = sm + pl.off_a_hi, *a_lo = sm + pl.off_a_lo, *bias = sm + pl.off_bias;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + pl.off_misc);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + pl.off_misc + 2);
+    constexpr uint32_t TMEM_COLS = 128;  // trunk accumulator at column 0, head accumulator at column 64
+
+    // ---- one-time setup: TMEM, mbarrier, split weights in the UMMA layout
+    if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    for (int l = 0; l <= d; ++l) {
+        const int K = l == 0 ? s.in_dim : H, Kp = l == 0 ? pl.K0p : H;
+        const int N = l == d ? O : H, Np = l == d ? TC_HEAD_N : H;
+        const float *W = a.params + net_w_off(s, l);
+        float *w_hi = sm + pl.off_w[l][0], *w_lo = sm + pl.off_w[l][1];
+        for (int i = tid; i < Np * Kp; i += TC_THREADS) {
+            const int n = i / Kp, k = i - n * Kp;
+            const float w = (n < N && k < K) ? __ldg(W + (int64_t)n * K + k) : 0.f;
+            float hi, lo;
+            split_tf32(w, hi, lo);
+            const int off = umma_off(n, k, Kp);
+            w_hi[off] = hi;
+            w_lo[off] = lo;
+        }
+        const float *b = a.params + net_b_off(s, l);
+        for (int i = tid; i < Np; i += TC_THREADS) bias[l * H + i] = i < N ? __ldg(b + i) : 0.f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc_trunk = umma_idesc_tf32(TC_ROWS, H), idesc_head = umma_idesc_tf32(TC_ROWS, TC_HEAD_N);
+    const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo);
+
+    // this thread's accumulator slice: TMEM lane = row, 32 columns
+    const int row = (warp & 3) * 32 + lane;
+    const int col0 = (warp >> 2) * 32;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t phase = 0;
+
+    const int64_t n_tiles = (a.rows + TC_ROWS - 1) / TC_ROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t r0 = tile * TC_ROWS;
+        // ---- stage the tile's input rows (split) as the first A operand
+        {
+            const int K = s.in_dim, Kp = pl.K0p;
+            for (int i = tid; i < TC_ROWS * Kp; i += TC_THREADS) {
+                const int r = i / Kp, k = i - r * Kp;
+                const float x = (r0 + r < a.rows && k < K) ? __ldg(a.x + (r0 + r) * K + k) : 0.f;
+                float hi, lo;
+                split_tf32(x, hi, lo);
+                const int off = umma_off(r, k, Kp);
+                a_hi[off] = hi;
+                a_lo[off] = lo;
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        for (int l = 0; l <= d; ++l) {
+            const int Kp = l == 0 ? pl.K0p : H;
+            const bool head = l == d;
+            // ---- MMA issue: cross terms first, the dominant hi.hi last
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t w_hi_addr = smem_u32(sm + pl.off_w[l][0]), w_lo_addr = smem_u32(sm + pl.off_w[l][1]);
+                const uint32_t sbo = (uint32_t)Kp * 32;  // bytes between 8-row groups: Kp/4 chunks x 128 B
+                const uint32_t d_tmem = tmem_base + (head ? 64u : 0u);
+                const uint32_t idesc = head ? idesc_head : idesc_trunk;
+                uint32_t acc = 0;
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t aa = term == 1 ? a_lo_addr : a_hi_addr;
+                    const uint32_t bb = term == 0 ? w_lo_addr : w_hi_addr;
+                    for (int k8 = 0; k8 < Kp / 8; ++k8) {
+                        tc_mma_tf32(d_tmem, umma_desc(aa + k8 * 256, 128, sbo), umma_desc(bb + k8 * 256, 128, sbo), idesc,
+                                    acc);
+                        acc = 1;
+                    }
+                }
+                tc_commit(bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+
+            if (!head) {
+                // ---- epilogue: bias + exact-erf GELU (+ residual) -> split -> next A operand
+                float v[32];
+                tmem_ld32(lane_addr + (uint32_t)col0, v);
+                const bool residual = (l == 0 ? s.in_dim : H) == H;
+                const float *bl = bias + l * H + col0;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const int off = umma_off(row, col0 + 4 * c4, H);
+                    float4 xh = make_float4(0.f, 0.f, 0.f, 0.f), xl = xh;
+                    if (residual) {
+                        xh = *reinterpret_cast<const float4 *>(a_hi + off);
+                        xl = *reinterpret_cast<const float4 *>(a_lo + off);
+                    }
+                    const float xr[4] = {xh.x + xl.x, xh.y + xl.y, xh.z + xl.z, xh.w + xl.w};
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float z = v[4 * c4 + j] + bl[4 * c4 + j];
+                        float y = gelu_erf(z);
+                        if (residual) y = y + xr[j];
+                        split_tf32(y, hi[j], lo[j]);
+                    }
+                    // a non-residual first layer may have K0p != H: its output still uses the H-wide layout,
+                    // which overlaps the input operand -> all reads of this layer's A are complete (MMA committed)
+                    *reinterpret_cast<float4 *>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                fence_proxy_async();
+            } else if (warp < 4) {
+                float v[16];
+                tmem_ld16(lane_addr + 64u, v);
+                if (r0 + row < a.rows) {
+                    const float *bl = bias + d * H;
+#pragma unroll
+                    for (int o = 0; o < TC_HEAD_N; ++o)
+                        if (o < O) a.out[(r0 + row) * O + o] = v[o] + bl[o];
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
+        }
+    }
+    tc_fence_after();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace asac
+
+using namespace asac;
+
+extern "C" int asac_mlp_forward_tc(const float *params, int in_dim, int hidden, int depth, int out_dim, const float *x,
+                                   int64_t rows, float *out, void *stream) {
+    ASAC_UNSUPPORTED(hidden != 64, "asac_mlp_forward_tc: hidden width %d (the tensor-core tile is built for 64)", hidden);
+    ASAC_UNSUPPORTED(depth < 1 || depth > ASAC_MAX_DEPTH, "asac_mlp_forward_tc: depth %d", depth);
+    ASAC_UNSUPPORTED(out_dim < 1 || out_dim > TC_HEAD_N, "asac_mlp_forward_tc: out_dim %d > %d", out_dim, TC_HEAD_N);
+    ASAC_REQUIRE(in_dim > 0 && rows > 0, "asac_mlp_forward_tc: bad sizes");
+    TcArgs a;
+    a.params = params; a.x = x; a.out = out;
+    a.s = NetShape{in_dim, hidden, depth, out_dim};
+    a.rows = rows;
+    const int bytes = tc_plan(a.s).total * 4 + 128;
+    ASAC_UNSUPPORTED(bytes > 227 * 1024, "asac_mlp_forward_tc: %d bytes of shared memory", bytes);
+    static thread_local int granted[16];
+    int dev = 0;
+    ASAC_CUDA(cudaGetDevice(&dev));
+    if (dev >= 16 || granted[dev] < bytes) {
+        ASAC_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (dev < 16) granted[dev] = bytes;
+    }
+    int sms = 148;
+    ASAC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t tiles = (rows + TC_ROWS - 1) / TC_ROWS;
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    k_mlp_forward_tc<<<grid, TC_THREADS, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_mlp_forward_tc");
+    return ASAC_OK;
+}

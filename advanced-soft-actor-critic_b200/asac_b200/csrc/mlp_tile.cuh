@@ -130,7 +130,7 @@ struct WeightPipe {
 // (A first version let warp 0 issue one cp.async.bulk per weight row — 65 TMA operations per
 // layer, ~600 per kernel from a single warp — and the consumers' mbarrier wait became the largest
 // stall of k_value_pass: per-row bulk copies are too fine-grained for the TMA unit.)
-__device__ __noinline__ int pipe_fill_impl(float *slots, uint64_t *bars, const WeightJob *jobs, int n_slots,
+static __device__ __noinline__ int pipe_fill_impl(float *slots, uint64_t *bars, const WeightJob *jobs, int n_slots,
                                            int slot_floats, int n_jobs, int issued, int consumed) {
     ASAC_SMEM(slots); ASAC_SMEM(jobs);
     const int tid = threadIdx.x;
@@ -357,7 +357,7 @@ __device__ __forceinline__ void layer_input_grad(int hidden, const float *dZ, in
 }
 
 // dZ = dY * gelu'(Z) over 16 rows (H a power of two); rows >= valid_rows are zeroed
-__device__ __noinline__ void gelu_backward(const float *dY, const float *Z, float *dZ, int ld, int H, int valid_rows) {
+static __device__ __noinline__ void gelu_backward(const float *dY, const float *Z, float *dZ, int ld, int H, int valid_rows) {
     ASAC_SMEM(dY); ASAC_SMEM(Z); ASAC_SMEM(dZ);
     const int sh = 31 - __clz(H);
 #pragma unroll 1
@@ -370,7 +370,7 @@ __device__ __noinline__ void gelu_backward(const float *dY, const float *Z, floa
 // Partial weight / bias gradient of one layer over the tile's rows:
 //   gW[j * K + k] = sum_r dZ[r][j] * X[r][k],  gb[j] = sum_r dZ[r][j]
 // 2 x 4 output blocks, consecutive threads along k (coalesced 16-byte stores).
-__device__ __noinline__ void layer_weight_grad(const float *dZ, int ldz, const float *X, int ldx, int H, int K,
+static __device__ __noinline__ void layer_weight_grad(const float *dZ, int ldz, const float *X, int ldx, int H, int K,
                                                int nrows, float *gW, float *gb) {
     ASAC_SMEM(dZ); ASAC_SMEM(X);
     const int tid = threadIdx.x;
@@ -416,7 +416,7 @@ __device__ __noinline__ void layer_weight_grad(const float *dZ, int ldz, const f
 }
 
 // Linear head: out[r * O + o] = X[r] . Wh[o] + bh[o]   (Wh, bh in global memory, 8 lanes per dot)
-__device__ __noinline__ void head_forward(const float *X, int ldx, int H, const float *Wh, const float *bh, int O,
+static __device__ __noinline__ void head_forward(const float *X, int ldx, int H, const float *Wh, const float *bh, int O,
                                           int nrows, float *out) {
     ASAC_SMEM(X); ASAC_SMEM(out);
     const int tid = threadIdx.x, grp = tid >> 3, sub = tid & 7;
@@ -440,7 +440,7 @@ __device__ __noinline__ void head_forward(const float *X, int ldx, int H, const 
 
 // Head backward.  dO[r * O + o] (rows >= valid rows must be zero):
 //   gWh[o * H + j] = sum_r dO[r][o] X[r][j];  gbh[o] = sum_r dO[r][o];  dH[r][j] = sum_o dO[r][o] Wh[o][j]
-__device__ __noinline__ void head_backward(const float *dO, int O, const float *X, int ldx, int H, const float *Wh,
+static __device__ __noinline__ void head_backward(const float *dO, int O, const float *X, int ldx, int H, const float *Wh,
                                            int nrows, float *gWh, float *gbh, float *dH, int ldh) {
     ASAC_SMEM(dO); ASAC_SMEM(dH);
     if (X) ASAC_SMEM(X);

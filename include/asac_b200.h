@@ -334,6 +334,13 @@ int asac_fill_normal(float *out, int64_t n, uint64_t seed, const int64_t *counte
 int asac_mlp_forward(const float *params, int in_dim, int hidden, int depth, int out_dim,
                      const float *x, int64_t rows, float *out, void *stream);
 
+/* The same forward on the tcgen05 tensor cores (kind::tf32, accumulator in TMEM, 3xTF32 split
+ * operands so that results stay within 1e-5 of the fp32 reference): one persistent CTA per SM over
+ * 128-row tiles.  hidden == 64 (the stock width), out_dim <= 16.  Meant for large row counts (actor-side
+ * batches, large-batch value passes); asac_mlp_forward stays the exact-fp32 FFMA path. */
+int asac_mlp_forward_tc(const float *params, int in_dim, int hidden, int depth, int out_dim,
+                        const float *x, int64_t rows, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

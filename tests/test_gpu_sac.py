@@ -437,6 +437,60 @@ def test_mlp_forward_matches_torch():
         assert rel_err(out.cpu().numpy(), ref) < TOL, (in_dim, H, depth, rows)
 
 
+def test_mlp_forward_tcgen05_matches_torch_and_ffma():
+    """asac_mlp_forward_tc (tcgen05 kind::tf32, 3xTF32 split operands, accumulator in TMEM) against the
+    torch fp32 forward of the same stock net and against the exact-fp32 FFMA kernel: 1e-5 of scale.
+    Covers ragged row counts, a residual first layer (in == hidden), K padding (in = 6 -> 8), the
+    policy head (out = 2A) and more tiles than SMs (persistent loop)."""
+    from asac_b200 import _lib
+    from asac_b200._lib import check, ptr
+    from oracle.sac_oracle import init_policy, init_q, policy_param_names, q_forward, trunk_forward
+    from asac_b200 import lowering
+    import torch.nn.functional as F
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(7)
+    s = torch.cuda.current_stream().cuda_stream
+    worst = {}
+    for (in_dim, H, depth, rows) in [(8, 64, 3, 1000), (8, 64, 3, 128), (6, 64, 3, 1), (64, 64, 2, 300), (5, 64, 2, 4097),
+                                     (8, 64, 3, 200 * 128 + 5)]:
+        S, A = in_dim - 2, 2
+        p = init_q(S, A, H, depth, gen)
+        for k in p:
+            if k.endswith('bias'):
+                p[k] = torch.randn(p[k].shape, generator=gen) * 0.1
+        x = torch.randn(rows, in_dim, generator=gen)
+        ref = q_forward(p, depth, x[:, :S], x[:, S:]).numpy()
+        shape = lowering.NetShape(in_dim, H, depth, 1)
+        flat = lowering.flat_from_state_dict(shape, p, policy=False).cuda()
+        xc = x.cuda().contiguous()
+        out_tc = torch.full((rows, 1), float('nan'), device='cuda')
+        out_ff = torch.zeros(rows, 1, device='cuda')
+        check(lib.asac_mlp_forward_tc(ptr(flat), in_dim, H, depth, 1, ptr(xc), rows, ptr(out_tc), s), 'mlp_forward_tc')
+        check(lib.asac_mlp_forward(ptr(flat), in_dim, H, depth, 1, ptr(xc), rows, ptr(out_ff), s), 'mlp_forward')
+        e_ref, e_ff = rel_err(out_tc.cpu().numpy(), ref), rel_err(out_tc.cpu().numpy(), out_ff.cpu().numpy())
+        worst[(in_dim, H, depth, rows)] = (e_ref, e_ff)
+        assert e_ref < TOL and e_ff < TOL, (in_dim, H, depth, rows, e_ref, e_ff)
+    # policy head: out = 2A pre-activations (mean, logstd rows of the flat layout)
+    S, A, H, depth, rows = 6, 2, 64, 3, 777
+    p = init_policy(S, A, H, depth, gen)
+    x = torch.randn(rows, S, generator=gen)
+    h = trunk_forward(p, depth, x)
+    names = policy_param_names(depth)
+    mean = F.linear(h, p[names[-4]], p[names[-3]])
+    logstd = F.linear(h, p[names[-2]], p[names[-1]])
+    ref = torch.cat([mean, logstd], dim=-1).numpy()
+    shape = lowering.NetShape(S, H, depth, 2 * A)
+    flat = lowering.flat_from_state_dict(shape, p, policy=True).cuda()
+    out_tc = torch.zeros(rows, 2 * A, device='cuda')
+    xc = x.cuda().contiguous()
+    check(lib.asac_mlp_forward_tc(ptr(flat), S, H, depth, 2 * A, ptr(xc), rows, ptr(out_tc), s), 'mlp_forward_tc')
+    e = rel_err(out_tc.cpu().numpy(), ref)
+    worst['policy'] = (e, 0.0)
+    _dump('mlp_tc', {str(k): v[0] for k, v in worst.items()})
+    print('tcgen05 forward: rel err vs torch / vs FFMA:', {k: (f'{a:.1e}', f'{b:.1e}') for k, (a, b) in worst.items()})
+    assert e < TOL, e
+
+
 def test_fill_normal_statistics():
     from asac_b200 import _lib
     from asac_b200._lib import check, ptr
