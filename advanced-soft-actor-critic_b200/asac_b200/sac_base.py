@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import os
 import random
 from pathlib import Path
 
@@ -237,6 +238,8 @@ class SAC_Base:
         self._graph = None
         self._graph_columns_key = None
         self._rank, self._world = adist.world()
+        # NCCL all-reduces are captured into the step's CUDA graph (ASAC_GRAPH_COLLECTIVES=0 keeps them eager)
+        self._graph_collectives = os.environ.get('ASAC_GRAPH_COLLECTIVES', '1') != '0'
         if self._world > 1:
             # replicated weights: every rank starts from rank 0's networks and optimizer state
             adist.broadcast_([self._q_flat, self._qt_flat, self._pi_flat, self._log_alpha_buf, self._q_m, self._q_v,
@@ -676,7 +679,7 @@ class SAC_Base:
                 self._specs = self._gather_specs()
                 self._graph, self._graph_columns_key = None, key
                 self._enqueue_step()  # eager warm-up (also sets the kernels' shared-memory attributes)
-            elif not self.use_cuda_graph or self._world > 1:  # NCCL collectives stay outside graphs for now
+            elif not self.use_cuda_graph or (self._world > 1 and not self._graph_collectives):
                 self._enqueue_step()
             else:
                 if self._graph is None:

@@ -232,12 +232,13 @@ def run_gpu(args):
         sac.train()
     barrier()
 
+    # kernels of this library per train(): counted on one eager step (every rank takes it, so the
+    # step's collectives stay matched across ranks)
     lib.asac_reset_launch_count()
-    sac._enqueue_step() if world == 1 else None
+    sac._enqueue_step()
     torch.cuda.synchronize()
-    launches_per_step = int(lib.asac_launch_count()) if world == 1 else 0
-    if world == 1:
-        sac.increase_global_step()
+    launches_per_step = int(lib.asac_launch_count())
+    sac.increase_global_step()
 
     # ---- timed: K steps, one CUDA-event pair per step, L2 flushed between steps
     clocks = ClockSampler(local_rank)
@@ -313,7 +314,7 @@ def run_gpu(args):
         'e2e': {'value': units_per_step * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(td_host.numel() * 4),
                 'what': f'put_episode({T_in} host transitions, pinned) + train() + D2H of td_error[256], per step'},
-        'gpu_launches': launches_per_step * args.steps,
+        'gpu_launches': launches_per_step * args.steps * world,
         'launches_per_step': launches_per_step,
         'clocks': clock_info,
         'fill_seconds': round(t_fill, 2),
