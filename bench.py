@@ -128,6 +128,7 @@ def stage_work(cfg):
         'policy_backward': dict(bound='tensor', flops=(3 * pi + 2 * E * q) * B),
         'adam_pi': dict(bound='hbm', bytes=Ppi * 4 * 7),
         'value_pass_post': dict(bound='tensor', flops=pi * B * L + E * q * (B * (n + 1) + B)),
+        'finish_step': dict(bound='hbm', bytes=B * (12 * D + 16) + B * 4 * (2 + E) + 64),
         'adam_alpha': dict(bound='hbm', bytes=64),
         'per_update': dict(bound='hbm', bytes=B * (12 * D + 16)),
         'write_back': dict(bound='hbm', bytes=B * (L - 1) * (A * 4 + 8)),
@@ -153,8 +154,8 @@ def build_learner(device, seed, capacity, fill):
 
 
 def profile_stages(sac, steps):
-    """Average device time of every kernel of the step: eager launches, one CUDA-event pair around
-    each C-ABI call on the launching stream."""
+    """Average device time of every stage of the step (plus the standalone alpha / priority-update
+    entry points the fused tail replaces), each captured in its own CUDA graph."""
     import ctypes as C
     from asac_b200 import _lib
     from asac_b200._lib import check, ptr
@@ -177,6 +178,9 @@ def profile_stages(sac, steps):
         ('policy_backward', lambda: check(lib.asac_sac_policy_backward(cfg, prm, batch, work, s()))),
         ('adam_pi', lambda: check(lib.asac_sac_reduce_adam(cfg, prm, work, 1, s()))),
         ('value_pass_post', lambda: check(lib.asac_sac_post(cfg, prm, batch, work, s()))),
+        ('finish_step', lambda: check(lib.asac_sac_finish_step(cfg, prm, work, ptr(rb._nodes), rb.capacity,
+                                                               ptr(rb._store_ids), ptr(smp['ids']),
+                                                               ptr(rb._per_state), s()))),
         ('adam_alpha', lambda: check(lib.asac_sac_reduce_adam(cfg, prm, work, 2, s()))),
         ('per_update', lambda: check(lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids),
                                                          ptr(smp['ids']), ptr(sac._wk['td_error']), B,
@@ -185,21 +189,56 @@ def profile_stages(sac, steps):
         ('write_back', lambda: rb.write_back(smp['ids'], 'mu_prob', sac._wk['pi_probs'], -sac.burn_in_step,
                                              sac._bt['padding_masks'])),
     ]
-    total = {name: 0.0 for name, _ in stages}
-    for it in range(steps + 3):
-        evs = []
-        for name, fn in stages:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            evs.append((name, e0, e1))
-        check(lib.asac_sac_advance_step(C.byref(sac._prm), s()))
+    # one tiny CUDA graph per stage, replayed back to back: device time without launch overhead
+    # (warm L2; the whole-step numbers of run_gpu() are the ones taken with a flushed L2)
+    out = {}
+    side = torch.cuda.Stream()
+    for name, fn in stages:
+        fn()
         torch.cuda.synchronize()
-        if it >= 3:
-            for name, e0, e1 in evs:
-                total[name] += e0.elapsed_time(e1) * 1e3  # us
-    return {k: v / steps for k, v in total.items()}
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            fn()
+        for _ in range(3):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) * 1e3 / steps  # us
+    return out
+
+
+def tensor_core_forward(rows=1 << 20, iters=10):
+    """The stock critic forward on `rows` rows: exact-fp32 FFMA kernel vs the tcgen05 3xTF32 kernel."""
+    from asac_b200 import _lib, lowering
+    from asac_b200._lib import check, ptr
+    lib = _lib.load()
+    in_dim, H, depth, out = CFG['obs_shape'][0] + CFG['A'], CFG['hidden'], CFG['depth'], 1
+    shape = lowering.NetShape(in_dim, H, depth, out)
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    flat = (torch.rand(shape.stride, device='cuda', generator=gen) - 0.5) * 0.3
+    x = torch.randn(rows, in_dim, device='cuda', generator=gen)
+    y = torch.zeros(rows, out, device='cuda')
+    s = _lib.current_stream()
+    flops = 2 * (in_dim * H + (depth - 1) * H * H + H * out) * rows
+    res = {'rows': rows, 'net': f'{in_dim}->{H}x{depth}->{out}'}
+    for name, fn in (('ffma_fp32', lib.asac_mlp_forward), ('tcgen05_3xtf32', lib.asac_mlp_forward_tc)):
+        for _ in range(3):
+            check(fn(ptr(flat), in_dim, H, depth, out, ptr(x), rows, ptr(y), s), name)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            check(fn(ptr(flat), in_dim, H, depth, out, ptr(x), rows, ptr(y), s), name)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        res[name] = {'ms': round(ms, 4), 'rows_per_s': rows / (ms * 1e-3), 'fp32_equiv_TFLOPs': flops / (ms * 1e-3) / 1e12}
+    res['tcgen05_3xtf32']['tensor_TFLOPs_issued'] = 3 * res['tcgen05_3xtf32']['fp32_equiv_TFLOPs'] * \
+        (8 * H + (depth - 1) * H * H + H * 16) / (in_dim * H + (depth - 1) * H * H + H * out)
+    return res
 
 
 def run_gpu(args):
@@ -341,14 +380,23 @@ def run_gpu(args):
                 ach = w['flops'] / (us * 1e-6) / 1e12
                 kernels[name] = {'us': round(us, 3), 'bound': 'tensor', 'algorithmic_flops': w['flops'],
                                  'achieved_TFLOPs': round(ach, 5), 'frac': ach / tf_peak}
-        top = max(prof, key=prof.get)
+        not_in_step = ('adam_alpha', 'per_update')  # standalone entry points; the step runs finish_step
+        in_step = {k: v for k, v in prof.items() if k not in not_in_step}
+        top = max(in_step, key=in_step.get)
         k = kernels[top]
+        traffic = None
+        tr = ROOT / 'profiles' / 'ncu_dram_traffic.json'  # dram__bytes_read+write per launch, `ncu --set full`
+        if tr.exists():
+            traffic = json.loads(tr.read_text()).get(top)
         out['roofline'] = {'kernel': top, 'bound': k['bound'],
                            'achieved': k.get('achieved_GBps', k.get('achieved_TFLOPs')),
                            'peak': hbm_peak if k['bound'] == 'hbm' else tf_peak,
-                           'unit': 'GB/s' if k['bound'] == 'hbm' else 'TFLOP/s', 'frac': k['frac'], 'traffic': None,
-                           'peak_source': src, 'share_of_step': prof[top] / sum(prof.values()),
-                           'note': 'fp32 FFMA row-tile kernel, latency-bound at B=256 (DESIGN.md §6)'}
+                           'unit': 'GB/s' if k['bound'] == 'hbm' else 'TFLOP/s', 'frac': k['frac'],
+                           'traffic': traffic, 'peak_source': src,
+                           'share_of_step': in_step[top] / sum(in_step.values()),
+                           'note': 'exact-fp32 FFMA row-tile kernel (1e-5 parity bound rules out plain tf32); one '
+                                   '16-row tile per SM at B=256, i.e. latency-bound, not pipe-bound (DESIGN.md §6)'}
+        out['tensor_core_forward'] = tensor_core_forward()
         per_us = prof['per_sample'] + prof['per_update']
         per_bytes = work['per_sample']['bytes'] + work['per_update']['bytes']
         out['per_sample_update'] = {'us': round(per_us, 3), 'algorithmic_bytes': per_bytes,
