@@ -65,6 +65,13 @@ class AsacWriteTable(C.Structure):
     _fields_ = [('n_columns', C.c_int32), ('col', AsacWriteColumn * MAX_COLUMNS)]
 
 
+MAX_PEERS = 16
+
+
+class AsacPeerTable(C.Structure):
+    _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('recv', vp * MAX_PEERS), ('recv_words', C.c_int64)]
+
+
 class AsacSacWork(C.Structure):
     _fields_ = [('n_tiles', C.c_int32),
                 ('y', vp), ('tq', vp), ('q_val', vp), ('loss_q', vp), ('grad_q_part', vp), ('grad_q', vp),
@@ -106,8 +113,11 @@ PROTOTYPES = {
     'asac_sac_td_error': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp]),
     'asac_sac_advance_step': (i32, [P(AsacSacParams), vp]),
     'asac_sac_step': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork), vp]),
-    'asac_sac_step_networks': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork), i32, vp]),
-    'asac_sac_finish_step': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp, i64, vp, vp, vp, vp]),
+    'asac_sac_step_networks': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork), i32,
+                                     P(AsacPeerTable), vp]),
+    'asac_sac_finish_step': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp, i64, vp, vp, vp,
+                                   P(AsacPeerTable), vp]),
+    'asac_peer_recv_words': (i64, [P(AsacSacConfig), i32]),
     'asac_fill_normal': (i32, [vp, i64, u64, vp, i32, vp]),
     'asac_mlp_forward': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp]),
     'asac_mlp_forward_tc': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp]),

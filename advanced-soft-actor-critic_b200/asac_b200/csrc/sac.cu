@@ -729,7 +729,50 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------ optimiser
+// ---- gradient exchange over NVLink peer memory (data-parallel learner)
+// Every rank owns a symmetric receive buffer of 8-byte words  recv[parity 2][source rank][total]
+// that all peers have mapped.  A thread that has reduced one element of the local gradient PUSHES
+// the pair {epoch, value} as ONE 64-bit store into every rank's buffer (its own included) and
+// then polls the words of all sources for the same element until they carry the step's epoch —
+// the flag travels with the data (the "LL" idea of NCCL's low-latency protocol), so no fence, no
+// separate flag round trip and no barrier sits between the backward pass and Adam: the cost is
+// one NVLink write latency.  Sources are summed in rank order, so every rank applies
+// bit-identical gradients.  Epochs only grow (optimizer step + 1) and the buffer alternates with
+// the epoch's parity: a source can be at most one epoch ahead of a consumer, never two.
+// (A first version used per-CTA flags behind __threadfence_system() + st.release.sys: two
+// system-scope fences with NVLink writes in flight per CTA cost more than the NCCL all-reduce.)
+struct PeerExchange {
+    int world, rank;          // world <= 1: no exchange
+    unsigned long long *recv[ASAC_MAX_PEERS];
+    int64_t total;            // words per (parity, source) block
+    int64_t off;              // where this gradient kind starts inside a block
+};
+__device__ __forceinline__ unsigned long long *peer_slot(const PeerExchange &x, int dst_rank, unsigned epoch,
+                                                         int src_rank) {
+    return x.recv[dst_rank] + ((int64_t)(epoch & 1u) * x.world + src_rank) * x.total + x.off;
+}
+__device__ __forceinline__ void peer_push(const PeerExchange &x, unsigned epoch, int64_t p, float v) {
+    const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+    for (int q = 0; q < x.world; ++q) {
+        unsigned long long *dst = peer_slot(x, q, epoch, x.rank) + p;
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(w) : "memory");
+    }
+}
+__device__ __forceinline__ float peer_sum(const PeerExchange &x, unsigned epoch, int64_t p) {
+    float s = 0.f;
+    for (int q = 0; q < x.world; ++q) {
+        const unsigned long long *src = peer_slot(x, x.rank, epoch, q) + p;
+        unsigned long long w;
+        do {
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+        } while ((unsigned)(w >> 32) != epoch);
+        s += __uint_as_float((unsigned)(w & 0xFFFFFFFFull));
+    }
+    return s;
+}
+
 struct AdamArgs {
+    PeerExchange px;
     float *param, *m, *v;
     const float *part;      // partial gradients (or nullptr: read `grad`)
     float *grad;            // reduced gradient (written when part != nullptr and write_grad)
@@ -771,14 +814,32 @@ __global__ void __launch_bounds__(ADAM_PARAMS_PER_CTA *ADAM_TILE_GROUPS) k_reduc
         s_bc[1] = (float)sqrt(bc2);
     }
     __syncthreads();
-    if (tg != 0 || p >= a.count) return;
-    if (a.part) {
-        gr = s_part[0][pl];
+    if (a.px.world > 1) {
+        // local slice -> every rank's receive buffer, then flags, then the rank-ordered sum
+        const unsigned epoch = (unsigned)(a.step[0] + 1);
+        if (tg == 0 && p < a.count) {
+            if (a.part) {
+                gr = s_part[0][pl];
 #pragma unroll
-        for (int g = 1; g < ADAM_TILE_GROUPS; ++g) gr += s_part[g][pl];
+                for (int g = 1; g < ADAM_TILE_GROUPS; ++g) gr += s_part[g][pl];
+            } else {
+                gr = a.grad[p];
+            }
+            peer_push(a.px, epoch, p, gr);
+        }
+        if (tg != 0 || p >= a.count) return;
+        gr = peer_sum(a.px, epoch, p);
         if (a.write_grad) a.grad[p] = gr;
     } else {
-        gr = a.grad[p];
+        if (tg != 0 || p >= a.count) return;
+        if (a.part) {
+            gr = s_part[0][pl];
+#pragma unroll
+            for (int g = 1; g < ADAM_TILE_GROUPS; ++g) gr += s_part[g][pl];
+            if (a.write_grad) a.grad[p] = gr;
+        } else {
+            gr = a.grad[p];
+        }
     }
     if (!a.do_adam) return;
     gr = gr * a.grad_scale;
@@ -797,9 +858,10 @@ __global__ void __launch_bounds__(ADAM_PARAMS_PER_CTA *ADAM_TILE_GROUPS) k_reduc
 // then y' = yq - alpha_new * yl and td = mean_i |Q_i(s_b, a_b) - y'|  (sac_base.py:2223-2245).  One CTA.
 // `staged` (shared memory, n_tiles floats) holds wrk.grad_alpha_part[t * 2], loaded by the whole CTA:
 // one thread summing the tiles straight from global memory serialised n_tiles L2 round trips
+// Executed by ONE thread.  With a peer exchange the scalar gradient travels like a 1-float slice.
 __device__ __forceinline__ void alpha_reduce_adam(const AsacSacParams &prm, const AsacSacWork &wrk, int n_tiles,
                                                   int batch, int do_reduce, int do_adam, float grad_scale,
-                                                  double lr, const float *staged) {
+                                                  double lr, const float *staged, const PeerExchange *px = nullptr) {
     {
         float gr;
         if (do_reduce) {
@@ -809,6 +871,12 @@ __device__ __forceinline__ void alpha_reduce_adam(const AsacSacParams &prm, cons
             wrk.grad_alpha[0] = gr;
         } else {
             gr = wrk.grad_alpha[0];
+        }
+        if (px && px->world > 1) {
+            const unsigned epoch = (unsigned)(prm.counters[3] + 1);
+            peer_push(*px, epoch, 0, gr);
+            gr = peer_sum(*px, epoch, 0);
+            wrk.grad_alpha[0] = gr;
         }
         if (do_adam) {
             gr = gr * grad_scale;
@@ -855,6 +923,8 @@ __global__ void __launch_bounds__(1024) k_alpha_td(const AsacSacParams prm, cons
 // y' and td error with the updated alpha (:2223-2245), PrioritizedReplayBuffer.update
 // (replay_buffer.py:412-427) and the step / optimizer counters (sac_base.py:2607).
 struct EpilogueArgs {
+    PeerExchange px;
+    float grad_scale;
     AsacSacParams prm;
     AsacSacWork wrk;
     int n_tiles, batch, ensemble, use_auto_alpha, counter_mask;
@@ -873,7 +943,7 @@ __global__ void __launch_bounds__(1024) k_step_epilogue(const __grid_constant__ 
     if (a.use_auto_alpha) {
         for (int i = t; i < a.n_tiles; i += blockDim.x) s_alpha[i] = __ldcg(a.wrk.grad_alpha_part + i * 2);
         __syncthreads();
-        if (t == 0) alpha_reduce_adam(a.prm, a.wrk, a.n_tiles, a.batch, 1, 1, 1.f, a.lr, s_alpha);
+        if (t == 0) alpha_reduce_adam(a.prm, a.wrk, a.n_tiles, a.batch, 1, 1, a.grad_scale, a.lr, s_alpha, &a.px);
     }
     __syncthreads();
     const float alpha = expf(__ldcg(a.prm.log_alpha));
@@ -1170,8 +1240,34 @@ extern "C" int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacP
     return ASAC_OK;
 }
 
+// fills the kernel-side exchange descriptor for gradient kind `which` (0 critics, 1 policy, 2 alpha)
+static int make_exchange(PeerExchange &x, const AsacSacConfig *cfg, const AsacPeerTable *peers, int which) {
+    memset(&x, 0, sizeof(x));
+    if (!peers || peers->world <= 1) return ASAC_OK;
+    ASAC_REQUIRE(peers->world <= ASAC_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+                 "peer table: world %d / rank %d", peers->world, peers->rank);
+    const int64_t nq = net_stride(q_shape(*cfg)) * cfg->ensemble, np = net_stride(pi_shape(*cfg));
+    x.world = peers->world; x.rank = peers->rank;
+    x.total = nq + np + 4;
+    x.off = which == 0 ? 0 : (which == 1 ? nq : nq + np);
+    ASAC_REQUIRE(peers->recv_words >= 2 * (int64_t)peers->world * x.total,
+                 "peer table: receive buffers hold %lld words, need %lld", (long long)peers->recv_words,
+                 (long long)(2 * (int64_t)peers->world * x.total));
+    for (int i = 0; i < peers->world; ++i) {
+        ASAC_REQUIRE(peers->recv[i] && (((uintptr_t)peers->recv[i]) & 7) == 0, "peer table: bad mapping for rank %d", i);
+        x.recv[i] = reinterpret_cast<unsigned long long *>(peers->recv[i]);
+    }
+    return ASAC_OK;
+}
+
+extern "C" int64_t asac_peer_recv_words(const AsacSacConfig *cfg, int world) {
+    if (validate(cfg) != ASAC_OK) return -1;
+    return 2 * (int64_t)world * (net_stride(q_shape(*cfg)) * cfg->ensemble + net_stride(pi_shape(*cfg)) + 4);
+}
+
 static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk, int which,
-                              int do_reduce, int do_adam, float grad_scale, void *stream, int do_td = 0) {
+                              int do_reduce, int do_adam, float grad_scale, void *stream, int do_td = 0,
+                              const AsacPeerTable *peers = nullptr) {
     int rc = validate(cfg);
     if (rc != ASAC_OK) return rc;
     ASAC_REQUIRE(which >= 0 && which <= 2, "which must be 0 (critics), 1 (policy) or 2 (alpha)");
@@ -1185,6 +1281,7 @@ static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm
         return ASAC_OK;
     }
     AdamArgs a;
+    if ((rc = make_exchange(a.px, cfg, peers, which)) != ASAC_OK) return rc;
     if (which == 0) {
         const int64_t stride = net_stride(q_shape(*cfg));
         a.param = prm->q; a.m = prm->q_m; a.v = prm->q_v;
@@ -1247,7 +1344,9 @@ extern "C" int asac_sac_td_error(const AsacSacConfig *cfg, const AsacSacParams *
 }
 
 extern "C" int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
-                                      const AsacSacWork *wrk, int with_polyak, void *stream) {
+                                      const AsacSacWork *wrk, int with_polyak, const AsacPeerTable *peers,
+                                      void *stream) {
+    const float gscale = (peers && peers->world > 1) ? 1.f / (float)peers->world : 1.f;
     SacArgs a;
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
@@ -1255,9 +1354,9 @@ extern "C" int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacPar
     if (with_polyak && (rc = asac_sac_polyak(cfg, prm, -1.f, stream)) != ASAC_OK) return rc;
     if ((rc = launch_value_pass(a, 0, stream)) != ASAC_OK) return rc;
     if ((rc = asac_sac_q_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
-    if ((rc = launch_reduce_adam(cfg, prm, wrk, 0, 1, 1, 1.f, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_reduce_adam(cfg, prm, wrk, 0, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
     if ((rc = asac_sac_policy_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
-    if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, 1.f, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
     const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
     if (need_post) {
         ASAC_REQUIRE(bat->eps_td && bat->eps_alpha, "asac_sac_step: missing eps_td / eps_alpha");
@@ -1268,7 +1367,7 @@ extern "C" int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacPar
 
 extern "C" int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
                              const AsacSacWork *wrk, void *stream) {
-    int rc = asac_sac_step_networks(cfg, prm, bat, wrk, 1, stream);
+    int rc = asac_sac_step_networks(cfg, prm, bat, wrk, 1, nullptr, stream);
     if (rc != ASAC_OK) return rc;
     int mask = 1 | 2 | 4;
     const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
@@ -1282,13 +1381,16 @@ extern "C" int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm,
 
 extern "C" int asac_sac_finish_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk,
                                     float *nodes, int64_t capacity, const int64_t *store_ids,
-                                    const int64_t *data_ids, double *per_state, void *stream) {
+                                    const int64_t *data_ids, double *per_state, const AsacPeerTable *peers,
+                                    void *stream) {
     int rc = validate(cfg);
     if (rc != ASAC_OK) return rc;
     ASAC_REQUIRE(is_pow2(capacity), "asac_sac_finish_step: capacity is not a power of two");
     ASAC_REQUIRE(cfg->batch <= 1024, "asac_sac_finish_step: batch %d > 1024", cfg->batch);
     ASAC_REQUIRE(prm && wrk && nodes && store_ids && data_ids && per_state, "asac_sac_finish_step: null pointer");
     EpilogueArgs a;
+    if ((rc = make_exchange(a.px, cfg, peers, 2)) != ASAC_OK) return rc;
+    a.grad_scale = (peers && peers->world > 1) ? 1.f / (float)peers->world : 1.f;
     a.prm = *prm; a.wrk = *wrk;
     a.n_tiles = wrk->n_tiles; a.batch = cfg->batch; a.ensemble = cfg->ensemble;
     a.use_auto_alpha = cfg->use_auto_alpha ? 1 : 0;

@@ -50,3 +50,33 @@ def broadcast_(tensors: list[torch.Tensor], src: int = 0, group=None) -> None:
     if world()[1] > 1:
         for t in tensors:
             dist.broadcast(t, src=src, group=group)
+
+
+class PeerGradientExchange:
+    """Symmetric NVLink-mapped receive buffer for the in-kernel gradient exchange
+    (include/asac_b200.h, AsacPeerTable).  Built on ``torch.distributed._symmetric_memory`` (CUDA
+    VMM handles exchanged through the process group's store): every rank allocates the buffer with
+    the same size, the rendezvous maps all of them into every process.  Raises when the mapping
+    cannot be established (the caller then keeps the NCCL all-reduce path)."""
+
+    def __init__(self, recv_words: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.recv = symm_mem.empty(int(recv_words), dtype=torch.int64, device=device)
+        self.recv.zero_()  # epoch 0 never matches: optimizer epochs start at 1
+        torch.cuda.synchronize(device)
+        self._hdl = symm_mem.rendezvous(self.recv, group.group_name)
+        self.recv_ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        if len(self.recv_ptrs) != self.world:
+            raise RuntimeError('symmetric memory rendezvous returned an unexpected number of peers')
+        dist.barrier(group)  # every rank's buffer is zeroed and mapped before the first kernel
+
+    def table(self):
+        from . import _lib
+        t = _lib.AsacPeerTable()
+        t.world, t.rank = self.world, self.rank
+        for i in range(self.world):
+            t.recv[i] = self.recv_ptrs[i]
+        t.recv_words = self.recv.numel()
+        return t

@@ -229,6 +229,7 @@ class SAC_Base:
                 self._logger.warning(f'no summary writer: {e}')
         self.summary_available = False
 
+        self._rank, self._world = adist.world()
         with torch.cuda.device(self.device):
             self._build_model(nn, nn_config, init_log_alpha)
             self._build_ckpt()
@@ -237,7 +238,6 @@ class SAC_Base:
             self._init_or_restore(int(last_ckpt) if last_ckpt is not None else None)
         self._graph = None
         self._graph_columns_key = None
-        self._rank, self._world = adist.world()
         # NCCL all-reduces are captured into the step's CUDA graph (ASAC_GRAPH_COLLECTIVES=0 keeps them eager)
         self._graph_collectives = os.environ.get('ASAC_GRAPH_COLLECTIVES', '1') != '0'
         if self._world > 1:
@@ -429,6 +429,17 @@ class SAC_Base:
         self._batch = batch
         self._noise_seed = (int(self._seed) if self._seed is not None else random.getrandbits(62)) ^ 0x5AC5AC
         self._side_stream = torch.cuda.Stream(device=dev)
+        # data-parallel learner: gradient exchange inside the reduce+Adam kernels over NVLink peer memory
+        # (ASAC_PEER_EXCHANGE=0, or a failed mapping, keeps the NCCL all-reduce between the kernels)
+        self._peers = self._peer_table = None
+        if self._world > 1 and os.environ.get('ASAC_PEER_EXCHANGE', '1') != '0':
+            try:
+                n_recv = self._lib.asac_peer_recv_words(C.byref(self._cfg), self._world)
+                self._peers = adist.PeerGradientExchange(n_recv, dev)
+                self._peer_table = self._peers.table()
+            except Exception as e:  # noqa: BLE001 - any failure of the mapping falls back to NCCL
+                self._logger.warning(f'peer-memory gradient exchange unavailable ({e}); using NCCL all-reduce')
+                self._peers = self._peer_table = None
 
     def _init_or_restore(self, last_ckpt: int | None) -> None:
         """sac_base.py:568-629."""
@@ -596,7 +607,8 @@ class SAC_Base:
         B = self.batch_size
         main = torch.cuda.current_stream(self.device)
         side = self._side_stream
-        fused = self._world == 1
+        peers = C.byref(self._peer_table) if self._peer_table is not None else None
+        fused = self._world == 1 or peers is not None  # one code path for 1 GPU and for NVLink peers
         fast_tail = fused and self.use_priority and B <= 1024
         # side branch: _update_target_variables (sac_base.py:2057-2058) + the four Gaussian draws
         side.wait_stream(main)
@@ -618,8 +630,10 @@ class SAC_Base:
         if not fused:
             self._enqueue_sac_step_data_parallel(stream)
         elif fast_tail:
-            check(lib.asac_sac_step_networks(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), 0, stream),
-                  'sac_step_networks')
+            check(lib.asac_sac_step_networks(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), 0, peers,
+                                             stream), 'sac_step_networks')
+        elif peers is not None:  # non-prioritized data-parallel run: NCCL path keeps the staged tail
+            self._enqueue_sac_step_data_parallel(stream)
         else:
             check(lib.asac_sac_step(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), stream), 'sac_step')
         # 4. mu-prob write-back (sac_base.py:2598-2605): needs the post pass only -> side branch
@@ -632,8 +646,8 @@ class SAC_Base:
         if self.use_priority:
             if fast_tail:
                 check(lib.asac_sac_finish_step(C.byref(cfg), C.byref(prm), C.byref(work), ptr(rb._nodes), rb.capacity,
-                                               ptr(rb._store_ids), ptr(smp['ids']), ptr(rb._per_state), stream),
-                      'sac_finish_step')
+                                               ptr(rb._store_ids), ptr(smp['ids']), ptr(rb._per_state), peers,
+                                               stream), 'sac_finish_step')
             else:
                 check(lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), ptr(smp['ids']),
                                           ptr(self._wk['td_error']), B, float(rb.td_error_min),

@@ -180,7 +180,7 @@ def profile_stages(sac, steps):
         ('value_pass_post', lambda: check(lib.asac_sac_post(cfg, prm, batch, work, s()))),
         ('finish_step', lambda: check(lib.asac_sac_finish_step(cfg, prm, work, ptr(rb._nodes), rb.capacity,
                                                                ptr(rb._store_ids), ptr(smp['ids']),
-                                                               ptr(rb._per_state), s()))),
+                                                               ptr(rb._per_state), None, s()))),
         ('adam_alpha', lambda: check(lib.asac_sac_reduce_adam(cfg, prm, work, 2, s()))),
         ('per_update', lambda: check(lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids),
                                                          ptr(smp['ids']), ptr(sac._wk['td_error']), B,

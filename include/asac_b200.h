@@ -32,6 +32,7 @@ extern "C" {
 #define ASAC_MAX_NSTEP 16
 #define ASAC_MAX_DEPTH 4
 #define ASAC_MAX_ENSEMBLE 8
+#define ASAC_MAX_PEERS 16
 
 const char *asac_last_error(void);
 int asac_version(void);
@@ -311,11 +312,28 @@ int asac_sac_advance_step(const AsacSacParams *prm, void *stream);
 int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
                   const AsacSacWork *work, void *stream);
 
+/* Data-parallel learner (new capability; the reference trains on one device, sac_base.py:237-243):
+ * the gradient exchange runs INSIDE the reduce+Adam kernels over NVLink peer memory.  Every rank
+ * allocates one ZERO-INITIALISED receive buffer of asac_peer_recv_words() 8-byte words in memory
+ * that all ranks of the node have mapped (torch symmetric memory / cudaIpc); recv[i] is rank i's
+ * buffer as seen from THIS process.  A thread pushes {optimizer-step epoch, gradient element} as
+ * one 64-bit store into every rank's buffer and polls the same element of all sources until it
+ * carries the epoch (flag-in-data, no fences), then sums the sources in rank order: all ranks
+ * step with bit-identical mean gradients and no all-reduce kernel sits between the backward
+ * pass and Adam.  NULL = single GPU. */
+typedef struct {
+    int32_t world, rank;
+    void *recv[ASAC_MAX_PEERS];
+    int64_t recv_words;    /* size of each receive buffer in 8-byte words */
+} AsacPeerTable;
+int64_t asac_peer_recv_words(const AsacSacConfig *cfg, int world);
+
 /* asac_sac_step without its tail: [polyak,] target_y, q_backward, reduce_adam(q), policy_backward,
  * reduce_adam(pi), post.  `with_polyak` = 0 when the caller has enqueued asac_sac_polyak itself
- * (e.g. on a parallel graph branch). */
+ * (e.g. on a parallel graph branch).  `peers` != NULL: gradients are averaged over the ranks. */
 int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
-                           const AsacSacWork *work, int with_polyak, void *stream);
+                           const AsacSacWork *work, int with_polyak, const AsacPeerTable *peers,
+                           void *stream);
 
 /* The tail of SAC_Base.train() for a prioritized run in one single-CTA kernel (batch <= 1024):
  * alpha reduce + Adam (sac_base.py:1941-1948), _get_td_error's tail with the updated alpha
@@ -324,7 +342,8 @@ int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacParams *prm, c
  * counters (sac_base.py:2607).  Equals asac_sac_step's tail followed by asac_per_update. */
 int asac_sac_finish_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *work,
                          float *nodes, int64_t capacity, const int64_t *store_ids,
-                         const int64_t *data_ids, double *per_state, void *stream);
+                         const int64_t *data_ids, double *per_state, const AsacPeerTable *peers,
+                         void *stream);
 
 /* N(0,1) draws for eps_* (Philox4x32-10 + Box-Muller), keyed by (seed, counter[0], stream_id) */
 int asac_fill_normal(float *out, int64_t n, uint64_t seed, const int64_t *counter, int stream_id,

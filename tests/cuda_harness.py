@@ -219,11 +219,11 @@ class SacCuda:
 
     def step_networks(self, batch, with_polyak=1):
         check(self.lib.asac_sac_step_networks(C.byref(self.cfg), C.byref(self.prm), C.byref(batch),
-                                              C.byref(self.work), int(with_polyak), self._s()), 'sac_step_networks')
+                                              C.byref(self.work), int(with_polyak), None, self._s()), 'sac_step_networks')
 
     def finish_step(self, nodes, capacity, store_ids, data_ids, per_state):
         check(self.lib.asac_sac_finish_step(C.byref(self.cfg), C.byref(self.prm), C.byref(self.work), ptr(nodes),
-                                            capacity, ptr(store_ids), ptr(data_ids), ptr(per_state), self._s()),
+                                            capacity, ptr(store_ids), ptr(data_ids), ptr(per_state), None, self._s()),
               'sac_finish_step')
 
     def staged_step(self, batch) -> dict:
