@@ -97,6 +97,10 @@ PROTOTYPES = {
     'asac_per_add': (i32, [vp, i64, vp, i64, i64, vp, i32, vp]),
     'asac_storage_write_rows': (i32, [vp, i64, i64, vp, i64, i64, vp]),
     'asac_storage_write_table': (i32, [P(AsacWriteTable), i64, i64, i64, vp]),
+    'asac_ingest_create': (i32, [P(vp), i64, i32, P(vp), P(i64), vp, vp, vp, vp]),
+    'asac_ingest_add': (i32, [vp, P(vp), i64, i64, i32, i32, vp]),
+    'asac_ingest_row_bytes': (i64, [vp]),
+    'asac_ingest_destroy': (None, [vp]),
     'asac_storage_gather': (i32, [P(AsacColumnTable), i64, vp, i32, i32, i32, vp, vp, vp]),
     'asac_storage_scatter': (i32, [vp, i64, vp, vp, i32, i32, i32, vp, i64, i64, vp, i64, vp]),
     'asac_sac_tile_batch': (i32, [P(AsacSacConfig)]),

@@ -34,6 +34,9 @@ _NP_TO_TORCH = {np.dtype('float32'): torch.float32, np.dtype('float64'): torch.f
                 np.dtype('float16'): torch.float16}
 
 
+_TORCH_TO_NP = {v: k for k, v in _NP_TO_TORCH.items()}
+
+
 def _align16(n: int) -> int:
     return (n + 15) & ~15
 
@@ -96,6 +99,8 @@ class PrioritizedReplayBuffer:
         self._next_id = 0
         self._seed = int(np.random.SeedSequence().entropy & 0x7FFFFFFFFFFFFFFF) if seed is None else int(seed)
         self._updates = 0
+        self._ingest = None   # native ingest handle (asac_ingest_*), bound to the current rings
+        self._columns_version = 0  # bumped whenever the rings change (the learner re-captures its graph)
         self._stage = [None, None, None, None]  # pinned host + device staging buffers, round robin
         self._stage_next = 0
         self._stage_limit = 64 << 20
@@ -117,6 +122,7 @@ class PrioritizedReplayBuffer:
         return col[0].numel() * col.element_size()
 
     def _allocate(self, transitions: dict) -> None:
+        self._drop_ingest()
         self._columns = {}
         for k, v in transitions.items():
             dtype = v.dtype if isinstance(v, torch.Tensor) else _NP_TO_TORCH[np.asarray(v).dtype]
@@ -191,8 +197,66 @@ class PrioritizedReplayBuffer:
         if self._next_id == self.max_id:
             self._next_id = 0
 
+    def _ingest_handle(self):
+        """Native ingest context over the current rings (created lazily, dropped with them)."""
+        if self._ingest is None:
+            keys = list(self._columns)
+            n = len(keys)
+            rings = (C.c_void_p * n)(*[self._columns[k].data_ptr() for k in keys])
+            rbs = (C.c_int64 * n)(*[self._row_bytes(k) for k in keys])
+            h = C.c_void_p()
+            check(self._lib.asac_ingest_create(C.byref(h), self.capacity, n, rings, rbs, ptr(self._nodes),
+                                               ptr(self._store_ids), ptr(self._max_p), ptr(self._td_max)),
+                  'ingest_create')
+            self._ingest = h
+            self._ingest_keys = keys
+            self._ingest_spec = [(k, _TORCH_TO_NP[self._columns[k].dtype], tuple(self._columns[k].shape[1:]))
+                                 for k in keys]
+            self._ingest_ptrs = (C.c_void_p * n)()
+        return self._ingest
+
+    def _drop_ingest(self) -> None:
+        """Called whenever the rings are (re)allocated or released."""
+        self._columns_version += 1
+        if getattr(self, '_ingest', None) is not None:
+            self._lib.asac_ingest_destroy(self._ingest)
+        self._ingest = None
+
+    def _add_native(self, transitions: dict, ignore_size: int) -> bool:
+        """add() for host arrays through asac_ingest_add: one call packs, copies and inserts.
+        Returns False when the episode does not qualify (device tensors, key order, T > capacity)."""
+        if self._columns is None:
+            self._allocate(transitions)
+        h = self._ingest_handle()
+        if len(transitions) != len(self._ingest_spec):
+            return False
+        T, keep = -1, []
+        for i, (k, dt, shape) in enumerate(self._ingest_spec):
+            v = transitions.get(k)
+            if not isinstance(v, np.ndarray) or v.dtype != dt or v.shape[1:] != shape:
+                if isinstance(v, np.ndarray) and (v.dtype != dt or v.shape[1:] != shape):
+                    raise ValueError(f'column {k}: got {v.dtype}{v.shape[1:]}, stored {dt}{shape}')
+                return False
+            if not v.flags.c_contiguous:
+                v = np.ascontiguousarray(v)
+            if T < 0:
+                T = v.shape[0]
+            elif v.shape[0] != T:
+                raise ValueError('columns disagree in length')
+            keep.append(v)
+            self._ingest_ptrs[i] = v.__array_interface__['data'][0]
+        if T <= 0 or T > self.capacity:
+            return False
+        first_id = self._next_id
+        check(self._lib.asac_ingest_add(h, self._ingest_ptrs, T, first_id, int(ignore_size),
+                                        1 if self._size == 0 else 0, self._stream), 'ingest_add')
+        self._advance(first_id, T)
+        return True
+
     def add(self, transitions: dict[str, np.ndarray], ignore_size=0) -> None:
         with torch.cuda.device(self.device):
+            if self._add_native(transitions, ignore_size):
+                return
             if self._size == 0:
                 max_p = self._td_max
             else:
@@ -384,6 +448,7 @@ class PrioritizedReplayBuffer:
             saved = np.load(storage_path)
             self._size = int(saved['p_size'])
             self._next_id = int(saved['p_id'])
+            self._drop_ingest()
             self._columns = {}
             for k in saved.files:
                 if k in ('p_size', 'p_id'):
@@ -395,6 +460,7 @@ class PrioritizedReplayBuffer:
                     self._columns[k] = t.contiguous()
 
     def clear(self) -> None:
+        self._drop_ingest()
         self._size = 0
         self._next_id = 0
         self._columns = None
@@ -404,6 +470,7 @@ class PrioritizedReplayBuffer:
     def copy(self, src: 'PrioritizedReplayBuffer') -> None:
         if src.capacity != self.capacity:
             raise ValueError('capacity mismatch')
+        self._drop_ingest()
         self._nodes.copy_(src._nodes)
         self._store_ids.copy_(src._store_ids)
         self._columns = None if src._columns is None else {k: v.to(self.device).clone()
@@ -434,4 +501,6 @@ class PrioritizedReplayBuffer:
         if self._closed:
             return
         self._closed = True
+        torch.cuda.synchronize(self.device)
+        self._drop_ingest()
         self._columns = None

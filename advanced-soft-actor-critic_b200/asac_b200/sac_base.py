@@ -688,7 +688,7 @@ class SAC_Base:
         if not rb.is_lg_batch_size:
             return step
         with torch.cuda.device(self.device):
-            key = tuple((k, v.data_ptr()) for k, v in rb._columns.items())
+            key = rb._columns_version
             if self._graph_columns_key != key:  # first step, or the storage was re-allocated (load / clear)
                 self._specs = self._gather_specs()
                 self._graph, self._graph_columns_key = None, key

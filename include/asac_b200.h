@@ -129,6 +129,24 @@ typedef struct {
 int asac_storage_write_table(const AsacWriteTable *table_host, int64_t capacity, int64_t first_id,
                              int64_t T, void *stream);
 
+/* PrioritizedReplayBuffer.add for a HOST-resident episode as one call (replay_buffer.py:293-315 +
+ * DataStorage.add :30-56): packs the columns into a pinned staging buffer owned by the handle,
+ * one cudaMemcpyAsync, then asac_tree_leaf_max (unless the buffer was empty: td_error_max is used,
+ * :296-299), asac_storage_write_table and asac_per_add on `stream`.  The handle owns only its
+ * staging buffers/events; `rings` (one [capacity, row_bytes] device array per key, in the order
+ * of `host_columns`), `nodes`, `store_ids`, `max_p_scratch` (device float) and `td_max_dev`
+ * (device float holding td_error_max) stay the caller's and must outlive the handle.
+ * host_columns[c] is [T, row_bytes[c]] contiguous host memory; T <= capacity; first_id is
+ * DataStorage._id before the call. */
+typedef struct AsacIngest AsacIngest;
+int asac_ingest_create(AsacIngest **out, int64_t capacity, int n_columns, void *const *rings,
+                       const int64_t *row_bytes, float *nodes, int64_t *store_ids, float *max_p_scratch,
+                       const float *td_max_dev);
+int asac_ingest_add(AsacIngest *h, const void *const *host_columns, int64_t T, int64_t first_id,
+                    int ignore_size, int buffer_empty, void *stream);
+int64_t asac_ingest_row_bytes(const AsacIngest *h);
+void asac_ingest_destroy(AsacIngest *h);
+
 enum {
     ASAC_ROLE_COPY = 0,      /* obs, last_mask: copied as stored                           */
     ASAC_ROLE_INDEX = 1,     /* int32 episode index: -1 on padded rows (sac_base.py:2445)  */
