@@ -1006,6 +1006,59 @@ __global__ void __launch_bounds__(256) k_fill_normal(float *out, int64_t n, uint
         if (q * 4 + i < n) out[q * 4 + i] = z[i];
 }
 
+// Actor side (sac_base.py:943-964, continuous branch of _choose_action): from the policy head's
+// pre-activations to the squashed action and its per-dimension probability.
+//   c_action = offline | tanh(mean) (disable_sample) | tanh(Normal(mu, sigma).sample())
+//   prob_j   = exp(logN(x_j)) / prod_k max(1 - tanh(x_k)^2, 1e-2),  x = atanh(clamp(c_action, +-0.999))
+// (utils/operators.py:17-19).  eps == nullptr: N(0,1) from Philox keyed by (seed, counter[0], row).
+struct ActArgs {
+    const float *pre;       // [rows, 2A]: mean, logstd pre-activations
+    const float *eps;       // [rows, A] or null
+    const float *offline;   // [rows, A] or null
+    float *action, *prob;   // [rows, A]
+    int64_t rows;
+    int A, disable_sample;
+    uint64_t seed;
+    const int64_t *counter;
+};
+__global__ void __launch_bounds__(256) k_policy_sample(const ActArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.rows) return;
+    const int A = a.A;
+    const float *pre = a.pre + r * 2 * A;
+    float fl = 1.f;
+    for (int j = 0; j < A; ++j) {
+        const float mu = policy_loc(pre[j]), sg = policy_scale(pre[A + j]);
+        float act;
+        if (a.offline) {
+            act = a.offline[r * A + j];
+        } else if (a.disable_sample) {
+            act = tanhf(mu);
+        } else {
+            float e;
+            if (a.eps) {
+                e = a.eps[r * A + j];
+            } else {
+                uint32_t rnd[4];
+                philox4(a.seed ^ 0xAC7ull, (uint64_t)a.counter[0], (uint64_t)(r * A + j), rnd);
+                const float u1 = ((float)(rnd[0] >> 8) + 1.f) * (1.f / 16777216.f);
+                const float u2 = (float)(rnd[1] >> 8) * (1.f / 16777216.f);
+                float sn, cs;
+                sincospif(2.f * u2, &sn, &cs);
+                e = sqrtf(-2.f * logf(u1)) * cs;
+            }
+            act = tanhf(mu + e * sg);  // torch.normal(mean, std)
+        }
+        a.action[r * A + j] = act;
+        fl *= squash_floor(atanhf(fminf(fmaxf(act, -0.999f), 0.999f)));
+    }
+    for (int j = 0; j < A; ++j) {
+        const float mu = policy_loc(pre[j]), sg = policy_scale(pre[A + j]);
+        const float x = atanhf(fminf(fmaxf(a.action[r * A + j], -0.999f), 0.999f));
+        a.prob[r * A + j] = expf(normal_log_prob(x, mu, sg)) / fl;
+    }
+}
+
 // standalone stock-net forward (actor side / tests)
 struct MlpArgs {
     const float *params, *x;
@@ -1430,5 +1483,29 @@ extern "C" int asac_mlp_forward(const float *params, int in_dim, int hidden, int
     if (rc != ASAC_OK) return rc;
     k_mlp_forward<<<(unsigned)((rows + a.rows_per_cta - 1) / a.rows_per_cta), NT, bytes, (cudaStream_t)stream>>>(a);
     ASAC_LAUNCHED("k_mlp_forward");
+    return ASAC_OK;
+}
+
+extern "C" int asac_mlp_forward_tc(const float *params, int in_dim, int hidden, int depth, int out_dim, const float *x,
+                                   int64_t rows, float *out, void *stream);
+
+extern "C" int asac_policy_act(const float *params, int state_size, int hidden, int depth, int action_size,
+                               const float *states, int64_t rows, const float *eps, const float *offline_action,
+                               int disable_sample, uint64_t seed, const int64_t *counter, float *scratch,
+                               float *out_action, float *out_prob, int use_tensor_cores, void *stream) {
+    ASAC_REQUIRE(params && states && scratch && out_action && out_prob, "asac_policy_act: null pointer");
+    ASAC_REQUIRE(rows > 0 && action_size > 0 && action_size <= 64, "asac_policy_act: bad sizes");
+    ASAC_REQUIRE(eps || offline_action || disable_sample || counter, "asac_policy_act: need eps or a Philox counter");
+    int rc;
+    if (use_tensor_cores && hidden == 64 && 2 * action_size <= 16)
+        rc = asac_mlp_forward_tc(params, state_size, hidden, depth, 2 * action_size, states, rows, scratch, stream);
+    else
+        rc = asac_mlp_forward(params, state_size, hidden, depth, 2 * action_size, states, rows, scratch, stream);
+    if (rc != ASAC_OK) return rc;
+    ActArgs a;
+    a.pre = scratch; a.eps = eps; a.offline = offline_action; a.action = out_action; a.prob = out_prob;
+    a.rows = rows; a.A = action_size; a.disable_sample = disable_sample; a.seed = seed; a.counter = counter;
+    k_policy_sample<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_policy_sample");
     return ASAC_OK;
 }

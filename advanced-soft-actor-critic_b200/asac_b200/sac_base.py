@@ -429,6 +429,8 @@ class SAC_Base:
         self._batch = batch
         self._noise_seed = (int(self._seed) if self._seed is not None else random.getrandbits(62)) ^ 0x5AC5AC
         self._side_stream = torch.cuda.Stream(device=dev)
+        self._act_counter = torch.zeros(1, dtype=torch.int64, device=dev)  # Philox counter of choose_action
+        self.actor_tensor_cores = False
         # data-parallel learner: gradient exchange inside the reduce+Adam kernels over NVLink peer memory
         # (ASAC_PEER_EXCHANGE=0, or a failed mapping, keeps the NCCL all-reduce between the kernels)
         self._peers = self._peer_table = None
@@ -535,9 +537,49 @@ class SAC_Base:
     # ------------------------------------------------------------------ actor side
     @torch.no_grad()
     def choose_action(self, obs_list, pre_action, pre_seq_hidden_state, offline_action=None,
-                      disable_sample: bool = False, force_rnd_if_available: bool = False):
-        """sac_base.py:968-1019 (continuous branch of _choose_action :882-966); torch modules on the
-        same parameter storage the kernels train."""
+                      disable_sample: bool = False, force_rnd_if_available: bool = False, eps=None):
+        """sac_base.py:968-1019 (continuous branch of _choose_action :882-966) on the device kernels:
+        the concatenated vector observations go through the policy's flat parameters
+        (asac_policy_act: exact-fp32 row-tile forward; with ``self.actor_tensor_cores = True`` the
+        tcgen05 3xTF32 forward from 2048 rows on) and one elementwise kernel samples, squashes and
+        evaluates the per-dimension probability.  The tensor-core forward is opt-in because the
+        probability amplifies the 1.5e-6 error of the pre-activations by |x - mu| / sigma^2.
+        ``eps`` ([batch, A] N(0,1) draws) replaces the on-device Philox draws (tests)."""
+        if self.action_noise is not None:
+            return self._choose_action_torch(obs_list, pre_action, pre_seq_hidden_state, offline_action,
+                                             disable_sample)
+        with torch.cuda.device(self.device):
+            A, S = self.c_action_size, self.state_size
+            parts = []
+            for (name, shape), o in zip(zip(self.obs_names, self.obs_shapes), obs_list):
+                if len(shape) != 1:
+                    continue  # ModelSimpleRep ignores non-vector observations (representation.py:74-83)
+                t = torch.from_numpy(np.ascontiguousarray(o)).to(self.device, non_blocking=True)
+                parts.append(t.float() if t.dtype != torch.float32 else t)
+            state = parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
+            state = state.contiguous()
+            rows = int(state.shape[0])
+            f32 = dict(dtype=torch.float32, device=self.device)
+            scratch, action, prob = torch.empty(rows, 2 * A, **f32), torch.empty(rows, A, **f32), \
+                torch.empty(rows, A, **f32)
+            off = None if offline_action is None else \
+                torch.from_numpy(np.ascontiguousarray(offline_action, dtype=np.float32)).to(self.device).contiguous()
+            e = None if eps is None else torch.as_tensor(eps, dtype=torch.float32).to(self.device).contiguous()
+            sh = self._pi_shape
+            check(self._lib.asac_policy_act(ptr(self._pi_flat), S, sh.hidden, sh.depth, A, ptr(state), rows, ptr(e),
+                                            ptr(off), int(bool(disable_sample)), self._noise_seed,
+                                            ptr(self._act_counter), ptr(scratch), ptr(action), ptr(prob),
+                                            1 if (self.actor_tensor_cores and rows >= 2048) else 0,
+                                            _lib.current_stream()), 'policy_act')
+            self._act_counter += 1
+            hidden = np.zeros((rows, *self.seq_hidden_state_shape), dtype=np.float32)
+            return action.cpu().numpy(), prob.cpu().numpy(), hidden
+
+    @torch.no_grad()
+    def _choose_action_torch(self, obs_list, pre_action, pre_seq_hidden_state, offline_action=None,
+                             disable_sample: bool = False, eps=None):
+        """The same computation with the plugin's torch modules on the shared parameter storage
+        (kept for action_noise runs and as the in-process cross-check of the kernels)."""
         obs = [torch.from_numpy(np.asarray(o)).to(self.device) for o in obs_list]
         for i, o in enumerate(obs):
             if o.dtype == torch.uint8:
@@ -551,8 +593,15 @@ class SAC_Base:
             c_action = torch.from_numpy(offline_action).to(self.device)
         elif disable_sample:
             c_action = torch.tanh(c_policy.mean)
+        elif eps is not None:
+            c_action = torch.tanh(c_policy.mean + c_policy.stddev * torch.as_tensor(eps, device=self.device))
         else:
             c_action = torch.tanh(c_policy.sample())
+        if self.action_noise is not None:  # sac_base.py:859-880
+            batch = c_action.shape[0]
+            noise = torch.linspace(*self.action_noise, steps=batch, device=self.device)
+            c_action = torch.tanh(torch.atanh(c_action) + torch.randn(batch, self.c_action_size, device=self.device)
+                                  * noise.unsqueeze(1))
         x = torch.atanh(torch.clamp(c_action, -0.999, 0.999))
         floor = torch.clamp_min(1 - torch.tanh(x) ** 2, 1e-2)
         prob = torch.exp(c_policy.log_prob(x)) / floor.prod(-1, keepdim=True)  # operators.py:17-19

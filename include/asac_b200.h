@@ -378,6 +378,16 @@ int asac_mlp_forward(const float *params, int in_dim, int hidden, int depth, int
 int asac_mlp_forward_tc(const float *params, int in_dim, int hidden, int depth, int out_dim,
                         const float *x, int64_t rows, float *out, void *stream);
 
+/* Actor side: SAC_Base._choose_action for a stock continuous policy (sac_base.py:882-966, branch
+ * :943-964): policy forward on `states` [rows, S] (asac_mlp_forward, or the tcgen05 kernel when
+ * use_tensor_cores != 0), then c_action = offline_action | tanh(mean) | tanh(Normal.sample()) and
+ * prob = squash_correction_prob(policy, atanh(clamp(c_action, +-0.999))) (utils/operators.py:17-19).
+ * eps: injected N(0,1) draws [rows, A] (NULL: Philox keyed by seed, counter[0]); scratch: [rows, 2A]. */
+int asac_policy_act(const float *params, int state_size, int hidden, int depth, int action_size,
+                    const float *states, int64_t rows, const float *eps, const float *offline_action,
+                    int disable_sample, uint64_t seed, const int64_t *counter, float *scratch,
+                    float *out_action, float *out_prob, int use_tensor_cores, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -162,3 +162,38 @@ def test_unsupported_configurations_fail_loudly(tmp_path):
         SAC_Base(d_action_sizes=[], use_rnd=True, **base)
     with pytest.raises(Exception):
         SAC_Base(d_action_sizes=[], device='cpu', **base)
+
+
+def test_choose_action_kernels_match_torch_modules(tmp_path):
+    """choose_action on asac_policy_act (FFMA forward for small batches, tcgen05 forward from 2048
+    rows on) against the plugin's torch modules on the same parameters, same injected draws
+    (sac_base.py:943-964): actions and per-dimension probabilities within 1e-5 of scale; the
+    deterministic and offline-action branches too."""
+    sac = _make(_plugin(tmp_path, PLUGIN_TEST, 'nn_plugin_act'), graph=True, batch_size=32)
+    rng = np.random.RandomState(0)
+    with torch.no_grad():
+        for p in sac.model_policy.parameters():
+            p.add_(torch.randn_like(p) * 0.05)  # in place: the kernels read the same storage
+    for rows, tc in ((1, False), (37, False), (4096, False), (4096, True)):
+        sac.actor_tensor_cores = tc
+        p_tol = 2e-3 if tc else 1e-4  # 3xTF32 pre-activations (1.5e-6) amplified by |x - mu| / sigma^2
+        obs = [rng.randn(rows, 6).astype(np.float32)]
+        eps = rng.randn(rows, 2).astype(np.float32)
+        pre_a, pre_h = np.zeros((rows, 2), np.float32), np.zeros((rows, 0), np.float32)
+        for kw in (dict(eps=eps), dict(disable_sample=True), dict(offline_action=rng.rand(rows, 2).astype(np.float32))):
+            a0, p0, h0 = sac.choose_action(obs, pre_a, pre_h, **kw)
+            a1, p1, h1 = sac._choose_action_torch(obs, pre_a, pre_h, **kw)
+            assert a0.shape == (rows, 2) and p0.shape == (rows, 2) and h0.shape == h1.shape == (rows, 0)
+            assert np.max(np.abs(a0 - a1)) < 1e-5, (rows, kw.keys())
+            # prob goes through atanh(tanh(x)): one ulp of the action is amplified by 1 / (1 - a^2) (x 50 at
+            # |a| = 0.99) and again by |x - mu| / sigma^2 in the Gaussian, so the MAX relative difference of
+            # two fp32 evaluations over thousands of samples is a heavy-tailed statistic: bound the bulk
+            # tightly and the tail loosely (actions themselves agree to 1e-5 above)
+            rel = (np.abs(p0 - p1) / np.maximum(1.0, np.abs(p1))).reshape(-1)
+            assert np.median(rel) < (1e-5 if tc else 1e-6) and np.quantile(rel, 0.99) < p_tol and rel.max() < 100 * p_tol, \
+                (rows, tc, kw.keys(), float(np.median(rel)), float(np.quantile(rel, 0.99)), float(rel.max()))
+    # on-device Philox draws: different every call, finite, inside the squashed range
+    a, p, _ = sac.choose_action([rng.randn(64, 6).astype(np.float32)], None, None)
+    b, _, _ = sac.choose_action([rng.randn(64, 6).astype(np.float32)], None, None)
+    assert np.all(np.abs(a) < 1) and np.all(np.isfinite(p)) and not np.array_equal(a, b)
+    sac.close()
