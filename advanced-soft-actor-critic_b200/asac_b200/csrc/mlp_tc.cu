@@ -6,7 +6,11 @@
 // forwards (nn_models/q.py:74-91, nn_models/policy.py:150-170) — the evaluation the actor side
 // and the large-batch value passes spend their time in.
 //
-// One persistent CTA per SM walks 128-row tiles:
+// One persistent CTA per SM walks 128-row tiles, TWO tile groups of 8 warps each when shared
+// memory allows: each group owns its A operands, its TMEM accumulator columns, its mbarrier and
+// a named barrier, and runs the layers of its tile independently of the other group, so the
+// tensor pipe works on one group's MMAs while the CUDA cores run the other group's epilogue
+// (v1 ran MMA and epilogue of a single tile back to back: tensor pipe 7.8 % active).
 //   * operands live in shared memory in the UMMA K-major, no-swizzle "core matrix" layout
 //     (8 rows x 16 bytes contiguous; consecutive K chunks 128 B apart, 8-row groups SBO apart),
 //     each as a (hi, lo) pair: hi = x with the 13 low mantissa bits cleared (exact in tf32),
@@ -27,8 +31,9 @@
 namespace asac {
 
 constexpr int TC_ROWS = 128;     // UMMA_M
-constexpr int TC_THREADS = 256;  // 8 warps: 2 per TMEM lane quarter
+constexpr int TC_THREADS = 256;  // per tile group: 8 warps, 2 per TMEM lane quarter
 constexpr int TC_HEAD_N = 16;    // padded head width (UMMA_N % 16 == 0 for M = 128)
+constexpr int TC_PREFETCH = 2;   // float4 registers per thread holding the next tile's input rows
 
 // ---------------------------------------------------------------- tcgen05 primitives
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
@@ -113,20 +118,22 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
 // ---------------------------------------------------------------- shared-memory plan
 struct TcPlan {
     int K0p;                  // first-layer K padded to 8
-    int off_a_hi, off_a_lo;   // [128, max(K0p, H)] activations
+    int off_a_hi[2], off_a_lo[2];   // per tile group: [128, max(K0p, H)] activations
     int off_w[ASAC_MAX_DEPTH + 1][2];  // per layer (head last): hi, lo
     int off_bias;             // depth * H + TC_HEAD_N
     int off_misc;             // mbarrier, tmem address
     int total;                // floats
 };
-__host__ __device__ __forceinline__ TcPlan tc_plan(const NetShape &s) {
+__host__ __device__ __forceinline__ TcPlan tc_plan(const NetShape &s, int groups) {
     TcPlan p;
     const int H = s.hidden;
     p.K0p = round_up(s.in_dim, 8);
     const int ka = p.K0p > H ? p.K0p : H;
     int o = 0;
-    p.off_a_hi = o; o += TC_ROWS * ka;
-    p.off_a_lo = o; o += TC_ROWS * ka;
+    for (int g = 0; g < 2; ++g) {
+        p.off_a_hi[g] = o; o += g < groups ? TC_ROWS * ka : 0;
+        p.off_a_lo[g] = o; o += g < groups ? TC_ROWS * ka : 0;
+    }
     for (int l = 0; l < s.depth; ++l) {
         const int K = l == 0 ? p.K0p : H;
         p.off_w[l][0] = o; o += H * K;
@@ -135,7 +142,7 @@ __host__ __device__ __forceinline__ TcPlan tc_plan(const NetShape &s) {
     p.off_w[s.depth][0] = o; o += TC_HEAD_N * H;
     p.off_w[s.depth][1] = o; o += TC_HEAD_N * H;
     p.off_bias = o; o += s.depth * H + TC_HEAD_N;
-    p.off_misc = o; o += 8;
+    p.off_misc = o; o += 8;   // 2 mbarriers (16 B), tmem address
     p.total = o;
     return p;
 }
@@ -147,20 +154,27 @@ struct TcArgs {
     int64_t rows;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_forward_tc(const TcArgs a) {
+__device__ __forceinline__ void group_sync(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(TC_THREADS) : "memory");
+}
+
+template <int GROUPS>
+__global__ void __launch_bounds__(TC_THREADS *GROUPS, 1) k_mlp_forward_tc(const TcArgs a) {
     extern __shared__ __align__(128) float smem_tc[];
     float *sm = smem_tc;
     const NetShape s = a.s;
     const int H = s.hidden, d = s.depth, O = s.out_dim;
-    const TcPlan pl = tc_plan(s);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float *a_hi = sm + pl.off_a_hi, *a_lo = sm + pl.off_a_lo, *bias = sm + pl.off_bias;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + pl.off_misc);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + pl.off_misc + 2);
-    constexpr uint32_t TMEM_COLS = 128;  // trunk accumulator at column 0, head accumulator at column 64
+    const TcPlan pl = tc_plan(s, GROUPS);
+    const int group = threadIdx.x / TC_THREADS;            // tile group of this thread
+    const int tid = threadIdx.x % TC_THREADS, warp = tid >> 5, lane = tid & 31;  // within the group
+    float *a_hi = sm + pl.off_a_hi[group], *a_lo = sm + pl.off_a_lo[group], *bias = sm + pl.off_bias;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + pl.off_misc) + group;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + pl.off_misc + 4);
+    // per group 128 columns: trunk accumulator at +0, head accumulator at +64
+    constexpr uint32_t TMEM_COLS = 128 * GROUPS;
 
     // ---- one-time setup: TMEM, mbarrier, split weights in the UMMA layout
-    if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (threadIdx.x < 32) tmem_alloc(tmem_slot, TMEM_COLS);
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_forward_tc(const TcArgs a
         const int N = l == d ? O : H, Np = l == d ? TC_HEAD_N : H;
         const float *W = a.params + net_w_off(s, l);
         float *w_hi = sm + pl.off_w[l][0], *w_lo = sm + pl.off_w[l][1];
-        for (int i = tid; i < Np * Kp; i += TC_THREADS) {
+        for (int i = threadIdx.x; i < Np * Kp; i += TC_THREADS * GROUPS) {
             const int n = i / Kp, k = i - n * Kp;
             const float w = (n < N && k < K) ? __ldg(W + (int64_t)n * K + k) : 0.f;
             float hi, lo;
@@ -180,13 +194,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_forward_tc(const TcArgs a
             w_lo[off] = lo;
         }
         const float *b = a.params + net_b_off(s, l);
-        for (int i = tid; i < Np; i += TC_THREADS) bias[l * H + i] = i < N ? __ldg(b + i) : 0.f;
+        for (int i = threadIdx.x; i < Np; i += TC_THREADS * GROUPS) bias[l * H + i] = i < N ? __ldg(b + i) : 0.f;
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot + (uint32_t)group * 128u;
     const uint32_t idesc_trunk = umma_idesc_tf32(TC_ROWS, H), idesc_head = umma_idesc_tf32(TC_ROWS, TC_HEAD_N);
     const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo);
 
@@ -197,24 +211,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_forward_tc(const TcArgs a
     uint32_t phase = 0;
 
     const int64_t n_tiles = (a.rows + TC_ROWS - 1) / TC_ROWS;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // input prefetch registers: TC_PREFETCH float4 per thread cover a tile of up to 16 input columns
+    const bool prefetch = (TC_ROWS * s.in_dim <= TC_PREFETCH * 4 * TC_THREADS) && ((((uintptr_t)a.x) & 15) == 0);
+    float4 nx[TC_PREFETCH];
+    auto load_tile = [&](int64_t t) {
+#pragma unroll
+        for (int q = 0; q < TC_PREFETCH; ++q) {
+            nx[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int e = 4 * (tid + TC_THREADS * q);
+            if (t < n_tiles && e < TC_ROWS * s.in_dim) {
+                const int64_t g = t * TC_ROWS * s.in_dim + e, total = a.rows * s.in_dim;
+                if (g + 3 < total) {
+                    nx[q] = __ldg(reinterpret_cast<const float4 *>(a.x + g));
+                } else {
+                    if (g < total) nx[q].x = __ldg(a.x + g);
+                    if (g + 1 < total) nx[q].y = __ldg(a.x + g + 1);
+                    if (g + 2 < total) nx[q].z = __ldg(a.x + g + 2);
+                }
+            }
+        }
+    };
+    if (prefetch) load_tile((int64_t)blockIdx.x * GROUPS + group);
+    for (int64_t tile = (int64_t)blockIdx.x * GROUPS + group; tile < n_tiles; tile += (int64_t)gridDim.x * GROUPS) {
         const int64_t r0 = tile * TC_ROWS;
-        // ---- stage the tile's input rows (split) as the first A operand
+        // ---- stage the tile's input rows (split) as the first A operand.  Narrow inputs are
+        // prefetched: the NEXT tile's rows are requested into registers before this tile's layers
+        // run, so their global-memory latency hides behind a whole tile of work.
         {
             const int K = s.in_dim, Kp = pl.K0p;
-            for (int i = tid; i < TC_ROWS * Kp; i += TC_THREADS) {
-                const int r = i / Kp, k = i - r * Kp;
-                const float x = (r0 + r < a.rows && k < K) ? __ldg(a.x + (r0 + r) * K + k) : 0.f;
-                float hi, lo;
-                split_tf32(x, hi, lo);
-                const int off = umma_off(r, k, Kp);
-                a_hi[off] = hi;
-                a_lo[off] = lo;
+            if (prefetch) {
+#pragma unroll
+                for (int q = 0; q < TC_PREFETCH; ++q) {
+                    const float xv[4] = {nx[q].x, nx[q].y, nx[q].z, nx[q].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int e = 4 * (tid + TC_THREADS * q) + j;
+                        if (e < TC_ROWS * K) {
+                            const int r = e / K, k = e - r * K;
+                            float hi, lo;
+                            split_tf32(xv[j], hi, lo);
+                            const int off = umma_off(r, k, Kp);
+                            a_hi[off] = hi;
+                            a_lo[off] = lo;
+                        }
+                    }
+                }
+                for (int i = tid; i < TC_ROWS * (Kp - K); i += TC_THREADS) {
+                    const int r = i / (Kp - K), k = K + i - r * (Kp - K);
+                    const int off = umma_off(r, k, Kp);
+                    a_hi[off] = 0.f;
+                    a_lo[off] = 0.f;
+                }
+                load_tile(tile + (int64_t)gridDim.x * GROUPS);
+            } else {
+                for (int i = tid; i < TC_ROWS * Kp; i += TC_THREADS) {
+                    const int r = i / Kp, k = i - r * Kp;
+                    const float x = (r0 + r < a.rows && k < K) ? __ldg(a.x + (r0 + r) * K + k) : 0.f;
+                    float hi, lo;
+                    split_tf32(x, hi, lo);
+                    const int off = umma_off(r, k, Kp);
+                    a_hi[off] = hi;
+                    a_lo[off] = lo;
+                }
             }
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
+        group_sync(group);
 
         for (int l = 0; l <= d; ++l) {
             const int Kp = l == 0 ? pl.K0p : H;
@@ -282,11 +345,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_forward_tc(const TcArgs a
                 }
             }
             tc_fence_before();
-            __syncthreads();
+            group_sync(group);
         }
     }
+    tc_fence_before();
+    __syncthreads();
     tc_fence_after();
-    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (threadIdx.x < 32) tmem_dealloc(*tmem_slot, TMEM_COLS);
 }
 
 }  // namespace asac
@@ -303,20 +368,27 @@ extern "C" int asac_mlp_forward_tc(const float *params, int in_dim, int hidden, 
     a.params = params; a.x = x; a.out = out;
     a.s = NetShape{in_dim, hidden, depth, out_dim};
     a.rows = rows;
-    const int bytes = tc_plan(a.s).total * 4 + 128;
-    ASAC_UNSUPPORTED(bytes > 227 * 1024, "asac_mlp_forward_tc: %d bytes of shared memory", bytes);
-    static thread_local int granted[16];
-    int dev = 0;
+    int dev = 0, sms = 148;
     ASAC_CUDA(cudaGetDevice(&dev));
-    if (dev >= 16 || granted[dev] < bytes) {
-        ASAC_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        if (dev < 16) granted[dev] = bytes;
-    }
-    int sms = 148;
     ASAC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t tiles = (rows + TC_ROWS - 1) / TC_ROWS;
-    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    k_mlp_forward_tc<<<grid, TC_THREADS, bytes, (cudaStream_t)stream>>>(a);
+    // two tile groups per CTA when their operands fit and there is more than one tile per SM
+    const int bytes2 = tc_plan(a.s, 2).total * 4 + 128, bytes1 = tc_plan(a.s, 1).total * 4 + 128;
+    const int groups = (bytes2 <= 227 * 1024 && tiles > sms) ? 2 : 1;
+    const int bytes = groups == 2 ? bytes2 : bytes1;
+    ASAC_UNSUPPORTED(bytes > 227 * 1024, "asac_mlp_forward_tc: %d bytes of shared memory", bytes);
+    static thread_local int granted[2][16];
+    if (dev >= 16 || granted[groups - 1][dev] < bytes) {
+        if (groups == 2)
+            ASAC_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        else
+            ASAC_CUDA(cudaFuncSetAttribute(k_mlp_forward_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (dev < 16) granted[groups - 1][dev] = bytes;
+    }
+    const int64_t ctas = (tiles + groups - 1) / groups;
+    const unsigned grid = (unsigned)(ctas < sms ? ctas : sms);
+    if (groups == 2) k_mlp_forward_tc<2><<<grid, TC_THREADS * 2, bytes, (cudaStream_t)stream>>>(a);
+    else k_mlp_forward_tc<1><<<grid, TC_THREADS, bytes, (cudaStream_t)stream>>>(a);
     ASAC_LAUNCHED("k_mlp_forward_tc");
     return ASAC_OK;
 }
