@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <utility>
 
 #include "asac_b200.h"
 
@@ -46,6 +49,48 @@ void count_launch(int n = 1);
             return (int)e__;                                                      \
         }                                                                         \
     } while (0)
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// The kernels on the critical path of a step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel of the stream (or graph
+// branch) may be scheduled while this one drains, and blocks in pdl_wait() — the first statement
+// of every such kernel, before any global-memory access — until its predecessor has completed and
+// flushed.  pdl_trigger() lets the successor's CTAs be scheduled early.  Both are no-ops for a
+// kernel launched without the attribute.  Measured on B200 inside the step's CUDA graph: 179.0 vs
+// 179.2 us per step with a flushed L2 and 157.8 vs 153.0 us with a warm one — no gain, so the
+// attribute is only set with ASAC_PDL=1 in the environment.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+// <<<>>> replacement carrying the launch attributes (cluster dimension along y, PDL)
+template <typename... KP, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             int cluster_y, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = grid;
+    lc.blockDim = block;
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_y > 0) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = 1;
+        attr[n].val.clusterDim.y = (unsigned)cluster_y;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl && pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    lc.attrs = attr;
+    lc.numAttrs = (unsigned)n;
+    return cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...);
+}
 
 // ---------------------------------------------------------------- Philox4x32-10
 struct Philox {

@@ -1,6 +1,7 @@
 // Error string, version and launch accounting of libasac_b200.so.
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -16,6 +17,13 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("ASAC_PDL");
+        return e && e[0] == '1';  // measured: no gain inside the step's CUDA graph, off by default
+    }();
+    return on;
+}
 }  // namespace asac
 
 extern "C" const char *asac_last_error(void) { return asac::g_error; }

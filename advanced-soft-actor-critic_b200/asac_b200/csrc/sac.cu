@@ -167,6 +167,8 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
 // policy (duplicated, it is the cheap part) and ONE ensemble member; the member outputs are
 // combined by cluster rank 0 through distributed shared memory (min over i, sac_base.py:1439-1442).
 __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacArgs a) {
+    pdl_wait();
+    pdl_trigger();
     cg::cluster_group cluster = cg::this_cluster();
     const int net = (int)cluster.block_rank();
     extern __shared__ float4 smem4[];
@@ -421,6 +423,8 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
 // (sac_base.py:1516, 1539-1570).  Partial gradients are sums over the tile's rows of
 // d(sum_i mean_B loss_i)/d theta_i.
 __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacArgs a) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
     const AsacSacConfig &c = a.cfg;
@@ -523,6 +527,8 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
 // (s_b, tanh x), min over the cluster, backward through the own critic to the action, sum of
 // the action gradients on rank 0, which then runs the policy backward (sac_base.py:1882-1908).
 __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ SacArgs a) {
+    pdl_wait();
+    pdl_trigger();
     cg::cluster_group cluster = cg::this_cluster();
     const int net = (int)cluster.block_rank();
     extern __shared__ float4 smem4[];
@@ -795,6 +801,8 @@ constexpr int ADAM_PARAMS_PER_CTA = 64, ADAM_TILE_GROUPS = 4;
 __global__ void __launch_bounds__(ADAM_PARAMS_PER_CTA *ADAM_TILE_GROUPS) k_reduce_adam(const AdamArgs a) {
     __shared__ float s_part[ADAM_TILE_GROUPS][ADAM_PARAMS_PER_CTA];
     __shared__ float s_bc[2];
+    pdl_wait();
+    pdl_trigger();
     const int tid = threadIdx.x, pl = tid & (ADAM_PARAMS_PER_CTA - 1), tg = tid / ADAM_PARAMS_PER_CTA;
     const int64_t p = (int64_t)blockIdx.x * ADAM_PARAMS_PER_CTA + pl;
     float gr = 0.f;
@@ -939,6 +947,8 @@ struct EpilogueArgs {
 __global__ void __launch_bounds__(1024) k_step_epilogue(const __grid_constant__ EpilogueArgs a) {
     __shared__ TreeApplySmem s_apply;
     __shared__ float s_alpha[1024];
+    pdl_wait();
+    pdl_trigger();
     const int t = threadIdx.x;
     if (a.use_auto_alpha) {
         for (int i = t; i < a.n_tiles; i += blockDim.x) s_alpha[i] = __ldcg(a.wrk.grad_alpha_part + i * 2);
@@ -1206,25 +1216,6 @@ static int set_smem(K kernel, int bytes, const char *name) {
     return ASAC_OK;
 }
 
-// launch with the E CTAs of a batch tile (grid.y) as one thread-block cluster
-static cudaError_t launch_cluster(void (*kernel)(const SacArgs), dim3 grid, int smem_bytes, cudaStream_t stream,
-                                  int cluster_y, const SacArgs &a) {
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof(lc));
-    lc.gridDim = grid;
-    lc.blockDim = dim3(NT);
-    lc.dynamicSmemBytes = (size_t)smem_bytes;
-    lc.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = (unsigned)cluster_y;
-    attr[0].val.clusterDim.z = 1;
-    lc.attrs = attr;
-    lc.numAttrs = 1;
-    return cudaLaunchKernelEx(&lc, kernel, a);
-}
-
 extern "C" int asac_sac_polyak(const AsacSacConfig *cfg, const AsacSacParams *prm, float force_tau, void *stream) {
     int rc = validate(cfg);
     if (rc != ASAC_OK) return rc;
@@ -1242,8 +1233,8 @@ static int launch_value_pass(SacArgs &a, int mode, void *stream) {
     const int bytes = value_plan(a.cfg, a.tile_batch, mode).total * 4;
     int rc = set_smem(k_value_pass, bytes, "k_value_pass");
     if (rc != ASAC_OK) return rc;
-    ASAC_CUDA(launch_cluster(k_value_pass, dim3(a.wrk.n_tiles, a.cfg.ensemble), bytes, (cudaStream_t)stream,
-                             a.cfg.ensemble, a));
+    ASAC_CUDA(launch_ex(k_value_pass, dim3(a.wrk.n_tiles, a.cfg.ensemble), dim3(NT), (size_t)bytes, (cudaStream_t)stream,
+                        a.cfg.ensemble, true, a));
     ASAC_LAUNCHED("k_value_pass");
     return ASAC_OK;
 }
@@ -1274,7 +1265,8 @@ extern "C" int asac_sac_q_backward(const AsacSacConfig *cfg, const AsacSacParams
     const int bytes = grad_plan(a.cfg, false).total * 4;
     rc = set_smem(k_q_backward, bytes, "k_q_backward");
     if (rc != ASAC_OK) return rc;
-    k_q_backward<<<dim3(a.wrk.n_tiles, cfg->ensemble), NT, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_CUDA(launch_ex(k_q_backward, dim3(a.wrk.n_tiles, cfg->ensemble), dim3(NT), (size_t)bytes, (cudaStream_t)stream, 0,
+                        true, a));
     ASAC_LAUNCHED("k_q_backward");
     return ASAC_OK;
 }
@@ -1287,8 +1279,8 @@ extern "C" int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacP
     const int bytes = grad_plan(a.cfg, true).total * 4;
     rc = set_smem(k_policy_backward, bytes, "k_policy_backward");
     if (rc != ASAC_OK) return rc;
-    ASAC_CUDA(launch_cluster(k_policy_backward, dim3(a.wrk.n_tiles, cfg->ensemble), bytes, (cudaStream_t)stream,
-                             cfg->ensemble, a));
+    ASAC_CUDA(launch_ex(k_policy_backward, dim3(a.wrk.n_tiles, cfg->ensemble), dim3(NT), (size_t)bytes,
+                        (cudaStream_t)stream, cfg->ensemble, true, a));
     ASAC_LAUNCHED("k_policy_backward");
     return ASAC_OK;
 }
@@ -1357,8 +1349,8 @@ static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm
     a.do_adam = do_adam;
     a.grad_scale = grad_scale;
     a.lr = cfg->learning_rate;
-    k_reduce_adam<<<(unsigned)((a.count + ADAM_PARAMS_PER_CTA - 1) / ADAM_PARAMS_PER_CTA),
-                    ADAM_PARAMS_PER_CTA * ADAM_TILE_GROUPS, 0, (cudaStream_t)stream>>>(a);
+    ASAC_CUDA(launch_ex(k_reduce_adam, dim3((unsigned)((a.count + ADAM_PARAMS_PER_CTA - 1) / ADAM_PARAMS_PER_CTA)),
+                        dim3(ADAM_PARAMS_PER_CTA * ADAM_TILE_GROUPS), 0, (cudaStream_t)stream, 0, true, a));
     ASAC_LAUNCHED("k_reduce_adam");
     return ASAC_OK;
 }
@@ -1454,7 +1446,7 @@ extern "C" int asac_sac_finish_step(const AsacSacConfig *cfg, const AsacSacParam
     a.td_min = cfg->td_error_min; a.td_max = cfg->td_error_max; a.per_alpha = cfg->per_alpha;
     a.per_state = per_state;
     const int threads = ((cfg->batch + 31) / 32) * 32;
-    k_step_epilogue<<<1, threads, 0, (cudaStream_t)stream>>>(a);
+    ASAC_CUDA(launch_ex(k_step_epilogue, dim3(1), dim3(threads), 0, (cudaStream_t)stream, 0, true, a));
     ASAC_LAUNCHED("k_step_epilogue");
     return ASAC_OK;
 }

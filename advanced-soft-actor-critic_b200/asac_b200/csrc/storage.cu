@@ -63,6 +63,8 @@ __global__ void k_storage_write_table(AsacWriteTable table, int64_t capacity, in
 // one warp per (batch element, time step) window row
 __global__ void k_storage_gather(AsacColumnTable table, int64_t capacity, const int64_t *data_ids, int batch,
                                  int prev_n, int L, const float *padding_action, uint8_t *out_padding_mask) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= (int64_t)batch * L) return;
@@ -177,9 +179,8 @@ extern "C" int asac_storage_gather(const AsacColumnTable *table_host, int64_t ca
     const int L = prev_n + 1 + post_n;
     const int threads = 256;
     const int64_t blocks = ((int64_t)batch * L * 32 + threads - 1) / threads;
-    k_storage_gather<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*table_host, capacity, data_ids, batch,
-                                                                            prev_n, L, padding_action,
-                                                                            out_padding_mask);
+    ASAC_CUDA(launch_ex(k_storage_gather, dim3((unsigned)blocks), dim3(threads), 0, (cudaStream_t)stream, 0, true,
+                        *table_host, capacity, data_ids, batch, prev_n, L, padding_action, out_padding_mask));
     ASAC_LAUNCHED("k_storage_gather");
     return ASAC_OK;
 }

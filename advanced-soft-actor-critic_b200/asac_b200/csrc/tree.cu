@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(1024) k_per_sample(const float *nodes, int64_t
                                                      float *out_w) {
     __shared__ float s_min[32];
     __shared__ __align__(16) float s_top[2 << TREE_TOP_LEVELS];
+    pdl_wait();
+    pdl_trigger();
     const int top_levels = stage_tree_top(nodes, levels, s_top);
     const int t = threadIdx.x;
     const bool active = t < batch;
@@ -332,9 +334,9 @@ extern "C" int asac_per_sample(const float *nodes, int64_t capacity, const int64
     ASAC_REQUIRE(batch > 0 && batch <= 1024, "asac_per_sample: batch %d outside (0, 1024]", batch);
     ASAC_REQUIRE(unit_uniform || draw_counter, "asac_per_sample: need unit_uniform or draw_counter");
     const int threads = ((batch + 31) / 32) * 32;
-    k_per_sample<<<1, threads, 0, (cudaStream_t)stream>>>(nodes, capacity, tree_levels(capacity), store_ids, batch,
-                                                          unit_uniform, seed, draw_counter, per_state, out_slot,
-                                                          out_data_id, out_p, out_is_weight);
+    ASAC_CUDA(launch_ex(k_per_sample, dim3(1), dim3(threads), 0, (cudaStream_t)stream, 0, true, nodes, capacity,
+                        tree_levels(capacity), store_ids, batch, unit_uniform, seed, draw_counter, per_state, out_slot,
+                        out_data_id, out_p, out_is_weight));
     ASAC_LAUNCHED("k_per_sample");
     return ASAC_OK;
 }
