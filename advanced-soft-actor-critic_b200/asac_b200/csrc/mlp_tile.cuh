@@ -109,6 +109,7 @@ struct WeightJob {
 };
 constexpr int MAX_WEIGHT_JOBS = 20;
 constexpr int MAX_WEIGHT_SLOTS = 16;
+constexpr int PIPE_LOOKAHEAD = MAX_WEIGHT_SLOTS;
 
 // shared-memory row stride of a staged [N, K] matrix: K rounded to 4 plus 4 floats, so that the
 // 16-byte operand loads of 8 consecutive rows fall into distinct banks (stride = 4 mod 32 for K = 64)
@@ -134,8 +135,12 @@ static __device__ __noinline__ int pipe_fill_impl(float *slots, uint64_t *bars, 
                                            int slot_floats, int n_jobs, int issued, int consumed) {
     ASAC_SMEM(slots); ASAC_SMEM(jobs);
     const int tid = threadIdx.x;
+    // Every free slot is filled at once.  (Limiting the lookahead to three layers moved 2.5 us from the
+    // kernels' setup phase into their layer phases and left the totals unchanged: the weights are not
+    // the bottleneck — CTA (0,0) waits 3.4 us per STEP on them, tools/phase_breakdown.py.)
+    const int ahead = n_slots < PIPE_LOOKAHEAD ? n_slots : PIPE_LOOKAHEAD;
 #pragma unroll 1
-    while (issued < n_jobs && issued - consumed < n_slots) {
+    while (issued < n_jobs && issued - consumed < ahead) {
         const WeightJob j = jobs[issued];
         const int slot = issued % n_slots;
         float *Ws = slots + (int64_t)slot * slot_floats;
@@ -187,10 +192,18 @@ __device__ __forceinline__ void pipe_init(WeightPipe &p, float *slots, uint64_t 
 }
 
 // waits for the oldest unconsumed job; returns its staged weights / bias
+// debug counters of CTA (0,0), thread 0: cycles spent waiting for staged weights / number of waits
+static __device__ long long g_pipe_wait[2];
 __device__ __forceinline__ void pipe_acquire(const WeightPipe &p, const float *&Ws, const float *&bs) {
     const int slot = p.consumed % p.n_slots;
     const unsigned parity = (unsigned)((p.consumed / p.n_slots) & 1);
+    const bool probe = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    const long long c0 = probe ? clock64() : 0;
     mbar_wait(p.bars + slot, parity);
+    if (probe) {
+        g_pipe_wait[0] += clock64() - c0;
+        g_pipe_wait[1] += 1;
+    }
     const WeightJob &j = p.jobs[p.consumed];
     Ws = p.slots + (int64_t)slot * p.slot_floats;
     bs = Ws + j.N * weight_ld(j.K);

@@ -54,6 +54,14 @@ __host__ __device__ __forceinline__ int slots_that_fit(int fixed, int slot_float
     return n < 2 ? 2 : n;
 }
 
+// Phase clocks of CTA (0,0) (debug aid read back by asac_debug_phase_clocks): kernel 0 = value pass,
+// 1 = critic backward, 2 = policy backward; slot 31 = kernel exit.
+__device__ long long g_phase_clock[3][32];
+#define ASAC_PHASE(k, i)                                                              \
+    do {                                                                              \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_phase_clock[k][i] = clock64(); \
+    } while (0)
+
 constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
 
 // torch.distributions.Normal.log_prob: -((x - loc)^2) / (2 var) - log(scale) - log(sqrt(2 pi))
@@ -194,6 +202,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     const NetShape ps = pi_shape(c), qsh = q_shape(c);
     const int64_t q_stride = net_stride(qsh);
 
+    ASAC_PHASE(0, 0);
     // ---- weight pipe: policy trunk, target critic `net`, (post) online critic `net`
     WeightJob *jobs = reinterpret_cast<WeightJob *>(sm + pl.off_pipe);
     uint64_t *bars = reinterpret_cast<uint64_t *>(jobs + MAX_WEIGHT_JOBS);
@@ -206,6 +215,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     WeightPipe pipe;
     pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
 
+    ASAC_PHASE(0, 1);
     // ---- policy over the P rows
     {
         const int S4 = round_up(S, 4);
@@ -226,6 +236,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         __syncthreads();
     }
 
+    ASAC_PHASE(0, 2);
     // ---- per P row: distribution, sampled action, log-probs, IS ratio, pi_probs, alpha terms
     float alpha_term = 0.f, alpha_loss = 0.f;
     const float log_alpha = a.prm.log_alpha[0];
@@ -298,6 +309,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     }
     __syncthreads();
 
+    ASAC_PHASE(0, 3);
     // ---- critic inputs: V rows [state(e, b+k), tanh(x)], then S rows [state(e, b), stored action]
     const int K0 = S + A, K04 = round_up(K0, 4);
     const int RVp = round_up(RV, PASS_ROWS);
@@ -319,6 +331,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     }
     __syncthreads();
 
+    ASAC_PHASE(0, 4);
     // ---- target critic `net` over the V rows (+ S rows for the clipped loss)
     {
         const int rq = need_tq ? RV + RS : RV;
@@ -334,6 +347,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         }
         __syncthreads();
     }
+    ASAC_PHASE(0, 5);
     // ---- post: online critic `net` over the S rows (sac_base.py:2211-2216)
     if (post) {
         const float *prm = a.prm.q + net * q_stride;
@@ -342,6 +356,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, RS, qs);
         __syncthreads();
     }
+    ASAC_PHASE(0, 6);
     // ---- ensemble combine on rank 0 over distributed shared memory, in member order
     cluster.sync();
     if (net == 0) {
@@ -357,6 +372,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     cluster.sync();  // remote shared memory stays alive until rank 0 has read it
     if (net != 0) return;
 
+    ASAC_PHASE(0, 7);
     // ---- per batch element: V, v-trace, y (sac_base.py:1244-1295, 1444-1464)
     // y is linear in alpha: V_k = qmin_k - alpha * logp_k.  The train pass knows alpha and writes y;
     // the post pass runs BEFORE the alpha Adam step of the same train() call but _get_td_error uses
@@ -416,6 +432,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
             a.wrk.grad_alpha_part[blockIdx.x * 2 + 1] = s1;
         }
     }
+    ASAC_PHASE(0, 31);
 }
 
 // ------------------------------------------------------------------------------------ critic
@@ -425,6 +442,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
 __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacArgs a) {
     pdl_wait();
     pdl_trigger();
+    ASAC_PHASE(1, 0);
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
     const AsacSacConfig &c = a.cfg;
@@ -465,7 +483,9 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
         px[0][r * lda + col] = v;
     }
     __syncthreads();
+    ASAC_PHASE(1, 1);
     net_trunk_forward(qsh, pipe, px[0], nullptr, nullptr, px, pz, lda, R, part);
+    ASAC_PHASE(1, 2);
     head_forward(px[d], lda, H, prm + net_w_off(qsh, d), prm + net_b_off(qsh, d), 1, TBa, qout);
     __syncthreads();
 
@@ -501,8 +521,10 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
     if (tid == 0) a.wrk.loss_q[blockIdx.x * E + net] = loss;
 
     // head backward, then the ResBlocks in reverse
+    ASAC_PHASE(1, 3);
     head_backward(dq, 1, px[d], lda, H, prm + net_w_off(qsh, d), R, gout + net_w_off(qsh, d),
                   gout + net_b_off(qsh, d), g[0], lda);
+    ASAC_PHASE(1, 4);
     int cur = 0;
 #pragma unroll 1
     for (int l = d - 1; l >= 0; --l) {
@@ -520,6 +542,7 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
             cur = (cur + 2) % 3;
         }
     }
+    ASAC_PHASE(1, 31);
 }
 
 // ------------------------------------------------------------------------------------ policy
@@ -529,6 +552,7 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
 __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ SacArgs a) {
     pdl_wait();
     pdl_trigger();
+    ASAC_PHASE(2, 0);
     cg::cluster_group cluster = cg::this_cluster();
     const int net = (int)cluster.block_rank();
     extern __shared__ float4 smem4[];
@@ -568,6 +592,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     WeightPipe pipe;
     pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, n_jobs);
 
+    ASAC_PHASE(2, 1);
     // ---- policy forward (saved)
     const int S4 = round_up(S, 4);
     for (int i = tid; i < R * S4; i += NT) {
@@ -579,6 +604,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     head_forward(px[dp], lda, Hp, a.prm.pi + net_w_off(ps, dp), a.prm.pi + net_b_off(ps, dp), 2 * A, TBa, ho);
     __syncthreads();
 
+    ASAC_PHASE(2, 2);
     // ---- sample, critic input
     const int K0 = S + A, K04 = round_up(K0, 4);
     for (int i = tid; i < R * K04; i += NT) {
@@ -600,6 +626,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     for (int i = tid; i < R * A; i += NT) da[i] = 0.f;
     __syncthreads();
 
+    ASAC_PHASE(2, 3);
     // ---- own critic forward (z saved), then the other members' values over DSMEM
     {
         const float *prm = a.prm.q + net * q_stride;
@@ -627,6 +654,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     }
     __syncthreads();
 
+    ASAC_PHASE(2, 4);
     // ---- backward through the own critic to its action input; d loss / d q_min = -1/B
     {
         const int i = net;
@@ -661,6 +689,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         }
         __syncthreads();
     }
+    ASAC_PHASE(2, 5);
     // ---- sum of the members' action gradients on rank 0, in member order
     cluster.sync();
     if (net == 0) {
@@ -672,6 +701,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     cluster.sync();
     if (net != 0) return;
 
+    ASAC_PHASE(2, 6);
     // ---- d loss / d (mean, logstd) pre-activations; loss and entropy sums
     float loss = 0.f, ent = 0.f;
     const float alpha = expf(a.prm.log_alpha[0]);
@@ -712,6 +742,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         a.wrk.stats_pi[blockIdx.x * 2 + 1] = ent;
     }
 
+    ASAC_PHASE(2, 7);
     // ---- policy backward
     head_backward(dO, 2 * A, px[dp], lda, Hp, a.prm.pi + net_w_off(ps, dp), R, gout + net_w_off(ps, dp),
                   gout + net_b_off(ps, dp), g[0], lda);
@@ -732,6 +763,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
             cur = (cur + 2) % 3;
         }
     }
+    ASAC_PHASE(2, 31);
 }
 
 // ------------------------------------------------------------------------------------ optimiser
@@ -1499,5 +1531,18 @@ extern "C" int asac_policy_act(const float *params, int state_size, int hidden, 
     a.rows = rows; a.A = action_size; a.disable_sample = disable_sample; a.seed = seed; a.counter = counter;
     k_policy_sample<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
     ASAC_LAUNCHED("k_policy_sample");
+    return ASAC_OK;
+}
+
+// debug: phase clocks of CTA (0,0) of the last value pass / critic backward / policy backward launch
+extern "C" int asac_debug_phase_clocks(int64_t *out_host) {
+    ASAC_REQUIRE(out_host != nullptr, "asac_debug_phase_clocks: null pointer");
+    ASAC_CUDA(cudaMemcpyFromSymbol(out_host, g_phase_clock, sizeof(long long) * 3 * 32));
+    // slots [0][29], [0][30]: cycles CTA (0,0) waited for staged weights since the last call, number of waits
+    long long w[2] = {0, 0}, zero[2] = {0, 0};
+    ASAC_CUDA(cudaMemcpyFromSymbol(w, g_pipe_wait, sizeof(w)));
+    ASAC_CUDA(cudaMemcpyToSymbol(g_pipe_wait, zero, sizeof(zero)));
+    out_host[29] = w[0];
+    out_host[30] = w[1];
     return ASAC_OK;
 }

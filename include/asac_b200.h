@@ -388,6 +388,11 @@ int asac_policy_act(const float *params, int state_size, int hidden, int depth, 
                     int disable_sample, uint64_t seed, const int64_t *counter, float *scratch,
                     float *out_action, float *out_prob, int use_tensor_cores, void *stream);
 
+/* Debug aid: SM clock stamps (clock64) taken by CTA (0,0) at the phase boundaries of the last value
+ * pass [0], critic backward [1] and policy backward [2] launch; out_host is int64[3][32], slot 31 is
+ * the kernel's exit (tools/phase_breakdown.py prints the differences).  Synchronises. */
+int asac_debug_phase_clocks(int64_t *out_host);
+
 #ifdef __cplusplus
 }
 #endif
