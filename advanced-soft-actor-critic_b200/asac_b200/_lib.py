@@ -7,10 +7,12 @@ and a missing CUDA device raises on the first call.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / 'libasac_b200.so'
+# ASAC_B200_LIB: alternative build of the same library (A/B timing of kernel variants)
+LIB_PATH = Path(os.environ['ASAC_B200_LIB']) if os.environ.get('ASAC_B200_LIB') else PKG_DIR / 'libasac_b200.so'
 CSRC_DIR = PKG_DIR / 'csrc'
 
 MAX_COLUMNS = 16

@@ -146,6 +146,11 @@ static __device__ __noinline__ int pipe_fill_impl(float *slots, uint64_t *bars, 
         float *Ws = slots + (int64_t)slot * slot_floats;
         const int ldw = weight_ld(j.K);
         float *bs = Ws + j.N * ldw;
+#ifdef ASAC_EXPERIMENT_NO_WEIGHT_COPIES  // timing experiment only: arrivals without the copies (results are garbage)
+        if (false) {
+        } else if (true) {
+        } else
+#endif
         if (((j.K & 3) == 0) && ((((uintptr_t)j.W) & 15) == 0)) {
             const int per_row = j.K >> 2, total = j.N * per_row;
 #pragma unroll 1
@@ -167,10 +172,12 @@ static __device__ __noinline__ int pipe_fill_impl(float *slots, uint64_t *bars, 
                 Ws[n * ldw + j.K + (i - n * pad)] = 0.f;
             }
         }
+#ifndef ASAC_EXPERIMENT_NO_WEIGHT_COPIES
         if (j.b) {
 #pragma unroll 1
             for (int n = tid; n < j.N; n += NT) cp_async4(bs + n, j.b + n);
         }
+#endif
         cp_async_mbar_arrive(bars + slot);
         ++issued;
     }
@@ -194,6 +201,7 @@ __device__ __forceinline__ void pipe_init(WeightPipe &p, float *slots, uint64_t 
 // waits for the oldest unconsumed job; returns its staged weights / bias
 // debug counters of CTA (0,0), thread 0: cycles spent waiting for staged weights / number of waits
 static __device__ long long g_pipe_wait[2];
+static __device__ long long g_layer_seg[8];  // layer_forward segments of CTA (0,0), thread 0 (debug)
 __device__ __forceinline__ void pipe_acquire(const WeightPipe &p, const float *&Ws, const float *&bs) {
     const int slot = p.consumed % p.n_slots;
     const unsigned parity = (unsigned)((p.consumed / p.n_slots) & 1);
@@ -239,8 +247,10 @@ __device__ __noinline__ void layer_forward_t(const float *X, int ldx, int K4, co
     const int ldw = K4 + 4;
     const int kchunk = round_up((K4 + KSPLIT - 1) / KSPLIT, 4);
     const int kb = ks * kchunk, ke = min(K4, kb + kchunk);
+    const bool probe = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
 #pragma unroll 1
     for (int r0 = 0; r0 < nrows; r0 += PASS_ROWS) {
+        const long long c0 = probe ? clock64() : 0;
         const int r = r0 + 2 * rg;
         float acc[2][CM];
 #pragma unroll
@@ -267,7 +277,9 @@ __device__ __noinline__ void layer_forward_t(const float *X, int ldx, int K4, co
         for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int c = 0; c < CM; ++c) part[(ks * PASS_ROWS + 2 * rg + i) * H + cg + 16 * c] = acc[i][c];
+        const long long c1 = probe ? clock64() : 0;
         __syncthreads();
+        const long long c2 = probe ? clock64() : 0;
 #pragma unroll 1
         for (int o = tid; o < PASS_ROWS * H; o += NT) {
             const int row = o / H, j = o - row * H;
@@ -279,7 +291,15 @@ __device__ __noinline__ void layer_forward_t(const float *X, int ldx, int K4, co
             if (residual) y = y + X[(r0 + row) * ldx + j];
             Ys[(r0 + row) * ldy + j] = y;
         }
+        const long long c3 = probe ? clock64() : 0;
         __syncthreads();
+        if (probe) {
+            g_layer_seg[0] += c1 - c0;            // K-split GEMM + partial stores
+            g_layer_seg[1] += c2 - c1;            // barrier
+            g_layer_seg[2] += c3 - c2;            // epilogue
+            g_layer_seg[3] += clock64() - c3;     // barrier
+            g_layer_seg[4] += 1;
+        }
     }
 }
 
@@ -428,7 +448,7 @@ static __device__ __noinline__ void layer_weight_grad(const float *dZ, int ldz, 
     }
 }
 
-// Linear head: out[r * O + o] = X[r] . Wh[o] + bh[o]   (Wh, bh in global memory, 8 lanes per dot)
+// Linear head: out[r * O + o] = X[r] . Wh[o] + bh[o]   (Wh, bh in shared or global memory, 8 lanes per dot)
 static __device__ __noinline__ void head_forward(const float *X, int ldx, int H, const float *Wh, const float *bh, int O,
                                           int nrows, float *out) {
     ASAC_SMEM(X); ASAC_SMEM(out);
@@ -442,12 +462,12 @@ static __device__ __noinline__ void head_forward(const float *X, int ldx, int H,
             const int r = d / O, o = d - r * O;
             const float *x = X + r * ldx;
             const float *w = Wh + (int64_t)o * H;
-            for (int k = sub; k < H; k += 8) s = fmaf(x[k], __ldg(w + k), s);
+            for (int k = sub; k < H; k += 8) s = fmaf(x[k], w[k], s);
         }
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (d < total && sub == 0) out[d] = s + __ldg(bh + (d % O));
+        if (d < total && sub == 0) out[d] = s + bh[d % O];
     }
 }
 
@@ -476,7 +496,7 @@ static __device__ __noinline__ void head_backward(const float *dO, int O, const 
     for (int i = tid; i < nrows * H; i += NT) {
         const int r = i / H, j = i - r * H;
         float s = 0.f;
-        for (int o = 0; o < O; ++o) s = fmaf(dO[r * O + o], __ldg(Wh + (int64_t)o * H + j), s);
+        for (int o = 0; o < O; ++o) s = fmaf(dO[r * O + o], Wh[(int64_t)o * H + j], s);
         dH[r * ldh + j] = s;
     }
 }
@@ -491,6 +511,15 @@ __host__ __device__ __forceinline__ int tile_wsz(int hidden, int in_dim) {
     return a > b ? a : b;
 }
 __host__ __device__ __forceinline__ int tile_part_floats(int hidden) { return KSPLIT * PASS_ROWS * hidden; }
+
+// copies a net's head (Whead[O, H] followed by bhead[O], contiguous in the flat layout) into shared
+// memory at kernel start, so that the head passes do not pay a global round trip on the critical path
+__device__ __forceinline__ void stage_head(float *dst, const NetShape &s, const float *params) {
+    const float *src = params + net_w_off(s, s.depth);
+    const int n = s.out_dim * s.hidden + s.out_dim;
+    for (int i = threadIdx.x; i < n; i += NT) dst[i] = __ldg(src + i);
+}
+__host__ __device__ __forceinline__ int head_floats(int hidden, int out_dim) { return round_up(out_dim * hidden + out_dim, 4); }
 
 // appends the `depth` trunk layers of a stock net to a job table (forward order)
 __device__ __forceinline__ int push_trunk_jobs(WeightJob *jobs, int n, const NetShape &s, const float *params) {

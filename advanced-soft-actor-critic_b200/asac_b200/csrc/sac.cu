@@ -94,8 +94,8 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
 // ------------------------------------------------------------------------------------ smem plans
 struct ValuePlan {
     int lda, wsz, rows_max;  // rows_max: multiple of 16
-    int off_xin, off_a, off_b, off_ho, off_xs, off_logp, off_qmin, off_ratio, off_qs, off_red, off_part, off_pipe,
-        off_slots;
+    int off_xin, off_a, off_b, off_ho, off_xs, off_logp, off_qmin, off_ratio, off_qs, off_red, off_part, off_heads,
+        off_pipe, off_slots;
     int n_jobs, n_slots;
     int total;  // floats
 };
@@ -121,6 +121,7 @@ __host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c,
     p.off_qs = o; o += round_up(c.ensemble * TB, 4);
     p.off_red = o; o += 32;
     p.off_part = o; o += sac_part(c);
+    p.off_heads = o; o += head_floats(c.pi_hidden, 2 * A) + 2 * head_floats(c.q_hidden, 1);  // policy, target, online
     p.off_pipe = o; o += PIPE_HEADER_FLOATS;
     p.off_slots = o;
     p.n_jobs = c.pi_depth + c.q_depth + (mode == 1 ? c.q_depth : 0);
@@ -132,7 +133,8 @@ __host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c,
 
 struct GradPlan {
     int lda, wsz;
-    int off_px, off_pz, off_qz, off_qin, off_g0, off_g1, off_g2, off_small, off_red, off_part, off_pipe, off_slots;
+    int off_px, off_pz, off_qz, off_qin, off_g0, off_g1, off_g2, off_small, off_red, off_part, off_heads, off_pipe,
+        off_slots;
     int n_jobs, n_slots;
     int total;
 };
@@ -154,6 +156,7 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
     p.off_small = o; o += round_up(rows * (6 * c.action_size + c.ensemble + 4), 4);
     p.off_red = o; o += 32;
     p.off_part = o; o += sac_part(c);
+    p.off_heads = o; o += head_floats(c.pi_hidden, 2 * c.action_size) + head_floats(c.q_hidden, 1);  // policy, critic
     p.off_pipe = o; o += PIPE_HEADER_FLOATS;
     p.off_slots = o;
     // critic kernel: forward + reverse walk of one critic; policy kernel: policy forward, critic forward,
@@ -211,6 +214,11 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         nj = push_trunk_jobs(jobs, nj, qsh, a.prm.q_target + net * q_stride);
         if (post) nj = push_trunk_jobs(jobs, nj, qsh, a.prm.q + net * q_stride);
     }
+    float *head_pi = sm + pl.off_heads, *head_qt = head_pi + head_floats(ps.hidden, 2 * A),
+          *head_q = head_qt + head_floats(qsh.hidden, 1);
+    stage_head(head_pi, ps, a.prm.pi);
+    stage_head(head_qt, qsh, a.prm.q_target + net * q_stride);
+    if (post) stage_head(head_q, qsh, a.prm.q + net * q_stride);
     __syncthreads();
     WeightPipe pipe;
     pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
@@ -231,24 +239,32 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         }
         __syncthreads();
         float *h = net_trunk_forward(ps, pipe, xin, bufA, bufB, nullptr, nullptr, lda, RPp, part);
-        head_forward(h, lda, ps.hidden, a.prm.pi + net_w_off(ps, ps.depth), a.prm.pi + net_b_off(ps, ps.depth),
-                     2 * A, RP, ho);
+        head_forward(h, lda, ps.hidden, head_pi, head_pi + 2 * A * ps.hidden, 2 * A, RP, ho);
         __syncthreads();
     }
 
     ASAC_PHASE(0, 2);
     // ---- per P row: distribution, sampled action, log-probs, IS ratio, pi_probs, alpha terms
+    // Stage A, one thread per (row, action dim): policy.py:169.  Stage B, three independent chains per
+    // row on three different WARPS (value-row log-prob / IS ratio + pi_probs / alpha terms): as one
+    // thread per row this block was 4.6 us of serial transcendentals with 8 of 512 threads busy.
     float alpha_term = 0.f, alpha_loss = 0.f;
     const float log_alpha = a.prm.log_alpha[0];
-    for (int r = tid; r < RP; r += NT) {
-        const int e = r / Lp, tt = r - e * Lp, t = t0 + tt, eg = e0 + e;
+    for (int i = tid; i < RP * A; i += NT) {
+        const int r = i / A, j = i - r * A;
         float *hr = ho + r * 2 * A;
-        for (int j = 0; j < A; ++j) {
-            const float m = hr[j], s = hr[A + j];
-            hr[j] = policy_loc(m);
-            hr[A + j] = policy_scale(s);
-        }
-        if (t >= b) {  // value row k = t - b
+        const float m = hr[j], s = hr[A + j];
+        hr[j] = policy_loc(m);
+        hr[A + j] = policy_scale(s);
+    }
+    __syncthreads();
+    const int RP32 = round_up(RP, 32);
+    for (int idx = tid; idx < 3 * RP32; idx += NT) {
+        const int part = idx / RP32, r = idx - part * RP32;
+        if (r >= RP) continue;
+        const int e = r / Lp, tt = r - e * Lp, t = t0 + tt, eg = e0 + e;
+        const float *hr = ho + r * 2 * A;
+        if (part == 0 && t >= b) {  // value row k = t - b
             const int k = t - b, rv = e * (n + 1) + k;
             const float *eps = (post ? a.bat.eps_td : a.bat.eps_y) + ((int64_t)eg * (n + 1) + k) * A;
             float corr = 0.f;
@@ -265,7 +281,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
             }
             logp[rv] = lp_sum;
         }
-        if (use_is && t < L - 1) {  // pi / mu of the stored action (sac_base.py:1450-1455, 1159-1189)
+        if (part == 1 && use_is && t < L - 1) {  // pi / mu of the stored action (sac_base.py:1450-1455, 1159-1189)
             const float *act = a.bat.actions + ((int64_t)eg * c.bn_stride + t) * A;
             float fl = 1.f;
             for (int j = 0; j < A; ++j) fl *= squash_floor(atanhf(fminf(fmaxf(act[j], -0.999f), 0.999f)));
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
             if (isinf(mu_prod) || isnan(mu_prod)) mu_prod = 1.f;
             if (t >= b) ratio[e * n + (t - b)] = pi_prod / fmaxf(mu_prod, 1e-8f);  // sac_base.py:1275
         }
-        if (post && c.use_auto_alpha && t == b) {  // sac_base.py:1931-1939
+        if (part == 2 && post && c.use_auto_alpha && t == b) {  // sac_base.py:1931-1939
             const float *eps = a.bat.eps_alpha + (int64_t)eg * A;
             float corr = 0.f;
             for (int j = 0; j < A; ++j) corr += logf(squash_floor(hr[j] + eps[j] * hr[A + j]));
@@ -336,10 +352,9 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     {
         const int rq = need_tq ? RV + RS : RV;
         const int rqp = round_up(rq, PASS_ROWS);
-        const float *prm = a.prm.q_target + net * q_stride;
         float *h = net_trunk_forward(qsh, pipe, xin, bufA, bufB, nullptr, nullptr, lda, rqp, part);
         float *qo = (h == bufA ? bufB : bufA);  // free buffer: head outputs [rq]
-        head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, rq, qo);
+        head_forward(h, lda, qsh.hidden, head_qt, head_qt + qsh.hidden, 1, rq, qo);
         __syncthreads();
         for (int r = tid; r < rq; r += NT) {
             if (r < RV) qmin[r] = qo[r];
@@ -350,10 +365,9 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     ASAC_PHASE(0, 5);
     // ---- post: online critic `net` over the S rows (sac_base.py:2211-2216)
     if (post) {
-        const float *prm = a.prm.q + net * q_stride;
         float *h = net_trunk_forward(qsh, pipe, xin + s_row0 * lda, bufA, bufB, nullptr, nullptr, lda,
                                      round_up(RS, PASS_ROWS), part);
-        head_forward(h, lda, qsh.hidden, prm + net_w_off(qsh, qsh.depth), prm + net_b_off(qsh, qsh.depth), 1, RS, qs);
+        head_forward(h, lda, qsh.hidden, head_q, head_q + qsh.hidden, 1, RS, qs);
         __syncthreads();
     }
     ASAC_PHASE(0, 6);
@@ -468,6 +482,8 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
         const int nj = push_trunk_jobs(jobs, 0, qsh, prm);
         push_trunk_jobs_reverse(jobs, nj, qsh, prm);
     }
+    float *head_q = sm + pl.off_heads + head_floats(c.pi_hidden, 2 * A);
+    stage_head(head_q, qsh, prm);
     __syncthreads();
     WeightPipe pipe;
     pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
@@ -486,7 +502,7 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
     ASAC_PHASE(1, 1);
     net_trunk_forward(qsh, pipe, px[0], nullptr, nullptr, px, pz, lda, R, part);
     ASAC_PHASE(1, 2);
-    head_forward(px[d], lda, H, prm + net_w_off(qsh, d), prm + net_b_off(qsh, d), 1, TBa, qout);
+    head_forward(px[d], lda, H, head_q, head_q + H, 1, TBa, qout);
     __syncthreads();
 
     float loss = 0.f;
@@ -522,8 +538,7 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
 
     // head backward, then the ResBlocks in reverse
     ASAC_PHASE(1, 3);
-    head_backward(dq, 1, px[d], lda, H, prm + net_w_off(qsh, d), R, gout + net_w_off(qsh, d),
-                  gout + net_b_off(qsh, d), g[0], lda);
+    head_backward(dq, 1, px[d], lda, H, head_q, R, gout + net_w_off(qsh, d), gout + net_b_off(qsh, d), g[0], lda);
     ASAC_PHASE(1, 4);
     int cur = 0;
 #pragma unroll 1
@@ -588,6 +603,9 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         nj = push_trunk_jobs_reverse(jobs, nj, qsh, q_prm);
         if (net == 0) nj = push_trunk_jobs_reverse(jobs, nj, ps, a.prm.pi);
     }
+    float *head_pi = sm + pl.off_heads, *head_q = head_pi + head_floats(Hp, 2 * A);
+    stage_head(head_pi, ps, a.prm.pi);
+    stage_head(head_q, qsh, q_prm);
     __syncthreads();
     WeightPipe pipe;
     pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, n_jobs);
@@ -601,7 +619,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     }
     __syncthreads();
     net_trunk_forward(ps, pipe, px[0], nullptr, nullptr, px, pz, lda, R, part);
-    head_forward(px[dp], lda, Hp, a.prm.pi + net_w_off(ps, dp), a.prm.pi + net_b_off(ps, dp), 2 * A, TBa, ho);
+    head_forward(px[dp], lda, Hp, head_pi, head_pi + 2 * A * Hp, 2 * A, TBa, ho);
     __syncthreads();
 
     ASAC_PHASE(2, 2);
@@ -629,11 +647,10 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     ASAC_PHASE(2, 3);
     // ---- own critic forward (z saved), then the other members' values over DSMEM
     {
-        const float *prm = a.prm.q + net * q_stride;
         float *qz[ASAC_MAX_DEPTH];
         for (int l = 0; l < dqn; ++l) qz[l] = sm + pl.off_qz + l * R * lda;
         float *h = net_trunk_forward(qsh, pipe, qin, g[0], g[1], nullptr, qz, lda, R, part);
-        head_forward(h, lda, Hq, prm + net_w_off(qsh, dqn), prm + net_b_off(qsh, dqn), 1, TBa, qv + net * R);
+        head_forward(h, lda, Hq, head_q, head_q + Hq, 1, TBa, qv + net * R);
         __syncthreads();
     }
     cluster.sync();
@@ -661,7 +678,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         const float *prm = a.prm.q + i * q_stride;
         if (tid < R) dq[tid] = (tid < TBa && (int)amin[tid] == i) ? -1.f / (float)B : 0.f;
         __syncthreads();
-        head_backward(dq, 1, nullptr, lda, Hq, prm + net_w_off(qsh, dqn), R, nullptr, nullptr, g[0], lda);
+        head_backward(dq, 1, nullptr, lda, Hq, head_q, R, nullptr, nullptr, g[0], lda);
         int cur = 0;
 #pragma unroll 1
         for (int l = dqn - 1; l >= 0; --l) {
@@ -744,8 +761,8 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
 
     ASAC_PHASE(2, 7);
     // ---- policy backward
-    head_backward(dO, 2 * A, px[dp], lda, Hp, a.prm.pi + net_w_off(ps, dp), R, gout + net_w_off(ps, dp),
-                  gout + net_b_off(ps, dp), g[0], lda);
+    head_backward(dO, 2 * A, px[dp], lda, Hp, head_pi, R, gout + net_w_off(ps, dp), gout + net_b_off(ps, dp), g[0],
+                  lda);
     int cur = 0;
 #pragma unroll 1
     for (int l = dp - 1; l >= 0; --l) {
@@ -1544,5 +1561,10 @@ extern "C" int asac_debug_phase_clocks(int64_t *out_host) {
     ASAC_CUDA(cudaMemcpyToSymbol(g_pipe_wait, zero, sizeof(zero)));
     out_host[29] = w[0];
     out_host[30] = w[1];
+    // slots [1][20..24]: layer_forward segments (GEMM, barrier, epilogue, barrier, passes)
+    long long seg[8], zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    ASAC_CUDA(cudaMemcpyFromSymbol(seg, g_layer_seg, sizeof(seg)));
+    ASAC_CUDA(cudaMemcpyToSymbol(g_layer_seg, zero8, sizeof(zero8)));
+    for (int i = 0; i < 5; ++i) out_host[32 + 20 + i] = seg[i];
     return ASAC_OK;
 }

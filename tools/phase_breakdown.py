@@ -35,6 +35,10 @@ def main():
     assert sac._lib.asac_debug_phase_clocks(buf) == 0
     print(f'weight waits of CTA (0,0): {buf[29] / 1965.0 / steps:.2f} us per step over {buf[30] // steps} layer acquisitions')
     clk = np.array(buf[:], dtype=np.int64).reshape(3, 32)
+    n_pass = max(int(clk[1, 24]), 1)
+    print('layer_forward of CTA (0,0), per 16-row pass: ' + ', '.join(
+        f'{name} {clk[1, 20 + i] / 1965.0 / n_pass:.2f} us' for i, name in
+        enumerate(['K-split GEMM', 'barrier', 'epilogue', 'barrier'])) + f'  ({n_pass // steps} passes per step)')
     mhz = 1965.0
     for k, title in ((0, 'k_value_pass (last launch = post pass)'), (1, 'k_q_backward'), (2, 'k_policy_backward')):
         print(title)
