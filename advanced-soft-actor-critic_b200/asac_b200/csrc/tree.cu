@@ -319,7 +319,7 @@ extern "C" int asac_tree_sample(const float *nodes, int64_t capacity, int batch,
     ASAC_REQUIRE(is_pow2(capacity), "asac_tree_sample: capacity is not a power of two");
     ASAC_REQUIRE(batch > 0, "asac_tree_sample: batch <= 0");
     ASAC_REQUIRE(unit_uniform || draw_counter, "asac_tree_sample: need unit_uniform or draw_counter");
-    const int threads = 128;
+    const int threads = batch >= 8192 ? 1024 : 128;  // bulk: amortise the 8 KB tree-top stage over more samples
     k_tree_sample<<<(batch + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
         nodes, capacity, tree_levels(capacity), batch, unit_uniform, seed, draw_counter, out_slot, out_p);
     ASAC_LAUNCHED("k_tree_sample");

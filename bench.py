@@ -234,6 +234,33 @@ def profile_stages(sac, steps):
     return out
 
 
+def per_bulk_sample(rb, batch=1 << 22, iters=10):
+    """SumTree.sample at a batch size where bandwidth, not the 19-level dependent chain, is the bound:
+    asac_tree_sample over the learner's full tree.  Algorithmic bytes = batch * (8 D + 8) (two fp32
+    children per level, slot + priority out); the 4 MiB tree is L2-resident, so the achieved figure
+    is compared with the HBM peak only as a yardstick."""
+    from asac_b200 import _lib
+    from asac_b200._lib import check, ptr
+    lib = _lib.load()
+    D = int(np.log2(rb.capacity))
+    slot = torch.empty(batch, dtype=torch.int32, device=rb.device)
+    p = torch.empty(batch, dtype=torch.float32, device=rb.device)
+    counter = torch.zeros(1, dtype=torch.int64, device=rb.device)
+    s = _lib.current_stream()
+    for _ in range(2):
+        check(lib.asac_tree_sample(ptr(rb._nodes), rb.capacity, batch, None, 1234, ptr(counter), ptr(slot), ptr(p), s))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        check(lib.asac_tree_sample(ptr(rb._nodes), rb.capacity, batch, None, 1234, ptr(counter), ptr(slot), ptr(p), s))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    nbytes = batch * (8 * D + 8)
+    return {'batch': batch, 'ms': round(ms, 4), 'samples_per_s': batch / (ms * 1e-3), 'algorithmic_bytes': nbytes,
+            'achieved_GBps': nbytes / (ms * 1e-3) / 1e9}
+
+
 def tensor_core_forward(rows=1 << 20, iters=10):
     """The stock critic forward on `rows` rows: exact-fp32 FFMA kernel vs the tcgen05 3xTF32 kernel."""
     from asac_b200 import _lib, lowering
@@ -369,7 +396,7 @@ def run_gpu(args):
                    'parallelism': f'dp{world}' if world > 1 else 'single',
                    'l2': 'flushed between timed steps (256 MiB memset, outside the event pairs)',
                    'cuda_graph': bool(sac._graph is not None),
-                   'value_definition': 'batch-256 gradient steps per second summed over ranks'},
+                   'value_definition': f"batch-{CFG['B']} gradient steps per second summed over ranks"},
         'value_warm_l2': units_per_step * args.steps / (warm_ms * 1e-3),
         'e2e': {'value': units_per_step * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(td_host.numel() * 4),
@@ -418,6 +445,8 @@ def run_gpu(args):
                            'note': 'exact-fp32 FFMA row-tile kernel (1e-5 parity bound rules out plain tf32); one '
                                    '16-row tile per SM at B=256, i.e. latency-bound, not pipe-bound (DESIGN.md §6)'}
         out['tensor_core_forward'] = tensor_core_forward()
+        out['per_bulk_sample'] = per_bulk_sample(sac.replay_buffer)
+        out['per_bulk_sample']['frac_of_hbm_peak'] = out['per_bulk_sample']['achieved_GBps'] / hbm_peak
         per_us = prof['per_sample'] + prof['per_update']
         per_bytes = work['per_sample']['bytes'] + work['per_update']['bytes']
         out['per_sample_update'] = {'us': round(per_us, 3), 'algorithmic_bytes': per_bytes,
