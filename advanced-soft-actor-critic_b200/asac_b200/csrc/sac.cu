@@ -46,12 +46,14 @@ __host__ __device__ __forceinline__ int sac_part(const AsacSacConfig &c) {
 // floats reserved in front of the weight slots for the job table and the slot mbarriers
 constexpr int PIPE_HEADER_FLOATS = (MAX_WEIGHT_JOBS * (int)sizeof(WeightJob) + MAX_WEIGHT_SLOTS * 8 + 15) / 16 * 4;
 constexpr int kSmemBudgetFloats = 227 * 1024 / 4;
-// weight slots that fit behind `fixed` floats of other shared memory (at least 2, at most n_jobs)
+// weight slots that fit behind `fixed` floats of other shared memory (at most n_jobs; a single slot —
+// hidden width 128 in the backward kernels — still works, the next layer is then staged only after
+// the current one has been consumed)
 __host__ __device__ __forceinline__ int slots_that_fit(int fixed, int slot_floats, int n_jobs) {
     int n = (kSmemBudgetFloats - fixed) / slot_floats;
     if (n > n_jobs) n = n_jobs;
     if (n > MAX_WEIGHT_SLOTS) n = MAX_WEIGHT_SLOTS;
-    return n < 2 ? 2 : n;
+    return n < 1 ? 1 : n;
 }
 
 // Phase clocks of CTA (0,0) (debug aid read back by asac_debug_phase_clocks): kernel 0 = value pass,

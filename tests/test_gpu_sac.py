@@ -412,6 +412,52 @@ def test_large_batch_against_oracle():
         assert not bad, f'B={B}: {len(bad)}/{len(ck.rows)} over {TOL} + 2*gap: {ck.report(bad)}'
 
 
+@pytest.mark.parametrize('cfg', [
+    # S,  A, E,  H, depth, burn_in, n,  B, extras
+    (17, 6, 1, 128, 1, 0, 1, 33, dict()),                                 # single member, widest net, ragged batch
+    (40, 1, 3, 16, 4, 3, 2, 20, dict(v_lambda=0.9, v_rho=0.8, v_c=0.7)),  # deepest / narrowest, burn-in, wide input
+    (9, 4, 2, 128, 3, 0, 10, 70, dict(gamma=0.95)),                       # long n-step, weight slots recycled (H = 128)
+    (6, 2, 4, 64, 2, 5, 3, 48, dict(clip_epsilon=0.0, use_n_step_is=False)),  # cluster of 4, no IS, unclipped loss
+    (3, 2, 2, 32, 3, 0, 4, 130, dict(use_auto_alpha=False, update_target_per_step=3, tau=0.1)),
+])
+def test_configuration_sweep_against_oracle(cfg):
+    """Shapes and switches the golden cases do not reach (hidden 16 / 128, depth 4, E = 1 and 4, n = 10,
+    burn-in, A = 6, S = 40, batches that are no multiple of the tile, recycled weight slots): two
+    steps of stage-by-stage parity against the torch-CPU oracle from identical inputs."""
+    from oracle.sac_oracle import SacBatch, SacHyper, SacNoise, SacOracle
+    from tests.cuda_harness import SacCuda
+    S, A, E, H, depth, b, n, B, extra = cfg
+    torch.set_num_threads(4)
+    hp = SacHyper(state_size=S, action_size=A, ensemble_q_num=E, hidden=H, q_depth=depth, policy_depth=depth,
+                  burn_in_step=b, n_step=n, **extra)
+    oracle = SacOracle(hp, seed=B)
+    gen = torch.Generator().manual_seed(1000 + B)
+    with torch.no_grad():
+        for net in oracle.q + oracle.q_target + [oracle.policy]:
+            for t in net.values():
+                t.add_(torch.randn(t.shape, generator=gen) * 0.03)
+    L = b + n + 1
+    r = lambda *shape: torch.randn(*shape, generator=gen)
+    pad = torch.zeros(B, L - 1, dtype=torch.bool)
+    if b > 0:
+        pad[::5, :b] = True  # some windows start inside an earlier episode: burn-in rows are padding
+    batch = SacBatch(states=r(B, L, S), actions=torch.rand(B, L - 1, A, generator=gen) * 1.8 - 0.9,
+                     rewards=r(B, L - 1), dones=torch.rand(B, L - 1, generator=gen) < 0.1,
+                     mu_probs=torch.rand(B, L - 1, A, generator=gen) + 0.05,
+                     last_masks=torch.rand(B, L - 1, generator=gen) < 0.05, padding_masks=pad,
+                     priority_is=torch.rand(B, 1, generator=gen) * 0.9 + 0.1)
+    noise = SacNoise(eps_y=r(B, n + 1, A), eps_pi=r(B, A), eps_alpha=r(B, A), eps_td=r(B, n + 1, A))
+    cuda = SacCuda(hp, B)
+    o64 = SacOracle(hp, dtype=torch.float64)
+    ck = Checks()
+    for s in range(2):
+        _oracle_stage_step(oracle, o64, cuda, batch, noise, ck, f's{s}.', mask_boundary=True)
+    ck.dump(f'sweep_S{S}A{A}E{E}H{H}d{depth}b{b}n{n}B{B}')
+    bad = ck.bad()
+    print(f'{cfg[:8]}: tile {cuda.tile}, {len(ck.rows)} checks; worst {ck.report(n=4)}')
+    assert not bad, f'{cfg[:8]}: {len(bad)}/{len(ck.rows)} over tolerance: {ck.report(bad)}'
+
+
 def test_mlp_forward_matches_torch():
     from asac_b200 import _lib
     from asac_b200._lib import check, ptr
