@@ -216,3 +216,75 @@ def test_write_back_skips_padding_and_stale_ids():
             if not pad[i, t] and store[wid % C] == wid:
                 ref[wid % C] = rows[i, t]
     assert np.array_equal(_np(rb._columns['mu_prob']), ref)
+
+
+def _rows(rng, T, first_index=0):
+    return {'index': (np.arange(T) + first_index).astype(np.int32), 'last_mask': np.arange(T) == T - 1,
+            'obs_vector': rng.randn(T, 3).astype(np.float32), 'action': rng.rand(T, 2).astype(np.float32),
+            'reward': rng.randn(T).astype(np.float32), 'done': rng.randint(0, 2, size=T).astype(bool),
+            'mu_prob': rng.rand(T, 2).astype(np.float32),
+            'pre_seq_hidden_state': np.zeros((T, 0), dtype=np.float32)}
+
+
+def _same_state(rb, ref, what):
+    assert np.array_equal(_np(rb.tree_nodes()), ref.tree.nodes), f'{what}: tree'
+    assert np.array_equal(_np(rb._store_ids), ref.store.columns['_id']), f'{what}: ids'
+    assert rb.size == ref.store.size and rb._next_id == ref.store.next_id, f'{what}: size / next id'
+    for k, col in ref.store.columns.items():
+        if k != '_id':
+            assert np.array_equal(_np(rb._columns[k]), col), f'{what}: column {k}'
+
+
+def test_ring_wrap_long_episodes_and_unsorted_updates_against_oracle():
+    """Edge cases of replay_buffer.py the golden traces do not reach, against the NumPy oracle (itself
+    pinned to the reference): ids wrapping at 10 * capacity (:28, 43-54), an episode longer than the
+    ring (only the last `capacity` rows survive, :48-50), ring-tail / episode-tail zero priorities
+    (:303-306), priority updates given in arbitrary order with duplicates and stale ids (sort path of
+    the tree kernel), add_with_td_error (:317-337), and sample() before the buffer exceeds a batch."""
+    from asac_b200 import PrioritizedReplayBuffer
+    from oracle.replay_oracle import PerOracle
+    C, B = 16, 4
+    rb = PrioritizedReplayBuffer(batch_size=B, sample_prev_n=1, sample_post_n=2, device='cuda:0', capacity=C,
+                                 alpha=0.7)
+    ref = PerOracle(batch_size=B, sample_prev_n=1, sample_post_n=2, capacity=C, alpha=0.7)
+    rng = np.random.RandomState(4)
+    first = _rows(rng, 3)
+    rb.add(first, ignore_size=1); ref.add(first, ignore_size=1)
+    assert rb.sample() is None and ref.sample(rng.random_sample(B)) is None  # size 3 <= batch 4
+    for step in range(40):  # 40 episodes of 5..9 rows: ids pass 10 * C = 160 more than once
+        T = 5 + step % 5
+        ep = _rows(rng, T)
+        if step % 7 == 3:
+            td = np.abs(rng.randn(T)).astype(np.float32)
+            rb.add_with_td_error(td, ep, ignore_size=1); ref.add_with_td_error(td, ep, ignore_size=1)
+        else:
+            rb.add(ep, ignore_size=1); ref.add(ep, ignore_size=1)
+        leaves, leaves_ref = _np(rb.tree_nodes())[C - 1:], ref.tree.nodes[C - 1:]
+        if step % 7 == 3:  # np.power vs float64 pow: an ulp or two on the new leaves (see test above)
+            ulp = np.abs(leaves.view(np.int32).astype(np.int64) - leaves_ref.view(np.int32).astype(np.int64))
+            assert ulp.max() <= 4
+            rb._nodes[1:].copy_(torch.from_numpy(ref.tree.nodes).cuda())
+        _same_state(rb, ref, f'episode {step}')
+        u = rng.random_sample(B)
+        got, want = rb.sample(unit_uniform=u), ref.sample(u)
+        assert np.array_equal(_np(got[0]), want[0]), f'step {step}: data ids'
+        for k in want[1]:
+            assert np.array_equal(_np(got[1][k]), want[1][k]), (step, k)
+        # priority update in arbitrary order: shuffled, one duplicate, one id that is no longer resident
+        ids = want[0][rng.permutation(B)].copy()
+        ids[1] = ids[0]
+        ids[2] -= 3 * C
+        p = np.power(np.clip(np.abs(rng.randn(B)).astype(np.float32), 0.01, 1.0), np.float32(0.7))
+        alive = ref.store.ids_at(ids) == ids
+        ref.tree.update(ids[alive] % C, p[alive])
+        t_ids, t_p = torch.from_numpy(ids).cuda(), torch.from_numpy(p).cuda()
+        assert rb._lib.asac_per_update(rb._nodes.data_ptr(), C, rb._store_ids.data_ptr(), t_ids.data_ptr(),
+                                       t_p.data_ptr(), B, 0.01, 1.0, 0.7, 1, rb._per_state.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream) == 0
+        _same_state(rb, ref, f'update {step}')
+    assert ref.store.next_id < 10 * C and rb._next_id == ref.store.next_id
+    # an episode longer than the ring
+    long_ep = _rows(rng, 3 * C + 5)
+    rb.add(long_ep, ignore_size=1); ref.add(long_ep, ignore_size=1)
+    _same_state(rb, ref, 'long episode')
+    rb.close()
