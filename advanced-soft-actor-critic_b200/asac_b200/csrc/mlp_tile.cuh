@@ -3,12 +3,15 @@
 // A CTA of NT = 512 threads (16 warps, 4 per SM sub-partition) owns a tile of <= 16 rows whose
 // activations live in shared memory and walks the net layer by layer.
 //
-//   * Weights: every layer the kernel will need is a "job" of a WeightPipe.  All threads stage
-//     jobs ahead of their use with 16-byte cp.async copies into padded, bank-conflict-free rows;
-//     each thread posts a deferred arrival on the slot's mbarrier and consumers wait on the
-//     barrier's phase, so the staging of later layers overlaps the math of the current one and
-//     nobody counts cp.async groups.  Slots are recycled round robin when shared memory cannot
-//     hold all jobs.
+//   * Weights: every layer the kernel will need is a "job" of a WeightPipe, staged ahead of its
+//     use into a slot guarded by an mbarrier; consumers wait on the barrier's phase, so the staging
+//     of later layers overlaps the math of the current one.  Hidden->hidden layers (K a multiple of
+//     32) arrive by TMA: ONE thread issues one `cp.async.bulk.tensor` per 32-column segment from a
+//     4-D tensor map over {k, row, layer, ensemble member} of the flat parameter buffer, with the
+//     128-byte swizzle, so the [rows][32] tiles land bank-conflict-free without padding and the
+//     readers only XOR the 16-byte chunk index with (row & 7).  First layers (K = 6, 8, ...) are
+//     copied by all threads with cp.async into padded rows.  Slots are recycled round robin when
+//     shared memory cannot hold all jobs.
 //   * GEMM core: thread (cg, rg, ks) = (tid & 15, (tid >> 4) & 7, tid >> 7) accumulates rows
 //     {2rg, 2rg+1} x CM columns over the ks-th quarter of K with float4 operand loads; the four
 //     K-partials meet in shared memory and the epilogue (bias, exact-erf GELU, residual) runs on
@@ -20,6 +23,8 @@
 // (algorithm/nn_models/layers/linear_layers.py:46-56).  The library is compiled with
 // -fmad=false, so only the explicit fmaf() of the GEMM cores contract.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is resolved at run time, see sac.cu)
+
 #include "common.cuh"
 
 namespace asac {
@@ -106,6 +111,8 @@ struct WeightJob {
     const float *W;  // [N, K] row-major (global)
     const float *b;  // [N] or null
     int N, K;
+    const CUtensorMap *map;  // non-null: stage by TMA (K % 32 == 0); coordinates {k, row, layer, net}
+    int layer, net;
 };
 constexpr int MAX_WEIGHT_JOBS = 20;
 constexpr int MAX_WEIGHT_SLOTS = 16;
@@ -114,70 +121,92 @@ constexpr int PIPE_LOOKAHEAD = MAX_WEIGHT_SLOTS;
 // shared-memory row stride of a staged [N, K] matrix: K rounded to 4 plus 4 floats, so that the
 // 16-byte operand loads of 8 consecutive rows fall into distinct banks (stride = 4 mod 32 for K = 64)
 __host__ __device__ __forceinline__ int weight_ld(int K) { return round_up(K, 4) + 4; }
-__host__ __device__ __forceinline__ int weight_slot_floats(int N, int K) { return round_up(N * weight_ld(K) + N, 4); }
+// slots start on 1024-byte boundaries (the 128-byte swizzle pattern is a function of address bits 7-9)
+__host__ __device__ __forceinline__ int weight_slot_floats(int N, int K) { return round_up(N * weight_ld(K) + N, 256); }
+// float offset of element (n, k) of a TMA-staged [N][K] matrix: K / 32 segments of [N][32] floats, the
+// 16-byte chunk index XORed with (n & 7)  (CU_TENSOR_MAP_SWIZZLE_128B)
+__device__ __forceinline__ int swz_off(int N, int n, int k) {
+    return (k >> 5) * (N * 32) + n * 32 + ((((k >> 2) & 7) ^ (n & 7)) << 2) + (k & 3);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
 
 struct WeightPipe {
     float *slots;      // n_slots x slot_floats
-    uint64_t *bars;    // n_slots mbarriers (NT deferred arrivals each, one per thread)
+    uint64_t *bars;    // n_slots mbarriers (NT deferred arrivals each, one per thread, plus the TMA bytes)
     WeightJob *jobs;   // shared-memory job table
     int n_slots, slot_floats, n_jobs, issued, consumed;
 };
 
 // Issues every job whose slot is free; returns the new `issued`.  Executed by ALL threads at
 // CTA-uniform points, after a __syncthreads() that follows the last read of any slot being
-// recycled.  Each thread copies its share with 16-byte cp.async (LDGSTS) into the padded rows and
-// then posts one deferred arrival on the slot's mbarrier (`cp.async.mbarrier.arrive.noinc`: it
-// fires when this thread's copies have landed), so a slot is complete after NT arrivals.
-// (A first version let warp 0 issue one cp.async.bulk per weight row — 65 TMA operations per
-// layer, ~600 per kernel from a single warp — and the consumers' mbarrier wait became the largest
-// stall of k_value_pass: per-row bulk copies are too fine-grained for the TMA unit.)
+// recycled.  Hidden -> hidden layers: thread 0 registers the bytes (expect_tx) and issues one TMA
+// tensor copy per 32-column segment.  First layers and biases: every thread copies its share with
+// cp.async.  Each thread then posts one deferred arrival on the slot's mbarrier
+// (`cp.async.mbarrier.arrive.noinc`: it fires when that thread's copies have landed), so a slot is
+// complete after NT arrivals plus the TMA bytes.
+// (History, each variant measured on the GPU: one cp.async.bulk per weight ROW from one warp made
+// the consumers' wait the largest stall of the value pass; staging from warp 0 alone lengthened
+// the kernels' setup phase from 6.8 to 8.0 us; limiting the lookahead only moved time between
+// phases.  The weights are not the bottleneck: CTA (0,0) waits 3.4 us per STEP on them.)
 static __device__ __noinline__ int pipe_fill_impl(float *slots, uint64_t *bars, const WeightJob *jobs, int n_slots,
                                            int slot_floats, int n_jobs, int issued, int consumed) {
     ASAC_SMEM(slots); ASAC_SMEM(jobs);
     const int tid = threadIdx.x;
-    // Every free slot is filled at once.  (Limiting the lookahead to three layers moved 2.5 us from the
-    // kernels' setup phase into their layer phases and left the totals unchanged: the weights are not
-    // the bottleneck — CTA (0,0) waits 3.4 us per STEP on them, tools/phase_breakdown.py.)
     const int ahead = n_slots < PIPE_LOOKAHEAD ? n_slots : PIPE_LOOKAHEAD;
 #pragma unroll 1
     while (issued < n_jobs && issued - consumed < ahead) {
         const WeightJob j = jobs[issued];
         const int slot = issued % n_slots;
         float *Ws = slots + (int64_t)slot * slot_floats;
-        const int ldw = weight_ld(j.K);
-        float *bs = Ws + j.N * ldw;
-#ifdef ASAC_EXPERIMENT_NO_WEIGHT_COPIES  // timing experiment only: arrivals without the copies (results are garbage)
-        if (false) {
-        } else if (true) {
-        } else
-#endif
-        if (((j.K & 3) == 0) && ((((uintptr_t)j.W) & 15) == 0)) {
-            const int per_row = j.K >> 2, total = j.N * per_row;
-#pragma unroll 1
-            for (int i = tid; i < total; i += NT) {
-                const int n = i / per_row, c = i - n * per_row;
-                cp_async16(Ws + n * ldw + 4 * c, j.W + (int64_t)n * j.K + 4 * c);
+        float *bs;
+        if (j.map) {
+            // TMA: K / 32 tensor copies of [N][32] floats, 128-byte swizzle
+            bs = Ws + j.N * j.K;
+            if (tid == 0) {
+                fence_proxy_async();  // generic-proxy reads of a recycled slot precede the async-proxy writes
+                mbar_expect_tx(bars + slot, (unsigned)(j.N * j.K * 4));
+                for (int seg = 0; seg < (j.K >> 5); ++seg)
+                    tma_load_4d(Ws + seg * j.N * 32, j.map, seg * 32, 0, j.layer, j.net, bars + slot);
             }
         } else {
-            // rows that are not 16-byte multiples (e.g. K = 6): 4-byte copies, zeroed pad columns
-            const int K4 = round_up(j.K, 4), pad = K4 - j.K;
+            const int ldw = weight_ld(j.K);
+            bs = Ws + j.N * ldw;
+            if (((j.K & 3) == 0) && ((((uintptr_t)j.W) & 15) == 0)) {
+                const int per_row = j.K >> 2, total = j.N * per_row;
 #pragma unroll 1
-            for (int i = tid; i < j.N * j.K; i += NT) {
-                const int n = i / j.K, k = i - n * j.K;
-                cp_async4(Ws + n * ldw + k, j.W + i);
-            }
+                for (int i = tid; i < total; i += NT) {
+                    const int n = i / per_row, c = i - n * per_row;
+                    cp_async16(Ws + n * ldw + 4 * c, j.W + (int64_t)n * j.K + 4 * c);
+                }
+            } else {
+                // rows that are not 16-byte multiples (e.g. K = 6): 4-byte copies, zeroed pad columns
+                const int K4 = round_up(j.K, 4), pad = K4 - j.K;
 #pragma unroll 1
-            for (int i = tid; i < j.N * pad; i += NT) {
-                const int n = i / pad;
-                Ws[n * ldw + j.K + (i - n * pad)] = 0.f;
+                for (int i = tid; i < j.N * j.K; i += NT) {
+                    const int n = i / j.K, k = i - n * j.K;
+                    cp_async4(Ws + n * ldw + k, j.W + i);
+                }
+#pragma unroll 1
+                for (int i = tid; i < j.N * pad; i += NT) {
+                    const int n = i / pad;
+                    Ws[n * ldw + j.K + (i - n * pad)] = 0.f;
+                }
             }
         }
-#ifndef ASAC_EXPERIMENT_NO_WEIGHT_COPIES
         if (j.b) {
 #pragma unroll 1
             for (int n = tid; n < j.N; n += NT) cp_async4(bs + n, j.b + n);
         }
-#endif
         cp_async_mbar_arrive(bars + slot);
         ++issued;
     }
@@ -214,8 +243,9 @@ __device__ __forceinline__ void pipe_acquire(const WeightPipe &p, const float *&
     }
     const WeightJob &j = p.jobs[p.consumed];
     Ws = p.slots + (int64_t)slot * p.slot_floats;
-    bs = Ws + j.N * weight_ld(j.K);
+    bs = Ws + (j.map ? j.N * j.K : j.N * weight_ld(j.K));
 }
+__device__ __forceinline__ bool pipe_front_swizzled(const WeightPipe &p) { return p.jobs[p.consumed].map != nullptr; }
 // the CTA has finished reading the oldest job (a __syncthreads() must separate the reads from this
 // call); refills the freed slot
 __device__ __forceinline__ void pipe_release(WeightPipe &p) {
@@ -238,7 +268,7 @@ __device__ __forceinline__ float gelu_erf_grad(float z) {
 // ResBlock forward over `nrows` (multiple of 16) rows:
 //   Z = X . W^T + b ;  Y = gelu(Z) (+ X when residual)        Zs may be null (no backward)
 // Ws: [H rows][ldw = K4 + 4] staged weights, `part`: KSPLIT x 16 x H floats of scratch.
-template <int CM>
+template <int CM, bool SWZ>
 __device__ __noinline__ void layer_forward_t(const float *X, int ldx, int K4, const float *Ws, const float *bs,
                                              float *Zs, float *Ys, int ldy, int nrows, bool residual, float *part) {
     ASAC_SMEM(X); ASAC_SMEM(Ws); ASAC_SMEM(bs); ASAC_SMEM(Ys); ASAC_SMEM(part);
@@ -256,13 +286,19 @@ __device__ __noinline__ void layer_forward_t(const float *X, int ldx, int K4, co
 #pragma unroll
         for (int c = 0; c < CM; ++c) acc[0][c] = acc[1][c] = 0.f;
         const float *a0p = X + r * ldx, *a1p = a0p + ldx, *wp = Ws + cg * ldw;
+        // TMA-staged weights: K4 == H, segments of [H][32] floats, chunk index XOR (row & 7); the rows of
+        // this thread are cg + 16 c, so (row & 7) == (cg & 7) for all of them
+        const float *wsz = Ws + cg * 32;
+        const int x7 = cg & 7;
 #pragma unroll 4
         for (int k = kb; k < ke; k += 4) {
             const float4 a0 = *reinterpret_cast<const float4 *>(a0p + k);
             const float4 a1 = *reinterpret_cast<const float4 *>(a1p + k);
+            const int koff = SWZ ? (k >> 5) * (H * 32) + ((((k >> 2) & 7) ^ x7) << 2) : k;
 #pragma unroll
             for (int c = 0; c < CM; ++c) {
-                const float4 w = *reinterpret_cast<const float4 *>(wp + 16 * c * ldw + k);
+                const float4 w = SWZ ? *reinterpret_cast<const float4 *>(wsz + 16 * c * 32 + koff)
+                                     : *reinterpret_cast<const float4 *>(wp + 16 * c * ldw + koff);
                 acc[0][c] = fmaf(a0.x, w.x, acc[0][c]);
                 acc[1][c] = fmaf(a1.x, w.x, acc[1][c]);
                 acc[0][c] = fmaf(a0.y, w.y, acc[0][c]);
@@ -305,12 +341,20 @@ __device__ __noinline__ void layer_forward_t(const float *X, int ldx, int K4, co
 
 __device__ __forceinline__ void layer_forward(int hidden, const float *X, int ldx, int K4, const float *Ws,
                                               const float *bs, float *Zs, float *Ys, int ldy, int nrows,
-                                              bool residual, float *part) {
+                                              bool residual, float *part, bool swizzled) {
+    if (swizzled) {  // hidden -> hidden layers staged by TMA (hidden >= 32)
+        switch (hidden >> 4) {
+            case 2: layer_forward_t<2, true>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+            case 4: layer_forward_t<4, true>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+            default: layer_forward_t<8, true>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+        }
+        return;
+    }
     switch (hidden >> 4) {
-        case 1: layer_forward_t<1>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
-        case 2: layer_forward_t<2>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
-        case 4: layer_forward_t<4>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
-        default: layer_forward_t<8>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+        case 1: layer_forward_t<1, false>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+        case 2: layer_forward_t<2, false>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+        case 4: layer_forward_t<4, false>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
+        default: layer_forward_t<8, false>(X, ldx, K4, Ws, bs, Zs, Ys, ldy, nrows, residual, part); break;
     }
 }
 
@@ -334,7 +378,7 @@ __device__ __forceinline__ void load_cm(const float *p, float (&w)[CM]) {
 // dX = dZ . W (+ dY when the block was residual) for a hidden -> hidden layer, 16 rows.
 // W is the forward staging (Ws[j * ldw + k], ldw = H + 4): thread (cg, rg, ks) owns the CM
 // consecutive columns k = CM*cg.. of rows {2rg, 2rg+1} over the ks-th quarter of j.
-template <int CM>
+template <int CM, bool SWZ>
 __device__ __noinline__ void layer_input_grad_t(const float *dZ, int ld, const float *Ws, const float *dY, float *dX,
                                                 bool residual, float *part) {
     ASAC_SMEM(dZ); ASAC_SMEM(Ws); ASAC_SMEM(dY); ASAC_SMEM(dX); ASAC_SMEM(part);
@@ -354,7 +398,20 @@ __device__ __noinline__ void layer_input_grad_t(const float *dZ, int ld, const f
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             float w[CM];
-            load_cm<CM>(Ws + (j + jj) * ldw + CM * cg, w);
+            if constexpr (SWZ) {  // columns CM*cg .. of row j+jj: whole 16-byte chunks (CM >= 4) or half a chunk (CM == 2)
+                const int row = j + jj;
+                if constexpr (CM >= 4) {
+#pragma unroll
+                    for (int q = 0; q < CM / 4; ++q) {
+                        const float4 v = *reinterpret_cast<const float4 *>(Ws + swz_off(H, row, CM * cg + 4 * q));
+                        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                    }
+                } else {
+                    load_cm<CM>(Ws + swz_off(H, row, CM * cg), w);
+                }
+            } else {
+                load_cm<CM>(Ws + (j + jj) * ldw + CM * cg, w);
+            }
 #pragma unroll
             for (int c = 0; c < CM; ++c) {
                 acc[0][c] = fmaf(d0v[jj], w[c], acc[0][c]);
@@ -380,12 +437,21 @@ __device__ __noinline__ void layer_input_grad_t(const float *dZ, int ld, const f
 }
 
 __device__ __forceinline__ void layer_input_grad(int hidden, const float *dZ, int ld, const float *Ws,
-                                                 const float *dY, float *dX, bool residual, float *part) {
+                                                 const float *dY, float *dX, bool residual, float *part,
+                                                 bool swizzled) {
+    if (swizzled) {
+        switch (hidden >> 4) {
+            case 2: layer_input_grad_t<2, true>(dZ, ld, Ws, dY, dX, residual, part); break;
+            case 4: layer_input_grad_t<4, true>(dZ, ld, Ws, dY, dX, residual, part); break;
+            default: layer_input_grad_t<8, true>(dZ, ld, Ws, dY, dX, residual, part); break;
+        }
+        return;
+    }
     switch (hidden >> 4) {
-        case 1: layer_input_grad_t<1>(dZ, ld, Ws, dY, dX, residual, part); break;
-        case 2: layer_input_grad_t<2>(dZ, ld, Ws, dY, dX, residual, part); break;
-        case 4: layer_input_grad_t<4>(dZ, ld, Ws, dY, dX, residual, part); break;
-        default: layer_input_grad_t<8>(dZ, ld, Ws, dY, dX, residual, part); break;
+        case 1: layer_input_grad_t<1, false>(dZ, ld, Ws, dY, dX, residual, part); break;
+        case 2: layer_input_grad_t<2, false>(dZ, ld, Ws, dY, dX, residual, part); break;
+        case 4: layer_input_grad_t<4, false>(dZ, ld, Ws, dY, dX, residual, part); break;
+        default: layer_input_grad_t<8, false>(dZ, ld, Ws, dY, dX, residual, part); break;
     }
 }
 
@@ -522,15 +588,23 @@ __device__ __forceinline__ void stage_head(float *dst, const NetShape &s, const 
 __host__ __device__ __forceinline__ int head_floats(int hidden, int out_dim) { return round_up(out_dim * hidden + out_dim, 4); }
 
 // appends the `depth` trunk layers of a stock net to a job table (forward order)
-__device__ __forceinline__ int push_trunk_jobs(WeightJob *jobs, int n, const NetShape &s, const float *params) {
+// `map` (may be null): 4-D tensor map of the net family's hidden -> hidden layers, `net` the member index
+__device__ __forceinline__ bool tma_layer(const NetShape &s, int l, const CUtensorMap *map) {
+    return map != nullptr && l >= 1 && s.hidden >= 32;
+}
+__device__ __forceinline__ int push_trunk_jobs(WeightJob *jobs, int n, const NetShape &s, const float *params,
+                                               const CUtensorMap *map = nullptr, int net = 0) {
     for (int l = 0; l < s.depth; ++l)
-        jobs[n++] = WeightJob{params + net_w_off(s, l), params + net_b_off(s, l), s.hidden, net_k(s, l)};
+        jobs[n++] = WeightJob{params + net_w_off(s, l), params + net_b_off(s, l), s.hidden, net_k(s, l),
+                              tma_layer(s, l, map) ? map : nullptr, l - 1, net};
     return n;
 }
 // appends layers depth-1 .. 1 (the input-gradient passes of a backward walk; no bias needed)
-__device__ __forceinline__ int push_trunk_jobs_reverse(WeightJob *jobs, int n, const NetShape &s, const float *params) {
+__device__ __forceinline__ int push_trunk_jobs_reverse(WeightJob *jobs, int n, const NetShape &s, const float *params,
+                                                       const CUtensorMap *map = nullptr, int net = 0) {
     for (int l = s.depth - 1; l >= 1; --l)
-        jobs[n++] = WeightJob{params + net_w_off(s, l), nullptr, s.hidden, s.hidden};
+        jobs[n++] = WeightJob{params + net_w_off(s, l), nullptr, s.hidden, s.hidden,
+                              tma_layer(s, l, map) ? map : nullptr, l - 1, net};
     return n;
 }
 
@@ -547,10 +621,12 @@ __device__ __forceinline__ float *net_trunk_forward(const NetShape &s, WeightPip
 #pragma unroll 1
     for (int l = 0; l < s.depth; ++l) {
         const float *Ws, *bs;
+        const bool swz = pipe_front_swizzled(pipe);
         pipe_acquire(pipe, Ws, bs);
         const int K = net_k(s, l);
         float *y = save_x ? save_x[l + 1] : (x == bufA ? bufB : bufA);
-        layer_forward(H, x, lda, round_up(K, 4), Ws, bs, save_z ? save_z[l] : nullptr, y, lda, nrows, K == H, part);
+        layer_forward(H, x, lda, round_up(K, 4), Ws, bs, save_z ? save_z[l] : nullptr, y, lda, nrows, K == H, part,
+                      swz);
         pipe_release(pipe);  // layer_forward ends with a CTA barrier
         x = y;
     }

@@ -8,6 +8,10 @@
 // reproduced on purpose are listed in DESIGN.md §5.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "mlp_tile.cuh"
@@ -18,6 +22,10 @@ namespace cg = cooperative_groups;
 namespace asac {
 
 struct SacArgs {
+    // 4-D TMA tensor maps {k, row, layer, member} over the hidden -> hidden layers of the flat parameter
+    // buffers: [0] online critics, [1] target critics, [2] policy (valid when use_tma != 0)
+    alignas(64) CUtensorMap maps[3];
+    int use_tma;
     AsacSacConfig cfg;
     AsacSacParams prm;
     AsacSacBatch bat;
@@ -38,7 +46,12 @@ __host__ __device__ __forceinline__ int sac_lda(const AsacSacConfig &c) {
 }
 __host__ __device__ __forceinline__ int sac_wsz(const AsacSacConfig &c) {
     const int a = tile_wsz(c.q_hidden, c.state_size + c.action_size), b = tile_wsz(c.pi_hidden, c.state_size);
-    return round_up(a > b ? a : b, 4);
+    return round_up(a > b ? a : b, 256);
+}
+// first 1024-byte aligned address at or after sm + off (the plans reserve 256 floats of slack for it)
+__device__ __forceinline__ float *aligned_slots(float *sm, int off) {
+    const unsigned a = smem_u32(sm + off);
+    return sm + off + (((1024u - (a & 1023u)) & 1023u) >> 2);
 }
 __host__ __device__ __forceinline__ int sac_part(const AsacSacConfig &c) {
     return tile_part_floats(c.q_hidden > c.pi_hidden ? c.q_hidden : c.pi_hidden);
@@ -126,6 +139,7 @@ __host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c,
     p.off_heads = o; o += head_floats(c.pi_hidden, 2 * A) + 2 * head_floats(c.q_hidden, 1);  // policy, target, online
     p.off_pipe = o; o += PIPE_HEADER_FLOATS;
     p.off_slots = o;
+    o += 256;  // the slots start on the next 1024-byte boundary (TMA 128-byte swizzle)
     p.n_jobs = c.pi_depth + c.q_depth + (mode == 1 ? c.q_depth : 0);
     p.n_slots = slots_that_fit(o, p.wsz, p.n_jobs);
     o += p.n_slots * p.wsz;
@@ -163,6 +177,7 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
     p.off_slots = o;
     // critic kernel: forward + reverse walk of one critic; policy kernel: policy forward, critic forward,
     // critic reverse, policy reverse (the last only on cluster rank 0, the plan reserves for it anyway)
+    o += 256;  // the slots start on the next 1024-byte boundary (TMA 128-byte swizzle)
     p.n_jobs = policy ? (c.pi_depth + c.q_depth + (c.q_depth - 1) + (c.pi_depth - 1)) : (c.q_depth + c.q_depth - 1);
     p.n_slots = slots_that_fit(o, p.wsz, p.n_jobs);
     o += p.n_slots * p.wsz;
@@ -212,9 +227,11 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     WeightJob *jobs = reinterpret_cast<WeightJob *>(sm + pl.off_pipe);
     uint64_t *bars = reinterpret_cast<uint64_t *>(jobs + MAX_WEIGHT_JOBS);
     if (tid == 0) {
-        int nj = push_trunk_jobs(jobs, 0, ps, a.prm.pi);
-        nj = push_trunk_jobs(jobs, nj, qsh, a.prm.q_target + net * q_stride);
-        if (post) nj = push_trunk_jobs(jobs, nj, qsh, a.prm.q + net * q_stride);
+        const CUtensorMap *mq = a.use_tma ? &a.maps[0] : nullptr, *mt = a.use_tma ? &a.maps[1] : nullptr,
+                          *mp = a.use_tma ? &a.maps[2] : nullptr;
+        int nj = push_trunk_jobs(jobs, 0, ps, a.prm.pi, mp, 0);
+        nj = push_trunk_jobs(jobs, nj, qsh, a.prm.q_target + net * q_stride, mt, net);
+        if (post) nj = push_trunk_jobs(jobs, nj, qsh, a.prm.q + net * q_stride, mq, net);
     }
     float *head_pi = sm + pl.off_heads, *head_qt = head_pi + head_floats(ps.hidden, 2 * A),
           *head_q = head_qt + head_floats(qsh.hidden, 1);
@@ -223,7 +240,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     if (post) stage_head(head_q, qsh, a.prm.q + net * q_stride);
     __syncthreads();
     WeightPipe pipe;
-    pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
+    pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
 
     ASAC_PHASE(0, 1);
     // ---- policy over the P rows
@@ -481,14 +498,15 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
     WeightJob *jobs = reinterpret_cast<WeightJob *>(sm + pl.off_pipe);
     uint64_t *bars = reinterpret_cast<uint64_t *>(jobs + MAX_WEIGHT_JOBS);
     if (tid == 0) {
-        const int nj = push_trunk_jobs(jobs, 0, qsh, prm);
-        push_trunk_jobs_reverse(jobs, nj, qsh, prm);
+        const CUtensorMap *mq = a.use_tma ? &a.maps[0] : nullptr;
+        const int nj = push_trunk_jobs(jobs, 0, qsh, prm, mq, net);
+        push_trunk_jobs_reverse(jobs, nj, qsh, prm, mq, net);
     }
     float *head_q = sm + pl.off_heads + head_floats(c.pi_hidden, 2 * A);
     stage_head(head_q, qsh, prm);
     __syncthreads();
     WeightPipe pipe;
-    pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
+    pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
 
     const int K0 = S + A, K04 = round_up(K0, 4);
     for (int i = tid; i < R * K04; i += NT) {
@@ -553,8 +571,9 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
         layer_weight_grad(dZ, lda, px[l], lda, H, K, TBa, gout + net_w_off(qsh, l), gout + net_b_off(qsh, l));
         if (l > 0) {
             const float *Ws, *bs;
+            const bool swz = pipe_front_swizzled(pipe);
             pipe_acquire(pipe, Ws, bs);
-            layer_input_grad(H, dZ, lda, Ws, dY, dX, true, part);  // ends with a CTA barrier
+            layer_input_grad(H, dZ, lda, Ws, dY, dX, true, part, swz);  // ends with a CTA barrier
             pipe_release(pipe);
             cur = (cur + 2) % 3;
         }
@@ -600,17 +619,18 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     // ranks != 0 leave before the policy backward: they must not have its weights in flight at exit
     const int n_jobs = pl.n_jobs - (net == 0 ? 0 : dp - 1);
     if (tid == 0) {
-        int nj = push_trunk_jobs(jobs, 0, ps, a.prm.pi);
-        nj = push_trunk_jobs(jobs, nj, qsh, q_prm);
-        nj = push_trunk_jobs_reverse(jobs, nj, qsh, q_prm);
-        if (net == 0) nj = push_trunk_jobs_reverse(jobs, nj, ps, a.prm.pi);
+        const CUtensorMap *mq = a.use_tma ? &a.maps[0] : nullptr, *mp = a.use_tma ? &a.maps[2] : nullptr;
+        int nj = push_trunk_jobs(jobs, 0, ps, a.prm.pi, mp, 0);
+        nj = push_trunk_jobs(jobs, nj, qsh, q_prm, mq, net);
+        nj = push_trunk_jobs_reverse(jobs, nj, qsh, q_prm, mq, net);
+        if (net == 0) nj = push_trunk_jobs_reverse(jobs, nj, ps, a.prm.pi, mp, 0);
     }
     float *head_pi = sm + pl.off_heads, *head_q = head_pi + head_floats(Hp, 2 * A);
     stage_head(head_pi, ps, a.prm.pi);
     stage_head(head_q, qsh, q_prm);
     __syncthreads();
     WeightPipe pipe;
-    pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, n_jobs);
+    pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, n_jobs);
 
     ASAC_PHASE(2, 1);
     // ---- policy forward (saved)
@@ -690,8 +710,9 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
             __syncthreads();
             if (l > 0) {
                 const float *Ws, *bs;
+                const bool swz = pipe_front_swizzled(pipe);
                 pipe_acquire(pipe, Ws, bs);
-                layer_input_grad(Hq, dZ, lda, Ws, dY, dX, true, part);  // ends with a CTA barrier
+                layer_input_grad(Hq, dZ, lda, Ws, dY, dX, true, part, swz);  // ends with a CTA barrier
                 pipe_release(pipe);
                 cur = (cur + 2) % 3;
             } else {
@@ -776,8 +797,9 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         layer_weight_grad(dZ, lda, px[l], lda, Hp, K, TBa, gout + net_w_off(ps, l), gout + net_b_off(ps, l));
         if (l > 0) {
             const float *Ws, *bs;
+            const bool swz = pipe_front_swizzled(pipe);
             pipe_acquire(pipe, Ws, bs);
-            layer_input_grad(Hp, dZ, lda, Ws, dY, dX, true, part);  // ends with a CTA barrier
+            layer_input_grad(Hp, dZ, lda, Ws, dY, dX, true, part, swz);  // ends with a CTA barrier
             pipe_release(pipe);
             cur = (cur + 2) % 3;
         }
@@ -1135,7 +1157,7 @@ struct MlpPlan {
 __host__ __device__ __forceinline__ MlpPlan mlp_plan(const NetShape &s, int rows_per_cta) {
     MlpPlan p;
     p.lda = tile_lda(s.hidden, s.in_dim);
-    p.wsz = round_up(tile_wsz(s.hidden, s.in_dim), 4);
+    p.wsz = round_up(tile_wsz(s.hidden, s.in_dim), 256);
     int o = rows_per_cta * p.lda;  // xin at 0
     p.off_a = o; o += rows_per_cta * p.lda;
     p.off_b = o; o += rows_per_cta * p.lda;
@@ -1143,6 +1165,7 @@ __host__ __device__ __forceinline__ MlpPlan mlp_plan(const NetShape &s, int rows
     p.off_part = o; o += tile_part_floats(s.hidden);
     p.off_pipe = o; o += PIPE_HEADER_FLOATS;
     p.off_slots = o;
+    o += 256;  // 1024-byte alignment slack of the slots
     p.n_slots = slots_that_fit(o, p.wsz, s.depth);
     p.total = o + p.n_slots * p.wsz;
     return p;
@@ -1163,7 +1186,7 @@ __global__ void __launch_bounds__(NT) k_mlp_forward(const MlpArgs a) {
     if (tid == 0) push_trunk_jobs(jobs, 0, s, a.params);
     __syncthreads();
     WeightPipe pipe;
-    pipe_init(pipe, sm + pl.off_slots, bars, jobs, pl.n_slots, pl.wsz, s.depth);
+    pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, s.depth);
     const int K4 = round_up(s.in_dim, 4);
     const int rp = round_up(rows, PASS_ROWS);
     for (int i = tid; i < rp * K4; i += NT) {
@@ -1225,11 +1248,73 @@ extern "C" int64_t asac_mlp_param_stride(int in_dim, int hidden, int depth, int 
     return net_stride(NetShape{in_dim, hidden, depth, out_dim});
 }
 
+// ---- TMA tensor maps of the hidden -> hidden weights (cached per parameter buffer)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = [] {
+        const char *e = getenv("ASAC_TMA");
+        if (e && e[0] == '0') return (TensorMapEncodeFn) nullptr;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (TensorMapEncodeFn)p;
+    }();
+    return fn;
+}
+struct CachedMap {
+    const float *base;
+    int hidden, depth, nets;
+    int64_t stride;
+    CUtensorMap map;
+};
+// dims {k = H, row = H, layer = depth - 1, member}: layer l >= 1 of member i starts at
+// base + i * stride + net_w_off(shape, l); consecutive hidden -> hidden layers are H * (H + 1) floats apart
+static bool weight_tensor_map(CUtensorMap *out, const float *base, const NetShape &s, int nets, int64_t stride) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc || s.depth < 2 || s.hidden < 32 || (((uintptr_t)base) & 15) != 0) return false;
+    static std::mutex mu;
+    static std::vector<CachedMap> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const CachedMap &c : cache)
+        if (c.base == base && c.hidden == s.hidden && c.depth == s.depth && c.nets == nets && c.stride == stride) {
+            *out = c.map;
+            return true;
+        }
+    const cuuint64_t H = (cuuint64_t)s.hidden;
+    cuuint64_t dims[4] = {H, H, (cuuint64_t)(s.depth - 1), (cuuint64_t)nets};
+    cuuint64_t strides[3] = {H * 4, H * (H + 1) * 4, (cuuint64_t)stride * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)s.hidden, 1, 1}, elem[4] = {1, 1, 1, 1};
+    CachedMap c;
+    c.base = base; c.hidden = s.hidden; c.depth = s.depth; c.nets = nets; c.stride = stride;
+    const CUresult r = enc(&c.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)(base + net_w_off(s, 1)), dims, strides, box,
+                           elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    if (cache.size() < 256) cache.push_back(c);
+    *out = c.map;
+    return true;
+}
+
 static int make_args(SacArgs &a, const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
                      const AsacSacWork *wrk) {
     int rc = validate(cfg);
     if (rc != ASAC_OK) return rc;
     ASAC_REQUIRE(prm && wrk, "null params/work");
+    memset(&a.maps, 0, sizeof(a.maps));
+    {
+        const NetShape qs = q_shape(*cfg), ps = pi_shape(*cfg);
+        const bool needq = qs.depth >= 2 && qs.hidden >= 32, needp = ps.depth >= 2 && ps.hidden >= 32;
+        const bool okq = !needq || (weight_tensor_map(&a.maps[0], prm->q, qs, cfg->ensemble, net_stride(qs)) &&
+                                    weight_tensor_map(&a.maps[1], prm->q_target, qs, cfg->ensemble, net_stride(qs)));
+        const bool okp = !needp || weight_tensor_map(&a.maps[2], prm->pi, ps, 1, net_stride(ps));
+        // one flag for the kernels: families without hidden -> hidden layers have no TMA jobs anyway
+        // (tma_layer() in mlp_tile.cuh); a failed encode disables TMA for the whole launch
+        a.use_tma = (okq && okp && tensor_map_encoder() != nullptr) ? 1 : 0;
+    }
     a.cfg = *cfg;
     a.prm = *prm;
     if (bat) a.bat = *bat; else memset(&a.bat, 0, sizeof(a.bat));
