@@ -35,12 +35,15 @@ constexpr int PASS_ROWS = 16;  // rows per GEMM pass
 
 __host__ __device__ __forceinline__ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// The layer routines below are deliberately NOT inlined: a tile kernel walks ~10 layers through
-// three or four call sites, and with everything inlined (x4 width instantiations) k_value_pass
-// grew to 18 K SASS instructions (290 KB) — the ncu source page showed > 50 % of the warp stall
-// samples in `no_instruction` (instruction-cache misses).  One copy per width keeps the hot loop
-// resident.  Pointer arguments that live in shared memory are declared to the compiler with
-// ASAC_SMEM so the out-of-line code still uses LDS/STS.
+// Code placement: a tile kernel walks ~10 layers through three or four call sites.  With everything
+// inlined (x4 width instantiations per site) k_value_pass grew to 18 K SASS instructions (290 KB)
+// and > 50 % of the warp stall samples were `no_instruction` (instruction-cache misses), so the
+// per-layer routines are out of line: one copy per width keeps the hot loop resident.  (Measured
+// alternative, same box: out-of-line TRUNK walks with the layers inlined into them — one call per
+// net instead of one per layer — were 2.2 % slower.)  Pointer PARAMETERS that live in shared memory
+// are declared with ASAC_SMEM so the out-of-line code still uses LDS/STS.  Hints on pointers that
+// are derived inside inlined code are not safe: the compiler folded one to false and deleted a
+// whole trunk walk.
 #define ASAC_SMEM(p) __builtin_assume(__isShared(p))
 
 // ---------------------------------------------------------------- flat parameter layout
@@ -229,12 +232,19 @@ __device__ __forceinline__ void pipe_init(WeightPipe &p, float *slots, uint64_t 
 
 // waits for the oldest unconsumed job; returns its staged weights / bias
 // debug counters of CTA (0,0), thread 0: cycles spent waiting for staged weights / number of waits
+#ifdef ASAC_PROBES
+#define ASAC_PROBE_ON 1
+#else
+#define ASAC_PROBE_ON 0
+#endif
+// (compiled in with -DASAC_PROBES only: the read-modify-write of a global counter by thread 0 after every
+// layer stalls the whole CTA at the next barrier — 2.7 % of the step when it was always on)
 static __device__ long long g_pipe_wait[2];
 static __device__ long long g_layer_seg[8];  // layer_forward segments of CTA (0,0), thread 0 (debug)
 __device__ __forceinline__ void pipe_acquire(const WeightPipe &p, const float *&Ws, const float *&bs) {
     const int slot = p.consumed % p.n_slots;
     const unsigned parity = (unsigned)((p.consumed / p.n_slots) & 1);
-    const bool probe = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    const bool probe = ASAC_PROBE_ON && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
     const long long c0 = probe ? clock64() : 0;
     mbar_wait(p.bars + slot, parity);
     if (probe) {
@@ -277,7 +287,7 @@ __device__ __noinline__ void layer_forward_t(const float *X, int ldx, int K4, co
     const int ldw = K4 + 4;
     const int kchunk = round_up((K4 + KSPLIT - 1) / KSPLIT, 4);
     const int kb = ks * kchunk, ke = min(K4, kb + kchunk);
-    const bool probe = threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    const bool probe = ASAC_PROBE_ON && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0;
 #pragma unroll 1
     for (int r0 = 0; r0 < nrows; r0 += PASS_ROWS) {
         const long long c0 = probe ? clock64() : 0;

@@ -1,6 +1,10 @@
 #!/usr/bin/env python
 """Phase breakdown of the three row-tile kernels inside a running learner: runs the bench workload
-for a few steps (CUDA graph), then reads the clock stamps CTA (0,0) took at its phase boundaries."""
+for a few steps (CUDA graph), then reads the clock stamps CTA (0,0) took at its phase boundaries.
+The per-layer accumulators (weight waits, layer_forward segments) are only compiled in with
+`make EXTRA=-DASAC_PROBES` — they perturb the timing they measure (one global read-modify-write
+per probe by thread 0) and cost 2.7 % of the step, so the product build leaves them out and
+prints zeros for them."""
 import ctypes as C
 import sys
 from pathlib import Path
@@ -39,6 +43,9 @@ def main():
     print('layer_forward of CTA (0,0), per 16-row pass: ' + ', '.join(
         f'{name} {clk[1, 20 + i] / 1965.0 / n_pass:.2f} us' for i, name in
         enumerate(['K-split GEMM', 'barrier', 'epilogue', 'barrier'])) + f'  ({n_pass // steps} passes per step)')
+    print(f'whole trunk layer (acquire + forward + release): {clk[1, 25] / 1965.0 / max(int(clk[1, 26]), 1):.2f} us; '
+          f'target-critic phase of the last value pass: before trunk {(clk[0, 10] - clk[0, 4]) / 1965.0:.2f}, '
+          f'trunk {(clk[0, 11] - clk[0, 10]) / 1965.0:.2f}, head + barrier {(clk[0, 12] - clk[0, 11]) / 1965.0:.2f} us')
     mhz = 1965.0
     for k, title in ((0, 'k_value_pass (last launch = post pass)'), (1, 'k_q_backward'), (2, 'k_policy_backward')):
         print(title)
