@@ -402,6 +402,166 @@ def gen_sac_case(name, *, S, A, E, hidden, depth, B, b, n, steps, seed, use_prio
     print('wrote', f'sac_{name}.npz', sum(v.nbytes for v in out.values()), 'bytes raw')
 
 
+def gen_sac_rnn_case(name, *, So, A, E, B, b, n, steps, seed, use_priority=True, **hyper):
+    """``_train`` + tail of ``train`` with the recurrent plugin ``envs/test/nn_rnn.py`` (GRU(So + A -> 8,
+    2 layers), hidden shape (2, 8)) and ``seq_encoder=SEQ_ENCODER.RNN``: the critic loss trains the
+    representation through every burn-in step (sac_base.py:2066-2116)."""
+    SAC_Base, _, _ = import_reference()
+    from algorithm.utils.enums import SEQ_ENCODER
+    nn = load_reference_nn('envs/test/nn_rnn.py')
+    torch.manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    with _NoThread():
+        sac = SAC_Base(obs_names=['vector'], obs_shapes=[(So,)], d_action_sizes=[], c_action_size=A,
+                       model_abs_dir=None, nn=nn, device='cpu', seed=seed, batch_size=B,
+                       burn_in_step=b, n_step=n, ensemble_q_num=E, ensemble_q_sample=E,
+                       seq_encoder=SEQ_ENCODER.RNN, use_priority=use_priority,
+                       replay_config={'capacity': 1024}, **hyper)
+    layers, H = tuple(sac.seq_hidden_state_shape)
+    S = sac.state_size
+    assert S == H
+    with torch.no_grad():
+        for net in sac.model_target_q_list + [sac.model_target_rep]:
+            for p in net.parameters():
+                p.add_(torch.randn_like(p) * 0.02)
+        for net in sac.model_q_list + [sac.model_policy]:
+            for pn, p in net.named_parameters():
+                if pn.endswith('bias'):
+                    p.add_(torch.randn_like(p) * 0.05)
+    L = b + n + 1
+    q_depth = len([k for k in sac.model_q_list[0].state_dict() if k.endswith('linear.weight')])
+    q_hidden = sac.model_q_list[0].state_dict()['c_dense.dense.0.linear.weight'].shape[0]
+    out = {'meta': np.array([So, A, E, q_hidden, q_depth, B, b, n, steps, int(use_priority), layers, H],
+                            dtype=np.int64)}
+    hp = dict(tau=sac.tau, update_target_per_step=sac.update_target_per_step, learning_rate=sac.learning_rate,
+              gamma=sac.gamma, v_lambda=sac.v_lambda, v_rho=float(sac.v_rho), v_c=float(sac.v_c),
+              clip_epsilon=sac.clip_epsilon, use_n_step_is=float(sac.use_n_step_is),
+              target_c_alpha=sac.target_c_alpha, init_log_alpha=float(sac.log_c_alpha),
+              use_auto_alpha=float(sac.use_auto_alpha))
+    for k, v in hp.items():
+        out[f'hp.{k}'] = np.float64(v)
+
+    def dump_params(prefix):
+        for i in range(E):
+            for k, t in sac.model_q_list[i].state_dict().items():
+                out[f'{prefix}.q{i}.{k}'] = t.detach().numpy().copy()
+            for k, t in sac.model_target_q_list[i].state_dict().items():
+                out[f'{prefix}.qt{i}.{k}'] = t.detach().numpy().copy()
+        for k, t in sac.model_policy.state_dict().items():
+            out[f'{prefix}.pi.{k}'] = t.detach().numpy().copy()
+        for k, t in sac.model_rep.state_dict().items():
+            out[f'{prefix}.rep.{k}'] = t.detach().numpy().copy()
+        for k, t in sac.model_target_rep.state_dict().items():
+            out[f'{prefix}.rept.{k}'] = t.detach().numpy().copy()
+        out[f'{prefix}.log_c_alpha'] = sac.log_c_alpha.detach().numpy().copy()
+
+    dump_params('init')
+    ys = []
+    orig_get_y = sac._get_y
+
+    def tap_get_y(**kw):
+        d_y, c_y = orig_get_y(**kw)
+        ys.append(c_y.clone())
+        return d_y, c_y
+
+    sac._get_y = tap_get_y
+    rep_grads = {}
+    orig_rep_step = sac.optimizer_rep.step
+
+    def tap_rep_step(*a, **k):  # gradients as the representation's Adam sees them
+        for kk, p in sac.model_rep.named_parameters():
+            rep_grads[kk] = p.grad.detach().numpy().copy()
+        return orig_rep_step(*a, **k)
+
+    sac.optimizer_rep.step = tap_rep_step
+
+    for s in range(steps):
+        obs = torch.from_numpy(rng.randn(B, L, So).astype(np.float32))
+        actions = torch.from_numpy((rng.rand(B, L - 1, A) * 1.9 - 0.95).astype(np.float32))
+        rewards = torch.from_numpy(rng.randn(B, L - 1).astype(np.float32))
+        dones = torch.from_numpy(rng.rand(B, L - 1) < 0.1)
+        mu_probs = torch.from_numpy((rng.rand(B, L - 1, A) * 1.5 + 0.01).astype(np.float32))
+        hidden = torch.from_numpy((rng.randn(B, L, layers, H) * 0.5).astype(np.float32))
+        pad = np.zeros((B, L - 1), dtype=bool)
+        last = np.zeros((B, L - 1), dtype=bool)
+        for r in range(B):
+            if L - 1 > 1 and rng.rand() < 0.4:
+                cut = rng.randint(b + 1, L)
+                if cut < L - 1:
+                    pad[r, cut:] = True
+                last[r, cut - 1] = rng.rand() < 0.7
+            if b > 0 and rng.rand() < 0.3:
+                pad[r, :rng.randint(1, b + 1)] = True
+        tpad = torch.from_numpy(pad)
+        mu_probs[tpad] = 1.
+        rewards[tpad] = 0.
+        dones[tpad] = True
+        actions[tpad] = 0.
+        hidden[:, :-1][tpad] = 0.  # sac_base.py:2453
+        index = torch.arange(L - 1, dtype=torch.int32).repeat(B, 1)
+        index[tpad] = -1
+        pri = torch.from_numpy((rng.rand(B, 1) * 0.9 + 0.1).astype(np.float32)) if use_priority else None
+        noise = dict(eps_y=torch.from_numpy(rng.randn(B, n + 1, A).astype(np.float32)),
+                     eps_pi=torch.from_numpy(rng.randn(B, A).astype(np.float32)),
+                     eps_alpha=torch.from_numpy(rng.randn(B, A).astype(np.float32)),
+                     eps_td=torch.from_numpy(rng.randn(B, n + 1, A).astype(np.float32)))
+        pre = f's{s}'
+        for k, t in dict(obs=obs, hidden0=hidden[:, 0], actions=actions, rewards=rewards, dones=dones,
+                         mu_probs=mu_probs, last_masks=torch.from_numpy(last), padding_masks=tpad).items():
+            out[f'{pre}.in.{k}'] = t.numpy().copy()
+        if pri is not None:
+            out[f'{pre}.in.priority_is'] = pri.numpy().copy()
+        for k, t in noise.items():
+            out[f'{pre}.in.{k}'] = t.numpy().copy()
+
+        ys.clear()
+        with _NoiseTap() as tap:
+            tap.queue = [noise['eps_y'], noise['eps_pi']]
+            if sac.use_auto_alpha:
+                tap.queue.append(noise['eps_alpha'])
+            if use_priority:
+                tap.queue.append(noise['eps_td'])
+            bnx_states, next_hidden, bnx_target_states = sac._train(
+                bn_indexes=index.clone(), bn_last_masks=torch.from_numpy(last).clone(),
+                bn_padding_masks=tpad.clone(), bnx_obses_list=[obs.clone()],
+                bn_actions=actions.clone(), bn_rewards=rewards.clone(), bn_dones=dones.clone(),
+                bn_mu_probs=mu_probs.clone(), bnx_pre_seq_hidden_states=hidden.clone(),
+                priority_is=pri.clone() if pri is not None else None)
+            out[f'{pre}.out.y'] = ys[0].numpy().copy()
+            out[f'{pre}.out.states_post'] = bnx_states.detach().numpy().copy()
+            out[f'{pre}.out.target_states'] = bnx_target_states.detach().numpy().copy()
+            out[f'{pre}.out.next_hidden'] = next_hidden[:, :-1].detach().numpy().copy()
+            for k, g in rep_grads.items():
+                out[f'{pre}.grad.rep.{k}'] = g
+            for i in range(E):
+                for k, p in sac.model_q_list[i].named_parameters():
+                    out[f'{pre}.grad.q{i}.{k}'] = p.grad.detach().numpy().copy()
+            for k, p in sac.model_policy.named_parameters():
+                out[f'{pre}.grad.pi.{k}'] = p.grad.detach().numpy().copy()
+            if sac.use_auto_alpha:
+                out[f'{pre}.grad.log_c_alpha'] = sac.log_c_alpha.grad.detach().numpy().copy()
+            pi_probs = None
+            bn_states = bnx_states[:, :-1]
+            if sac.use_n_step_is:
+                pi_probs = sac.get_l_probs(l_obses_list=[obs[:, :-1]], l_states=bn_states, l_actions=actions)
+                out[f'{pre}.out.pi_probs'] = pi_probs.numpy().copy()
+            if use_priority:
+                td = sac._get_td_error(
+                    n_last_masks=torch.from_numpy(last)[:, b:], n_padding_masks=tpad[:, b:],
+                    nx_obses_list=[obs[:, b:]], state=bn_states[:, b],
+                    nx_target_states=bnx_target_states[:, b:], n_actions=actions[:, b:],
+                    n_rewards=rewards[:, b:].clone(), n_dones=dones[:, b:],
+                    n_mu_probs=pi_probs[:, b:].clone() if sac.use_n_step_is else None)
+                out[f'{pre}.out.td_error'] = td.numpy().copy()
+                out[f'{pre}.out.y_td'] = ys[1].numpy().copy()
+            assert not tap.queue
+        sac.increase_global_step()
+        dump_params(f'{pre}.after')
+    sac.close()
+    np.savez_compressed(GOLDEN / f'sac_{name}.npz', **out)
+    print('wrote', f'sac_{name}.npz', sum(v.nbytes for v in out.values()), 'bytes raw')
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     gen_per_case('small', capacity=64, batch_size=8, prev_n=2, post_n=3, alpha=0.9,
@@ -422,6 +582,9 @@ def main():
                  update_target_per_step=2, gamma=0.97)
     gen_sac_case('nois', S=4, A=2, E=2, hidden=32, depth=2, B=10, b=0, n=2, steps=2, seed=13,
                  use_n_step_is=False, use_auto_alpha=False)
+    # config-4 shapes (envs/test/nn_rnn.py: GRU(6 + 2 -> 8, 2 layers)), shorter burn-in, 2 steps
+    gen_sac_rnn_case('rnn', So=6, A=2, E=2, B=16, b=5, n=3, steps=2, seed=14, v_lambda=0.95)
+    gen_sac_rnn_case('rnn_b0', So=6, A=2, E=2, B=8, b=0, n=1, steps=2, seed=15, use_n_step_is=False)
 
 
 if __name__ == '__main__':

@@ -15,9 +15,12 @@ def load_golden(name: str) -> dict:
 
 
 def sac_case_meta(g: dict) -> dict:
-    S, A, E, hidden, depth, B, b, n, steps, use_priority = [int(x) for x in g['meta']]
-    return dict(S=S, A=A, E=E, hidden=hidden, depth=depth, B=B, b=b, n=n, steps=steps,
-                use_priority=bool(use_priority))
+    S, A, E, hidden, depth, B, b, n, steps, use_priority = [int(x) for x in g['meta'][:10]]
+    m = dict(S=S, A=A, E=E, hidden=hidden, depth=depth, B=B, b=b, n=n, steps=steps,
+             use_priority=bool(use_priority))
+    if len(g['meta']) > 10:  # recurrent fixtures: S above is the observation width, the state is the GRU width
+        m.update(So=S, rep_layers=int(g['meta'][10]), S=int(g['meta'][11]))
+    return m
 
 
 def sac_hyper_from_golden(g: dict):
@@ -52,6 +55,36 @@ def golden_batch(g: dict, step: int):
                      priority_is=t('priority_is') if (pre + 'priority_is') in g else None)
     noise = SacNoise(eps_y=t('eps_y'), eps_pi=t('eps_pi'), eps_alpha=t('eps_alpha'), eps_td=t('eps_td'))
     return batch, noise
+
+
+def golden_rep_params(g: dict, prefix: str):
+    """-> (rep dict, target rep dict) keyed by the plugin's state_dict names (rnn._grus.<l>.*)."""
+    def sub(tag):
+        pre = f'{prefix}.{tag}.'
+        return {k[len(pre):]: v for k, v in g.items() if k.startswith(pre)}
+    return sub('rep'), sub('rept')
+
+
+def golden_rep_batch(g: dict, step: int):
+    from oracle.rep_oracle import SacRepBatch
+    from oracle.sac_oracle import SacNoise
+    pre = f's{step}.in.'
+    t = lambda k: torch.from_numpy(g[pre + k])
+    batch = SacRepBatch(obs=t('obs'), hidden0=t('hidden0'), actions=t('actions'), rewards=t('rewards'),
+                        dones=t('dones'), mu_probs=t('mu_probs'), last_masks=t('last_masks'),
+                        padding_masks=t('padding_masks'),
+                        priority_is=t('priority_is') if (pre + 'priority_is') in g else None)
+    noise = SacNoise(eps_y=t('eps_y'), eps_pi=t('eps_pi'), eps_alpha=t('eps_alpha'), eps_td=t('eps_td'))
+    return batch, noise
+
+
+def rep_oracle_from_golden(g: dict, dtype=torch.float32):
+    from oracle.rep_oracle import SacRepOracle
+    m = sac_case_meta(g)
+    oracle = SacRepOracle(sac_hyper_from_golden(g), m['So'], m['rep_layers'], dtype=dtype)
+    oracle.load_params(*golden_params(g, 'init', m['E']))
+    oracle.load_rep(*golden_rep_params(g, 'init'))
+    return oracle
 
 
 def rel_err(a, b) -> float:

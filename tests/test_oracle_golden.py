@@ -105,6 +105,45 @@ def test_sac_oracle_matches_reference(name):
             assert rel_err(v, g[f'{pre}after.{k}']) < 1e-5, (s, k)
 
 
+@pytest.mark.parametrize('name', ['sac_rnn.npz', 'sac_rnn_b0.npz'])
+def test_recurrent_sac_oracle_matches_reference(name):
+    """The GRU-representation flow (envs/test/nn_rnn.py, seq_encoder=RNN) against the real reference:
+    BPTT gradients of the representation, re-encoded states, next hidden states, td error on the
+    target states."""
+    from tests.helpers import golden_rep_batch, rep_oracle_from_golden
+    torch.set_num_threads(1)
+    g = load_golden(name)
+    m = sac_case_meta(g)
+    oracle = rep_oracle_from_golden(g)
+    hp = oracle.hp
+    tol = 2e-6
+    for s in range(m['steps']):
+        batch, noise = golden_rep_batch(g, s)
+        out = oracle.step(batch, noise)
+        pre = f's{s}.'
+        assert rel_err(out['y'], g[pre + 'out.y']) < tol
+        assert rel_err(out['target_states'], g[pre + 'out.target_states']) < tol
+        assert rel_err(out['states_post'], g[pre + 'out.states_post']) < tol
+        assert rel_err(out['next_hidden'], g[pre + 'out.next_hidden']) < tol
+        for k, v in out['grad_rep'].items():
+            assert rel_err(v, g[f'{pre}grad.rep.{k}']) < tol, (s, k)
+            assert np.abs(g[f'{pre}grad.rep.{k}']).max() > 0, 'fixture should exercise the representation gradient'
+        for i in range(m['E']):
+            for k, v in out['grad_q'][i].items():
+                assert rel_err(v, g[f'{pre}grad.q{i}.{k}']) < tol, (s, i, k)
+        for k, v in out['grad_policy'].items():
+            assert rel_err(v, g[f'{pre}grad.pi.{k}']) < tol, (s, k)
+        if hp.use_auto_alpha:
+            assert rel_err(out['grad_log_alpha'], g[pre + 'grad.log_c_alpha']) < tol
+        if hp.use_n_step_is:
+            assert rel_err(out['pi_probs'], g[pre + 'out.pi_probs']) < 1e-5
+        if hp.use_priority:
+            assert rel_err(out['td_error'], g[pre + 'out.td_error']) < 1e-5
+            assert rel_err(out['y_td'], g[pre + 'out.y_td']) < 1e-5
+        for k, v in oracle.snapshot().items():
+            assert rel_err(v, g[f'{pre}after.{k}']) < 1e-5, (s, k)
+
+
 def test_vectorized_descent_equals_scalar():
     rng = np.random.RandomState(5)
     t = SumTreeOracle(1024)
