@@ -44,7 +44,8 @@ class AsacSacConfig(C.Structure):
                 ('tau', C.c_float), ('one_minus_tau', C.c_float), ('gamma', C.c_float), ('v_rho', C.c_float),
                 ('v_c', C.c_float), ('clip_epsilon', C.c_float), ('target_c_alpha', C.c_float),
                 ('td_error_min', C.c_float), ('td_error_max', C.c_float), ('per_alpha', C.c_float),
-                ('gamma_ratio', C.c_float * MAX_NSTEP), ('lambda_ratio', C.c_float * MAX_NSTEP)]
+                ('gamma_ratio', C.c_float * MAX_NSTEP), ('lambda_ratio', C.c_float * MAX_NSTEP),
+                ('rep_kind', C.c_int32), ('reserved_', C.c_int32)]
 
 
 class AsacSacParams(C.Structure):
@@ -56,7 +57,8 @@ class AsacSacParams(C.Structure):
 class AsacSacBatch(C.Structure):
     _fields_ = [('states', vp), ('actions', vp), ('rewards', vp), ('dones', vp), ('last_masks', vp),
                 ('padding_masks', vp), ('mu_probs', vp), ('priority_is', vp),
-                ('eps_y', vp), ('eps_pi', vp), ('eps_alpha', vp), ('eps_td', vp)]
+                ('eps_y', vp), ('eps_pi', vp), ('eps_alpha', vp), ('eps_td', vp),
+                ('states_post', vp), ('target_states', vp)]
 
 
 class AsacWriteColumn(C.Structure):
@@ -78,7 +80,26 @@ class AsacSacWork(C.Structure):
     _fields_ = [('n_tiles', C.c_int32),
                 ('y', vp), ('tq', vp), ('q_val', vp), ('loss_q', vp), ('grad_q_part', vp), ('grad_q', vp),
                 ('grad_pi_part', vp), ('grad_pi', vp), ('stats_pi', vp), ('grad_alpha_part', vp),
-                ('grad_alpha', vp), ('pi_probs', vp), ('post_parts', vp), ('y_td', vp), ('td_error', vp)]
+                ('grad_alpha', vp), ('pi_probs', vp), ('post_parts', vp), ('y_td', vp), ('td_error', vp),
+                ('grad_state', vp)]
+
+
+GRU_MAX_LAYERS = 4
+
+
+class AsacGruShape(C.Structure):
+    _fields_ = [('obs_size', C.c_int32), ('action_size', C.c_int32), ('hidden', C.c_int32), ('layers', C.c_int32)]
+
+
+class AsacGruNet(C.Structure):
+    _fields_ = [('params', vp), ('states', vp), ('hn', vp), ('save', vp)]
+
+
+class AsacGruRep(C.Structure):
+    _fields_ = [('shape', AsacGruShape), ('params', vp), ('params_target', vp), ('m', vp), ('v', vp),
+                ('obs', vp), ('h0', vp), ('h0_b_stride', C.c_int64),
+                ('states', vp), ('states_post', vp), ('target_states', vp), ('hn', vp), ('hn_post', vp),
+                ('save', vp), ('grad_part', vp), ('grad', vp), ('rep_tiles', C.c_int32), ('reserved_', C.c_int32)]
 
 
 i32, i64, u64, f32 = C.c_int, C.c_int64, C.c_uint64, C.c_float
@@ -124,6 +145,16 @@ PROTOTYPES = {
     'asac_sac_finish_step': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp, i64, vp, vp, vp,
                                    P(AsacPeerTable), vp]),
     'asac_peer_recv_words': (i64, [P(AsacSacConfig), i32]),
+    'asac_gru_param_count': (i64, [P(AsacGruShape)]),
+    'asac_gru_backward_tile': (i32, [P(AsacGruShape), i32]),
+    'asac_gru_forward': (i32, [P(AsacGruShape), P(AsacGruNet), i32, vp, vp, i32, vp, vp, i64, i32, i32, vp]),
+    'asac_gru_backward': (i32, [P(AsacGruShape), vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, vp, i32, vp, vp, vp,
+                                vp]),
+    'asac_flat_reduce_adam': (i32, [vp, vp, vp, vp, i32, i64, i64, vp, vp, C.c_double, vp]),
+    'asac_flat_polyak': (i32, [vp, vp, i64, vp, i32, f32, f32, i32, vp]),
+    'asac_sac_step_networks_rep': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork),
+                                         P(AsacGruRep), i32, vp]),
+    'asac_sac_staged_tail': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp]),
     'asac_fill_normal': (i32, [vp, i64, u64, vp, i32, vp]),
     'asac_mlp_forward': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp]),
     'asac_mlp_forward_tc': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp]),

@@ -119,7 +119,10 @@ __host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c,
     const int L = c.seq_len, n = c.n_step, A = c.action_size;
     const int t0 = (mode == 1 && c.use_n_step_is) ? 0 : c.burn_in;
     const int Lp = L - t0;
-    const int rp = round_up(TB * Lp, PASS_ROWS);
+    // post pass of a run with a trained representation: the value rows go through the policy a second
+    // time on the TARGET representation's states (sac_base.py:2571-2582)
+    const int extra = (mode == 1 && c.rep_kind != 0) ? TB * (n + 1) : 0;
+    const int rp = round_up(TB * Lp + extra, PASS_ROWS);
     const int rq = round_up(TB * (n + 1), PASS_ROWS) + round_up(TB, PASS_ROWS);
     p.rows_max = rp > rq ? rp : rq;
     p.lda = sac_lda(c);
@@ -213,6 +216,14 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     const int Lp = L - t0;
     const int RP = TBa * Lp, RV = TBa * (n + 1), RS = TBa;
     const bool need_tq = !post && c.clip_epsilon > 0.f;
+    // which representation's states feed what (sac_base.py:2066-2105, 2558-2582): the train pass sees the
+    // online states before the representation's Adam step everywhere; the post pass evaluates the
+    // probabilities, the alpha loss and Q_i(s_b, a_b) on the re-encoded online states (st_p) and
+    // _get_y on the target representation's states (st_v).  Without a trained representation all three coincide.
+    const float *st_p = post && a.bat.states_post ? a.bat.states_post : a.bat.states;
+    const float *st_v = post && a.bat.target_states ? a.bat.target_states : st_p;
+    const bool split = post && c.rep_kind != 0;  // value rows run through the policy separately (rows RP ...)
+    const int RPt = RP + (split ? RV : 0);
     const ValuePlan pl = value_plan(c, TB, a.mode);
     const int lda = pl.lda;
     float *xin = sm + pl.off_xin, *bufA = sm + pl.off_a, *bufB = sm + pl.off_b;
@@ -246,19 +257,22 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     // ---- policy over the P rows
     {
         const int S4 = round_up(S, 4);
-        const int RPp = round_up(RP, PASS_ROWS);
+        const int RPp = round_up(RPt, PASS_ROWS);
         for (int i = tid; i < RPp * S4; i += NT) {
             const int r = i / S4, col = i - r * S4;
             float v = 0.f;
             if (r < RP && col < S) {
                 const int e = r / Lp, tt = r - e * Lp;
-                v = a.bat.states[((int64_t)(e0 + e) * L + t0 + tt) * S + col];
+                v = st_p[((int64_t)(e0 + e) * L + t0 + tt) * S + col];
+            } else if (r < RPt && col < S) {
+                const int rv = r - RP, e = rv / (n + 1), k = rv - e * (n + 1);
+                v = st_v[((int64_t)(e0 + e) * L + b + k) * S + col];
             }
             xin[r * lda + col] = v;
         }
         __syncthreads();
         float *h = net_trunk_forward(ps, pipe, xin, bufA, bufB, nullptr, nullptr, lda, RPp, part);
-        head_forward(h, lda, ps.hidden, head_pi, head_pi + 2 * A * ps.hidden, 2 * A, RP, ho);
+        head_forward(h, lda, ps.hidden, head_pi, head_pi + 2 * A * ps.hidden, 2 * A, RPt, ho);
         __syncthreads();
     }
 
@@ -269,7 +283,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     // thread per row this block was 4.6 us of serial transcendentals with 8 of 512 threads busy.
     float alpha_term = 0.f, alpha_loss = 0.f;
     const float log_alpha = a.prm.log_alpha[0];
-    for (int i = tid; i < RP * A; i += NT) {
+    for (int i = tid; i < RPt * A; i += NT) {
         const int r = i / A, j = i - r * A;
         float *hr = ho + r * 2 * A;
         const float m = hr[j], s = hr[A + j];
@@ -283,8 +297,11 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         if (r >= RP) continue;
         const int e = r / Lp, tt = r - e * Lp, t = t0 + tt, eg = e0 + e;
         const float *hr = ho + r * 2 * A;
+        // the policy's output on the value row of (e, t): the same row, or the extra row on st_v
+        const float *hv = (split && t >= b) ? ho + (RP + e * (n + 1) + (t - b)) * 2 * A : hr;
         if (part == 0 && t >= b) {  // value row k = t - b
             const int k = t - b, rv = e * (n + 1) + k;
+            hr = hv;
             const float *eps = (post ? a.bat.eps_td : a.bat.eps_y) + ((int64_t)eg * (n + 1) + k) * A;
             float corr = 0.f;
             for (int j = 0; j < A; ++j) {
@@ -312,6 +329,8 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
                 if (post) {
                     if (net == 0) a.wrk.pi_probs[((int64_t)eg * (L - 1) + t) * A + j] = pj;
                     mj = pj;
+                    // _get_y inside _get_td_error: pi from the target states' policy, mu := pi_probs
+                    if (split && t >= b) pj = expf(normal_log_prob(xa, hv[j], hv[A + j])) / fl;
                 } else {
                     mj = a.bat.mu_probs[((int64_t)eg * c.bn_stride + t) * A + j];
                 }
@@ -355,11 +374,11 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         float v = 0.f;
         if (r < RV) {
             const int e = r / (n + 1), k = r - e * (n + 1);
-            if (col < S) v = a.bat.states[((int64_t)(e0 + e) * L + b + k) * S + col];
+            if (col < S) v = st_v[((int64_t)(e0 + e) * L + b + k) * S + col];
             else if (col < K0) v = tanhf(xs[r * A + (col - S)]);
         } else if (r >= s_row0 && r < s_row0 + RS) {
             const int e = r - s_row0;
-            if (col < S) v = a.bat.states[((int64_t)(e0 + e) * L + b) * S + col];
+            if (col < S) v = st_p[((int64_t)(e0 + e) * L + b) * S + col];
             else if (col < K0) v = a.bat.actions[((int64_t)(e0 + e) * c.bn_stride + b) * A + (col - S)];
         }
         xin[r * lda + col] = v;
@@ -576,6 +595,17 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
             layer_input_grad(H, dZ, lda, Ws, dY, dX, true, part, swz);  // ends with a CTA barrier
             pipe_release(pipe);
             cur = (cur + 2) % 3;
+        } else if (a.wrk.grad_state) {
+            // trained representation: d loss_i / d state[:, b] (the state columns of the first layer's
+            // input gradient; target_c_q sees state.detach(), sac_base.py:1541)
+            const float *W0 = prm + net_w_off(qsh, 0);
+            for (int t = tid; t < TBa * S; t += NT) {
+                const int r = t / S, k = t - r * S;
+                float s = 0.f;
+                for (int h = 0; h < H; ++h) s = fmaf(dZ[r * lda + h], __ldg(W0 + (int64_t)h * K0 + k), s);
+                if (K0 == H) s += dY[r * lda + k];  // residual first block
+                a.wrk.grad_state[((int64_t)net * B + e0 + r) * S + k] = s;
+            }
         }
     }
     ASAC_PHASE(1, 31);
@@ -633,11 +663,12 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, n_jobs);
 
     ASAC_PHASE(2, 1);
-    // ---- policy forward (saved)
+    // ---- policy forward (saved); with a trained representation: on the re-encoded states (sac_base.py:2107-2113)
+    const float *st = a.bat.states_post ? a.bat.states_post : a.bat.states;
     const int S4 = round_up(S, 4);
     for (int i = tid; i < R * S4; i += NT) {
         const int r = i / S4, col = i - r * S4;
-        px[0][r * lda + col] = (r < TBa && col < S) ? a.bat.states[((int64_t)(e0 + r) * L + b) * S + col] : 0.f;
+        px[0][r * lda + col] = (r < TBa && col < S) ? st[((int64_t)(e0 + r) * L + b) * S + col] : 0.f;
     }
     __syncthreads();
     net_trunk_forward(ps, pipe, px[0], nullptr, nullptr, px, pz, lda, R, part);
@@ -1046,7 +1077,7 @@ __global__ void __launch_bounds__(1024) k_step_epilogue(const __grid_constant__ 
         value = td_to_priority(td, a.td_min, a.td_max, a.per_alpha, &bad);
         active = (a.store_ids[slot] == id);
     }
-    if (t < 4 && ((a.counter_mask >> t) & 1)) a.prm.counters[t] += 1;  // after the Adam step read counters[3]
+    if (t < 8 && ((a.counter_mask >> t) & 1)) a.prm.counters[t] += 1;  // after the Adam step read counters[3]
     if (__syncthreads_or(bad)) {
         if (t == 0) a.per_state[3] = 1.0;  // the reference raises 'td_error has nan'
         return;
@@ -1055,7 +1086,7 @@ __global__ void __launch_bounds__(1024) k_step_epilogue(const __grid_constant__ 
 }
 
 __global__ void k_bump(int64_t *counters, int mask) {
-    if (threadIdx.x < 4 && ((mask >> threadIdx.x) & 1)) counters[threadIdx.x] += 1;
+    if (threadIdx.x < 8 && ((mask >> threadIdx.x) & 1)) counters[threadIdx.x] += 1;
 }
 
 // sac_base.py:745-764: target = target * (1 - tau) + source * tau, gated on the global step
@@ -1546,6 +1577,98 @@ extern "C" int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacPar
     return ASAC_OK;
 }
 
+extern "C" int asac_flat_reduce_adam(float *param, float *m, float *v, const float *grad_part, int n_tiles,
+                                     int64_t tile_stride, int64_t count, float *grad, const int64_t *step_counter,
+                                     double learning_rate, void *stream) {
+    ASAC_REQUIRE(param && m && v && grad_part && grad && step_counter && n_tiles > 0 && count > 0,
+                 "asac_flat_reduce_adam: bad arguments");
+    AdamArgs a;
+    memset(&a.px, 0, sizeof(a.px));
+    a.param = param; a.m = m; a.v = v; a.part = grad_part; a.grad = grad; a.step = step_counter;
+    a.count = count; a.tile_stride = tile_stride; a.n_tiles = n_tiles;
+    a.write_grad = 1; a.do_adam = 1; a.grad_scale = 1.f; a.lr = learning_rate;
+    ASAC_CUDA(launch_ex(k_reduce_adam, dim3((unsigned)((count + ADAM_PARAMS_PER_CTA - 1) / ADAM_PARAMS_PER_CTA)),
+                        dim3(ADAM_PARAMS_PER_CTA * ADAM_TILE_GROUPS), 0, (cudaStream_t)stream, 0, true, a));
+    ASAC_LAUNCHED("k_reduce_adam");
+    return ASAC_OK;
+}
+
+extern "C" int asac_flat_polyak(float *target, const float *source, int64_t count, const int64_t *counters,
+                                int per_step, float tau, float one_minus_tau, int force, void *stream) {
+    ASAC_REQUIRE(target && source && count > 0 && (force || (counters && per_step >= 1)), "asac_flat_polyak: bad arguments");
+    k_polyak<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(target, source, count, counters,
+                                                                               per_step, tau, one_minus_tau, force);
+    ASAC_LAUNCHED("k_polyak");
+    return ASAC_OK;
+}
+
+extern "C" int asac_sac_step_networks_rep(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
+                                          const AsacSacWork *wrk, const AsacGruRep *rep, int with_polyak,
+                                          void *stream) {
+    SacArgs a;
+    int rc = make_args(a, cfg, prm, bat, wrk);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(rep && cfg->rep_kind == 1, "asac_sac_step_networks_rep: cfg.rep_kind must be 1 (GRU)");
+    ASAC_REQUIRE(rep->shape.hidden == cfg->state_size && rep->shape.action_size == cfg->action_size,
+                 "asac_sac_step_networks_rep: GRU width %d / action %d vs state_size %d / action_size %d",
+                 rep->shape.hidden, rep->shape.action_size, cfg->state_size, cfg->action_size);
+    ASAC_REQUIRE(bat && bat->eps_y && bat->eps_pi && bat->actions, "asac_sac_step: missing batch tensors");
+    ASAC_REQUIRE(bat->states == rep->states && bat->states_post == rep->states_post &&
+                     bat->target_states == rep->target_states && wrk->grad_state,
+                 "asac_sac_step_networks_rep: batch / work do not point at the representation's buffers");
+    ASAC_REQUIRE(rep->params && rep->params_target && rep->m && rep->v && rep->obs && rep->hn && rep->hn_post &&
+                     rep->save && rep->grad_part && rep->grad, "asac_sac_step_networks_rep: null pointer in rep");
+    const int tile = asac_gru_backward_tile(&rep->shape, cfg->burn_in);
+    if (tile < 1) return tile;
+    ASAC_REQUIRE(rep->rep_tiles == (cfg->batch + tile - 1) / tile, "rep.rep_tiles %d != ceil(B / %d)", rep->rep_tiles, tile);
+    const int64_t P = asac_gru_param_count(&rep->shape), Ps = (P + 3) / 4 * 4;
+    const int B = cfg->batch, L = cfg->seq_len;
+    if (with_polyak) {
+        if ((rc = asac_sac_polyak(cfg, prm, -1.f, stream)) != ASAC_OK) return rc;
+        if ((rc = asac_flat_polyak(rep->params_target, rep->params, P, prm->counters, cfg->update_target_per_step,
+                                   cfg->tau, cfg->one_minus_tau, 0, stream)) != ASAC_OK) return rc;
+    }
+    // get_l_states x 2 (sac_base.py:2066-2078): online (gates kept for the backward pass) and target
+    AsacGruNet nets[2] = {{rep->params, rep->states, rep->hn, rep->save},
+                          {rep->params_target, rep->target_states, nullptr, nullptr}};
+    if ((rc = asac_gru_forward(&rep->shape, nets, 2, rep->obs, bat->actions, cfg->bn_stride, nullptr, rep->h0,
+                               rep->h0_b_stride, B, L, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_value_pass(a, 0, stream)) != ASAC_OK) return rc;
+    if ((rc = asac_sac_q_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_reduce_adam(cfg, prm, wrk, 0, 1, 1, 1.f, stream, 0, nullptr)) != ASAC_OK) return rc;
+    // the representation's share of loss.backward() and optimizer_rep.step() (sac_base.py:1573-1601)
+    if ((rc = asac_gru_backward(&rep->shape, rep->params, rep->obs, bat->actions, cfg->bn_stride, nullptr, rep->h0,
+                                rep->h0_b_stride, B, L, cfg->burn_in, wrk->grad_state, cfg->ensemble, rep->hn,
+                                rep->save, rep->grad_part, stream)) != ASAC_OK) return rc;
+    if ((rc = asac_flat_reduce_adam(rep->params, rep->m, rep->v, rep->grad_part, rep->rep_tiles, Ps, P, rep->grad,
+                                    prm->counters + 4, cfg->learning_rate, stream)) != ASAC_OK) return rc;
+    // get_l_states again with the new weights (sac_base.py:2099-2105)
+    AsacGruNet again = {rep->params, rep->states_post, rep->hn_post, nullptr};
+    if ((rc = asac_gru_forward(&rep->shape, &again, 1, rep->obs, bat->actions, cfg->bn_stride, nullptr, rep->h0,
+                               rep->h0_b_stride, B, L, stream)) != ASAC_OK) return rc;
+    if ((rc = asac_sac_policy_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, 1.f, stream, 0, nullptr)) != ASAC_OK) return rc;
+    const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
+    if (need_post) {
+        ASAC_REQUIRE(bat->eps_td && bat->eps_alpha, "asac_sac_step: missing eps_td / eps_alpha");
+        if ((rc = launch_value_pass(a, 1, stream)) != ASAC_OK) return rc;
+    }
+    return ASAC_OK;
+}
+
+extern "C" int asac_sac_staged_tail(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk,
+                                    void *stream) {
+    int rc;
+    int mask = 1 | 2 | 4 | (cfg->rep_kind != 0 ? 16 : 0);
+    const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
+    if (cfg->use_auto_alpha || need_post) {
+        const int aa = cfg->use_auto_alpha ? 1 : 0;
+        if ((rc = launch_reduce_adam(cfg, prm, wrk, 2, aa, aa, 1.f, stream, need_post ? 1 : 0)) != ASAC_OK) return rc;
+        if (aa) mask |= 8;
+    }
+    return bump(prm, mask, stream);
+}
+
 extern "C" int asac_sac_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
                              const AsacSacWork *wrk, void *stream) {
     int rc = asac_sac_step_networks(cfg, prm, bat, wrk, 1, nullptr, stream);
@@ -1575,7 +1698,7 @@ extern "C" int asac_sac_finish_step(const AsacSacConfig *cfg, const AsacSacParam
     a.prm = *prm; a.wrk = *wrk;
     a.n_tiles = wrk->n_tiles; a.batch = cfg->batch; a.ensemble = cfg->ensemble;
     a.use_auto_alpha = cfg->use_auto_alpha ? 1 : 0;
-    a.counter_mask = 1 | 2 | 4 | (cfg->use_auto_alpha ? 8 : 0);
+    a.counter_mask = 1 | 2 | 4 | (cfg->use_auto_alpha ? 8 : 0) | (cfg->rep_kind != 0 ? 16 : 0);
     a.lr = cfg->learning_rate;
     a.nodes = nodes; a.capacity = capacity; a.levels = tree_levels(capacity);
     a.store_ids = store_ids; a.data_ids = data_ids;

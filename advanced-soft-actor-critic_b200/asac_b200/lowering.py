@@ -183,3 +183,87 @@ def state_dict_from_flat(shape: NetShape, flat: torch.Tensor, policy: bool) -> d
         out[f'c_dense.dense.{2 * shape.depth}.weight'] = take(H, 1, H)
         out[f'c_dense.dense.{2 * shape.depth}.bias'] = take(1, 1)
     return out
+
+
+# --------------------------------------------------------------------------------------- representation
+@dataclass(frozen=True)
+class GruShape:
+    """Stock multi-layer GRU over cat[obs, pre_action] (include/asac_b200.h, AsacGruShape)."""
+    obs_size: int
+    action_size: int
+    hidden: int
+    layers: int
+
+    def in_dim(self, layer: int) -> int:
+        return self.obs_size + self.action_size if layer == 0 else self.hidden
+
+    @property
+    def count(self) -> int:
+        return sum(3 * self.hidden * (self.in_dim(l) + self.hidden + 2) for l in range(self.layers))
+
+    @property
+    def stride(self) -> int:
+        return (self.count + 3) // 4 * 4
+
+
+_GRU_TENSORS = ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0')
+
+
+def gru_flat_from_state_dict(shape: GruShape, state: dict, prefix: str = 'rnn.') -> torch.Tensor:
+    """Flat fp32 vector of a stock ``GRU`` wrapper from its ``state_dict`` (keys
+    ``<prefix>_grus.<layer>.{weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0}``,
+    seq_layers.py:27-39).  CPU helper for tests / import."""
+    parts = [torch.as_tensor(state[f'{prefix}_grus.{l}.{name}'], dtype=torch.float32).reshape(-1)
+             for l in range(shape.layers) for name in _GRU_TENSORS]
+    flat = torch.cat(parts)
+    if flat.numel() != shape.count:
+        raise ValueError(f'state_dict holds {flat.numel()} values, the shape needs {shape.count}')
+    out = torch.zeros(shape.stride, dtype=torch.float32)
+    out[:shape.count] = flat
+    return out
+
+
+def gru_state_dict_from_flat(shape: GruShape, flat: torch.Tensor, prefix: str = 'rnn.') -> dict[str, torch.Tensor]:
+    out, off, H = {}, 0, shape.hidden
+    for l in range(shape.layers):
+        k = shape.in_dim(l)
+        for name, view in (('weight_ih_l0', (3 * H, k)), ('weight_hh_l0', (3 * H, H)), ('bias_ih_l0', (3 * H,)),
+                           ('bias_hh_l0', (3 * H,))):
+            n = 1
+            for d in view:
+                n *= d
+            out[f'{prefix}_grus.{l}.{name}'] = flat[off:off + n].view(*view)
+            off += n
+    return out
+
+
+def analyze_rep(rep: nn.Module, obs_shapes: list[tuple], action_size: int) -> tuple[GruShape, list[nn.Parameter]] | None:
+    """-> None for a parameter-free ``ModelSimpleRep``; (shape, parameters in flat order) for a
+    representation that is ONE stock ``GRU`` wrapper applied to ``cat[obs_list[0], pre_action]``
+    with ``pre_seq_hidden_state[:, 0]`` as initial state (envs/test/nn_rnn.py:6-21).  The structure
+    is checked here; that ``forward`` really computes that function is checked by the learner with a
+    probe against the kernels (``SAC_Base._probe_rep``).  Raises NotStockNetwork otherwise."""
+    n_params = sum(p.numel() for p in rep.parameters())
+    if n_params == 0:
+        if type(rep).forward is not m.ModelSimpleRep.forward:
+            raise NotStockNetwork('parameter-free representation that is not ModelSimpleRep')
+        return None
+    grus = [mod for mod in rep.modules() if isinstance(mod, m.GRU)]
+    if len(grus) != 1:
+        raise NotStockNetwork('representation is not a single stock GRU (encoder representations beyond the '
+                              'GRU-over-vector-observation form are outside the fused path)')
+    gru = grus[0]
+    cells = list(gru._grus)
+    H = cells[0].hidden_size
+    if len(obs_shapes) < 1 or len(obs_shapes[0]) != 1:
+        raise NotStockNetwork('GRU representation needs a vector observation first')
+    shape = GruShape(obs_shapes[0][0], action_size, H, len(cells))
+    params = []
+    for l, cell in enumerate(cells):
+        if (cell.hidden_size != H or cell.input_size != shape.in_dim(l) or cell.num_layers != 1 or not cell.bias
+                or cell.bidirectional or not cell.batch_first or cell.dropout != 0):
+            raise NotStockNetwork(f'GRU layer {l} is not a plain single-layer batch-first GRU of width {H}')
+        params += [cell.weight_ih_l0, cell.weight_hh_l0, cell.bias_ih_l0, cell.bias_hh_l0]
+    if n_params != shape.count:
+        raise NotStockNetwork('representation has parameters outside its GRU')
+    return shape, params

@@ -392,14 +392,16 @@ class PrioritizedReplayBuffer:
                                                  None, 0, self._stream), 'storage_scatter')
 
     def write_back(self, data_ids: torch.Tensor, key: str, rows: torch.Tensor, first_offset: int,
-                   padding_mask: torch.Tensor) -> None:
+                   padding_mask: torch.Tensor, n_rows: int | None = None) -> None:
         """The learner's per-window write-backs (sac_base.py:2586-2605) in one launch:
-        ring[data_id + first_offset + t] = rows[b, t] unless padded / overwritten."""
+        ring[data_id + first_offset + t] = rows[b, t] for t < n_rows (default: all of rows.shape[1])
+        unless padded / overwritten."""
         col = self._columns[key]
-        n_rows = rows.shape[1]
+        b_stride = rows.shape[1]
+        n_rows = b_stride if n_rows is None else n_rows
         check(self._lib.asac_storage_scatter(ptr(col), self.capacity, ptr(self._store_ids), ptr(data_ids),
                                              int(data_ids.numel()), int(first_offset), int(n_rows), ptr(rows),
-                                             self._row_bytes(key), int(n_rows), ptr(padding_mask),
+                                             self._row_bytes(key), int(b_stride), ptr(padding_mask),
                                              int(padding_mask.stride(0)), self._stream), 'storage_scatter')
 
     def check_nan(self) -> None:

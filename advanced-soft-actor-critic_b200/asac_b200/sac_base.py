@@ -8,9 +8,11 @@ Polyak, ``_get_y``, critic / policy / alpha losses with hand-derived backward pa
 ``get_l_probs``, ``_get_td_error``, the priority update and the mu-prob write-back are kernels of
 ``libasac_b200.so`` enqueued on one stream and (by default) replayed as a single CUDA graph.
 
-Scope: continuous actions, vector observations through ``ModelSimpleRep`` and
-stock ``ModelQ`` / ``ModelPolicy`` topologies.  Anything else raises ``NotImplementedError`` at
-construction — there is no silent torch or CPU fallback for the update path.
+Scope: continuous actions, stock ``ModelQ`` / ``ModelPolicy`` topologies, and a
+representation that is either ``ModelSimpleRep`` (vector observations) or ONE stock ``GRU`` over
+``cat[obs, pre_action]`` (``seq_encoder=SEQ_ENCODER.RNN``, envs/test/nn_rnn.py) trained through the
+critic loss by ``csrc/rep_gru.cu``.  Anything else raises ``NotImplementedError`` at construction —
+there is no silent torch or CPU fallback for the update path.
 """
 from __future__ import annotations
 
@@ -190,7 +192,7 @@ class SAC_Base:
         unsupported = {
             'discrete action branches (d_action_sizes)': bool(d_action_sizes),
             'c_action_size == 0': not c_action_size,
-            'seq_encoder': seq_encoder is not None,
+            'seq_encoder=ATTN': seq_encoder is not None and getattr(seq_encoder, 'name', str(seq_encoder)) != 'RNN',
             'siamese': siamese is not None,
             'use_prediction': use_prediction,
             'curiosity': curiosity is not None,
@@ -263,16 +265,42 @@ class SAC_Base:
                                      self.model_abs_dir, **nn_config['rep']).to(dev)
         self.model_target_rep = nn.ModelRep(self.obs_names, self.obs_shapes, self.d_action_sizes, A, True,
                                             self.model_abs_dir, **nn_config['rep']).to(dev)
-        if type(self.model_rep).forward is not m.ModelSimpleRep.forward or \
-                sum(p.numel() for p in self.model_rep.parameters()) != 0:
-            raise NotImplementedError('only ModelSimpleRep (vector observations) is on the B200 hot path; '
-                                      'encoder representations are the next scope row (SURVEY.md §8f)')
+        for p in self.model_target_rep.parameters():
+            p.requires_grad = False
+        f32 = dict(dtype=torch.float32, device=dev)
+        # counters: global_step, Adam steps of critics / policy / alpha / representation
+        self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        lowered = lowering.analyze_rep(self.model_rep, self.obs_shapes, A)
         self.optimizer_rep = None
+        self._gru = None
         self._vector_obs = [(name, shape) for name, shape in zip(self.obs_names, self.obs_shapes) if len(shape) == 1]
-        self.state_size = sum(shape[0] for _, shape in self._vector_obs)
-        if self.state_size == 0:
-            raise NotImplementedError('ModelSimpleRep needs at least one vector observation')
-        self.seq_hidden_state_shape = (0,)
+        if lowered is None:
+            if self.seq_encoder is not None:
+                raise NotImplementedError('seq_encoder is set but ModelRep is ModelSimpleRep')
+            self.state_size = sum(shape[0] for _, shape in self._vector_obs)
+            if self.state_size == 0:
+                raise NotImplementedError('ModelSimpleRep needs at least one vector observation')
+            self.seq_hidden_state_shape = (0,)
+        else:
+            if self.seq_encoder is None:
+                raise NotImplementedError('a recurrent ModelRep needs seq_encoder=SEQ_ENCODER.RNN')
+            if self._world > 1:
+                raise NotImplementedError('data-parallel learner with a trained representation')
+            self._gru, rep_params = lowered
+            target = lowering.analyze_rep(self.model_target_rep, self.obs_shapes, A)
+            if target is None or target[0] != self._gru:
+                raise lowering.NotStockNetwork('target representation differs from the online one')
+            P = self._gru.stride
+            self._rep_flat, self._rept_flat = torch.zeros(P, **f32), torch.zeros(P, **f32)
+            self._rep_m, self._rep_v = torch.zeros(P, **f32), torch.zeros(P, **f32)
+            lowering.bind_parameters(rep_params, self._rep_flat)
+            lowering.bind_parameters(target[1], self._rept_flat)
+            self.state_size = self._gru.hidden
+            self.seq_hidden_state_shape = (self._gru.layers, self._gru.hidden)
+            self._gru_c = _lib.AsacGruShape(self._gru.obs_size, A, self._gru.hidden, self._gru.layers)
+            self._probe_rep()
+            self.optimizer_rep = _FlatAdam(rep_params, self._rep_flat, self._rep_m, self._rep_v, self._counters, 4,
+                                           self.learning_rate)
 
         E = self.ensemble_q_num
         self.model_q_list = [nn.ModelQ(self.state_size, self.d_action_sizes, A, False, self.model_abs_dir).to(dev)
@@ -292,7 +320,6 @@ class SAC_Base:
             raise lowering.NotStockNetwork('ensemble members differ in shape')
         self._pi_shape, pi_params = lowering.analyze_policy(self.model_policy)
         Pq, Ppi = self._q_shape.stride, self._pi_shape.stride
-        f32 = dict(dtype=torch.float32, device=dev)
         self._q_flat = torch.zeros(E, Pq, **f32)
         self._qt_flat = torch.zeros(E, Pq, **f32)
         self._pi_flat = torch.zeros(Ppi, **f32)
@@ -307,8 +334,6 @@ class SAC_Base:
         self.log_c_alpha = torch.full((1,), init_log_alpha, **f32)[0]  # 0-dim view of a 1-element buffer
         self._log_alpha_buf = self.log_c_alpha.view(1)
         self._alpha_m, self._alpha_v = torch.zeros(1, **f32), torch.zeros(1, **f32)
-        # counters: global_step, adam steps of critics / policy / alpha
-        self._counters = torch.zeros(4, dtype=torch.int64, device=dev)
         self.global_step = torch.tensor(0, dtype=torch.int64)
         self._host_step = 0
 
@@ -333,6 +358,7 @@ class SAC_Base:
         cfg.use_auto_alpha = int(self.use_auto_alpha)
         cfg.update_target_per_step = int(self.update_target_per_step)
         cfg.bn_stride = cfg.seq_len
+        cfg.rep_kind = 0 if self._gru is None else 1
         cfg.tau, cfg.one_minus_tau = float(self.tau), float(np.float32(1. - self.tau))
         cfg.gamma, cfg.v_rho, cfg.v_c = float(self.gamma), float(self.v_rho), float(self.v_c)
         cfg.clip_epsilon, cfg.target_c_alpha = float(self.clip_epsilon), float(self.target_c_alpha)
@@ -358,6 +384,10 @@ class SAC_Base:
     def _build_ckpt(self) -> None:
         """Same key names as sac_base.py:493-566 so .pth files interchange."""
         ck = {'global_step': self.global_step}
+        if self.optimizer_rep is not None:  # sac_base.py:506-509
+            ck['model_rep'] = self.model_rep
+            ck['model_target_rep'] = self.model_target_rep
+            ck['optimizer_rep'] = self.optimizer_rep
         for i in range(self.ensemble_q_num):
             ck[f'model_q_{i}'] = self.model_q_list[i]
             ck[f'model_target_q_{i}'] = self.model_target_q_list[i]
@@ -412,6 +442,8 @@ class SAC_Base:
             'pi_probs': torch.zeros(B, L - 1, A, **f32), 'post_parts': torch.zeros(B, 2 + E, **f32), 'y_td': torch.zeros(B, **f32),
             'td_error': torch.zeros(B, **f32),
         }
+        if self._gru is not None:
+            wk['grad_state'] = torch.zeros(E, B, S, **f32)
         work = _lib.AsacSacWork()
         work.n_tiles = T
         for k, t in wk.items():
@@ -427,6 +459,32 @@ class SAC_Base:
         batch.priority_is = ptr(self._smp['w']) if self.use_priority else None
         batch.eps_y, batch.eps_pi, batch.eps_alpha, batch.eps_td = [ptr(e) for e in self._eps]
         self._batch = batch
+        self._rep = None
+        if self._gru is not None:
+            g = self._gru
+            NL, H = g.layers, g.hidden
+            bt['obs'] = torch.zeros(B, L, g.obs_size, **f32)
+            bt['hidden'] = torch.zeros(B, L, NL * H, **f32)
+            bt['states_post'], bt['target_states'] = torch.zeros(B, L, S, **f32), torch.zeros(B, L, S, **f32)
+            rtile = self._lib.asac_gru_backward_tile(C.byref(self._gru_c), self.burn_in_step)
+            if rtile < 1:
+                check(rtile, 'asac_gru_backward_tile')
+            rt = (B + rtile - 1) // rtile
+            rw = self._rw = {'hn': torch.zeros(B, L, NL, H, **f32), 'hn_post': torch.zeros(B, L, NL * H, **f32),
+                             'save': torch.zeros(B, L, NL, 4 * H, **f32), 'grad_part': torch.zeros(rt, g.stride, **f32),
+                             'grad': torch.zeros(g.stride, **f32)}
+            rep = _lib.AsacGruRep()
+            rep.shape = self._gru_c
+            rep.params, rep.params_target = ptr(self._rep_flat), ptr(self._rept_flat)
+            rep.m, rep.v = ptr(self._rep_m), ptr(self._rep_v)
+            rep.obs, rep.h0, rep.h0_b_stride = ptr(bt['obs']), ptr(bt['hidden']), L * NL * H
+            rep.states, rep.states_post, rep.target_states = ptr(bt['states']), ptr(bt['states_post']), \
+                ptr(bt['target_states'])
+            for k, t in rw.items():
+                setattr(rep, k, ptr(t))
+            rep.rep_tiles = rt
+            self._rep = rep
+            batch.states_post, batch.target_states = ptr(bt['states_post']), ptr(bt['target_states'])
         self._noise_seed = (int(self._seed) if self._seed is not None else random.getrandbits(62)) ^ 0x5AC5AC
         self._side_stream = torch.cuda.Stream(device=dev)
         self._act_counter = torch.zeros(1, dtype=torch.int64, device=dev)  # Philox counter of choose_action
@@ -490,6 +548,10 @@ class SAC_Base:
         with torch.cuda.device(self.device):
             check(self._lib.asac_sac_polyak(C.byref(self._cfg), C.byref(self._prm), float(tau),
                                             _lib.current_stream()), 'sac_polyak')
+            if self._gru is not None:
+                check(self._lib.asac_flat_polyak(ptr(self._rept_flat), ptr(self._rep_flat), self._gru.count, None, 1,
+                                                 float(tau), float(np.float32(1. - tau)), 1, _lib.current_stream()),
+                      'flat_polyak')
 
     def set_train_mode(self, train_mode=True):
         self.train_mode = train_mode
@@ -635,7 +697,15 @@ class SAC_Base:
                  ('done', bt['dones'], 1, 0, _lib.ROLE_DONE),
                  ('mu_prob', bt['mu_probs'], 4 * A, 0, _lib.ROLE_MU_PROB)]
         off = 0
-        for name, shape in self._vector_obs:
+        if self._gru is not None:  # the representation reads obs_list[0] and the stored hidden state of the first row
+            name, g = self.obs_names[0], self._gru
+            if rb._columns[f'obs_{name}'].dtype != torch.float32:
+                raise NotImplementedError(f'vector observation {name} is not stored as float32')
+            specs.append((f'obs_{name}', bt['obs'], 4 * g.obs_size, 0, _lib.ROLE_COPY))
+            specs.append(('pre_seq_hidden_state', bt['hidden'], 4 * g.layers * g.hidden, 0, _lib.ROLE_HIDDEN))
+            if rb._row_bytes('pre_seq_hidden_state') != 4 * g.layers * g.hidden:
+                raise ValueError('stored pre_seq_hidden_state rows do not have the shape (layers, hidden)')
+        for name, shape in ([] if self._gru is not None else self._vector_obs):
             col = rb._columns[f'obs_{name}']
             if col.dtype != torch.float32:
                 raise NotImplementedError(f'vector observation {name} is stored as {col.dtype}; float32 expected')
@@ -663,8 +733,12 @@ class SAC_Base:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             s2 = side.cuda_stream
-            if fast_tail:
+            if fast_tail or self._rep is not None:
                 check(lib.asac_sac_polyak(C.byref(cfg), C.byref(prm), -1.0, s2), 'sac_polyak')
+            if self._rep is not None:
+                check(lib.asac_flat_polyak(ptr(self._rept_flat), ptr(self._rep_flat), self._gru.count,
+                                           ptr(self._counters), int(self.update_target_per_step), cfg.tau,
+                                           cfg.one_minus_tau, 0, s2), 'flat_polyak')
             check(lib.asac_fill_normal(ptr(self._noise), self._noise.numel(), self._noise_seed, ptr(self._counters),
                                        0, s2), 'fill_normal')
         stream = main.cuda_stream
@@ -676,7 +750,12 @@ class SAC_Base:
         rb._gather(smp['ids'], self._specs, self._padding_action, self._bt['padding_masks'])
         main.wait_stream(side)
         # 3. _train + get_l_probs + _get_td_error
-        if not fused:
+        if self._rep is not None:  # trained GRU representation (sac_base.py:2066-2116)
+            check(lib.asac_sac_step_networks_rep(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work),
+                                                 C.byref(self._rep), 0, stream), 'sac_step_networks_rep')
+            if not fast_tail:
+                check(lib.asac_sac_staged_tail(C.byref(cfg), C.byref(prm), C.byref(work), stream), 'sac_staged_tail')
+        elif not fused:
             self._enqueue_sac_step_data_parallel(stream)
         elif fast_tail:
             check(lib.asac_sac_step_networks(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), 0, peers,
@@ -686,11 +765,15 @@ class SAC_Base:
         else:
             check(lib.asac_sac_step(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), stream), 'sac_step')
         # 4. mu-prob write-back (sac_base.py:2598-2605): needs the post pass only -> side branch
-        if self.use_n_step_is:
+        if self.use_n_step_is or self._rep is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                rb.write_back(smp['ids'], 'mu_prob', self._wk['pi_probs'], -self.burn_in_step,
-                              self._bt['padding_masks'])
+                if self._rep is not None:  # next hidden states -> pre_seq_hidden_state of the following rows (:2589-2596)
+                    rb.write_back(smp['ids'], 'pre_seq_hidden_state', self._rw['hn_post'], 1 - self.burn_in_step,
+                                  self._bt['padding_masks'], n_rows=cfg.seq_len - 1)
+                if self.use_n_step_is:
+                    rb.write_back(smp['ids'], 'mu_prob', self._wk['pi_probs'], -self.burn_in_step,
+                                  self._bt['padding_masks'])
         # 5. alpha step, td error, priority update (sac_base.py:2115-2116, 2571-2584), step counters
         if self.use_priority:
             if fast_tail:
@@ -702,7 +785,7 @@ class SAC_Base:
                                           ptr(self._wk['td_error']), B, float(rb.td_error_min),
                                           float(rb.td_error_max), float(rb.alpha), 0, ptr(rb._per_state), stream),
                       'per_update')
-        if self.use_n_step_is:
+        if self.use_n_step_is or self._rep is not None:
             main.wait_stream(side)
 
     def _enqueue_sac_step_data_parallel(self, stream) -> None:

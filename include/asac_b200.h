@@ -216,6 +216,9 @@ typedef struct {
     float td_error_min, td_error_max, per_alpha;
     float gamma_ratio[ASAC_MAX_NSTEP];   /* torch.logspace(0, n-1, n, gamma)    (sac_base.py:285) */
     float lambda_ratio[ASAC_MAX_NSTEP];  /* torch.logspace(0, n-1, n, v_lambda) (sac_base.py:286) */
+    int32_t rep_kind;       /* 0: ModelSimpleRep (state = concat obs); 1: trained GRU representation,
+                               the states of the online / re-encoded / target representation differ  */
+    int32_t reserved_;
 } AsacSacConfig;
 
 typedef struct {
@@ -228,7 +231,7 @@ typedef struct {
     float *q_m, *q_v;    /* [E, Pq]  */
     float *pi_m, *pi_v;  /* [Ppi]    */
     float *alpha_m, *alpha_v; /* [1] */
-    /* counters: int64[4] = {global_step, adam_step_q, adam_step_pi, adam_step_alpha} */
+    /* counters: int64[8] = {global_step, adam_step_q, adam_step_pi, adam_step_alpha, adam_step_rep, -, -, -} */
     int64_t *counters;
 } AsacSacParams;
 
@@ -246,6 +249,11 @@ typedef struct {
     const float *eps_pi;          /* [B, A]      */
     const float *eps_alpha;       /* [B, A]      */
     const float *eps_td;          /* [B, n+1, A] */
+    /* trained representation (cfg.rep_kind != 0; NULL otherwise).  `states` is then the online
+     * representation BEFORE its Adam step (seen by _train_rep_q, sac_base.py:2066-2097), */
+    const float *states_post;     /* [B, L, S]  online representation re-evaluated after it (:2099-2105):
+                                     policy / alpha losses, get_l_probs, Q_i(s_b, a_b) of _get_td_error   */
+    const float *target_states;   /* [B, L, S]  target representation (:2073-2078): _get_y inside _get_td_error */
 } AsacSacBatch;
 
 typedef struct {
@@ -265,6 +273,7 @@ typedef struct {
     float *post_parts;    /* [B, 2+E]  post pass: y' critic part, y' log-prob part, Q_i(s_b,a_b) */
     float *y_td;          /* [B]       _get_y inside _get_td_error                      */
     float *td_error;      /* [B]                                                        */
+    float *grad_state;    /* [E, B, S] d(sum_i mean_B loss_i) / d state[:, b] through critic i, or NULL  */
 } AsacSacWork;
 
 /* batch elements handled by one CTA of the row-tiled kernels for this configuration
@@ -362,6 +371,97 @@ int asac_sac_finish_step(const AsacSacConfig *cfg, const AsacSacParams *prm, con
                          float *nodes, int64_t capacity, const int64_t *store_ids,
                          const int64_t *data_ids, double *per_state, const AsacPeerTable *peers,
                          void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Recurrent representation — replaces the stock multi-layer GRU wrapper
+ * (algorithm/nn_models/layers/seq_layers.py:14-114, no padding mask) inside a plugin ModelRep of the
+ * form of envs/test/nn_rnn.py:6-21: state, hn = GRU(cat[obs, pre_action], h0), called by
+ * get_l_states (sac_base.py:1118-1146) three times per _train (:2066-2105), trained by the critic
+ * loss through every burn-in step (:1573-1601) and by choose_action on the actor side (:1003).
+ *
+ * Flat parameter layout, layer after layer, torch.nn.GRU's own order and gate order (r, z, n):
+ *     weight_ih[3H, in_l]  weight_hh[3H, H]  bias_ih[3H]  bias_hh[3H]      in_0 = obs + action, in_l = H
+ * Cell, as ATen evaluates it: r = sigmoid(Wir x + bir + Whr h + bhr), z likewise,
+ * n = tanh(Win x + bin + r * (Whn h + bhn)), h' = (h - n) * z + n.
+ * ---------------------------------------------------------------------------------- */
+#define ASAC_GRU_MAX_LAYERS 4
+typedef struct {
+    int32_t obs_size;    /* floats of the (vector) observation per step        */
+    int32_t action_size; /* floats of pre_action appended to it                */
+    int32_t hidden;      /* H (<= 64); the state is the top layer's output     */
+    int32_t layers;      /* <= ASAC_GRU_MAX_LAYERS; hidden state shape (layers, H) */
+} AsacGruShape;
+
+int64_t asac_gru_param_count(const AsacGruShape *shape);
+/* sequences one CTA of asac_gru_backward handles (grad_part has ceil(batch / this) rows) */
+int asac_gru_backward_tile(const AsacGruShape *shape, int t_grad);
+
+/* GRU.forward over [batch, seq_len]: x_t = [obs[b, t], pre_action], pre_action = pre_actions[b, t] when
+ * given, else actions[b, t-1] (zeros at t = 0): gen_n_pre_actions(keep_last_action=True),
+ * utils/operators.py:39-59.  h0: [batch] rows of [layers, H], h0_b_stride floats apart (NULL = zeros).
+ * Outputs: states [batch, seq_len, H]; hn [batch, seq_len, layers, H] (may be NULL);
+ * save [batch, seq_len, layers, 4H] = (r, z, n, Whn h + bhn) for asac_gru_backward (may be NULL).
+ * n_nets (1 or 2) parameter sets run in one launch on the same inputs (online + target). */
+typedef struct {
+    const float *params;
+    float *states, *hn, *save;
+} AsacGruNet;
+int asac_gru_forward(const AsacGruShape *shape, const AsacGruNet *nets_host, int n_nets, const float *obs,
+                     const float *actions, int bn_stride, const float *pre_actions, const float *h0,
+                     int64_t h0_b_stride, int batch, int seq_len, void *stream);
+
+/* Back-propagation through time of sum_e grad_state[e, b, :] applied to the top layer's output at
+ * step t_grad (= burn_in: the only state the critic loss reads, sac_base.py:1510) back to step 0,
+ * through every layer.  hn / save come from asac_gru_forward with the same parameters and inputs.
+ * grad_part[tile, P]: per-CTA partial sums (tile = asac_gru_backward_tile sequences), summed in
+ * tile order by asac_flat_reduce_adam. */
+int asac_gru_backward(const AsacGruShape *shape, const float *params, const float *obs, const float *actions,
+                      int bn_stride, const float *pre_actions, const float *h0, int64_t h0_b_stride, int batch,
+                      int seq_len, int t_grad, const float *grad_state, int ensemble, const float *hn,
+                      const float *save, float *grad_part, void *stream);
+
+/* Deterministic sum of n_tiles partial gradients (tile_stride floats apart) -> grad[count], then
+ * torch.optim.Adam.step on param with moments m, v (the kernel of asac_sac_reduce_adam on a caller-
+ * supplied flat buffer).  step_counter[0] = steps taken so far; NOT advanced by this call. */
+int asac_flat_reduce_adam(float *param, float *m, float *v, const float *grad_part, int n_tiles,
+                          int64_t tile_stride, int64_t count, float *grad, const int64_t *step_counter,
+                          double learning_rate, void *stream);
+/* target = target * one_minus_tau + source * tau when counters[0] % per_step == 0 or force != 0
+ * (_update_target_variables, sac_base.py:745-764, for the representation's parameters) */
+int asac_flat_polyak(float *target, const float *source, int64_t count, const int64_t *counters, int per_step,
+                     float tau, float one_minus_tau, int force, void *stream);
+
+/* Everything the learner holds for a GRU representation (device pointers owned by the caller). */
+typedef struct {
+    AsacGruShape shape;
+    float *params, *params_target, *m, *v;  /* [P] each                                             */
+    const float *obs;          /* [B, L, obs_size]   gathered observation windows                   */
+    const float *h0;           /* first row of the gathered pre_seq_hidden_state windows            */
+    int64_t h0_b_stride;       /* floats between batch elements of h0 (L * layers * H)              */
+    float *states;             /* [B, L, H]  out: online representation before its step             */
+    float *states_post;        /* [B, L, H]  out: online representation after its step              */
+    float *target_states;      /* [B, L, H]  out: target representation                             */
+    float *hn;                 /* [B, L, layers, H]  scratch: hidden states of the first pass       */
+    float *hn_post;            /* [B, L, layers, H]  out: next_bnx_seq_hidden_states (:2099-2105)   */
+    float *save;               /* [B, L, layers, 4H] scratch: gates of the first pass               */
+    float *grad_part;          /* [rep_tiles, P]                                                    */
+    float *grad;               /* [P]  reduced gradient                                             */
+    int32_t rep_tiles;         /* ceil(B / asac_gru_backward_tile)                                  */
+    int32_t reserved_;
+} AsacGruRep;
+
+/* asac_sac_step_networks for a run with a trained GRU representation (sac_base.py:2057-2116):
+ * [polyak of critics and representation,] online + target representation, _get_y, critic loss and
+ * backward (+ d loss / d state), critic Adam, representation BPTT + Adam, representation again,
+ * policy loss / Adam, post pass on (states_post, target_states).  batch->states / states_post /
+ * target_states and work->grad_state must be the buffers named in `rep`.  Single GPU.  Follow with
+ * asac_sac_finish_step (advances counters[4] too when cfg->rep_kind != 0) or asac_sac_staged_tail. */
+int asac_sac_step_networks_rep(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
+                               const AsacSacWork *work, const AsacGruRep *rep, int with_polyak, void *stream);
+
+/* asac_sac_step's tail on its own: alpha reduce + Adam, td error, all step counters
+ * (the non-prioritized / batch > 1024 counterpart of asac_sac_finish_step). */
+int asac_sac_staged_tail(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *work, void *stream);
 
 /* N(0,1) draws for eps_* (Philox4x32-10 + Box-Muller), keyed by (seed, counter[0], stream_id) */
 int asac_fill_normal(float *out, int64_t n, uint64_t seed, const int64_t *counter, int stream_id,

@@ -15,7 +15,7 @@ class SacCuda:
     """Holds the flat parameters / Adam state / work buffers for one SacHyper and exposes the
     staged entry points of include/asac_b200.h."""
 
-    def __init__(self, hp, batch_size: int, device='cuda:0'):
+    def __init__(self, hp, batch_size: int, device='cuda:0', rep_kind: int = 0):
         self.lib = _lib.load()
         self.hp, self.B = hp, batch_size
         self.dev = torch.device(device)
@@ -40,6 +40,7 @@ class SacCuda:
         cfg.gamma, cfg.v_rho, cfg.v_c = float(hp.gamma), float(hp.v_rho), float(hp.v_c)
         cfg.clip_epsilon, cfg.target_c_alpha = float(hp.clip_epsilon), float(hp.target_c_alpha)
         cfg.td_error_min, cfg.td_error_max, cfg.per_alpha = 0.01, 1.0, 0.9
+        cfg.rep_kind = rep_kind
         gr = torch.logspace(0, n - 1, n, hp.gamma)
         lr = torch.logspace(0, n - 1, n, hp.v_lambda)
         for k in range(n):
@@ -59,7 +60,7 @@ class SacCuda:
         self.q_m, self.q_v = torch.zeros_like(self.q), torch.zeros_like(self.q)
         self.pi_m, self.pi_v = torch.zeros_like(self.pi), torch.zeros_like(self.pi)
         self.alpha_m, self.alpha_v = torch.zeros(1, **f32), torch.zeros(1, **f32)
-        self.counters = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        self.counters = torch.zeros(8, dtype=torch.int64, device=self.dev)
         prm = _lib.AsacSacParams()
         prm.q, prm.q_target, prm.pi, prm.log_alpha = ptr(self.q), ptr(self.qt), ptr(self.pi), ptr(self.log_alpha)
         prm.q_m, prm.q_v, prm.pi_m, prm.pi_v = ptr(self.q_m), ptr(self.q_v), ptr(self.pi_m), ptr(self.pi_v)
@@ -260,3 +261,129 @@ class SacCuda:
             out['y_td'] = self.wk['y_td'].cpu().numpy()
         self.advance()
         return out
+
+
+# ------------------------------------------------------------------------------------------ GRU representation
+def gru_forward(shape: lowering.GruShape, params_list, obs, actions=None, pre_actions=None, h0=None,
+                save=False, want_hn=True):
+    """asac_gru_forward on explicit CUDA tensors -> list of dicts (states, hn, save) per parameter set."""
+    lib = _lib.load()
+    B, L = obs.shape[:2]
+    H, NL = shape.hidden, shape.layers
+    f32 = dict(dtype=torch.float32, device=obs.device)
+    cs = _lib.AsacGruShape(shape.obs_size, shape.action_size, H, NL)
+    nets = (_lib.AsacGruNet * len(params_list))()
+    outs = []
+    for i, prm in enumerate(params_list):
+        o = {'states': torch.zeros(B, L, H, **f32), 'hn': torch.zeros(B, L, NL, H, **f32) if want_hn else None,
+             'save': torch.zeros(B, L, NL, 4 * H, **f32) if save else None}
+        nets[i].params, nets[i].states, nets[i].hn, nets[i].save = ptr(prm), ptr(o['states']), ptr(o['hn']), ptr(o['save'])
+        outs.append(o)
+    bn_stride = 0 if actions is None else actions.shape[1]
+    check(lib.asac_gru_forward(C.byref(cs), nets, len(params_list), ptr(obs), ptr(actions), bn_stride,
+                               ptr(pre_actions), ptr(h0), 0 if h0 is None else h0[0].numel(), B, L,
+                               torch.cuda.current_stream(obs.device).cuda_stream), 'gru_forward')
+    return outs
+
+
+def gru_backward(shape: lowering.GruShape, params, obs, actions, h0, t_grad, grad_state, fwd):
+    """asac_gru_backward -> reduced gradient [P] (the partial tiles summed in tile order, as
+    asac_flat_reduce_adam does)."""
+    lib = _lib.load()
+    B, L = obs.shape[:2]
+    cs = _lib.AsacGruShape(shape.obs_size, shape.action_size, shape.hidden, shape.layers)
+    tile = lib.asac_gru_backward_tile(C.byref(cs), t_grad)
+    assert tile >= 1, lib.asac_last_error()
+    tiles = (B + tile - 1) // tile
+    part = torch.full((tiles, shape.stride), float('nan'), dtype=torch.float32, device=obs.device)
+    check(lib.asac_gru_backward(C.byref(cs), ptr(params), ptr(obs), ptr(actions), actions.shape[1], None, ptr(h0),
+                                0 if h0 is None else h0[0].numel(), B, L, t_grad, ptr(grad_state),
+                                grad_state.shape[0], ptr(fwd['hn']), ptr(fwd['save']), ptr(part),
+                                torch.cuda.current_stream(obs.device).cuda_stream), 'gru_backward')
+    total = torch.zeros(shape.stride, dtype=torch.float32, device=obs.device)
+    for t in range(tiles):
+        total += part[t]
+    return total[:shape.count], part
+
+
+class SacRepCuda(SacCuda):
+    """SacCuda + a trained GRU representation (asac_sac_step_networks_rep)."""
+
+    def __init__(self, hp, batch_size: int, obs_size: int, rep_layers: int, device='cuda:0'):
+        super().__init__(hp, batch_size, device, rep_kind=1)
+        B, L, H, A, E = batch_size, self.L, hp.state_size, hp.action_size, hp.ensemble_q_num
+        self.gshape = lowering.GruShape(obs_size, A, H, rep_layers)
+        cs = _lib.AsacGruShape(obs_size, A, H, rep_layers)
+        assert self.lib.asac_gru_param_count(C.byref(cs)) == self.gshape.count
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        P = self.gshape.stride
+        self.rep_p, self.rep_t = torch.zeros(P, **f32), torch.zeros(P, **f32)
+        self.rep_m, self.rep_v = torch.zeros(P, **f32), torch.zeros(P, **f32)
+        rtile = self.lib.asac_gru_backward_tile(C.byref(cs), hp.burn_in_step)
+        assert rtile >= 1, self.lib.asac_last_error()
+        rt = (B + rtile - 1) // rtile
+        self.rb = {'obs': torch.zeros(B, L, obs_size, **f32), 'h0': torch.zeros(B, rep_layers, H, **f32),
+                   'states': torch.zeros(B, L, H, **f32), 'states_post': torch.zeros(B, L, H, **f32),
+                   'target_states': torch.zeros(B, L, H, **f32), 'hn': torch.zeros(B, L, rep_layers, H, **f32),
+                   'hn_post': torch.zeros(B, L, rep_layers, H, **f32),
+                   'save': torch.zeros(B, L, rep_layers, 4 * H, **f32), 'grad_part': torch.zeros(rt, P, **f32),
+                   'grad': torch.zeros(P, **f32)}
+        self.wk['grad_state'] = torch.zeros(E, B, H, **f32)
+        self.work.grad_state = ptr(self.wk['grad_state'])
+        rep = _lib.AsacGruRep()
+        rep.shape = cs
+        rep.params, rep.params_target, rep.m, rep.v = ptr(self.rep_p), ptr(self.rep_t), ptr(self.rep_m), ptr(self.rep_v)
+        rep.obs, rep.h0, rep.h0_b_stride = ptr(self.rb['obs']), ptr(self.rb['h0']), rep_layers * H
+        for k in ('states', 'states_post', 'target_states', 'hn', 'hn_post', 'save', 'grad_part', 'grad'):
+            setattr(rep, k, ptr(self.rb[k]))
+        rep.rep_tiles = rt
+        self.rep = rep
+
+    def load_rep(self, rep_sd, rep_target_sd):
+        self.rep_p.copy_(lowering.gru_flat_from_state_dict(self.gshape, rep_sd))
+        self.rep_t.copy_(lowering.gru_flat_from_state_dict(self.gshape, rep_target_sd))
+
+    def make_rep_batch(self, b, noise) -> _lib.AsacSacBatch:
+        """b: oracle SacRepBatch."""
+        from oracle.sac_oracle import SacBatch
+        self.rb['obs'].copy_(b.obs.float())
+        self.rb['h0'].copy_(b.hidden0.float())
+        fake = SacBatch(states=torch.zeros(1), actions=b.actions, rewards=b.rewards, dones=b.dones,
+                        mu_probs=b.mu_probs, last_masks=b.last_masks, padding_masks=b.padding_masks,
+                        priority_is=b.priority_is)
+        batch = self.make_batch(fake, noise)
+        batch.states, batch.states_post = ptr(self.rb['states']), ptr(self.rb['states_post'])
+        batch.target_states = ptr(self.rb['target_states'])
+        return batch
+
+    def step_rep(self, batch) -> dict:
+        check(self.lib.asac_sac_step_networks_rep(C.byref(self.cfg), C.byref(self.prm), C.byref(batch),
+                                                  C.byref(self.work), C.byref(self.rep), 1, self._s()),
+              'sac_step_networks_rep')
+        check(self.lib.asac_sac_staged_tail(C.byref(self.cfg), C.byref(self.prm), C.byref(self.work), self._s()),
+              'sac_staged_tail')
+        hp = self.hp
+        out = {'y': self.wk['y'].cpu().numpy(), 'grad_q': [self.grad_q_dict(i) for i in range(hp.ensemble_q_num)],
+               'grad_policy': self.grad_pi_dict(),
+               'grad_rep': {k: t.cpu().numpy() for k, t in
+                            lowering.gru_state_dict_from_flat(self.gshape, self.rb['grad']).items()},
+               'states': self.rb['states'].cpu().numpy(), 'states_post': self.rb['states_post'].cpu().numpy(),
+               'target_states': self.rb['target_states'].cpu().numpy(),
+               'next_hidden': self.rb['hn_post'][:, :-1].cpu().numpy(),
+               'grad_state': self.wk['grad_state'].cpu().numpy()}
+        if hp.use_n_step_is:
+            out['pi_probs'] = self.wk['pi_probs'].cpu().numpy()
+        if hp.use_auto_alpha:
+            out['grad_log_alpha'] = self.wk['grad_alpha'].cpu().numpy()
+        if hp.use_priority:
+            out['td_error'] = self.wk['td_error'].cpu().numpy()
+            out['y_td'] = self.wk['y_td'].cpu().numpy()
+        return out
+
+    def snapshot(self) -> dict:
+        d = super().snapshot()
+        for k, t in lowering.gru_state_dict_from_flat(self.gshape, self.rep_p).items():
+            d[f'rep.{k}'] = t.cpu().numpy()
+        for k, t in lowering.gru_state_dict_from_flat(self.gshape, self.rep_t).items():
+            d[f'rept.{k}'] = t.cpu().numpy()
+        return d

@@ -38,9 +38,10 @@ def test_struct_layout_matches_c(tmp_path):
     from asac_b200 import _lib
     src = tmp_path / 'layout.c'
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "asac_b200.h"\nint main(void){\n'
-                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(AsacSacConfig), sizeof(AsacSacParams), '
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(AsacSacConfig), sizeof(AsacSacParams), '
                    'sizeof(AsacSacBatch), sizeof(AsacSacWork), sizeof(AsacColumnTable), sizeof(AsacColumn), '
-                   'sizeof(AsacWriteTable), sizeof(AsacPeerTable));\n'
+                   'sizeof(AsacWriteTable), sizeof(AsacPeerTable), sizeof(AsacGruShape), sizeof(AsacGruNet), '
+                   'sizeof(AsacGruRep));\n'
                    'printf("%zu %zu %zu %zu %zu\\n", offsetof(AsacSacConfig, tau), offsetof(AsacSacConfig, gamma_ratio), '
                    'offsetof(AsacSacConfig, lambda_ratio), offsetof(AsacSacWork, y), offsetof(AsacColumnTable, col));\n'
                    'return 0;}\n')
@@ -49,7 +50,8 @@ def test_struct_layout_matches_c(tmp_path):
     sizes, offs = [list(map(int, line.split())) for line in subprocess.check_output([str(exe)]).decode().splitlines()]
     assert sizes == [C.sizeof(_lib.AsacSacConfig), C.sizeof(_lib.AsacSacParams), C.sizeof(_lib.AsacSacBatch),
                      C.sizeof(_lib.AsacSacWork), C.sizeof(_lib.AsacColumnTable), C.sizeof(_lib.AsacColumn),
-                     C.sizeof(_lib.AsacWriteTable), C.sizeof(_lib.AsacPeerTable)]
+                     C.sizeof(_lib.AsacWriteTable), C.sizeof(_lib.AsacPeerTable), C.sizeof(_lib.AsacGruShape),
+                     C.sizeof(_lib.AsacGruNet), C.sizeof(_lib.AsacGruRep)]
     assert offs == [_lib.AsacSacConfig.tau.offset, _lib.AsacSacConfig.gamma_ratio.offset,
                     _lib.AsacSacConfig.lambda_ratio.offset, _lib.AsacSacWork.y.offset,
                     _lib.AsacColumnTable.col.offset]

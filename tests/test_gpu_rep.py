@@ -1,0 +1,135 @@
+"""GPU: the recurrent-representation kernels (csrc/rep_gru.cu) and the SAC step with a trained GRU
+representation (asac_sac_step_networks_rep) through the C ABI, against torch.nn.GRU / autograd and
+against the CPU oracle pinned to the reference's envs/test/nn_rnn.py run (tests/golden/sac_rnn*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import golden_rep_batch, load_golden, rel_err, rep_oracle_from_golden, sac_case_meta
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # relative to scale
+
+
+def _random_gru(shape, seed):
+    from oracle.rep_oracle import init_gru
+    gen = torch.Generator().manual_seed(seed)
+    return init_gru(shape.obs_size + shape.action_size, shape.hidden, shape.layers, gen)
+
+
+@pytest.mark.parametrize('So,A,H,NL,B,L', [(6, 2, 8, 2, 37, 9), (3, 1, 16, 1, 8, 5), (10, 3, 40, 3, 5, 4), (6, 2, 64, 1, 3, 3)])
+def test_gru_forward_matches_torch(So, A, H, NL, B, L):
+    """States, every layer's hidden states and the actor-side single step against torch.nn.GRU
+    (seq_layers.py:41-113 without a padding mask); two parameter sets in one launch."""
+    from asac_b200 import lowering
+    from asac_b200.nn_models import GRU
+    from tests.cuda_harness import gru_forward
+    shape = lowering.GruShape(So, A, H, NL)
+    dev = torch.device('cuda:0')
+    rng = np.random.RandomState(So * 100 + H)
+    sds = [_random_gru(shape, 1), _random_gru(shape, 2)]
+    flats = [lowering.gru_flat_from_state_dict(shape, sd).to(dev) for sd in sds]
+    obs = torch.from_numpy(rng.randn(B, L, So).astype(np.float32))
+    actions = torch.from_numpy(rng.rand(B, L - 1, A).astype(np.float32) * 2 - 1)
+    h0 = torch.from_numpy(rng.randn(B, NL, H).astype(np.float32) * 0.5)
+    outs = gru_forward(shape, flats, obs.to(dev), actions.to(dev), None, h0.to(dev), save=True)
+    pre = torch.cat([torch.zeros(B, 1, A), actions], dim=1)
+    for sd, out in zip(sds, outs):
+        ref = GRU(So + A, H, NL)
+        ref.load_state_dict({k[len('rnn.'):]: v for k, v in sd.items()})
+        with torch.no_grad():
+            states, hn = ref(torch.cat([obs, pre], -1), h0)
+        assert rel_err(out['states'].cpu(), states) < TOL
+        assert rel_err(out['hn'].cpu(), hn) < TOL
+        assert torch.equal(out['hn'][:, :, -1], out['states'])
+    # actor side: one step, pre_action handed over directly, zero initial state
+    pa = torch.from_numpy(rng.rand(B, 1, A).astype(np.float32))
+    one = gru_forward(shape, flats[:1], obs[:, :1].contiguous().to(dev), None, pa.to(dev), None)[0]
+    ref = GRU(So + A, H, NL)
+    ref.load_state_dict({k[len('rnn.'):]: v for k, v in sds[0].items()})
+    with torch.no_grad():
+        states, hn = ref(torch.cat([obs[:, :1], pa], -1), None)
+    assert rel_err(one['states'].cpu(), states) < TOL and rel_err(one['hn'].cpu(), hn) < TOL
+
+
+@pytest.mark.parametrize('So,A,H,NL,B,L,tg,E', [(6, 2, 8, 2, 19, 9, 5, 2), (3, 1, 16, 1, 8, 5, 0, 1),
+                                                 (10, 3, 40, 3, 6, 6, 5, 3), (6, 2, 8, 2, 7, 46, 40, 2)])
+def test_gru_backward_matches_autograd(So, A, H, NL, B, L, tg, E):
+    """BPTT of a state gradient applied at step t_grad, against autograd through the oracle's
+    restatement of the cell (in float64, so that the comparison measures the kernel alone)."""
+    from asac_b200 import lowering
+    from oracle.rep_oracle import gru_forward as oracle_gru
+    from tests.cuda_harness import gru_backward, gru_forward
+    shape = lowering.GruShape(So, A, H, NL)
+    dev = torch.device('cuda:0')
+    rng = np.random.RandomState(tg * 7 + H)
+    sd = _random_gru(shape, 3)
+    flat = lowering.gru_flat_from_state_dict(shape, sd).to(dev)
+    obs = torch.from_numpy(rng.randn(B, L, So).astype(np.float32))
+    actions = torch.from_numpy(rng.rand(B, L - 1, A).astype(np.float32) * 2 - 1)
+    h0 = torch.from_numpy(rng.randn(B, NL, H).astype(np.float32) * 0.5)
+    gs = torch.from_numpy(rng.randn(E, B, H).astype(np.float32))
+    fwd = gru_forward(shape, [flat], obs.to(dev), actions.to(dev), None, h0.to(dev), save=True)[0]
+    grad, part = gru_backward(shape, flat, obs.to(dev), actions.to(dev), h0.to(dev), tg, gs.to(dev), fwd)
+    assert not torch.isnan(part[:, :shape.count]).any(), 'every partial-gradient element must be written'
+    p64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    pre = torch.cat([torch.zeros(B, 1, A), actions], dim=1)
+    states, _ = oracle_gru(p64, NL, torch.cat([obs, pre], -1).double(), h0.double())
+    (states[:, tg] * gs.double().sum(0)).sum().backward()
+    ref = lowering.gru_flat_from_state_dict(shape, {k: v.grad for k, v in p64.items()})[:shape.count]
+    got = grad.cpu()
+    for k, v in lowering.gru_state_dict_from_flat(shape, got).items():
+        r = lowering.gru_state_dict_from_flat(shape, ref)[k]
+        assert rel_err(v, r) < TOL, (k, rel_err(v, r))
+
+
+@pytest.mark.parametrize('name', ['sac_rnn.npz', 'sac_rnn_b0.npz'])
+def test_recurrent_step_against_oracle_and_golden(name):
+    """asac_sac_step_networks_rep + tail, consecutive steps from the golden initial parameters: every
+    output against the oracle run on the same inputs and against the reference's own numbers."""
+    from tests.cuda_harness import SacRepCuda
+    torch.set_num_threads(1)
+    g = load_golden(name)
+    m = sac_case_meta(g)
+    oracle = rep_oracle_from_golden(g)
+    hp = oracle.hp
+    cu = SacRepCuda(hp, m['B'], m['So'], m['rep_layers'])
+    from tests.helpers import golden_params, golden_rep_params
+    cu.load_params(*golden_params(g, 'init', m['E']))
+    cu.load_rep(*golden_rep_params(g, 'init'))
+    for s in range(m['steps']):
+        batch, noise = golden_rep_batch(g, s)
+        cb = cu.make_rep_batch(batch, noise)
+        want = oracle.step(batch, noise)
+        got = cu.step_rep(cb)
+        torch.cuda.synchronize()
+        pre = f's{s}.'
+        assert rel_err(got['states'], want['states']) < TOL
+        assert rel_err(got['target_states'], want['target_states']) < TOL
+        assert rel_err(got['y'], want['y'].view(-1)) < TOL
+        for i in range(m['E']):
+            for k, v in got['grad_q'][i].items():
+                assert rel_err(v, want['grad_q'][i][k]) < TOL, (s, i, k)
+        for k, v in got['grad_rep'].items():
+            assert rel_err(v, want['grad_rep'][k]) < TOL, (s, k, rel_err(v, want['grad_rep'][k]))
+            assert rel_err(v, g[f'{pre}grad.rep.{k}']) < TOL, (s, k)
+        assert rel_err(got['states_post'], want['states_post']) < TOL
+        assert rel_err(got['states_post'], g[pre + 'out.states_post']) < TOL
+        assert rel_err(got['next_hidden'], want['next_hidden']) < TOL
+        assert rel_err(got['next_hidden'], g[pre + 'out.next_hidden']) < TOL
+        for k, v in got['grad_policy'].items():
+            assert rel_err(v, want['grad_policy'][k]) < TOL, (s, k)
+        if hp.use_auto_alpha:
+            assert rel_err(got['grad_log_alpha'], want['grad_log_alpha']) < TOL
+        if hp.use_n_step_is:
+            assert rel_err(got['pi_probs'], want['pi_probs']) < 5e-5
+        if hp.use_priority:
+            assert rel_err(got['y_td'], want['y_td'].view(-1)) < 5e-5
+            assert rel_err(got['td_error'], want['td_error'].view(-1)) < 5e-5
+            assert rel_err(got['td_error'], g[pre + 'out.td_error'].reshape(-1)) < 5e-5
+        snap, ref = cu.snapshot(), oracle.snapshot()
+        for k, v in snap.items():
+            assert rel_err(v, ref[k]) < 2e-5, (s, k, rel_err(v, ref[k]))
+        cnt = cu.counters.cpu().tolist()
+        assert cnt[0] == s + 1 and cnt[1] == s + 1 and cnt[2] == s + 1 and cnt[4] == s + 1
