@@ -381,6 +381,48 @@ class SAC_Base:
         prm.counters = ptr(self._counters)
         self._prm = prm
 
+    def _gru_forward(self, obs0: torch.Tensor, pre_action: torch.Tensor, h0: torch.Tensor | None):
+        """asac_gru_forward with the online representation: obs0 [rows, l, So], pre_action [rows, l, A],
+        h0 [rows, layers, H] -> (state [rows, l, H], hn [rows, l, layers, H])."""
+        g = self._gru
+        rows, l = int(obs0.shape[0]), int(obs0.shape[1])
+        f32 = dict(dtype=torch.float32, device=self.device)
+        state, hn = torch.empty(rows, l, g.hidden, **f32), torch.empty(rows, l, g.layers, g.hidden, **f32)
+        net = _lib.AsacGruNet(ptr(self._rep_flat), ptr(state), ptr(hn), None)
+        check(self._lib.asac_gru_forward(C.byref(self._gru_c), C.byref(net), 1, ptr(obs0.contiguous()), None, 0,
+                                         ptr(pre_action.contiguous()), ptr(None if h0 is None else h0.contiguous()),
+                                         g.layers * g.hidden, rows, l, _lib.current_stream()), 'gru_forward')
+        return state, hn
+
+    @torch.no_grad()
+    def _probe_rep(self) -> None:
+        """The structural lowering (lowering.analyze_rep) only proves that the plugin's ModelRep OWNS one
+        stock GRU; that its forward IS ``GRU(cat[obs_list[0], pre_action], pre_seq_hidden_state[:, 0])``
+        is checked here by running the plugin's torch forward and the kernel on the same random
+        inputs (with an initial state, and with None as at sac_base.py:353-357)."""
+        g, dev = self._gru, self.device
+        gen = torch.Generator(device='cpu').manual_seed(1234)
+        rows, l = 5, 3
+        obs_list = [torch.randn(rows, l, *shape, generator=gen).to(dev) for shape in self.obs_shapes]
+        pre_action = torch.rand(rows, l, self.c_action_size, generator=gen).to(dev)
+        hidden = (torch.randn(rows, l, g.layers, g.hidden, generator=gen) * 0.5).to(dev)
+        import warnings
+        for h in (hidden, None):
+            try:
+                # cuDNN notes that the weights are views of one flat buffer; its RNNs default to TF32
+                with warnings.catch_warnings(), torch.backends.cudnn.flags(allow_tf32=False):
+                    warnings.simplefilter('ignore')
+                    want_state, want_hn = self.model_rep(obs_list, pre_action, h)
+            except Exception as e:  # noqa: BLE001
+                raise lowering.NotStockNetwork(f'ModelRep.forward failed on the probe inputs: {e}') from e
+            state, hn = self._gru_forward(obs_list[0], pre_action, None if h is None else h[:, 0])
+            if want_state.shape != state.shape or want_hn.shape != hn.shape or \
+                    not torch.allclose(want_state, state, atol=2e-5, rtol=0) or \
+                    not torch.allclose(want_hn, hn, atol=2e-5, rtol=0):
+                raise lowering.NotStockNetwork(
+                    'ModelRep.forward is not GRU(cat[obs_list[0], pre_action], pre_seq_hidden_state[:, 0]) '
+                    '(envs/test/nn_rnn.py form); other recurrent representations are outside the fused path')
+
     def _build_ckpt(self) -> None:
         """Same key names as sac_base.py:493-566 so .pth files interchange."""
         ck = {'global_step': self.global_step}
@@ -618,7 +660,14 @@ class SAC_Base:
                     continue  # ModelSimpleRep ignores non-vector observations (representation.py:74-83)
                 t = torch.from_numpy(np.ascontiguousarray(o)).to(self.device, non_blocking=True)
                 parts.append(t.float() if t.dtype != torch.float32 else t)
-            state = parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
+            hidden_out = None
+            if self._gru is not None:  # one GRU step from the caller's hidden state (sac_base.py:1003)
+                to_dev = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
+                state, hn = self._gru_forward(parts[0].unsqueeze(1), to_dev(pre_action).unsqueeze(1),
+                                              to_dev(pre_seq_hidden_state))
+                state, hidden_out = state.squeeze(1), hn.squeeze(1)
+            else:
+                state = parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
             state = state.contiguous()
             rows = int(state.shape[0])
             f32 = dict(dtype=torch.float32, device=self.device)
@@ -634,7 +683,8 @@ class SAC_Base:
                                             1 if (self.actor_tensor_cores and rows >= 2048) else 0,
                                             _lib.current_stream()), 'policy_act')
             self._act_counter += 1
-            hidden = np.zeros((rows, *self.seq_hidden_state_shape), dtype=np.float32)
+            hidden = np.zeros((rows, *self.seq_hidden_state_shape), dtype=np.float32) if hidden_out is None \
+                else hidden_out.cpu().numpy()
             return action.cpu().numpy(), prob.cpu().numpy(), hidden
 
     @torch.no_grad()
@@ -648,7 +698,13 @@ class SAC_Base:
                 obs[i] = o.float() / 255.
             elif o.dtype == torch.bool:
                 obs[i] = o.float()
-        state, hidden = self.model_rep([o.unsqueeze(1) for o in obs], None, None)
+        if self._gru is not None:
+            to_dev = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
+            with torch.backends.cudnn.flags(allow_tf32=False):  # cuDNN RNNs default to TF32
+                state, hidden = self.model_rep([o.unsqueeze(1) for o in obs], to_dev(pre_action).unsqueeze(1),
+                                               to_dev(pre_seq_hidden_state).unsqueeze(1))
+        else:
+            state, hidden = self.model_rep([o.unsqueeze(1) for o in obs], None, None)
         state, hidden = state.squeeze(1), hidden.squeeze(1)
         _, c_policy = self.model_policy(state, obs)
         if offline_action is not None:

@@ -34,18 +34,25 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 CFG = dict(obs_shape=(6,), A=2, B=256, n_step=1, burn_in=0, E=2, hidden=64, depth=3, capacity=524288,
-           per_alpha=0.9, episode_len=100)
+           per_alpha=0.9, episode_len=100, rep=None)
 # BASELINE.json configs[2] (Pendulum shapes, n_step=5 + V-trace, batch 1024): `--config c3`, a secondary
 # measurement — the default run is configs[1], the one the metric is quoted on
 CONFIGS = {
     'c2': dict(CFG),
     'c3': dict(CFG, obs_shape=(3,), A=1, B=1024, n_step=5, depth=2),
+    # BASELINE.json configs[3] on ONE GPU (the 8-GPU replay sharding of that config is `--gpus 8` once the
+    # representation's gradient joins the peer exchange): envs/test/nn_rnn.py GRU(6 + 2 -> 8, 2 layers),
+    # burn-in 40, n_step 5 -> windows of 46 rows, batch 256 sequences, PER
+    'c4': dict(CFG, burn_in=40, n_step=5, rep=dict(hidden=8, layers=2)),
 }
 WORKLOADS = {
     'c2': 'TEST vector-obs(6,) A=2 SAC+PER alpha=0.9 capacity=524288 (full) batch=256 ensemble_q=2 n_step=1, '
           'stock envs/test/nn.py nets (H=64, depth 3)',
     'c3': 'Pendulum-v1 shapes obs(3,) A=1 SAC+PER n_step=5 V-trace (v_lambda=1, use_n_step_is) capacity=524288 (full) '
           'batch=1024 ensemble_q=2, envs/gym/pendulum/nn.py nets (H=64, depth 2), synthetic episodes',
+    'c4': 'R2D2-style TEST vector-obs(6,) A=2 seq_encoder=RNN (envs/test/nn_rnn.py: GRU(8 -> 8, 2 layers) trained '
+          'through the critic loss) burn_in_step=40 n_step=5 (46-row windows) SAC+PER capacity=524288 (full) '
+          'batch=256 sequences ensemble_q=2, stock H=64 depth-3 Q / policy nets, single GPU',
 }
 WORKLOAD = WORKLOADS['c2']
 METRIC = 'sac_grad_steps_per_sec_batch256'
@@ -53,16 +60,21 @@ UNIT = 'steps/s'
 
 
 # --------------------------------------------------------------------------- synthetic data
+def hidden_shape():
+    r = CFG.get('rep')
+    return (r['layers'], r['hidden']) if r else (0,)
+
+
 def synth_episode(rng, T, S, A):
     """tests/get_synthesis_data.py:114-126 of the reference: obs randn, action rand, reward randn,
-    done randint, probs rand (float32), empty hidden state."""
+    done randint, probs rand (float32), hidden state randn (empty without a recurrent representation)."""
     return dict(ep_indexes=np.arange(T, dtype=np.int32)[None],
                 ep_obses_list=[rng.randn(1, T, S).astype(np.float32)],
                 ep_actions=rng.rand(1, T, A).astype(np.float32),
                 ep_rewards=rng.randn(1, T).astype(np.float32),
                 ep_dones=rng.randint(0, 2, size=(1, T)).astype(bool),
                 ep_probs=rng.rand(1, T, A).astype(np.float32),
-                ep_pre_seq_hidden_states=np.zeros((1, T, 0), dtype=np.float32))
+                ep_pre_seq_hidden_states=rng.randn(1, T, *hidden_shape()).astype(np.float32))
 
 
 def pin_episode(ep):
@@ -123,14 +135,17 @@ def flops_per_row(S, A, H, d):
 def stage_work(cfg):
     """ALGORITHMIC flops / bytes per launch of each kernel."""
     S, A, B, n, E, H, d = cfg['obs_shape'][0], cfg['A'], cfg['B'], cfg['n_step'], cfg['E'], cfg['hidden'], cfg['depth']
+    So, r = S, cfg.get('rep')
+    if r:
+        S = r['hidden']  # the nets see the GRU's output
     b = cfg['burn_in']
     L = b + n + 1
     D = int(np.log2(cfg['capacity']))
     q, pi = flops_per_row(S, A, H, d)
     Pq = (S + A) * H + H + (d - 1) * (H * H + H) + H + 1
     Ppi = S * H + H + (d - 1) * (H * H + H) + 2 * A * H + 2 * A
-    row = 4 + 1 + 4 * S + 4 * A + 4 + 1 + 4 * A
-    return {
+    row = 4 + 1 + 4 * So + 4 * A + 4 + 1 + 4 * A + (4 * r['layers'] * r['hidden'] if r else 0)
+    work = {
         'per_sample': dict(bound='hbm', bytes=B * (8 * D + 28)),
         'gather': dict(bound='hbm', bytes=2 * B * L * row),
         'fill_normal': dict(bound='hbm', bytes=4 * (2 * B * (n + 1) * A + 2 * B * A)),
@@ -146,6 +161,17 @@ def stage_work(cfg):
         'per_update': dict(bound='hbm', bytes=B * (12 * D + 16)),
         'write_back': dict(bound='hbm', bytes=B * (L - 1) * (A * 4 + 8)),
     }
+    if r:
+        Hg, NL = r['hidden'], r['layers']
+        cell = sum(2 * 3 * Hg * ((So + A if l == 0 else Hg) + Hg) for l in range(NL))  # flops of one step, all layers
+        Pg = sum(3 * Hg * ((So + A if l == 0 else Hg) + Hg + 2) for l in range(NL))
+        work['value_pass_post'] = dict(bound='tensor', flops=pi * B * (L + n + 1) + E * q * (B * (n + 1) + B))
+        work['gru_forward_pair'] = dict(bound='tensor', flops=2 * cell * B * L)
+        work['gru_backward'] = dict(bound='tensor', flops=3 * cell * B * (b + 1))  # dX/dH chain + weight gradients
+        work['adam_rep'] = dict(bound='hbm', bytes=Pg * 4 * 7)
+        work['gru_forward_post'] = dict(bound='tensor', flops=cell * B * L)
+        work['write_back_hidden'] = dict(bound='hbm', bytes=B * (L - 1) * (4 * NL * Hg + 8))
+    return work
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -163,11 +189,25 @@ def build_learner(device, seed, capacity, fill):
         def _build_model(self):
             super()._build_model(c_dense_n=CFG['hidden'], c_dense_depth=depth)
 
-    nn = types.SimpleNamespace(ModelRep=m.ModelSimpleRep, ModelQ=ModelQ, ModelPolicy=ModelPolicy)
+    ModelRep, seq_encoder = m.ModelSimpleRep, None
+    if CFG.get('rep'):
+        from asac_b200.config_enums import SEQ_ENCODER
+        seq_encoder = SEQ_ENCODER.RNN
+
+        class ModelRep(m.ModelBaseRep):  # the form of envs/test/nn_rnn.py
+            def _build_model(self):
+                self.rnn = m.GRU(self.obs_shapes[0][0] + self.c_action_size, CFG['rep']['hidden'], CFG['rep']['layers'])
+
+            def forward(self, obs_list, pre_action, pre_seq_hidden_state, padding_mask=None):
+                h0 = None if pre_seq_hidden_state is None else pre_seq_hidden_state[:, 0]
+                return self.rnn(torch.cat([obs_list[0], pre_action], dim=-1), h0)
+
+    nn = types.SimpleNamespace(ModelRep=ModelRep, ModelQ=ModelQ, ModelPolicy=ModelPolicy)
     sac = SAC_Base(obs_names=['vector'], obs_shapes=[CFG['obs_shape']], d_action_sizes=[], c_action_size=CFG['A'],
                    model_abs_dir=None, nn=nn, device=device, seed=seed, batch_size=CFG['B'], n_step=CFG['n_step'],
                    burn_in_step=CFG['burn_in'], ensemble_q_num=CFG['E'], ensemble_q_sample=CFG['E'],
-                   use_priority=True, replay_config={'capacity': capacity, 'alpha': CFG['per_alpha']})
+                   seq_encoder=seq_encoder, use_priority=True,
+                   replay_config={'capacity': capacity, 'alpha': CFG['per_alpha']})
     rng = np.random.RandomState(seed)
     S, A, T = CFG['obs_shape'][0], CFG['A'], CFG['episode_len']
     while sac.replay_buffer.size < fill:
@@ -212,6 +252,29 @@ def profile_stages(sac, steps):
         ('write_back', lambda: rb.write_back(smp['ids'], 'mu_prob', sac._wk['pi_probs'], -sac.burn_in_step,
                                              sac._bt['padding_masks'])),
     ]
+    if sac._rep is not None:  # trained GRU representation: its kernels, each alone
+        rp, gshape = sac._rep, sac._gru_c
+        L, bn = sac._cfg.seq_len, sac._cfg.bn_stride
+        acts, P = ptr(sac._bt['actions']), sac._gru.count
+        pair = (_lib.AsacGruNet * 2)()
+        pair[0] = _lib.AsacGruNet(rp.params, rp.states, rp.hn, rp.save)
+        pair[1] = _lib.AsacGruNet(rp.params_target, rp.target_states, None, None)
+        again = _lib.AsacGruNet(rp.params, rp.states_post, rp.hn_post, None)
+        stages += [
+            ('gru_forward_pair', lambda: check(lib.asac_gru_forward(C.byref(gshape), pair, 2, rp.obs, acts, bn, None, rp.h0,
+                                                                    rp.h0_b_stride, B, L, s()))),
+            ('gru_backward', lambda: check(lib.asac_gru_backward(C.byref(gshape), rp.params, rp.obs, acts, bn, None, rp.h0,
+                                                                 rp.h0_b_stride, B, L, sac.burn_in_step,
+                                                                 ptr(sac._wk['grad_state']), sac.ensemble_q_num, rp.hn,
+                                                                 rp.save, rp.grad_part, s()))),
+            ('adam_rep', lambda: check(lib.asac_flat_reduce_adam(rp.params, rp.m, rp.v, rp.grad_part, rp.rep_tiles,
+                                                                 sac._gru.stride, P, rp.grad, ptr(sac._counters[4:]),
+                                                                 float(sac.learning_rate), s()))),
+            ('gru_forward_post', lambda: check(lib.asac_gru_forward(C.byref(gshape), C.byref(again), 1, rp.obs, acts, bn,
+                                                                    None, rp.h0, rp.h0_b_stride, B, L, s()))),
+            ('write_back_hidden', lambda: rb.write_back(smp['ids'], 'pre_seq_hidden_state', sac._rw['hn_post'],
+                                                        1 - sac.burn_in_step, sac._bt['padding_masks'], n_rows=L - 1)),
+        ]
     # one tiny CUDA graph per stage, replayed back to back: device time without launch overhead
     # (warm L2; the whole-step numbers of run_gpu() are the ones taken with a flushed L2)
     out = {}
@@ -481,14 +544,18 @@ def cpu_port_setup(seed=0):
         'obs_vector': rng.randn(C, S).astype(np.float32), 'action': rng.rand(C, A).astype(np.float32),
         'reward': rng.randn(C).astype(np.float32), 'done': rng.randint(0, 2, size=C).astype(bool),
         'mu_prob': rng.rand(C, A).astype(np.float32),
-        'pre_seq_hidden_state': np.zeros((C, 0), dtype=np.float32)}
+        'pre_seq_hidden_state': rng.randn(C, *hidden_shape()).astype(np.float32)}
     per.store.size, per.store.next_id = C, C
     leaves = np.power(np.clip(np.abs(rng.randn(C)).astype(np.float32), 0.01, 1.0), np.float32(CFG['per_alpha']))
     leaves[index == T - 1] = 0
     per.tree.nodes[C - 1:] = leaves
     per.tree.rebuild()
-    hp = SacHyper(state_size=S, action_size=A, ensemble_q_num=CFG['E'], hidden=CFG['hidden'], q_depth=CFG['depth'],
-                  policy_depth=CFG['depth'], burn_in_step=CFG['burn_in'], n_step=CFG['n_step'])
+    r = CFG.get('rep')
+    hp = SacHyper(state_size=r['hidden'] if r else S, action_size=A, ensemble_q_num=CFG['E'], hidden=CFG['hidden'],
+                  q_depth=CFG['depth'], policy_depth=CFG['depth'], burn_in_step=CFG['burn_in'], n_step=CFG['n_step'])
+    if r:
+        from oracle.rep_oracle import SacRepOracle
+        return per, SacRepOracle(hp, S, r['layers'], seed=seed), rng
     return per, SacOracle(hp, seed=seed), rng
 
 
@@ -500,10 +567,15 @@ def cpu_port_step(per, sac, rng):
     data_ids, batch, weights, _ = per.sample(rng.random_sample(B))
     batch = pad_sampled_batch(batch, b, np.zeros(A, dtype=np.float32))
     t = torch.from_numpy
-    sb = SacBatch(states=t(batch['obs_vector']), actions=t(batch['action'][:, :-1]), rewards=t(batch['reward'][:, :-1]),
+    common = dict(actions=t(batch['action'][:, :-1]), rewards=t(batch['reward'][:, :-1]),
                   dones=t(batch['done'][:, :-1]), mu_probs=t(batch['mu_prob'][:, :-1]),
                   last_masks=t(batch['last_mask'][:, :-1]), padding_masks=t(batch['padding_mask'][:, :-1]),
                   priority_is=t(weights))
+    if CFG.get('rep'):
+        from oracle.rep_oracle import SacRepBatch
+        sb = SacRepBatch(obs=t(batch['obs_vector']), hidden0=t(batch['pre_seq_hidden_state'][:, 0]), **common)
+    else:
+        sb = SacBatch(states=t(batch['obs_vector']), **common)
     noise = SacNoise(eps_y=torch.randn(B, n + 1, A), eps_pi=torch.randn(B, A), eps_alpha=torch.randn(B, A),
                      eps_td=torch.randn(B, n + 1, A))
     out = sac.step(sb, noise)
@@ -511,6 +583,9 @@ def cpu_port_step(per, sac, rng):
     pad = batch['padding_mask'][:, :-1].reshape(-1)
     ptrs = (data_ids[:, None] + np.arange(-b, n)[None, :]).reshape(-1)
     per.update_transitions(ptrs[~pad], 'mu_prob', out['pi_probs'].numpy().reshape(-1, A)[~pad])
+    if CFG.get('rep'):  # sac_base.py:2589-2596
+        nh = out['next_hidden'].numpy()
+        per.update_transitions(ptrs[~pad] + 1, 'pre_seq_hidden_state', nh.reshape(-1, *nh.shape[2:])[~pad])
 
 
 def cpu_port_baseline(budget_s=12.0, steps=None, warmup=5):
@@ -527,7 +602,7 @@ def cpu_port_baseline(budget_s=12.0, steps=None, warmup=5):
             break
     dt = time.perf_counter() - t0
     return {'value': done / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-            'sample': f'{done} train() steps of the same workload (B=256, capacity 524288 full) in {dt:.1f} s: '
+            'sample': f"{done} train() steps of the same workload (B={CFG['B']}, capacity {CFG['capacity']} full) in {dt:.1f} s: "
                       f'NumPy sumtree + torch-CPU fp32 update (oracle/), {threads} torch threads',
             'ms_per_step': dt / done * 1e3}
 

@@ -33,6 +33,25 @@ class ModelPolicy(m.ModelPolicy):
 '''
 
 
+PLUGIN_RNN = '''import torch
+
+import algorithm.nn_models as m
+
+
+class ModelRep(m.ModelBaseRep):
+    def _build_model(self):
+        self.rnn = m.GRU(self.obs_shapes[0][0] + self.c_action_size, 8, 2)
+
+    def forward(self, obs_list, pre_action, pre_seq_hidden_state, padding_mask=None):
+        h0 = None if pre_seq_hidden_state is None else pre_seq_hidden_state[:, 0]
+        return self.rnn(torch.cat([obs_list[0], pre_action], dim=-1), h0)
+
+
+ModelQ = m.ModelQ
+ModelPolicy = m.ModelPolicy
+'''
+
+
 def _plugin(tmp_path: Path, text: str, name: str):
     path = tmp_path / f'{name}.py'
     path.write_text(text)  # same text as the reference's envs/test/nn.py / envs/gym/pendulum/nn.py
@@ -42,15 +61,15 @@ def _plugin(tmp_path: Path, text: str, name: str):
     return mod
 
 
-def _episode(rng, obs_shapes, A, T):
+def _episode(rng, obs_shapes, A, T, hidden_shape=(0,)):
     return dict(ep_indexes=np.arange(T, dtype=np.int32)[None],
                 ep_obses_list=[rng.randn(1, T, *s).astype(np.float32) for s in obs_shapes],
                 ep_actions=rng.rand(1, T, A).astype(np.float32), ep_rewards=rng.randn(1, T).astype(np.float32),
                 ep_dones=rng.randint(0, 2, size=(1, T)).astype(bool), ep_probs=rng.rand(1, T, A).astype(np.float32),
-                ep_pre_seq_hidden_states=np.zeros((1, T, 0), dtype=np.float32))
+                ep_pre_seq_hidden_states=(rng.randn(1, T, *hidden_shape) * 0.3).astype(np.float32))
 
 
-def _make(nn, graph, obs_shapes=((6,),), A=2, **kw):
+def _make(nn, graph, obs_shapes=((6,),), A=2, hidden_shape=(0,), **kw):
     from algorithm.sac_base import SAC_Base  # the alias package: reference-style import
     kw.setdefault('batch_size', 64)
     kw.setdefault('replay_config', {'capacity': 4096})
@@ -58,7 +77,7 @@ def _make(nn, graph, obs_shapes=((6,),), A=2, **kw):
                    d_action_sizes=[], c_action_size=A, model_abs_dir=None, nn=nn, seed=7, use_cuda_graph=graph, **kw)
     rng = np.random.RandomState(0)
     for _ in range(12):
-        sac.put_episode(**_episode(rng, obs_shapes, A, 50))
+        sac.put_episode(**_episode(rng, obs_shapes, A, 50, hidden_shape))
     return sac
 
 
@@ -197,3 +216,81 @@ def test_choose_action_kernels_match_torch_modules(tmp_path):
     b, _, _ = sac.choose_action([rng.randn(64, 6).astype(np.float32)], None, None)
     assert np.all(np.abs(a) < 1) and np.all(np.isfinite(p)) and not np.array_equal(a, b)
     sac.close()
+
+
+def test_recurrent_representation_learner(tmp_path):
+    """seq_encoder=RNN with the envs/test/nn_rnn.py form of ModelRep: the plugin loads unchanged, the
+    representation trains, the CUDA graph replays the eager sequence bit for bit, the window gather
+    feeds the GRU kernels the stored observations / first hidden state, the next hidden states go
+    back to pre_seq_hidden_state of the following rows (sac_base.py:2589-2596), choose_action runs
+    one GRU step + the policy on the kernels and agrees with the torch modules."""
+    from algorithm.utils.enums import SEQ_ENCODER
+    nn = _plugin(tmp_path, PLUGIN_RNN, 'nn_plugin_rnn')
+    kw = dict(seq_encoder=SEQ_ENCODER.RNN, burn_in_step=4, n_step=3, hidden_shape=(2, 8), batch_size=32,
+              replay_config={'capacity': 1024})
+    a = _make(nn, graph=False, **kw)
+    b = _make(nn, graph=True, **kw)
+    assert a.state_size == 8 and tuple(a.seq_hidden_state_shape) == (2, 8)
+    assert a.get_initial_seq_hidden_state(3).shape == (3, 2, 8)
+    rep0 = a._rep_flat.clone()
+    hid0 = a.replay_buffer._columns['pre_seq_hidden_state'].clone()
+    # one eager step, then check the data movement around the kernels against the ring
+    assert a.train() == 1 and b.train() == 1
+    torch.cuda.synchronize()
+    rb, cap, L, bi = a.replay_buffer, a.replay_buffer.capacity, 8, 4
+    ids = a._smp['ids'].cpu().numpy()
+    pad = a._bt['padding_masks'].cpu().numpy().astype(bool)
+    obs_ring = rb._columns['obs_o0'].cpu().numpy()
+    got_obs = a._bt['obs'].cpu().numpy()
+    hn_post = a._rw['hn_post'].cpu().numpy().reshape(len(ids), L, 2, 8)
+    ring_h = rb._columns['pre_seq_hidden_state'].cpu().numpy().reshape(cap, 2, 8)
+    store_ids = rb._store_ids.cpu().numpy()
+    targets = {}
+    for i, d in enumerate(ids):
+        for t in range(L):  # observations are copied as stored, padded rows included (sac_base.py:2435-2453)
+            assert np.array_equal(got_obs[i, t], obs_ring[(d - bi + t) % cap]), (i, t)
+        h_first = a._bt['hidden'].cpu().numpy()[i, 0].reshape(2, 8)
+        want_first = np.zeros((2, 8), np.float32) if pad[i, 0] else hid0.cpu().numpy().reshape(cap, 2, 8)[(d - bi) % cap]
+        assert np.array_equal(h_first, want_first), i
+        for t in range(L - 1):
+            if not pad[i, t] and store_ids[(d + 1 - bi + t) % cap] == d + 1 - bi + t:
+                targets.setdefault(int(d + 1 - bi + t), []).append((i, t))
+    assert len(targets) > 50
+    for tid, srcs in targets.items():
+        if len({(hn_post[i, t]).tobytes() for i, t in srcs}) == 1:  # a single writer (or identical rows)
+            i, t = srcs[0]
+            assert np.array_equal(ring_h[tid % cap], hn_post[i, t]), (tid, srcs)
+    for i in range(2, 7):
+        assert a.train() == i and b.train() == i
+    torch.cuda.synchronize()
+    assert b._graph is not None and a._graph is None
+    assert not torch.equal(rep0, a._rep_flat), 'the representation must train'
+    assert not torch.equal(a._rep_flat, a._rept_flat)
+    for x, y in ((a._rep_flat, b._rep_flat), (a._rept_flat, b._rept_flat), (a._q_flat, b._q_flat),
+                 (a._pi_flat, b._pi_flat), (a._rep_m, b._rep_m), (a.replay_buffer._nodes, b.replay_buffer._nodes),
+                 (a.replay_buffer._columns['pre_seq_hidden_state'], b.replay_buffer._columns['pre_seq_hidden_state']),
+                 (a.replay_buffer._columns['mu_prob'], b.replay_buffer._columns['mu_prob'])):
+        assert torch.equal(x, y)
+    assert not torch.equal(hid0, a.replay_buffer._columns['pre_seq_hidden_state'])
+    assert int(a._counters[4]) == 6
+    assert all(np.isfinite(v) for v in b.last_step_stats().values())
+    # parameters of the torch modules alias the flat buffers the kernels train
+    w = a.model_rep.rnn._grus[1].weight_hh_l0
+    assert w.data_ptr() >= a._rep_flat.data_ptr() and torch.equal(
+        w, a._rep_flat[w.data_ptr() - a._rep_flat.data_ptr() >> 2:][:w.numel()].view_as(w))
+    # actor side
+    rng = np.random.RandomState(3)
+    rows = 33
+    obs = [rng.randn(rows, 6).astype(np.float32)]
+    pre_a, pre_h = rng.rand(rows, 2).astype(np.float32), (rng.randn(rows, 2, 8) * 0.3).astype(np.float32)
+    eps = rng.randn(rows, 2).astype(np.float32)
+    a0, p0, h0 = a.choose_action(obs, pre_a, pre_h, eps=eps)
+    a1, p1, h1 = a._choose_action_torch(obs, pre_a, pre_h, eps=eps)
+    assert h0.shape == (rows, 2, 8) and np.max(np.abs(h0 - h1)) < 1e-5
+    assert np.max(np.abs(a0 - a1)) < 1e-5
+    assert np.median(np.abs(p0 - p1) / np.maximum(1.0, np.abs(p1))) < 1e-5
+    # checkpoint keys of a run with a trained representation (sac_base.py:506-509)
+    assert {'model_rep', 'model_target_rep', 'optimizer_rep'} <= set(a.ckpt_dict)
+    sd = a.ckpt_dict['optimizer_rep'].state_dict()
+    assert float(sd['state'][0]['step']) == 6 and len(sd['state']) == 8
+    a.close(); b.close()
