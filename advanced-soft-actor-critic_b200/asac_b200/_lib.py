@@ -45,7 +45,7 @@ class AsacSacConfig(C.Structure):
                 ('v_c', C.c_float), ('clip_epsilon', C.c_float), ('target_c_alpha', C.c_float),
                 ('td_error_min', C.c_float), ('td_error_max', C.c_float), ('per_alpha', C.c_float),
                 ('gamma_ratio', C.c_float * MAX_NSTEP), ('lambda_ratio', C.c_float * MAX_NSTEP),
-                ('rep_kind', C.c_int32), ('reserved_', C.c_int32)]
+                ('rep_kind', C.c_int32), ('rep_param_stride', C.c_int32)]
 
 
 class AsacSacParams(C.Structure):
@@ -153,7 +153,7 @@ PROTOTYPES = {
     'asac_flat_reduce_adam': (i32, [vp, vp, vp, vp, i32, i64, i64, vp, vp, C.c_double, vp]),
     'asac_flat_polyak': (i32, [vp, vp, i64, vp, i32, f32, f32, i32, vp]),
     'asac_sac_step_networks_rep': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork),
-                                         P(AsacGruRep), i32, vp]),
+                                         P(AsacGruRep), i32, P(AsacPeerTable), vp]),
     'asac_sac_staged_tail': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp]),
     'asac_fill_normal': (i32, [vp, i64, u64, vp, i32, vp]),
     'asac_mlp_forward': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp]),

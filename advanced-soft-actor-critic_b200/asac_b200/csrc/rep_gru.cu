@@ -37,6 +37,27 @@ __host__ __device__ __forceinline__ int gru_weight_floats(const AsacGruShape &s)
     return (o + 3) & ~3;
 }
 
+// Cooperative global -> shared staging with U loads of every thread in flight before the first store
+// (the recurrent kernels start with a few thousand scattered floats; one load per loop trip would
+// serialise that many DRAM / L2 round trips): element i comes from load(i) and goes to dst[where(i)].
+template <int U, typename Load, typename Where>
+__device__ __forceinline__ void staged_fill(float *dst, int n, Load load, Where where) {
+    const int nt = blockDim.x;
+    for (int base = threadIdx.x; base < n; base += U * nt) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * nt;
+            v[u] = i < n ? load(i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * nt;
+            if (i < n) dst[where(i)] = v[u];
+        }
+    }
+}
+
 // flat parameters of every layer -> padded shared-memory rows (whole CTA)
 __device__ void gru_stage_weights(float *w_sm, const float *params, const AsacGruShape &s) {
     const int H = s.hidden;
@@ -45,31 +66,35 @@ __device__ void gru_stage_weights(float *w_sm, const float *params, const AsacGr
         const int in = gru_in(s, l), rs = gru_row_stride(s, l);
         const float *p = params + gru_layer_off(s, l);
         const int n_ih = 3 * H * in, n_hh = 3 * H * H;
-        for (int i = threadIdx.x; i < n_ih + n_hh + 6 * H; i += blockDim.x) {
-            int g, c;
-            if (i < n_ih) { g = i / in; c = i - g * in; }
-            else if (i < n_ih + n_hh) { const int j = i - n_ih; g = j / H; c = in + (j - g * H); }
-            else if (i < n_ih + n_hh + 3 * H) { g = i - n_ih - n_hh; c = in + H; }
-            else { g = i - n_ih - n_hh - 3 * H; c = in + H + 1; }
-            w_sm[base + g * rs + c] = __ldg(p + i);
-        }
+        staged_fill<8>(w_sm + base, n_ih + n_hh + 6 * H, [&](int i) { return __ldg(p + i); },
+                       [&](int i) {
+                           int g, c;
+                           if (i < n_ih) { g = i / in; c = i - g * in; }
+                           else if (i < n_ih + n_hh) { const int j = i - n_ih; g = j / H; c = in + (j - g * H); }
+                           else if (i < n_ih + n_hh + 3 * H) { g = i - n_ih - n_hh; c = in + H; }
+                           else { g = i - n_ih - n_hh - 3 * H; c = in + H + 1; }
+                           return g * rs + c;
+                       });
         base += 3 * H * rs;
     }
 }
 
-// x_t = [obs[b, t], pre_action[b, t]] for t < T into xs[T][in0] (one warp)
-__device__ __forceinline__ void gru_stage_inputs(float *xs, const float *obs, const float *actions, int bn_stride,
-                                                 const float *pre_actions, int64_t seq, int L, int T, int So, int A,
-                                                 int lane) {
-    const int in0 = So + A;
-    for (int i = lane; i < T * in0; i += 32) {
-        const int t = i / in0, c = i - t * in0;
-        float v;
-        if (c < So) v = obs[(seq * L + t) * So + c];
-        else if (pre_actions) v = pre_actions[(seq * L + t) * A + (c - So)];
-        else v = t > 0 ? actions[(seq * bn_stride + t - 1) * A + (c - So)] : 0.f;  // operators.py:39-59
-        xs[i] = v;
-    }
+// x_t = [obs[b, t], pre_action[b, t]] for t < T of the CTA's n_seq sequences (seq0 ...) into
+// region[w * region_stride + t * row_stride + c] (whole CTA); columns in0 .. row_stride - 1 are zeroed
+__device__ __forceinline__ void gru_stage_inputs(float *region, int region_stride, int row_stride, const float *obs,
+                                                 const float *actions, int bn_stride, const float *pre_actions,
+                                                 int64_t seq0, int n_seq, int L, int T, int So, int A) {
+    const int in0 = So + A, per = T * row_stride;
+    staged_fill<8>(region, n_seq * per,
+                   [&](int i) {
+                       const int w = i / per, r = i - w * per, t = r / row_stride, c = r - t * row_stride;
+                       const int64_t seq = seq0 + w;
+                       if (c >= in0) return 0.f;
+                       if (c < So) return obs[(seq * L + t) * So + c];
+                       if (pre_actions) return pre_actions[(seq * L + t) * A + (c - So)];
+                       return t > 0 ? actions[(seq * bn_stride + t - 1) * A + (c - So)] : 0.f;  // operators.py:39-59
+                   },
+                   [&](int i) { const int w = i / per; return w * region_stride + (i - w * per); });
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -84,8 +109,130 @@ struct GruFwdArgs {
 
 constexpr int GRU_FWD_WARPS = 2;
 
+// per-warp shared memory of the forward kernel: inputs xs[L][in0], layer 0's input projection
+// gi0[L][3H], current hidden states h[layers][H], gate scratch [4H] (sequential path only)
 __host__ __device__ __forceinline__ int gru_fwd_warp_floats(const AsacGruShape &s, int L) {
-    return ((L * (s.obs_size + s.action_size) + s.layers * s.hidden + 4 * s.hidden) + 3) & ~3;
+    return L * ((s.obs_size + s.action_size + 3) & ~3) + ((L * 3 * s.hidden + 3) & ~3) +
+           ((s.layers * s.hidden + 3) & ~3) + 4 * s.hidden;
+}
+
+// One GRU cell for hidden unit j of a layer whose three gate rows start at wr / wz / wn (shared
+// memory, [W_ih row | W_hh row | b_ih | b_hh]).  gi != nullptr: the input projection (bias included)
+// was computed up front (layer 0); otherwise xin is the layer below's output of this step.
+struct GruCellOut {
+    float r, z, n, ghn, h;
+};
+__device__ __forceinline__ GruCellOut gru_cell(const float *wr, const float *wz, const float *wn, int in, int H,
+                                               const float *gi, const float *xin, const float *hp, int j) {
+    float ir, iz, inn;
+    if (gi) {
+        ir = gi[j]; iz = gi[H + j]; inn = gi[2 * H + j];
+    } else {
+        ir = wr[in + H]; iz = wz[in + H]; inn = wn[in + H];
+#pragma unroll 4
+        for (int k = 0; k < in; ++k) {
+            const float xv = xin[k];
+            ir = fmaf(wr[k], xv, ir); iz = fmaf(wz[k], xv, iz); inn = fmaf(wn[k], xv, inn);
+        }
+    }
+    float hr = wr[in + H + 1], hz = wz[in + H + 1], hn = wn[in + H + 1];
+#pragma unroll 4
+    for (int k = 0; k < H; ++k) {
+        const float hv = hp[k];
+        hr = fmaf(wr[in + k], hv, hr); hz = fmaf(wz[in + k], hv, hz); hn = fmaf(wn[in + k], hv, hn);
+    }
+    GruCellOut o;
+    o.r = sigmoidf_(hr + ir);
+    o.z = sigmoidf_(hz + iz);
+    o.ghn = hn;
+    o.n = tanhf(inn + hn * o.r);
+    o.h = (hp[j] - o.n) * o.z + o.n;
+    return o;
+}
+
+// Wavefront forward with the lane's weights in REGISTERS (widths 8 / 16 / 32): lane (l, j) owns unit j of
+// layer l and keeps its three W_hh rows (and, above layer 0, its three W_ih rows) in registers; at stage
+// st layer l runs step st - l.  Per stage a lane issues 2 x H/4 vector loads of the hidden vectors,
+// 6H FMAs in six independent chains and the three activations: no weight traffic, no gate exchange,
+// L + layers - 1 stages instead of L x layers dependent cells.  Lanes of layer 0 take their input
+// projection from gi0 (computed for every step up front) and multiply the layer-below vector by
+// zeros, so the warp does not diverge.
+template <int H, bool MULTI>
+__device__ __forceinline__ void gru_wave_forward(const AsacGruShape &s, const AsacGruNet &net, const float *w_sm,
+                                                 const float *gi0, const float *xs, int in0p, bool inloop, float *hbuf,
+                                                 int64_t seq, int L, int lane) {
+    const int NL = s.layers;
+    const int l = lane / H, j = lane - l * H;
+    const bool valid = lane < NL * H;
+    const int lc = valid ? l : 0;
+    int wbase = 0;
+    for (int i = 0; i < lc; ++i) wbase += 3 * H * gru_row_stride(s, i);
+    const int in = gru_in(s, lc), rs = gru_row_stride(s, lc);
+    const float *wr = w_sm + wbase + j * rs, *wz = wr + H * rs, *wn = wz + H * rs;
+    float whh[3][H], wih[MULTI ? 3 : 1][MULTI ? H : 1];
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        whh[0][k] = wr[in + k]; whh[1][k] = wz[in + k]; whh[2][k] = wn[in + k];
+        if (MULTI) {
+            // layer 0 (inloop: its inputs fit in H columns): W_ih rows zero-padded to H; else zeros (gi0 is used)
+            const bool has = lc > 0 ? true : (inloop && k < in);
+            wih[0][k] = has ? wr[k] : 0.f; wih[1][k] = has ? wz[k] : 0.f; wih[2][k] = has ? wn[k] : 0.f;
+        }
+    }
+    const float bir = wr[in + H], biz = wz[in + H], bin = wn[in + H];
+    const float bhr = wr[in + H + 1], bhz = wz[in + H + 1], bhn = wn[in + H + 1];
+    const float4 *hp4 = reinterpret_cast<const float4 *>(hbuf + lc * H);
+    const float4 *xp4 = reinterpret_cast<const float4 *>(hbuf + (lc > 0 ? lc - 1 : 0) * H);
+    float *hself = hbuf + lc * H + j;
+    // layer-0 lanes with inloop read x_t (row stride in0p <= H, zero padded) where the others read the layer below
+    const int nx4 = (MULTI && lc == 0 && inloop) ? in0p / 4 : H / 4;
+#pragma unroll 1
+    for (int st = 0; st < L + NL - 1; ++st) {
+        const int t = st - l;
+        const bool active = valid && t >= 0 && t < L;
+        const int tc = min(max(t, 0), L - 1);
+        const float *gi = gi0 + tc * 3 * H;
+        const bool pre = lc == 0 && !inloop;  // input projection taken from the up-front pass
+        float ir = pre ? gi[j] : bir, iz = pre ? gi[H + j] : biz, inn = pre ? gi[2 * H + j] : bin;
+        if (MULTI && lc == 0) xp4 = reinterpret_cast<const float4 *>(inloop ? xs + tc * in0p : hbuf);
+        float hr = bhr, hz = bhz, hn = bhn;
+#pragma unroll
+        for (int k4 = 0; k4 < H / 4; ++k4) {
+            const float4 hv = hp4[k4];
+            const float h_[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                hr = fmaf(whh[0][k4 * 4 + c], h_[c], hr);
+                hz = fmaf(whh[1][k4 * 4 + c], h_[c], hz);
+                hn = fmaf(whh[2][k4 * 4 + c], h_[c], hn);
+            }
+            if (MULTI) {
+                const float4 xv = k4 < nx4 ? xp4[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float x_[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    ir = fmaf(wih[0][k4 * 4 + c], x_[c], ir);
+                    iz = fmaf(wih[1][k4 * 4 + c], x_[c], iz);
+                    inn = fmaf(wih[2][k4 * 4 + c], x_[c], inn);
+                }
+            }
+        }
+        const float r = __frcp_rn(1.f + expf(-(hr + ir))), z = __frcp_rn(1.f + expf(-(hz + iz)));
+        const float n = tanhf(inn + hn * r);
+        const float hnew = (*hself - n) * z + n;
+        __syncwarp();
+        if (active) {
+            *hself = hnew;
+            const int64_t cell = (seq * L + t) * NL + l;
+            if (net.hn) net.hn[cell * H + j] = hnew;
+            if (net.save) {
+                float *sv = net.save + cell * 4 * H;
+                sv[j] = r; sv[H + j] = z; sv[2 * H + j] = n; sv[3 * H + j] = hn;
+            }
+            if (l == NL - 1) net.states[(seq * L + t) * H + j] = hnew;
+        }
+        __syncwarp();
+    }
 }
 
 // grid (ceil(B / GRU_FWD_WARPS), n_nets)
@@ -100,47 +247,96 @@ __global__ void __launch_bounds__(GRU_FWD_WARPS * 32) k_gru_forward(const __grid
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t seq = (int64_t)blockIdx.x * GRU_FWD_WARPS + wid;
     float *xs = sm + gru_weight_floats(s) + wid * gru_fwd_warp_floats(s, L);
-    float *hbuf = xs + L * in0, *gates = hbuf + NL * H;
-    if (seq < a.batch) {
-        gru_stage_inputs(xs, a.obs, a.actions, a.bn_stride, a.pre_actions, seq, L, L, s.obs_size, s.action_size, lane);
-        for (int i = lane; i < NL * H; i += 32) hbuf[i] = a.h0 ? a.h0[seq * a.h0_b_stride + i] : 0.f;
+    const int in0p = (in0 + 3) & ~3;  // row stride of the staged inputs (zero padded)
+    float *gi0 = xs + L * in0p, *hbuf = gi0 + ((L * 3 * H + 3) & ~3);  // 16-byte aligned regions
+    // widths 8 / 16 with inputs no wider than the GRU: layer 0's lanes multiply x_t inside the stage loop
+    const bool inloop = NL * H <= 32 && (H == 8 || H == 16) && in0p <= H;
+    {
+        const int64_t seq0 = (int64_t)blockIdx.x * GRU_FWD_WARPS;
+        const int n_seq = (int)min((int64_t)GRU_FWD_WARPS, a.batch - seq0), wf = gru_fwd_warp_floats(s, L);
+        float *first = sm + gru_weight_floats(s);
+        gru_stage_inputs(first, wf, in0p, a.obs, a.actions, a.bn_stride, a.pre_actions, seq0, n_seq, L, L, s.obs_size,
+                         s.action_size);
+        const int hoff = (int)(hbuf - xs), nh = NL * H;
+        staged_fill<2>(first + hoff, n_seq * nh,
+                       [&](int i) { const int w = i / nh; return a.h0 ? a.h0[(seq0 + w) * a.h0_b_stride + (i - w * nh)] : 0.f; },
+                       [&](int i) { const int w = i / nh; return w * wf + (i - w * nh); });
     }
     __syncthreads();
     if (seq >= a.batch) return;
+    // layer 0's input projection W_ih x_t + b_ih of EVERY step, off the recurrent chain
+    if (!inloop) {
+        const int rs0 = gru_row_stride(s, 0);
+        for (int idx = lane; idx < L * 3 * H; idx += 32) {
+            const int t = idx / (3 * H), g = idx - t * 3 * H;
+            const float *wr = w_sm + g * rs0, *x = xs + t * in0p;
+            float acc = wr[in0 + H];
+#pragma unroll 4
+            for (int k = 0; k < in0; ++k) acc = fmaf(wr[k], x[k], acc);
+            gi0[idx] = acc;
+        }
+    }
+    __syncwarp();
+    if (NL * H <= 32 && (H == 8 || H == 16 || H == 32)) {
+        if (H == 8) gru_wave_forward<8, true>(s, net, w_sm, gi0, xs, in0p, inloop, hbuf, seq, L, lane);
+        else if (H == 16) gru_wave_forward<16, true>(s, net, w_sm, gi0, xs, in0p, inloop, hbuf, seq, L, lane);
+        else gru_wave_forward<32, false>(s, net, w_sm, gi0, xs, in0p, false, hbuf, seq, L, lane);
+        return;
+    }
+    if (NL * H <= 32) {
+        // wavefront: lane (l, j) owns unit j of layer l; at stage s layer l runs step s - l, reading the
+        // layer below's output of that step (written one stage earlier) -> L + layers - 1 stages
+        // instead of L x layers dependent cells, no gate exchange between lanes
+        const int l = lane / H, j = lane - l * H;
+        const bool valid = lane < NL * H;
+        int wbase = 0;
+        for (int i = 0; i < l && valid; ++i) wbase += 3 * H * gru_row_stride(s, i);
+        const int in = valid ? gru_in(s, l) : 0, rs = valid ? gru_row_stride(s, l) : 0;
+        const float *wr = w_sm + wbase + j * rs, *wz = wr + H * rs, *wn = wz + H * rs;
+#pragma unroll 1
+        for (int st = 0; st < L + NL - 1; ++st) {
+            const int t = st - l;
+            const bool active = valid && t >= 0 && t < L;
+            GruCellOut o;
+            if (active)
+                o = gru_cell(wr, wz, wn, in, H, l == 0 ? gi0 + t * 3 * H : nullptr, hbuf + (l - 1) * H, hbuf + l * H, j);
+            __syncwarp();
+            if (active) {
+                hbuf[l * H + j] = o.h;
+                const int64_t cell = (seq * L + t) * NL + l;
+                if (net.hn) net.hn[cell * H + j] = o.h;
+                if (net.save) {
+                    float *sv = net.save + cell * 4 * H;
+                    sv[j] = o.r; sv[H + j] = o.z; sv[2 * H + j] = o.n; sv[3 * H + j] = o.ghn;
+                }
+                if (l == NL - 1) net.states[(seq * L + t) * H + j] = o.h;
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    // wide / deep GRUs: layers one after the other, a lane owns units lane, lane + 32
 #pragma unroll 1
     for (int t = 0; t < L; ++t) {
         int wbase = 0;
 #pragma unroll 1
         for (int l = 0; l < NL; ++l) {
             const int in = gru_in(s, l), rs = gru_row_stride(s, l);
-            const float *x = l == 0 ? xs + t * in0 : hbuf + (l - 1) * H;  // layer l-1's output of this step
-            float *hp = hbuf + l * H;
-            for (int g = lane; g < 3 * H; g += 32) {
-                const float *wr = w_sm + wbase + g * rs;
-                float gi = wr[in + H], gh = wr[in + H + 1];
-                for (int k = 0; k < in; ++k) gi = fmaf(wr[k], x[k], gi);
-                for (int k = 0; k < H; ++k) gh = fmaf(wr[in + k], hp[k], gh);
-                if (g < 2 * H) {
-                    gates[g] = gh + gi;
-                } else {
-                    gates[g] = gi;
-                    gates[g + H] = gh;
-                }
+            GruCellOut o[2];
+            for (int u = 0, j = lane; j < H; ++u, j += 32) {
+                const float *wr = w_sm + wbase + j * rs, *wz = wr + H * rs, *wn = wz + H * rs;
+                o[u] = gru_cell(wr, wz, wn, in, H, l == 0 ? gi0 + t * 3 * H : nullptr, hbuf + (l - 1) * H, hbuf + l * H, j);
             }
             __syncwarp();
-            for (int j = lane; j < H; j += 32) {
-                const float r = sigmoidf_(gates[j]), z = sigmoidf_(gates[H + j]);
-                const float ghn = gates[3 * H + j];
-                const float n = tanhf(gates[2 * H + j] + ghn * r);
-                const float hnew = (hp[j] - n) * z + n;
-                hp[j] = hnew;
+            for (int u = 0, j = lane; j < H; ++u, j += 32) {
+                hbuf[l * H + j] = o[u].h;
                 const int64_t cell = (seq * L + t) * NL + l;
-                if (net.hn) net.hn[cell * H + j] = hnew;
+                if (net.hn) net.hn[cell * H + j] = o[u].h;
                 if (net.save) {
                     float *sv = net.save + cell * 4 * H;
-                    sv[j] = r; sv[H + j] = z; sv[2 * H + j] = n; sv[3 * H + j] = ghn;
+                    sv[j] = o[u].r; sv[H + j] = o[u].z; sv[2 * H + j] = o[u].n; sv[3 * H + j] = o[u].ghn;
                 }
-                if (l == NL - 1) net.states[(seq * L + t) * H + j] = hnew;
+                if (l == NL - 1) net.states[(seq * L + t) * H + j] = o[u].h;
             }
             __syncwarp();
             wbase += 3 * H * rs;
@@ -160,25 +356,96 @@ constexpr int GRU_BWD_THREADS = 256;
 
 // per-sequence shared memory of the backward kernel (floats); T1 = t_grad + 1 steps carry gradient
 struct GruBwdPlan {
-    int off_xs, off_hn, off_h0, off_sv, off_dg, off_dh, off_dhd, total;
+    int off_xs, off_hn, off_h0, off_sv, off_dg, off_dh, off_dhd, off_dx, total;
 };
 __host__ __device__ __forceinline__ GruBwdPlan gru_bwd_plan(const AsacGruShape &s, int T1) {
     GruBwdPlan p;
     const int H = s.hidden, NL = s.layers;
     int o = 0;
-    p.off_xs = o; o += T1 * (s.obs_size + s.action_size);
-    p.off_hn = o; o += T1 * NL * H;
-    p.off_h0 = o; o += NL * H;
-    p.off_sv = o; o += T1 * NL * 4 * H;
-    p.off_dg = o; o += T1 * NL * 4 * H;
-    p.off_dh = o; o += NL * H;
-    p.off_dhd = o; o += H;
-    p.total = (o + 3) & ~3;
+    auto take = [&o](int n) { const int at = o; o += (n + 3) & ~3; return at; };  // 16-byte aligned regions
+    p.off_xs = take(T1 * (s.obs_size + s.action_size));
+    p.off_hn = take(T1 * NL * H);
+    p.off_h0 = take(NL * H);
+    p.off_sv = take(T1 * NL * 4 * H);
+    p.off_dg = take(T1 * NL * 4 * H);
+    p.off_dh = take(NL * H);
+    p.off_dhd = take(NL * H);
+    p.off_dx = take(NL * H);
+    p.total = o;
     return p;
 }
 
+// Wavefront BPTT with the lane's weight COLUMNS in registers (see gru_wave_forward): lane (l, j) keeps
+// W_hh[:, j] and (above layer 0) W_ih[:, j]; per stage it turns its unit's output gradient into the
+// four gate gradients (shared memory, kept for the weight-gradient phase), then reads the layer's
+// 4H gate gradients back as vectors and forms d h_{t-1}[j] and the input gradient for the layer below.
+template <int H, bool MULTI>
+__device__ __forceinline__ void gru_wave_backward(const AsacGruShape &s, const float *w_sm, float *me,
+                                                  const GruBwdPlan &pl, int T1, int lane) {
+    const int NL = s.layers;
+    float *dh = me + pl.off_dh, *dhd = me + pl.off_dhd, *dx = me + pl.off_dx;
+    const int l = lane / H, j = lane - l * H;
+    const bool valid = lane < NL * H;
+    const int lc = valid ? l : 0;
+    int wbase = 0;
+    for (int i = 0; i < lc; ++i) wbase += 3 * H * gru_row_stride(s, i);
+    const int in = gru_in(s, lc), rs = gru_row_stride(s, lc);
+    const float *wcol = w_sm + wbase;
+    float chh[3 * H], cih[MULTI ? 3 * H : 1];
+#pragma unroll
+    for (int g = 0; g < 3 * H; ++g) {
+        chh[g] = wcol[g * rs + in + j];
+        if (MULTI) cih[g] = lc > 0 ? wcol[g * rs + j] : 0.f;
+    }
+#pragma unroll 1
+    for (int st = 0; st < T1 + NL - 1; ++st) {
+        const int t = (T1 - 1) - (st - (NL - 1 - l));
+        const bool active = valid && t >= 0 && t <= T1 - 1;
+        const int tc = min(max(t, 0), T1 - 1);
+        float *dg = me + pl.off_dg + (tc * NL + lc) * 4 * H;
+        if (active) {
+            const float *sv = me + pl.off_sv + (t * NL + l) * 4 * H;
+            const float hprev = t > 0 ? me[pl.off_hn + ((t - 1) * NL + l) * H + j] : me[pl.off_h0 + l * H + j];
+            const float r = sv[j], z = sv[H + j], n = sv[2 * H + j], ghn = sv[3 * H + j];
+            const float d = dh[l * H + j] + dx[l * H + j];
+            const float dz = d * (hprev - n), dn = d * (1.f - z);
+            const float dan = dn * (1.f - n * n);
+            const float dr = dan * ghn;
+            dg[j] = dr * (r * (1.f - r));
+            dg[H + j] = dz * (z * (1.f - z));
+            dg[2 * H + j] = dan;
+            dg[3 * H + j] = dan * r;
+            dhd[l * H + j] = d * z;
+        }
+        __syncwarp();
+        float sh = dhd[lc * H + j], sx = 0.f;
+        const float4 *dg4 = reinterpret_cast<const float4 *>(dg);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {        // gate blocks: d a_r, d a_z, d (W_in x), d (W_hn h)
+#pragma unroll
+            for (int k4 = 0; k4 < H / 4; ++k4) {
+                const float4 v = dg4[q * (H / 4) + k4];
+                const float v_[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int u = k4 * 4 + c;
+                    if (q < 2) sh = fmaf(chh[q * H + u], v_[c], sh);
+                    if (q == 3) sh = fmaf(chh[2 * H + u], v_[c], sh);
+                    if (MULTI && q < 3) sx = fmaf(cih[q * H + u], v_[c], sx);
+                }
+            }
+        }
+        __syncwarp();
+        if (active) {
+            dh[l * H + j] = sh;
+            if (MULTI && l > 0) dx[(l - 1) * H + j] = sx;
+        }
+        __syncwarp();
+    }
+}
+
 // grid ceil(B / tile); warp w < tile runs the BPTT of sequence blockIdx.x * tile + w, then the whole CTA
-// turns the stored gate gradients into this tile's partial weight gradients.
+// turns the stored gate gradients into one partial weight gradient per sequence.
 __global__ void __launch_bounds__(GRU_BWD_THREADS) k_gru_backward(const __grid_constant__ GruBwdArgs a) {
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
@@ -191,23 +458,89 @@ __global__ void __launch_bounds__(GRU_BWD_THREADS) k_gru_backward(const __grid_c
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t seq0 = (int64_t)blockIdx.x * a.tile;
     const int n_seq = (int)min((int64_t)a.tile, a.batch - seq0);
+    {   // the tile's sequences: inputs, hidden states and gates of the first t_grad + 1 steps (whole CTA)
+        gru_stage_inputs(seq_sm + pl.off_xs, pl.total, in0, a.obs, a.actions, a.bn_stride, a.pre_actions, seq0, n_seq, L, T1,
+                         s.obs_size, s.action_size);
+        const int n_hn = T1 * NL * H, n_sv = T1 * NL * 4 * H, n_h0 = NL * H;
+        staged_fill<8>(seq_sm + pl.off_hn, n_seq * n_hn,
+                       [&](int i) { const int w = i / n_hn; return a.hn[(seq0 + w) * L * NL * H + (i - w * n_hn)]; },
+                       [&](int i) { const int w = i / n_hn; return w * pl.total + (i - w * n_hn); });
+        staged_fill<8>(seq_sm + pl.off_sv, n_seq * n_sv,
+                       [&](int i) { const int w = i / n_sv; return a.save[(seq0 + w) * L * NL * 4 * H + (i - w * n_sv)]; },
+                       [&](int i) { const int w = i / n_sv; return w * pl.total + (i - w * n_sv); });
+        staged_fill<2>(seq_sm + pl.off_h0, n_seq * n_h0,
+                       [&](int i) { const int w = i / n_h0; return a.h0 ? a.h0[(seq0 + w) * a.h0_b_stride + (i - w * n_h0)] : 0.f; },
+                       [&](int i) { const int w = i / n_h0; return w * pl.total + (i - w * n_h0); });
+    }
     if (wid < n_seq) {
         const int64_t seq = seq0 + wid;
         float *me = seq_sm + wid * pl.total;
-        gru_stage_inputs(me + pl.off_xs, a.obs, a.actions, a.bn_stride, a.pre_actions, seq, L, T1, s.obs_size,
-                         s.action_size, lane);
-        for (int i = lane; i < T1 * NL * H; i += 32) me[pl.off_hn + i] = a.hn[seq * L * NL * H + i];
-        for (int i = lane; i < NL * H; i += 32) me[pl.off_h0 + i] = a.h0 ? a.h0[seq * a.h0_b_stride + i] : 0.f;
-        for (int i = lane; i < T1 * NL * 4 * H; i += 32) me[pl.off_sv + i] = a.save[seq * L * NL * 4 * H + i];
         for (int i = lane; i < NL * H; i += 32) {
             float g = 0.f;
             if (i >= (NL - 1) * H)  // d loss / d state[:, t_grad], summed over the critics in member order
                 for (int e = 0; e < a.ensemble; ++e) g += a.grad_state[((int64_t)e * a.batch + seq) * H + (i - (NL - 1) * H)];
             me[pl.off_dh + i] = g;
+            me[pl.off_dx + i] = 0.f;
         }
     }
     __syncthreads();
-    if (wid < n_seq) {
+    if (wid < n_seq && NL * H <= 32 && (H == 8 || H == 16 || H == 32)) {
+        float *me = seq_sm + wid * pl.total;
+        if (H == 8) gru_wave_backward<8, true>(s, w_sm, me, pl, T1, lane);
+        else if (H == 16) gru_wave_backward<16, true>(s, w_sm, me, pl, T1, lane);
+        else gru_wave_backward<32, false>(s, w_sm, me, pl, T1, lane);
+    } else if (wid < n_seq && NL * H <= 32) {
+        // wavefront over (layer, step): lane (l, j); the top layer leads, layer l runs step t one stage
+        // after layer l + 1 has produced its input gradient for that step.  d h_t^l = recurrent part
+        // (dh, from cell (l, t+1)) + input gradient of the layer above (dx, from cell (l+1, t)).
+        float *me = seq_sm + wid * pl.total;
+        float *dh = me + pl.off_dh, *dhd = me + pl.off_dhd, *dx = me + pl.off_dx;
+        const int l = lane / H, j = lane - l * H;
+        const bool valid = lane < NL * H;
+        int wbase = 0;
+        for (int i = 0; i < l && valid; ++i) wbase += 3 * H * gru_row_stride(s, i);
+        const int in = valid ? gru_in(s, l) : 0, rs = valid ? gru_row_stride(s, l) : 1;
+        const float *wcol = w_sm + wbase;
+#pragma unroll 1
+        for (int st = 0; st < T1 + NL - 1; ++st) {
+            const int t = (T1 - 1) - (st - (NL - 1 - l));
+            const bool active = valid && t >= 0 && t <= T1 - 1;
+            float *dg = me + pl.off_dg + (t * NL + l) * 4 * H;
+            if (active) {
+                const float *sv = me + pl.off_sv + (t * NL + l) * 4 * H;
+                const float hprev = t > 0 ? me[pl.off_hn + ((t - 1) * NL + l) * H + j] : me[pl.off_h0 + l * H + j];
+                const float r = sv[j], z = sv[H + j], n = sv[2 * H + j], ghn = sv[3 * H + j];
+                const float d = dh[l * H + j] + dx[l * H + j];
+                const float dz = d * (hprev - n), dn = d * (1.f - z);
+                const float dan = dn * (1.f - n * n);
+                const float dr = dan * ghn;
+                dg[j] = dr * (r * (1.f - r));
+                dg[H + j] = dz * (z * (1.f - z));
+                dg[2 * H + j] = dan;
+                dg[3 * H + j] = dan * r;
+                dhd[l * H + j] = d * z;
+            }
+            __syncwarp();
+            float sh = 0.f, sx = 0.f;
+            if (active) {
+                sh = dhd[l * H + j];
+#pragma unroll 4
+                for (int g = 0; g < 2 * H; ++g) sh = fmaf(wcol[g * rs + in + j], dg[g], sh);
+#pragma unroll 4
+                for (int g = 2 * H; g < 3 * H; ++g) sh = fmaf(wcol[g * rs + in + j], dg[g + H], sh);
+                if (l > 0) {
+#pragma unroll 4
+                    for (int g = 0; g < 3 * H; ++g) sx = fmaf(wcol[g * rs + j], dg[g], sx);
+                }
+            }
+            __syncwarp();
+            if (active) {
+                dh[l * H + j] = sh;
+                if (l > 0) dx[(l - 1) * H + j] = sx;
+            }
+            __syncwarp();
+        }
+    } else if (wid < n_seq) {
         float *me = seq_sm + wid * pl.total;
         float *dh = me + pl.off_dh, *dhd = me + pl.off_dhd;
 #pragma unroll 1
@@ -252,32 +585,47 @@ __global__ void __launch_bounds__(GRU_BWD_THREADS) k_gru_backward(const __grid_c
         }
     }
     __syncthreads();
-    // ---- partial weight gradients of this tile: sum over its sequences and steps, in that order
-    float *gout = a.grad_part + (int64_t)blockIdx.x * a.part_stride;
-    for (int l = 0; l < NL; ++l) {
-        const int in = gru_in(s, l);
-        const int n_ih = 3 * H * in, n_hh = 3 * H * H;
-        float *gl = gout + gru_layer_off(s, l);
-        for (int i = threadIdx.x; i < n_ih + n_hh + 6 * H; i += blockDim.x) {
-            int g, c, kind;  // kind 0: W_ih, 1: W_hh, 2: b_ih, 3: b_hh
-            if (i < n_ih) { g = i / in; c = i - g * in; kind = 0; }
-            else if (i < n_ih + n_hh) { const int j = i - n_ih; g = j / H; c = j - g * H; kind = 1; }
-            else if (i < n_ih + n_hh + 3 * H) { g = i - n_ih - n_hh; c = 0; kind = 2; }
-            else { g = i - n_ih - n_hh - 3 * H; c = 0; kind = 3; }
-            const bool hh = (kind & 1) != 0;
-            const int gi = (hh && g >= 2 * H) ? g + H : g;  // W_hh / b_hh see d(W_hn h + b_hn) for the n gate
-            float acc = 0.f;
-            for (int w = 0; w < n_seq; ++w) {
-                const float *me = seq_sm + w * pl.total;
-                for (int t = 0; t < T1; ++t) {
-                    const float d = me[pl.off_dg + (t * NL + l) * 4 * H + gi];
-                    float v = 1.f;
-                    if (kind == 0) v = l == 0 ? me[pl.off_xs + t * in0 + c] : me[pl.off_hn + (t * NL + l - 1) * H + c];
-                    else if (kind == 1) v = t > 0 ? me[pl.off_hn + ((t - 1) * NL + l) * H + c] : me[pl.off_h0 + l * H + c];
-                    acc = fmaf(d, v, acc);
-                }
+    // ---- partial weight gradients, one row of grad_part per SEQUENCE (summed in sequence order by the
+    // reduce + Adam kernel).  A work item is (sequence, layer, W_ih | W_hh, gate row, chunk of 8 columns):
+    // the gate gradient of a step is read once for 8 FMAs, and the row's bias gradient rides along.
+    {
+        constexpr int CH = 8;
+        int per_seq = 0;
+        for (int l = 0; l < NL; ++l) per_seq += 3 * H * ((gru_in(s, l) + CH - 1) / CH + (H + CH - 1) / CH);
+        for (int item = threadIdx.x; item < n_seq * per_seq; item += blockDim.x) {
+            const int w = item / per_seq;
+            int r = item - w * per_seq, l = 0;
+            for (;; ++l) {
+                const int n_l = 3 * H * ((gru_in(s, l) + CH - 1) / CH + (H + CH - 1) / CH);
+                if (r < n_l) break;
+                r -= n_l;
             }
-            gl[i] = acc;
+            const int in = gru_in(s, l), c_ih = (in + CH - 1) / CH, c_hh = (H + CH - 1) / CH;
+            const bool hh = r >= 3 * H * c_ih;
+            if (hh) r -= 3 * H * c_ih;
+            const int nch = hh ? c_hh : c_ih, g = r / nch, c0 = (r - g * nch) * CH;
+            const int K = hh ? H : in, nc = min(CH, K - c0);
+            const int gi = (hh && g >= 2 * H) ? g + H : g;  // W_hh / b_hh see d(W_hn h + b_hn) for the n gate
+            const float *me = seq_sm + w * pl.total;
+            float acc[CH], accb = 0.f;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+#pragma unroll 2
+            for (int t = 0; t < T1; ++t) {
+                const float d = me[pl.off_dg + (t * NL + l) * 4 * H + gi];
+                const float *v = !hh ? (l == 0 ? me + pl.off_xs + t * in0 : me + pl.off_hn + (t * NL + l - 1) * H)
+                                     : (t > 0 ? me + pl.off_hn + ((t - 1) * NL + l) * H : me + pl.off_h0 + l * H);
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                    if (c < nc) acc[c] = fmaf(d, v[c0 + c], acc[c]);
+                accb += d;
+            }
+            float *gl = a.grad_part + (seq0 + w) * a.part_stride + gru_layer_off(s, l);
+            float *gw = gl + (hh ? 3 * H * in + g * H : g * in) + c0;
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                if (c < nc) gw[c] = acc[c];
+            if (c0 == 0) gl[3 * H * in + 3 * H * H + (hh ? 3 * H : 0) + g] = accb;
         }
     }
 }

@@ -1460,8 +1460,8 @@ static int make_exchange(PeerExchange &x, const AsacSacConfig *cfg, const AsacPe
                  "peer table: world %d / rank %d", peers->world, peers->rank);
     const int64_t nq = net_stride(q_shape(*cfg)) * cfg->ensemble, np = net_stride(pi_shape(*cfg));
     x.world = peers->world; x.rank = peers->rank;
-    x.total = nq + np + 4;
-    x.off = which == 0 ? 0 : (which == 1 ? nq : nq + np);
+    x.total = nq + np + 4 + cfg->rep_param_stride;
+    x.off = which == 0 ? 0 : (which == 1 ? nq : (which == 2 ? nq + np : nq + np + 4));  // 3: representation
     ASAC_REQUIRE(peers->recv_words >= 2 * (int64_t)peers->world * x.total,
                  "peer table: receive buffers hold %lld words, need %lld", (long long)peers->recv_words,
                  (long long)(2 * (int64_t)peers->world * x.total));
@@ -1474,7 +1474,8 @@ static int make_exchange(PeerExchange &x, const AsacSacConfig *cfg, const AsacPe
 
 extern "C" int64_t asac_peer_recv_words(const AsacSacConfig *cfg, int world) {
     if (validate(cfg) != ASAC_OK) return -1;
-    return 2 * (int64_t)world * (net_stride(q_shape(*cfg)) * cfg->ensemble + net_stride(pi_shape(*cfg)) + 4);
+    return 2 * (int64_t)world *
+           (net_stride(q_shape(*cfg)) * cfg->ensemble + net_stride(pi_shape(*cfg)) + 4 + cfg->rep_param_stride);
 }
 
 static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk, int which,
@@ -1577,20 +1578,27 @@ extern "C" int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacPar
     return ASAC_OK;
 }
 
-extern "C" int asac_flat_reduce_adam(float *param, float *m, float *v, const float *grad_part, int n_tiles,
-                                     int64_t tile_stride, int64_t count, float *grad, const int64_t *step_counter,
-                                     double learning_rate, void *stream) {
+static int flat_reduce_adam(float *param, float *m, float *v, const float *grad_part, int n_tiles, int64_t tile_stride,
+                            int64_t count, float *grad, const int64_t *step_counter, double learning_rate,
+                            const PeerExchange *px, float grad_scale, void *stream) {
     ASAC_REQUIRE(param && m && v && grad_part && grad && step_counter && n_tiles > 0 && count > 0,
                  "asac_flat_reduce_adam: bad arguments");
     AdamArgs a;
-    memset(&a.px, 0, sizeof(a.px));
+    if (px) a.px = *px; else memset(&a.px, 0, sizeof(a.px));
     a.param = param; a.m = m; a.v = v; a.part = grad_part; a.grad = grad; a.step = step_counter;
     a.count = count; a.tile_stride = tile_stride; a.n_tiles = n_tiles;
-    a.write_grad = 1; a.do_adam = 1; a.grad_scale = 1.f; a.lr = learning_rate;
+    a.write_grad = 1; a.do_adam = 1; a.grad_scale = grad_scale; a.lr = learning_rate;
     ASAC_CUDA(launch_ex(k_reduce_adam, dim3((unsigned)((count + ADAM_PARAMS_PER_CTA - 1) / ADAM_PARAMS_PER_CTA)),
                         dim3(ADAM_PARAMS_PER_CTA * ADAM_TILE_GROUPS), 0, (cudaStream_t)stream, 0, true, a));
     ASAC_LAUNCHED("k_reduce_adam");
     return ASAC_OK;
+}
+
+extern "C" int asac_flat_reduce_adam(float *param, float *m, float *v, const float *grad_part, int n_tiles,
+                                     int64_t tile_stride, int64_t count, float *grad, const int64_t *step_counter,
+                                     double learning_rate, void *stream) {
+    return flat_reduce_adam(param, m, v, grad_part, n_tiles, tile_stride, count, grad, step_counter, learning_rate,
+                            nullptr, 1.f, stream);
 }
 
 extern "C" int asac_flat_polyak(float *target, const float *source, int64_t count, const int64_t *counters,
@@ -1604,7 +1612,8 @@ extern "C" int asac_flat_polyak(float *target, const float *source, int64_t coun
 
 extern "C" int asac_sac_step_networks_rep(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
                                           const AsacSacWork *wrk, const AsacGruRep *rep, int with_polyak,
-                                          void *stream) {
+                                          const AsacPeerTable *peers, void *stream) {
+    const float gscale = (peers && peers->world > 1) ? 1.f / (float)peers->world : 1.f;
     SacArgs a;
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
@@ -1620,9 +1629,13 @@ extern "C" int asac_sac_step_networks_rep(const AsacSacConfig *cfg, const AsacSa
                      rep->save && rep->grad_part && rep->grad, "asac_sac_step_networks_rep: null pointer in rep");
     const int tile = asac_gru_backward_tile(&rep->shape, cfg->burn_in);
     if (tile < 1) return tile;
-    ASAC_REQUIRE(rep->rep_tiles == (cfg->batch + tile - 1) / tile, "rep.rep_tiles %d != ceil(B / %d)", rep->rep_tiles, tile);
+    ASAC_REQUIRE(rep->rep_tiles == cfg->batch, "rep.rep_tiles %d != batch %d", rep->rep_tiles, cfg->batch);
     const int64_t P = asac_gru_param_count(&rep->shape), Ps = (P + 3) / 4 * 4;
     const int B = cfg->batch, L = cfg->seq_len;
+    PeerExchange px_rep;
+    ASAC_REQUIRE(!(peers && peers->world > 1) || cfg->rep_param_stride == Ps,
+                 "cfg.rep_param_stride %d != the representation's gradient stride %lld", cfg->rep_param_stride, (long long)Ps);
+    if ((rc = make_exchange(px_rep, cfg, peers, 3)) != ASAC_OK) return rc;
     if (with_polyak) {
         if ((rc = asac_sac_polyak(cfg, prm, -1.f, stream)) != ASAC_OK) return rc;
         if ((rc = asac_flat_polyak(rep->params_target, rep->params, P, prm->counters, cfg->update_target_per_step,
@@ -1635,19 +1648,19 @@ extern "C" int asac_sac_step_networks_rep(const AsacSacConfig *cfg, const AsacSa
                                rep->h0_b_stride, B, L, stream)) != ASAC_OK) return rc;
     if ((rc = launch_value_pass(a, 0, stream)) != ASAC_OK) return rc;
     if ((rc = asac_sac_q_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
-    if ((rc = launch_reduce_adam(cfg, prm, wrk, 0, 1, 1, 1.f, stream, 0, nullptr)) != ASAC_OK) return rc;
+    if ((rc = launch_reduce_adam(cfg, prm, wrk, 0, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
     // the representation's share of loss.backward() and optimizer_rep.step() (sac_base.py:1573-1601)
     if ((rc = asac_gru_backward(&rep->shape, rep->params, rep->obs, bat->actions, cfg->bn_stride, nullptr, rep->h0,
                                 rep->h0_b_stride, B, L, cfg->burn_in, wrk->grad_state, cfg->ensemble, rep->hn,
                                 rep->save, rep->grad_part, stream)) != ASAC_OK) return rc;
-    if ((rc = asac_flat_reduce_adam(rep->params, rep->m, rep->v, rep->grad_part, rep->rep_tiles, Ps, P, rep->grad,
-                                    prm->counters + 4, cfg->learning_rate, stream)) != ASAC_OK) return rc;
+    if ((rc = flat_reduce_adam(rep->params, rep->m, rep->v, rep->grad_part, rep->rep_tiles, Ps, P, rep->grad,
+                               prm->counters + 4, cfg->learning_rate, &px_rep, gscale, stream)) != ASAC_OK) return rc;
     // get_l_states again with the new weights (sac_base.py:2099-2105)
     AsacGruNet again = {rep->params, rep->states_post, rep->hn_post, nullptr};
     if ((rc = asac_gru_forward(&rep->shape, &again, 1, rep->obs, bat->actions, cfg->bn_stride, nullptr, rep->h0,
                                rep->h0_b_stride, B, L, stream)) != ASAC_OK) return rc;
     if ((rc = asac_sac_policy_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
-    if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, 1.f, stream, 0, nullptr)) != ASAC_OK) return rc;
+    if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
     const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
     if (need_post) {
         ASAC_REQUIRE(bat->eps_td && bat->eps_alpha, "asac_sac_step: missing eps_td / eps_alpha");

@@ -246,6 +246,11 @@ class SAC_Base:
             # replicated weights: every rank starts from rank 0's networks and optimizer state
             adist.broadcast_([self._q_flat, self._qt_flat, self._pi_flat, self._log_alpha_buf, self._q_m, self._q_v,
                               self._pi_m, self._pi_v, self._alpha_m, self._alpha_v, self._counters])
+            if self._gru is not None:
+                if self._peer_table is None or not (self.use_priority and self.batch_size <= 1024):
+                    raise NotImplementedError('data-parallel learner with a trained representation needs the '
+                                              'peer-memory gradient exchange and the fused tail (PER, batch <= 1024)')
+                adist.broadcast_([self._rep_flat, self._rept_flat, self._rep_m, self._rep_v])
             self._noise_seed ^= 0x9E3779B97F4A7C15 * (self._rank + 1) & 0x3FFFFFFFFFFFFFFF
             self.replay_buffer._seed ^= 0xD1B54A32D192ED03 * (self._rank + 1) & 0x3FFFFFFFFFFFFFFF
 
@@ -284,8 +289,6 @@ class SAC_Base:
         else:
             if self.seq_encoder is None:
                 raise NotImplementedError('a recurrent ModelRep needs seq_encoder=SEQ_ENCODER.RNN')
-            if self._world > 1:
-                raise NotImplementedError('data-parallel learner with a trained representation')
             self._gru, rep_params = lowered
             target = lowering.analyze_rep(self.model_target_rep, self.obs_shapes, A)
             if target is None or target[0] != self._gru:
@@ -359,6 +362,7 @@ class SAC_Base:
         cfg.update_target_per_step = int(self.update_target_per_step)
         cfg.bn_stride = cfg.seq_len
         cfg.rep_kind = 0 if self._gru is None else 1
+        cfg.rep_param_stride = 0 if self._gru is None else self._gru.stride
         cfg.tau, cfg.one_minus_tau = float(self.tau), float(np.float32(1. - self.tau))
         cfg.gamma, cfg.v_rho, cfg.v_c = float(self.gamma), float(self.v_rho), float(self.v_c)
         cfg.clip_epsilon, cfg.target_c_alpha = float(self.clip_epsilon), float(self.target_c_alpha)
@@ -511,7 +515,7 @@ class SAC_Base:
             rtile = self._lib.asac_gru_backward_tile(C.byref(self._gru_c), self.burn_in_step)
             if rtile < 1:
                 check(rtile, 'asac_gru_backward_tile')
-            rt = (B + rtile - 1) // rtile
+            rt = B  # one partial gradient per sequence
             rw = self._rw = {'hn': torch.zeros(B, L, NL, H, **f32), 'hn_post': torch.zeros(B, L, NL * H, **f32),
                              'save': torch.zeros(B, L, NL, 4 * H, **f32), 'grad_part': torch.zeros(rt, g.stride, **f32),
                              'grad': torch.zeros(g.stride, **f32)}
@@ -808,7 +812,7 @@ class SAC_Base:
         # 3. _train + get_l_probs + _get_td_error
         if self._rep is not None:  # trained GRU representation (sac_base.py:2066-2116)
             check(lib.asac_sac_step_networks_rep(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work),
-                                                 C.byref(self._rep), 0, stream), 'sac_step_networks_rep')
+                                                 C.byref(self._rep), 0, peers, stream), 'sac_step_networks_rep')
             if not fast_tail:
                 check(lib.asac_sac_staged_tail(C.byref(cfg), C.byref(prm), C.byref(work), stream), 'sac_staged_tail')
         elif not fused:

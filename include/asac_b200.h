@@ -218,7 +218,8 @@ typedef struct {
     float lambda_ratio[ASAC_MAX_NSTEP];  /* torch.logspace(0, n-1, n, v_lambda) (sac_base.py:286) */
     int32_t rep_kind;       /* 0: ModelSimpleRep (state = concat obs); 1: trained GRU representation,
                                the states of the online / re-encoded / target representation differ  */
-    int32_t reserved_;
+    int32_t rep_param_stride; /* floats of the representation's flat gradient (0 without one): its slice of the
+                               peer-exchange buffers (asac_peer_recv_words)                              */
 } AsacSacConfig;
 
 typedef struct {
@@ -393,7 +394,7 @@ typedef struct {
 } AsacGruShape;
 
 int64_t asac_gru_param_count(const AsacGruShape *shape);
-/* sequences one CTA of asac_gru_backward handles (grad_part has ceil(batch / this) rows) */
+/* sequences one CTA of asac_gru_backward handles (>= 1 when t_grad + 1 steps fit in shared memory) */
 int asac_gru_backward_tile(const AsacGruShape *shape, int t_grad);
 
 /* GRU.forward over [batch, seq_len]: x_t = [obs[b, t], pre_action], pre_action = pre_actions[b, t] when
@@ -413,8 +414,8 @@ int asac_gru_forward(const AsacGruShape *shape, const AsacGruNet *nets_host, int
 /* Back-propagation through time of sum_e grad_state[e, b, :] applied to the top layer's output at
  * step t_grad (= burn_in: the only state the critic loss reads, sac_base.py:1510) back to step 0,
  * through every layer.  hn / save come from asac_gru_forward with the same parameters and inputs.
- * grad_part[tile, P]: per-CTA partial sums (tile = asac_gru_backward_tile sequences), summed in
- * tile order by asac_flat_reduce_adam. */
+ * grad_part[batch, P rounded up to 4]: one partial gradient per sequence, summed in sequence order by
+ * asac_flat_reduce_adam. */
 int asac_gru_backward(const AsacGruShape *shape, const float *params, const float *obs, const float *actions,
                       int bn_stride, const float *pre_actions, const float *h0, int64_t h0_b_stride, int batch,
                       int seq_len, int t_grad, const float *grad_state, int ensemble, const float *hn,
@@ -444,9 +445,9 @@ typedef struct {
     float *hn;                 /* [B, L, layers, H]  scratch: hidden states of the first pass       */
     float *hn_post;            /* [B, L, layers, H]  out: next_bnx_seq_hidden_states (:2099-2105)   */
     float *save;               /* [B, L, layers, 4H] scratch: gates of the first pass               */
-    float *grad_part;          /* [rep_tiles, P]                                                    */
+    float *grad_part;          /* [rep_tiles, P rounded up to 4]                                    */
     float *grad;               /* [P]  reduced gradient                                             */
-    int32_t rep_tiles;         /* ceil(B / asac_gru_backward_tile)                                  */
+    int32_t rep_tiles;         /* rows of grad_part = B (one per sequence)                          */
     int32_t reserved_;
 } AsacGruRep;
 
@@ -454,10 +455,13 @@ typedef struct {
  * [polyak of critics and representation,] online + target representation, _get_y, critic loss and
  * backward (+ d loss / d state), critic Adam, representation BPTT + Adam, representation again,
  * policy loss / Adam, post pass on (states_post, target_states).  batch->states / states_post /
- * target_states and work->grad_state must be the buffers named in `rep`.  Single GPU.  Follow with
- * asac_sac_finish_step (advances counters[4] too when cfg->rep_kind != 0) or asac_sac_staged_tail. */
+ * target_states and work->grad_state must be the buffers named in `rep`.  `peers` != NULL: the three
+ * gradients (critics, representation, policy) are averaged over the ranks inside their reduce+Adam
+ * kernels, as in asac_sac_step_networks.  Follow with asac_sac_finish_step (advances counters[4] too when
+ * cfg->rep_kind != 0) or, single GPU, asac_sac_staged_tail. */
 int asac_sac_step_networks_rep(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
-                               const AsacSacWork *work, const AsacGruRep *rep, int with_polyak, void *stream);
+                               const AsacSacWork *work, const AsacGruRep *rep, int with_polyak,
+                               const AsacPeerTable *peers, void *stream);
 
 /* asac_sac_step's tail on its own: alpha reduce + Adam, td error, all step counters
  * (the non-prioritized / batch > 1024 counterpart of asac_sac_finish_step). */

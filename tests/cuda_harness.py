@@ -294,7 +294,7 @@ def gru_backward(shape: lowering.GruShape, params, obs, actions, h0, t_grad, gra
     cs = _lib.AsacGruShape(shape.obs_size, shape.action_size, shape.hidden, shape.layers)
     tile = lib.asac_gru_backward_tile(C.byref(cs), t_grad)
     assert tile >= 1, lib.asac_last_error()
-    tiles = (B + tile - 1) // tile
+    tiles = B  # one partial gradient per sequence
     part = torch.full((tiles, shape.stride), float('nan'), dtype=torch.float32, device=obs.device)
     check(lib.asac_gru_backward(C.byref(cs), ptr(params), ptr(obs), ptr(actions), actions.shape[1], None, ptr(h0),
                                 0 if h0 is None else h0[0].numel(), B, L, t_grad, ptr(grad_state),
@@ -321,7 +321,7 @@ class SacRepCuda(SacCuda):
         self.rep_m, self.rep_v = torch.zeros(P, **f32), torch.zeros(P, **f32)
         rtile = self.lib.asac_gru_backward_tile(C.byref(cs), hp.burn_in_step)
         assert rtile >= 1, self.lib.asac_last_error()
-        rt = (B + rtile - 1) // rtile
+        rt = B
         self.rb = {'obs': torch.zeros(B, L, obs_size, **f32), 'h0': torch.zeros(B, rep_layers, H, **f32),
                    'states': torch.zeros(B, L, H, **f32), 'states_post': torch.zeros(B, L, H, **f32),
                    'target_states': torch.zeros(B, L, H, **f32), 'hn': torch.zeros(B, L, rep_layers, H, **f32),
@@ -358,7 +358,7 @@ class SacRepCuda(SacCuda):
 
     def step_rep(self, batch) -> dict:
         check(self.lib.asac_sac_step_networks_rep(C.byref(self.cfg), C.byref(self.prm), C.byref(batch),
-                                                  C.byref(self.work), C.byref(self.rep), 1, self._s()),
+                                                  C.byref(self.work), C.byref(self.rep), 1, None, self._s()),
               'sac_step_networks_rep')
         check(self.lib.asac_sac_staged_tail(C.byref(self.cfg), C.byref(self.prm), C.byref(self.work), self._s()),
               'sac_staged_tail')

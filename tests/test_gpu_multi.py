@@ -16,7 +16,23 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank: int, world: int, port: int, out_dir: str, peer_exchange: int, graph: int):
+def _rnn_plugin():
+    import types
+    import asac_b200.nn_models as m
+
+    class ModelRep(m.ModelBaseRep):  # the form of envs/test/nn_rnn.py
+        def _build_model(self):
+            self.rnn = m.GRU(self.obs_shapes[0][0] + self.c_action_size, 8, 2)
+
+        def forward(self, obs_list, pre_action, pre_seq_hidden_state, padding_mask=None):
+            h0 = None if pre_seq_hidden_state is None else pre_seq_hidden_state[:, 0]
+            return self.rnn(torch.cat([obs_list[0], pre_action], dim=-1), h0)
+
+    return types.SimpleNamespace(ModelRep=ModelRep, ModelQ=m.ModelQ, ModelPolicy=m.ModelPolicy)
+
+
+def _worker(rank: int, world: int, port: int, out_dir: str, peer_exchange: int, graph: int, rep: int = 0,
+            same_data: int = 0, tag: str = ''):
     import sys
     import types
     from pathlib import Path
@@ -31,11 +47,19 @@ def _worker(rank: int, world: int, port: int, out_dir: str, peer_exchange: int, 
     from asac_b200 import SAC_Base
     try:
         nn = types.SimpleNamespace(ModelRep=m.ModelSimpleRep, ModelQ=m.ModelQ, ModelPolicy=m.ModelPolicy)
+        kw, hidden_shape = {}, (0,)
+        if rep:
+            from asac_b200.config_enums import SEQ_ENCODER
+            nn, hidden_shape = _rnn_plugin(), (2, 8)
+            kw = dict(seq_encoder=SEQ_ENCODER.RNN, burn_in_step=3, n_step=2)
         sac = SAC_Base(obs_names=['vector'], obs_shapes=[(6,)], d_action_sizes=[], c_action_size=2, model_abs_dir=None,
                        nn=nn, device=f'cuda:{rank}', batch_size=64, seed=11, use_priority=True,
-                       replay_config={'capacity': 2048, 'seed': 100 + rank})
-        assert (sac._peer_table is not None) == bool(peer_exchange), 'peer exchange state'
-        rng = np.random.RandomState(5 + rank)  # different data on every rank
+                       replay_config={'capacity': 2048, 'seed': 100 + (0 if same_data else rank)}, **kw)
+        assert (sac._peer_table is not None) == bool(peer_exchange and world > 1), 'peer exchange state'
+        if same_data:  # every rank draws the same samples and the same noise: mean gradient == local gradient
+            sac._noise_seed = 777
+            sac.replay_buffer._seed = 4242
+        rng = np.random.RandomState(5 + (0 if same_data else rank))  # different data on every rank
         for _ in range(6):
             T = 50
             sac.put_episode(ep_indexes=np.arange(T, dtype=np.int32)[None],
@@ -44,21 +68,22 @@ def _worker(rank: int, world: int, port: int, out_dir: str, peer_exchange: int, 
                             ep_rewards=rng.randn(1, T).astype(np.float32),
                             ep_dones=rng.randint(0, 2, size=(1, T)).astype(bool),
                             ep_probs=rng.rand(1, T, 2).astype(np.float32),
-                            ep_pre_seq_hidden_states=np.zeros((1, T, 0), dtype=np.float32))
+                            ep_pre_seq_hidden_states=(rng.randn(1, T, *hidden_shape) * 0.3).astype(np.float32))
         for _ in range(6):
             sac.train()
         torch.cuda.synchronize()
         flat = torch.cat([sac._q_flat.reshape(-1), sac._pi_flat.reshape(-1), sac._log_alpha_buf.reshape(-1),
-                          sac._q_m.reshape(-1), sac._pi_v.reshape(-1)])
+                          sac._q_m.reshape(-1), sac._pi_v.reshape(-1)] +
+                         ([sac._rep_flat, sac._rept_flat, sac._rep_v] if rep else []))
         gathered = [torch.zeros_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)
         for r in range(world):
             assert torch.equal(gathered[0], gathered[r]), f'replica {r} diverged from replica 0'
         assert torch.isfinite(flat).all()
         if rank == 0:
-            np.save(os.path.join(out_dir, f'params_px{peer_exchange}_g{graph}.npy'), flat.cpu().numpy())
+            np.save(os.path.join(out_dir, f'params{tag}_px{peer_exchange}_g{graph}.npy'), flat.cpu().numpy())
         sac.close()
-        np.save(os.path.join(out_dir, f'ok_px{peer_exchange}_g{graph}_{rank}.npy'), np.array([1]))
+        np.save(os.path.join(out_dir, f'ok{tag}_px{peer_exchange}_g{graph}_{rank}.npy'), np.array([1]))
     finally:
         dist.destroy_process_group()
 
@@ -75,3 +100,28 @@ def test_peer_exchange_matches_nccl_allreduce(tmp_path):
     b = np.load(tmp_path / 'params_px1_g1.npy')
     # two ranks: the sum of two floats does not depend on the order -> bit-identical trajectories
     assert np.array_equal(a, b), f'max |diff| {np.max(np.abs(a - b))}'
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('rep', [0, 1])
+def test_two_identical_shards_equal_one_gpu(tmp_path, rep):
+    """When both ranks hold the same data and draw the same samples, the averaged gradient IS the
+    local gradient ((g + g) / 2 is exact), so two GPUs must retrace the single-GPU run bit for bit —
+    for the stock learner and for the one with a trained GRU representation, whose gradient travels
+    through the same in-kernel peer exchange."""
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(1, _free_port(), str(tmp_path), 1, 1, rep, 1, '_one'), nprocs=1, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), 1, 1, rep, 1, '_two'), nprocs=2, join=True)
+    a = np.load(tmp_path / 'params_one_px1_g1.npy')
+    b = np.load(tmp_path / 'params_two_px1_g1.npy')
+    assert np.array_equal(a, b), f'max |diff| {np.max(np.abs(a - b))}'
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_recurrent_replicas_stay_identical(tmp_path):
+    """Different data per rank, trained GRU representation: replicas bit-identical after the steps
+    (checked inside the worker), CUDA graph with the peer exchange inside."""
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), 1, 1, 1, 0, '_rnn'), nprocs=2, join=True)
+    for r in range(2):
+        assert (tmp_path / f'ok_rnn_px1_g1_{r}.npy').exists()

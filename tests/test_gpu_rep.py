@@ -18,7 +18,8 @@ def _random_gru(shape, seed):
     return init_gru(shape.obs_size + shape.action_size, shape.hidden, shape.layers, gen)
 
 
-@pytest.mark.parametrize('So,A,H,NL,B,L', [(6, 2, 8, 2, 37, 9), (3, 1, 16, 1, 8, 5), (10, 3, 40, 3, 5, 4), (6, 2, 64, 1, 3, 3)])
+@pytest.mark.parametrize('So,A,H,NL,B,L', [(6, 2, 8, 2, 37, 9), (3, 1, 16, 1, 8, 5), (10, 3, 40, 3, 5, 4), (6, 2, 64, 1, 3, 3),
+                                           (5, 2, 16, 2, 9, 7), (7, 1, 32, 1, 6, 6), (5, 2, 10, 3, 7, 6), (4, 2, 8, 4, 5, 8)])
 def test_gru_forward_matches_torch(So, A, H, NL, B, L):
     """States, every layer's hidden states and the actor-side single step against torch.nn.GRU
     (seq_layers.py:41-113 without a padding mask); two parameter sets in one launch."""
@@ -54,7 +55,9 @@ def test_gru_forward_matches_torch(So, A, H, NL, B, L):
 
 
 @pytest.mark.parametrize('So,A,H,NL,B,L,tg,E', [(6, 2, 8, 2, 19, 9, 5, 2), (3, 1, 16, 1, 8, 5, 0, 1),
-                                                 (10, 3, 40, 3, 6, 6, 5, 3), (6, 2, 8, 2, 7, 46, 40, 2)])
+                                                 (10, 3, 40, 3, 6, 6, 5, 3), (6, 2, 8, 2, 7, 46, 40, 2),
+                                                 (5, 2, 16, 2, 9, 7, 4, 2), (7, 1, 32, 1, 6, 6, 5, 1),
+                                                 (5, 2, 10, 3, 7, 6, 3, 2), (4, 2, 8, 4, 5, 8, 7, 2)])
 def test_gru_backward_matches_autograd(So, A, H, NL, B, L, tg, E):
     """BPTT of a state gradient applied at step t_grad, against autograd through the oracle's
     restatement of the cell (in float64, so that the comparison measures the kernel alone)."""
