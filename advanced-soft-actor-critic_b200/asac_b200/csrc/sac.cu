@@ -258,7 +258,14 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     {
         const int S4 = round_up(S, 4);
         const int RPp = round_up(RPt, PASS_ROWS);
-        for (int i = tid; i < RPp * S4; i += NT) {
+        // Long windows (get_l_probs over a burn-in, sac_base.py:2563-2568): the policy rows are the bulk of
+        // the pass, so the E cluster ranks each run a slice of them and hand their head outputs to the
+        // others over distributed shared memory instead of all running every row.
+        const int NP = RPp / PASS_ROWS;
+        const bool share = E > 1 && NP >= 2 * E;
+        const int p_lo = share ? (NP * net / E) * PASS_ROWS : 0;
+        const int p_hi = share ? (NP * (net + 1) / E) * PASS_ROWS : RPp;
+        for (int i = tid + p_lo * S4; i < p_hi * S4; i += NT) {
             const int r = i / S4, col = i - r * S4;
             float v = 0.f;
             if (r < RP && col < S) {
@@ -271,9 +278,21 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
             xin[r * lda + col] = v;
         }
         __syncthreads();
-        float *h = net_trunk_forward(ps, pipe, xin, bufA, bufB, nullptr, nullptr, lda, RPp, part);
-        head_forward(h, lda, ps.hidden, head_pi, head_pi + 2 * A * ps.hidden, 2 * A, RPt, ho);
+        float *h = net_trunk_forward(ps, pipe, xin + p_lo * lda, bufA + p_lo * lda, bufB + p_lo * lda, nullptr, nullptr,
+                                     lda, p_hi - p_lo, part);
+        head_forward(h, lda, ps.hidden, head_pi, head_pi + 2 * A * ps.hidden, 2 * A, min(RPt, p_hi) - p_lo,
+                     ho + p_lo * 2 * A);
         __syncthreads();
+        if (share) {
+            cluster.sync();  // every rank of the cluster is running (remote shared memory may be written)
+            const int lo = p_lo * 2 * A, hi = min(RPt, p_hi) * 2 * A;
+            for (int q = 0; q < E; ++q) {
+                if (q == net) continue;
+                float *remote = cluster.map_shared_rank(ho, q);
+                for (int i = lo + tid; i < hi; i += NT) remote[i] = ho[i];
+            }
+            cluster.sync();
+        }
     }
 
     ASAC_PHASE(0, 2);

@@ -136,3 +136,56 @@ def test_recurrent_step_against_oracle_and_golden(name):
             assert rel_err(v, ref[k]) < 2e-5, (s, k, rel_err(v, ref[k]))
         cnt = cu.counters.cpu().tolist()
         assert cnt[0] == s + 1 and cnt[1] == s + 1 and cnt[2] == s + 1 and cnt[4] == s + 1
+
+
+def test_recurrent_step_large_batch_shares_policy_rows():
+    """B = 1024 sequences of 5 rows: 16 batch elements per tile, so the post pass holds 128 policy rows
+    per tile and the two cluster ranks each run half of them and exchange the head outputs over
+    distributed shared memory (k_value_pass, `share`).  Random parameters and inputs against the oracle."""
+    from oracle.rep_oracle import SacRepBatch, SacRepOracle
+    from oracle.sac_oracle import SacHyper, SacNoise
+    from tests.cuda_harness import SacRepCuda
+    torch.set_num_threads(4)
+    B, So, A, NL, H, b, n = 1024, 6, 2, 2, 8, 2, 2
+    L = b + n + 1
+    hp = SacHyper(state_size=H, action_size=A, ensemble_q_num=2, hidden=64, q_depth=3, policy_depth=3,
+                  burn_in_step=b, n_step=n, clip_epsilon=0.0, v_lambda=0.9)
+    oracle = SacRepOracle(hp, So, NL, seed=5)
+    with torch.no_grad():  # targets differ from the online nets, biases off zero
+        for net in oracle.q_target + [oracle.rep_target]:
+            for t in net.values():
+                t.add_(torch.randn_like(t) * 0.02)
+    cu = SacRepCuda(hp, B, So, NL)
+    assert cu.tile == 16
+    snap = lambda d: {k: v.detach() for k, v in d.items()}
+    cu.load_params([snap(q) for q in oracle.q], [snap(q) for q in oracle.q_target], snap(oracle.policy),
+                   float(oracle.log_c_alpha))
+    cu.load_rep(snap(oracle.rep), snap(oracle.rep_target))
+    rng = np.random.RandomState(9)
+    t = lambda x: torch.from_numpy(x)
+    pad = np.zeros((B, L - 1), dtype=bool)
+    pad[rng.rand(B) < 0.2, :1] = True
+    batch = SacRepBatch(obs=t(rng.randn(B, L, So).astype(np.float32)),
+                        hidden0=t((rng.randn(B, NL, H) * 0.5).astype(np.float32)),
+                        actions=t((rng.rand(B, L - 1, A) * 1.8 - 0.9).astype(np.float32)),
+                        rewards=t(rng.randn(B, L - 1).astype(np.float32)), dones=t(rng.rand(B, L - 1) < 0.1),
+                        mu_probs=t((rng.rand(B, L - 1, A) + 0.05).astype(np.float32)),
+                        last_masks=t(rng.rand(B, L - 1) < 0.05), padding_masks=t(pad),
+                        priority_is=t((rng.rand(B, 1) * 0.9 + 0.1).astype(np.float32)))
+    noise = SacNoise(eps_y=t(rng.randn(B, n + 1, A).astype(np.float32)), eps_pi=t(rng.randn(B, A).astype(np.float32)),
+                     eps_alpha=t(rng.randn(B, A).astype(np.float32)), eps_td=t(rng.randn(B, n + 1, A).astype(np.float32)))
+    want = oracle.step(batch, noise)
+    got = cu.step_rep(cu.make_rep_batch(batch, noise))
+    torch.cuda.synchronize()
+    assert rel_err(got['y'], want['y'].view(-1)) < TOL
+    for i in range(2):
+        for k, v in got['grad_q'][i].items():
+            assert rel_err(v, want['grad_q'][i][k]) < TOL, (i, k)
+    for k, v in got['grad_rep'].items():
+        assert rel_err(v, want['grad_rep'][k]) < TOL, (k, rel_err(v, want['grad_rep'][k]))
+    for k, v in got['grad_policy'].items():
+        assert rel_err(v, want['grad_policy'][k]) < TOL, k
+    assert rel_err(got['states_post'], want['states_post']) < TOL
+    rel = np.abs(got['pi_probs'] - want['pi_probs'].numpy()) / np.maximum(1.0, np.abs(want['pi_probs'].numpy()))
+    assert np.quantile(rel, 0.999) < 5e-5 and rel.max() < 5e-3  # heavy-tailed amplification (see test_gpu_sac)
+    assert np.quantile(np.abs(got['td_error'] - want['td_error'].view(-1).numpy()), 0.999) < 1e-4
