@@ -37,6 +37,15 @@ __host__ __device__ __forceinline__ int gru_weight_floats(const AsacGruShape &s)
     return (o + 3) & ~3;
 }
 
+// i / d for 0 <= i < 2^20 and a divisor known only at run time, through its float reciprocal (three
+// instructions instead of the ~25 of an integer division; (i + 0.5) / d is never within rounding of an integer)
+struct FastDiv {
+    int d;
+    float inv;
+    __device__ __forceinline__ explicit FastDiv(int d_) : d(d_), inv(1.f / (float)d_) {}
+    __device__ __forceinline__ int div(int i) const { return __float2int_rz(((float)i + 0.5f) * inv); }
+};
+
 // Cooperative global -> shared staging with U loads of every thread in flight before the first store
 // (the recurrent kernels start with a few thousand scattered floats; one load per loop trip would
 // serialise that many DRAM / L2 round trips): element i comes from load(i) and goes to dst[where(i)].
@@ -66,11 +75,12 @@ __device__ void gru_stage_weights(float *w_sm, const float *params, const AsacGr
         const int in = gru_in(s, l), rs = gru_row_stride(s, l);
         const float *p = params + gru_layer_off(s, l);
         const int n_ih = 3 * H * in, n_hh = 3 * H * H;
+        const FastDiv by_in(in), by_h(H);
         staged_fill<8>(w_sm + base, n_ih + n_hh + 6 * H, [&](int i) { return __ldg(p + i); },
                        [&](int i) {
                            int g, c;
-                           if (i < n_ih) { g = i / in; c = i - g * in; }
-                           else if (i < n_ih + n_hh) { const int j = i - n_ih; g = j / H; c = in + (j - g * H); }
+                           if (i < n_ih) { g = by_in.div(i); c = i - g * in; }
+                           else if (i < n_ih + n_hh) { const int j = i - n_ih; g = by_h.div(j); c = in + (j - g * H); }
                            else if (i < n_ih + n_hh + 3 * H) { g = i - n_ih - n_hh; c = in + H; }
                            else { g = i - n_ih - n_hh - 3 * H; c = in + H + 1; }
                            return g * rs + c;
@@ -85,16 +95,17 @@ __device__ __forceinline__ void gru_stage_inputs(float *region, int region_strid
                                                  const float *actions, int bn_stride, const float *pre_actions,
                                                  int64_t seq0, int n_seq, int L, int T, int So, int A) {
     const int in0 = So + A, per = T * row_stride;
+    const FastDiv by_per(per), by_row(row_stride);
     staged_fill<8>(region, n_seq * per,
                    [&](int i) {
-                       const int w = i / per, r = i - w * per, t = r / row_stride, c = r - t * row_stride;
+                       const int w = by_per.div(i), r = i - w * per, t = by_row.div(r), c = r - t * row_stride;
                        const int64_t seq = seq0 + w;
                        if (c >= in0) return 0.f;
                        if (c < So) return obs[(seq * L + t) * So + c];
                        if (pre_actions) return pre_actions[(seq * L + t) * A + (c - So)];
                        return t > 0 ? actions[(seq * bn_stride + t - 1) * A + (c - So)] : 0.f;  // operators.py:39-59
                    },
-                   [&](int i) { const int w = i / per; return w * region_stride + (i - w * per); });
+                   [&](int i) { const int w = by_per.div(i); return w * region_stride + (i - w * per); });
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -186,6 +197,10 @@ __device__ __forceinline__ void gru_wave_forward(const AsacGruShape &s, const As
     float *hself = hbuf + lc * H + j;
     // layer-0 lanes with inloop read x_t (row stride in0p <= H, zero padded) where the others read the layer below
     const int nx4 = (MULTI && lc == 0 && inloop) ? in0p / 4 : H / 4;
+    // output cursors of this lane (advanced once per active stage: step t = 0, 1, ...)
+    float *p_hn = net.hn ? net.hn + ((seq * L) * NL + lc) * H + j : nullptr;
+    float *p_sv = net.save ? net.save + ((seq * L) * NL + lc) * 4 * H + j : nullptr;
+    float *p_st = (valid && l == NL - 1) ? net.states + (seq * L) * H + j : nullptr;
 #pragma unroll 1
     for (int st = 0; st < L + NL - 1; ++st) {
         const int t = st - l;
@@ -223,13 +238,12 @@ __device__ __forceinline__ void gru_wave_forward(const AsacGruShape &s, const As
         __syncwarp();
         if (active) {
             *hself = hnew;
-            const int64_t cell = (seq * L + t) * NL + l;
-            if (net.hn) net.hn[cell * H + j] = hnew;
-            if (net.save) {
-                float *sv = net.save + cell * 4 * H;
-                sv[j] = r; sv[H + j] = z; sv[2 * H + j] = n; sv[3 * H + j] = hn;
+            if (p_hn) { *p_hn = hnew; p_hn += NL * H; }
+            if (p_sv) {
+                p_sv[0] = r; p_sv[H] = z; p_sv[2 * H] = n; p_sv[3 * H] = hn;
+                p_sv += NL * 4 * H;
             }
-            if (l == NL - 1) net.states[(seq * L + t) * H + j] = hnew;
+            if (p_st) { *p_st = hnew; p_st += H; }
         }
         __syncwarp();
     }
@@ -258,9 +272,10 @@ __global__ void __launch_bounds__(GRU_FWD_WARPS * 32) k_gru_forward(const __grid
         gru_stage_inputs(first, wf, in0p, a.obs, a.actions, a.bn_stride, a.pre_actions, seq0, n_seq, L, L, s.obs_size,
                          s.action_size);
         const int hoff = (int)(hbuf - xs), nh = NL * H;
+        const FastDiv by_nh(nh);
         staged_fill<2>(first + hoff, n_seq * nh,
-                       [&](int i) { const int w = i / nh; return a.h0 ? a.h0[(seq0 + w) * a.h0_b_stride + (i - w * nh)] : 0.f; },
-                       [&](int i) { const int w = i / nh; return w * wf + (i - w * nh); });
+                       [&](int i) { const int w = by_nh.div(i); return a.h0 ? a.h0[(seq0 + w) * a.h0_b_stride + (i - w * nh)] : 0.f; },
+                       [&](int i) { const int w = by_nh.div(i); return w * wf + (i - w * nh); });
     }
     __syncthreads();
     if (seq >= a.batch) return;
@@ -462,15 +477,16 @@ __global__ void __launch_bounds__(GRU_BWD_THREADS) k_gru_backward(const __grid_c
         gru_stage_inputs(seq_sm + pl.off_xs, pl.total, in0, a.obs, a.actions, a.bn_stride, a.pre_actions, seq0, n_seq, L, T1,
                          s.obs_size, s.action_size);
         const int n_hn = T1 * NL * H, n_sv = T1 * NL * 4 * H, n_h0 = NL * H;
+        const FastDiv by_hn(n_hn), by_sv(n_sv), by_h0(n_h0);
         staged_fill<8>(seq_sm + pl.off_hn, n_seq * n_hn,
-                       [&](int i) { const int w = i / n_hn; return a.hn[(seq0 + w) * L * NL * H + (i - w * n_hn)]; },
-                       [&](int i) { const int w = i / n_hn; return w * pl.total + (i - w * n_hn); });
+                       [&](int i) { const int w = by_hn.div(i); return a.hn[(seq0 + w) * L * NL * H + (i - w * n_hn)]; },
+                       [&](int i) { const int w = by_hn.div(i); return w * pl.total + (i - w * n_hn); });
         staged_fill<8>(seq_sm + pl.off_sv, n_seq * n_sv,
-                       [&](int i) { const int w = i / n_sv; return a.save[(seq0 + w) * L * NL * 4 * H + (i - w * n_sv)]; },
-                       [&](int i) { const int w = i / n_sv; return w * pl.total + (i - w * n_sv); });
+                       [&](int i) { const int w = by_sv.div(i); return a.save[(seq0 + w) * L * NL * 4 * H + (i - w * n_sv)]; },
+                       [&](int i) { const int w = by_sv.div(i); return w * pl.total + (i - w * n_sv); });
         staged_fill<2>(seq_sm + pl.off_h0, n_seq * n_h0,
-                       [&](int i) { const int w = i / n_h0; return a.h0 ? a.h0[(seq0 + w) * a.h0_b_stride + (i - w * n_h0)] : 0.f; },
-                       [&](int i) { const int w = i / n_h0; return w * pl.total + (i - w * n_h0); });
+                       [&](int i) { const int w = by_h0.div(i); return a.h0 ? a.h0[(seq0 + w) * a.h0_b_stride + (i - w * n_h0)] : 0.f; },
+                       [&](int i) { const int w = by_h0.div(i); return w * pl.total + (i - w * n_h0); });
     }
     if (wid < n_seq) {
         const int64_t seq = seq0 + wid;
