@@ -562,6 +562,58 @@ def gen_sac_rnn_case(name, *, So, A, E, B, b, n, steps, seed, use_priority=True,
     print('wrote', f'sac_{name}.npz', sum(v.nbytes for v in out.values()), 'bytes raw')
 
 
+def gen_ckpt_case(name, *, rnn: bool, seed: int):
+    """A checkpoint directory written by the REAL reference (`save_model(save_replay_buffer=True)`,
+    sac_base.py:654-668; replay_buffer.py:96-111, 220-227, 436-446) after a few real `train()` steps,
+    plus what the restored learner must reproduce: the deterministic action of `choose_action`
+    (sac_base.py:968-1019) on recorded observations.  Interchange fixture for SURVEY §8f rank 2."""
+    import shutil
+    SAC_Base, _, _ = import_reference()
+    synth = _load_synth()
+    kw, hidden_shape = {}, (0,)
+    if rnn:
+        from algorithm.utils.enums import SEQ_ENCODER
+        nn = load_reference_nn('envs/test/nn_rnn.py')
+        kw, hidden_shape = dict(seq_encoder=SEQ_ENCODER.RNN, burn_in_step=3, n_step=2), (2, 8)
+    else:
+        nn = load_reference_nn('envs/test/nn.py')
+    out_dir = GOLDEN / f'ckpt_{name}'
+    shutil.rmtree(out_dir, ignore_errors=True)
+    out_dir.mkdir(parents=True)
+    torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
+    sac = SAC_Base(obs_names=['vector'], obs_shapes=[(6,)], d_action_sizes=[], c_action_size=2,
+                   model_abs_dir=out_dir, nn=nn, device='cpu', seed=seed, batch_size=8, summary_path=None,
+                   save_model_per_step=10 ** 9, replay_config={'capacity': 64}, **kw)
+    for _ in range(3):
+        ep = synth.gen_episode_trans(obs_shapes=[(6,)], d_action_sizes=[], c_action_size=2,
+                                     seq_hidden_state_shape=hidden_shape, episode_len=12)
+        sac.put_episode(**ep)
+    import time
+    done = 0
+    for _ in range(200):  # the prefetch thread fills the queue asynchronously
+        if sac.train() > done:
+            done += 1
+        if done == 4:
+            break
+        time.sleep(0.01)
+    assert done == 4, done
+    sac.save_model(save_replay_buffer=True)
+    rng = np.random.RandomState(seed)
+    obs = rng.randn(5, 6).astype(np.float32)
+    pre_action = rng.rand(5, 2).astype(np.float32)
+    pre_hidden = (rng.randn(5, *hidden_shape) * 0.3).astype(np.float32)
+    action, prob, hidden = sac.choose_action([obs], pre_action, pre_hidden, disable_sample=True)
+    np.savez(out_dir / 'expect.npz', obs=obs, pre_action=pre_action, pre_hidden=pre_hidden, action=action,
+             prob=prob, hidden=hidden, global_step=np.int64(sac.get_global_step()),
+             rb_size=np.int64(sac.replay_buffer.size))
+    sac.close()
+    for p in out_dir.iterdir():  # keep model/ and expect.npz only
+        if p.name not in ('model', 'expect.npz'):
+            shutil.rmtree(p) if p.is_dir() else p.unlink()
+    (out_dir / 'model' / '0.pth').unlink()  # the step-0 save of sac_base.py:2555-2556; the fixture is step 4
+    print('wrote', out_dir, sorted(x.name for x in (out_dir / 'model').iterdir()))
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     gen_per_case('small', capacity=64, batch_size=8, prev_n=2, post_n=3, alpha=0.9,
@@ -585,6 +637,9 @@ def main():
     # config-4 shapes (envs/test/nn_rnn.py: GRU(6 + 2 -> 8, 2 layers)), shorter burn-in, 2 steps
     gen_sac_rnn_case('rnn', So=6, A=2, E=2, B=16, b=5, n=3, steps=2, seed=14, v_lambda=0.95)
     gen_sac_rnn_case('rnn_b0', So=6, A=2, E=2, B=8, b=0, n=1, steps=2, seed=15, use_n_step_is=False)
+    # checkpoint directories written by the reference itself (interchange)
+    gen_ckpt_case('vector', rnn=False, seed=21)
+    gen_ckpt_case('rnn', rnn=True, seed=22)
 
 
 if __name__ == '__main__':

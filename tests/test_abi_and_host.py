@@ -174,3 +174,28 @@ def test_product_never_imports_the_oracle():
     for path in pkg.rglob('*.py'):
         text = path.read_text()
         assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), path
+
+
+def test_reference_checkpoint_fixtures_have_the_expected_layout():
+    """CPU-side check of tests/golden/ckpt_*: files and key names as the reference writes them
+    (sac_base.py:493-566, 654-668; replay_buffer.py:96-111, 220-227) — what the GPU resume test loads."""
+    import numpy as np
+    import torch
+    from tests.helpers import GOLDEN
+    for name, rep in (('vector', False), ('rnn', True)):
+        d = GOLDEN / f'ckpt_{name}' / 'model'
+        saved = torch.load(d / '4.pth', weights_only=True)
+        want = {'global_step', 'model_policy', 'optimizer_policy', 'log_d_alpha', 'log_c_alpha', 'optimizer_alpha'}
+        want |= {f'{k}_{i}' for i in range(2) for k in ('model_q', 'model_target_q', 'optimizer_q')}
+        if rep:
+            want |= {'model_rep', 'model_target_rep', 'optimizer_rep'}
+            assert set(saved['model_rep']) == {f'rnn._grus.{l}.{t}_l0' for l in range(2)
+                                               for t in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')}
+        assert set(saved) == want
+        assert int(saved['global_step']) == 4
+        tree = np.load(d / '4-rb_tree.npy')
+        assert tree.shape == (2 * 64 - 1,) and tree.dtype == np.float32
+        store = np.load(d / '4-rb_storage.npz')
+        assert {'_id', 'index', 'last_mask', 'obs_vector', 'action', 'reward', 'done', 'mu_prob',
+                'pre_seq_hidden_state', 'p_size', 'p_id'} == set(store.files)
+        assert store['pre_seq_hidden_state'].shape[1:] == ((2, 8) if rep else (0,))

@@ -294,3 +294,59 @@ def test_recurrent_representation_learner(tmp_path):
     sd = a.ckpt_dict['optimizer_rep'].state_dict()
     assert float(sd['state'][0]['step']) == 6 and len(sd['state']) == 8
     a.close(); b.close()
+
+
+@pytest.mark.parametrize('name', ['vector', 'rnn'])
+def test_resume_from_a_checkpoint_written_by_the_reference(tmp_path, name):
+    """tests/golden/ckpt_<name>/ was written by the REFERENCE (`save_model(save_replay_buffer=True)` after 4
+    train() steps, oracle/gen_golden.py:gen_ckpt_case): the B200 learner restores networks, optimizers,
+    sum tree and transition storage from those files (sac_base.py:568-629; replay_buffer.py:96-111,
+    220-227), reproduces the reference's deterministic action on recorded observations and trains on."""
+    import shutil
+    from tests.helpers import GOLDEN
+    shutil.copytree(GOLDEN / f'ckpt_{name}', tmp_path / 'run')
+    exp = np.load(tmp_path / 'run' / 'expect.npz')
+    kw = {}
+    if name == 'rnn':
+        from algorithm.utils.enums import SEQ_ENCODER
+        nn, kw = _plugin(tmp_path, PLUGIN_RNN, 'nn_plugin_ckpt_rnn'), dict(seq_encoder=SEQ_ENCODER.RNN, burn_in_step=3, n_step=2)
+    else:
+        nn = _plugin(tmp_path, PLUGIN_TEST, 'nn_plugin_ckpt')
+    from algorithm.sac_base import SAC_Base
+    sac = SAC_Base(obs_names=['vector'], obs_shapes=[(6,)], d_action_sizes=[], c_action_size=2,
+                   model_abs_dir=tmp_path / 'run', nn=nn, batch_size=8, summary_path=None, save_model_per_step=10 ** 9,
+                   replay_config={'capacity': 64}, **kw)
+    saved = torch.load(tmp_path / 'run' / 'model' / '4.pth', weights_only=True)
+    assert sac.get_global_step() == int(exp['global_step']) == 4
+    for key, mod in sac.ckpt_dict.items():
+        assert key in saved, key
+        if isinstance(mod, torch.nn.Module):
+            for k, v in mod.state_dict().items():
+                assert torch.equal(v.cpu(), saved[key][k]), (key, k)
+    assert set(saved) == set(sac.ckpt_dict)
+    assert float(sac.log_c_alpha) == float(saved['log_c_alpha'])
+    cnt = sac._counters.cpu().tolist()
+    assert cnt[0] == 4 and cnt[1] == 4 and cnt[2] == 4 and cnt[3] == 4 and (name != 'rnn' or cnt[4] == 4)
+    st = saved['optimizer_policy']['state'][0]
+    w0 = next(iter(sac.model_policy.parameters()))
+    off = (w0.data_ptr() - sac._pi_flat.data_ptr()) // 4
+    assert torch.equal(sac._pi_m[off:off + w0.numel()].view_as(w0).cpu(), st['exp_avg'])
+    # replay: the reference's tree is nodes[1:], its storage columns are the rings
+    rb = sac.replay_buffer
+    tree = np.load(tmp_path / 'run' / 'model' / '4-rb_tree.npy')
+    assert np.array_equal(rb._nodes.cpu().numpy()[1:], tree)
+    store = np.load(tmp_path / 'run' / 'model' / '4-rb_storage.npz')
+    assert rb.size == int(exp['rb_size']) == int(store['p_size'])
+    for k in store.files:
+        if k in ('p_size', 'p_id'):
+            continue
+        col = rb._store_ids if k == '_id' else rb._columns[k]
+        assert np.array_equal(col.cpu().numpy().reshape(store[k].shape), store[k]), k
+    a, p, h = sac.choose_action([exp['obs']], exp['pre_action'], exp['pre_hidden'], disable_sample=True)
+    assert np.max(np.abs(a - exp['action'])) < 1e-5
+    assert np.max(np.abs(p - exp['prob']) / np.maximum(1.0, np.abs(exp['prob']))) < 1e-4
+    assert h.shape == exp['hidden'].shape and (h.size == 0 or np.max(np.abs(h - exp['hidden'])) < 1e-5)
+    assert sac.train() == 5
+    torch.cuda.synchronize()
+    assert all(np.isfinite(v) for v in sac.last_step_stats().values())
+    sac.close()
