@@ -156,6 +156,7 @@ PROTOTYPES = {
                                          P(AsacGruRep), i32, P(AsacPeerTable), vp]),
     'asac_sac_staged_tail': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp]),
     'asac_fill_normal': (i32, [vp, i64, u64, vp, i32, vp]),
+    'asac_l2_prefetch': (i32, [P(vp), P(i64), i32, vp]),
     'asac_mlp_forward': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp]),
     'asac_mlp_forward_tc': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp]),
     'asac_debug_phase_clocks': (i32, [vp]),

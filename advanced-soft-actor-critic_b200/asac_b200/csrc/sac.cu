@@ -1139,6 +1139,21 @@ __global__ void __launch_bounds__(256) k_fill_normal(float *out, int64_t n, uint
         if (q * 4 + i < n) out[q * 4 + i] = z[i];
 }
 
+struct PrefetchArgs {
+    const char *base[8];
+    int64_t lines[8];  // 128-byte lines per region (prefix sums in `first`)
+    int64_t first[9];
+    int n;
+};
+__global__ void __launch_bounds__(256) k_l2_prefetch(const PrefetchArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.first[a.n]) return;
+    int r = 0;
+    while (r + 1 < a.n && i >= a.first[r + 1]) ++r;
+    const char *p = a.base[r] + (i - a.first[r]) * 128;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // Actor side (sac_base.py:943-964, continuous branch of _choose_action): from the policy head's
 // pre-activations to the squashed action and its per-dimension probability.
 //   c_action = offline | tanh(mean) (disable_sample) | tanh(Normal(mu, sigma).sample())
@@ -1739,6 +1754,22 @@ extern "C" int asac_sac_finish_step(const AsacSacConfig *cfg, const AsacSacParam
     const int threads = ((cfg->batch + 31) / 32) * 32;
     ASAC_CUDA(launch_ex(k_step_epilogue, dim3(1), dim3(threads), 0, (cudaStream_t)stream, 0, true, a));
     ASAC_LAUNCHED("k_step_epilogue");
+    return ASAC_OK;
+}
+
+extern "C" int asac_l2_prefetch(const void *const *regions, const int64_t *bytes, int n, void *stream) {
+    ASAC_REQUIRE(regions && bytes && n >= 1 && n <= 8, "asac_l2_prefetch: 1..8 regions");
+    PrefetchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n;
+    for (int i = 0; i < n; ++i) {
+        ASAC_REQUIRE(regions[i] && bytes[i] > 0, "asac_l2_prefetch: empty region %d", i);
+        a.base[i] = reinterpret_cast<const char *>(regions[i]);
+        a.lines[i] = (bytes[i] + 127) / 128;
+        a.first[i + 1] = a.first[i] + a.lines[i];
+    }
+    k_l2_prefetch<<<(unsigned)((a.first[n] + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_l2_prefetch");
     return ASAC_OK;
 }
 

@@ -533,6 +533,18 @@ class SAC_Base:
             batch.states_post, batch.target_states = ptr(bt['states_post']), ptr(bt['target_states'])
         self._noise_seed = (int(self._seed) if self._seed is not None else random.getrandbits(62)) ^ 0x5AC5AC
         self._side_stream = torch.cuda.Stream(device=dev)
+        # Optional (ASAC_L2_PREFETCH=1): pull the buffers the critical-path kernels touch first and nothing
+        # else of the step has brought into L2 (policy parameters, Adam moments; the Polyak kernel reads the
+        # critics) on the side branch.  Measured on B200, same box, L2 flushed between steps: 5352 vs 5348
+        # steps/s, warm 6527 vs 6540 — the weight pipe already has every slot in flight behind ONE
+        # HBM round trip per kernel, so there is nothing left to hide; off by default.
+        self._prefetch = None
+        if os.environ.get('ASAC_L2_PREFETCH', '0') == '1':
+            regions = [self._pi_flat, self._q_m, self._q_v, self._pi_m, self._pi_v]
+            if self._gru is not None:
+                regions += [self._rep_flat, self._rep_m, self._rep_v]
+            self._prefetch = ((C.c_void_p * len(regions))(*[t.data_ptr() for t in regions]),
+                              (C.c_int64 * len(regions))(*[t.numel() * 4 for t in regions]), regions)
         self._act_counter = torch.zeros(1, dtype=torch.int64, device=dev)  # Philox counter of choose_action
         self.actor_tensor_cores = False
         # data-parallel learner: gradient exchange inside the reduce+Adam kernels over NVLink peer memory
@@ -793,6 +805,9 @@ class SAC_Base:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             s2 = side.cuda_stream
+            if self._prefetch is not None:  # policy parameters and Adam moments -> L2 while sample / gather run
+                check(lib.asac_l2_prefetch(self._prefetch[0], self._prefetch[1], len(self._prefetch[2]), s2),
+                      'l2_prefetch')
             if fast_tail or self._rep is not None:
                 check(lib.asac_sac_polyak(C.byref(cfg), C.byref(prm), -1.0, s2), 'sac_polyak')
             if self._rep is not None:

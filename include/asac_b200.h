@@ -471,6 +471,11 @@ int asac_sac_staged_tail(const AsacSacConfig *cfg, const AsacSacParams *prm, con
 int asac_fill_normal(float *out, int64_t n, uint64_t seed, const int64_t *counter, int stream_id,
                      void *stream);
 
+/* Pulls up to 8 device regions into L2 (prefetch.global.L2, one 128-byte line per thread): the learner
+ * issues it on the side branch of a step for the buffers the critical-path kernels will touch first
+ * (policy parameters, Adam moments) while the sample / gather kernels run. */
+int asac_l2_prefetch(const void *const *regions_host, const int64_t *bytes_host, int n_regions, void *stream);
+
 /* Stock-net forward for the actor side / tests: out[rows, O] = net(x[rows, in]). */
 int asac_mlp_forward(const float *params, int in_dim, int hidden, int depth, int out_dim,
                      const float *x, int64_t rows, float *out, void *stream);
