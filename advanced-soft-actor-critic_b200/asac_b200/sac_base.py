@@ -238,7 +238,7 @@ class SAC_Base:
             self._init_replay_buffer(replay_config)
             self._build_step_buffers()
             self._init_or_restore(int(last_ckpt) if last_ckpt is not None else None)
-        self._graph = None
+        self._graphs = [None, None]
         self._graph_columns_key = None
         # NCCL all-reduces are captured into the step's CUDA graph (ASAC_GRAPH_COLLECTIVES=0 keeps them eager)
         self._graph_collectives = os.environ.get('ASAC_GRAPH_COLLECTIVES', '1') != '0'
@@ -465,14 +465,6 @@ class SAC_Base:
         n, T = self.n_step, self._n_tiles
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
-        u8 = dict(dtype=torch.uint8, device=dev)
-        bt = self._bt = {
-            'index': torch.zeros(B, L, dtype=torch.int32, device=dev),
-            'states': torch.zeros(B, L, S, **f32), 'actions': torch.zeros(B, L, A, **f32),
-            'rewards': torch.zeros(B, L, **f32), 'dones': torch.zeros(B, L, **u8),
-            'last_masks': torch.zeros(B, L, **u8), 'padding_masks': torch.zeros(B, L, **u8),
-            'mu_probs': torch.zeros(B, L, A, **f32),
-        }
         # one noise buffer, four views: eps_y, eps_pi, eps_alpha, eps_td
         sizes = [B * (n + 1) * A, B * A, B * A, B * (n + 1) * A]
         self._noise = torch.zeros(sum(sizes), **f32)
@@ -495,42 +487,24 @@ class SAC_Base:
         for k, t in wk.items():
             setattr(work, k, ptr(t))
         self._work = work
-        self._smp = {'slots': torch.zeros(B, dtype=torch.int32, device=dev),
-                     'ids': torch.zeros(B, dtype=torch.int64, device=dev),
-                     'p': torch.zeros(B, **f32), 'w': torch.zeros(B, **f32)}
-        batch = _lib.AsacSacBatch()
-        batch.states, batch.actions, batch.rewards = ptr(bt['states']), ptr(bt['actions']), ptr(bt['rewards'])
-        batch.dones, batch.last_masks = ptr(bt['dones']), ptr(bt['last_masks'])
-        batch.padding_masks, batch.mu_probs = ptr(bt['padding_masks']), ptr(bt['mu_probs'])
-        batch.priority_is = ptr(self._smp['w']) if self.use_priority else None
-        batch.eps_y, batch.eps_pi, batch.eps_alpha, batch.eps_td = [ptr(e) for e in self._eps]
-        self._batch = batch
-        self._rep = None
+        self._rw = None
         if self._gru is not None:
             g = self._gru
-            NL, H = g.layers, g.hidden
-            bt['obs'] = torch.zeros(B, L, g.obs_size, **f32)
-            bt['hidden'] = torch.zeros(B, L, NL * H, **f32)
-            bt['states_post'], bt['target_states'] = torch.zeros(B, L, S, **f32), torch.zeros(B, L, S, **f32)
             rtile = self._lib.asac_gru_backward_tile(C.byref(self._gru_c), self.burn_in_step)
             if rtile < 1:
                 check(rtile, 'asac_gru_backward_tile')
-            rt = B  # one partial gradient per sequence
-            rw = self._rw = {'hn': torch.zeros(B, L, NL, H, **f32), 'hn_post': torch.zeros(B, L, NL * H, **f32),
-                             'save': torch.zeros(B, L, NL, 4 * H, **f32), 'grad_part': torch.zeros(rt, g.stride, **f32),
-                             'grad': torch.zeros(g.stride, **f32)}
-            rep = _lib.AsacGruRep()
-            rep.shape = self._gru_c
-            rep.params, rep.params_target = ptr(self._rep_flat), ptr(self._rept_flat)
-            rep.m, rep.v = ptr(self._rep_m), ptr(self._rep_v)
-            rep.obs, rep.h0, rep.h0_b_stride = ptr(bt['obs']), ptr(bt['hidden']), L * NL * H
-            rep.states, rep.states_post, rep.target_states = ptr(bt['states']), ptr(bt['states_post']), \
-                ptr(bt['target_states'])
-            for k, t in rw.items():
-                setattr(rep, k, ptr(t))
-            rep.rep_tiles = rt
-            self._rep = rep
-            batch.states_post, batch.target_states = ptr(bt['states_post']), ptr(bt['target_states'])
+            self._rw = {'hn': torch.zeros(B, L, g.layers, g.hidden, **f32),
+                        'hn_post': torch.zeros(B, L, g.layers * g.hidden, **f32),
+                        'save': torch.zeros(B, L, g.layers, 4 * g.hidden, **f32),
+                        'grad_part': torch.zeros(B, g.stride, **f32),  # one partial gradient per sequence
+                        'grad': torch.zeros(g.stride, **f32)}
+        # The sampled batch lives in a "batch set" (sample outputs, gathered windows, the C structs pointing
+        # at them).  Two sets: while the networks train on one, the NEXT step's sample + gather fill the
+        # other on a parallel branch (ASAC_SAMPLE_AHEAD=0: one set, sample and gather on the critical path).
+        self._sample_ahead = os.environ.get('ASAC_SAMPLE_AHEAD', '1') != '0'
+        self._sets = [self._make_batch_set() for _ in range(2 if self._sample_ahead else 1)]
+        self._cur, self._primed = 0, False
+        self._prefetch_stream = torch.cuda.Stream(device=dev)
         self._noise_seed = (int(self._seed) if self._seed is not None else random.getrandbits(62)) ^ 0x5AC5AC
         self._side_stream = torch.cuda.Stream(device=dev)
         # Optional (ASAC_L2_PREFETCH=1): pull the buffers the critical-path kernels touch first and nothing
@@ -558,6 +532,57 @@ class SAC_Base:
             except Exception as e:  # noqa: BLE001 - any failure of the mapping falls back to NCCL
                 self._logger.warning(f'peer-memory gradient exchange unavailable ({e}); using NCCL all-reduce')
                 self._peers = self._peer_table = None
+
+    def _make_batch_set(self) -> dict:
+        B, L, S, A = self.batch_size, self._cfg.seq_len, self.state_size, self.c_action_size
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        bt = {
+            'index': torch.zeros(B, L, dtype=torch.int32, device=dev),
+            'states': torch.zeros(B, L, S, **f32), 'actions': torch.zeros(B, L, A, **f32),
+            'rewards': torch.zeros(B, L, **f32), 'dones': torch.zeros(B, L, **u8),
+            'last_masks': torch.zeros(B, L, **u8), 'padding_masks': torch.zeros(B, L, **u8),
+            'mu_probs': torch.zeros(B, L, A, **f32),
+        }
+        smp = {'slots': torch.zeros(B, dtype=torch.int32, device=dev), 'ids': torch.zeros(B, dtype=torch.int64, device=dev),
+               'p': torch.zeros(B, **f32), 'w': torch.zeros(B, **f32)}
+        batch = _lib.AsacSacBatch()
+        batch.states, batch.actions, batch.rewards = ptr(bt['states']), ptr(bt['actions']), ptr(bt['rewards'])
+        batch.dones, batch.last_masks = ptr(bt['dones']), ptr(bt['last_masks'])
+        batch.padding_masks, batch.mu_probs = ptr(bt['padding_masks']), ptr(bt['mu_probs'])
+        batch.priority_is = ptr(smp['w']) if self.use_priority else None
+        batch.eps_y, batch.eps_pi, batch.eps_alpha, batch.eps_td = [ptr(e) for e in self._eps]
+        rep = None
+        if self._gru is not None:
+            g = self._gru
+            NL, H = g.layers, g.hidden
+            bt['obs'] = torch.zeros(B, L, g.obs_size, **f32)
+            bt['hidden'] = torch.zeros(B, L, NL * H, **f32)
+            bt['states_post'], bt['target_states'] = torch.zeros(B, L, S, **f32), torch.zeros(B, L, S, **f32)
+            rep = _lib.AsacGruRep()
+            rep.shape = self._gru_c
+            rep.params, rep.params_target = ptr(self._rep_flat), ptr(self._rept_flat)
+            rep.m, rep.v = ptr(self._rep_m), ptr(self._rep_v)
+            rep.obs, rep.h0, rep.h0_b_stride = ptr(bt['obs']), ptr(bt['hidden']), L * NL * H
+            rep.states, rep.states_post, rep.target_states = ptr(bt['states']), ptr(bt['states_post']), \
+                ptr(bt['target_states'])
+            for k, t in self._rw.items():
+                setattr(rep, k, ptr(t))
+            rep.rep_tiles = B
+            batch.states_post, batch.target_states = ptr(bt['states_post']), ptr(bt['target_states'])
+        return {'bt': bt, 'smp': smp, 'batch': batch, 'rep': rep, 'specs': None}
+
+    # the batch set of the most recent train() call (tests, bench and summaries read these)
+    _bt = property(lambda self: self._sets[self._cur]['bt'])
+    _smp = property(lambda self: self._sets[self._cur]['smp'])
+    _batch = property(lambda self: self._sets[self._cur]['batch'])
+    _rep = property(lambda self: self._sets[self._cur]['rep'])
+    _specs = property(lambda self: self._sets[self._cur]['specs'])
+
+    @property
+    def _graph(self):
+        return next((g for g in self._graphs if g is not None), None)
 
     def _init_or_restore(self, last_ckpt: int | None) -> None:
         """sac_base.py:568-629."""
@@ -759,8 +784,8 @@ class SAC_Base:
         self.replay_buffer.add(storage, ignore_size=1)
 
     # ------------------------------------------------------------------ the step
-    def _gather_specs(self):
-        rb, bt = self.replay_buffer, self._bt
+    def _gather_specs(self, bt: dict):
+        rb = self.replay_buffer
         S, A = self.state_size, self.c_action_size
         specs = [('index', bt['index'], 4, 0, _lib.ROLE_INDEX),
                  ('last_mask', bt['last_masks'], 1, 0, _lib.ROLE_COPY),
@@ -788,16 +813,42 @@ class SAC_Base:
                 raise ValueError(f'stored column {key} has {rb._row_bytes(key)} bytes per row, expected {nbytes}')
         return specs
 
+    def _enqueue_sample(self, st: dict) -> None:
+        """Prioritized sample + IS weights (replay_buffer.py:347-354) and the window gather fused with the
+        padding rule (replay_buffer.py:356-362, sac_base.py:2435-2453) into batch set `st`, on the current stream."""
+        lib, rb, smp = self._lib, self.replay_buffer, st['smp']
+        check(lib.asac_per_sample(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), self.batch_size, None, rb._seed,
+                                  ptr(rb._draw_counter), ptr(rb._per_state), ptr(smp['slots']), ptr(smp['ids']),
+                                  ptr(smp['p']), ptr(smp['w']), _lib.current_stream()), 'per_sample')
+        rb._gather(smp['ids'], st['specs'], self._padding_action, st['bt']['padding_masks'])
+
     def _enqueue_step(self) -> None:
-        """Everything one train() does on the device (graph-capturable).  Critical path: sample ->
-        gather -> value pass -> critics -> Adam -> policy -> Adam -> post pass -> fused tail; the
-        Polyak update and the Gaussian draws (independent of the sample) and the mu-prob write-back
-        (independent of the tail) run on a forked stream, i.e. as parallel branches of the graph."""
+        """One train() on the device, eagerly: picks the batch sets, primes the first batch when needed."""
+        cur = (1 - self._cur) if (self._sample_ahead and self._primed) else self._cur
+        if self._sample_ahead and not self._primed:
+            self._enqueue_sample(self._sets[cur])
+            self._primed = True
+        self._enqueue_step_sets(cur)
+        self._cur = cur
+
+    def _enqueue_step_sets(self, cur: int) -> None:
+        """Everything one train() does on the device (graph-capturable) for batch set `cur`.  Critical
+        path: value pass -> critics -> Adam -> policy -> Adam -> post pass -> fused tail.  Parallel
+        branches of the graph: the Polyak update and the Gaussian draws; the mu-prob / hidden-state
+        write-backs; and — like the reference's prefetch thread, which samples while `_train` runs
+        (replay_buffer.py:339-375) — the sample + gather of the NEXT step into the other batch set.
+        That branch reads the tree before this step's priority update and the rings before this
+        step's write-backs (both ordered after it), so the schedule is deterministic: batch N + 1
+        sees the priorities as of update N - 1."""
         lib, rb = self._lib, self.replay_buffer
-        smp, cfg, prm, batch, work = self._smp, self._cfg, self._prm, self._batch, self._work
+        st = self._sets[cur]
+        nxt = self._sets[1 - cur] if self._sample_ahead else None
+        smp, cfg, prm, batch, work = st['smp'], self._cfg, self._prm, st['batch'], self._work
+        bt, rep_c = st['bt'], st['rep']
         B = self.batch_size
         main = torch.cuda.current_stream(self.device)
         side = self._side_stream
+        ahead = self._prefetch_stream
         peers = C.byref(self._peer_table) if self._peer_table is not None else None
         fused = self._world == 1 or peers is not None  # one code path for 1 GPU and for NVLink peers
         fast_tail = fused and self.use_priority and B <= 1024
@@ -808,47 +859,52 @@ class SAC_Base:
             if self._prefetch is not None:  # policy parameters and Adam moments -> L2 while sample / gather run
                 check(lib.asac_l2_prefetch(self._prefetch[0], self._prefetch[1], len(self._prefetch[2]), s2),
                       'l2_prefetch')
-            if fast_tail or self._rep is not None:
+            if fast_tail or rep_c is not None:
                 check(lib.asac_sac_polyak(C.byref(cfg), C.byref(prm), -1.0, s2), 'sac_polyak')
-            if self._rep is not None:
+            if rep_c is not None:
                 check(lib.asac_flat_polyak(ptr(self._rept_flat), ptr(self._rep_flat), self._gru.count,
                                            ptr(self._counters), int(self.update_target_per_step), cfg.tau,
                                            cfg.one_minus_tau, 0, s2), 'flat_polyak')
             check(lib.asac_fill_normal(ptr(self._noise), self._noise.numel(), self._noise_seed, ptr(self._counters),
                                        0, s2), 'fill_normal')
         stream = main.cuda_stream
-        # 1. prioritized sample + IS weights (replay_buffer.py:347-354)
-        check(lib.asac_per_sample(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), B, None, rb._seed,
-                                  ptr(rb._draw_counter), ptr(rb._per_state), ptr(smp['slots']), ptr(smp['ids']),
-                                  ptr(smp['p']), ptr(smp['w']), stream), 'per_sample')
-        # 2. window gather fused with the padding rule (replay_buffer.py:356-362, sac_base.py:2435-2453)
-        rb._gather(smp['ids'], self._specs, self._padding_action, self._bt['padding_masks'])
+        # 1 + 2. sample and gather: of the next step on its own branch, or (single batch set) of this one here
+        if nxt is not None:
+            ahead.wait_stream(main)
+            with torch.cuda.stream(ahead):
+                self._enqueue_sample(nxt)
+        else:
+            self._enqueue_sample(st)
         main.wait_stream(side)
         # 3. _train + get_l_probs + _get_td_error
-        if self._rep is not None:  # trained GRU representation (sac_base.py:2066-2116)
+        if rep_c is not None:  # trained GRU representation (sac_base.py:2066-2116)
             check(lib.asac_sac_step_networks_rep(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work),
-                                                 C.byref(self._rep), 0, peers, stream), 'sac_step_networks_rep')
+                                                 C.byref(rep_c), 0, peers, stream), 'sac_step_networks_rep')
             if not fast_tail:
                 check(lib.asac_sac_staged_tail(C.byref(cfg), C.byref(prm), C.byref(work), stream), 'sac_staged_tail')
         elif not fused:
-            self._enqueue_sac_step_data_parallel(stream)
+            self._enqueue_sac_step_data_parallel(stream, batch)
         elif fast_tail:
             check(lib.asac_sac_step_networks(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), 0, peers,
                                              stream), 'sac_step_networks')
         elif peers is not None:  # non-prioritized data-parallel run: NCCL path keeps the staged tail
-            self._enqueue_sac_step_data_parallel(stream)
+            self._enqueue_sac_step_data_parallel(stream, batch)
         else:
             check(lib.asac_sac_step(C.byref(cfg), C.byref(prm), C.byref(batch), C.byref(work), stream), 'sac_step')
         # 4. mu-prob write-back (sac_base.py:2598-2605): needs the post pass only -> side branch
-        if self.use_n_step_is or self._rep is not None:
+        if self.use_n_step_is or rep_c is not None:
             side.wait_stream(main)
+            if nxt is not None:
+                side.wait_stream(ahead)  # the next batch was gathered from the rings as they were before these writes
             with torch.cuda.stream(side):
-                if self._rep is not None:  # next hidden states -> pre_seq_hidden_state of the following rows (:2589-2596)
+                if rep_c is not None:  # next hidden states -> pre_seq_hidden_state of the following rows (:2589-2596)
                     rb.write_back(smp['ids'], 'pre_seq_hidden_state', self._rw['hn_post'], 1 - self.burn_in_step,
-                                  self._bt['padding_masks'], n_rows=cfg.seq_len - 1)
+                                  bt['padding_masks'], n_rows=cfg.seq_len - 1)
                 if self.use_n_step_is:
                     rb.write_back(smp['ids'], 'mu_prob', self._wk['pi_probs'], -self.burn_in_step,
-                                  self._bt['padding_masks'])
+                                  bt['padding_masks'])
+        if nxt is not None:
+            main.wait_stream(ahead)  # ... and sampled from the tree as it was before this step's priority update
         # 5. alpha step, td error, priority update (sac_base.py:2115-2116, 2571-2584), step counters
         if self.use_priority:
             if fast_tail:
@@ -860,13 +916,13 @@ class SAC_Base:
                                           ptr(self._wk['td_error']), B, float(rb.td_error_min),
                                           float(rb.td_error_max), float(rb.alpha), 0, ptr(rb._per_state), stream),
                       'per_update')
-        if self.use_n_step_is or self._rep is not None:
+        if self.use_n_step_is or rep_c is not None:
             main.wait_stream(side)
 
-    def _enqueue_sac_step_data_parallel(self, stream) -> None:
+    def _enqueue_sac_step_data_parallel(self, stream, batch_struct) -> None:
         """asac_sac_step with a SUM all-reduce of each reduced gradient buffer between the backward
         pass and its Adam kernel (grad_scale = 1/world): the only collective of the step."""
-        lib, cfg, prm, batch, work = self._lib, C.byref(self._cfg), C.byref(self._prm), C.byref(self._batch), \
+        lib, cfg, prm, batch, work = self._lib, C.byref(self._cfg), C.byref(self._prm), C.byref(batch_struct), \
             C.byref(self._work)
         scale = 1.0 / self._world
         check(lib.asac_sac_polyak(cfg, prm, -1.0, stream), 'polyak')
@@ -897,18 +953,21 @@ class SAC_Base:
         with torch.cuda.device(self.device):
             key = rb._columns_version
             if self._graph_columns_key != key:  # first step, or the storage was re-allocated (load / clear)
-                self._specs = self._gather_specs()
-                self._graph, self._graph_columns_key = None, key
+                for st in self._sets:
+                    st['specs'] = self._gather_specs(st['bt'])
+                self._graphs, self._graph_columns_key, self._primed = [None, None], key, False
                 self._enqueue_step()  # eager warm-up (also sets the kernels' shared-memory attributes)
             elif not self.use_cuda_graph or (self._world > 1 and not self._graph_collectives):
                 self._enqueue_step()
-            else:
-                if self._graph is None:
+            else:  # one captured graph per batch set (they alternate)
+                cur = (1 - self._cur) if self._sample_ahead else self._cur
+                if self._graphs[cur] is None:
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
-                        self._enqueue_step()
-                    self._graph = graph
-                self._graph.replay()
+                        self._enqueue_step_sets(cur)
+                    self._graphs[cur] = graph
+                self._graphs[cur].replay()
+                self._cur = cur
         if self.save_model_per_step and step % self.save_model_per_step == 0:
             self.save_model()
         if self.summary_writer is not None and step % self.write_summary_per_step == 0:
@@ -936,7 +995,7 @@ class SAC_Base:
 
     def close(self):
         self._closed = True
-        self._graph = None
+        self._graphs = [None, None]
         if hasattr(self, 'replay_buffer'):
             self.replay_buffer.check_nan()
             self.replay_buffer.close()

@@ -288,3 +288,39 @@ def test_ring_wrap_long_episodes_and_unsorted_updates_against_oracle():
     rb.add(long_ep, ignore_size=1); ref.add(long_ep, ignore_size=1)
     _same_state(rb, ref, 'long episode')
     rb.close()
+
+
+def test_capacity_rounding_clear_copy_and_storage_access():
+    """The remaining public surface of PrioritizedReplayBuffer (replay_buffer.py:264, 401-410, 448-470):
+    capacity rounded DOWN to a power of two, get_storage_data / get_storage_data_ids, copy() into a
+    second buffer (same samples afterwards), clear() (empty again, sample() is None, is_full False)."""
+    from asac_b200 import PrioritizedReplayBuffer
+    B = 4
+    rb = PrioritizedReplayBuffer(batch_size=B, sample_prev_n=0, sample_post_n=1, device='cuda:0', capacity=24, alpha=0.9)
+    assert rb.capacity == 16  # 2 ** floor(log2(24))
+    rng = np.random.RandomState(8)
+    eps = [_rows(rng, 7), _rows(rng, 6)]
+    for ep in eps:
+        rb.add(ep, ignore_size=1)
+    assert rb.size == 13 and not rb.is_full and rb.is_lg_batch_size and rb.get_curr_id() == 13
+    ids = np.array([0, 5, 7, 12], dtype=np.int64)
+    got = rb.get_storage_data(ids)
+    stacked = {k: np.concatenate([e[k] for e in eps]) for k in eps[0]}
+    for k, v in stacked.items():
+        assert np.array_equal(_np(got[k]), v[ids]), k
+    assert np.array_equal(_np(rb.get_storage_data_ids(ids)), ids)
+    other = PrioritizedReplayBuffer(batch_size=B, sample_prev_n=0, sample_post_n=1, device='cuda:0', capacity=16, alpha=0.9)
+    other.copy(rb)
+    assert other.size == rb.size and torch.equal(other.tree_nodes(), rb.tree_nodes())
+    u = rng.random_sample(B)
+    a, b = rb.sample(unit_uniform=u), other.sample(unit_uniform=u)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    for k in a[1]:
+        assert torch.equal(a[1][k], b[1][k]), k
+    rb.add(_rows(rng, 9), ignore_size=1)  # 22 rows into 16 slots
+    assert rb.is_full and rb.size == 16
+    rb.clear()
+    assert rb.size == 0 and not rb.is_full and rb.sample() is None and float(rb.tree_nodes()[1]) == 0.0
+    rb.add(eps[0], ignore_size=1)  # usable again after clear()
+    assert rb.size == 7
+    rb.close(); other.close()
