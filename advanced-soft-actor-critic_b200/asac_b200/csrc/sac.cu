@@ -1101,7 +1101,7 @@ __global__ void __launch_bounds__(1024) k_step_epilogue(const __grid_constant__ 
         if (t == 0) a.per_state[3] = 1.0;  // the reference raises 'td_error has nan'
         return;
     }
-    block_tree_apply(a.nodes, a.capacity, a.levels, slot, value, active, s_apply);
+    if (a.nodes) block_tree_apply(a.nodes, a.capacity, a.levels, slot, value, active, s_apply);  // else: deferred
 }
 
 __global__ void k_bump(int64_t *counters, int mask) {
@@ -1738,7 +1738,7 @@ extern "C" int asac_sac_finish_step(const AsacSacConfig *cfg, const AsacSacParam
     if (rc != ASAC_OK) return rc;
     ASAC_REQUIRE(is_pow2(capacity), "asac_sac_finish_step: capacity is not a power of two");
     ASAC_REQUIRE(cfg->batch <= 1024, "asac_sac_finish_step: batch %d > 1024", cfg->batch);
-    ASAC_REQUIRE(prm && wrk && nodes && store_ids && data_ids && per_state, "asac_sac_finish_step: null pointer");
+    ASAC_REQUIRE(prm && wrk && store_ids && data_ids && per_state, "asac_sac_finish_step: null pointer");
     EpilogueArgs a;
     if ((rc = make_exchange(a.px, cfg, peers, 2)) != ASAC_OK) return rc;
     a.grad_scale = (peers && peers->world > 1) ? 1.f / (float)peers->world : 1.f;

@@ -504,6 +504,12 @@ class SAC_Base:
         self._sample_ahead = os.environ.get('ASAC_SAMPLE_AHEAD', '1') != '0'
         self._sets = [self._make_batch_set() for _ in range(2 if self._sample_ahead else 1)]
         self._cur, self._primed = 0, False
+        # With sampling one step ahead the tree update of step N is only needed by the sample of step N + 2:
+        # the fused tail then writes the td errors and the update itself runs first thing on the NEXT
+        # step's ahead branch, off the critical path (same priorities seen by every batch as before;
+        # ASAC_DEFER_TREE=0 keeps it inside the tail).  `_pending` = a step's tree update has not run yet.
+        self._defer_tree = self._sample_ahead and os.environ.get('ASAC_DEFER_TREE', '1') != '0'
+        self._pending = self._defer_active = False
         self._prefetch_stream = torch.cuda.Stream(device=dev)
         self._noise_seed = (int(self._seed) if self._seed is not None else random.getrandbits(62)) ^ 0x5AC5AC
         self._side_stream = torch.cuda.Stream(device=dev)
@@ -663,6 +669,7 @@ class SAC_Base:
     def save_model(self, save_replay_buffer=False) -> None:
         if self.ckpt_dir is None:
             return
+        self.flush_priority_update()
         step = self.get_global_step()
         path = self.ckpt_dir.joinpath(f'{step}.pth')
         torch.save({k: (v.detach().clone() if isinstance(v, torch.Tensor) else v.state_dict())
@@ -822,16 +829,33 @@ class SAC_Base:
                                   ptr(smp['p']), ptr(smp['w']), _lib.current_stream()), 'per_sample')
         rb._gather(smp['ids'], st['specs'], self._padding_action, st['bt']['padding_masks'])
 
+    def _enqueue_tree_update(self, st: dict) -> None:
+        """PrioritizedReplayBuffer.update (replay_buffer.py:412-427) for the batch of set `st` from the td
+        errors of the last step, on the current stream."""
+        rb = self.replay_buffer
+        check(self._lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), ptr(st['smp']['ids']),
+                                        ptr(self._wk['td_error']), self.batch_size, float(rb.td_error_min),
+                                        float(rb.td_error_max), float(rb.alpha), 0, ptr(rb._per_state),
+                                        _lib.current_stream()), 'per_update')
+
+    def flush_priority_update(self) -> None:
+        """Applies a deferred tree update now (before the replay is saved, closed or read from outside).
+        A later step re-applying the same td errors is harmless: same ids, same values, same guard."""
+        if self._pending:
+            with torch.cuda.device(self.device):
+                self._enqueue_tree_update(self._sets[self._cur])
+            self._pending = False
+
     def _enqueue_step(self) -> None:
         """One train() on the device, eagerly: picks the batch sets, primes the first batch when needed."""
         cur = (1 - self._cur) if (self._sample_ahead and self._primed) else self._cur
         if self._sample_ahead and not self._primed:
             self._enqueue_sample(self._sets[cur])
             self._primed = True
-        self._enqueue_step_sets(cur)
+        self._enqueue_step_sets(cur, apply_pending=self._pending)
         self._cur = cur
 
-    def _enqueue_step_sets(self, cur: int) -> None:
+    def _enqueue_step_sets(self, cur: int, apply_pending: bool = True) -> None:
         """Everything one train() does on the device (graph-capturable) for batch set `cur`.  Critical
         path: value pass -> critics -> Adam -> policy -> Adam -> post pass -> fused tail.  Parallel
         branches of the graph: the Polyak update and the Gaussian draws; the mu-prob / hidden-state
@@ -869,9 +893,12 @@ class SAC_Base:
                                        0, s2), 'fill_normal')
         stream = main.cuda_stream
         # 1 + 2. sample and gather: of the next step on its own branch, or (single batch set) of this one here
+        defer = self._defer_active = self._defer_tree and fast_tail
         if nxt is not None:
             ahead.wait_stream(main)
             with torch.cuda.stream(ahead):
+                if defer and apply_pending:  # the previous step trained on `nxt`'s buffers: its tree update, deferred
+                    self._enqueue_tree_update(nxt)
                 self._enqueue_sample(nxt)
         else:
             self._enqueue_sample(st)
@@ -908,9 +935,11 @@ class SAC_Base:
         # 5. alpha step, td error, priority update (sac_base.py:2115-2116, 2571-2584), step counters
         if self.use_priority:
             if fast_tail:
-                check(lib.asac_sac_finish_step(C.byref(cfg), C.byref(prm), C.byref(work), ptr(rb._nodes), rb.capacity,
+                check(lib.asac_sac_finish_step(C.byref(cfg), C.byref(prm), C.byref(work),
+                                               None if defer else ptr(rb._nodes), rb.capacity,
                                                ptr(rb._store_ids), ptr(smp['ids']), ptr(rb._per_state), peers,
                                                stream), 'sac_finish_step')
+                self._pending = defer
             else:
                 check(lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), ptr(smp['ids']),
                                           ptr(self._wk['td_error']), B, float(rb.td_error_min),
@@ -956,6 +985,7 @@ class SAC_Base:
                 for st in self._sets:
                     st['specs'] = self._gather_specs(st['bt'])
                 self._graphs, self._graph_columns_key, self._primed = [None, None], key, False
+                self._pending = False  # the storage was re-allocated: a deferred update has nothing to apply to
                 self._enqueue_step()  # eager warm-up (also sets the kernels' shared-memory attributes)
             elif not self.use_cuda_graph or (self._world > 1 and not self._graph_collectives):
                 self._enqueue_step()
@@ -968,6 +998,7 @@ class SAC_Base:
                     self._graphs[cur] = graph
                 self._graphs[cur].replay()
                 self._cur = cur
+                self._pending = self._defer_active  # (a flush in between cleared it; the replay deferred again)
         if self.save_model_per_step and step % self.save_model_per_step == 0:
             self.save_model()
         if self.summary_writer is not None and step % self.write_summary_per_step == 0:
@@ -995,6 +1026,8 @@ class SAC_Base:
 
     def close(self):
         self._closed = True
+        if hasattr(self, 'replay_buffer') and getattr(self, '_pending', False):
+            self.flush_priority_update()
         self._graphs = [None, None]
         if hasattr(self, 'replay_buffer'):
             self.replay_buffer.check_nan()

@@ -367,7 +367,9 @@ int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacParams *prm, c
  * alpha reduce + Adam (sac_base.py:1941-1948), _get_td_error's tail with the updated alpha
  * (:2223-2245) -> work.y_td / work.td_error, PrioritizedReplayBuffer.update on those td errors
  * (replay_buffer.py:412-427; cfg->td_error_min/max/per_alpha), and the global-step / optimizer
- * counters (sac_base.py:2607).  Equals asac_sac_step's tail followed by asac_per_update. */
+ * counters (sac_base.py:2607).  Equals asac_sac_step's tail followed by asac_per_update.
+ * nodes == NULL defers the tree update: td errors are written, the caller applies them later with
+ * asac_per_update(work->td_error) (the learner does so on the sample-ahead branch of its next step). */
 int asac_sac_finish_step(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *work,
                          float *nodes, int64_t capacity, const int64_t *store_ids,
                          const int64_t *data_ids, double *per_state, const AsacPeerTable *peers,
