@@ -156,7 +156,8 @@ def stage_work(cfg):
         'policy_backward': dict(bound='tensor', flops=(3 * pi + 2 * E * q) * B),
         'adam_pi': dict(bound='hbm', bytes=Ppi * 4 * 7),
         'value_pass_post': dict(bound='tensor', flops=pi * B * L + E * q * (B * (n + 1) + B)),
-        'finish_step': dict(bound='hbm', bytes=B * (12 * D + 16) + B * 4 * (2 + E) + 64),
+        'finish_step': dict(bound='hbm', bytes=B * 4 * (2 + E) + B * 8 + 64),
+        'finish_step_fused_tree': dict(bound='hbm', bytes=B * (12 * D + 16) + B * 4 * (2 + E) + 64),
         'adam_alpha': dict(bound='hbm', bytes=64),
         'per_update': dict(bound='hbm', bytes=B * (12 * D + 16)),
         'write_back': dict(bound='hbm', bytes=B * (L - 1) * (A * 4 + 8)),
@@ -241,9 +242,15 @@ def profile_stages(sac, steps):
         ('policy_backward', lambda: check(lib.asac_sac_policy_backward(cfg, prm, batch, work, s()))),
         ('adam_pi', lambda: check(lib.asac_sac_reduce_adam(cfg, prm, work, 1, s()))),
         ('value_pass_post', lambda: check(lib.asac_sac_post(cfg, prm, batch, work, s()))),
-        ('finish_step', lambda: check(lib.asac_sac_finish_step(cfg, prm, work, ptr(rb._nodes), rb.capacity,
-                                                               ptr(rb._store_ids), ptr(smp['ids']),
+        # the step's tail as the learner runs it (tree update deferred to the next step's ahead branch when
+        # sampling one step ahead) and the fully fused variant (alpha + td + tree update in one CTA)
+        ('finish_step', lambda: check(lib.asac_sac_finish_step(cfg, prm, work,
+                                                               None if sac._defer_active else ptr(rb._nodes),
+                                                               rb.capacity, ptr(rb._store_ids), ptr(smp['ids']),
                                                                ptr(rb._per_state), None, s()))),
+        ('finish_step_fused_tree', lambda: check(lib.asac_sac_finish_step(cfg, prm, work, ptr(rb._nodes), rb.capacity,
+                                                                          ptr(rb._store_ids), ptr(smp['ids']),
+                                                                          ptr(rb._per_state), None, s()))),
         ('adam_alpha', lambda: check(lib.asac_sac_reduce_adam(cfg, prm, work, 2, s()))),
         ('per_update', lambda: check(lib.asac_per_update(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids),
                                                          ptr(smp['ids']), ptr(sac._wk['td_error']), B,
@@ -491,7 +498,9 @@ def run_gpu(args):
                 ach = w['flops'] / (us * 1e-6) / 1e12
                 kernels[name] = {'us': round(us, 3), 'bound': 'tensor', 'algorithmic_flops': w['flops'],
                                  'achieved_TFLOPs': round(ach, 5), 'frac': ach / tf_peak}
-        not_in_step = ('adam_alpha', 'per_update')  # standalone entry points; the step runs finish_step
+        # standalone entry points that are not part of the step as the learner schedules it
+        not_in_step = ('adam_alpha', 'finish_step_fused_tree') if sac._defer_active else \
+            ('adam_alpha', 'per_update', 'finish_step_fused_tree')
         in_step = {k: v for k, v in prof.items() if k not in not_in_step}
         top = max(in_step, key=in_step.get)
         k = kernels[top]
