@@ -3,12 +3,16 @@
 // the form of envs/test/nn_rnn.py:6-21 — forward over whole sampled windows and back-propagation
 // through time of the critic loss's state gradient (sac_base.py:1510-1601, 2066-2105).
 //
-// The recurrence is a chain of L x layers dependent cells of a few hundred FMAs each: there is no
-// parallelism inside a sequence worth a block barrier, so ONE WARP owns one sequence (lanes = gate
-// rows in the matrix-vector phase, = hidden units in the gate phase, __syncwarp between them) and
-// the batch spreads over the SMs.  Weights sit in shared memory in rows of odd stride
-// [W_ih row | W_hh row | b_ih | b_hh] (conflict-free for row-per-lane and column-per-lane reads);
-// the sequence's inputs are staged once, coalesced, before the chain starts.
+// The recurrence is a chain of dependent cells of a few hundred FMAs each: there is no parallelism
+// inside a sequence worth a block barrier, so ONE WARP owns one sequence and the batch spreads over
+// the SMs.  A lane owns a hidden unit (all three gates of it, so no gate exchange); when
+// layers x width <= 32 the layers run as a WAVEFRONT — lane (l, j), layer l one step behind layer
+// l - 1 — which turns L x layers dependent cells into L + layers - 1 stages, and for widths 8 / 16 / 32
+// the lane's weight rows (forward) or columns (backward) live in registers.  Otherwise weights are
+// read from shared memory, staged in rows of odd stride [W_ih row | W_hh row | b_ih | b_hh]
+// (conflict-free for row-per-lane and column-per-lane reads).  Inputs, saved gates and hidden
+// states of a sequence are staged once, with 8 loads per thread in flight, before the chain starts.
+// Measured history (config 4, B200): forward 95 -> 22.5 us, backward 113 -> 34.8 us.
 #include <math.h>
 
 #include "common.cuh"
@@ -120,11 +124,11 @@ struct GruFwdArgs {
 
 constexpr int GRU_FWD_WARPS = 2;
 
-// per-warp shared memory of the forward kernel: inputs xs[L][in0], layer 0's input projection
-// gi0[L][3H], current hidden states h[layers][H], gate scratch [4H] (sequential path only)
+// per-warp shared memory of the forward kernel: inputs xs[L][in0 padded to 4], layer 0's input
+// projection gi0[L][3H] (used unless the projection runs inside the stage loop), hidden states h[layers][H]
 __host__ __device__ __forceinline__ int gru_fwd_warp_floats(const AsacGruShape &s, int L) {
     return L * ((s.obs_size + s.action_size + 3) & ~3) + ((L * 3 * s.hidden + 3) & ~3) +
-           ((s.layers * s.hidden + 3) & ~3) + 4 * s.hidden;
+           ((s.layers * s.hidden + 3) & ~3);
 }
 
 // One GRU cell for hidden unit j of a layer whose three gate rows start at wr / wz / wn (shared
