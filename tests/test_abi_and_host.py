@@ -199,3 +199,69 @@ def test_reference_checkpoint_fixtures_have_the_expected_layout():
         assert {'_id', 'index', 'last_mask', 'obs_vector', 'action', 'reward', 'done', 'mu_prob',
                 'pre_seq_hidden_state', 'p_size', 'p_id'} == set(store.files)
         assert store['pre_seq_hidden_state'].shape[1:] == ((2, 8) if rep else (0,))
+
+
+def test_recurrent_representation_lowering_on_the_host():
+    """lowering.analyze_rep / GRU flat layout without a GPU: the envs/test/nn_rnn.py form lowers to a
+    GruShape whose flat order is torch.nn.GRU's own, the state_dict round-trips through the flat
+    vector, the `m.GRU` wrapper equals the oracle's restatement of the cell (and, when the reference
+    is mounted, nothing else), and representations that are not ONE stock GRU are rejected."""
+    import numpy as np
+    from asac_b200 import _lib, lowering
+    import asac_b200.nn_models as m
+    from oracle.rep_oracle import gru_forward
+
+    class Rep(m.ModelBaseRep):
+        def _build_model(self):
+            self.rnn = m.GRU(self.obs_shapes[0][0] + self.c_action_size, 8, 2)
+
+        def forward(self, obs_list, pre_action, pre_seq_hidden_state, padding_mask=None):
+            h0 = None if pre_seq_hidden_state is None else pre_seq_hidden_state[:, 0]
+            return self.rnn(torch.cat([obs_list[0], pre_action], dim=-1), h0)
+
+    rep = Rep(['v'], [(6,)], [], 2, False)
+    shape, params = lowering.analyze_rep(rep, [(6,)], 2)
+    assert shape == lowering.GruShape(6, 2, 8, 2) and shape.count == 864 == sum(p.numel() for p in params)
+    cs = _lib.AsacGruShape(6, 2, 8, 2)
+    assert _lib.load().asac_gru_param_count(C.byref(cs)) == shape.count
+    assert _lib.load().asac_gru_backward_tile(C.byref(cs), 40) == 4  # config 4: 4 sequences per CTA fit
+    sd = {k: v.detach().clone() for k, v in rep.state_dict().items()}
+    flat = lowering.gru_flat_from_state_dict(shape, sd)
+    back = lowering.gru_state_dict_from_flat(shape, flat)
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    # binding: the nn.GRU parameters become views of the flat buffer, in flat order
+    buf = torch.zeros(shape.stride)
+    lowering.bind_parameters(params, buf)
+    assert torch.equal(buf[:shape.count], flat[:shape.count])
+    assert rep.rnn._grus[0].weight_ih_l0.data_ptr() == buf.data_ptr()
+    # the wrapper (what the probe and the actor-side cross-check run) == the oracle's cell
+    rng = np.random.RandomState(0)
+    obs = torch.from_numpy(rng.randn(3, 5, 6).astype(np.float32))
+    pre = torch.from_numpy(rng.rand(3, 5, 2).astype(np.float32))
+    hid = torch.from_numpy(rng.randn(3, 5, 2, 8).astype(np.float32))
+    with torch.no_grad():
+        state, hn = rep([obs], pre, hid)
+        s2, hn2 = gru_forward(sd, 2, torch.cat([obs, pre], -1), hid[:, 0])
+    assert state.shape == (3, 5, 8) and hn.shape == (3, 5, 2, 8)
+    assert torch.allclose(state, s2, atol=1e-6) and torch.allclose(hn, hn2, atol=1e-6)
+    assert lowering.analyze_rep(m.ModelSimpleRep(['v'], [(6,)], [], 2, False), [(6,)], 2) is None
+
+    class TwoGrus(Rep):
+        def _build_model(self):
+            super()._build_model()
+            self.rnn2 = m.GRU(8, 8, 1)
+
+    class GruAndDense(Rep):
+        def _build_model(self):
+            super()._build_model()
+            self.dense = m.LinearLayers(8, 8, 1)
+
+    class WrongInput(m.ModelBaseRep):
+        def _build_model(self):
+            self.rnn = m.GRU(6, 8, 1)  # no pre_action column
+
+    for bad in (TwoGrus, GruAndDense, WrongInput):
+        with pytest.raises(lowering.NotStockNetwork):
+            lowering.analyze_rep(bad(['v'], [(6,)], [], 2, False), [(6,)], 2)
+    with pytest.raises(NotImplementedError):
+        m.GRU(8, 8, 1)(torch.zeros(1, 2, 8), None, torch.zeros(1, 2, dtype=torch.bool))
