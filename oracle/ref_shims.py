@@ -36,6 +36,10 @@ def install_shims() -> None:
     if not torch.cuda.is_available():
         torch.cuda.Stream = lambda *a, **k: None
         torch.Tensor.pin_memory = lambda self, *a, **k: self
+    try:  # first import of torchvision walks sys.modules with inspect and trips over a namespace package
+        import torchvision  # noqa: F401  (the reference's `algorithm`): get it over with beforehand
+    except Exception:  # noqa: BLE001
+        pass
     root = str(REFERENCE_ROOT)
     if root not in sys.path:
         sys.path.insert(0, root)
@@ -62,6 +66,16 @@ def import_reference():
         mod = sys.modules[name]
         if not str(getattr(mod, '__file__', '')).startswith(str(REFERENCE_ROOT)):
             del sys.modules[name]
-    from algorithm import replay_buffer as ref_rb
-    from algorithm.sac_base import SAC_Base
+    # The reference's ``algorithm`` directory has no __init__.py (a namespace package), and a regular
+    # package of the same name ANYWHERE on sys.path beats a namespace package: hide the directories that
+    # hold the product's alias package while importing (e.g. under pytest).  Once imported, submodules
+    # resolve through ``algorithm.__path__``, not sys.path.
+    saved = list(sys.path)
+    sys.path[:] = [str(REFERENCE_ROOT)] + [p for p in saved
+                                            if not (Path(p or '.') / 'algorithm' / '__init__.py').exists()]
+    try:
+        from algorithm import replay_buffer as ref_rb
+        from algorithm.sac_base import SAC_Base
+    finally:
+        sys.path[:] = saved
     return SAC_Base, ref_rb, None
