@@ -465,11 +465,6 @@ class SAC_Base:
         n, T = self.n_step, self._n_tiles
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
-        # one noise buffer, four views: eps_y, eps_pi, eps_alpha, eps_td
-        sizes = [B * (n + 1) * A, B * A, B * A, B * (n + 1) * A]
-        self._noise = torch.zeros(sum(sizes), **f32)
-        offs = np.cumsum([0] + sizes)
-        self._eps = [self._noise[offs[i]:offs[i + 1]] for i in range(4)]
         Pq, Ppi = self._q_shape.stride, self._pi_shape.stride
         wk = self._wk = {
             'y': torch.zeros(B, **f32), 'tq': torch.zeros(E, B, **f32), 'q_val': torch.zeros(E, B, **f32),
@@ -508,6 +503,7 @@ class SAC_Base:
         # the fused tail then writes the td errors and the update itself runs first thing on the NEXT
         # step's ahead branch, off the critical path (same priorities seen by every batch as before;
         # ASAC_DEFER_TREE=0 keeps it inside the tail).  `_pending` = a step's tree update has not run yet.
+        self._noise_ahead = self._sample_ahead and os.environ.get('ASAC_NOISE_AHEAD', '1') != '0'
         self._defer_tree = self._sample_ahead and os.environ.get('ASAC_DEFER_TREE', '1') != '0'
         self._pending = self._defer_active = False
         self._prefetch_stream = torch.cuda.Stream(device=dev)
@@ -558,7 +554,12 @@ class SAC_Base:
         batch.dones, batch.last_masks = ptr(bt['dones']), ptr(bt['last_masks'])
         batch.padding_masks, batch.mu_probs = ptr(bt['padding_masks']), ptr(bt['mu_probs'])
         batch.priority_is = ptr(smp['w']) if self.use_priority else None
-        batch.eps_y, batch.eps_pi, batch.eps_alpha, batch.eps_td = [ptr(e) for e in self._eps]
+        # one noise buffer per batch set, four views: eps_y, eps_pi, eps_alpha, eps_td
+        n = self.n_step
+        sizes = [B * (n + 1) * A, B * A, B * A, B * (n + 1) * A]
+        noise = torch.zeros(sum(sizes), **f32)
+        offs = np.cumsum([0] + sizes)
+        batch.eps_y, batch.eps_pi, batch.eps_alpha, batch.eps_td = [ptr(noise[offs[i]:offs[i + 1]]) for i in range(4)]
         rep = None
         if self._gru is not None:
             g = self._gru
@@ -577,7 +578,7 @@ class SAC_Base:
                 setattr(rep, k, ptr(t))
             rep.rep_tiles = B
             batch.states_post, batch.target_states = ptr(bt['states_post']), ptr(bt['target_states'])
-        return {'bt': bt, 'smp': smp, 'batch': batch, 'rep': rep, 'specs': None}
+        return {'bt': bt, 'smp': smp, 'batch': batch, 'rep': rep, 'specs': None, 'noise': noise}
 
     # the batch set of the most recent train() call (tests, bench and summaries read these)
     _bt = property(lambda self: self._sets[self._cur]['bt'])
@@ -585,6 +586,7 @@ class SAC_Base:
     _batch = property(lambda self: self._sets[self._cur]['batch'])
     _rep = property(lambda self: self._sets[self._cur]['rep'])
     _specs = property(lambda self: self._sets[self._cur]['specs'])
+    _noise = property(lambda self: self._sets[self._cur]['noise'])
 
     @property
     def _graph(self):
@@ -820,6 +822,12 @@ class SAC_Base:
                 raise ValueError(f'stored column {key} has {rb._row_bytes(key)} bytes per row, expected {nbytes}')
         return specs
 
+    def _enqueue_noise(self, st: dict, stream_id: int) -> None:
+        """The four Gaussian draws of a step (sac_base.py:1346, 1883, 1932, 2223) into batch set `st`:
+        Philox keyed by (seed, global step at execution, stream_id)."""
+        check(self._lib.asac_fill_normal(ptr(st['noise']), st['noise'].numel(), self._noise_seed, ptr(self._counters),
+                                         stream_id, _lib.current_stream()), 'fill_normal')
+
     def _enqueue_sample(self, st: dict) -> None:
         """Prioritized sample + IS weights (replay_buffer.py:347-354) and the window gather fused with the
         padding rule (replay_buffer.py:356-362, sac_base.py:2435-2453) into batch set `st`, on the current stream."""
@@ -851,6 +859,8 @@ class SAC_Base:
         cur = (1 - self._cur) if (self._sample_ahead and self._primed) else self._cur
         if self._sample_ahead and not self._primed:
             self._enqueue_sample(self._sets[cur])
+            if self._noise_ahead:
+                self._enqueue_noise(self._sets[cur], 1)  # later steps get theirs one step ahead (stream 0)
             self._primed = True
         self._enqueue_step_sets(cur, apply_pending=self._pending)
         self._cur = cur
@@ -889,8 +899,8 @@ class SAC_Base:
                 check(lib.asac_flat_polyak(ptr(self._rept_flat), ptr(self._rep_flat), self._gru.count,
                                            ptr(self._counters), int(self.update_target_per_step), cfg.tau,
                                            cfg.one_minus_tau, 0, s2), 'flat_polyak')
-            check(lib.asac_fill_normal(ptr(self._noise), self._noise.numel(), self._noise_seed, ptr(self._counters),
-                                       0, s2), 'fill_normal')
+            if nxt is None or not self._noise_ahead:  # this step's draws, next to the Polyak update
+                self._enqueue_noise(st, 0)
         stream = main.cuda_stream
         # 1 + 2. sample and gather: of the next step on its own branch, or (single batch set) of this one here
         defer = self._defer_active = self._defer_tree and fast_tail
@@ -900,6 +910,9 @@ class SAC_Base:
                 if defer and apply_pending:  # the previous step trained on `nxt`'s buffers: its tree update, deferred
                     self._enqueue_tree_update(nxt)
                 self._enqueue_sample(nxt)
+                if self._noise_ahead:
+                    self._enqueue_noise(nxt, 0)  # the next step's draws too (the global step is read before this
+                #                              step's tail advances it: the branch is joined ahead of the tail)
         else:
             self._enqueue_sample(st)
         main.wait_stream(side)
