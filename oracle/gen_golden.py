@@ -614,6 +614,154 @@ def gen_ckpt_case(name, *, rnn: bool, seed: int):
     print('wrote', out_dir, sorted(x.name for x in (out_dir / 'model').iterdir()))
 
 
+def gen_sac_discrete_case(name, *, S, d_action_sizes, A, E, B, b, n, steps, seed, use_priority=True, **hyper):
+    """``_train`` + ``get_l_probs`` + ``_get_td_error`` with discrete (A = 0) or hybrid (A > 0) action
+    branches and the stock nets of envs/test/nn.py (sac_base.py:1356-1421, 1858-1880, 1924-1929):
+    fixture for oracle/discrete_oracle.py."""
+    SAC_Base, _, _ = import_reference()
+    nn = load_reference_nn('envs/test/nn.py')
+    torch.manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    with _NoThread():
+        sac = SAC_Base(obs_names=['vector'], obs_shapes=[(S,)], d_action_sizes=list(d_action_sizes), c_action_size=A,
+                       model_abs_dir=None, nn=nn, device='cpu', seed=seed, batch_size=B,
+                       burn_in_step=b, n_step=n, ensemble_q_num=E, ensemble_q_sample=E,
+                       use_priority=use_priority, replay_config={'capacity': 1024}, **hyper)
+    assert not sac.discrete_dqn_like
+    with torch.no_grad():
+        for tq in sac.model_target_q_list:
+            for p in tq.parameters():
+                p.add_(torch.randn_like(p) * 0.02)
+        for net in sac.model_q_list + [sac.model_policy]:
+            for pn, p in net.named_parameters():
+                if pn.endswith('bias'):
+                    p.add_(torch.randn_like(p) * 0.05)
+    D, L = sum(d_action_sizes), b + n + 1
+    out = {'meta': np.array([S, A, E, 64, 3, B, b, n, steps, int(use_priority)], dtype=np.int64),
+           'd_action_sizes': np.array(d_action_sizes, dtype=np.int64)}
+    hp = dict(tau=sac.tau, update_target_per_step=sac.update_target_per_step, learning_rate=sac.learning_rate,
+              gamma=sac.gamma, v_lambda=sac.v_lambda, v_rho=float(sac.v_rho), v_c=float(sac.v_c),
+              clip_epsilon=sac.clip_epsilon, use_n_step_is=float(sac.use_n_step_is),
+              target_c_alpha=sac.target_c_alpha, init_log_alpha=float(sac.log_c_alpha.detach()),
+              use_auto_alpha=float(sac.use_auto_alpha), target_d_alpha=sac.target_d_alpha,
+              d_policy_entropy_penalty=sac.d_policy_entropy_penalty)
+    for k, v in hp.items():
+        out[f'hp.{k}'] = np.float64(v)
+
+    def dump_params(prefix):
+        for i in range(E):
+            for k, t in sac.model_q_list[i].state_dict().items():
+                out[f'{prefix}.q{i}.{k}'] = t.detach().numpy().copy()
+            for k, t in sac.model_target_q_list[i].state_dict().items():
+                out[f'{prefix}.qt{i}.{k}'] = t.detach().numpy().copy()
+        for k, t in sac.model_policy.state_dict().items():
+            out[f'{prefix}.pi.{k}'] = t.detach().numpy().copy()
+        out[f'{prefix}.log_c_alpha'] = sac.log_c_alpha.detach().numpy().copy()
+        out[f'{prefix}.log_d_alpha'] = sac.log_d_alpha.detach().numpy().copy()
+
+    dump_params('init')
+    ys = []
+    orig_get_y = sac._get_y
+
+    def tap_get_y(**kw):
+        d_y, c_y = orig_get_y(**kw)
+        ys.append((d_y.clone(), None if c_y is None else c_y.clone()))
+        return d_y, c_y
+
+    sac._get_y = tap_get_y
+    for s in range(steps):
+        states = torch.from_numpy(rng.randn(B, L, S).astype(np.float32))
+        onehots, mus = [], []
+        for size in d_action_sizes:
+            idx = rng.randint(0, size, size=(B, L - 1))
+            onehots.append(np.eye(size, dtype=np.float32)[idx])
+            m = rng.rand(B, L - 1, size).astype(np.float32) + 0.05
+            mus.append(m / m.sum(-1, keepdims=True))
+        act_parts, mu_parts = onehots, mus
+        if A:
+            act_parts = onehots + [(rng.rand(B, L - 1, A) * 1.9 - 0.95).astype(np.float32)]
+            mu_parts = mus + [(rng.rand(B, L - 1, A) * 1.5 + 0.01).astype(np.float32)]
+        actions = torch.from_numpy(np.concatenate(act_parts, axis=-1))
+        mu_probs = torch.from_numpy(np.concatenate(mu_parts, axis=-1))
+        rewards = torch.from_numpy(rng.randn(B, L - 1).astype(np.float32))
+        dones = torch.from_numpy(rng.rand(B, L - 1) < 0.15)
+        pad = np.zeros((B, L - 1), dtype=bool)
+        last = np.zeros((B, L - 1), dtype=bool)
+        for r in range(B):
+            if L - 1 > 1 and rng.rand() < 0.4:
+                cut = rng.randint(b + 1, L)
+                if cut < L - 1:
+                    pad[r, cut:] = True
+                last[r, cut - 1] = rng.rand() < 0.7
+            if b > 0 and rng.rand() < 0.3:
+                pad[r, :rng.randint(1, b + 1)] = True
+        tpad = torch.from_numpy(pad)
+        mu_probs[tpad] = 1.
+        rewards[tpad] = 0.
+        dones[tpad] = True
+        actions[tpad] = 0.  # padding_action (sac_base.py:291-294)
+        index = torch.arange(L - 1, dtype=torch.int32).repeat(B, 1)
+        index[tpad] = -1
+        pri = torch.from_numpy((rng.rand(B, 1) * 0.9 + 0.1).astype(np.float32)) if use_priority else None
+        noise = dict(eps_y=torch.from_numpy(rng.randn(B, n + 1, A).astype(np.float32)),
+                     eps_pi=torch.from_numpy(rng.randn(B, A).astype(np.float32)),
+                     eps_alpha=torch.from_numpy(rng.randn(B, A).astype(np.float32)),
+                     eps_td=torch.from_numpy(rng.randn(B, n + 1, A).astype(np.float32)))
+        pre = f's{s}'
+        for k, t in dict(states=states, actions=actions, rewards=rewards, dones=dones, mu_probs=mu_probs,
+                         last_masks=torch.from_numpy(last), padding_masks=tpad).items():
+            out[f'{pre}.in.{k}'] = t.numpy().copy()
+        if pri is not None:
+            out[f'{pre}.in.priority_is'] = pri.numpy().copy()
+        for k, t in noise.items():
+            out[f'{pre}.in.{k}'] = t.numpy().copy()
+        ys.clear()
+        with _NoiseTap() as tap:
+            if A:
+                tap.queue = [noise['eps_y'], noise['eps_pi']]
+                if sac.use_auto_alpha:
+                    tap.queue.append(noise['eps_alpha'])
+                if use_priority:
+                    tap.queue.append(noise['eps_td'])
+            bnx_states, _, bnx_target_states = sac._train(
+                bn_indexes=index.clone(), bn_last_masks=torch.from_numpy(last).clone(),
+                bn_padding_masks=tpad.clone(), bnx_obses_list=[states.clone()],
+                bn_actions=actions.clone(), bn_rewards=rewards.clone(), bn_dones=dones.clone(),
+                bn_mu_probs=mu_probs.clone(), bnx_pre_seq_hidden_states=torch.zeros(B, L, 0),
+                priority_is=pri.clone() if pri is not None else None)
+            out[f'{pre}.out.d_y'] = ys[0][0].numpy().copy()
+            if A:
+                out[f'{pre}.out.y'] = ys[0][1].numpy().copy()
+            for i in range(E):
+                for k, p in sac.model_q_list[i].named_parameters():
+                    out[f'{pre}.grad.q{i}.{k}'] = p.grad.detach().numpy().copy()
+            for k, p in sac.model_policy.named_parameters():
+                out[f'{pre}.grad.pi.{k}'] = p.grad.detach().numpy().copy()
+            if sac.use_auto_alpha:
+                out[f'{pre}.grad.log_d_alpha'] = sac.log_d_alpha.grad.detach().numpy().copy()
+                if A:
+                    out[f'{pre}.grad.log_c_alpha'] = sac.log_c_alpha.grad.detach().numpy().copy()
+            pi_probs = None
+            bn_states = bnx_states[:, :-1]
+            if sac.use_n_step_is:
+                pi_probs = sac.get_l_probs(l_obses_list=[states[:, :-1]], l_states=bn_states, l_actions=actions)
+                out[f'{pre}.out.pi_probs'] = pi_probs.numpy().copy()
+            if use_priority:
+                td = sac._get_td_error(
+                    n_last_masks=torch.from_numpy(last)[:, b:], n_padding_masks=tpad[:, b:],
+                    nx_obses_list=[states[:, b:]], state=bn_states[:, b],
+                    nx_target_states=bnx_target_states[:, b:], n_actions=actions[:, b:],
+                    n_rewards=rewards[:, b:].clone(), n_dones=dones[:, b:],
+                    n_mu_probs=pi_probs[:, b:].clone() if sac.use_n_step_is else None)
+                out[f'{pre}.out.td_error'] = td.numpy().copy()
+            assert not tap.queue
+        sac.increase_global_step()
+        dump_params(f'{pre}.after')
+    sac.close()
+    np.savez_compressed(GOLDEN / f'sac_{name}.npz', **out)
+    print('wrote', f'sac_{name}.npz', sum(v.nbytes for v in out.values()), 'bytes raw')
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     gen_per_case('small', capacity=64, batch_size=8, prev_n=2, post_n=3, alpha=0.9,
@@ -637,6 +785,9 @@ def main():
     # config-4 shapes (envs/test/nn_rnn.py: GRU(6 + 2 -> 8, 2 layers)), shorter burn-in, 2 steps
     gen_sac_rnn_case('rnn', So=6, A=2, E=2, B=16, b=5, n=3, steps=2, seed=14, v_lambda=0.95)
     gen_sac_rnn_case('rnn_b0', So=6, A=2, E=2, B=8, b=0, n=1, steps=2, seed=15, use_n_step_is=False)
+    # discrete / hybrid action branches (oracle groundwork)
+    gen_sac_discrete_case('disc', S=6, d_action_sizes=[3, 4], A=0, E=2, B=10, b=0, n=3, steps=2, seed=16, v_lambda=0.9)
+    gen_sac_discrete_case('hybrid', S=6, d_action_sizes=[3], A=2, E=2, B=10, b=1, n=2, steps=2, seed=17)
     # checkpoint directories written by the reference itself (interchange)
     gen_ckpt_case('vector', rnn=False, seed=21)
     gen_ckpt_case('rnn', rnn=True, seed=22)

@@ -26,7 +26,7 @@ def sac_case_meta(g: dict) -> dict:
 def sac_hyper_from_golden(g: dict):
     from oracle.sac_oracle import SacHyper
     m = sac_case_meta(g)
-    hp = {k[3:]: float(v) for k, v in g.items() if k.startswith('hp.')}
+    hp = {k[3:]: float(v) for k, v in g.items() if k.startswith('hp.') and np.ndim(v) == 0}
     return SacHyper(state_size=m['S'], action_size=m['A'], ensemble_q_num=m['E'], hidden=m['hidden'],
                     q_depth=m['depth'], policy_depth=m['depth'], burn_in_step=m['b'], n_step=m['n'],
                     tau=hp['tau'], update_target_per_step=int(hp['update_target_per_step']),

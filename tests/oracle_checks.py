@@ -108,3 +108,42 @@ def check_recurrent_sac_steps(g: dict) -> None:
             assert rel_err(out['y_td'], g[pre + 'out.y_td']) < 1e-5
         for k, v in oracle.snapshot().items():
             assert rel_err(v, g[f'{pre}after.{k}']) < 1e-5, (s, k)
+
+
+def check_hybrid_sac_steps(g: dict) -> None:
+    """Discrete / hybrid action branches (oracle/discrete_oracle.py) against a reference fixture."""
+    from oracle.discrete_oracle import HybridHyper, SacHybridOracle
+    torch.set_num_threads(1)
+    m = sac_case_meta(g)
+    base = sac_hyper_from_golden(g)
+    hpv = {k[3:]: (float(v) if np.ndim(v) == 0 else torch.from_numpy(np.asarray(v, dtype=np.float32)))
+           for k, v in g.items() if k.startswith('hp.')}
+    hp = HybridHyper(**{**base.__dict__, 'd_action_sizes': [int(x) for x in g['d_action_sizes']],
+                        'target_d_alpha': hpv['target_d_alpha'],
+                        'd_policy_entropy_penalty': hpv['d_policy_entropy_penalty'], 'd_depth': 3})
+    oracle = SacHybridOracle(hp)
+    oracle.load_params(*golden_params(g, 'init', m['E']), log_d_alpha=g['init.log_d_alpha'])
+    tol = 2e-6
+    for s in range(m['steps']):
+        batch, noise = golden_batch(g, s)
+        out = oracle.step(batch, noise)
+        pre = f's{s}.'
+        assert rel_err(out['d_y'], g[pre + 'out.d_y']) < tol
+        if hp.action_size:
+            assert rel_err(out['y'], g[pre + 'out.y']) < tol
+        for i in range(m['E']):
+            for k, v in out['grad_q'][i].items():
+                assert rel_err(v, g[f'{pre}grad.q{i}.{k}']) < tol, (s, i, k)
+        for k, v in out['grad_policy'].items():
+            assert rel_err(v, g[f'{pre}grad.pi.{k}']) < tol, (s, k)
+            assert np.abs(g[f'{pre}grad.pi.{k}']).max() > 0, k
+        if hp.use_auto_alpha:
+            assert rel_err(out['grad_log_d_alpha'], g[pre + 'grad.log_d_alpha']) < tol
+            if hp.action_size:
+                assert rel_err(out['grad_log_alpha'], g[pre + 'grad.log_c_alpha']) < tol
+        if hp.use_n_step_is:
+            assert rel_err(out['pi_probs'], g[pre + 'out.pi_probs']) < 1e-5
+        if hp.use_priority:
+            assert rel_err(out['td_error'], g[pre + 'out.td_error']) < 1e-5
+        for k, v in oracle.snapshot().items():
+            assert rel_err(v, g[f'{pre}after.{k}']) < 1e-5, (s, k)

@@ -6,7 +6,8 @@ import torch
 
 from oracle.replay_oracle import SumTreeOracle, pad_sampled_batch
 from tests.helpers import load_golden
-from tests.oracle_checks import check_per_trace, check_recurrent_sac_steps, check_sac_steps
+from tests.oracle_checks import (check_hybrid_sac_steps, check_per_trace, check_recurrent_sac_steps,
+                                 check_sac_steps)
 
 @pytest.mark.parametrize('name', ['per_small.npz', 'per_zeros.npz'])
 def test_per_trace_bit_exact(name):
@@ -52,6 +53,12 @@ def test_recurrent_sac_oracle_matches_reference(name):
     BPTT gradients of the representation, re-encoded states, next hidden states, td error on the
     target states."""
     check_recurrent_sac_steps(load_golden(name))
+
+
+@pytest.mark.parametrize('name', ['sac_disc.npz', 'sac_hybrid.npz'])
+def test_discrete_and_hybrid_oracle_matches_reference(name):
+    """Groundwork for SURVEY §8f rank 4 (no CUDA path yet): discrete-only and hybrid action branches."""
+    check_hybrid_sac_steps(load_golden(name))
 
 
 def test_vectorized_descent_equals_scalar():

@@ -56,3 +56,14 @@ def test_recurrent_sac_step_fresh_seed(mint):
     gen, load = mint
     gen.gen_sac_rnn_case('live', So=6, A=2, E=2, B=6, b=4, n=2, steps=2, seed=103)
     check_recurrent_sac_steps(load('sac_live.npz'))
+
+
+def test_discrete_and_hybrid_step_fresh_seed(mint):
+    from tests.oracle_checks import check_hybrid_sac_steps
+    gen, load = mint
+    gen.gen_sac_discrete_case('live_d', S=5, d_action_sizes=[2, 5, 3], A=0, E=3, B=7, b=1, n=2, steps=2, seed=104,
+                              v_rho=0.9, v_c=0.8)
+    check_hybrid_sac_steps(load('sac_live_d.npz'))
+    gen.gen_sac_discrete_case('live_h', S=5, d_action_sizes=[4], A=3, E=2, B=7, b=0, n=1, steps=1, seed=105,
+                              use_n_step_is=False)
+    check_hybrid_sac_steps(load('sac_live_h.npz'))
