@@ -199,7 +199,6 @@ class SAC_Base:
             'use_rnd': use_rnd,
             'use_normalization': use_normalization,
             'offline_enabled': offline_enabled,
-            'use_replay_buffer=False (on-policy BatchBuffer)': not use_replay_buffer,
             'ensemble_q_sample != ensemble_q_num': ensemble_q_sample != ensemble_q_num,
             'action_noise': action_noise is not None,
         }
@@ -449,6 +448,15 @@ class SAC_Base:
     def _init_replay_buffer(self, replay_config: dict | None) -> None:
         if not self.train_mode:
             return
+        if not self.use_replay_buffer:  # on-policy: every window once, in shuffled batches (sac_base.py:642-646)
+            if self._world > 1:
+                raise NotImplementedError('data-parallel learner without a replay buffer')
+            from .batch_buffer import BatchBuffer
+            self.batch_buffer = BatchBuffer(burn_in_step=self.burn_in_step, n_step=self.n_step,
+                                            padding_action=self._np_padding_action, batch_size=self.batch_size,
+                                            device=self.device)
+            self._cfg.use_priority = 0  # priority_is is None without a replay buffer (sac_base.py:2553)
+            return
         replay_config = {} if replay_config is None else dict(replay_config)
         if self._seed is not None:
             replay_config.setdefault('seed', int(self._seed))
@@ -496,7 +504,7 @@ class SAC_Base:
         # The sampled batch lives in a "batch set" (sample outputs, gathered windows, the C structs pointing
         # at them).  Two sets: while the networks train on one, the NEXT step's sample + gather fill the
         # other on a parallel branch (ASAC_SAMPLE_AHEAD=0: one set, sample and gather on the critical path).
-        self._sample_ahead = os.environ.get('ASAC_SAMPLE_AHEAD', '1') != '0'
+        self._sample_ahead = self.use_replay_buffer and os.environ.get('ASAC_SAMPLE_AHEAD', '1') != '0'
         self._sets = [self._make_batch_set() for _ in range(2 if self._sample_ahead else 1)]
         self._cur, self._primed = 0, False
         # With sampling one step ahead the tree update of step N is only needed by the sample of step N + 2:
@@ -553,7 +561,7 @@ class SAC_Base:
         batch.states, batch.actions, batch.rewards = ptr(bt['states']), ptr(bt['actions']), ptr(bt['rewards'])
         batch.dones, batch.last_masks = ptr(bt['dones']), ptr(bt['last_masks'])
         batch.padding_masks, batch.mu_probs = ptr(bt['padding_masks']), ptr(bt['mu_probs'])
-        batch.priority_is = ptr(smp['w']) if self.use_priority else None
+        batch.priority_is = ptr(smp['w']) if (self.use_priority and self.use_replay_buffer) else None
         # one noise buffer per batch set, four views: eps_y, eps_pi, eps_alpha, eps_td
         n = self.n_step
         sizes = [B * (n + 1) * A, B * A, B * A, B * (n + 1) * A]
@@ -626,7 +634,7 @@ class SAC_Base:
                 self._host_step = int(self.global_step.item())
                 self._counters[0] = self._host_step
                 self._logger.info(f'Restored from {path}')
-                if self.train_mode:
+                if self.train_mode and self.use_replay_buffer:
                     self.replay_buffer.load(ckpt_dir, last_ckpt)
         if fresh:
             self._logger.info('Initializing from scratch')
@@ -677,7 +685,7 @@ class SAC_Base:
         torch.save({k: (v.detach().clone() if isinstance(v, torch.Tensor) else v.state_dict())
                     for k, v in self.ckpt_dict.items()}, path)
         self._logger.info(f'Model saved at {path}')
-        if save_replay_buffer:
+        if save_replay_buffer and self.use_replay_buffer:
             self.replay_buffer.save(self.ckpt_dir, step)
 
     def write_constant_summaries(self, constant_summaries: list[dict], iteration=None) -> None:
@@ -785,6 +793,11 @@ class SAC_Base:
         last = np.zeros_like(ep_indexes, dtype=bool)
         last[:, -1] = True
         last[ep_indexes == -1] = True
+        if not self.use_replay_buffer:  # sac_base.py:2341-2349
+            self.batch_buffer.put_episode(ep_indexes=ep_indexes, ep_last_masks=last, ep_obses_list=ep_obses_list,
+                                          ep_actions=ep_actions, ep_rewards=ep_rewards, ep_dones=ep_dones,
+                                          ep_probs=ep_probs, ep_pre_seq_hidden_states=ep_pre_seq_hidden_states)
+            return
         storage = {'index': ep_indexes.squeeze(0), 'last_mask': last.squeeze(0)}
         for name, o in zip(self.obs_names, ep_obses_list):
             storage[f'obs_{name}'] = o.squeeze(0)
@@ -987,8 +1000,55 @@ class SAC_Base:
             check(lib.asac_sac_td_error(cfg, prm, work, stream), 'td_error')
         check(lib.asac_sac_advance_step(prm, stream), 'advance_step')
 
+    def _train_on_policy(self, step: int) -> int:
+        """train() without a replay buffer (sac_base.py:2509-2515, 2553): the oldest shuffled batch of windows
+        from the BatchBuffer goes into the step's device buffers and the same kernels run — Polyak, _get_y,
+        critic / [representation /] policy / alpha steps — with no IS weights, priorities or write-backs."""
+        batch = self.batch_buffer.get_batch()
+        if batch is None:
+            return step
+        (bn_indexes, bn_last_masks, bn_padding_masks, bnx_obses_list, bn_actions, bn_rewards, bn_dones, bn_mu_probs,
+         bnx_hidden) = batch
+        st = self._sets[0]
+        bt, bn = st['bt'], self.burn_in_step + self.n_step
+        with torch.cuda.device(self.device):
+            bt['index'][:, :bn].copy_(bn_indexes)
+            bt['last_masks'][:, :bn].copy_(bn_last_masks)
+            bt['padding_masks'][:, :bn].copy_(bn_padding_masks)
+            bt['actions'][:, :bn].copy_(bn_actions)
+            bt['rewards'][:, :bn].copy_(bn_rewards)
+            bt['dones'][:, :bn].copy_(bn_dones)
+            bt['mu_probs'][:, :bn].copy_(bn_mu_probs)
+            if self._gru is not None:
+                bt['obs'].copy_(bnx_obses_list[0])
+                bt['hidden'].copy_(bnx_hidden.reshape(bt['hidden'].shape))
+            else:
+                off = 0
+                for (name, shape), o in zip(zip(self.obs_names, self.obs_shapes), bnx_obses_list):
+                    if len(shape) == 1:  # ModelSimpleRep: state = concat of the vector observations
+                        bt['states'][:, :, off:off + shape[0]].copy_(o)
+                        off += shape[0]
+            lib, cfg, prm, work = self._lib, C.byref(self._cfg), C.byref(self._prm), C.byref(self._work)
+            stream = _lib.current_stream()
+            self._enqueue_noise(st, 0)
+            if st['rep'] is not None:
+                check(lib.asac_flat_polyak(ptr(self._rept_flat), ptr(self._rep_flat), self._gru.count,
+                                           ptr(self._counters), int(self.update_target_per_step), self._cfg.tau,
+                                           self._cfg.one_minus_tau, 0, stream), 'flat_polyak')
+                check(lib.asac_sac_polyak(cfg, prm, -1.0, stream), 'sac_polyak')
+                check(lib.asac_sac_step_networks_rep(cfg, prm, C.byref(st['batch']), work, C.byref(st['rep']), 0, None,
+                                                     stream), 'sac_step_networks_rep')
+                check(lib.asac_sac_staged_tail(cfg, prm, work, stream), 'sac_staged_tail')
+            else:
+                check(lib.asac_sac_step(cfg, prm, C.byref(st['batch']), work, stream), 'sac_step')
+        if self.save_model_per_step and step % self.save_model_per_step == 0:
+            self.save_model()
+        return self.increase_global_step()
+
     def train(self) -> int:
         step = self.get_global_step()
+        if not self.use_replay_buffer:
+            return self._train_on_policy(step)
         rb = self.replay_buffer
         if not rb.is_lg_batch_size:
             return step

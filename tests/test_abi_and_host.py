@@ -265,3 +265,32 @@ def test_recurrent_representation_lowering_on_the_host():
             lowering.analyze_rep(bad(['v'], [(6,)], [], 2, False), [(6,)], 2)
     with pytest.raises(NotImplementedError):
         m.GRU(8, 8, 1)(torch.zeros(1, 2, 8), None, torch.zeros(1, 2, dtype=torch.bool))
+
+
+def test_batch_buffer_windows_without_the_reference():
+    """asac_b200.batch_buffer on its own (the comparison with the reference's implementation is
+    tests/test_oracle_vs_reference.py): window count, contents, the front-only padding flag, leftovers."""
+    import numpy as np
+    from asac_b200.batch_buffer import BatchBuffer, episode_to_batch
+    T, b, n = 6, 2, 3
+    idx = np.arange(T, dtype=np.int32)[None]
+    last = np.zeros((1, T), dtype=bool); last[:, -1] = True
+    obs = np.arange(T, dtype=np.float32).reshape(1, T, 1) + 100
+    act = np.arange(T, dtype=np.float32).reshape(1, T, 1)
+    out = episode_to_batch(b, n, np.array([9.], np.float32), idx, last, [obs], act, np.ones((1, T), np.float32),
+                           np.zeros((1, T), bool), np.full((1, T, 1), 0.5, np.float32), np.zeros((1, T, 0), np.float32))
+    bn_idx, bn_last, bn_pad, (bnx_obs,), bn_act, bn_rew, bn_done, bn_prob, bnx_h = out
+    assert bn_idx.shape == (T - 1, b + n) and bnx_obs.shape == (T - 1, b + n + 1, 1) and bnx_h.shape == (T - 1, b + n + 1, 0)
+    assert bn_idx[0].tolist() == [-1, -1, 0, 1, 2] and bn_idx[-1].tolist() == [2, 3, 4, 5, -1]
+    assert bn_pad[0].tolist() == [True, True, False, False, False] and not bn_pad[2:].any()  # trailing pad: not flagged
+    assert bn_last[-1].tolist() == [False, False, False, True, True] and bn_done[-1, -1] and bn_rew[-1, -1] == 0
+    assert bn_act[0].ravel().tolist() == [9., 9., 0., 1., 2.] and bn_prob[0].ravel().tolist() == [1., 1., .5, .5, .5]
+    assert bnx_obs[0].ravel().tolist() == [0., 0., 100., 101., 102., 103.]
+    buf = BatchBuffer(b, n, np.array([9.], np.float32), batch_size=4)
+    np.random.seed(0)
+    buf.put_episode(idx, last, [obs], act, np.ones((1, T), np.float32), np.zeros((1, T), bool),
+                    np.full((1, T, 1), 0.5, np.float32), np.zeros((1, T, 0), np.float32))
+    first = buf.get_batch()
+    assert first[0].shape == (4, b + n) and buf.get_batch() is None and buf._rest_batch[0].shape[0] == 1
+    seen = sorted(int(r[2]) for r in first[0].tolist()) + [int(buf._rest_batch[0][0, 2])]
+    assert sorted(seen) == [0, 1, 2, 3, 4]  # every window exactly once

@@ -350,3 +350,57 @@ def test_resume_from_a_checkpoint_written_by_the_reference(tmp_path, name):
     torch.cuda.synchronize()
     assert all(np.isfinite(v) for v in sac.last_step_stats().values())
     sac.close()
+
+
+def test_on_policy_batch_buffer_path(tmp_path):
+    """use_replay_buffer=False (sac_base.py:642-646, 2341-2349, 2509-2515): episodes go through the
+    BatchBuffer, train() consumes one shuffled batch of windows per call and runs the same kernels with no
+    IS weights / priorities — bit-identical to asac_sac_step driven through the C ABI on the same batch,
+    parameters and Gaussian draws."""
+    from algorithm.sac_base import SAC_Base
+    from oracle.sac_oracle import SacBatch, SacHyper, SacNoise
+    from tests.cuda_harness import SacCuda
+    nn = _plugin(tmp_path, PLUGIN_TEST, 'nn_plugin_onpolicy')
+    B, b, n, A = 16, 2, 3, 2
+    sac = SAC_Base(obs_names=['o0'], obs_shapes=[(6,)], d_action_sizes=[], c_action_size=A, model_abs_dir=None, nn=nn,
+                   batch_size=B, burn_in_step=b, n_step=n, use_replay_buffer=False, seed=3)
+    assert not hasattr(sac, 'replay_buffer') and sac.train() == 0  # nothing buffered yet
+    rng = np.random.RandomState(1)
+    np.random.seed(5)
+    for _ in range(2):
+        sac.put_episode(**_episode(rng, [(6,)], A, 30))   # 2 x 29 windows -> 3 full batches, 10 left over
+    seen = {}
+    pop = sac.batch_buffer.get_batch
+
+    def tap():
+        seen['batch'] = pop()
+        return seen['batch']
+    sac.batch_buffer.get_batch = tap
+    hp = SacHyper(state_size=6, action_size=A, burn_in_step=b, n_step=n, use_priority=False)
+    cu = SacCuda(hp, B)
+    cu.q.copy_(sac._q_flat); cu.qt.copy_(sac._qt_flat); cu.pi.copy_(sac._pi_flat)
+    cu.log_alpha.copy_(sac._log_alpha_buf)
+    assert sac.train() == 1
+    torch.cuda.synchronize()
+    (idx, last, pad, obs_list, actions, rewards, dones, mu, hidden) = seen['batch']
+    assert idx.shape == (B, b + n) and obs_list[0].shape == (B, b + n + 1, 6) and hidden.shape == (B, b + n + 1, 0)
+    assert bool(pad[:, :b].any()) and not bool(pad[:, b:].any())  # only burn-in rows are ever padding here
+    noise = sac._noise.cpu()
+    sizes = [B * (n + 1) * A, B * A, B * A, B * (n + 1) * A]
+    offs = np.cumsum([0] + sizes)
+    eps = [noise[offs[i]:offs[i + 1]] for i in range(4)]
+    batch = SacBatch(states=obs_list[0].cpu(), actions=actions.cpu(), rewards=rewards.cpu(), dones=dones.cpu(),
+                     mu_probs=mu.cpu(), last_masks=last.cpu(), padding_masks=pad.cpu(), priority_is=None)
+    cu.step(cu.make_batch(batch, SacNoise(eps_y=eps[0].view(B, n + 1, A), eps_pi=eps[1].view(B, A),
+                                          eps_alpha=eps[2].view(B, A), eps_td=eps[3].view(B, n + 1, A))))
+    torch.cuda.synchronize()
+    assert torch.equal(cu.q, sac._q_flat) and torch.equal(cu.qt, sac._qt_flat) and torch.equal(cu.pi, sac._pi_flat)
+    assert torch.equal(cu.log_alpha, sac._log_alpha_buf)
+    assert sac._counters.cpu().tolist()[:4] == [1, 1, 1, 1]
+    assert sac.train() == 2 and sac.train() == 3
+    assert sac.train() == 3  # the incomplete fourth batch waits for more windows
+    sac.put_episode(**_episode(rng, [(6,)], A, 12))  # 10 left over + 11 windows -> one more batch
+    assert sac.train() == 4
+    torch.cuda.synchronize()
+    assert all(np.isfinite(v) for v in sac.last_step_stats().values())
+    sac.close()

@@ -67,3 +67,63 @@ def test_discrete_and_hybrid_step_fresh_seed(mint):
     gen.gen_sac_discrete_case('live_h', S=5, d_action_sizes=[4], A=3, E=2, B=7, b=0, n=1, steps=1, seed=105,
                               use_n_step_is=False)
     check_hybrid_sac_steps(load('sac_live_h.npz'))
+
+
+def test_batch_buffer_equals_reference(mint):
+    """asac_b200.batch_buffer (on-policy path, use_replay_buffer=False) against the reference's
+    episode_to_batch / BatchBuffer (utils/operators.py:105-207, batch_buffer.py:10-95) on the same episodes
+    and the same NumPy seed: identical windows, padding quirk included, identical batches in identical order."""
+    import torch
+    from oracle.ref_shims import import_reference
+    import_reference()
+    from algorithm.batch_buffer import BatchBuffer as RefBuffer
+    from algorithm.utils import episode_to_batch as ref_e2b
+    from asac_b200.batch_buffer import BatchBuffer, episode_to_batch
+
+    rng = np.random.RandomState(7)
+
+    def episode(T, hidden=(2, 4)):
+        idx = np.arange(T, dtype=np.int32)[None]
+        last = np.zeros((1, T), dtype=bool); last[:, -1] = True
+        return dict(ep_indexes=idx, ep_last_masks=last,
+                    ep_obses_list=[rng.randn(1, T, 5).astype(np.float32), rng.randn(1, T, 2, 3).astype(np.float32)],
+                    ep_actions=rng.rand(1, T, 3).astype(np.float32), ep_rewards=rng.randn(1, T).astype(np.float32),
+                    ep_dones=rng.rand(1, T) < 0.2, ep_probs=rng.rand(1, T, 3).astype(np.float32),
+                    ep_pre_seq_hidden_states=rng.randn(1, T, *hidden).astype(np.float32))
+
+    pad_action = np.array([0.5, -0.5, 0.25], dtype=np.float32)
+    for b, n, T in ((0, 1, 6), (3, 2, 9), (2, 4, 5)):
+        ep = episode(T)
+        args = dict(l_indexes=ep['ep_indexes'], l_last_masks=ep['ep_last_masks'], l_actions=ep['ep_actions'],
+                    l_rewards=ep['ep_rewards'], l_dones=ep['ep_dones'], l_probs=ep['ep_probs'],
+                    l_pre_seq_hidden_states=ep['ep_pre_seq_hidden_states'])
+        want = ref_e2b(burn_in_step=b, n_step=n, padding_action=pad_action,
+                       l_obses_list=[o.copy() for o in ep['ep_obses_list']], **args)
+        got = episode_to_batch(b, n, pad_action, l_obses_list=ep['ep_obses_list'], **args)
+        for i, (w, g) in enumerate(zip(want, got)):
+            if isinstance(w, list):
+                assert all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(w, g)), (b, n, i)
+            else:
+                assert np.array_equal(w, g) and w.dtype == g.dtype and w.shape == g.shape, (b, n, i)
+    ours = BatchBuffer(2, 3, pad_action, batch_size=8, max_size=3)
+    ref = RefBuffer(2, 3, pad_action, batch_size=8, max_size=3)
+    eps = [episode(T) for T in (7, 12, 4, 30, 9)]
+    np.random.seed(11)
+    for ep in eps:
+        ours.put_episode(**{k: ([o.copy() for o in v] if isinstance(v, list) else v) for k, v in ep.items()})
+    np.random.seed(11)
+    for ep in eps:
+        ref.put_episode(**{k: ([o.copy() for o in v] if isinstance(v, list) else v) for k, v in ep.items()})
+    n_batches = 0
+    while True:
+        a, r = ours.get_batch(), ref.get_batch()
+        assert (a is None) == (r is None)
+        if a is None:
+            break
+        n_batches += 1
+        for x, y in zip(a, r):
+            if isinstance(x, list):
+                assert all(torch.equal(p, q) for p, q in zip(x, y))
+            else:
+                assert torch.equal(x, y) and x.shape[0] == 8
+    assert n_batches == 3  # max_size keeps the newest three of the seven full batches
