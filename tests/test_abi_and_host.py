@@ -294,3 +294,38 @@ def test_batch_buffer_windows_without_the_reference():
     assert first[0].shape == (4, b + n) and buf.get_batch() is None and buf._rest_batch[0].shape[0] == 1
     seen = sorted(int(r[2]) for r in first[0].tolist()) + [int(buf._rest_batch[0][0, 2])]
     assert sorted(seen) == [0, 1, 2, 3, 4]  # every window exactly once
+
+
+def test_flat_adam_state_dict_loads_into_torch_adam():
+    """The optimizer entries of a checkpoint written here must load into the reference's
+    ``torch.optim.Adam`` objects (sac_base.py:296-300, 609-624): ``_FlatAdam.state_dict()`` (views of the flat
+    moment buffers the CUDA Adam kernel updates) goes through ``Adam.load_state_dict`` and the next torch
+    step continues from those moments; the reverse direction restores moments and step count."""
+    from asac_b200.sac_base import _FlatAdam
+    torch.manual_seed(0)
+    shapes = [(4, 3), (4,), (2, 4), (2,)]
+    n = sum(int(np.prod(s)) for s in shapes)
+    flat, m_flat, v_flat = torch.randn(n), torch.rand(n) * 0.1, torch.rand(n) * 0.01
+    counters = torch.tensor([9, 7, 0, 0, 0, 0, 0, 0], dtype=torch.int64)
+    params, off = [], 0
+    for s in shapes:
+        k = int(np.prod(s))
+        params.append(torch.nn.Parameter(flat[off:off + k].view(s)))
+        off += k
+    ours = _FlatAdam(params, flat, m_flat, v_flat, counters, 1, 3e-4)
+    sd = ours.state_dict()
+    assert set(sd) == {'state', 'param_groups'} and float(sd['state'][0]['step']) == 7
+    clones = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    ref = torch.optim.Adam(clones, lr=3e-4)
+    ref.load_state_dict(sd)
+    assert torch.equal(ref.state[clones[2]]['exp_avg'], m_flat[16:24].view(2, 4))
+    for c in clones:
+        c.grad = torch.ones_like(c)
+    ref.step()
+    assert float(ref.state[clones[0]]['step']) == 8
+    # and back: a state dict written by torch.optim.Adam restores the flat moments and the step counter
+    m_flat.zero_(); v_flat.zero_(); counters[1] = 0
+    ours.load_state_dict(ref.state_dict())
+    assert int(counters[1]) == 8
+    assert torch.equal(m_flat[16:24].view(2, 4), ref.state[clones[2]]['exp_avg'])
+    assert torch.equal(v_flat[:12].view(4, 3), ref.state[clones[0]]['exp_avg_sq'])
