@@ -16,36 +16,37 @@ class ModelBaseQ(nn.Module):
     def __init__(self, state_size: int, d_action_sizes: list[int], c_action_size: int, is_target: bool,
                  model_abs_dir: Path | None = None):
         super().__init__()
-        self.state_size = state_size
-        self.d_action_sizes = d_action_sizes
-        self.c_action_size = c_action_size
-        self.is_target = is_target
-        self.model_abs_dir = model_abs_dir
+        vars(self).update(state_size=state_size, d_action_sizes=d_action_sizes, c_action_size=c_action_size,
+                          is_target=is_target, model_abs_dir=model_abs_dir)
         self._build_model()
 
     def _build_model(self):
-        pass
+        """Subclasses create their layers here (called once from the constructor)."""
 
     def forward(self, state, action, obs_list):
         raise Exception('ModelQ not implemented')
 
 
 class ModelQ(ModelBaseQ):
-    """state -> dense -> { d heads, c_dense(cat[c_state_dense(.), c_action_dense(action)]) -> 1 }."""
+    """state -> dense -> { one head per discrete branch, c_dense(cat[c_state_dense(.), c_action_dense(action)]) -> 1 }.
+    Attribute names and registration order are the reference's (q.py:34-72): they are the ``state_dict`` keys
+    and the parameter indices of the optimizer state in a checkpoint."""
 
     def _build_model(self, dense_n=64, dense_depth=0, d_dense_n=64, d_dense_depth=3,
                      c_state_n=64, c_state_depth=0, c_action_n=64, c_action_depth=0,
                      c_dense_n=64, c_dense_depth=3, dropout=0.):
-        self.dense = LinearLayers(self.state_size, dense_n, dense_depth, dropout=dropout)
+        def mlp(in_dim, width, depth, out=None):
+            return LinearLayers(in_dim, width, depth, out, dropout=dropout)
+
+        self.dense = mlp(self.state_size, dense_n, dense_depth)
+        trunk_width = self.dense.output_size
         if self.d_action_sizes:
-            self.d_dense_list = nn.ModuleList(
-                LinearLayers(self.dense.output_size, d_dense_n, d_dense_depth, size, dropout=dropout)
-                for size in self.d_action_sizes)
+            self.d_dense_list = nn.ModuleList(mlp(trunk_width, d_dense_n, d_dense_depth, k) for k in self.d_action_sizes)
         if self.c_action_size:
-            self.c_state_dense = LinearLayers(self.dense.output_size, c_state_n, c_state_depth, dropout=dropout)
-            self.c_action_dense = LinearLayers(self.c_action_size, c_action_n, c_action_depth, dropout=dropout)
-            self.c_dense = LinearLayers(self.c_state_dense.output_size + self.c_action_dense.output_size,
-                                        c_dense_n, c_dense_depth, 1, dropout=dropout)
+            self.c_state_dense = mlp(trunk_width, c_state_n, c_state_depth)
+            self.c_action_dense = mlp(self.c_action_size, c_action_n, c_action_depth)
+            self.c_dense = mlp(self.c_state_dense.output_size + self.c_action_dense.output_size, c_dense_n,
+                               c_dense_depth, 1)
 
     def forward(self, state, c_action, obs_list):
         trunk = self.dense(state)
