@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.replay_oracle import PerOracle
+from oracle.replay_oracle import PerOracle, pad_sampled_batch
 from oracle.sac_oracle import SacOracle
 from tests.helpers import golden_batch, golden_params, rel_err, sac_case_meta, sac_hyper_from_golden
 
@@ -147,3 +147,20 @@ def check_hybrid_sac_steps(g: dict) -> None:
             assert rel_err(out['td_error'], g[pre + 'out.td_error']) < 1e-5
         for k, v in oracle.snapshot().items():
             assert rel_err(v, g[f'{pre}after.{k}']) < 1e-5, (s, k)
+
+
+def check_padding(g: dict) -> None:
+    """sac_base.py:2435-2453 (learner-side padding of a sampled window) against a reference fixture."""
+    b = int(g['meta'][0])
+    raw = {k[4:]: v for k, v in g.items() if k.startswith('raw.')}
+    out = pad_sampled_batch(raw, b, np.zeros(raw['action'].shape[-1], dtype=np.float32))
+    assert np.array_equal(out['index'][:, :-1], g['padded.bn_indexes'])
+    assert np.array_equal(out['padding_mask'][:, :-1], g['padded.bn_padding_masks'])
+    assert np.array_equal(out['last_mask'][:, :-1], g['padded.bn_last_masks'])
+    assert np.array_equal(out['action'][:, :-1], g['padded.bn_actions'])
+    assert np.array_equal(out['reward'][:, :-1], g['padded.bn_rewards'])
+    assert np.array_equal(out['done'][:, :-1], g['padded.bn_dones'])
+    assert np.array_equal(out['mu_prob'][:, :-1], g['padded.bn_mu_probs'])
+    assert np.array_equal(out['obs_vector'], g['padded.bnx_obs'])
+    if b > 0:  # with b == 0 the zero-priority episode tail (ignore_size=1) keeps windows inside an episode
+        assert out['padding_mask'].any(), 'fixture should contain padded rows'

@@ -4,10 +4,10 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.replay_oracle import SumTreeOracle, pad_sampled_batch
+from oracle.replay_oracle import SumTreeOracle
 from tests.helpers import load_golden
-from tests.oracle_checks import (check_hybrid_sac_steps, check_per_trace, check_recurrent_sac_steps,
-                                 check_sac_steps)
+from tests.oracle_checks import (check_hybrid_sac_steps, check_padding, check_per_trace,
+                                 check_recurrent_sac_steps, check_sac_steps)
 
 @pytest.mark.parametrize('name', ['per_small.npz', 'per_zeros.npz'])
 def test_per_trace_bit_exact(name):
@@ -26,20 +26,7 @@ def test_rebuild_equals_incremental():
 
 @pytest.mark.parametrize('name', ['pad_b2n3.npz', 'pad_b0n1.npz'])
 def test_padding_matches_reference(name):
-    g = load_golden(name)
-    b = int(g['meta'][0])
-    raw = {k[4:]: v for k, v in g.items() if k.startswith('raw.')}
-    out = pad_sampled_batch(raw, b, np.zeros(raw['action'].shape[-1], dtype=np.float32))
-    assert np.array_equal(out['index'][:, :-1], g['padded.bn_indexes'])
-    assert np.array_equal(out['padding_mask'][:, :-1], g['padded.bn_padding_masks'])
-    assert np.array_equal(out['last_mask'][:, :-1], g['padded.bn_last_masks'])
-    assert np.array_equal(out['action'][:, :-1], g['padded.bn_actions'])
-    assert np.array_equal(out['reward'][:, :-1], g['padded.bn_rewards'])
-    assert np.array_equal(out['done'][:, :-1], g['padded.bn_dones'])
-    assert np.array_equal(out['mu_prob'][:, :-1], g['padded.bn_mu_probs'])
-    assert np.array_equal(out['obs_vector'], g['padded.bnx_obs'])
-    if b > 0:  # with b == 0 the zero-priority episode tail (ignore_size=1) keeps windows inside an episode
-        assert out['padding_mask'].any(), 'fixture should contain padded rows'
+    check_padding(load_golden(name))
 
 
 @pytest.mark.parametrize('name', ['sac_c2.npz', 'sac_c3.npz', 'sac_odd.npz', 'sac_nois.npz'])

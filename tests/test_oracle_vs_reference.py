@@ -127,3 +127,10 @@ def test_batch_buffer_equals_reference(mint):
             else:
                 assert torch.equal(x, y) and x.shape[0] == 8
     assert n_batches == 3  # max_size keeps the newest three of the seven full batches
+
+
+def test_padding_fresh_seed(mint):
+    from tests.oracle_checks import check_padding
+    gen, load = mint
+    gen.gen_padding_case('live', burn_in_step=3, n_step=2, batch_size=12, capacity=64, seed=106)
+    check_padding(load('pad_live.npz'))
