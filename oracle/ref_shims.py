@@ -40,6 +40,11 @@ def install_shims() -> None:
         import torchvision  # noqa: F401  (the reference's `algorithm`): get it over with beforehand
     except Exception:  # noqa: BLE001
         pass
+    try:  # no tqdm monitor thread: the fixture generators patch Thread.start while the reference starts up,
+        import tqdm  # and a monitor created meanwhile would fail to join at interpreter exit
+        tqdm.tqdm.monitor_interval = 0
+    except Exception:  # noqa: BLE001
+        pass
     root = str(REFERENCE_ROOT)
     if root not in sys.path:
         sys.path.insert(0, root)
