@@ -10,7 +10,8 @@ False, stock ``ModelQ`` / ``ModelPolicy`` (identity ``dense``, one ``LinearLayer
 * ``d_heads_forward``          <- ``ModelQ.forward`` / ``ModelPolicy.forward`` discrete heads (q.py:74-80,
                                   policy.py:152-160)
 * ``JointCategorical``         <- ``JointOneHotCategorical``                (policy.py:47-84)
-* ``SacHybridOracle.get_y``    <- ``_get_y`` discrete branch + continuous   (sac_base.py:1356-1464)
+* ``SacHybridOracle.get_y``    <- ``_get_y`` discrete branch + continuous   (sac_base.py:1356-1464),
+                                  ``get_dqn_like_d_y`` with ``discrete_dqn_like`` (sac_base.py:1193-1242)
 * ``.train_q``                 <- ``_train_rep_q``                          (sac_base.py:1516-1603)
 * ``.train_policy``            <- ``_train_policy`` incl. entropy penalty   (sac_base.py:1858-1911)
 * ``.train_alpha``             <- ``_train_alpha`` (one Adam over both log alphas, :472, 1913-1949)
@@ -37,6 +38,7 @@ class HybridHyper(SacHyper):
     target_d_alpha: object = 0.98
     d_policy_entropy_penalty: float = 0.5
     d_depth: int = 3
+    discrete_dqn_like: bool = False  # sac_base.py:1193-1242: double-DQN target, no discrete policy / alpha loss
 
     @property
     def d_sum(self) -> int:
@@ -159,7 +161,11 @@ class SacHybridOracle(SacOracle):
 
     # ---- sac_base.py:1297-1466
     @torch.no_grad()
-    def get_y(self, last_masks, padding_masks, nx_states, n_actions, rewards, dones, mu_probs, eps):
+    def get_y(self, last_masks, padding_masks, nx_states, n_actions, rewards, dones, mu_probs, eps, perms=None):
+        """``perms`` (DQN-like only): the two ``torch.randperm(E)`` draws of sac_base.py:1366 and :1377.  The
+        reference permutes the TARGET stack and the ONLINE stack independently before pairing member i's
+        argmax with member i's target value, so with E > 1 its result depends on those draws; the
+        fixtures record them, identity permutations otherwise."""
         hp = self.hp
         D = hp.d_sum
         nx_actions = torch.cat([n_actions, torch.zeros_like(n_actions[:, :1])], dim=1)
@@ -170,7 +176,26 @@ class SacHybridOracle(SacOracle):
             sampled = loc + eps * scale
         qs = [self._q(q, nx_states, torch.tanh(sampled) if sampled is not None else None) for q in self.q_target]
         d_y = c_y = None
-        if hp.branches:
+        if hp.branches and hp.discrete_dqn_like:
+            # double DQN on the last solid step: argmax of the ONLINE critics, value of the TARGET critics,
+            # min over the ensemble, n-step discounted rewards in front (sac_base.py:1193-1242, 1368-1383)
+            solid = torch.logical_or(last_masks, padding_masks)
+            last_idx = solid.shape[1] - torch.flip(solid.to(torch.uint8), dims=[1]).argmin(1) - 1   # operators.py:7-9
+            rows = torch.arange(solid.shape[0])
+            nxt_states = nx_states[:, 1:]
+            nxt_c = torch.tanh(sampled[:, 1:]) if sampled is not None else None
+            eval_q = torch.stack([self._q(q, nxt_states, nxt_c)[0] for q in self.q])[:, rows, last_idx]
+            tgt_q = torch.stack([q[0][:, 1:] for q in qs])[:, rows, last_idx]
+            if perms is not None:
+                tgt_q, eval_q = tgt_q[torch.as_tensor(perms[0])], eval_q[torch.as_tensor(perms[1])]
+            masks = [F.one_hot(part.argmax(dim=-1), size) for part, size in
+                     zip(eval_q.split(hp.d_action_sizes, dim=-1), hp.d_action_sizes)]
+            chosen = torch.sum(tgt_q * torch.cat(masks, dim=-1), dim=-1, keepdim=True) / hp.branches
+            next_q = chosen.min(dim=0)[0]
+            done = dones[rows, last_idx].unsqueeze(-1)
+            g = torch.sum(self.gamma_ratio * rewards, dim=-1, keepdim=True)
+            d_y = g + torch.pow(torch.tensor(hp.gamma, dtype=self.dtype), last_idx.unsqueeze(-1) + 1) * next_q * ~done
+        elif hp.branches:
             d_alpha = torch.exp(self.log_d_alpha)
             mean_q = torch.stack([q[0] for q in qs]).mean(dim=0)          # mean over the ensemble (:1384-1385)
             probs = d_pi.probs
@@ -196,12 +221,12 @@ class SacHybridOracle(SacOracle):
         return d_y, c_y
 
     # ---- sac_base.py:1516-1603
-    def train_q(self, b: SacBatch, eps_y):
+    def train_q(self, b: SacBatch, eps_y, perms=None):
         hp = self.hp; s0 = hp.burn_in_step; D = hp.d_sum
         state, action = b.states[:, s0], b.actions[:, s0]
         q_vals = [self._q(q, state, action[..., D:]) for q in self.q]
         d_y, c_y = self.get_y(b.last_masks[:, s0:], b.padding_masks[:, s0:], b.states[:, s0:], b.actions[:, s0:],
-                              b.rewards[:, s0:], b.dones[:, s0:], b.mu_probs[:, s0:], eps_y)
+                              b.rewards[:, s0:], b.dones[:, s0:], b.mu_probs[:, s0:], eps_y, perms)
         losses = []
         for i, (d_q, c_q) in enumerate(q_vals):
             loss = torch.zeros((state.shape[0], 1), dtype=self.dtype)
@@ -235,7 +260,7 @@ class SacHybridOracle(SacOracle):
         loss = torch.zeros((state.shape[0], 1), dtype=self.dtype)
         with torch.no_grad():
             d_alpha, c_alpha = torch.exp(self.log_d_alpha), torch.exp(self.log_c_alpha)
-        if hp.branches:
+        if hp.branches and not hp.discrete_dqn_like:
             probs = d_pi.probs
             with torch.no_grad():
                 mean_q = torch.stack([self._q(q, state, action[..., D:])[0] for q in self.q]).mean(dim=0)
@@ -252,11 +277,13 @@ class SacHybridOracle(SacOracle):
             logp = sum_log_prob(squash_log_prob(loc, scale, sampled), keepdim=True)
             loss = loss + c_alpha * logp - torch.stack(qs).min(dim=0)[0]
         total = torch.mean(loss)
-        self.opt_policy.zero_grad()
-        total.backward(inputs=list(self.policy.values()))
-        grads = {k: t.grad.clone() for k, t in self.policy.items()}
-        self.opt_policy.step()
-        out = dict(loss_policy=total.detach(), grad_policy=grads)
+        out = dict(loss_policy=total.detach())
+        if (hp.branches and not hp.discrete_dqn_like) or hp.action_size:  # sac_base.py:1904-1907
+            self.opt_policy.zero_grad()
+            total.backward(inputs=list(self.policy.values()))
+            out['grad_policy'] = {k: (t.grad.clone() if t.grad is not None else torch.zeros_like(t))
+                                  for k, t in self.policy.items()}
+            self.opt_policy.step()
         if hp.branches:
             out['d_entropy'] = torch.mean(d_pi.entropy().sum(-1) / hp.branches).detach()
         return out
@@ -268,7 +295,8 @@ class SacHybridOracle(SacOracle):
         with torch.no_grad():
             d_pi, c_pi = self._pi(state)
         loss = torch.zeros((state.shape[0], 1), dtype=self.dtype)
-        if hp.branches:
+        d_on = hp.branches and not hp.discrete_dqn_like
+        if d_on:
             probs = d_pi.probs
             inner = self.log_d_alpha * (-torch.log(probs.clamp(min=1e-8)) - hp.target_d_alpha)
             loss = loss + torch.sum(probs * inner, dim=1, keepdim=True) / hp.branches
@@ -280,10 +308,10 @@ class SacHybridOracle(SacOracle):
             loss = loss + self.log_c_alpha * (-sum_log_prob(lp, keepdim=True) - hp.target_c_alpha * -valid)
         total = torch.mean(loss)
         self.opt_alpha.zero_grad()
-        used = ([self.log_d_alpha] if hp.branches else []) + ([self.log_c_alpha] if hp.action_size else [])
+        used = ([self.log_d_alpha] if d_on else []) + ([self.log_c_alpha] if hp.action_size else [])
         total.backward(inputs=used)
         out = dict(loss_alpha=total.detach())
-        if hp.branches:
+        if d_on:
             out['grad_log_d_alpha'] = self.log_d_alpha.grad.clone()
         if hp.action_size:
             out['grad_log_alpha'] = self.log_c_alpha.grad.clone()
@@ -305,13 +333,13 @@ class SacHybridOracle(SacOracle):
 
     # ---- sac_base.py:2182-2245
     @torch.no_grad()
-    def td_error(self, b: SacBatch, pi_probs, eps_td):
+    def td_error(self, b: SacBatch, pi_probs, eps_td, perms=None):
         hp = self.hp; s0 = hp.burn_in_step; D = hp.d_sum
         state, action = b.states[:, s0], b.actions[:, s0]
         q_vals = [self._q(q, state, action[..., D:]) for q in self.q]
         d_y, c_y = self.get_y(b.last_masks[:, s0:], b.padding_masks[:, s0:], b.states[:, s0:], b.actions[:, s0:],
                               b.rewards[:, s0:], b.dones[:, s0:],
-                              pi_probs[:, s0:] if pi_probs is not None else None, eps_td)
+                              pi_probs[:, s0:] if pi_probs is not None else None, eps_td, perms)
         errs = []
         for d_q, c_q in q_vals:
             e = torch.zeros((state.shape[0], 1), dtype=self.dtype)
@@ -322,20 +350,23 @@ class SacHybridOracle(SacOracle):
             errs.append(e)
         return torch.mean(torch.cat(errs, dim=-1), dim=-1, keepdim=True), (d_y, c_y)
 
-    def step(self, b: SacBatch, noise: SacNoise) -> dict:
+    def step(self, b: SacBatch, noise: SacNoise, perms=None) -> dict:
+        """``perms``: [(target, online) for _train_rep_q's _get_y, (target, online) for _get_td_error's] — the
+        reference's randperm draws of a DQN-like discrete-only step, in call order."""
         hp = self.hp
         if self.global_step % hp.update_target_per_step == 0:
             self.polyak(hp.tau)
-        out = self.train_q(b, noise.eps_y)
+        out = self.train_q(b, noise.eps_y, None if perms is None else perms[0])
         out.update(self.train_policy(b, noise.eps_pi))
-        if hp.use_auto_alpha:
+        if hp.use_auto_alpha and ((hp.branches and not hp.discrete_dqn_like) or hp.action_size):  # sac_base.py:2115
             out.update(self.train_alpha(b, noise.eps_alpha))
         pi_probs = None
         if hp.use_n_step_is:
             pi_probs = self.l_probs(b.states[:, :-1], b.actions)
             out['pi_probs'] = pi_probs
         if hp.use_priority:
-            out['td_error'], (out['d_y_td'], out['y_td']) = self.td_error(b, pi_probs, noise.eps_td)
+            out['td_error'], (out['d_y_td'], out['y_td']) = self.td_error(b, pi_probs, noise.eps_td,
+                                                                          None if perms is None else perms[1])
         self.global_step += 1
         return out
 

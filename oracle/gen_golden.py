@@ -627,7 +627,6 @@ def gen_sac_discrete_case(name, *, S, d_action_sizes, A, E, B, b, n, steps, seed
                        model_abs_dir=None, nn=nn, device='cpu', seed=seed, batch_size=B,
                        burn_in_step=b, n_step=n, ensemble_q_num=E, ensemble_q_sample=E,
                        use_priority=use_priority, replay_config={'capacity': 1024}, **hyper)
-    assert not sac.discrete_dqn_like
     with torch.no_grad():
         for tq in sac.model_target_q_list:
             for p in tq.parameters():
@@ -644,7 +643,8 @@ def gen_sac_discrete_case(name, *, S, d_action_sizes, A, E, B, b, n, steps, seed
               clip_epsilon=sac.clip_epsilon, use_n_step_is=float(sac.use_n_step_is),
               target_c_alpha=sac.target_c_alpha, init_log_alpha=float(sac.log_c_alpha.detach()),
               use_auto_alpha=float(sac.use_auto_alpha), target_d_alpha=sac.target_d_alpha,
-              d_policy_entropy_penalty=sac.d_policy_entropy_penalty)
+              d_policy_entropy_penalty=sac.d_policy_entropy_penalty,
+              discrete_dqn_like=float(sac.discrete_dqn_like))
     for k, v in hp.items():
         out[f'hp.{k}'] = np.float64(v)
 
@@ -716,6 +716,13 @@ def gen_sac_discrete_case(name, *, S, d_action_sizes, A, E, B, b, n, steps, seed
         for k, t in noise.items():
             out[f'{pre}.in.{k}'] = t.numpy().copy()
         ys.clear()
+        perms, real_randperm = [], torch.randperm
+
+        def tap_randperm(*a, **k):  # the ensemble shuffles of sac_base.py:1366, 1377, ... in call order
+            p = real_randperm(*a, **k)
+            perms.append(p.numpy().copy())
+            return p
+        torch.randperm = tap_randperm
         with _NoiseTap() as tap:
             if A:
                 tap.queue = [noise['eps_y'], noise['eps_pi']]
@@ -736,9 +743,11 @@ def gen_sac_discrete_case(name, *, S, d_action_sizes, A, E, B, b, n, steps, seed
                 for k, p in sac.model_q_list[i].named_parameters():
                     out[f'{pre}.grad.q{i}.{k}'] = p.grad.detach().numpy().copy()
             for k, p in sac.model_policy.named_parameters():
-                out[f'{pre}.grad.pi.{k}'] = p.grad.detach().numpy().copy()
+                if p.grad is not None:
+                    out[f'{pre}.grad.pi.{k}'] = p.grad.detach().numpy().copy()
             if sac.use_auto_alpha:
-                out[f'{pre}.grad.log_d_alpha'] = sac.log_d_alpha.grad.detach().numpy().copy()
+                if sac.log_d_alpha.grad is not None:
+                    out[f'{pre}.grad.log_d_alpha'] = sac.log_d_alpha.grad.detach().numpy().copy()
                 if A:
                     out[f'{pre}.grad.log_c_alpha'] = sac.log_c_alpha.grad.detach().numpy().copy()
             pi_probs = None
@@ -755,6 +764,8 @@ def gen_sac_discrete_case(name, *, S, d_action_sizes, A, E, B, b, n, steps, seed
                     n_mu_probs=pi_probs[:, b:].clone() if sac.use_n_step_is else None)
                 out[f'{pre}.out.td_error'] = td.numpy().copy()
             assert not tap.queue
+        torch.randperm = real_randperm
+        out[f'{pre}.in.perms'] = np.stack(perms) if perms else np.zeros((0, E), dtype=np.int64)
         sac.increase_global_step()
         dump_params(f'{pre}.after')
     sac.close()
@@ -788,6 +799,8 @@ def main():
     # discrete / hybrid action branches (oracle groundwork)
     gen_sac_discrete_case('disc', S=6, d_action_sizes=[3, 4], A=0, E=2, B=10, b=0, n=3, steps=2, seed=16, v_lambda=0.9)
     gen_sac_discrete_case('hybrid', S=6, d_action_sizes=[3], A=2, E=2, B=10, b=1, n=2, steps=2, seed=17)
+    gen_sac_discrete_case('dqn', S=6, d_action_sizes=[4, 2], A=0, E=2, B=10, b=0, n=3, steps=2, seed=18,
+                          discrete_dqn_like=True)
     # checkpoint directories written by the reference itself (interchange)
     gen_ckpt_case('vector', rnn=False, seed=21)
     gen_ckpt_case('rnn', rnn=True, seed=22)

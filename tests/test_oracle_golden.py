@@ -42,7 +42,7 @@ def test_recurrent_sac_oracle_matches_reference(name):
     check_recurrent_sac_steps(load_golden(name))
 
 
-@pytest.mark.parametrize('name', ['sac_disc.npz', 'sac_hybrid.npz'])
+@pytest.mark.parametrize('name', ['sac_disc.npz', 'sac_hybrid.npz', 'sac_dqn.npz'])
 def test_discrete_and_hybrid_oracle_matches_reference(name):
     """Groundwork for SURVEY §8f rank 4 (no CUDA path yet): discrete-only and hybrid action branches."""
     check_hybrid_sac_steps(load_golden(name))

@@ -67,6 +67,9 @@ def test_discrete_and_hybrid_step_fresh_seed(mint):
     gen.gen_sac_discrete_case('live_h', S=5, d_action_sizes=[4], A=3, E=2, B=7, b=0, n=1, steps=1, seed=105,
                               use_n_step_is=False)
     check_hybrid_sac_steps(load('sac_live_h.npz'))
+    gen.gen_sac_discrete_case('live_q', S=5, d_action_sizes=[3, 3], A=0, E=3, B=9, b=1, n=4, steps=2, seed=107,
+                              discrete_dqn_like=True)
+    check_hybrid_sac_steps(load('sac_live_q.npz'))
 
 
 def test_batch_buffer_equals_reference(mint):
