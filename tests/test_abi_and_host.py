@@ -83,6 +83,13 @@ def test_host_only_entry_points():
     cfg.q_hidden, cfg.burn_in, cfg.n_step, cfg.seq_len, cfg.bn_stride = 64, 40, 5, 46, 46
     cfg.use_n_step_is = 1
     assert 1 <= lib.asac_sac_tile_batch(C.byref(cfg)) < 16
+    # BASELINE configs[3] exactly: GRU state of width 8, trained representation (the post pass carries the
+    # value rows a second time) -> 4 sequences per tile still fit; the peer buffers grow by the GRU's gradient
+    cfg.state_size, cfg.rep_kind = 8, 1
+    assert lib.asac_sac_tile_batch(C.byref(cfg)) == 4
+    plain = lib.asac_peer_recv_words(C.byref(cfg), 8)
+    cfg.rep_param_stride = 864
+    assert lib.asac_peer_recv_words(C.byref(cfg), 8) == plain + 2 * 8 * 864
 
 
 def _load_plugin(tmp_path, text):
