@@ -11,6 +11,8 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+__all__ = ['ResBlock', 'LinearLayers']
+
 
 def _kaiming_zero_bias(linear: nn.Linear) -> nn.Linear:
     # linear_layers.py:40-42,105-108: kaiming_uniform_ weight (a=0), zero bias
@@ -61,32 +63,3 @@ class LinearLayers(nn.Module):
         if x.shape[-1] != self.input_size:
             raise AssertionError(f'LinearLayers expects {self.input_size} features, got {x.shape[-1]}')
         return self.dense(x)
-
-
-class GRU(nn.Module):
-    """Stock multi-layer GRU wrapper of the plugin surface (seq_layers.py:14-114): ``num_layers``
-    single-layer batch-first ``nn.GRU`` modules under ``_grus`` (same ``state_dict`` keys),
-    ``forward(x [B, L, in], h0 [B, layers, H]) -> (output [B, L, H], hn [B, L, layers, H])`` — every
-    layer's output at every step.  This torch module is the parameter container and the probe /
-    cross-check path; the learner runs ``csrc/rep_gru.cu`` on the same storage.  The padding-mask
-    variant (pack / unpack with left and right padding, seq_layers.py:60-103) is not on the fused path."""
-
-    def __init__(self, input_size: int, hidden_size: int, num_layers: int = 1, bias: bool = True,
-                 dropout: float = 0.0, device=None, dtype=None):
-        super().__init__()
-        self.num_layers = num_layers
-        self._grus = nn.ModuleList([
-            nn.GRU(input_size=input_size if i == 0 else hidden_size, hidden_size=hidden_size, num_layers=1,
-                   bias=bias, batch_first=True, dropout=dropout, device=device, dtype=dtype)
-            for i in range(num_layers)])
-
-    def forward(self, x: torch.Tensor, h0: torch.Tensor | None = None, padding_mask: torch.Tensor | None = None):
-        if padding_mask is not None:
-            raise NotImplementedError('GRU with a padding mask (packed sequences) is outside the B200 hot path')
-        if h0 is not None:
-            h0 = h0.transpose(0, 1).contiguous()
-        per_layer = []
-        for i, gru in enumerate(self._grus):
-            x, _ = gru(x, None if h0 is None else h0[i:i + 1])
-            per_layer.append(x.unsqueeze(2))
-        return x, torch.cat(per_layer, dim=2)

@@ -8,6 +8,8 @@ from torch import nn
 
 from .layers import LinearLayers
 
+__all__ = ['ModelBaseQ', 'ModelQ']
+
 
 class ModelBaseQ(nn.Module):
     """``ModelQ(state_size, d_action_sizes, c_action_size, is_target, model_abs_dir)``

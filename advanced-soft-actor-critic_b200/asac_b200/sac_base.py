@@ -277,6 +277,7 @@ class SAC_Base:
         lowered = lowering.analyze_rep(self.model_rep, self.obs_shapes, A)
         self.optimizer_rep = None
         self._gru = None
+        self._attn = None
         self._vector_obs = [(name, shape) for name, shape in zip(self.obs_names, self.obs_shapes) if len(shape) == 1]
         if lowered is None:
             if self.seq_encoder is not None:
@@ -530,6 +531,7 @@ class SAC_Base:
             self._prefetch = ((C.c_void_p * len(regions))(*[t.data_ptr() for t in regions]),
                               (C.c_int64 * len(regions))(*[t.numel() * 4 for t in regions]), regions)
         self._act_counter = torch.zeros(1, dtype=torch.int64, device=dev)  # Philox counter of choose_action
+        self._actor_bufs = {}
         self.actor_tensor_cores = False
         # data-parallel learner: gradient exchange inside the reduce+Adam kernels over NVLink peer memory
         # (ASAC_PEER_EXCHANGE=0, or a failed mapping, keeps the NCCL all-reduce between the kernels)
@@ -697,53 +699,160 @@ class SAC_Base:
         self.summary_writer.flush()
 
     # ------------------------------------------------------------------ actor side
+    def _actor_io(self, rows: int) -> dict:
+        """Per batch size: ONE pinned host staging block + its device mirror for everything choose_action
+        sends (vector observations, pre_action, hidden state, offline action / injected draws) and ONE
+        device block + pinned mirror for everything it returns (action, prob, next hidden state) — one
+        H2D and one D2H copy per call instead of one per tensor."""
+        io = self._actor_bufs.get(rows)
+        if io is not None:
+            return io
+        A, S = self.c_action_size, self.state_size
+        So = self._gru.obs_size if self._gru is not None else sum(shape[0] for _, shape in self._vector_obs)
+        NLH = 0 if self._gru is None else self._gru.layers * self._gru.hidden
+        f32 = dict(dtype=torch.float32, device=self.device)
+        n_in = rows * (So + A + NLH + A)           # obs | pre_action | hidden | offline action or eps
+        n_out = rows * (2 * A + NLH)
+        io = {'h_in': torch.empty(n_in, dtype=torch.float32).pin_memory(), 'd_in': torch.empty(n_in, **f32),
+              'h_out': torch.empty(n_out, dtype=torch.float32).pin_memory(), 'd_out': torch.empty(n_out, **f32),
+              'scratch': torch.empty(rows, 2 * A, **f32), 'state': torch.empty(rows, 1, S, **f32)}
+        cuts = np.cumsum([0, rows * So, rows * A, rows * NLH, rows * A])
+        io['in_cuts'] = [int(c) for c in cuts]
+        cuts = np.cumsum([0, rows * A, rows * A, rows * NLH])
+        io['out_cuts'] = [int(c) for c in cuts]
+        if len(self._actor_bufs) > 8:
+            self._actor_bufs.clear()
+        self._actor_bufs[rows] = io
+        return io
+
+    def _policy_act(self, state: torch.Tensor, action: torch.Tensor, prob: torch.Tensor, scratch: torch.Tensor,
+                    offline: torch.Tensor | None, eps: torch.Tensor | None, disable_sample: bool) -> None:
+        """asac_policy_act on ``state [rows, S]`` into ``action`` / ``prob [rows, A]`` (device, contiguous)."""
+        rows, sh = int(state.shape[0]), self._pi_shape
+        check(self._lib.asac_policy_act(ptr(self._pi_flat), self.state_size, sh.hidden, sh.depth, self.c_action_size,
+                                        ptr(state), rows, ptr(eps), ptr(offline), int(bool(disable_sample)),
+                                        self._noise_seed, ptr(self._act_counter), ptr(scratch), ptr(action), ptr(prob),
+                                        1 if (self.actor_tensor_cores and rows >= 2048) else 0,
+                                        _lib.current_stream()), 'policy_act')
+        self._act_counter += 1
+
     @torch.no_grad()
     def choose_action(self, obs_list, pre_action, pre_seq_hidden_state, offline_action=None,
                       disable_sample: bool = False, force_rnd_if_available: bool = False, eps=None):
         """sac_base.py:968-1019 (continuous branch of _choose_action :882-966) on the device kernels:
-        the concatenated vector observations go through the policy's flat parameters
-        (asac_policy_act: exact-fp32 row-tile forward; with ``self.actor_tensor_cores = True`` the
-        tcgen05 3xTF32 forward from 2048 rows on) and one elementwise kernel samples, squashes and
-        evaluates the per-dimension probability.  The tensor-core forward is opt-in because the
-        probability amplifies the 1.5e-6 error of the pre-activations by |x - mu| / sigma^2.
-        ``eps`` ([batch, A] N(0,1) draws) replaces the on-device Philox draws (tests)."""
-        if self.action_noise is not None:
+        the concatenated vector observations (through one GRU step when the representation is recurrent,
+        :1003) go through the policy's flat parameters (asac_policy_act: exact-fp32 row-tile forward; with
+        ``self.actor_tensor_cores = True`` the tcgen05 3xTF32 forward from 2048 rows on) and one elementwise
+        kernel samples, squashes and evaluates the per-dimension probability.  The tensor-core forward is
+        opt-in because the probability amplifies the 1.5e-6 error of the pre-activations by |x - mu| / sigma^2.
+        ``eps`` ([batch, A] N(0,1) draws) replaces the on-device Philox draws (tests).
+        Host traffic: one pinned staging block in, one out (``_actor_io``)."""
+        if self.action_noise is not None or self._attn is not None:
             return self._choose_action_torch(obs_list, pre_action, pre_seq_hidden_state, offline_action,
                                              disable_sample)
         with torch.cuda.device(self.device):
             A, S = self.c_action_size, self.state_size
-            parts = []
-            for (name, shape), o in zip(zip(self.obs_names, self.obs_shapes), obs_list):
-                if len(shape) != 1:
-                    continue  # ModelSimpleRep ignores non-vector observations (representation.py:74-83)
-                t = torch.from_numpy(np.ascontiguousarray(o)).to(self.device, non_blocking=True)
-                parts.append(t.float() if t.dtype != torch.float32 else t)
-            hidden_out = None
+            rows = int(np.shape(obs_list[0])[0])
+            io = self._actor_io(rows)
+            c = io['in_cuts']
+            h_in = io['h_in'].numpy()
+            # ModelSimpleRep: concat of the vector observations (representation.py:74-83); the recurrent
+            # representation reads obs_list[0] only (envs/test/nn_rnn.py)
+            vec = [np.asarray(o, dtype=np.float32).reshape(rows, -1)
+                   for shape, o in zip(self.obs_shapes, obs_list) if len(shape) == 1]
+            vec = vec[:1] if self._gru is not None else vec
+            h_in[c[0]:c[1]] = (vec[0] if len(vec) == 1 else np.concatenate(vec, axis=-1)).reshape(-1)
+            if self._gru is not None:
+                h_in[c[1]:c[2]] = np.asarray(pre_action, dtype=np.float32).reshape(-1)
+                h_in[c[2]:c[3]] = np.asarray(pre_seq_hidden_state, dtype=np.float32).reshape(-1)
+            extra = offline_action if offline_action is not None else eps
+            if extra is not None:
+                h_in[c[3]:c[4]] = (extra.detach().cpu().numpy() if isinstance(extra, torch.Tensor)
+                                   else np.asarray(extra, dtype=np.float32)).reshape(-1)
+            used = c[4] if extra is not None else (c[3] if self._gru is not None else c[1])
+            d_in, d_out = io['d_in'], io['d_out']
+            d_in[:used].copy_(io['h_in'][:used], non_blocking=True)
+            oc = io['out_cuts']
+            action, prob = d_out[oc[0]:oc[1]].view(rows, A), d_out[oc[1]:oc[2]].view(rows, A)
             if self._gru is not None:  # one GRU step from the caller's hidden state (sac_base.py:1003)
-                to_dev = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
-                state, hn = self._gru_forward(parts[0].unsqueeze(1), to_dev(pre_action).unsqueeze(1),
-                                              to_dev(pre_seq_hidden_state))
-                state, hidden_out = state.squeeze(1), hn.squeeze(1)
+                g = self._gru
+                hn = d_out[oc[2]:oc[3]]
+                net = _lib.AsacGruNet(ptr(self._rep_flat), ptr(io['state']), ptr(hn), None)
+                check(self._lib.asac_gru_forward(C.byref(self._gru_c), C.byref(net), 1, ptr(d_in[c[0]:c[1]]), None, 0,
+                                                 ptr(d_in[c[1]:c[2]]), ptr(d_in[c[2]:c[3]]), g.layers * g.hidden,
+                                                 rows, 1, _lib.current_stream()), 'gru_forward')
+                state = io['state'].view(rows, S)
             else:
-                state = parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
-            state = state.contiguous()
-            rows = int(state.shape[0])
+                state = d_in[c[0]:c[1]].view(rows, S)
+            extra_dev = None if extra is None else d_in[c[3]:c[4]].view(rows, A)
+            self._policy_act(state, action, prob, io['scratch'],
+                             extra_dev if offline_action is not None else None,
+                             extra_dev if (offline_action is None and eps is not None) else None, disable_sample)
+            io['h_out'].copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            out = io['h_out'].numpy()
+            hidden = out[oc[2]:oc[3]].reshape(rows, *self.seq_hidden_state_shape).copy() if self._gru is not None \
+                else np.zeros((rows, *self.seq_hidden_state_shape), dtype=np.float32)
+            return out[oc[0]:oc[1]].reshape(rows, A).copy(), out[oc[1]:oc[2]].reshape(rows, A).copy(), hidden
+
+    @torch.no_grad()
+    def choose_attn_action(self, ep_indexes, ep_padding_masks, ep_obses_list, ep_pre_actions, ep_pre_attn_states,
+                           offline_action=None, disable_sample: bool = False, force_rnd_if_available: bool = False,
+                           eps=None):
+        """sac_base.py:1022-1086: the last ``burn_in_step`` steps of the running episode go through the
+        attention representation with ONE query step (``is_prev_hidden_state=False``); the policy kernels
+        act on the resulting state.  -> (action [batch, A], prob [batch, A], attn_state [batch, *shape]).
+        The representation runs as the plugin's torch module on the parameters it shares with the learner."""
+        if self._attn is None:
+            raise NotImplementedError('choose_attn_action needs seq_encoder=SEQ_ENCODER.ATTN (sac_base.py:1022)')
+        with torch.cuda.device(self.device):
+            b = self.burn_in_step
+            tail = lambda x: torch.from_numpy(np.ascontiguousarray(x[:, -b:])).to(self.device)
+            obs = self._process_torch_obs_list([tail(o) for o in ep_obses_list])
+            state, attn_state, _ = self.model_rep(1, tail(ep_indexes), obs, tail(ep_pre_actions),
+                                                  pre_seq_hidden_state=tail(ep_pre_attn_states),
+                                                  is_prev_hidden_state=False, padding_mask=tail(ep_padding_masks))
+            state = state.squeeze(1).contiguous()
+            rows, A = int(state.shape[0]), self.c_action_size
             f32 = dict(dtype=torch.float32, device=self.device)
-            scratch, action, prob = torch.empty(rows, 2 * A, **f32), torch.empty(rows, A, **f32), \
-                torch.empty(rows, A, **f32)
-            off = None if offline_action is None else \
-                torch.from_numpy(np.ascontiguousarray(offline_action, dtype=np.float32)).to(self.device).contiguous()
-            e = None if eps is None else torch.as_tensor(eps, dtype=torch.float32).to(self.device).contiguous()
-            sh = self._pi_shape
-            check(self._lib.asac_policy_act(ptr(self._pi_flat), S, sh.hidden, sh.depth, A, ptr(state), rows, ptr(e),
-                                            ptr(off), int(bool(disable_sample)), self._noise_seed,
-                                            ptr(self._act_counter), ptr(scratch), ptr(action), ptr(prob),
-                                            1 if (self.actor_tensor_cores and rows >= 2048) else 0,
-                                            _lib.current_stream()), 'policy_act')
-            self._act_counter += 1
-            hidden = np.zeros((rows, *self.seq_hidden_state_shape), dtype=np.float32) if hidden_out is None \
-                else hidden_out.cpu().numpy()
-            return action.cpu().numpy(), prob.cpu().numpy(), hidden
+            out, scratch = torch.empty(2, rows, A, **f32), torch.empty(rows, 2 * A, **f32)
+            to_dev = lambda x: None if x is None else torch.as_tensor(x, dtype=torch.float32).to(self.device).contiguous()
+            self._policy_act(state, out[0], out[1], scratch, to_dev(offline_action), to_dev(eps), disable_sample)
+            host = out.cpu().numpy()
+            return host[0], host[1], attn_state.squeeze(1).cpu().numpy()
+
+    def _process_torch_obs_list(self, obs_list: list[torch.Tensor]) -> list[torch.Tensor]:
+        """uint8 images -> [0, 1] floats, bool -> float (sac_base.py:1088-1099 convention)."""
+        for i, o in enumerate(obs_list):
+            if o.dtype == torch.uint8:
+                obs_list[i] = o.float() / 255.
+            elif o.dtype == torch.bool:
+                obs_list[i] = o.float()
+        return obs_list
+
+    def log_episode(self, force: bool = False, **episode_trans) -> None:
+        """sac_base.py:2247-2300: called by AgentManager after every episode (agent.py:688).  With an
+        attention representation and a summary writer, the attention maps of the episode go to
+        TensorBoard (needs matplotlib); in every case the pending-summary flag is cleared."""
+        if not force and (self.summary_writer is None or not self.summary_available):
+            return
+        if self.summary_writer is not None and self._attn is not None:
+            try:
+                from matplotlib.figure import Figure
+                with torch.no_grad(), torch.cuda.device(self.device):
+                    idx = torch.from_numpy(episode_trans['ep_indexes']).to(self.device)
+                    obs = self._process_torch_obs_list([torch.from_numpy(o).to(self.device)
+                                                        for o in episode_trans['ep_obses_list']])
+                    from .utils.operators import gen_n_pre_actions
+                    pre = torch.from_numpy(gen_n_pre_actions(episode_trans['ep_actions'])).to(self.device)
+                    *_, maps = self.model_rep(idx.shape[1], idx, obs, pre, None)
+                for i, w in enumerate(maps):
+                    fig = Figure()
+                    fig.subplots().imshow(w[0].cpu().numpy())
+                    self.summary_writer.add_figure(f'attn_weight/{i}', fig, self.get_global_step())
+            except ImportError:
+                self._logger.warning('matplotlib is not installed: attention maps are not logged')
+        self.summary_available = False
 
     @torch.no_grad()
     def _choose_action_torch(self, obs_list, pre_action, pre_seq_hidden_state, offline_action=None,

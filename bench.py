@@ -33,17 +33,17 @@ for p in (str(ROOT), str(ROOT / 'advanced-soft-actor-critic_b200')):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-CFG = dict(obs_shape=(6,), A=2, B=256, n_step=1, burn_in=0, E=2, hidden=64, depth=3, capacity=524288,
+CFG = dict(name='c2', obs_shape=(6,), A=2, B=256, n_step=1, burn_in=0, E=2, hidden=64, depth=3, capacity=524288,
            per_alpha=0.9, episode_len=100, rep=None)
 # BASELINE.json configs[2] (Pendulum shapes, n_step=5 + V-trace, batch 1024): `--config c3`, a secondary
 # measurement — the default run is configs[1], the one the metric is quoted on
 CONFIGS = {
-    'c2': dict(CFG),
-    'c3': dict(CFG, obs_shape=(3,), A=1, B=1024, n_step=5, depth=2),
+    'c2': dict(CFG, name='c2'),
+    'c3': dict(CFG, name='c3', obs_shape=(3,), A=1, B=1024, n_step=5, depth=2),
     # BASELINE.json configs[3] on ONE GPU (the 8-GPU replay sharding of that config is `--gpus 8` once the
     # representation's gradient joins the peer exchange): envs/test/nn_rnn.py GRU(6 + 2 -> 8, 2 layers),
     # burn-in 40, n_step 5 -> windows of 46 rows, batch 256 sequences, PER
-    'c4': dict(CFG, burn_in=40, n_step=5, rep=dict(hidden=8, layers=2)),
+    'c4': dict(CFG, name='c4', burn_in=40, n_step=5, rep=dict(hidden=8, layers=2)),
 }
 WORKLOADS = {
     'c2': 'TEST vector-obs(6,) A=2 SAC+PER alpha=0.9 capacity=524288 (full) batch=256 ensemble_q=2 n_step=1, '
@@ -176,34 +176,28 @@ def stage_work(cfg):
 
 
 # --------------------------------------------------------------------------- GPU arm
+PLUGIN_FILES = {'c2': 'envs_test_nn.py', 'c3': 'envs_gym_pendulum_nn.py', 'c4': 'envs_test_nn_rnn.py'}
+
+
+def load_plugin(config: str):
+    """The reference's own plugin file for the config, VERBATIM (tests/golden/plugins; byte-compared with the
+    checkout by tests/test_plugin_surface.py), executed the way sac_main.py:353-364 does — through the
+    `algorithm` alias package."""
+    import importlib.util
+    path = ROOT / 'tests' / 'golden' / 'plugins' / PLUGIN_FILES[config]
+    spec = importlib.util.spec_from_file_location(f'bench_nn_{config}', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def build_learner(device, seed, capacity, fill):
-    import types
-    import asac_b200.nn_models as m
     from asac_b200 import SAC_Base
-    depth = CFG['depth']
-
-    class ModelQ(m.ModelQ):  # what envs/gym/pendulum/nn.py does for its depth
-        def _build_model(self):
-            super()._build_model(c_dense_n=CFG['hidden'], c_dense_depth=depth)
-
-    class ModelPolicy(m.ModelPolicy):
-        def _build_model(self):
-            super()._build_model(c_dense_n=CFG['hidden'], c_dense_depth=depth)
-
-    ModelRep, seq_encoder = m.ModelSimpleRep, None
+    nn = load_plugin(CFG['name'])
+    seq_encoder = None
     if CFG.get('rep'):
-        from asac_b200.config_enums import SEQ_ENCODER
+        from asac_b200.utils.enums import SEQ_ENCODER
         seq_encoder = SEQ_ENCODER.RNN
-
-        class ModelRep(m.ModelBaseRep):  # the form of envs/test/nn_rnn.py
-            def _build_model(self):
-                self.rnn = m.GRU(self.obs_shapes[0][0] + self.c_action_size, CFG['rep']['hidden'], CFG['rep']['layers'])
-
-            def forward(self, obs_list, pre_action, pre_seq_hidden_state, padding_mask=None):
-                h0 = None if pre_seq_hidden_state is None else pre_seq_hidden_state[:, 0]
-                return self.rnn(torch.cat([obs_list[0], pre_action], dim=-1), h0)
-
-    nn = types.SimpleNamespace(ModelRep=ModelRep, ModelQ=ModelQ, ModelPolicy=ModelPolicy)
     sac = SAC_Base(obs_names=['vector'], obs_shapes=[CFG['obs_shape']], d_action_sizes=[], c_action_size=CFG['A'],
                    model_abs_dir=None, nn=nn, device=device, seed=seed, batch_size=CFG['B'], n_step=CFG['n_step'],
                    burn_in_step=CFG['burn_in'], ensemble_q_num=CFG['E'], ensemble_q_sample=CFG['E'],

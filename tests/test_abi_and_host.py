@@ -93,8 +93,9 @@ def test_host_only_entry_points():
 
 
 def _load_plugin(tmp_path, text):
-    path = tmp_path / 'nn_plugin_cpu.py'
-    path.write_text(text)
+    path = Path(text) if str(text).endswith('.py') else tmp_path / 'nn_plugin_cpu.py'
+    if not str(text).endswith('.py'):
+        path.write_text(text)
     spec = importlib.util.spec_from_file_location('nn_plugin_cpu', path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
@@ -105,11 +106,7 @@ def test_plugin_file_loads_unchanged_and_matches_oracle_forward(tmp_path):
     """envs/gym/pendulum/nn.py's text, imported through the `algorithm` alias package."""
     from asac_b200 import lowering
     from oracle.sac_oracle import policy_forward, q_forward
-    nn = _load_plugin(tmp_path, 'import algorithm.nn_models as m\n\nModelRep = m.ModelSimpleRep\n\n\n'
-                                'class ModelQ(m.ModelQ):\n    def _build_model(self):\n'
-                                '        super()._build_model(c_dense_n=64, c_dense_depth=2)\n\n\n'
-                                'class ModelPolicy(m.ModelPolicy):\n    def _build_model(self):\n'
-                                '        super()._build_model(c_dense_n=64, c_dense_depth=2)\n')
+    nn = _load_plugin(tmp_path, Path(__file__).resolve().parent / 'golden' / 'plugins' / 'envs_gym_pendulum_nn.py')
     torch.manual_seed(0)
     q = nn.ModelQ(3, [], 1, False, None)
     pi = nn.ModelPolicy(3, [], 1, None)
@@ -270,8 +267,9 @@ def test_recurrent_representation_lowering_on_the_host():
     for bad in (TwoGrus, GruAndDense, WrongInput):
         with pytest.raises(lowering.NotStockNetwork):
             lowering.analyze_rep(bad(['v'], [(6,)], [], 2, False), [(6,)], 2)
-    with pytest.raises(NotImplementedError):
-        m.GRU(8, 8, 1)(torch.zeros(1, 2, 8), None, torch.zeros(1, 2, dtype=torch.bool))
+    # the torch wrapper itself supports the padding-mask (packed) form of seq_layers.py:60-103
+    out, hn = m.GRU(8, 8, 1)(torch.zeros(1, 2, 8), None, torch.tensor([[True, False]]))
+    assert out.shape == (1, 2, 8) and float(out[0, 0].abs().sum()) == 0.0
 
 
 def test_batch_buffer_windows_without_the_reference():

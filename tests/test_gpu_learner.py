@@ -10,51 +10,16 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-PLUGIN_TEST = '''import algorithm.nn_models as m
-
-ModelRep = m.ModelSimpleRep
-ModelQ = m.ModelQ
-ModelPolicy = m.ModelPolicy
-'''
-
-PLUGIN_PENDULUM = '''import algorithm.nn_models as m
-
-ModelRep = m.ModelSimpleRep
+PLUGINS = Path(__file__).resolve().parent / 'golden' / 'plugins'
+# VERBATIM copies of the reference's plugin files (tests/test_plugin_surface.py compares them byte for byte
+# with the checkout where it is mounted): envs/test/nn.py, envs/gym/pendulum/nn.py, envs/test/nn_rnn.py
+PLUGIN_TEST = PLUGINS / 'envs_test_nn.py'
+PLUGIN_PENDULUM = PLUGINS / 'envs_gym_pendulum_nn.py'
+PLUGIN_RNN = PLUGINS / 'envs_test_nn_rnn.py'
 
 
-class ModelQ(m.ModelQ):
-    def _build_model(self):
-        super()._build_model(c_dense_n=64, c_dense_depth=2)
-
-
-class ModelPolicy(m.ModelPolicy):
-    def _build_model(self):
-        super()._build_model(c_dense_n=64, c_dense_depth=2)
-'''
-
-
-PLUGIN_RNN = '''import torch
-
-import algorithm.nn_models as m
-
-
-class ModelRep(m.ModelBaseRep):
-    def _build_model(self):
-        self.rnn = m.GRU(self.obs_shapes[0][0] + self.c_action_size, 8, 2)
-
-    def forward(self, obs_list, pre_action, pre_seq_hidden_state, padding_mask=None):
-        h0 = None if pre_seq_hidden_state is None else pre_seq_hidden_state[:, 0]
-        return self.rnn(torch.cat([obs_list[0], pre_action], dim=-1), h0)
-
-
-ModelQ = m.ModelQ
-ModelPolicy = m.ModelPolicy
-'''
-
-
-def _plugin(tmp_path: Path, text: str, name: str):
-    path = tmp_path / f'{name}.py'
-    path.write_text(text)  # same text as the reference's envs/test/nn.py / envs/gym/pendulum/nn.py
+def _plugin(tmp_path: Path, path: Path, name: str):
+    """Executes the plugin file the way sac_main.py:353-364 does."""
     spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

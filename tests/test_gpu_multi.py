@@ -17,18 +17,14 @@ def _free_port() -> int:
 
 
 def _rnn_plugin():
-    import types
-    import asac_b200.nn_models as m
-
-    class ModelRep(m.ModelBaseRep):  # the form of envs/test/nn_rnn.py
-        def _build_model(self):
-            self.rnn = m.GRU(self.obs_shapes[0][0] + self.c_action_size, 8, 2)
-
-        def forward(self, obs_list, pre_action, pre_seq_hidden_state, padding_mask=None):
-            h0 = None if pre_seq_hidden_state is None else pre_seq_hidden_state[:, 0]
-            return self.rnn(torch.cat([obs_list[0], pre_action], dim=-1), h0)
-
-    return types.SimpleNamespace(ModelRep=ModelRep, ModelQ=m.ModelQ, ModelPolicy=m.ModelPolicy)
+    """The verbatim envs/test/nn_rnn.py of the reference (tests/golden/plugins)."""
+    import importlib.util
+    from pathlib import Path
+    path = Path(__file__).resolve().parent / 'golden' / 'plugins' / 'envs_test_nn_rnn.py'
+    spec = importlib.util.spec_from_file_location('nn_plugin_rnn_multi', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def _worker(rank: int, world: int, port: int, out_dir: str, peer_exchange: int, graph: int, rep: int = 0,
@@ -49,7 +45,7 @@ def _worker(rank: int, world: int, port: int, out_dir: str, peer_exchange: int, 
         nn = types.SimpleNamespace(ModelRep=m.ModelSimpleRep, ModelQ=m.ModelQ, ModelPolicy=m.ModelPolicy)
         kw, hidden_shape = {}, (0,)
         if rep:
-            from asac_b200.config_enums import SEQ_ENCODER
+            from asac_b200.utils.enums import SEQ_ENCODER
             nn, hidden_shape = _rnn_plugin(), (2, 8)
             kw = dict(seq_encoder=SEQ_ENCODER.RNN, burn_in_step=3, n_step=2)
         sac = SAC_Base(obs_names=['vector'], obs_shapes=[(6,)], d_action_sizes=[], c_action_size=2, model_abs_dir=None,
