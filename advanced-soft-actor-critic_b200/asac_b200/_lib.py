@@ -145,6 +145,7 @@ PROTOTYPES = {
     'asac_sac_finish_step': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacWork), vp, i64, vp, vp, vp,
                                    P(AsacPeerTable), vp]),
     'asac_peer_recv_words': (i64, [P(AsacSacConfig), i32]),
+    'asac_peer_timeouts': (i32, [i32]),
     'asac_gru_param_count': (i64, [P(AsacGruShape)]),
     'asac_gru_backward_tile': (i32, [P(AsacGruShape), i32]),
     'asac_gru_forward': (i32, [P(AsacGruShape), P(AsacGruNet), i32, vp, vp, i32, vp, vp, i64, i32, i32, vp]),

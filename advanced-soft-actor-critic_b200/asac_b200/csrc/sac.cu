@@ -887,14 +887,35 @@ __device__ __forceinline__ void peer_push(const PeerExchange &x, unsigned epoch,
         asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(w) : "memory");
     }
 }
+// Polls are bounded: a peer that crashed, or ranks that disagree on the number of train() calls, must not
+// hang the GPU inside a kernel.  After PEER_TIMEOUT_NS without the expected epoch the wait is abandoned,
+// g_peer_timeouts is bumped (the host reads it through asac_peer_timeouts and raises) and the missing
+// contribution counts as zero.
+__device__ unsigned int g_peer_timeouts;
+constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ float peer_sum(const PeerExchange &x, unsigned epoch, int64_t p) {
     float s = 0.f;
     for (int q = 0; q < x.world; ++q) {
         const unsigned long long *src = peer_slot(x, x.rank, epoch, q) + p;
         unsigned long long w;
-        do {
-            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
-        } while ((unsigned)(w >> 32) != epoch);
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+        if ((unsigned)(w >> 32) != epoch) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned spins = 0;
+            do {
+                asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+                if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > PEER_TIMEOUT_NS) {
+                    atomicAdd(&g_peer_timeouts, 1u);
+                    w = (unsigned long long)epoch << 32;  // +0.0f
+                    break;
+                }
+            } while ((unsigned)(w >> 32) != epoch);
+        }
         s += __uint_as_float((unsigned)(w & 0xFFFFFFFFull));
     }
     return s;
@@ -1510,6 +1531,16 @@ extern "C" int64_t asac_peer_recv_words(const AsacSacConfig *cfg, int world) {
     if (validate(cfg) != ASAC_OK) return -1;
     return 2 * (int64_t)world *
            (net_stride(q_shape(*cfg)) * cfg->ensemble + net_stride(pi_shape(*cfg)) + 4 + cfg->rep_param_stride);
+}
+
+extern "C" int asac_peer_timeouts(int reset) {
+    unsigned int n = 0;
+    if (cudaMemcpyFromSymbol(&n, asac::g_peer_timeouts, sizeof(n)) != cudaSuccess) return -1;
+    if (reset && n) {
+        const unsigned int zero = 0;
+        cudaMemcpyToSymbol(asac::g_peer_timeouts, &zero, sizeof(zero));
+    }
+    return (int)n;
 }
 
 static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk, int which,

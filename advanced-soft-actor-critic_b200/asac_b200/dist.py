@@ -52,6 +52,18 @@ def broadcast_(tensors: list[torch.Tensor], src: int = 0, group=None) -> None:
             dist.broadcast(t, src=src, group=group)
 
 
+def all_agree(flag: bool, device=None, group=None) -> bool:
+    """True iff ``flag`` is true on EVERY rank (MIN all-reduce; the tensor lives on the CPU for gloo, on
+    ``device`` for NCCL).  Used for decisions every rank must take identically: whether to step, which
+    gradient exchange to run."""
+    if world()[1] == 1:
+        return bool(flag)
+    on_cpu = dist.get_backend(group) == 'gloo' or device is None
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device='cpu' if on_cpu else device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
+
+
 class PeerGradientExchange:
     """Symmetric NVLink-mapped receive buffer for the in-kernel gradient exchange
     (include/asac_b200.h, AsacPeerTable).  Built on ``torch.distributed._symmetric_memory`` (CUDA

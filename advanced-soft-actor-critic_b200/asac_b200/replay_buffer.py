@@ -17,8 +17,10 @@ every ``nan_check_every`` updates and on ``save`` / ``close``).
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import logging
 import math
+import threading
 from pathlib import Path
 
 import numpy as np
@@ -39,6 +41,18 @@ _TORCH_TO_NP = {v: k for k, v in _NP_TO_TORCH.items()}
 
 def _align16(n: int) -> int:
     return (n + 15) & ~15
+
+
+def _locked(fn):
+    """Host-side mutual exclusion for the mutating public methods: the reference guards its rings with a
+    read/write lock (replay_buffer.py:273-274, utils/lock.py) because actor threads call ``add`` while the
+    learner trains; here one re-entrant mutex serialises the bookkeeping (``_size``, ``_next_id``, the
+    staging slot ring) — the device work itself is ordered by the stream."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with self._mutex:
+            return fn(self, *args, **kwargs)
+    return wrapper
 
 
 def _to_device(v, device) -> torch.Tensor:
@@ -106,6 +120,10 @@ class PrioritizedReplayBuffer:
         self._stage_limit = 64 << 20
         self._nan_check_every = nan_check_every
         self._closed = False
+        self._mutex = threading.RLock()
+        # a learner that defers its priority update registers a hook here; everything that READS the tree
+        # from outside the learner's own schedule (sample / save / copy) applies the pending update first
+        self._flush_hook = None
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -253,6 +271,7 @@ class PrioritizedReplayBuffer:
         self._advance(first_id, T)
         return True
 
+    @_locked
     def add(self, transitions: dict[str, np.ndarray], ignore_size=0) -> None:
         with torch.cuda.device(self.device):
             if self._add_native(transitions, ignore_size):
@@ -268,13 +287,19 @@ class PrioritizedReplayBuffer:
                                          ptr(max_p), int(ignore_size), self._stream), 'per_add')
             self._advance(first_id, T)
 
+    @_locked
     def add_with_td_error(self, td_error: np.ndarray, transitions: dict[str, np.ndarray],
                           ignore_size: int = 0) -> None:
         with torch.cuda.device(self.device):
-            td = _to_device(np.asarray(td_error, dtype=np.float32).flatten(), self.device)
-            first_id, T = self._store(transitions)
-            if td.numel() != T:
+            td_host = np.asarray(td_error, dtype=np.float32).flatten()
+            T = int(next(iter(transitions.values())).shape[0])
+            if td_host.shape[0] != T:  # before anything is written
                 raise ValueError('td_error and transitions disagree in length')
+            if np.isnan(td_host).any():  # replay_buffer.py:418-420 raises before touching the tree
+                self._logger.error('td_error has nan')
+                raise Exception('td_error has nan')
+            td = _to_device(td_host, self.device)
+            first_id, T = self._store(transitions)
             # ids first (per_add with zero priorities), then the td-derived priorities with the
             # reference's tail masking (replay_buffer.py:330-336)
             zero = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -334,7 +359,8 @@ class PrioritizedReplayBuffer:
         """
         if not self.is_lg_batch_size:
             return None
-        with torch.cuda.device(self.device):
+        with self._mutex, torch.cuda.device(self.device):
+            self._flush()
             _, data_ids, _, w = self._draw(unit_uniform)
             L = self.prev_n + 1 + self.post_n
             out, specs = {}, []
@@ -370,6 +396,7 @@ class PrioritizedReplayBuffer:
         if self._nan_check_every and self._updates % self._nan_check_every == 0:
             self.check_nan()
 
+    @_locked
     def update(self, data_ids, td_error) -> None:
         with torch.cuda.device(self.device):
             ids = self._ids_tensor(data_ids)
@@ -380,6 +407,7 @@ class PrioritizedReplayBuffer:
                 raise ValueError('data_ids and td_error disagree in length')
             self._update_priorities(ids, td)
 
+    @_locked
     def update_transitions(self, data_ids, key: str, data) -> None:
         with torch.cuda.device(self.device):
             ids = self._ids_tensor(data_ids)
@@ -424,9 +452,15 @@ class PrioritizedReplayBuffer:
         return self._store_ids[self._ids_tensor(data_ids) % self.capacity]
 
     # ------------------------------------------------------------------ checkpoint interchange
+    def _flush(self) -> None:
+        if self._flush_hook is not None:
+            self._flush_hook()
+
+    @_locked
     def save(self, save_dir: Path, ckpt: int) -> None:
         """Writes the reference's files: ``<ckpt>-rb_tree.npy`` (float32[2C-1], root first) and
         ``<ckpt>-rb_storage.npz`` (replay_buffer.py:436-441,96-97,220-221)."""
+        self._flush()
         self.check_nan()
         save_dir = Path(save_dir)
         np.save(save_dir.joinpath(f'{ckpt}-rb_tree.npy'), self._nodes[1:].cpu().numpy())
@@ -435,32 +469,53 @@ class PrioritizedReplayBuffer:
             cols[k] = col.cpu().numpy()
         np.savez(save_dir.joinpath(f'{ckpt}-rb_storage.npz'), **cols, p_size=self._size, p_id=self._next_id)
 
+    @_locked
     def load(self, save_dir: Path, ckpt: int) -> None:
+        """Reads the reference's files.  Everything is validated against THIS buffer before any state
+        changes: node count, ``_id`` length, every column's leading dimension; float64 columns (a NumPy
+        default that slips into hand-written episodes) are cast to float32, the dtype the kernels gather."""
         save_dir = Path(save_dir)
         tree_path = save_dir.joinpath(f'{ckpt}-rb_tree.npy')
+        storage_path = save_dir.joinpath(f'{ckpt}-rb_storage.npz')
+        tree = cols = None
         if tree_path.exists():
             tree = np.load(tree_path)
-            if tree.shape[0] != 2 * self.capacity - 1:
-                raise ValueError(f'tree file holds {tree.shape[0]} nodes, capacity {self.capacity} needs '
+            if tree.ndim != 1 or tree.shape[0] != 2 * self.capacity - 1:
+                raise ValueError(f'tree file holds {tree.shape} nodes, capacity {self.capacity} needs '
                                  f'{2 * self.capacity - 1}')
-            self._nodes[1:].copy_(torch.from_numpy(tree.astype(np.float32)))
-            self._nodes[0] = 0
-        storage_path = save_dir.joinpath(f'{ckpt}-rb_storage.npz')
         if storage_path.exists():
-            saved = np.load(storage_path)
-            self._size = int(saved['p_size'])
-            self._next_id = int(saved['p_id'])
-            self._drop_ingest()
-            self._columns = {}
-            for k in saved.files:
+            with np.load(storage_path) as saved:
+                cols = {k: saved[k] for k in saved.files}
+            for need in ('p_size', 'p_id', '_id'):
+                if need not in cols:
+                    raise ValueError(f'{storage_path.name} has no {need!r} entry')
+            for k, v in cols.items():
                 if k in ('p_size', 'p_id'):
                     continue
-                t = torch.from_numpy(saved[k]).to(self.device)
-                if k == '_id':
-                    self._store_ids.copy_(t)
-                else:
-                    self._columns[k] = t.contiguous()
+                if v.shape[:1] != (self.capacity,):
+                    raise ValueError(f'{storage_path.name}: column {k!r} holds {v.shape[0] if v.ndim else 0} rows, '
+                                     f'this buffer has capacity {self.capacity}')
+                if v.dtype == np.float64:
+                    cols[k] = v.astype(np.float32)
+                elif v.dtype not in _NP_TO_TORCH:
+                    raise ValueError(f'{storage_path.name}: column {k!r} has unsupported dtype {v.dtype}')
+            if cols['_id'].dtype != np.int64:
+                raise ValueError(f"{storage_path.name}: '_id' is {cols['_id'].dtype}, expected int64")
+            if not 0 <= int(cols['p_size']) <= self.capacity or not 0 <= int(cols['p_id']) < self.max_id:
+                raise ValueError(f'{storage_path.name}: p_size / p_id out of range')
+        with torch.cuda.device(self.device):
+            if tree is not None:
+                self._nodes[1:].copy_(torch.from_numpy(tree.astype(np.float32)))
+                self._nodes[0] = 0
+            if cols is not None:
+                self._drop_ingest()
+                self._store_ids.copy_(torch.from_numpy(cols['_id']))
+                self._columns = {k: torch.from_numpy(v).to(self.device).contiguous() for k, v in cols.items()
+                                 if k not in ('p_size', 'p_id', '_id')}
+                self._size = int(cols['p_size'])
+                self._next_id = int(cols['p_id'])
 
+    @_locked
     def clear(self) -> None:
         self._drop_ingest()
         self._size = 0
@@ -469,9 +524,11 @@ class PrioritizedReplayBuffer:
         self._nodes.zero_()
         self._store_ids.zero_()
 
+    @_locked
     def copy(self, src: 'PrioritizedReplayBuffer') -> None:
         if src.capacity != self.capacity:
             raise ValueError('capacity mismatch')
+        src._flush()
         self._drop_ingest()
         self._nodes.copy_(src._nodes)
         self._store_ids.copy_(src._store_ids)

@@ -239,6 +239,7 @@ class SAC_Base:
             self._init_or_restore(int(last_ckpt) if last_ckpt is not None else None)
         self._graphs = [None, None]
         self._graph_columns_key = None
+        self._steps_since_check = 0
         # NCCL all-reduces are captured into the step's CUDA graph (ASAC_GRAPH_COLLECTIVES=0 keeps them eager)
         self._graph_collectives = os.environ.get('ASAC_GRAPH_COLLECTIVES', '1') != '0'
         if self._world > 1:
@@ -464,6 +465,7 @@ class SAC_Base:
         self.replay_buffer = PrioritizedReplayBuffer(batch_size=self.batch_size, sample_prev_n=self.burn_in_step,
                                                      sample_post_n=self.n_step, device=self.device,
                                                      logger_parent_name=self._logger.name, **replay_config)
+        self.replay_buffer._flush_hook = self.flush_priority_update
         self._cfg.td_error_min = float(self.replay_buffer.td_error_min)
         self._cfg.td_error_max = float(self.replay_buffer.td_error_max)
         self._cfg.per_alpha = float(self.replay_buffer.alpha)
@@ -544,6 +546,13 @@ class SAC_Base:
             except Exception as e:  # noqa: BLE001 - any failure of the mapping falls back to NCCL
                 self._logger.warning(f'peer-memory gradient exchange unavailable ({e}); using NCCL all-reduce')
                 self._peers = self._peer_table = None
+            # every rank must run the SAME exchange: one rank on NCCL while the others poll peer memory would
+            # spin until the exchange's timeout
+            if not adist.all_agree(self._peer_table is not None, dev):
+                if self._peer_table is not None:
+                    self._logger.warning('a peer rank could not map the exchange buffers; all ranks use NCCL')
+                self._peers = self._peer_table = None
+        self._ready_version = None  # replay version for which every rank was seen ready to step
 
     def _make_batch_set(self) -> dict:
         B, L, S, A = self.batch_size, self._cfg.seq_len, self.state_size, self.c_action_size
@@ -1159,9 +1168,11 @@ class SAC_Base:
         if not self.use_replay_buffer:
             return self._train_on_policy(step)
         rb = self.replay_buffer
-        if not rb.is_lg_batch_size:
+        if not self._ready_to_step():
             return step
-        with torch.cuda.device(self.device):
+        # the replay's host mutex: an actor thread's add() must not interleave its bookkeeping / staging
+        # copies with the enqueue (or the capture) of a step
+        with rb._mutex, torch.cuda.device(self.device):
             key = rb._columns_version
             if self._graph_columns_key != key:  # first step, or the storage was re-allocated (load / clear)
                 for st in self._sets:
@@ -1175,22 +1186,50 @@ class SAC_Base:
                 cur = (1 - self._cur) if self._sample_ahead else self._cur
                 if self._graphs[cur] is None:
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
+                    # thread_local: an actor thread allocating / synchronising elsewhere must not invalidate the capture
+                    with torch.cuda.graph(graph, capture_error_mode='thread_local'):
                         self._enqueue_step_sets(cur)
                     self._graphs[cur] = graph
                 self._graphs[cur].replay()
                 self._cur = cur
                 self._pending = self._defer_active  # (a flush in between cleared it; the replay deferred again)
+        self._steps_since_check += 1
+        if self._world > 1 and self._peer_table is not None and self._steps_since_check >= 256:
+            self.check_peer_exchange()
         if self.save_model_per_step and step % self.save_model_per_step == 0:
             self.save_model()
         if self.summary_writer is not None and step % self.write_summary_per_step == 0:
             self._write_summaries(step)
         return self.increase_global_step()
 
+    def _ready_to_step(self) -> bool:
+        """sac_base.py:2503-2506 (train() is a no-op until the buffer holds more than one batch) — agreed on
+        ACROSS ranks: shards fill unevenly, and a rank that stepped alone would wait inside the gradient
+        exchange for peers that never enqueued the step.  One MIN all-reduce per call until every shard is
+        ready; after that the check is free."""
+        rb = self.replay_buffer
+        if self._ready_version == rb._columns_version and rb.is_lg_batch_size:
+            return True
+        ready = rb.is_lg_batch_size
+        if self._world > 1:
+            ready = adist.all_agree(ready, self.device)
+        if ready:
+            self._ready_version = rb._columns_version
+        return ready
+
+    def check_peer_exchange(self) -> None:
+        """Raises when a kernel gave up waiting for a peer's gradients (a crashed or diverged rank):
+        the in-kernel exchange polls with a time limit and reports here instead of hanging the GPU."""
+        self._steps_since_check = 0
+        n = int(self._lib.asac_peer_timeouts(1))
+        if n:
+            raise _lib.AsacError(f'gradient exchange: {n} wait(s) for a peer rank timed out — a rank crashed or '
+                                 'the ranks called train() a different number of times')
+
     def _write_summaries(self, step: int) -> None:
         wk, B = self._wk, self.batch_size
         w = self.summary_writer
-        w.add_scalar('loss/q', float(wk['loss_q'][:, 0].sum().item()) / B, step)
+        w.add_scalar('loss/q', float(wk['loss_q'].sum().item()) / (B * self.ensemble_q_num), step)  # ensemble mean
         w.add_scalar('loss/c_entropy', float(wk['stats_pi'][:, 1].sum().item()) / B, step)
         w.add_scalar('loss/c_alpha', float(torch.exp(self.log_c_alpha).item()), step)
         w.add_scalar('metric/replay_id', self.replay_buffer.get_curr_id(), step)
@@ -1200,7 +1239,7 @@ class SAC_Base:
     def last_step_stats(self) -> dict[str, float]:
         """Scalars of the most recent step (synchronises): what sac_base.py:2128-2178 logs."""
         wk, B = self._wk, self.batch_size
-        return {'loss_q': float(wk['loss_q'][:, 0].sum().item()) / B,
+        return {'loss_q': float(wk['loss_q'].sum().item()) / (B * self.ensemble_q_num),  # mean over the ensemble
                 'loss_policy': float(wk['stats_pi'][:, 0].sum().item()) / B,
                 'c_entropy': float(wk['stats_pi'][:, 1].sum().item()) / B,
                 'c_alpha': float(torch.exp(self.log_c_alpha).item()),
@@ -1208,6 +1247,9 @@ class SAC_Base:
 
     def close(self):
         self._closed = True
+        if getattr(self, '_peer_table', None) is not None:
+            torch.cuda.synchronize(self.device)
+            self.check_peer_exchange()
         if hasattr(self, 'replay_buffer') and getattr(self, '_pending', False):
             self.flush_priority_update()
         self._graphs = [None, None]

@@ -355,6 +355,12 @@ typedef struct {
     int64_t recv_words;    /* size of each receive buffer in 8-byte words */
 } AsacPeerTable;
 int64_t asac_peer_recv_words(const AsacSacConfig *cfg, int world);
+/* The polls above are bounded (20 s): a crashed peer, or ranks that called train() a different number of
+ * times, would otherwise hang the GPU inside a kernel.  An abandoned wait counts the missing gradient as
+ * zero and bumps a device counter; this returns it (and clears it when reset != 0).  Synchronises with the
+ * device.  The learner polls it every 256 steps and on close() and raises (no reference counterpart: the
+ * reference trains on one device). */
+int asac_peer_timeouts(int reset);
 
 /* asac_sac_step without its tail: [polyak,] target_y, q_backward, reduce_adam(q), policy_backward,
  * reduce_adam(pi), post.  `with_polyak` = 0 when the caller has enqueued asac_sac_polyak itself

@@ -773,37 +773,54 @@ def gen_sac_discrete_case(name, *, S, d_action_sizes, A, E, B, b, n, steps, seed
     print('wrote', f'sac_{name}.npz', sum(v.nbytes for v in out.values()), 'bytes raw')
 
 
-def main():
-    GOLDEN.mkdir(parents=True, exist_ok=True)
-    gen_per_case('small', capacity=64, batch_size=8, prev_n=2, post_n=3, alpha=0.9,
-                 episode_lens=[9, 5, 17, 30, 12], n_rounds=3, seed=1)
-    gen_per_case('zeros', capacity=256, batch_size=32, prev_n=0, post_n=1, alpha=0.6,
-                 episode_lens=[100, 100, 90, 40], n_rounds=2, seed=2, zero_fraction=0.3)
-    gen_padding_case('b2n3', burn_in_step=2, n_step=3, batch_size=16, capacity=128, seed=3)
-    gen_padding_case('b0n1', burn_in_step=0, n_step=1, batch_size=16, capacity=128, seed=4)
+CASES = {
+    'per_small': lambda: gen_per_case('small', capacity=64, batch_size=8, prev_n=2, post_n=3, alpha=0.9,
+                                      episode_lens=[9, 5, 17, 30, 12], n_rounds=3, seed=1),
+    'per_zeros': lambda: gen_per_case('zeros', capacity=256, batch_size=32, prev_n=0, post_n=1, alpha=0.6,
+                                      episode_lens=[100, 100, 90, 40], n_rounds=2, seed=2, zero_fraction=0.3),
+    'pad_b2n3': lambda: gen_padding_case('b2n3', burn_in_step=2, n_step=3, batch_size=16, capacity=128, seed=3),
+    'pad_b0n1': lambda: gen_padding_case('b0n1', burn_in_step=0, n_step=1, batch_size=16, capacity=128, seed=4),
     # config-2 shapes (envs/test/nn.py: H=64, depth 3), small batch, 3 consecutive steps
-    gen_sac_case('c2', S=6, A=2, E=2, hidden=64, depth=3, B=32, b=0, n=1, steps=3, seed=10,
-                 nn_rel='envs/test/nn.py')
+    'sac_c2': lambda: gen_sac_case('c2', S=6, A=2, E=2, hidden=64, depth=3, B=32, b=0, n=1, steps=3, seed=10,
+                                   nn_rel='envs/test/nn.py'),
     # config-3 shapes (envs/gym/pendulum/nn.py: depth 2), n=5 V-trace with IS
-    gen_sac_case('c3', S=3, A=1, E=2, hidden=64, depth=2, B=24, b=0, n=5, steps=2, seed=11,
-                 nn_rel='envs/gym/pendulum/nn.py', v_lambda=1.0, use_n_step_is=True)
+    'sac_c3': lambda: gen_sac_case('c3', S=3, A=1, E=2, hidden=64, depth=2, B=24, b=0, n=5, steps=2, seed=11,
+                                   nn_rel='envs/gym/pendulum/nn.py', v_lambda=1.0, use_n_step_is=True),
     # odd sizes: 3 critics, burn-in rows, lambda/rho/c != 1, no PER weights, clip_epsilon<=0 branch
-    gen_sac_case('odd', S=5, A=3, E=3, hidden=32, depth=1, B=12, b=2, n=3, steps=2, seed=12,
-                 use_priority=False, v_lambda=0.95, v_rho=0.9, v_c=0.8, clip_epsilon=0.0, tau=0.05,
-                 update_target_per_step=2, gamma=0.97)
-    gen_sac_case('nois', S=4, A=2, E=2, hidden=32, depth=2, B=10, b=0, n=2, steps=2, seed=13,
-                 use_n_step_is=False, use_auto_alpha=False)
+    'sac_odd': lambda: gen_sac_case('odd', S=5, A=3, E=3, hidden=32, depth=1, B=12, b=2, n=3, steps=2, seed=12,
+                                    use_priority=False, v_lambda=0.95, v_rho=0.9, v_c=0.8, clip_epsilon=0.0, tau=0.05,
+                                    update_target_per_step=2, gamma=0.97),
+    'sac_nois': lambda: gen_sac_case('nois', S=4, A=2, E=2, hidden=32, depth=2, B=10, b=0, n=2, steps=2, seed=13,
+                                     use_n_step_is=False, use_auto_alpha=False),
     # config-4 shapes (envs/test/nn_rnn.py: GRU(6 + 2 -> 8, 2 layers)), shorter burn-in, 2 steps
-    gen_sac_rnn_case('rnn', So=6, A=2, E=2, B=16, b=5, n=3, steps=2, seed=14, v_lambda=0.95)
-    gen_sac_rnn_case('rnn_b0', So=6, A=2, E=2, B=8, b=0, n=1, steps=2, seed=15, use_n_step_is=False)
-    # discrete / hybrid action branches (oracle groundwork)
-    gen_sac_discrete_case('disc', S=6, d_action_sizes=[3, 4], A=0, E=2, B=10, b=0, n=3, steps=2, seed=16, v_lambda=0.9)
-    gen_sac_discrete_case('hybrid', S=6, d_action_sizes=[3], A=2, E=2, B=10, b=1, n=2, steps=2, seed=17)
-    gen_sac_discrete_case('dqn', S=6, d_action_sizes=[4, 2], A=0, E=2, B=10, b=0, n=3, steps=2, seed=18,
-                          discrete_dqn_like=True)
+    'sac_rnn': lambda: gen_sac_rnn_case('rnn', So=6, A=2, E=2, B=16, b=5, n=3, steps=2, seed=14, v_lambda=0.95),
+    'sac_rnn_b0': lambda: gen_sac_rnn_case('rnn_b0', So=6, A=2, E=2, B=8, b=0, n=1, steps=2, seed=15,
+                                           use_n_step_is=False),
+    # the BASELINE configs at their FULL shapes, one step each: configs[1] B=256; configs[2] B=1024, n=5;
+    # configs[3] B=256 sequences of burn-in 40 + n_step 5 (46-row windows, padding inside the burn-in)
+    'sac_c2_b256': lambda: gen_sac_case('c2_b256', S=6, A=2, E=2, hidden=64, depth=3, B=256, b=0, n=1, steps=1,
+                                        seed=30, nn_rel='envs/test/nn.py'),
+    'sac_c3_b1024': lambda: gen_sac_case('c3_b1024', S=3, A=1, E=2, hidden=64, depth=2, B=1024, b=0, n=5, steps=1,
+                                         seed=31, nn_rel='envs/gym/pendulum/nn.py', v_lambda=1.0, use_n_step_is=True),
+    'sac_rnn_c4': lambda: gen_sac_rnn_case('rnn_c4', So=6, A=2, E=2, B=256, b=40, n=5, steps=1, seed=32),
+    # discrete / hybrid action branches
+    'sac_disc': lambda: gen_sac_discrete_case('disc', S=6, d_action_sizes=[3, 4], A=0, E=2, B=10, b=0, n=3, steps=2,
+                                              seed=16, v_lambda=0.9),
+    'sac_hybrid': lambda: gen_sac_discrete_case('hybrid', S=6, d_action_sizes=[3], A=2, E=2, B=10, b=1, n=2, steps=2,
+                                                seed=17),
+    'sac_dqn': lambda: gen_sac_discrete_case('dqn', S=6, d_action_sizes=[4, 2], A=0, E=2, B=10, b=0, n=3, steps=2,
+                                             seed=18, discrete_dqn_like=True),
     # checkpoint directories written by the reference itself (interchange)
-    gen_ckpt_case('vector', rnn=False, seed=21)
-    gen_ckpt_case('rnn', rnn=True, seed=22)
+    'ckpt_vector': lambda: gen_ckpt_case('vector', rnn=False, seed=21),
+    'ckpt_rnn': lambda: gen_ckpt_case('rnn', rnn=True, seed=22),
+}
+
+
+def main():
+    """python oracle/gen_golden.py [case ...]   (no arguments: every case)"""
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    for name in (sys.argv[1:] or list(CASES)):
+        CASES[name]()
 
 
 if __name__ == '__main__':

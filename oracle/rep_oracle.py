@@ -117,10 +117,12 @@ class SacRepOracle(SacOracle):
         self.rep, self.rep_target = to_t(rep), to_t(rep_target)
         self._wire()
 
-    def copy_state_from(self, other: 'SacRepOracle') -> None:
+    def copy_state_from(self, other: 'SacRepOracle', adam: bool = False) -> None:
         self.rep = {k: v.detach().to(self.dtype).clone() for k, v in other.rep.items()}
         self.rep_target = {k: v.detach().to(self.dtype).clone() for k, v in other.rep_target.items()}
-        super().copy_state_from(other)
+        super().copy_state_from(other, adam)
+        if adam:
+            self._copy_adam(self.opt_rep, self.rep, other.opt_rep, other.rep)
 
     @torch.no_grad()
     def polyak(self, tau: float):  # sac_base.py:745-764: representation first, then the critics

@@ -242,10 +242,24 @@ class SacOracle:
         self.log_c_alpha = torch.as_tensor(log_c_alpha).detach().to(self.dtype).reshape(()).clone()
         self._wire()
 
-    def copy_state_from(self, other: 'SacOracle') -> None:
-        """Parameters and step counter of ``other`` (cast to this oracle's dtype); fresh Adam state."""
+    def copy_state_from(self, other: 'SacOracle', adam: bool = False) -> None:
+        """Parameters and step counter of ``other`` (cast to this oracle's dtype); fresh Adam state unless
+        ``adam`` (then the moments and step counts travel too, so a float64 twin can follow a float32 oracle
+        over several steps)."""
         self.load_params(other.q, other.q_target, other.policy, other.log_c_alpha)
         self.global_step = other.global_step
+        if adam:
+            for i in range(len(self.q)):
+                self._copy_adam(self.opt_q[i], self.q[i], other.opt_q[i], other.q[i])
+            self._copy_adam(self.opt_policy, self.policy, other.opt_policy, other.policy)
+            self._copy_adam(self.opt_alpha, {'a': self.log_c_alpha}, other.opt_alpha, {'a': other.log_c_alpha})
+
+    def _copy_adam(self, opt, params: dict, src_opt, src_params: dict) -> None:
+        for k, p in params.items():
+            st = src_opt.state.get(src_params[k])
+            if st:
+                opt.state[p] = {'step': st['step'].clone(), 'exp_avg': st['exp_avg'].to(self.dtype).clone(),
+                                'exp_avg_sq': st['exp_avg_sq'].to(self.dtype).clone()}
 
     # ---- sac_base.py:745-764
     @torch.no_grad()

@@ -380,6 +380,20 @@ class SacRepCuda(SacCuda):
             out['y_td'] = self.wk['y_td'].cpu().numpy()
         return out
 
+    def sync_from_oracle(self, oracle, what=('q', 'qt', 'pi', 'alpha', 'rep')) -> None:
+        """SacCuda.sync_from_oracle + the representation's parameters, target copy and Adam state."""
+        super().sync_from_oracle(oracle, tuple(w for w in what if w != 'rep'))
+        if 'rep' in what:
+            flat = lambda d: lowering.gru_flat_from_state_dict(self.gshape, {k: v.detach().float() for k, v in d.items()})
+            self.rep_p.copy_(flat(oracle.rep))
+            self.rep_t.copy_(flat(oracle.rep_target))
+            st = oracle.opt_rep.state
+            mom = lambda key: {k: (st[p][key].detach() if p in st else torch.zeros_like(p)) for k, p in oracle.rep.items()}
+            self.rep_m.copy_(flat(mom('exp_avg')))
+            self.rep_v.copy_(flat(mom('exp_avg_sq')))
+            steps = {int(float(st[p]['step'])) for p in oracle.rep.values() if p in st}
+            self.counters[4] = steps.pop() if steps else 0
+
     def snapshot(self) -> dict:
         d = super().snapshot()
         for k, t in lowering.gru_state_dict_from_flat(self.gshape, self.rep_p).items():

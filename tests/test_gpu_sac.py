@@ -23,7 +23,8 @@ from tests.helpers import (golden_batch, golden_params, load_golden, rel_err, sa
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-CASES = ['sac_c2.npz', 'sac_c3.npz', 'sac_odd.npz', 'sac_nois.npz']
+# the last two are BASELINE configs[1] / configs[2] at their full batch sizes (256 / 1024), minted from the reference
+CASES = ['sac_c2.npz', 'sac_c3.npz', 'sac_odd.npz', 'sac_nois.npz', 'sac_c2_b256.npz', 'sac_c3_b1024.npz']
 DIAG = Path(__file__).resolve().parent.parent / 'gpurun_out'
 
 

@@ -29,12 +29,13 @@ def test_padding_matches_reference(name):
     check_padding(load_golden(name))
 
 
-@pytest.mark.parametrize('name', ['sac_c2.npz', 'sac_c3.npz', 'sac_odd.npz', 'sac_nois.npz'])
+@pytest.mark.parametrize('name', ['sac_c2.npz', 'sac_c3.npz', 'sac_odd.npz', 'sac_nois.npz',
+                                  'sac_c2_b256.npz', 'sac_c3_b1024.npz'])  # the last two: BASELINE's full shapes
 def test_sac_oracle_matches_reference(name):
     check_sac_steps(load_golden(name))
 
 
-@pytest.mark.parametrize('name', ['sac_rnn.npz', 'sac_rnn_b0.npz'])
+@pytest.mark.parametrize('name', ['sac_rnn.npz', 'sac_rnn_b0.npz', 'sac_rnn_c4.npz'])  # c4: B=256, b=40, n=5 (L=46)
 def test_recurrent_sac_oracle_matches_reference(name):
     """The GRU-representation flow (envs/test/nn_rnn.py, seq_encoder=RNN) against the real reference:
     BPTT gradients of the representation, re-encoded states, next hidden states, td error on the
