@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "mlp_tile.cuh"
+#include "tc_engine.cuh"
 
 namespace asac {
 
@@ -35,31 +36,6 @@ constexpr int TC_THREADS = 256;  // per tile group: 8 warps, 2 per TMEM lane qua
 constexpr int TC_HEAD_N = 16;    // padded head width (UMMA_N % 16 == 0 for M = 128)
 constexpr int TC_PREFETCH = 2;   // float4 registers per thread holding the next tile's input rows
 
-// ---------------------------------------------------------------- tcgen05 primitives
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, cta_group::1
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
 // 32 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -89,30 +65,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor): start address,
-// leading (K-chunk) byte offset and stride (8-row group) byte offset, all in 16-byte units; version 1.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-// cute::UMMA::InstrDescriptor: D fp32, A/B tf32, both K-major, dense
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// float offset of element (row, k) of an operand with Kp (multiple of 8) columns in the core-matrix layout
-__host__ __device__ __forceinline__ int umma_off(int row, int k, int Kp) {
-    return (row >> 3) * (Kp * 8) + (k >> 2) * 32 + (row & 7) * 4 + (k & 3);
-}
-__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    lo = x - hi;
 }
 
 // ---------------------------------------------------------------- shared-memory plan
@@ -354,6 +306,166 @@ __global__ void __launch_bounds__(TC_THREADS *GROUPS, 1) k_mlp_forward_tc(const 
     if (threadIdx.x < 32) tmem_dealloc(*tmem_slot, TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------- features-on-M engine: standalone forward
+// The layer engine of the update kernels (tc_engine.cuh) on its own: one CTA per `rows_per_cta` rows
+// (a multiple of 8, <= 256), D[64, R] = W . X^T per layer, activations kept IN PLACE as (hi, lo) operand
+// planes, next layer's weights fetched into registers while the tensor pipe and the epilogue work.
+// `variant` 0: epilogue on tcgen05.ld.16x256b fragments (all 32 lanes of a warp carry data);
+// `variant` 1: tcgen05.ld.32x32b (lane = feature; half of each warp idles with M = 64).  Exists so that the
+// fragment mapping is pinned by a test before the fused kernels rely on it.
+struct TcfArgs {
+    const float *params, *x;
+    float *out;
+    NetShape s;
+    int64_t rows;
+    int rows_per_cta, variant;
+};
+
+__global__ void __launch_bounds__(NT, 1) k_mlp_forward_tcf(const TcfArgs a) {
+    extern __shared__ __align__(128) float smem_tc[];
+    const NetShape s = a.s;
+    const int H = s.hidden, d = s.depth, O = s.out_dim;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int RC = a.rows_per_cta;
+    const int64_t r0 = (int64_t)blockIdx.x * RC;
+    const int rows = (int)min((int64_t)RC, a.rows - r0);
+    const int R = round_up(rows, 8);
+    const int K0p = round_up(s.in_dim, 8);
+    const int ka = K0p > H ? K0p : H;
+    // plan: activations (hi, lo) [RC, ka]; two weight slots (hi, lo) [64, ka]; biases; mbarrier + tmem slot
+    float *x_hi = smem_tc, *x_lo = x_hi + RC * ka;
+    float *w_slot[2][2];
+    float *p = x_lo + RC * ka;
+    for (int q = 0; q < 2; ++q)
+        for (int h = 0; h < 2; ++h) { w_slot[q][h] = p; p += TCF_M * ka; }
+    float *bias = p; p += 2 * TCF_M;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(p);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p + 2);
+
+    if (warp == 0) tmem_alloc(tmem_slot, TCF_TMEM_COLS);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < R * K0p; i += NT) {
+        const int r = i / K0p, k = i - r * K0p;
+        const float x = (r < rows && k < s.in_dim) ? __ldg(a.x + (r0 + r) * s.in_dim + k) : 0.f;
+        float hi, lo;
+        split_tf32(x, hi, lo);
+        const int off = umma_off(r, k, K0p);
+        x_hi[off] = hi;
+        x_lo[off] = lo;
+    }
+    tcf_stage_weights(w_slot[0][0], w_slot[0][1], a.params + net_w_off(s, 0), H, s.in_dim, K0p);
+    if (tid < TCF_M) bias[tid] = __ldg(a.params + net_b_off(s, 0) + tid);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    uint32_t phase = 0;
+
+    for (int l = 0; l <= d; ++l) {
+        const int Kp = l == 0 ? K0p : H;
+        const bool head = l == d;
+        const int cur = l & 1, nxt = cur ^ 1;
+        if (tid == 0)
+            tcf_issue(tmem, smem_u32(w_slot[cur][0]), smem_u32(w_slot[cur][1]), smem_u32(x_hi), smem_u32(x_lo), Kp, R, bar);
+        // next layer's weights (and bias): global -> registers while the MMAs run
+        float4 wn[2];
+        float bn = 0.f;
+        const bool more = l < d;
+        const int Nn = (l + 1 == d) ? O : H;  // rows of the next weight matrix (the head is zero padded to 64)
+        if (more) {
+            const float *Wn = a.params + net_w_off(s, l + 1);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = 4 * (tid + NT * q);  // element index in [64, H]
+                const int n = e / H;
+                wn[q] = n < Nn ? __ldg(reinterpret_cast<const float4 *>(Wn + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (tid < TCF_M) bn = tid < Nn ? __ldg(a.params + net_b_off(s, l + 1) + tid) : 0.f;
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+
+        const bool residual = !head && Kp == H;
+        const float *bl = bias + cur * TCF_M;
+        const int sp = warp & 3, cgrp = warp >> 2;
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * sp) << 16);
+        for (int c8 = cgrp; c8 < (R >> 3); c8 += 4) {
+            if (a.variant == 0) {
+                float v[4];
+                tmem_ld_16x256b(lane_base + (uint32_t)(c8 * 8), v);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 16 * sp + (lane >> 2) + 8 * h;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int r = c8 * 8 + 2 * (lane & 3) + cc;
+                        const float z = v[2 * h + cc] + bl[j];
+                        if (head) {
+                            if (j < O && r < rows) a.out[(r0 + r) * O + j] = z;
+                        } else {
+                            const int off = umma_off(r, j, H);
+                            float y = gelu_erf(z);
+                            if (residual) y = y + (x_hi[off] + x_lo[off]);
+                            float hi, lo;
+                            split_tf32(y, hi, lo);
+                            x_hi[off] = hi;
+                            x_lo[off] = lo;
+                        }
+                    }
+                }
+            } else {
+                float v[8];
+                tmem_ld_32x32b_x8(lane_base + (uint32_t)(c8 * 8), v);
+                if (lane < 16) {
+                    const int j = 16 * sp + lane;
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {
+                        const int r = c8 * 8 + cc;
+                        const float z = v[cc] + bl[j];
+                        if (head) {
+                            if (j < O && r < rows) a.out[(r0 + r) * O + j] = z;
+                        } else {
+                            const int off = umma_off(r, j, H);
+                            float y = gelu_erf(z);
+                            if (residual) y = y + (x_hi[off] + x_lo[off]);
+                            float hi, lo;
+                            split_tf32(y, hi, lo);
+                            x_hi[off] = hi;
+                            x_lo[off] = lo;
+                        }
+                    }
+                }
+            }
+        }
+        if (more) {  // registers -> the other weight slot (its last reader, layer l - 1, has committed)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = 4 * (tid + NT * q);
+                const int n = e / H, k = e - n * H;
+                const float wv[4] = {wn[q].x, wn[q].y, wn[q].z, wn[q].w};
+                float hi[4], lo[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) split_tf32(wv[t], hi[t], lo[t]);
+                const int off = umma_off(n, k, H);
+                *reinterpret_cast<float4 *>(w_slot[nxt][0] + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(w_slot[nxt][1] + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (tid < TCF_M) bias[nxt * TCF_M + tid] = bn;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_after();
+    if (warp == 0) tmem_dealloc(tmem, TCF_TMEM_COLS);
+}
+
 }  // namespace asac
 
 using namespace asac;
@@ -390,5 +502,32 @@ extern "C" int asac_mlp_forward_tc(const float *params, int in_dim, int hidden, 
     if (groups == 2) k_mlp_forward_tc<2><<<grid, TC_THREADS * 2, bytes, (cudaStream_t)stream>>>(a);
     else k_mlp_forward_tc<1><<<grid, TC_THREADS, bytes, (cudaStream_t)stream>>>(a);
     ASAC_LAUNCHED("k_mlp_forward_tc");
+    return ASAC_OK;
+}
+
+extern "C" int asac_mlp_forward_tcf(const float *params, int in_dim, int hidden, int depth, int out_dim, const float *x,
+                                    int64_t rows, float *out, int rows_per_cta, int variant, void *stream) {
+    ASAC_UNSUPPORTED(hidden != 64, "asac_mlp_forward_tcf: hidden width %d (UMMA_M is the hidden width: 64)", hidden);
+    ASAC_UNSUPPORTED(depth < 1 || depth > ASAC_MAX_DEPTH, "asac_mlp_forward_tcf: depth %d", depth);
+    ASAC_UNSUPPORTED(out_dim < 1 || out_dim > TCF_M, "asac_mlp_forward_tcf: out_dim %d > 64", out_dim);
+    ASAC_REQUIRE(in_dim > 0 && rows > 0, "asac_mlp_forward_tcf: bad sizes");
+    ASAC_REQUIRE(rows_per_cta >= 8 && rows_per_cta <= TCF_MAX_ROWS && rows_per_cta % 8 == 0,
+                 "asac_mlp_forward_tcf: rows_per_cta %d must be a multiple of 8 in [8, 256]", rows_per_cta);
+    TcfArgs a;
+    a.params = params; a.x = x; a.out = out;
+    a.s = NetShape{in_dim, hidden, depth, out_dim};
+    a.rows = rows; a.rows_per_cta = rows_per_cta; a.variant = variant;
+    const int K0p = round_up(in_dim, 8), ka = K0p > hidden ? K0p : hidden;
+    const int bytes = (2 * rows_per_cta * ka + 4 * TCF_M * ka + 2 * TCF_M + 8) * 4 + 128;
+    ASAC_UNSUPPORTED(bytes > 227 * 1024, "asac_mlp_forward_tcf: %d bytes of shared memory", bytes);
+    static thread_local int granted[16];
+    int dev = 0;
+    ASAC_CUDA(cudaGetDevice(&dev));
+    if (dev >= 16 || granted[dev] < bytes) {
+        ASAC_CUDA(cudaFuncSetAttribute(k_mlp_forward_tcf, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (dev < 16) granted[dev] = bytes;
+    }
+    k_mlp_forward_tcf<<<(unsigned)((rows + rows_per_cta - 1) / rows_per_cta), NT, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_mlp_forward_tcf");
     return ASAC_OK;
 }

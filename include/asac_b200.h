@@ -495,6 +495,14 @@ int asac_mlp_forward(const float *params, int in_dim, int hidden, int depth, int
 int asac_mlp_forward_tc(const float *params, int in_dim, int hidden, int depth, int out_dim,
                         const float *x, int64_t rows, float *out, void *stream);
 
+/* The layer engine of the UPDATE kernels on its own (tests, actor side): the same forward with the
+ * tensor-core tile turned around — D[64 features, R rows] = W . X^T, UMMA_M = hidden width (64), UMMA_N =
+ * rows_per_cta (multiple of 8, 8..256) — so that small row tiles (16 rows of a batch-256 step) and long
+ * windows (208 rows of get_l_probs over a burn-in) are both ONE batch of tcgen05.mma per layer.
+ * variant 0 / 1 selects the TMEM fragment shape of the epilogue (16x256b / 32x32b); both must agree. */
+int asac_mlp_forward_tcf(const float *params, int in_dim, int hidden, int depth, int out_dim,
+                         const float *x, int64_t rows, float *out, int rows_per_cta, int variant, void *stream);
+
 /* Actor side: SAC_Base._choose_action for a stock continuous policy (sac_base.py:882-966, branch
  * :943-964): policy forward on `states` [rows, S] (asac_mlp_forward, or the tcgen05 kernel when
  * use_tensor_cores != 0), then c_action = offline_action | tanh(mean) | tanh(Normal.sample()) and

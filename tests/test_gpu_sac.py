@@ -538,6 +538,51 @@ def test_mlp_forward_tcgen05_matches_torch_and_ffma():
     assert e < TOL, e
 
 
+@pytest.mark.parametrize('variant', [0, 1])
+def test_mlp_forward_features_on_m_engine(variant):
+    """asac_mlp_forward_tcf — the update kernels' layer engine (tc_engine.cuh): UMMA_M = hidden width 64,
+    UMMA_N = rows per CTA, transposed accumulator with 16 lanes per TMEM sub-partition — against the torch
+    fp32 forward and the exact-fp32 FFMA kernel, for both epilogue fragment shapes (16x256b / 32x32b), row
+    tiles from 8 to 256, ragged last tiles, K padding (in = 6 -> 8), a residual first layer and a 4-wide head."""
+    from asac_b200 import _lib, lowering
+    from asac_b200._lib import check, ptr
+    from oracle.sac_oracle import init_policy, init_q, policy_param_names, q_forward, trunk_forward
+    import torch.nn.functional as F
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(11)
+    s = torch.cuda.current_stream().cuda_stream
+    worst = {}
+    for (in_dim, depth, rows, rc) in [(8, 3, 16, 16), (8, 3, 1000, 16), (6, 3, 77, 8), (8, 2, 999, 64), (64, 2, 300, 32),
+                                      (5, 1, 4097, 256), (8, 3, 208 * 3 + 1, 208), (8, 3, 5000, 128)]:
+        S, A, H = in_dim - 2, 2, 64
+        p = init_q(S, A, H, depth, gen)
+        for k in p:
+            if k.endswith('bias'):
+                p[k] = torch.randn(p[k].shape, generator=gen) * 0.1
+        x = torch.randn(rows, in_dim, generator=gen)
+        ref = q_forward(p, depth, x[:, :S], x[:, S:]).numpy()
+        flat = lowering.flat_from_state_dict(lowering.NetShape(in_dim, H, depth, 1), p, policy=False).cuda()
+        xc = x.cuda().contiguous()
+        out = torch.full((rows, 1), float('nan'), device='cuda')
+        check(lib.asac_mlp_forward_tcf(ptr(flat), in_dim, H, depth, 1, ptr(xc), rows, ptr(out), rc, variant, s),
+              'mlp_forward_tcf')
+        worst[(in_dim, depth, rows, rc)] = rel_err(out.cpu().numpy(), ref)
+    S, A, H, depth, rows = 6, 2, 64, 3, 777
+    p = init_policy(S, A, H, depth, gen)
+    x = torch.randn(rows, S, generator=gen)
+    h = trunk_forward(p, depth, x)
+    names = policy_param_names(depth)
+    ref = torch.cat([F.linear(h, p[names[-4]], p[names[-3]]), F.linear(h, p[names[-2]], p[names[-1]])], dim=-1).numpy()
+    flat = lowering.flat_from_state_dict(lowering.NetShape(S, H, depth, 2 * A), p, policy=True).cuda()
+    out = torch.full((rows, 2 * A), float('nan'), device='cuda')
+    check(lib.asac_mlp_forward_tcf(ptr(flat), S, H, depth, 2 * A, ptr(x.cuda().contiguous()), rows, ptr(out), 24,
+                                   variant, s), 'mlp_forward_tcf')
+    worst['policy'] = rel_err(out.cpu().numpy(), ref)
+    _dump(f'mlp_tcf_v{variant}', {str(k): v for k, v in worst.items()})
+    print(f'features-on-M engine, variant {variant}: rel err vs torch:', {k: f'{v:.1e}' for k, v in worst.items()})
+    assert all(v < TOL for v in worst.values()), worst
+
+
 def test_fill_normal_statistics():
     from asac_b200 import _lib
     from asac_b200._lib import check, ptr
