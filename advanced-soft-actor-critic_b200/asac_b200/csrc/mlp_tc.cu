@@ -320,6 +320,7 @@ struct TcfArgs {
     NetShape s;
     int64_t rows;
     int rows_per_cta, variant;
+    long long *probe;  // optional: per layer {issue start, MMAs done, epilogue done, layer done} clocks of CTA 0, thread 0
 };
 
 __global__ void __launch_bounds__(NT, 1) k_mlp_forward_tcf(const TcfArgs a) {
@@ -343,7 +344,8 @@ __global__ void __launch_bounds__(NT, 1) k_mlp_forward_tcf(const TcfArgs a) {
     uint64_t *bar = reinterpret_cast<uint64_t *>(p);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(p + 2);
 
-    if (warp == 0) tmem_alloc(tmem_slot, TCF_TMEM_COLS);
+    const uint32_t tmem_cols = tcf_tmem_cols(RC, a.variant == 2);
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -366,12 +368,40 @@ __global__ void __launch_bounds__(NT, 1) k_mlp_forward_tcf(const TcfArgs a) {
     const uint32_t tmem = *tmem_slot;
     uint32_t phase = 0;
 
+    if (a.variant != 1) {  // the fused kernels' own layer routine (tc_engine.cuh); 2: cross terms in their own accumulator
+        TcfCtx cx;
+        cx.x_hi = x_hi; cx.x_lo = x_lo;
+        for (int q = 0; q < 2; ++q)
+            for (int h = 0; h < 2; ++h) cx.w[q][h] = w_slot[q][h];
+        cx.bias = bias; cx.bar = bar; cx.tmem = tmem; cx.phase = 0; cx.slot = 0;
+        cx.cross_cols = a.variant == 2 ? (uint32_t)round_up(RC, 8) : 0u;
+        TcfJob job = tcf_trunk_job(s, a.params, 0);
+        for (int l = 0; l <= d; ++l) {
+            const bool probe = a.probe && blockIdx.x == 0 && tid == 0;
+            if (probe) a.probe[l * 5 + 0] = clock64();
+            if (l < d) {
+                const TcfJob nxt = l + 1 < d ? tcf_trunk_job(s, a.params, l + 1) : tcf_head_job(s, a.params);
+                tcf_layer<false>(cx, job, &nxt, R, job.K == TCF_M, nullptr, 0, 0);
+                job = nxt;
+            } else {
+                tcf_layer<true>(cx, job, nullptr, R, false, a.out + r0 * O, O, rows);
+            }
+            if (probe) a.probe[l * 5 + 4] = clock64();
+        }
+        tc_fence_after();
+        if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+        return;
+    }
     for (int l = 0; l <= d; ++l) {
         const int Kp = l == 0 ? K0p : H;
         const bool head = l == d;
         const int cur = l & 1, nxt = cur ^ 1;
-        if (tid == 0)
-            tcf_issue(tmem, smem_u32(w_slot[cur][0]), smem_u32(w_slot[cur][1]), smem_u32(x_hi), smem_u32(x_lo), Kp, R, bar);
+        const bool probe = a.probe && blockIdx.x == 0 && tid == 0;
+        if (probe) a.probe[l * 5 + 0] = clock64();
+        if (warp == 0)
+            tcf_issue(tmem, tmem, smem_u32(w_slot[cur][0]), smem_u32(w_slot[cur][1]), smem_u32(x_hi), smem_u32(x_lo), Kp, R,
+                      bar);
+        if (probe) a.probe[l * 5 + 1] = clock64();
         // next layer's weights (and bias): global -> registers while the MMAs run
         float4 wn[2];
         float bn = 0.f;
@@ -390,6 +420,7 @@ __global__ void __launch_bounds__(NT, 1) k_mlp_forward_tcf(const TcfArgs a) {
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
+        if (probe) a.probe[l * 5 + 2] = clock64();
 
         const bool residual = !head && Kp == H;
         const float *bl = bias + cur * TCF_M;
@@ -443,6 +474,7 @@ __global__ void __launch_bounds__(NT, 1) k_mlp_forward_tcf(const TcfArgs a) {
                 }
             }
         }
+        if (probe) a.probe[l * 5 + 3] = clock64();
         if (more) {  // registers -> the other weight slot (its last reader, layer l - 1, has committed)
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -461,9 +493,10 @@ __global__ void __launch_bounds__(NT, 1) k_mlp_forward_tcf(const TcfArgs a) {
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
+        if (probe) a.probe[l * 5 + 4] = clock64();
     }
     tc_fence_after();
-    if (warp == 0) tmem_dealloc(tmem, TCF_TMEM_COLS);
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
 }  // namespace asac
@@ -505,8 +538,8 @@ extern "C" int asac_mlp_forward_tc(const float *params, int in_dim, int hidden, 
     return ASAC_OK;
 }
 
-extern "C" int asac_mlp_forward_tcf(const float *params, int in_dim, int hidden, int depth, int out_dim, const float *x,
-                                    int64_t rows, float *out, int rows_per_cta, int variant, void *stream) {
+static int mlp_forward_tcf(const float *params, int in_dim, int hidden, int depth, int out_dim, const float *x,
+                           int64_t rows, float *out, int rows_per_cta, int variant, long long *probe, void *stream) {
     ASAC_UNSUPPORTED(hidden != 64, "asac_mlp_forward_tcf: hidden width %d (UMMA_M is the hidden width: 64)", hidden);
     ASAC_UNSUPPORTED(depth < 1 || depth > ASAC_MAX_DEPTH, "asac_mlp_forward_tcf: depth %d", depth);
     ASAC_UNSUPPORTED(out_dim < 1 || out_dim > TCF_M, "asac_mlp_forward_tcf: out_dim %d > 64", out_dim);
@@ -516,7 +549,7 @@ extern "C" int asac_mlp_forward_tcf(const float *params, int in_dim, int hidden,
     TcfArgs a;
     a.params = params; a.x = x; a.out = out;
     a.s = NetShape{in_dim, hidden, depth, out_dim};
-    a.rows = rows; a.rows_per_cta = rows_per_cta; a.variant = variant;
+    a.rows = rows; a.rows_per_cta = rows_per_cta; a.variant = variant; a.probe = probe;
     const int K0p = round_up(in_dim, 8), ka = K0p > hidden ? K0p : hidden;
     const int bytes = (2 * rows_per_cta * ka + 4 * TCF_M * ka + 2 * TCF_M + 8) * 4 + 128;
     ASAC_UNSUPPORTED(bytes > 227 * 1024, "asac_mlp_forward_tcf: %d bytes of shared memory", bytes);
@@ -530,4 +563,16 @@ extern "C" int asac_mlp_forward_tcf(const float *params, int in_dim, int hidden,
     k_mlp_forward_tcf<<<(unsigned)((rows + rows_per_cta - 1) / rows_per_cta), NT, bytes, (cudaStream_t)stream>>>(a);
     ASAC_LAUNCHED("k_mlp_forward_tcf");
     return ASAC_OK;
+}
+
+extern "C" int asac_mlp_forward_tcf(const float *params, int in_dim, int hidden, int depth, int out_dim, const float *x,
+                                    int64_t rows, float *out, int rows_per_cta, int variant, void *stream) {
+    return mlp_forward_tcf(params, in_dim, hidden, depth, out_dim, x, rows, out, rows_per_cta, variant, nullptr, stream);
+}
+
+// debug: the same launch with per-layer phase clocks of CTA 0 written to probe[(depth + 1) * 5] (device memory)
+extern "C" int asac_mlp_forward_tcf_probe(const float *params, int in_dim, int hidden, int depth, int out_dim,
+                                          const float *x, int64_t rows, float *out, int rows_per_cta, int variant,
+                                          long long *probe, void *stream) {
+    return mlp_forward_tcf(params, in_dim, hidden, depth, out_dim, x, rows, out, rows_per_cta, variant, probe, stream);
 }

@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "mlp_tile.cuh"
+#include "tc_engine.cuh"
 #include "tree_apply.cuh"
 
 namespace cg = cooperative_groups;
@@ -505,6 +506,8 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     }
     ASAC_PHASE(0, 31);
 }
+
+#include "sac_tc.cuh"  // the same passes on the tcgen05 layer engine (hidden width 64)
 
 // ------------------------------------------------------------------------------------ critic
 // grid (n_tiles, E): forward of Q_i on (s_b, a_b), clipped double loss, backward
@@ -1420,13 +1423,14 @@ template <typename K>
 static int set_smem(K kernel, int bytes, const char *name) {
     ASAC_UNSUPPORTED(bytes > kSmemLimit, "%s needs %d bytes of shared memory (> %d)", name, bytes, kSmemLimit);
     if (bytes <= 48 * 1024) return ASAC_OK;
-    static thread_local int granted[4][16];  // [kernel slot][device]
-    static thread_local const void *slots[4] = {nullptr, nullptr, nullptr, nullptr};
+    constexpr int KSLOTS = 12;
+    static thread_local int granted[KSLOTS][16];  // [kernel slot][device]
+    static thread_local const void *slots[KSLOTS] = {};
     int dev = 0;
     ASAC_CUDA(cudaGetDevice(&dev));
     int slot = 0;
-    while (slot < 4 && slots[slot] != nullptr && slots[slot] != (const void *)kernel) ++slot;
-    if (slot == 4 || dev >= 16) {
+    while (slot < KSLOTS && slots[slot] != nullptr && slots[slot] != (const void *)kernel) ++slot;
+    if (slot == KSLOTS || dev >= 16) {
         ASAC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         return ASAC_OK;
     }
@@ -1450,8 +1454,38 @@ extern "C" int asac_sac_polyak(const AsacSacConfig *cfg, const AsacSacParams *pr
     return ASAC_OK;
 }
 
+// The tcgen05 layer engine serves the stock width (UMMA_M = hidden = 64) when every row batch of a tile fits
+// one MMA (<= 256 rows) and the first layers' K fits the 64-wide operand planes — and when the tile holds more rows
+// than ONE FFMA pass (PASS_ROWS): a 16-row tile is latency-bound either way and the FFMA pass is the shorter chain
+// (config 2, measured: 32.8 vs 34.8 us for the post pass), from two passes on the tensor-core layer wins
+// (config 3: 36.9 -> 26.7 us, config 4: 61.5 -> 49.1 us).  ASAC_TC=0 keeps the FFMA kernels, ASAC_TC=2 forces
+// the tensor-core engine for every tile size it supports.
+static int tc_mode() {
+    static const int mode = [] {
+        const char *e = getenv("ASAC_TC");
+        return e ? atoi(e) : 1;
+    }();
+    return mode;
+}
+static bool tc_enabled() { return tc_mode() != 0; }
+static bool value_pass_on_tc(const AsacSacConfig &c, int tile_batch, int mode) {
+    if (!tc_enabled() || c.q_hidden != TCF_M || c.pi_hidden != TCF_M || c.state_size + c.action_size > TCF_M) return false;
+    const ValueTcPlan p = value_tc_plan(c, tile_batch, mode);
+    if (p.RA <= PASS_ROWS && tc_mode() < 2) return false;
+    return p.RA <= TCF_MAX_ROWS && p.total * 4 <= 227 * 1024;
+}
+
 static int launch_value_pass(SacArgs &a, int mode, void *stream) {
     a.mode = mode;
+    if (value_pass_on_tc(a.cfg, a.tile_batch, mode)) {
+        const int bytes = value_tc_plan(a.cfg, a.tile_batch, mode).total * 4;
+        int rc = set_smem(k_value_pass_tc, bytes, "k_value_pass_tc");
+        if (rc != ASAC_OK) return rc;
+        ASAC_CUDA(launch_ex(k_value_pass_tc, dim3(a.wrk.n_tiles, a.cfg.ensemble), dim3(NT), (size_t)bytes,
+                            (cudaStream_t)stream, a.cfg.ensemble, true, a));
+        ASAC_LAUNCHED("k_value_pass_tc");
+        return ASAC_OK;
+    }
     const int bytes = value_plan(a.cfg, a.tile_batch, mode).total * 4;
     int rc = set_smem(k_value_pass, bytes, "k_value_pass");
     if (rc != ASAC_OK) return rc;

@@ -502,6 +502,11 @@ int asac_mlp_forward_tc(const float *params, int in_dim, int hidden, int depth, 
  * variant 0 / 1 selects the TMEM fragment shape of the epilogue (16x256b / 32x32b); both must agree. */
 int asac_mlp_forward_tcf(const float *params, int in_dim, int hidden, int depth, int out_dim,
                          const float *x, int64_t rows, float *out, int rows_per_cta, int variant, void *stream);
+/* debug: same launch; probe[(depth + 1) * 5] (device int64) receives, per layer, CTA 0's clocks at
+ * {issue start, MMAs issued, MMAs complete, epilogue done, layer done} */
+int asac_mlp_forward_tcf_probe(const float *params, int in_dim, int hidden, int depth, int out_dim,
+                               const float *x, int64_t rows, float *out, int rows_per_cta, int variant,
+                               long long *probe, void *stream);
 
 /* Actor side: SAC_Base._choose_action for a stock continuous policy (sac_base.py:882-966, branch
  * :943-964): policy forward on `states` [rows, S] (asac_mlp_forward, or the tcgen05 kernel when
