@@ -192,7 +192,6 @@ class SAC_Base:
         unsupported = {
             'discrete action branches (d_action_sizes)': bool(d_action_sizes),
             'c_action_size == 0': not c_action_size,
-            'seq_encoder=ATTN': seq_encoder is not None and getattr(seq_encoder, 'name', str(seq_encoder)) != 'RNN',
             'siamese': siamese is not None,
             'use_prediction': use_prediction,
             'curiosity': curiosity is not None,
@@ -246,6 +245,8 @@ class SAC_Base:
             # replicated weights: every rank starts from rank 0's networks and optimizer state
             adist.broadcast_([self._q_flat, self._qt_flat, self._pi_flat, self._log_alpha_buf, self._q_m, self._q_v,
                               self._pi_m, self._pi_v, self._alpha_m, self._alpha_v, self._counters])
+            if self._bridge is not None:
+                adist.broadcast_([self._rep_flat, self._rept_flat, self._rep_m, self._rep_v])
             if self._gru is not None:
                 if self._peer_table is None or not (self.use_priority and self.batch_size <= 1024):
                     raise NotImplementedError('data-parallel learner with a trained representation needs the '
@@ -275,12 +276,31 @@ class SAC_Base:
         f32 = dict(dtype=torch.float32, device=dev)
         # counters: global_step, Adam steps of critics / policy / alpha / representation
         self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
-        lowered = lowering.analyze_rep(self.model_rep, self.obs_shapes, A)
+        self._is_attn = self.seq_encoder is not None and getattr(self.seq_encoder, 'name', str(self.seq_encoder)) == 'ATTN'
         self.optimizer_rep = None
         self._gru = None
-        self._attn = None
+        self._bridge = None
         self._vector_obs = [(name, shape) for name, shape in zip(self.obs_names, self.obs_shapes) if len(shape) == 1]
-        if lowered is None:
+        try:
+            if self._is_attn:
+                raise lowering.NotStockNetwork('attention representation')
+            lowered = lowering.analyze_rep(self.model_rep, self.obs_shapes, A)
+            if lowered is not None and os.environ.get('ASAC_REP_BRIDGE', '1') == '2':  # tests: stock GRU through torch
+                raise lowering.NotStockNetwork('ASAC_REP_BRIDGE=2')
+        except lowering.NotStockNetwork as e:
+            if os.environ.get('ASAC_REP_BRIDGE', '1') == '0':
+                raise
+            # any other ModelRep: the plugin's torch modules produce the states, the kernels do the rest
+            from .rep_bridge import TorchRepBridge
+            self._logger.info(f'representation runs as the plugin\'s torch module ({e})')
+            lowered = None
+            self._bridge = TorchRepBridge(self.model_rep, self.model_target_rep, self._is_attn, self.burn_in_step, dev)
+        if self._bridge is not None:
+            br = self._bridge
+            self.state_size, self.seq_hidden_state_shape = br.probe(self.obs_shapes, A)
+            self._rep_flat, self._rept_flat, self._rep_m, self._rep_v = br.flat, br.flat_target, br.m, br.v
+            self.optimizer_rep = _FlatAdam(br.params, br.flat, br.m, br.v, self._counters, 4, self.learning_rate)
+        elif lowered is None:
             if self.seq_encoder is not None:
                 raise NotImplementedError('seq_encoder is set but ModelRep is ModelSimpleRep')
             self.state_size = sum(shape[0] for _, shape in self._vector_obs)
@@ -362,7 +382,7 @@ class SAC_Base:
         cfg.use_auto_alpha = int(self.use_auto_alpha)
         cfg.update_target_per_step = int(self.update_target_per_step)
         cfg.bn_stride = cfg.seq_len
-        cfg.rep_kind = 0 if self._gru is None else 1
+        cfg.rep_kind = 0 if (self._gru is None and self._bridge is None) else 1
         cfg.rep_param_stride = 0 if self._gru is None else self._gru.stride
         cfg.tau, cfg.one_minus_tau = float(self.tau), float(np.float32(1. - self.tau))
         cfg.gamma, cfg.v_rho, cfg.v_c = float(self.gamma), float(self.v_rho), float(self.v_c)
@@ -453,6 +473,8 @@ class SAC_Base:
         if not self.use_replay_buffer:  # on-policy: every window once, in shuffled batches (sac_base.py:642-646)
             if self._world > 1:
                 raise NotImplementedError('data-parallel learner without a replay buffer')
+            if self._bridge is not None:
+                raise NotImplementedError('on-policy training (use_replay_buffer=False) with a torch-module representation')
             from .batch_buffer import BatchBuffer
             self.batch_buffer = BatchBuffer(burn_in_step=self.burn_in_step, n_step=self.n_step,
                                             padding_action=self._np_padding_action, batch_size=self.batch_size,
@@ -486,7 +508,7 @@ class SAC_Base:
             'pi_probs': torch.zeros(B, L - 1, A, **f32), 'post_parts': torch.zeros(B, 2 + E, **f32), 'y_td': torch.zeros(B, **f32),
             'td_error': torch.zeros(B, **f32),
         }
-        if self._gru is not None:
+        if self._gru is not None or self._bridge is not None:
             wk['grad_state'] = torch.zeros(E, B, S, **f32)
         work = _lib.AsacSacWork()
         work.n_tiles = T
@@ -507,7 +529,8 @@ class SAC_Base:
         # The sampled batch lives in a "batch set" (sample outputs, gathered windows, the C structs pointing
         # at them).  Two sets: while the networks train on one, the NEXT step's sample + gather fill the
         # other on a parallel branch (ASAC_SAMPLE_AHEAD=0: one set, sample and gather on the critical path).
-        self._sample_ahead = self.use_replay_buffer and os.environ.get('ASAC_SAMPLE_AHEAD', '1') != '0'
+        self._sample_ahead = self.use_replay_buffer and os.environ.get('ASAC_SAMPLE_AHEAD', '1') != '0' \
+            and self._bridge is None  # (the bridged step runs eagerly, in program order)
         self._sets = [self._make_batch_set() for _ in range(2 if self._sample_ahead else 1)]
         self._cur, self._primed = 0, False
         # With sampling one step ahead the tree update of step N is only needed by the sample of step N + 2:
@@ -596,6 +619,12 @@ class SAC_Base:
             for k, t in self._rw.items():
                 setattr(rep, k, ptr(t))
             rep.rep_tiles = B
+            batch.states_post, batch.target_states = ptr(bt['states_post']), ptr(bt['target_states'])
+        if self._bridge is not None:
+            # observation windows are allocated with the stored dtypes once the replay's columns exist (_gather_specs)
+            hid = int(np.prod(self.seq_hidden_state_shape))
+            bt['hidden'] = torch.zeros(B, L, max(hid, 0), **f32)
+            bt['states_post'], bt['target_states'] = torch.zeros(B, L, S, **f32), torch.zeros(B, L, S, **f32)
             batch.states_post, batch.target_states = ptr(bt['states_post']), ptr(bt['target_states'])
         return {'bt': bt, 'smp': smp, 'batch': batch, 'rep': rep, 'specs': None, 'noise': noise}
 
@@ -756,7 +785,7 @@ class SAC_Base:
         opt-in because the probability amplifies the 1.5e-6 error of the pre-activations by |x - mu| / sigma^2.
         ``eps`` ([batch, A] N(0,1) draws) replaces the on-device Philox draws (tests).
         Host traffic: one pinned staging block in, one out (``_actor_io``)."""
-        if self.action_noise is not None or self._attn is not None:
+        if self.action_noise is not None or self._bridge is not None:
             return self._choose_action_torch(obs_list, pre_action, pre_seq_hidden_state, offline_action,
                                              disable_sample)
         with torch.cuda.device(self.device):
@@ -812,7 +841,7 @@ class SAC_Base:
         attention representation with ONE query step (``is_prev_hidden_state=False``); the policy kernels
         act on the resulting state.  -> (action [batch, A], prob [batch, A], attn_state [batch, *shape]).
         The representation runs as the plugin's torch module on the parameters it shares with the learner."""
-        if self._attn is None:
+        if not self._is_attn:
             raise NotImplementedError('choose_attn_action needs seq_encoder=SEQ_ENCODER.ATTN (sac_base.py:1022)')
         with torch.cuda.device(self.device):
             b = self.burn_in_step
@@ -845,7 +874,7 @@ class SAC_Base:
         TensorBoard (needs matplotlib); in every case the pending-summary flag is cleared."""
         if not force and (self.summary_writer is None or not self.summary_available):
             return
-        if self.summary_writer is not None and self._attn is not None:
+        if self.summary_writer is not None and self._is_attn:
             try:
                 from matplotlib.figure import Figure
                 with torch.no_grad(), torch.cuda.device(self.device):
@@ -874,7 +903,7 @@ class SAC_Base:
                 obs[i] = o.float() / 255.
             elif o.dtype == torch.bool:
                 obs[i] = o.float()
-        if self._gru is not None:
+        if self._gru is not None or self._bridge is not None:
             to_dev = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
             with torch.backends.cudnn.flags(allow_tf32=False):  # cuDNN RNNs default to TF32
                 state, hidden = self.model_rep([o.unsqueeze(1) for o in obs], to_dev(pre_action).unsqueeze(1),
@@ -942,7 +971,21 @@ class SAC_Base:
             specs.append(('pre_seq_hidden_state', bt['hidden'], 4 * g.layers * g.hidden, 0, _lib.ROLE_HIDDEN))
             if rb._row_bytes('pre_seq_hidden_state') != 4 * g.layers * g.hidden:
                 raise ValueError('stored pre_seq_hidden_state rows do not have the shape (layers, hidden)')
-        for name, shape in ([] if self._gru is not None else self._vector_obs):
+        if self._bridge is not None:  # every observation window as stored + the stored hidden states of the window
+            bt['obs_list'] = []
+            for name, shape in zip(self.obs_names, self.obs_shapes):
+                col = rb._columns[f'obs_{name}']
+                if tuple(col.shape[1:]) != tuple(shape):
+                    raise ValueError(f'stored obs_{name} rows have shape {tuple(col.shape[1:])}, expected {tuple(shape)}')
+                win = torch.zeros(self.batch_size, self._cfg.seq_len, *shape, dtype=col.dtype, device=self.device)
+                bt['obs_list'].append(win)
+                specs.append((f'obs_{name}', win, rb._row_bytes(f'obs_{name}'), 0, _lib.ROLE_COPY))
+            hb = rb._row_bytes('pre_seq_hidden_state')
+            if hb != 4 * bt['hidden'].shape[-1]:
+                raise ValueError('stored pre_seq_hidden_state rows do not have seq_hidden_state_shape')
+            if hb:
+                specs.append(('pre_seq_hidden_state', bt['hidden'], hb, 0, _lib.ROLE_HIDDEN))
+        for name, shape in ([] if (self._gru is not None or self._bridge is not None) else self._vector_obs):
             col = rb._columns[f'obs_{name}']
             if col.dtype != torch.float32:
                 raise NotImplementedError(f'vector observation {name} is stored as {col.dtype}; float32 expected')
@@ -987,6 +1030,8 @@ class SAC_Base:
 
     def _enqueue_step(self) -> None:
         """One train() on the device, eagerly: picks the batch sets, primes the first batch when needed."""
+        if self._bridge is not None:
+            return self._enqueue_step_bridge()
         cur = (1 - self._cur) if (self._sample_ahead and self._primed) else self._cur
         if self._sample_ahead and not self._primed:
             self._enqueue_sample(self._sets[cur])
@@ -1092,6 +1137,86 @@ class SAC_Base:
         if self.use_n_step_is or rep_c is not None:
             main.wait_stream(side)
 
+    def _enqueue_step_bridge(self) -> None:
+        """One train() with a representation that runs as the plugin's torch module (rep_bridge.py): the
+        kernels of the staged step with the three get_l_states passes, the representation's backward and its
+        Adam step in between, in the reference's order (sac_base.py:2057-2116, 2556-2605).  Eager, one stream."""
+        rb, st = self.replay_buffer, self._sets[self._cur]
+        bt, smp = st['bt'], st['smp']
+        b, L = self.burn_in_step, self._cfg.seq_len
+        self._enqueue_sample(st)
+        self._enqueue_noise(st, 0)
+        hidden_post = self._bridge_step_networks(st)
+        if self.use_priority:
+            self._enqueue_tree_update(st)
+        # write-backs (sac_base.py:2586-2605)
+        if int(np.prod(self.seq_hidden_state_shape)) != 0:
+            hp = hidden_post.reshape(self.batch_size, L, -1).contiguous()
+            rb.write_back(smp['ids'], 'pre_seq_hidden_state', hp, 1 - b, bt['padding_masks'], n_rows=L - 1)
+        if self.use_n_step_is:
+            rb.write_back(smp['ids'], 'mu_prob', self._wk['pi_probs'], -b, bt['padding_masks'])
+
+    def _bridge_step_networks(self, st: dict) -> torch.Tensor:
+        """_train + get_l_probs + _get_td_error on the batch held by set `st` (sac_base.py:2057-2116, 2556-2583);
+        -> next_bnx_seq_hidden_states."""
+        lib, br = self._lib, self._bridge
+        bt, wk = st['bt'], self._wk
+        cfg, prm, batch, work = C.byref(self._cfg), C.byref(self._prm), C.byref(st['batch']), C.byref(self._work)
+        stream = _lib.current_stream()
+        scale = 1.0 / self._world
+        b, L = self.burn_in_step, self._cfg.seq_len
+        check(lib.asac_sac_polyak(cfg, prm, -1.0, stream), 'sac_polyak')
+        check(lib.asac_flat_polyak(ptr(br.flat_target), ptr(br.flat), br.count, ptr(self._counters),
+                                   int(self.update_target_per_step), self._cfg.tau, self._cfg.one_minus_tau, 0,
+                                   stream), 'flat_polyak')
+        # get_bnx_data (sac_base.py:1090-1116) from the b + n stored rows
+        bn_index = bt['index'][:, :L - 1]
+        index = torch.cat([bn_index, bn_index[:, -1:] + (bn_index[:, -1:] != -1)], dim=1)
+        bn_pad = bt['padding_masks'][:, :L - 1].bool()
+        padding = torch.cat([bn_pad, bn_pad[:, -1:]], dim=1)
+        actions = bt['actions'][:, :L - 1]
+        pre_action = torch.cat([torch.zeros_like(actions[:, :1]), actions], dim=1)
+        obs_list = self._process_torch_obs_list(list(bt['obs_list']))
+        hidden = bt['hidden'].view(self.batch_size, L, *self.seq_hidden_state_shape)
+        states, _ = br.l_states(index, padding, obs_list, pre_action, hidden, target=False)
+        with torch.no_grad():
+            target_states, _ = br.l_states(index, padding, obs_list, pre_action, hidden, target=True)
+            bt['states'].copy_(states)
+            bt['target_states'].copy_(target_states)
+        check(lib.asac_sac_target_y(cfg, prm, batch, work, stream), 'target_y')
+        check(lib.asac_sac_q_backward(cfg, prm, batch, work, stream), 'q_backward')
+        check(lib.asac_sac_reduce_grads(cfg, work, 0, stream), 'reduce_grads')
+        adist.all_reduce_sum_(wk['grad_q'])
+        check(lib.asac_sac_adam(cfg, prm, work, 0, scale, stream), 'adam')
+        # the representation's share of loss.backward() and optimizer_rep.step() (sac_base.py:1573-1601)
+        br.backward(states, wk['grad_state'])
+        adist.all_reduce_sum_(br.grad)
+        if self._world > 1:
+            br.grad.mul_(scale)
+        check(lib.asac_flat_reduce_adam(ptr(br.flat), ptr(br.m), ptr(br.v), ptr(br.grad), 1, br.stride, br.count,
+                                        ptr(br.grad_out), ptr(self._counters[4:]), float(self.learning_rate), stream),
+              'flat_reduce_adam')
+        self._counters[4] += 1
+        with torch.no_grad():  # get_l_states with the new weights (sac_base.py:2099-2105)
+            states_post, hidden_post = br.l_states(index, padding, obs_list, pre_action, hidden, target=False)
+            bt['states_post'].copy_(states_post)
+        check(lib.asac_sac_policy_backward(cfg, prm, batch, work, stream), 'policy_backward')
+        check(lib.asac_sac_reduce_grads(cfg, work, 1, stream), 'reduce_grads')
+        adist.all_reduce_sum_(wk['grad_pi'])
+        check(lib.asac_sac_adam(cfg, prm, work, 1, scale, stream), 'adam')
+        need_post = self.use_auto_alpha or self.use_n_step_is or self.use_priority
+        if need_post:
+            check(lib.asac_sac_post(cfg, prm, batch, work, stream), 'post')
+        if self.use_auto_alpha:
+            check(lib.asac_sac_reduce_grads(cfg, work, 2, stream), 'reduce_grads')
+            adist.all_reduce_sum_(wk['grad_alpha'])
+            check(lib.asac_sac_adam(cfg, prm, work, 2, scale, stream), 'adam')
+        if need_post:
+            check(lib.asac_sac_td_error(cfg, prm, work, stream), 'td_error')
+        check(lib.asac_sac_advance_step(prm, stream), 'advance_step')
+        self._last_bridge = {'states': states.detach(), 'hidden_post': hidden_post}
+        return hidden_post
+
     def _enqueue_sac_step_data_parallel(self, stream, batch_struct) -> None:
         """asac_sac_step with a SUM all-reduce of each reduced gradient buffer between the backward
         pass and its Adam kernel (grad_scale = 1/world): the only collective of the step."""
@@ -1180,7 +1305,8 @@ class SAC_Base:
                 self._graphs, self._graph_columns_key, self._primed = [None, None], key, False
                 self._pending = False  # the storage was re-allocated: a deferred update has nothing to apply to
                 self._enqueue_step()  # eager warm-up (also sets the kernels' shared-memory attributes)
-            elif not self.use_cuda_graph or (self._world > 1 and not self._graph_collectives):
+            elif self._bridge is not None or not self.use_cuda_graph or \
+                    (self._world > 1 and not self._graph_collectives):
                 self._enqueue_step()
             else:  # one captured graph per batch set (they alternate)
                 cur = (1 - self._cur) if self._sample_ahead else self._cur

@@ -562,6 +562,174 @@ def gen_sac_rnn_case(name, *, So, A, E, B, b, n, steps, seed, use_priority=True,
     print('wrote', f'sac_{name}.npz', sum(v.nbytes for v in out.values()), 'bytes raw')
 
 
+def gen_sac_plugin_rep_case(name, *, nn_rel, obs_names, obs_shapes, seq_encoder, A, E, B, b, n, steps, seed,
+                            use_priority=True, **hyper):
+    """``_train`` + tail of ``train`` with ANY representation plugin of the reference (``nn_rel``): convolutional
+    encoders, the packed GRU, the episode attention stack (``seq_encoder`` 'RNN' / 'ATTN' / None).  Same
+    recording as ``gen_sac_rnn_case``; the representation's parameters are stored under their state_dict keys."""
+    SAC_Base, _, _ = import_reference()
+    from algorithm.utils.enums import SEQ_ENCODER
+    nn = load_reference_nn(nn_rel)
+    torch.manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    enc = None if seq_encoder is None else SEQ_ENCODER[seq_encoder]
+    with _NoThread():
+        sac = SAC_Base(obs_names=list(obs_names), obs_shapes=[tuple(s) for s in obs_shapes], d_action_sizes=[],
+                       c_action_size=A, model_abs_dir=None, nn=nn, device='cpu', seed=seed, batch_size=B,
+                       burn_in_step=b, n_step=n, ensemble_q_num=E, ensemble_q_sample=E, seq_encoder=enc,
+                       use_priority=use_priority, replay_config={'capacity': 1024}, **hyper)
+    hshape = tuple(int(x) for x in sac.seq_hidden_state_shape)
+    S = sac.state_size
+    with torch.no_grad():
+        for net in sac.model_target_q_list + [sac.model_target_rep]:
+            for p in net.parameters():
+                p.add_(torch.randn_like(p) * 0.02)
+        for net in sac.model_q_list + [sac.model_policy]:
+            for pn, p in net.named_parameters():
+                if pn.endswith('bias'):
+                    p.add_(torch.randn_like(p) * 0.05)
+    L = b + n + 1
+    q_depth = len([k for k in sac.model_q_list[0].state_dict() if k.endswith('linear.weight')])
+    q_hidden = sac.model_q_list[0].state_dict()['c_dense.dense.0.linear.weight'].shape[0]
+    out = {'meta': np.array([S, A, E, q_hidden, q_depth, B, b, n, steps, int(use_priority)], dtype=np.int64),
+           'hidden_shape': np.array(hshape, dtype=np.int64),
+           'seq_encoder': np.array(seq_encoder or ''), 'nn_rel': np.array(nn_rel),
+           'obs_names': np.array(list(obs_names))}
+    for i, shape in enumerate(obs_shapes):
+        out[f'obs_shape{i}'] = np.array(shape, dtype=np.int64)
+    hp = dict(tau=sac.tau, update_target_per_step=sac.update_target_per_step, learning_rate=sac.learning_rate,
+              gamma=sac.gamma, v_lambda=sac.v_lambda, v_rho=float(sac.v_rho), v_c=float(sac.v_c),
+              clip_epsilon=sac.clip_epsilon, use_n_step_is=float(sac.use_n_step_is),
+              target_c_alpha=sac.target_c_alpha, init_log_alpha=float(sac.log_c_alpha),
+              use_auto_alpha=float(sac.use_auto_alpha))
+    for k, v in hp.items():
+        out[f'hp.{k}'] = np.float64(v)
+
+    def dump_params(prefix):
+        for i in range(E):
+            for k, t in sac.model_q_list[i].state_dict().items():
+                out[f'{prefix}.q{i}.{k}'] = t.detach().numpy().copy()
+            for k, t in sac.model_target_q_list[i].state_dict().items():
+                out[f'{prefix}.qt{i}.{k}'] = t.detach().numpy().copy()
+        for k, t in sac.model_policy.state_dict().items():
+            out[f'{prefix}.pi.{k}'] = t.detach().numpy().copy()
+        for k, t in sac.model_rep.state_dict().items():
+            out[f'{prefix}.rep.{k}'] = t.detach().numpy().copy()
+        for k, t in sac.model_target_rep.state_dict().items():
+            out[f'{prefix}.rept.{k}'] = t.detach().numpy().copy()
+        out[f'{prefix}.log_c_alpha'] = sac.log_c_alpha.detach().numpy().copy()
+
+    dump_params('init')
+    ys = []
+    orig_get_y = sac._get_y
+
+    def tap_get_y(**kw):
+        d_y, c_y = orig_get_y(**kw)
+        ys.append(c_y.clone())
+        return d_y, c_y
+
+    sac._get_y = tap_get_y
+    rep_grads = {}
+    orig_rep_step = sac.optimizer_rep.step
+
+    def tap_rep_step(*a, **k):  # gradients as the representation's Adam sees them
+        for kk, p in sac.model_rep.named_parameters():
+            rep_grads[kk] = (torch.zeros_like(p) if p.grad is None else p.grad).detach().numpy().copy()
+        return orig_rep_step(*a, **k)
+
+    sac.optimizer_rep.step = tap_rep_step
+
+    for s in range(steps):
+        obses = [torch.from_numpy(rng.randn(B, L, *shape).astype(np.float32)) for shape in obs_shapes]
+        actions = torch.from_numpy((rng.rand(B, L - 1, A) * 1.9 - 0.95).astype(np.float32))
+        rewards = torch.from_numpy(rng.randn(B, L - 1).astype(np.float32))
+        dones = torch.from_numpy(rng.rand(B, L - 1) < 0.1)
+        mu_probs = torch.from_numpy((rng.rand(B, L - 1, A) * 1.5 + 0.01).astype(np.float32))
+        hidden = torch.from_numpy((rng.randn(B, L, *hshape) * 0.5).astype(np.float32))
+        pad = np.zeros((B, L - 1), dtype=bool)
+        last = np.zeros((B, L - 1), dtype=bool)
+        for r in range(B):
+            if L - 1 > 1 and rng.rand() < 0.4:
+                cut = rng.randint(b + 1, L)
+                if cut < L - 1:
+                    pad[r, cut:] = True
+                last[r, cut - 1] = rng.rand() < 0.7
+            if b > 0 and rng.rand() < 0.3:
+                pad[r, :rng.randint(1, b + 1)] = True
+        tpad = torch.from_numpy(pad)
+        mu_probs[tpad] = 1.
+        rewards[tpad] = 0.
+        dones[tpad] = True
+        actions[tpad] = 0.
+        hidden[:, :-1][tpad] = 0.  # sac_base.py:2453
+        first = torch.from_numpy(rng.randint(0, 50, size=(B, 1)).astype(np.int32))
+        index = torch.arange(L - 1, dtype=torch.int32).repeat(B, 1) + first  # episode positions of the rows
+        index[tpad] = -1
+        pri = torch.from_numpy((rng.rand(B, 1) * 0.9 + 0.1).astype(np.float32)) if use_priority else None
+        noise = dict(eps_y=torch.from_numpy(rng.randn(B, n + 1, A).astype(np.float32)),
+                     eps_pi=torch.from_numpy(rng.randn(B, A).astype(np.float32)),
+                     eps_alpha=torch.from_numpy(rng.randn(B, A).astype(np.float32)),
+                     eps_td=torch.from_numpy(rng.randn(B, n + 1, A).astype(np.float32)))
+        pre = f's{s}'
+        for i, o in enumerate(obses):
+            out[f'{pre}.in.obs{i}'] = o.numpy().copy()
+        for k, t in dict(hidden=hidden, index=index, actions=actions, rewards=rewards, dones=dones, mu_probs=mu_probs,
+                         last_masks=torch.from_numpy(last), padding_masks=tpad).items():
+            out[f'{pre}.in.{k}'] = t.numpy().copy()
+        if pri is not None:
+            out[f'{pre}.in.priority_is'] = pri.numpy().copy()
+        for k, t in noise.items():
+            out[f'{pre}.in.{k}'] = t.numpy().copy()
+
+        ys.clear()
+        with _NoiseTap() as tap:
+            tap.queue = [noise['eps_y'], noise['eps_pi']]
+            if sac.use_auto_alpha:
+                tap.queue.append(noise['eps_alpha'])
+            if use_priority:
+                tap.queue.append(noise['eps_td'])
+            bnx_states, next_hidden, bnx_target_states = sac._train(
+                bn_indexes=index.clone(), bn_last_masks=torch.from_numpy(last).clone(),
+                bn_padding_masks=tpad.clone(), bnx_obses_list=[o.clone() for o in obses],
+                bn_actions=actions.clone(), bn_rewards=rewards.clone(), bn_dones=dones.clone(),
+                bn_mu_probs=mu_probs.clone(), bnx_pre_seq_hidden_states=hidden.clone(),
+                priority_is=pri.clone() if pri is not None else None)
+            out[f'{pre}.out.y'] = ys[0].numpy().copy()
+            out[f'{pre}.out.states_post'] = bnx_states.detach().numpy().copy()
+            out[f'{pre}.out.target_states'] = bnx_target_states.detach().numpy().copy()
+            out[f'{pre}.out.next_hidden'] = next_hidden[:, :-1].detach().numpy().copy()
+            for k, g in rep_grads.items():
+                out[f'{pre}.grad.rep.{k}'] = g
+            for i in range(E):
+                for k, p in sac.model_q_list[i].named_parameters():
+                    out[f'{pre}.grad.q{i}.{k}'] = p.grad.detach().numpy().copy()
+            for k, p in sac.model_policy.named_parameters():
+                out[f'{pre}.grad.pi.{k}'] = p.grad.detach().numpy().copy()
+            if sac.use_auto_alpha:
+                out[f'{pre}.grad.log_c_alpha'] = sac.log_c_alpha.grad.detach().numpy().copy()
+            pi_probs = None
+            bn_states = bnx_states[:, :-1]
+            if sac.use_n_step_is:
+                pi_probs = sac.get_l_probs(l_obses_list=[o[:, :-1] for o in obses], l_states=bn_states,
+                                           l_actions=actions)
+                out[f'{pre}.out.pi_probs'] = pi_probs.numpy().copy()
+            if use_priority:
+                td = sac._get_td_error(
+                    n_last_masks=torch.from_numpy(last)[:, b:], n_padding_masks=tpad[:, b:],
+                    nx_obses_list=[o[:, b:] for o in obses], state=bn_states[:, b],
+                    nx_target_states=bnx_target_states[:, b:], n_actions=actions[:, b:],
+                    n_rewards=rewards[:, b:].clone(), n_dones=dones[:, b:],
+                    n_mu_probs=pi_probs[:, b:].clone() if sac.use_n_step_is else None)
+                out[f'{pre}.out.td_error'] = td.numpy().copy()
+                out[f'{pre}.out.y_td'] = ys[1].numpy().copy()
+            assert not tap.queue
+        sac.increase_global_step()
+        dump_params(f'{pre}.after')
+    sac.close()
+    np.savez_compressed(GOLDEN / f'sac_{name}.npz', **out)
+    print('wrote', f'sac_{name}.npz', sum(v.nbytes for v in out.values()), 'bytes raw')
+
+
 def gen_ckpt_case(name, *, rnn: bool, seed: int):
     """A checkpoint directory written by the REAL reference (`save_model(save_replay_buffer=True)`,
     sac_base.py:654-668; replay_buffer.py:96-111, 220-227, 436-446) after a few real `train()` steps,
@@ -803,6 +971,17 @@ CASES = {
     'sac_c3_b1024': lambda: gen_sac_case('c3_b1024', S=3, A=1, E=2, hidden=64, depth=2, B=1024, b=0, n=5, steps=1,
                                          seed=31, nn_rel='envs/gym/pendulum/nn.py', v_lambda=1.0, use_n_step_is=True),
     'sac_rnn_c4': lambda: gen_sac_rnn_case('rnn_c4', So=6, A=2, E=2, B=256, b=40, n=5, steps=1, seed=32),
+    # representations that run as the plugin's torch module (asac_b200/rep_bridge.py): the reference's own test
+    # plugins with a convolutional encoder in front of a packed GRU / the episode attention stack / nothing
+    'sac_conv_rnn': lambda: gen_sac_plugin_rep_case('conv_rnn', nn_rel='tests/nn_conv_rnn.py',
+                                                    obs_names=['vector', 'image'], obs_shapes=[(10,), (3, 30, 30)],
+                                                    seq_encoder='RNN', A=2, E=2, B=12, b=5, n=3, steps=2, seed=40),
+    'sac_conv_attn': lambda: gen_sac_plugin_rep_case('conv_attn', nn_rel='tests/nn_conv_attn.py',
+                                                     obs_names=['vector', 'image'], obs_shapes=[(10,), (3, 30, 30)],
+                                                     seq_encoder='ATTN', A=2, E=2, B=12, b=5, n=3, steps=2, seed=41),
+    'sac_conv_vanilla': lambda: gen_sac_plugin_rep_case('conv_vanilla', nn_rel='tests/nn_conv_vanilla.py',
+                                                        obs_names=['vector', 'image'], obs_shapes=[(10,), (3, 30, 30)],
+                                                        seq_encoder=None, A=2, E=2, B=12, b=0, n=3, steps=2, seed=42),
     # discrete / hybrid action branches
     'sac_disc': lambda: gen_sac_discrete_case('disc', S=6, d_action_sizes=[3, 4], A=0, E=2, B=10, b=0, n=3, steps=2,
                                               seed=16, v_lambda=0.9),
