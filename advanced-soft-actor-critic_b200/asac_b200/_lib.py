@@ -116,6 +116,7 @@ PROTOTYPES = {
     'asac_tree_leaf_max': (i32, [vp, i64, vp, vp]),
     'asac_tree_sample': (i32, [vp, i64, i32, vp, u64, vp, vp, vp, vp]),
     'asac_per_sample': (i32, [vp, i64, vp, i32, vp, u64, vp, vp, vp, vp, vp, vp, vp]),
+    'asac_per_shard_weights': (i32, [vp, i32, vp, vp, vp, vp, vp]),
     'asac_per_update': (i32, [vp, i64, vp, vp, vp, i32, f32, f32, f32, i32, vp, vp]),
     'asac_per_add': (i32, [vp, i64, vp, i64, i64, vp, i32, vp]),
     'asac_storage_write_rows': (i32, [vp, i64, i64, vp, i64, i64, vp]),
@@ -129,6 +130,7 @@ PROTOTYPES = {
     'asac_sac_tile_batch': (i32, [P(AsacSacConfig)]),
     'asac_mlp_param_count': (i64, [i32, i32, i32, i32]),
     'asac_mlp_param_stride': (i64, [i32, i32, i32, i32]),
+    'asac_sac_value_pass_on_tc': (i32, [P(AsacSacConfig), i32]),
     'asac_sac_polyak': (i32, [P(AsacSacConfig), P(AsacSacParams), f32, vp]),
     'asac_sac_target_y': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork), vp]),
     'asac_sac_q_backward': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork), vp]),

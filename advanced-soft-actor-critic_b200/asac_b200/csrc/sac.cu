@@ -1475,6 +1475,12 @@ static bool value_pass_on_tc(const AsacSacConfig &c, int tile_batch, int mode) {
     return p.RA <= TCF_MAX_ROWS && p.total * 4 <= 227 * 1024;
 }
 
+extern "C" int asac_sac_value_pass_on_tc(const AsacSacConfig *cfg, int mode) {
+    if (!cfg || validate(cfg) != ASAC_OK) return 0;
+    const int tile = asac_sac_tile_batch(cfg);
+    return tile >= 1 && value_pass_on_tc(*cfg, tile, mode) ? 1 : 0;
+}
+
 static int launch_value_pass(SacArgs &a, int mode, void *stream) {
     a.mode = mode;
     if (value_pass_on_tc(a.cfg, a.tile_batch, mode)) {

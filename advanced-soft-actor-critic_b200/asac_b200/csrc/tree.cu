@@ -215,8 +215,23 @@ __global__ void __launch_bounds__(1024) k_per_sample(const float *nodes, int64_t
     if (active) out_w[t] = (float)pow((double)__fdiv_rn(w, s_min[0]), -beta);
     if (t == 0) {
         per_state[0] = beta;
+        per_state[2] = (double)s_min[0];  // smallest sampling probability of this batch (sharded replay: asac_per_shard_weights)
         if (!unit_uniform) draw_counter[0] += 1;
     }
+}
+
+// Sharded replay (one tree per GPU, B draws each): a transition of shard r is drawn with probability
+// p / total_r, so its importance weight is ((p / total_r) / min)^-beta with the minimum taken over the batches
+// of ALL shards — the single-buffer rule of replay_buffer.py:352-354 applied to the union of the draws.
+// global_min[0] is that minimum (MIN all-reduce of per_state[2]); total_r is the shard's own root.
+__global__ void __launch_bounds__(1024) k_per_shard_weights(const float *nodes, int batch, const float *p,
+                                                            const double *per_state, const double *global_min,
+                                                            float *out_w) {
+    const int t = threadIdx.x;
+    if (t >= batch) return;
+    const float total = nodes[1];
+    const float w = __fdiv_rn(p[t], total);
+    out_w[t] = (float)pow((double)__fdiv_rn(w, (float)global_min[0]), -per_state[0]);
 }
 
 // replay_buffer.py:412-427 — one CTA, k <= 1024
@@ -338,6 +353,16 @@ extern "C" int asac_per_sample(const float *nodes, int64_t capacity, const int64
                         tree_levels(capacity), store_ids, batch, unit_uniform, seed, draw_counter, per_state, out_slot,
                         out_data_id, out_p, out_is_weight));
     ASAC_LAUNCHED("k_per_sample");
+    return ASAC_OK;
+}
+
+extern "C" int asac_per_shard_weights(const float *nodes, int batch, const float *p, const double *per_state,
+                                      const double *global_min, float *out_is_weight, void *stream) {
+    ASAC_REQUIRE(nodes && p && per_state && global_min && out_is_weight, "asac_per_shard_weights: null pointer");
+    ASAC_REQUIRE(batch > 0 && batch <= 1024, "asac_per_shard_weights: batch %d outside (0, 1024]", batch);
+    k_per_shard_weights<<<1, ((batch + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(nodes, batch, p, per_state, global_min,
+                                                                                 out_is_weight);
+    ASAC_LAUNCHED("k_per_shard_weights");
     return ASAC_OK;
 }
 

@@ -71,7 +71,7 @@ class TorchRepBridge:
     @staticmethod
     def _math():
         """fp32 everywhere: cuDNN convolutions / RNNs default to TF32, the parity bound is 1e-5."""
-        return torch.backends.cudnn.flags(allow_tf32=False)
+        return torch.backends.cudnn.flags(enabled=True, allow_tf32=False)
 
     # ------------------------------------------------------------------ get_l_states (sac_base.py:1118-1157)
     def l_states(self, index, padding_mask, obs_list, pre_action, hidden, target: bool):

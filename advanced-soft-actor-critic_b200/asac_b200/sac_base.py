@@ -435,7 +435,7 @@ class SAC_Base:
         for h in (hidden, None):
             try:
                 # cuDNN notes that the weights are views of one flat buffer; its RNNs default to TF32
-                with warnings.catch_warnings(), torch.backends.cudnn.flags(allow_tf32=False):
+                with warnings.catch_warnings(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                     warnings.simplefilter('ignore')
                     want_state, want_hn = self.model_rep(obs_list, pre_action, h)
             except Exception as e:  # noqa: BLE001
@@ -484,6 +484,18 @@ class SAC_Base:
         replay_config = {} if replay_config is None else dict(replay_config)
         if self._seed is not None:
             replay_config.setdefault('seed', int(self._seed))
+        # Data-parallel learner: `capacity` is the GLOBAL capacity; every rank owns capacity / world ring slots with
+        # its own segment tree (asac_b200/dist.py).  `episode_routing`: 'local' — every rank stores the episodes its
+        # own actors hand to put_episode (the usual one-process-per-GPU deployment); 'round_robin' — every rank is
+        # handed EVERY episode (one replicated actor stream) and keeps the ones dist.episode_owner assigns to it.
+        self._episode_routing = replay_config.pop('episode_routing', os.environ.get('ASAC_EPISODE_ROUTING', 'local'))
+        if self._episode_routing not in ('local', 'round_robin'):
+            raise ValueError(f"episode_routing '{self._episode_routing}' (local | round_robin)")
+        self._episode_counter = 0
+        self.global_replay_capacity = None
+        if self._world > 1 and replay_config.pop('shard', True):
+            self.global_replay_capacity = int(replay_config.get('capacity', 524288))
+            replay_config['capacity'] = adist.shard_capacity(self.global_replay_capacity, self._world)
         self.replay_buffer = PrioritizedReplayBuffer(batch_size=self.batch_size, sample_prev_n=self.burn_in_step,
                                                      sample_post_n=self.n_step, device=self.device,
                                                      logger_parent_name=self._logger.name, **replay_config)
@@ -555,6 +567,7 @@ class SAC_Base:
                 regions += [self._rep_flat, self._rep_m, self._rep_v]
             self._prefetch = ((C.c_void_p * len(regions))(*[t.data_ptr() for t in regions]),
                               (C.c_int64 * len(regions))(*[t.numel() * 4 for t in regions]), regions)
+        self._min_prob = torch.zeros(1, dtype=torch.float64, device=dev)    # sharded replay: global min sampling probability
         self._act_counter = torch.zeros(1, dtype=torch.int64, device=dev)  # Philox counter of choose_action
         self._actor_bufs = {}
         self.actor_tensor_cores = False
@@ -905,7 +918,7 @@ class SAC_Base:
                 obs[i] = o.float()
         if self._gru is not None or self._bridge is not None:
             to_dev = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
-            with torch.backends.cudnn.flags(allow_tf32=False):  # cuDNN RNNs default to TF32
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):  # cuDNN RNNs default to TF32
                 state, hidden = self.model_rep([o.unsqueeze(1) for o in obs], to_dev(pre_action).unsqueeze(1),
                                                to_dev(pre_seq_hidden_state).unsqueeze(1))
         else:
@@ -945,6 +958,11 @@ class SAC_Base:
                                           ep_actions=ep_actions, ep_rewards=ep_rewards, ep_dones=ep_dones,
                                           ep_probs=ep_probs, ep_pre_seq_hidden_states=ep_pre_seq_hidden_states)
             return
+        if self._world > 1 and self._episode_routing == 'round_robin':
+            owner = adist.episode_owner(self._episode_counter, self._world)
+            self._episode_counter += 1
+            if owner != self._rank:
+                return
         storage = {'index': ep_indexes.squeeze(0), 'last_mask': last.squeeze(0)}
         for name, o in zip(self.obs_names, ep_obses_list):
             storage[f'obs_{name}'] = o.squeeze(0)
@@ -1009,6 +1027,14 @@ class SAC_Base:
         check(lib.asac_per_sample(ptr(rb._nodes), rb.capacity, ptr(rb._store_ids), self.batch_size, None, rb._seed,
                                   ptr(rb._draw_counter), ptr(rb._per_state), ptr(smp['slots']), ptr(smp['ids']),
                                   ptr(smp['p']), ptr(smp['w']), _lib.current_stream()), 'per_sample')
+        if self._world > 1 and self.use_priority:
+            # IS weights against the smallest sampling probability over ALL shards' batches (replay_buffer.py:352-354
+            # on the union of the draws): one 8-byte MIN all-reduce, off the critical path with sampling one step ahead
+            self._min_prob.copy_(rb._per_state[2:3])
+            torch.distributed.all_reduce(self._min_prob, op=torch.distributed.ReduceOp.MIN)
+            check(lib.asac_per_shard_weights(ptr(rb._nodes), self.batch_size, ptr(smp['p']), ptr(rb._per_state),
+                                             ptr(self._min_prob), ptr(smp['w']), _lib.current_stream()),
+                  'per_shard_weights')
         rb._gather(smp['ids'], st['specs'], self._padding_action, st['bt']['padding_masks'])
 
     def _enqueue_tree_update(self, st: dict) -> None:

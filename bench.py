@@ -44,6 +44,13 @@ CONFIGS = {
     # representation's gradient joins the peer exchange): envs/test/nn_rnn.py GRU(6 + 2 -> 8, 2 layers),
     # burn-in 40, n_step 5 -> windows of 46 rows, batch 256 sequences, PER
     'c4': dict(CFG, name='c4', burn_in=40, n_step=5, rep=dict(hidden=8, layers=2)),
+    # BASELINE.json configs[4]: the reference's tests/nn_conv_attn.py (ConvLayers 'simple' + EpisodeMultiheadAttention;
+    # the plugin fixes the image at 3x30x30, observation shapes of tests/test_sac_params.py), seq_encoder=ATTN,
+    # PER, batch 512.  The representation runs as the plugin's torch module (asac_b200/rep_bridge.py), everything
+    # else on this repo's kernels; replay capacity 65536 (the float32 images of 524288 transitions would not fit
+    # the stock storage layout: 5.6 GB per 524288 x 2700 floats is fine on 180 GB, but filling it takes minutes)
+    'c5': dict(CFG, name='c5', B=512, burn_in=8, n_step=5, capacity=65536, bridge=dict(
+        obs_names=['vector', 'image'], obs_shapes=[(10,), (3, 30, 30)], seq_encoder='ATTN')),
 }
 WORKLOADS = {
     'c2': 'TEST vector-obs(6,) A=2 SAC+PER alpha=0.9 capacity=524288 (full) batch=256 ensemble_q=2 n_step=1, '
@@ -54,22 +61,36 @@ WORKLOADS = {
           'through the critic loss) burn_in_step=40 n_step=5 (46-row windows) SAC+PER capacity=524288 (full) '
           'batch=256 sequences ensemble_q=2, stock H=64 depth-3 Q / policy nets, single GPU',
 }
+WORKLOADS['c5'] = ('tests/nn_conv_attn.py (ConvLayers(30,30,3,simple) + EpisodeMultiheadAttention), obs vector(10,) + '
+                   'image(3,30,30), A=2, seq_encoder=ATTN, burn_in_step=8 n_step=5 (14-row windows), SAC+PER '
+                   'capacity=65536 (full) batch=512 ensemble_q=2; representation = plugin torch module (cuDNN/cuBLAS, '
+                   'TF32 off), everything else on the hand-written kernels')
 WORKLOAD = WORKLOADS['c2']
 METRIC = 'sac_grad_steps_per_sec_batch256'
 UNIT = 'steps/s'
 
 
 # --------------------------------------------------------------------------- synthetic data
+_HIDDEN_SHAPE = None  # set by build_learner for a bridged representation (the learner probes it)
+
+
 def hidden_shape():
+    if _HIDDEN_SHAPE is not None:
+        return _HIDDEN_SHAPE
     r = CFG.get('rep')
     return (r['layers'], r['hidden']) if r else (0,)
+
+
+def obs_shapes():
+    br = CFG.get('bridge')
+    return [tuple(s) for s in br['obs_shapes']] if br else [tuple(CFG['obs_shape'])]
 
 
 def synth_episode(rng, T, S, A):
     """tests/get_synthesis_data.py:114-126 of the reference: obs randn, action rand, reward randn,
     done randint, probs rand (float32), hidden state randn (empty without a recurrent representation)."""
     return dict(ep_indexes=np.arange(T, dtype=np.int32)[None],
-                ep_obses_list=[rng.randn(1, T, S).astype(np.float32)],
+                ep_obses_list=[rng.randn(1, T, *shape).astype(np.float32) for shape in obs_shapes()],
                 ep_actions=rng.rand(1, T, A).astype(np.float32),
                 ep_rewards=rng.randn(1, T).astype(np.float32),
                 ep_dones=rng.randint(0, 2, size=(1, T)).astype(bool),
@@ -117,6 +138,11 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        return self.snapshot()
+
+    def snapshot(self) -> dict:
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -176,7 +202,8 @@ def stage_work(cfg):
 
 
 # --------------------------------------------------------------------------- GPU arm
-PLUGIN_FILES = {'c2': 'envs_test_nn.py', 'c3': 'envs_gym_pendulum_nn.py', 'c4': 'envs_test_nn_rnn.py'}
+PLUGIN_FILES = {'c2': 'envs_test_nn.py', 'c3': 'envs_gym_pendulum_nn.py', 'c4': 'envs_test_nn_rnn.py',
+                'c5': 'tests_nn_conv_attn.py'}
 
 
 def load_plugin(config: str):
@@ -191,20 +218,30 @@ def load_plugin(config: str):
     return mod
 
 
-def build_learner(device, seed, capacity, fill):
+def build_learner(device, seed, capacity, fill, batch=None):
+    """`capacity` is the GLOBAL replay capacity: under torch.distributed the learner shards it (SAC_Base owns the
+    sharding); `fill` = transitions to store on this rank (None: the rank's whole shard)."""
+    global _HIDDEN_SHAPE
     from asac_b200 import SAC_Base
     nn = load_plugin(CFG['name'])
-    seq_encoder = None
+    seq_encoder, names, shapes = None, ['vector'], [CFG['obs_shape']]
+    from asac_b200.utils.enums import SEQ_ENCODER
     if CFG.get('rep'):
-        from asac_b200.utils.enums import SEQ_ENCODER
         seq_encoder = SEQ_ENCODER.RNN
-    sac = SAC_Base(obs_names=['vector'], obs_shapes=[CFG['obs_shape']], d_action_sizes=[], c_action_size=CFG['A'],
-                   model_abs_dir=None, nn=nn, device=device, seed=seed, batch_size=CFG['B'], n_step=CFG['n_step'],
+    if CFG.get('bridge'):
+        br = CFG['bridge']
+        seq_encoder = SEQ_ENCODER[br['seq_encoder']] if br['seq_encoder'] else None
+        names, shapes = list(br['obs_names']), obs_shapes()
+    sac = SAC_Base(obs_names=names, obs_shapes=shapes, d_action_sizes=[], c_action_size=CFG['A'],
+                   model_abs_dir=None, nn=nn, device=device, seed=seed, batch_size=batch or CFG['B'], n_step=CFG['n_step'],
                    burn_in_step=CFG['burn_in'], ensemble_q_num=CFG['E'], ensemble_q_sample=CFG['E'],
                    seq_encoder=seq_encoder, use_priority=True,
                    replay_config={'capacity': capacity, 'alpha': CFG['per_alpha']})
+    if CFG.get('bridge'):
+        _HIDDEN_SHAPE = tuple(sac.seq_hidden_state_shape)
     rng = np.random.RandomState(seed)
     S, A, T = CFG['obs_shape'][0], CFG['A'], CFG['episode_len']
+    fill = sac.replay_buffer.capacity if fill is None else fill
     while sac.replay_buffer.size < fill:
         sac.put_episode(**synth_episode(rng, T, S, A))
     torch.cuda.synchronize()
@@ -355,22 +392,33 @@ def tensor_core_forward(rows=1 << 20, iters=10):
     return res
 
 
-def run_gpu(args):
+def _params_checksum(sac) -> torch.Tensor:
+    """Bit pattern of every replicated parameter summed as int64 (an exact, order-free checksum)."""
+    flats = [sac._q_flat, sac._qt_flat, sac._pi_flat, sac._log_alpha_buf]
+    if getattr(sac, '_rep_flat', None) is not None:
+        flats += [sac._rep_flat, sac._rept_flat]
+    return torch.stack([t.reshape(-1).view(torch.int32).to(torch.int64).sum() for t in flats]).sum().reshape(1)
+
+
+def measure(args, steps, warmup, clocks=None, detail=True):
+    """Builds the learner of the current CFG, times `steps` train() calls (L2 flushed between them, CUDA events on
+    the launching stream, max over ranks), the same steps with a warm L2, and the end-to-end loop through the public
+    API.  -> the JSON line as a dict (rank 0; None on the other ranks)."""
     from asac_b200 import _lib
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
-    torch.cuda.set_device(local_rank)
     device = f'cuda:{local_rank}'
-    if world > 1:
-        torch.distributed.init_process_group('nccl', device_id=torch.device(device))
-    from asac_b200 import dist as adist
-    capacity = adist.shard_capacity(CFG['capacity'], world) if world > 1 else CFG['capacity']
     lib = _lib.load()
+    strong = args.scaling == 'strong' and world > 1
+    if strong and CFG['B'] % world:
+        raise SystemExit(f"--scaling strong: batch {CFG['B']} is not divisible by {world} ranks")
+    batch = CFG['B'] // world if strong else CFG['B']
 
     t_fill = time.perf_counter()
-    sac, rng = build_learner(device, seed=1 + rank, capacity=capacity, fill=capacity)
+    sac, rng = build_learner(device, seed=1 + rank, capacity=CFG['capacity'], fill=None, batch=batch)
     t_fill = time.perf_counter() - t_fill
+    capacity = sac.replay_buffer.capacity
     S, A = CFG['obs_shape'][0], CFG['A']
 
     def barrier():
@@ -381,7 +429,7 @@ def run_gpu(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     # ---- warm-up (first call eager, second captures the CUDA graph)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         sac.train()
     barrier()
 
@@ -394,12 +442,10 @@ def run_gpu(args):
     sac.increase_global_step()
 
     # ---- timed: K steps, one CUDA-event pair per step, L2 flushed between steps
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     barrier()
     torch.cuda.profiler.start()  # `ncu --profile-from-start off` captures exactly the timed steps
     events = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -415,26 +461,25 @@ def run_gpu(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         sac.train()
     e1.record()
     barrier()
     warm_ms = e0.elapsed_time(e1)
-    clock_info = clocks.stop()
 
     # ---- end to end through the public API: host transitions in, td-errors out, every step
     T_in = 8
     eps = [pin_episode(synth_episode(rng, T_in, S, A)) for _ in range(32)]
     h2d = sum(v.nbytes for k, v in eps[0].items() if not isinstance(v, list)) + sum(x.nbytes for x in eps[0]['ep_obses_list'])
     h2d += T_in  # the derived last_mask column
-    td_host = torch.empty(CFG['B'], dtype=torch.float32).pin_memory()
+    td_host = torch.empty(batch, dtype=torch.float32).pin_memory()
     for i in range(5):
         sac.put_episode(**eps[i % 32]); sac.train(); td_host.copy_(sac._wk['td_error']); torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         sac.put_episode(**eps[i % 32])
         sac.train()
         td_host.copy_(sac._wk['td_error'], non_blocking=True)
@@ -443,35 +488,51 @@ def run_gpu(args):
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    clock_info = clocks.snapshot() if clocks is not None else None
 
-    # ---- max over ranks
+    # ---- max over ranks; replicas must hold bit-identical parameters after all those steps
+    replicas_identical = None
     if world > 1:
         t = torch.tensor([total_ms, warm_ms, e2e_ms], device=device, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         total_ms, warm_ms, e2e_ms = [float(x) for x in t.tolist()]
+        ck = _params_checksum(sac)
+        cks = [torch.zeros_like(ck) for _ in range(world)]
+        torch.distributed.all_gather(cks, ck)
+        replicas_identical = all(int(c.item()) == int(cks[0].item()) for c in cks)
+        assert replicas_identical, f'data-parallel replicas diverged: parameter checksums {[int(c.item()) for c in cks]}'
 
-    units_per_step = world  # each rank processes one batch-256 update per step (weak scaling)
-    value = units_per_step * args.steps / (total_ms * 1e-3)
+    # weak scaling: every rank runs a batch-B update per step (global batch B x N), `value` counts them all;
+    # strong scaling: the global batch stays B (B / N per rank), `value` = optimizer steps per second
+    opt_steps_per_s = steps / (total_ms * 1e-3)
+    units_per_step = 1 if strong else world
+    value = units_per_step * opt_steps_per_s
     out = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'global_batch': CFG['B'] * world, 'replay_capacity_per_gpu': capacity,
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
+        'ms_per_step': total_ms / steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'global_batch': batch * world, 'replay_capacity_per_gpu': capacity,
                    'parallelism': f'dp{world}' if world > 1 else 'single',
                    'l2': 'flushed between timed steps (256 MiB memset, outside the event pairs)',
                    'cuda_graph': bool(sac._graph is not None),
-                   'value_definition': f"batch-{CFG['B']} gradient steps per second summed over ranks"},
-        'value_warm_l2': units_per_step * args.steps / (warm_ms * 1e-3),
-        'e2e': {'value': units_per_step * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
+                   'value_definition': (f"optimizer steps per second at a global batch of {batch * world}" if strong else
+                                        f"batch-{CFG['B']} gradient steps per second summed over ranks "
+                                        f"(= optimizer_steps_per_s x {world} ranks, each on its own batch)")},
+        'optimizer_steps_per_s': opt_steps_per_s,
+        'samples_per_s': opt_steps_per_s * batch * world,
+        'value_warm_l2': units_per_step * steps / (warm_ms * 1e-3),
+        'e2e': {'value': units_per_step * steps / (e2e_ms * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(td_host.numel() * 4),
-                'what': f'put_episode({T_in} host transitions, pinned) + train() + D2H of td_error[256], per step'},
-        'gpu_launches': launches_per_step * args.steps * world,
+                'what': f'put_episode({T_in} host transitions, pinned) + train() + D2H of td_error[{batch}], per step'},
+        'gpu_launches': launches_per_step * steps * world,
         'launches_per_step': launches_per_step,
         'clocks': clock_info,
         'fill_seconds': round(t_fill, 2),
     }
+    if replicas_identical is not None:
+        out['replicas_identical'] = replicas_identical
 
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and sac._bridge is None:
         prof = profile_stages(sac, steps=200)
         work = stage_work(CFG)
         peaks = {}
@@ -480,7 +541,12 @@ def run_gpu(args):
             peaks = json.loads(pk.read_text())
         hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
         tf_peak = float(peaks.get('bf16_tflops', 1590.0))
+        # fp32 FFMA peak of the part: 148 SMs x 128 lanes x 2 flop x SM clock (the row-tile kernels' own ceiling)
+        sm_mhz = (clock_info or {}).get('sm_max_mhz') or 1965.0
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
+        tc_value_pass = {0: bool(lib.asac_sac_value_pass_on_tc(ctypes_byref(sac._cfg), 0)),
+                         1: bool(lib.asac_sac_value_pass_on_tc(ctypes_byref(sac._cfg), 1))}
         kernels = {}
         for name, us in prof.items():
             w = work[name]
@@ -490,8 +556,11 @@ def run_gpu(args):
                                  'achieved_GBps': round(ach, 3), 'frac': ach / hbm_peak}
             else:
                 ach = w['flops'] / (us * 1e-6) / 1e12
+                on_tc = (name == 'value_pass_train' and tc_value_pass[0]) or (name == 'value_pass_post' and tc_value_pass[1])
                 kernels[name] = {'us': round(us, 3), 'bound': 'tensor', 'algorithmic_flops': w['flops'],
-                                 'achieved_TFLOPs': round(ach, 5), 'frac': ach / tf_peak}
+                                 'achieved_TFLOPs': round(ach, 5), 'frac': ach / tf_peak,
+                                 'pipe': 'tcgen05 3xTF32 (k_value_pass_tc)' if on_tc else 'fp32 FFMA row tiles',
+                                 'frac_of_fp32_ffma_peak': ach / fp32_peak}
         # standalone entry points that are not part of the step as the learner schedules it
         not_in_step = ('adam_alpha', 'finish_step_fused_tree') if sac._defer_active else \
             ('adam_alpha', 'per_update', 'finish_step_fused_tree')
@@ -501,27 +570,72 @@ def run_gpu(args):
         traffic = None
         tr = ROOT / 'profiles' / 'ncu_dram_traffic.json'  # dram__bytes_read+write per launch, `ncu --set full`
         if tr.exists():
-            traffic = json.loads(tr.read_text()).get(top)
+            traffic = json.loads(tr.read_text()).get(f"{CFG['name']}:{top}", json.loads(tr.read_text()).get(top))
         out['roofline'] = {'kernel': top, 'bound': k['bound'],
                            'achieved': k.get('achieved_GBps', k.get('achieved_TFLOPs')),
                            'peak': hbm_peak if k['bound'] == 'hbm' else tf_peak,
                            'unit': 'GB/s' if k['bound'] == 'hbm' else 'TFLOP/s', 'frac': k['frac'],
                            'traffic': traffic, 'peak_source': src,
                            'share_of_step': in_step[top] / sum(in_step.values()),
-                           'note': 'exact-fp32 FFMA row-tile kernel (1e-5 parity bound rules out plain tf32); one '
-                                   '16-row tile per SM at B=256, i.e. latency-bound, not pipe-bound (DESIGN.md §6)'}
-        out['tensor_core_forward'] = tensor_core_forward()
-        out['per_bulk_sample'] = per_bulk_sample(sac.replay_buffer)
-        out['per_bulk_sample']['frac_of_hbm_peak'] = out['per_bulk_sample']['achieved_GBps'] / hbm_peak
-        per_us = prof['per_sample'] + prof['per_update']
-        per_bytes = work['per_sample']['bytes'] + work['per_update']['bytes']
-        out['per_sample_update'] = {'us': round(per_us, 3), 'algorithmic_bytes': per_bytes,
-                                    'achieved_GBps': per_bytes / (per_us * 1e-6) / 1e9,
-                                    'frac_of_hbm_peak': per_bytes / (per_us * 1e-6) / 1e9 / hbm_peak,
-                                    'dependent_levels': int(np.log2(capacity))}
+                           'pipe': k.get('pipe'), 'fp32_ffma_peak_TFLOPs': round(fp32_peak, 2),
+                           'frac_of_fp32_ffma_peak': k.get('frac_of_fp32_ffma_peak'),
+                           'note': 'flop-bound stage of a latency-bound step: one 16-row tile per SM at B=256 '
+                                   '(DESIGN.md §6); `peak` is the dense bf16 tensor peak the contract names, the '
+                                   'fp32 FFMA ceiling of the kernel that actually runs is given beside it'}
         out['kernels'] = kernels
-        out['cpu_baseline'] = cpu_port_baseline(budget_s=args.cpu_seconds)
+        if detail:
+            out['tensor_core_forward'] = tensor_core_forward()
+            out['per_bulk_sample'] = per_bulk_sample(sac.replay_buffer)
+            out['per_bulk_sample']['frac_of_hbm_peak'] = out['per_bulk_sample']['achieved_GBps'] / hbm_peak
+            per_us = prof['per_sample'] + prof['per_update']
+            per_bytes = work['per_sample']['bytes'] + work['per_update']['bytes']
+            out['per_sample_update'] = {'us': round(per_us, 3), 'algorithmic_bytes': per_bytes,
+                                        'achieved_GBps': per_bytes / (per_us * 1e-6) / 1e9,
+                                        'frac_of_hbm_peak': per_bytes / (per_us * 1e-6) / 1e9 / hbm_peak,
+                                        'dependent_levels': int(np.log2(capacity))}
     sac.close()
+    del sac, flush
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
+def ctypes_byref(x):
+    import ctypes
+    return ctypes.byref(x)
+
+
+def run_gpu(args):
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
+    clocks = ClockSampler(local_rank)
+    clocks.start()  # from before the warm-up on: a 100 ms sampler never fires inside a few-ms timed region
+    out = measure(args, args.steps, args.warmup, clocks=clocks, detail=True)
+    # the other BASELINE configs, short runs of the same measurement, embedded so that one default run records them
+    if world == 1 and args.config == 'c2' and not args.no_sub_results:
+        global WORKLOAD, METRIC
+        subs = {}
+        for name, (k, w) in (('c3', (400, 10)), ('c4', (400, 10)), ('c5', (40, 5))):
+            CFG.clear(); CFG.update(CONFIGS[name])
+            WORKLOAD, METRIC = WORKLOADS[name], f"sac_grad_steps_per_sec_batch{CFG['B']}"
+            try:
+                r = measure(args, k, w, clocks=None, detail=False)
+                subs[name] = {kk: r[kk] for kk in ('metric', 'value', 'unit', 'steps', 'ms_per_step', 'value_warm_l2', 'e2e',
+                                                  'launches_per_step', 'roofline', 'kernels') if kk in r}
+                subs[name]['workload'] = WORKLOADS[name]
+            except Exception as e:  # noqa: BLE001 - a secondary measurement must not take the headline down
+                subs[name] = {'error': f'{type(e).__name__}: {e}'}
+        CFG.clear(); CFG.update(CONFIGS['c2'])
+        WORKLOAD, METRIC = WORKLOADS['c2'], f"sac_grad_steps_per_sec_batch{CFG['B']}"
+        out['other_configs'] = subs
+    if rank == 0 and world == 1:
+        out['cpu_baseline'] = cpu_port_baseline(budget_s=args.cpu_seconds)
+    out_clocks = clocks.stop()
+    if rank == 0:
+        out['clocks'] = out_clocks
     if world > 1:
         torch.distributed.destroy_process_group()
     if rank == 0:
@@ -592,6 +706,12 @@ def cpu_port_step(per, sac, rng):
 
 
 def cpu_port_baseline(budget_s=12.0, steps=None, warmup=5):
+    if CFG.get('bridge'):  # no port of a plugin-defined representation: only the reference itself can run it
+        root = real_reference_root()
+        if root is None:
+            return {'unavailable': 'this configuration\'s representation is the plugin\'s own torch module; its CPU arm is '
+                                   'the reference itself, which is not on this box'}
+        return real_reference_baseline(root, steps or 20, warmup)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     per, sac, rng = cpu_port_setup()
@@ -610,18 +730,84 @@ def cpu_port_baseline(budget_s=12.0, steps=None, warmup=5):
             'ms_per_step': dt / done * 1e3}
 
 
+def real_reference_root():
+    """A checkout / install of the UNMODIFIED reference, when one is reachable: $ASAC_REFERENCE_ROOT, baseline/_ref
+    (driver-written on some boxes), /root/reference (the build container).  None on a bare GPU box."""
+    for c in (os.environ.get('ASAC_REFERENCE_ROOT'), ROOT / 'baseline' / '_ref', '/root/reference'):
+        if c and (Path(c) / 'algorithm' / 'sac_base.py').exists() and (Path(c) / 'algorithm' / 'replay_buffer.py').exists():
+            return Path(c)
+    return None
+
+
+def real_reference_baseline(root: Path, steps: int, warmup: int):
+    """The reference's own SAC_Base on the host cores: stock code path (its NumPy sumtree, prefetch thread, torch-CPU
+    update) through its public API — put_episode to fill the replay, then train() — with the plugin file of the
+    config.  Nothing of this repo is on that path except the import shims for what a GPU-less box lacks
+    (oracle/ref_shims.py: matplotlib, torch.cuda.Stream, pin_memory)."""
+    import importlib.util
+    import oracle.ref_shims as rs
+    rs.REFERENCE_ROOT = Path(root)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    SAC_Base, _, _ = rs.import_reference()
+    from algorithm.utils.enums import SEQ_ENCODER  # the reference's own enum (its package is imported now)
+    path = ROOT / 'tests' / 'golden' / 'plugins' / PLUGIN_FILES[CFG['name']]  # verbatim copy of the reference's file
+    spec = importlib.util.spec_from_file_location(f'ref_bench_nn_{CFG["name"]}', path)
+    nn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nn)
+    seq_encoder, names, shapes = None, ['vector'], [tuple(CFG['obs_shape'])]
+    if CFG.get('rep'):
+        seq_encoder = SEQ_ENCODER.RNN
+    if CFG.get('bridge'):
+        br = CFG['bridge']
+        seq_encoder = SEQ_ENCODER[br['seq_encoder']] if br['seq_encoder'] else None
+        names, shapes = list(br['obs_names']), obs_shapes()
+    sac = SAC_Base(obs_names=names, obs_shapes=shapes, d_action_sizes=[], c_action_size=CFG['A'], model_abs_dir=None,
+                   nn=nn, device='cpu', seed=1, batch_size=CFG['B'], n_step=CFG['n_step'], burn_in_step=CFG['burn_in'],
+                   ensemble_q_num=CFG['E'], ensemble_q_sample=CFG['E'], seq_encoder=seq_encoder, use_priority=True,
+                   replay_config={'capacity': CFG['capacity'], 'alpha': CFG['per_alpha']})
+    global _HIDDEN_SHAPE
+    _HIDDEN_SHAPE = tuple(int(x) for x in sac.seq_hidden_state_shape)
+    rng = np.random.RandomState(1)
+    S, A, T = CFG['obs_shape'][0], CFG['A'], CFG['episode_len']
+    t_fill = time.perf_counter()
+    while not sac.replay_buffer.is_full:
+        sac.put_episode(**synth_episode(rng, T, S, A))
+    t_fill = time.perf_counter() - t_fill
+    for _ in range(warmup):
+        sac.train()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sac.train()
+    dt = time.perf_counter() - t0
+    sac.close()
+    return {'value': steps / dt, 'unit': UNIT, 'cores': threads, 'kind': 'reference',
+            'sample': f"{steps} SAC_Base.train() calls of the UNMODIFIED reference at {root} (B={CFG['B']}, capacity "
+                      f"{CFG['capacity']} full, filled through put_episode in {t_fill:.0f} s) in {dt:.1f} s, {threads} torch threads",
+            'ms_per_step': dt / steps * 1e3}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    base = cpu_port_baseline(steps=args.steps, warmup=max(args.warmup, 3))
+    base, note = None, None
+    root = real_reference_root()
+    if root is not None and os.environ.get('ASAC_REFERENCE_ARM', 'auto') != 'port':
+        try:
+            base = real_reference_baseline(root, args.steps, max(args.warmup, 3))
+            note = f'the unmodified reference at {root}, stock code path, CPU'
+        except Exception as e:  # noqa: BLE001 - e.g. a missing dependency of the reference on this box
+            note = f'reference at {root} did not run ({type(e).__name__}: {e}); '
+    if base is None:
+        base = cpu_port_baseline(steps=args.steps, warmup=max(args.warmup, 3))
+        note = (note or '') + ('CPU port of the reference path (oracle/): the Python reference itself is not on this box '
+                               '(it cannot travel with the snapshot)')
     world = int(os.environ.get('WORLD_SIZE', 1))
     out = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': world,
            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': base['ms_per_step'], 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': WORKLOAD,
-                      'note': 'CPU port of the reference path (oracle/); the Python reference itself cannot travel '
-                              'to the GPU box'},
+           'config': {'workload': WORKLOAD, 'note': note},
            'cpu_baseline': base,
            'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
            'gpu_launches': 0}
@@ -636,6 +822,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='N > 1: weak = every rank a full batch (default), strong = the global batch stays B')
+    ap.add_argument('--no-sub-results', action='store_true', help='skip the short runs of the other BASELINE configs')
     args = ap.parse_args()
     global WORKLOAD, METRIC
     CFG.update(CONFIGS[args.config])

@@ -76,7 +76,8 @@ int asac_tree_sample(const float *nodes, int64_t capacity, int batch, const doub
 /* ------------------------------------------------------------------------------------
  * Prioritized replay — replaces PrioritizedReplayBuffer (replay_buffer.py:245-477).
  * `store_ids` is DataStorage's `_id` column, int64[capacity] (replay_buffer.py:36).
- * `per_state` is double[4] on the device: {beta, beta_increment, unused, nan_flag}.
+ * `per_state` is double[4] on the device: {beta, beta_increment, min sampling probability of the last
+ * batch, nan_flag}.
  * ---------------------------------------------------------------------------------- */
 
 /* One iteration of _prefetch_loop's sampling block (replay_buffer.py:347-354): tree
@@ -87,6 +88,13 @@ int asac_per_sample(const float *nodes, int64_t capacity, const int64_t *store_i
                     const double *unit_uniform, uint64_t seed, int64_t *draw_counter,
                     double *per_state, int32_t *out_slot, int64_t *out_data_id, float *out_p,
                     float *out_is_weight, void *stream);
+
+/* Sharded replay (one tree per GPU; new capability, the reference has one buffer): recomputes the batch's IS
+ * weights against the smallest sampling probability over ALL shards' batches, global_min[0] = MIN over ranks of
+ * per_state[2] after asac_per_sample — replay_buffer.py:352-354 applied to the union of the shards' draws:
+ * w = ((p / total_of_this_shard) / global_min)^-beta.  With one shard it reproduces asac_per_sample's weights. */
+int asac_per_shard_weights(const float *nodes, int batch, const float *p, const double *per_state,
+                           const double *global_min, float *out_is_weight, void *stream);
 
 /* PrioritizedReplayBuffer.update (replay_buffer.py:412-427): p = clip(|td|, min, max)^alpha in
  * fp32, skipped where store_ids[id % capacity] != id, then SumTree.update.  A NaN td sets
@@ -284,6 +292,10 @@ int asac_sac_tile_batch(const AsacSacConfig *cfg);
 int64_t asac_mlp_param_stride(int in_dim, int hidden, int depth, int out_dim);
 /* float count of one flat net: in -> (H x depth) -> out */
 int64_t asac_mlp_param_count(int in_dim, int hidden, int depth, int out_dim);
+
+/* 1 when the value pass of this configuration (mode 0: _get_y, mode 1: get_l_probs / _get_td_error) runs on the
+ * tcgen05 layer engine (k_value_pass_tc), 0 when it runs on the FFMA row-tile kernel — for reports. */
+int asac_sac_value_pass_on_tc(const AsacSacConfig *cfg, int mode);
 
 /* _update_target_variables (sac_base.py:745-764) when counters[0] % update_target_per_step == 0
  * (sac_base.py:2057-2058); `force_tau` >= 0 applies that tau unconditionally (hard copy at

