@@ -237,6 +237,7 @@ class SAC_Base:
             self._build_step_buffers()
             self._init_or_restore(int(last_ckpt) if last_ckpt is not None else None)
         self._graphs = [None, None]
+        self._bridge_graph, self._bridge_eager_steps = None, 0
         self._graph_columns_key = None
         self._steps_since_check = 0
         # NCCL all-reduces are captured into the step's CUDA graph (ASAC_GRAPH_COLLECTIVES=0 keeps them eager)
@@ -1329,8 +1330,35 @@ class SAC_Base:
                 for st in self._sets:
                     st['specs'] = self._gather_specs(st['bt'])
                 self._graphs, self._graph_columns_key, self._primed = [None, None], key, False
+                self._bridge_graph, self._bridge_eager_steps = (None if os.environ.get('ASAC_BRIDGE_GRAPH', '1') != '0'
+                                                                else False), 0
                 self._pending = False  # the storage was re-allocated: a deferred update has nothing to apply to
                 self._enqueue_step()  # eager warm-up (also sets the kernels' shared-memory attributes)
+            elif self._bridge is not None and self.use_cuda_graph and self._bridge_graph is not False and \
+                    (self._world == 1 or self._graph_collectives):
+                # the plugin's module inside the step's CUDA graph (forward x3, autograd backward): tried after a few
+                # eager steps (cuDNN plans, lazy initialisation); a module that synchronises or branches on device
+                # data cannot be captured — the step then stays eager for good
+                self._bridge_eager_steps += 1
+                if self._bridge_graph is None and self._bridge_eager_steps >= 3:
+                    try:
+                        torch.cuda.synchronize(self.device)
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                            self._enqueue_step()
+                        self._bridge_graph = graph
+                        self._graphs[0] = graph
+                    except Exception as e:  # noqa: BLE001
+                        self._logger.warning(f'representation module is not CUDA-graph capturable ({type(e).__name__}: '
+                                             f'{str(e).splitlines()[0] if str(e) else ""}); the step runs eagerly')
+                        self._bridge_graph = False
+                        torch.cuda.synchronize(self.device)
+                        self._bridge.zero_grad()
+                        self._enqueue_step()
+                elif self._bridge_graph is None:
+                    self._enqueue_step()
+                if self._bridge_graph:
+                    self._bridge_graph.replay()
             elif self._bridge is not None or not self.use_cuda_graph or \
                     (self._world > 1 and not self._graph_collectives):
                 self._enqueue_step()
