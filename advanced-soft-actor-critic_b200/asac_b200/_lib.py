@@ -16,6 +16,7 @@ LIB_PATH = Path(os.environ['ASAC_B200_LIB']) if os.environ.get('ASAC_B200_LIB') 
 CSRC_DIR = PKG_DIR / 'csrc'
 
 MAX_COLUMNS = 16
+MAX_BRANCHES = 8
 MAX_NSTEP = 16
 MAX_DEPTH = 4
 MAX_ENSEMBLE = 8
@@ -87,6 +88,12 @@ class AsacSacWork(C.Structure):
 GRU_MAX_LAYERS = 4
 
 
+class AsacDiscreteConfig(C.Structure):
+    _fields_ = [('branches', C.c_int32), ('sizes', C.c_int32 * MAX_BRANCHES), ('hidden', C.c_int32),
+                ('depth', C.c_int32), ('state_size', C.c_int32), ('target_d_alpha', C.c_float),
+                ('entropy_penalty', C.c_float)]
+
+
 class AsacGruShape(C.Structure):
     _fields_ = [('obs_size', C.c_int32), ('action_size', C.c_int32), ('hidden', C.c_int32), ('layers', C.c_int32)]
 
@@ -130,6 +137,17 @@ PROTOTYPES = {
     'asac_sac_tile_batch': (i32, [P(AsacSacConfig)]),
     'asac_mlp_param_count': (i64, [i32, i32, i32, i32]),
     'asac_mlp_param_stride': (i64, [i32, i32, i32, i32]),
+    'asac_dnets_member_floats': (i64, [P(AsacDiscreteConfig)]),
+    'asac_dnets_tiles': (i32, [i32]),
+    'asac_dnets_forward': (i32, [P(AsacDiscreteConfig), vp, i64, i32, vp, i64, i32, vp, vp]),
+    'asac_dnets_backward': (i32, [P(AsacDiscreteConfig), vp, i64, i32, vp, i64, i32, vp, vp, vp]),
+    'asac_d_target': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'asac_d_q_grad': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, f32, vp, vp, vp, vp]),
+    'asac_d_pi_grad': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    'asac_d_probs': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp]),
+    'asac_d_alpha': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, vp, f32, vp, vp, vp]),
+    'asac_d_td': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, i32, vp]),
+    'asac_bump_counters': (i32, [vp, i32, vp]),
     'asac_sac_value_pass_on_tc': (i32, [P(AsacSacConfig), i32]),
     'asac_sac_polyak': (i32, [P(AsacSacConfig), P(AsacSacParams), f32, vp]),
     'asac_sac_target_y': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork), vp]),

@@ -1290,6 +1290,8 @@ __global__ void __launch_bounds__(NT) k_mlp_forward(const MlpArgs a) {
     for (int i = tid; i < rows * s.out_dim; i += NT) a.out[r0 * s.out_dim + i] = ho[i];
 }
 
+#include "sac_discrete.cuh"  // discrete / hybrid action branches
+
 }  // namespace asac
 
 using namespace asac;
@@ -1910,5 +1912,187 @@ extern "C" int asac_debug_phase_clocks(int64_t *out_host) {
     ASAC_CUDA(cudaMemcpyFromSymbol(seg, g_layer_seg, sizeof(seg)));
     ASAC_CUDA(cudaMemcpyToSymbol(g_layer_seg, zero8, sizeof(zero8)));
     for (int i = 0; i < 5; ++i) out_host[32 + 20 + i] = seg[i];
+    return ASAC_OK;
+}
+
+// ------------------------------------------------------------------------------------ discrete action branches
+static int fill_dnets(DNets &n, const AsacDiscreteConfig *d, const float *params, int64_t member_stride, int members) {
+    ASAC_REQUIRE(d && params && members >= 1 && members <= ASAC_MAX_ENSEMBLE, "discrete nets: bad arguments");
+    ASAC_UNSUPPORTED(d->branches < 1 || d->branches > ASAC_MAX_BRANCHES, "%d discrete action branches (1..%d)", d->branches,
+                     ASAC_MAX_BRANCHES);
+    ASAC_UNSUPPORTED(!(d->hidden == 16 || d->hidden == 32 || d->hidden == 64 || d->hidden == 128),
+                     "d_dense_n %d not in {16, 32, 64, 128}", d->hidden);
+    ASAC_UNSUPPORTED(d->depth < 1 || d->depth > ASAC_MAX_DEPTH, "d_dense_depth %d outside [1, %d]", d->depth, ASAC_MAX_DEPTH);
+    ASAC_REQUIRE(d->state_size > 0, "discrete nets: state_size");
+    memset(&n, 0, sizeof(n));
+    n.params = params; n.member_stride = member_stride; n.members = members; n.branches = d->branches;
+    n.S = d->state_size; n.H = d->hidden; n.depth = d->depth;
+    int64_t off = 0;
+    int col = 0;
+    for (int k = 0; k < d->branches; ++k) {
+        ASAC_REQUIRE(d->sizes[k] >= 1, "discrete branch %d has size %d", k, d->sizes[k]);
+        n.sizes[k] = d->sizes[k];
+        n.branch_off[k] = off;
+        n.col_off[k] = col;
+        off += net_stride(NetShape{n.S, n.H, n.depth, d->sizes[k]});
+        col += d->sizes[k];
+    }
+    n.D = col;
+    ASAC_UNSUPPORTED(col > D_MAX_COLS, "%d discrete action columns > %d", col, D_MAX_COLS);
+    return ASAC_OK;
+}
+
+extern "C" int64_t asac_dnets_member_floats(const AsacDiscreteConfig *d) {
+    if (!d) return 0;
+    int64_t off = 0;
+    for (int k = 0; k < d->branches && k < ASAC_MAX_BRANCHES; ++k)
+        off += net_stride(NetShape{d->state_size, d->hidden, d->depth, d->sizes[k]});
+    return off;
+}
+
+extern "C" int asac_dnets_tiles(int rows) { return (rows + PASS_ROWS - 1) / PASS_ROWS; }
+
+extern "C" int asac_dnets_forward(const AsacDiscreteConfig *d, const float *params, int64_t member_stride, int members,
+                                  const float *x, int64_t x_row_stride, int rows, float *out, void *stream) {
+    DFwdArgs a;
+    int rc = fill_dnets(a.nets, d, params, member_stride, members);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(x && out && rows > 0 && x_row_stride >= d->state_size, "asac_dnets_forward: bad arguments");
+    a.x = x; a.x_row_stride = x_row_stride; a.rows = rows; a.out = out;
+    const int bytes = dfwd_plan(a.nets.S, a.nets.H, a.nets.depth, D_MAX_COLS).total * 4;
+    rc = set_smem(k_dnets_forward, bytes, "k_dnets_forward");
+    if (rc != ASAC_OK) return rc;
+    k_dnets_forward<<<dim3(asac_dnets_tiles(rows), members * d->branches), NT, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_dnets_forward");
+    return ASAC_OK;
+}
+
+extern "C" int asac_dnets_backward(const AsacDiscreteConfig *d, const float *params, int64_t member_stride, int members,
+                                   const float *x, int64_t x_row_stride, int rows, const float *d_out, float *grad_part,
+                                   void *stream) {
+    DBwdArgs a;
+    int rc = fill_dnets(a.nets, d, params, member_stride, members);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(x && d_out && grad_part && rows > 0 && x_row_stride >= d->state_size, "asac_dnets_backward: bad arguments");
+    a.x = x; a.x_row_stride = x_row_stride; a.rows = rows; a.d_out = d_out; a.grad_part = grad_part;
+    a.member_floats = asac_dnets_member_floats(d);
+    const int bytes = dbwd_plan(a.nets.S, a.nets.H, a.nets.depth, D_MAX_COLS).total * 4;
+    rc = set_smem(k_dnets_backward, bytes, "k_dnets_backward");
+    if (rc != ASAC_OK) return rc;
+    k_dnets_backward<<<dim3(asac_dnets_tiles(rows), members * d->branches), NT, bytes, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_dnets_backward");
+    return ASAC_OK;
+}
+
+static int d_sizes(const AsacDiscreteConfig *d, int *sizes, int &D) {
+    ASAC_REQUIRE(d && d->branches >= 1 && d->branches <= ASAC_MAX_BRANCHES, "discrete config: branches");
+    D = 0;
+    for (int k = 0; k < ASAC_MAX_BRANCHES; ++k) {
+        sizes[k] = k < d->branches ? d->sizes[k] : 0;
+        D += sizes[k];
+    }
+    ASAC_UNSUPPORTED(D > D_MAX_COLS, "%d discrete action columns > %d", D, D_MAX_COLS);
+    return ASAC_OK;
+}
+
+extern "C" int asac_d_target(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *pi_logits, const float *tq,
+                             const float *actions_full, const float *mu_full, const float *pi_probs_d,
+                             const float *rewards, const uint8_t *dones, const uint8_t *last_masks,
+                             const uint8_t *padding_masks, const float *log_d_alpha, float *d_y, void *stream) {
+    DTargetArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = d_sizes(d, a.sizes, a.D);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(cfg && pi_logits && tq && actions_full && rewards && dones && last_masks && padding_masks && log_d_alpha && d_y,
+                 "asac_d_target: null pointer");
+    ASAC_REQUIRE(!cfg->use_n_step_is || mu_full || pi_probs_d, "asac_d_target: use_n_step_is needs mu probabilities");
+    ASAC_UNSUPPORTED(cfg->n_step > ASAC_MAX_NSTEP, "n_step %d > %d", cfg->n_step, ASAC_MAX_NSTEP);
+    a.cfg = *cfg; a.branches = d->branches; a.AF = a.D + cfg->action_size;
+    a.pi_logits = pi_logits; a.tq = tq; a.actions_full = actions_full; a.mu_full = mu_full; a.pi_probs_d = pi_probs_d;
+    a.rewards = rewards; a.dones = dones; a.last_masks = last_masks; a.padding_masks = padding_masks;
+    a.log_d_alpha = log_d_alpha; a.post = pi_probs_d ? 1 : 0; a.d_y = d_y;
+    k_d_target<<<(cfg->batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_d_target");
+    return ASAC_OK;
+}
+
+extern "C" int asac_d_q_grad(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *q, const float *actions_full,
+                             const float *d_y, const float *weights, float scale, float *d_out, float *loss, float *q_single,
+                             void *stream) {
+    int sizes[ASAC_MAX_BRANCHES], D;
+    int rc = d_sizes(d, sizes, D);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(cfg && q && actions_full && d_y && d_out && loss && q_single, "asac_d_q_grad: null pointer");
+    DQGradArgs a{cfg->batch, cfg->seq_len, cfg->burn_in, cfg->ensemble, d->branches, D, D + cfg->action_size,
+                 q, actions_full, d_y, weights, scale, d_out, loss, q_single};
+    k_d_q_grad<<<(cfg->ensemble * cfg->batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_d_q_grad");
+    return ASAC_OK;
+}
+
+extern "C" int asac_d_pi_grad(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *logits, int stride_rows,
+                              int row_off, const float *q, const float *mu_full, const float *log_d_alpha, float *d_out,
+                              float *loss, float *entropy, void *stream) {
+    DPiGradArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = d_sizes(d, a.sizes, a.D);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(cfg && logits && q && mu_full && log_d_alpha && d_out && loss && entropy, "asac_d_pi_grad: null pointer");
+    a.B = cfg->batch; a.L = cfg->seq_len; a.b = cfg->burn_in; a.E = cfg->ensemble; a.branches = d->branches;
+    a.AF = a.D + cfg->action_size; a.stride_rows = stride_rows; a.row_off = row_off;
+    a.logits = logits; a.q = q; a.mu_full = mu_full; a.log_d_alpha = log_d_alpha; a.penalty = d->entropy_penalty;
+    a.d_out = d_out; a.loss = loss; a.entropy = entropy;
+    k_d_pi_grad<<<(cfg->batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_d_pi_grad");
+    return ASAC_OK;
+}
+
+extern "C" int asac_d_probs(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *logits, float *pi_probs_d,
+                            float *pi_probs_full, void *stream) {
+    DPostArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = d_sizes(d, a.sizes, a.D);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(cfg && logits && pi_probs_d, "asac_d_probs: null pointer");
+    a.B = cfg->batch; a.L = cfg->seq_len; a.b = cfg->burn_in; a.E = cfg->ensemble; a.branches = d->branches;
+    a.AF = a.D + cfg->action_size; a.logits = logits; a.pi_probs_d = pi_probs_d; a.pi_probs_full = pi_probs_full;
+    k_d_probs<<<(cfg->batch * (cfg->seq_len - 1) + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_d_probs");
+    return ASAC_OK;
+}
+
+extern "C" int asac_d_alpha(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *logits, float *log_d_alpha,
+                            float *m, float *v, const int64_t *step, float grad_scale, float *grad_out, float *loss_out,
+                            void *stream) {
+    DAlphaArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = d_sizes(d, a.sizes, a.D);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(cfg && logits && log_d_alpha && m && v && step && grad_out && loss_out, "asac_d_alpha: null pointer");
+    a.B = cfg->batch; a.L = cfg->seq_len; a.b = cfg->burn_in; a.branches = d->branches;
+    a.target_ratio = d->target_d_alpha; a.logits = logits; a.log_d_alpha = log_d_alpha; a.m = m; a.v = v; a.step = step;
+    a.lr = cfg->learning_rate; a.grad_scale = grad_scale; a.grad_out = grad_out; a.loss_out = loss_out;
+    k_d_alpha<<<1, NT, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_d_alpha");
+    return ASAC_OK;
+}
+
+extern "C" int asac_d_td(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *q, const float *actions_full,
+                         const float *d_y, float *td_error, int accumulate, void *stream) {
+    int sizes[ASAC_MAX_BRANCHES], D;
+    int rc = d_sizes(d, sizes, D);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(cfg && q && actions_full && d_y && td_error, "asac_d_td: null pointer");
+    DTdArgs a{cfg->batch, cfg->seq_len, cfg->burn_in, cfg->ensemble, d->branches, D, D + cfg->action_size, accumulate,
+              q, actions_full, d_y, td_error};
+    k_d_td<<<(cfg->batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_d_td");
+    return ASAC_OK;
+}
+
+extern "C" int asac_bump_counters(int64_t *counters, int mask, void *stream) {
+    ASAC_REQUIRE(counters, "asac_bump_counters: null pointer");
+    k_bump<<<1, 32, 0, (cudaStream_t)stream>>>(counters, mask);
+    ASAC_LAUNCHED("k_bump");
     return ASAC_OK;
 }

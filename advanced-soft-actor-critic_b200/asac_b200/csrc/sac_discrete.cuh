@@ -406,7 +406,7 @@ struct DAlphaArgs {
     float *grad_out, *loss_out;
 };
 // _train_alpha, discrete part (sac_base.py:1924-1929) + torch.optim.Adam on log_d_alpha; one CTA
-__global__ void __launch_bounds__(1024) k_d_alpha(const DAlphaArgs a) {
+__global__ void __launch_bounds__(NT) k_d_alpha(const DAlphaArgs a) {  // NT threads: block_sum's contract
     __shared__ float red[32];
     float acc = 0.f;
     for (int e = threadIdx.x; e < a.B; e += blockDim.x) {

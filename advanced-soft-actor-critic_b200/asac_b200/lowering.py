@@ -78,31 +78,56 @@ def _trunk_blocks(layers: m.LinearLayers, what: str) -> tuple[list[m.ResBlock], 
     return blocks, head
 
 
-def analyze_q(q: nn.Module) -> tuple[NetShape, list[nn.Parameter]]:
-    """-> (shape, parameters in flat order).  Raises NotStockNetwork otherwise."""
+def analyze_d_heads(mod: nn.Module, what: str) -> tuple[list[NetShape], list[list[nn.Parameter]]]:
+    """The discrete-action heads of a stock ModelQ / ModelPolicy (q.py:60-64, policy.py:143-147): one
+    ``LinearLayers(state -> d_dense_n x d_dense_depth -> d_action_size_k)`` per branch.
+    -> (shape per branch, parameters per branch in flat order)."""
+    shapes, params = [], []
+    for k, layers in enumerate(mod.d_dense_list):
+        blocks, head = _trunk_blocks(layers, f'{what}.d_dense_list[{k}]')
+        if head is None or head.out_features != mod.d_action_sizes[k]:
+            raise NotStockNetwork(f'{what}.d_dense_list[{k}] has no output layer of size {mod.d_action_sizes[k]}')
+        shapes.append(NetShape(blocks[0].linear.in_features, blocks[0].linear.out_features, len(blocks), head.out_features))
+        params.append([p for b in blocks for p in (b.linear.weight, b.linear.bias)] + [head.weight, head.bias])
+    if len({(s.in_dim, s.hidden, s.depth) for s in shapes}) != 1:
+        raise NotStockNetwork(f'{what}: discrete heads of unequal width / depth')
+    return shapes, params
+
+
+def analyze_q(q: nn.Module) -> tuple[NetShape | None, list[nn.Parameter]]:
+    """-> (shape, parameters in flat order) of the continuous critic (None, [] without continuous actions).
+    Discrete heads are lowered separately (``analyze_d_heads``).  Raises NotStockNetwork otherwise."""
     if not isinstance(q, m.ModelQ) or type(q).forward is not m.ModelQ.forward:
         raise NotStockNetwork('ModelQ overrides forward')
-    if q.d_action_sizes or not q.c_action_size:
-        raise NotStockNetwork('only continuous-action critics are lowered')
-    if not (_no_params(q.dense) and _no_params(q.c_state_dense) and _no_params(q.c_action_dense)):
+    n_d = sum(p.numel() for p in q.d_dense_list.parameters()) if q.d_action_sizes else 0
+    if not _no_params(q.dense):
+        raise NotStockNetwork('ModelQ with a shared dense trunk')
+    if not q.c_action_size:
+        if sum(p.numel() for p in q.parameters()) != n_d:
+            raise NotStockNetwork('ModelQ has parameters outside d_dense_list')
+        return None, []
+    if not (_no_params(q.c_state_dense) and _no_params(q.c_action_dense)):
         raise NotStockNetwork('ModelQ with dense / c_state_dense / c_action_dense layers')
     blocks, head = _trunk_blocks(q.c_dense, 'ModelQ.c_dense')
     if head is None or head.out_features != 1:
         raise NotStockNetwork('ModelQ.c_dense has no scalar output layer')
     shape = NetShape(blocks[0].linear.in_features, blocks[0].linear.out_features, len(blocks), 1)
     params = [p for b in blocks for p in (b.linear.weight, b.linear.bias)] + [head.weight, head.bias]
-    if sum(p.numel() for p in q.parameters()) != shape.count:
-        raise NotStockNetwork('ModelQ has parameters outside c_dense')
+    if sum(p.numel() for p in q.parameters()) != shape.count + n_d:
+        raise NotStockNetwork('ModelQ has parameters outside c_dense / d_dense_list')
     return shape, params
 
 
-def analyze_policy(pi: nn.Module) -> tuple[NetShape, list[nn.Parameter]]:
+def analyze_policy(pi: nn.Module) -> tuple[NetShape | None, list[nn.Parameter]]:
     if not isinstance(pi, m.ModelPolicy) or type(pi).forward is not m.ModelPolicy.forward:
         raise NotStockNetwork('ModelPolicy overrides forward')
-    if pi.d_action_sizes or not pi.c_action_size:
-        raise NotStockNetwork('only continuous-action policies are lowered')
+    n_d = sum(p.numel() for p in pi.d_dense_list.parameters()) if pi.d_action_sizes else 0
     if not _no_params(pi.dense):
         raise NotStockNetwork('ModelPolicy with a shared dense trunk')
+    if not pi.c_action_size:
+        if sum(p.numel() for p in pi.parameters()) != n_d:
+            raise NotStockNetwork('ModelPolicy has parameters outside d_dense_list')
+        return None, []
     blocks, head = _trunk_blocks(pi.c_dense, 'ModelPolicy.c_dense')
     if head is not None:
         raise NotStockNetwork('ModelPolicy.c_dense has an output layer')
@@ -117,8 +142,8 @@ def analyze_policy(pi: nn.Module) -> tuple[NetShape, list[nn.Parameter]]:
     # flat order: trunk, then head weight rows [mean; logstd], then head bias [mean; logstd]
     params = [p for b in blocks for p in (b.linear.weight, b.linear.bias)]
     params += [heads[0].weight, heads[1].weight, heads[0].bias, heads[1].bias]
-    if sum(p.numel() for p in pi.parameters()) != shape.count:
-        raise NotStockNetwork('ModelPolicy has parameters outside c_dense / mean_dense / logstd_dense')
+    if sum(p.numel() for p in pi.parameters()) != shape.count + n_d:
+        raise NotStockNetwork('ModelPolicy has parameters outside c_dense / mean_dense / logstd_dense / d_dense_list')
     return shape, params
 
 

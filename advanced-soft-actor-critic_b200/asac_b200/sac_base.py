@@ -36,15 +36,23 @@ class _FlatAdam:
     """``torch.optim.Adam``-shaped view (``state_dict`` / ``load_state_dict``) of flat moment
     buffers that the CUDA Adam kernel updates (sac_base.py:296-300)."""
 
-    def __init__(self, params: list[torch.nn.Parameter], flat_param: torch.Tensor, m_flat: torch.Tensor,
-                 v_flat: torch.Tensor, counters: torch.Tensor, counter_index: int, lr: float):
+    def __init__(self, params: list[torch.nn.Parameter], flat_param, m_flat: torch.Tensor | None,
+                 v_flat: torch.Tensor | None, counters: torch.Tensor, counter_index: int, lr: float):
+        """``flat_param``: one flat buffer (with ``m_flat`` / ``v_flat``) or a list of (flat, m, v) triples — a module
+        whose parameters live in two buffers (continuous net + discrete heads) still has ONE optimizer."""
         self._params, self._lr = params, lr
         self._counters, self._ci = counters, counter_index
-        base = flat_param.data_ptr()
+        triples = flat_param if isinstance(flat_param, list) else [(flat_param, m_flat, v_flat)]
         self._views = []
         for p in params:
-            off = (p.data_ptr() - base) // 4
-            self._views.append((m_flat[off:off + p.numel()].view(p.shape), v_flat[off:off + p.numel()].view(p.shape)))
+            for flat, mf, vf in triples:
+                off = (p.data_ptr() - flat.data_ptr()) // 4
+                if 0 <= off and off + p.numel() <= flat.numel() and flat.numel() > 0:
+                    mf, vf = mf.reshape(-1), vf.reshape(-1)
+                    self._views.append((mf[off:off + p.numel()].view(p.shape), vf[off:off + p.numel()].view(p.shape)))
+                    break
+            else:
+                raise AssertionError('parameter outside the flat buffers of its optimizer')
 
     def state_dict(self) -> dict:
         step = float(self._counters[self._ci].item())
@@ -188,10 +196,13 @@ class SAC_Base:
         self.use_n_step_is = use_n_step_is
         self.action_noise = action_noise
         self.use_cuda_graph = use_cuda_graph
+        self.discrete_dqn_like = discrete_dqn_like
+        self._init_log_alpha = init_log_alpha
 
         unsupported = {
-            'discrete action branches (d_action_sizes)': bool(d_action_sizes),
-            'c_action_size == 0': not c_action_size,
+            'neither discrete nor continuous actions': not d_action_sizes and not c_action_size,
+            'discrete_dqn_like': bool(d_action_sizes) and bool(discrete_dqn_like),
+            'discrete action branches without a replay buffer': bool(d_action_sizes) and not use_replay_buffer,
             'siamese': siamese is not None,
             'use_prediction': use_prediction,
             'curiosity': curiosity is not None,
@@ -262,11 +273,19 @@ class SAC_Base:
         nn_config = {k: ({} if nn_config.get(k) is None else nn_config[k]) for k in ('rep', 'policy')}
         dev = self.device
         A = self.c_action_size
+        D = self.d_action_summed_size
+        # Discrete-only runs (A == 0) keep the continuous structures of the step at width 1 — buffers and config only,
+        # no continuous kernel is ever launched for them (self._c_enabled) — so that one code path sizes everything.
+        self._c_enabled = A > 0
+        Ae = max(A, 1)
 
         self._gamma_ratio = torch.logspace(0, self.n_step - 1, self.n_step, self.gamma)      # sac_base.py:285
         self._lambda_ratio = torch.logspace(0, self.n_step - 1, self.n_step, self.v_lambda)  # sac_base.py:286
-        self._padding_action = torch.zeros(A, dtype=torch.float32, device=dev)               # sac_base.py:291-294
-        self._np_padding_action = np.zeros(A, dtype=np.float32)
+        # sac_base.py:291-294: first option of every discrete branch, zeros for the continuous part
+        self._np_padding_action = np.concatenate([np.eye(k, dtype=np.float32)[0] for k in self.d_action_sizes] +
+                                                 [np.zeros(A, dtype=np.float32)])
+        self._padding_action_full = torch.from_numpy(self._np_padding_action).to(dev)
+        self._padding_action = torch.zeros(Ae, dtype=torch.float32, device=dev)
 
         self.model_rep = nn.ModelRep(self.obs_names, self.obs_shapes, self.d_action_sizes, A, False,
                                      self.model_abs_dir, **nn_config['rep']).to(dev)
@@ -340,10 +359,13 @@ class SAC_Base:
 
         # ---- lower the stock nets onto flat buffers shared with the kernels
         q_shapes = [lowering.analyze_q(q) for q in self.model_q_list + self.model_target_q_list]
+        self._pi_shape, pi_params = lowering.analyze_policy(self.model_policy)
         self._q_shape = q_shapes[0][0]
         if any(s != self._q_shape for s, _ in q_shapes):
             raise lowering.NotStockNetwork('ensemble members differ in shape')
-        self._pi_shape, pi_params = lowering.analyze_policy(self.model_policy)
+        if not self._c_enabled:  # placeholders for the sizes below; never launched
+            self._q_shape = lowering.NetShape(self.state_size + 1, 64, 1, 1)
+            self._pi_shape = lowering.NetShape(self.state_size, 64, 1, 2)
         Pq, Ppi = self._q_shape.stride, self._pi_shape.stride
         self._q_flat = torch.zeros(E, Pq, **f32)
         self._qt_flat = torch.zeros(E, Pq, **f32)
@@ -354,8 +376,17 @@ class SAC_Base:
         lowering.bind_parameters(pi_params, self._pi_flat)
         self._q_m, self._q_v = torch.zeros_like(self._q_flat), torch.zeros_like(self._q_flat)
         self._pi_m, self._pi_v = torch.zeros_like(self._pi_flat), torch.zeros_like(self._pi_flat)
+        self._disc = None
+        if self.d_action_sizes:
+            if self._gru is not None or self._bridge is not None:
+                raise NotImplementedError('discrete action branches together with a trained representation')
+            if self._world > 1:
+                raise NotImplementedError('discrete action branches in the data-parallel learner')
+            from .discrete import DiscreteBranch
+            self._disc = DiscreteBranch(self, self.model_q_list, self.model_target_q_list, self.model_policy)
 
-        self.log_d_alpha = torch.tensor(init_log_alpha, dtype=torch.float32, device=dev)
+        self.log_d_alpha = self._disc.log_alpha[0] if self._disc is not None else \
+            torch.tensor(init_log_alpha, dtype=torch.float32, device=dev)
         self.log_c_alpha = torch.full((1,), init_log_alpha, **f32)[0]  # 0-dim view of a 1-element buffer
         self._log_alpha_buf = self.log_c_alpha.view(1)
         self._alpha_m, self._alpha_v = torch.zeros(1, **f32), torch.zeros(1, **f32)
@@ -363,20 +394,27 @@ class SAC_Base:
         self._host_step = 0
 
         lr = self.learning_rate
-        self.optimizer_q_list = [_FlatAdam(list(q.parameters()), self._q_flat[i], self._q_m[i], self._q_v[i],
-                                           self._counters, 1, lr) for i, q in enumerate(self.model_q_list)]
-        self.optimizer_policy = _FlatAdam(list(self.model_policy.parameters()), self._pi_flat, self._pi_m, self._pi_v,
+        dq = self._disc
+        flats_q = lambda i: [(self._q_flat[i], self._q_m[i], self._q_v[i])] + \
+            ([(dq.q[i], dq.q_m[i], dq.q_v[i])] if dq is not None else [])
+        self.optimizer_q_list = [_FlatAdam(list(q.parameters()), flats_q(i), None, None, self._counters, 1, lr)
+                                 for i, q in enumerate(self.model_q_list)]
+        self.optimizer_policy = _FlatAdam(list(self.model_policy.parameters()),
+                                          [(self._pi_flat, self._pi_m, self._pi_v)] +
+                                          ([(dq.pi, dq.pi_m, dq.pi_v)] if dq is not None else []), None, None,
                                           self._counters, 2, lr)
         self.optimizer_alpha = None
         if self.use_auto_alpha:
-            self.optimizer_alpha = _AlphaAdam(self._alpha_m, self._alpha_v, self._counters, lr)
+            self.optimizer_alpha = _AlphaAdam(self._alpha_m, self._alpha_v, self._counters, lr,
+                                              d_state=(dq.alpha_m, dq.alpha_v) if dq is not None else None,
+                                              c_enabled=self._c_enabled)
 
         # ---- C structs
         cfg = _lib.AsacSacConfig()
         cfg.learning_rate = float(lr)
         cfg.batch, cfg.burn_in, cfg.n_step = self.batch_size, self.burn_in_step, self.n_step
         cfg.seq_len = self.burn_in_step + self.n_step + 1
-        cfg.state_size, cfg.action_size, cfg.ensemble = self.state_size, A, E
+        cfg.state_size, cfg.action_size, cfg.ensemble = self.state_size, Ae, E
         cfg.q_hidden, cfg.q_depth = self._q_shape.hidden, self._q_shape.depth
         cfg.pi_hidden, cfg.pi_depth = self._pi_shape.hidden, self._pi_shape.depth
         cfg.use_n_step_is, cfg.use_priority = int(self.use_n_step_is), int(self.use_priority)
@@ -394,6 +432,8 @@ class SAC_Base:
             cfg.gamma_ratio[k] = float(self._gamma_ratio[k])
             cfg.lambda_ratio[k] = float(self._lambda_ratio[k])
         self._cfg = cfg
+        self._cfg_d = _lib.AsacSacConfig.from_buffer_copy(cfg)  # what the discrete kernels see: the true action width
+        self._cfg_d.action_size = A
         tile = self._lib.asac_sac_tile_batch(C.byref(cfg))
         if tile < 1:
             check(tile, 'asac_sac_tile_batch')
@@ -507,7 +547,7 @@ class SAC_Base:
 
     def _build_step_buffers(self) -> None:
         """Persistent device buffers of one train() call (static addresses -> CUDA graph)."""
-        B, L, S, A, E = self.batch_size, self._cfg.seq_len, self.state_size, self.c_action_size, self.ensemble_q_num
+        B, L, S, A, E = self.batch_size, self._cfg.seq_len, self.state_size, self._cfg.action_size, self.ensemble_q_num
         n, T = self.n_step, self._n_tiles
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -523,6 +563,8 @@ class SAC_Base:
         }
         if self._gru is not None or self._bridge is not None:
             wk['grad_state'] = torch.zeros(E, B, S, **f32)
+        if self._disc is not None:
+            wk['pi_probs_full'] = torch.ones(B, L - 1, self._disc.AF, **f32)
         work = _lib.AsacSacWork()
         work.n_tiles = T
         for k, t in wk.items():
@@ -543,7 +585,7 @@ class SAC_Base:
         # at them).  Two sets: while the networks train on one, the NEXT step's sample + gather fill the
         # other on a parallel branch (ASAC_SAMPLE_AHEAD=0: one set, sample and gather on the critical path).
         self._sample_ahead = self.use_replay_buffer and os.environ.get('ASAC_SAMPLE_AHEAD', '1') != '0' \
-            and self._bridge is None  # (the bridged step runs eagerly, in program order)
+            and self._bridge is None and self._disc is None  # (those steps run in program order on one stream)
         self._sets = [self._make_batch_set() for _ in range(2 if self._sample_ahead else 1)]
         self._cur, self._primed = 0, False
         # With sampling one step ahead the tree update of step N is only needed by the sample of step N + 2:
@@ -592,7 +634,7 @@ class SAC_Base:
         self._ready_version = None  # replay version for which every rank was seen ready to step
 
     def _make_batch_set(self) -> dict:
-        B, L, S, A = self.batch_size, self._cfg.seq_len, self.state_size, self.c_action_size
+        B, L, S, A = self.batch_size, self._cfg.seq_len, self.state_size, self._cfg.action_size
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
         u8 = dict(dtype=torch.uint8, device=dev)
@@ -603,6 +645,9 @@ class SAC_Base:
             'last_masks': torch.zeros(B, L, **u8), 'padding_masks': torch.zeros(B, L, **u8),
             'mu_probs': torch.zeros(B, L, A, **f32),
         }
+        if self._disc is not None:
+            bt['actions_full'] = torch.zeros(B, L, self._disc.AF, **f32)
+            bt['mu_full'] = torch.zeros(B, L, self._disc.AF, **f32)
         smp = {'slots': torch.zeros(B, dtype=torch.int32, device=dev), 'ids': torch.zeros(B, dtype=torch.int64, device=dev),
                'p': torch.zeros(B, **f32), 'w': torch.zeros(B, **f32)}
         batch = _lib.AsacSacBatch()
@@ -701,6 +746,12 @@ class SAC_Base:
         with torch.cuda.device(self.device):
             check(self._lib.asac_sac_polyak(C.byref(self._cfg), C.byref(self._prm), float(tau),
                                             _lib.current_stream()), 'sac_polyak')
+            if self._disc is not None:
+                self._disc.polyak(force_tau=float(tau))
+            if self._bridge is not None:
+                check(self._lib.asac_flat_polyak(ptr(self._rept_flat), ptr(self._rep_flat), self._bridge.count, None, 1,
+                                                 float(tau), float(np.float32(1. - tau)), 1, _lib.current_stream()),
+                      'flat_polyak')
             if self._gru is not None:
                 check(self._lib.asac_flat_polyak(ptr(self._rept_flat), ptr(self._rep_flat), self._gru.count, None, 1,
                                                  float(tau), float(np.float32(1. - tau)), 1, _lib.current_stream()),
@@ -799,7 +850,7 @@ class SAC_Base:
         opt-in because the probability amplifies the 1.5e-6 error of the pre-activations by |x - mu| / sigma^2.
         ``eps`` ([batch, A] N(0,1) draws) replaces the on-device Philox draws (tests).
         Host traffic: one pinned staging block in, one out (``_actor_io``)."""
-        if self.action_noise is not None or self._bridge is not None:
+        if self.action_noise is not None or self._bridge is not None or self._disc is not None:
             return self._choose_action_torch(obs_list, pre_action, pre_seq_hidden_state, offline_action,
                                              disable_sample)
         with torch.cuda.device(self.device):
@@ -925,23 +976,38 @@ class SAC_Base:
         else:
             state, hidden = self.model_rep([o.unsqueeze(1) for o in obs], None, None)
         state, hidden = state.squeeze(1), hidden.squeeze(1)
-        _, c_policy = self.model_policy(state, obs)
-        if offline_action is not None:
-            c_action = torch.from_numpy(offline_action).to(self.device)
-        elif disable_sample:
-            c_action = torch.tanh(c_policy.mean)
-        elif eps is not None:
-            c_action = torch.tanh(c_policy.mean + c_policy.stddev * torch.as_tensor(eps, device=self.device))
-        else:
-            c_action = torch.tanh(c_policy.sample())
-        if self.action_noise is not None:  # sac_base.py:859-880
-            batch = c_action.shape[0]
-            noise = torch.linspace(*self.action_noise, steps=batch, device=self.device)
-            c_action = torch.tanh(torch.atanh(c_action) + torch.randn(batch, self.c_action_size, device=self.device)
-                                  * noise.unsqueeze(1))
-        x = torch.atanh(torch.clamp(c_action, -0.999, 0.999))
-        floor = torch.clamp_min(1 - torch.tanh(x) ** 2, 1e-2)
-        prob = torch.exp(c_policy.log_prob(x)) / floor.prod(-1, keepdim=True)  # operators.py:17-19
+        d_policy, c_policy = self.model_policy(state, obs)
+        D = self.d_action_summed_size
+        offline = None if offline_action is None else torch.as_tensor(offline_action, dtype=torch.float32).to(self.device)
+        actions, probs = [], []
+        if self.d_action_sizes:  # sac_base.py:901-936, 954-956 (policy branch; the DQN-like one is not supported)
+            if offline is not None:
+                d_action = offline[..., :D]
+            elif disable_sample:
+                d_action = d_policy.sample_deter().float()
+            else:
+                d_action = d_policy.sample()
+            actions.append(d_action)
+            probs.append(d_policy.probs)
+        if self.c_action_size:
+            if offline is not None:
+                c_action = offline[..., D:]
+            elif disable_sample:
+                c_action = torch.tanh(c_policy.mean)
+            elif eps is not None:
+                c_action = torch.tanh(c_policy.mean + c_policy.stddev * torch.as_tensor(eps, device=self.device))
+            else:
+                c_action = torch.tanh(c_policy.sample())
+            if self.action_noise is not None:  # sac_base.py:859-880
+                batch = c_action.shape[0]
+                noise = torch.linspace(*self.action_noise, steps=batch, device=self.device)
+                c_action = torch.tanh(torch.atanh(c_action) + torch.randn(batch, self.c_action_size, device=self.device)
+                                      * noise.unsqueeze(1))
+            x = torch.atanh(torch.clamp(c_action, -0.999, 0.999))
+            floor = torch.clamp_min(1 - torch.tanh(x) ** 2, 1e-2)
+            actions.append(c_action)
+            probs.append(torch.exp(c_policy.log_prob(x)) / floor.prod(-1, keepdim=True))  # operators.py:17-19
+        c_action, prob = torch.cat(actions, dim=-1), torch.cat(probs, dim=-1)
         return c_action.cpu().numpy(), prob.cpu().numpy(), hidden.cpu().numpy()
 
     # ------------------------------------------------------------------ ingest
@@ -975,12 +1041,14 @@ class SAC_Base:
     def _gather_specs(self, bt: dict):
         rb = self.replay_buffer
         S, A = self.state_size, self.c_action_size
+        if self._disc is not None:  # stored rows are [one-hot per branch ..., continuous ...]: gathered whole, split after
+            A = self._disc.AF
         specs = [('index', bt['index'], 4, 0, _lib.ROLE_INDEX),
                  ('last_mask', bt['last_masks'], 1, 0, _lib.ROLE_COPY),
-                 ('action', bt['actions'], 4 * A, 0, _lib.ROLE_ACTION),
+                 ('action', bt['actions_full' if self._disc is not None else 'actions'], 4 * A, 0, _lib.ROLE_ACTION),
                  ('reward', bt['rewards'], 4, 0, _lib.ROLE_REWARD),
                  ('done', bt['dones'], 1, 0, _lib.ROLE_DONE),
-                 ('mu_prob', bt['mu_probs'], 4 * A, 0, _lib.ROLE_MU_PROB)]
+                 ('mu_prob', bt['mu_full' if self._disc is not None else 'mu_probs'], 4 * A, 0, _lib.ROLE_MU_PROB)]
         off = 0
         if self._gru is not None:  # the representation reads obs_list[0] and the stored hidden state of the first row
             name, g = self.obs_names[0], self._gru
@@ -1036,6 +1104,13 @@ class SAC_Base:
             check(lib.asac_per_shard_weights(ptr(rb._nodes), self.batch_size, ptr(smp['p']), ptr(rb._per_state),
                                              ptr(self._min_prob), ptr(smp['w']), _lib.current_stream()),
                   'per_shard_weights')
+        if self._disc is not None:
+            rb._gather(smp['ids'], st['specs'], self._padding_action_full, st['bt']['padding_masks'])
+            if self._c_enabled:  # the continuous kernels read their own columns
+                D = self._disc.D
+                st['bt']['actions'].copy_(st['bt']['actions_full'][..., D:])
+                st['bt']['mu_probs'].copy_(st['bt']['mu_full'][..., D:])
+            return
         rb._gather(smp['ids'], st['specs'], self._padding_action, st['bt']['padding_masks'])
 
     def _enqueue_tree_update(self, st: dict) -> None:
@@ -1059,6 +1134,8 @@ class SAC_Base:
         """One train() on the device, eagerly: picks the batch sets, primes the first batch when needed."""
         if self._bridge is not None:
             return self._enqueue_step_bridge()
+        if self._disc is not None:
+            return self._enqueue_step_discrete()
         cur = (1 - self._cur) if (self._sample_ahead and self._primed) else self._cur
         if self._sample_ahead and not self._primed:
             self._enqueue_sample(self._sets[cur])
@@ -1163,6 +1240,71 @@ class SAC_Base:
                       'per_update')
         if self.use_n_step_is or rep_c is not None:
             main.wait_stream(side)
+
+    def _enqueue_step_discrete(self) -> None:
+        """One train() with discrete (or hybrid) action branches: the discrete stages of asac_b200/discrete.py
+        interleaved with the staged continuous kernels in the reference's order (sac_base.py:2057-2116, 2556-2605)."""
+        rb, st = self.replay_buffer, self._sets[self._cur]
+        self._enqueue_sample(st)
+        self._enqueue_noise(st, 0)
+        self._discrete_step_networks(st)
+        if self.use_priority:
+            self._enqueue_tree_update(st)
+        if self.use_n_step_is:  # sac_base.py:2598-2605: [discrete probabilities, continuous densities] per row
+            rb.write_back(st['smp']['ids'], 'mu_prob', self._wk['pi_probs_full'], -self.burn_in_step,
+                          st['bt']['padding_masks'])
+
+    def _discrete_step_networks(self, st: dict) -> None:
+        lib, dq, wk, bt = self._lib, self._disc, self._wk, st['bt']
+        cfg, prm, batch, work = C.byref(self._cfg), C.byref(self._prm), C.byref(st['batch']), C.byref(self._work)
+        stream = _lib.current_stream()
+        c = self._c_enabled
+        states = bt['states']
+        bump = lambda mask: check(lib.asac_bump_counters(ptr(self._counters), mask, stream), 'bump_counters')
+        # _update_target_variables
+        if c:
+            check(lib.asac_sac_polyak(cfg, prm, -1.0, stream), 'polyak')
+        dq.polyak()
+        # _train_rep_q: y of both parts, ONE loss per critic, one Adam step per ModelQ
+        dq.stage_target(st, states, states, post=False)
+        if c:
+            check(lib.asac_sac_target_y(cfg, prm, batch, work, stream), 'target_y')
+            check(lib.asac_sac_q_backward(cfg, prm, batch, work, stream), 'q_backward')
+            check(lib.asac_sac_reduce_grads(cfg, work, 0, stream), 'reduce_grads')
+        # `loss += loss + mse` (sac_base.py:1562): without the clipped loss the reference counts the discrete part twice
+        dq.stage_q(st, states, 2.0 if (c and self.clip_epsilon <= 0) else 1.0)
+        dq.adam_q()  # same optimizer as the continuous part: reads the step counter before it advances
+        if c:
+            check(lib.asac_sac_adam(cfg, prm, work, 0, 1.0, stream), 'adam')
+        else:
+            bump(2)
+        # _train_policy
+        if c:
+            check(lib.asac_sac_policy_backward(cfg, prm, batch, work, stream), 'policy_backward')
+            check(lib.asac_sac_reduce_grads(cfg, work, 1, stream), 'reduce_grads')
+        dq.stage_pi(st, states)
+        dq.adam_pi()
+        if c:
+            check(lib.asac_sac_adam(cfg, prm, work, 1, 1.0, stream), 'adam')
+        else:
+            bump(4)
+        # _train_alpha, get_l_probs, _get_td_error
+        need_post = self.use_auto_alpha or self.use_n_step_is or self.use_priority
+        if c and need_post:
+            check(lib.asac_sac_post(cfg, prm, batch, work, stream), 'post')
+        dq.stage_alpha(st, states)
+        if self.use_auto_alpha:
+            if c:
+                check(lib.asac_sac_reduce_grads(cfg, work, 2, stream), 'reduce_grads')
+                check(lib.asac_sac_adam(cfg, prm, work, 2, 1.0, stream), 'adam')
+            else:
+                bump(8)
+        if c and need_post:
+            check(lib.asac_sac_td_error(cfg, prm, work, stream), 'td_error')
+            if self.use_n_step_is:
+                wk['pi_probs_full'][..., dq.D:].copy_(wk['pi_probs'])
+        dq.stage_probs_td(st, states, states, states, accumulate_td=c)
+        check(lib.asac_sac_advance_step(prm, stream), 'advance_step')
 
     def _enqueue_step_bridge(self) -> None:
         """One train() with a representation that runs as the plugin's torch module (rep_bridge.py): the
@@ -1334,8 +1476,9 @@ class SAC_Base:
                                                                 else False), 0
                 self._pending = False  # the storage was re-allocated: a deferred update has nothing to apply to
                 self._enqueue_step()  # eager warm-up (also sets the kernels' shared-memory attributes)
-            elif self._bridge is not None and self.use_cuda_graph and self._bridge_graph is not False and \
-                    (self._world == 1 or self._graph_collectives):
+            elif (self._bridge is not None or self._disc is not None) and self.use_cuda_graph and \
+                    self._bridge_graph is not False and (self._world == 1 or self._graph_collectives):
+                # (also the discrete / hybrid step: one stream, program order, captured whole)
                 # the plugin's module inside the step's CUDA graph (forward x3, autograd backward): tried after a few
                 # eager steps (cuDNN plans, lazy initialisation); a module that synchronises or branches on device
                 # data cannot be captured — the step then stays eager for good
@@ -1353,13 +1496,14 @@ class SAC_Base:
                                              f'{str(e).splitlines()[0] if str(e) else ""}); the step runs eagerly')
                         self._bridge_graph = False
                         torch.cuda.synchronize(self.device)
-                        self._bridge.zero_grad()
+                        if self._bridge is not None:
+                            self._bridge.zero_grad()
                         self._enqueue_step()
                 elif self._bridge_graph is None:
                     self._enqueue_step()
                 if self._bridge_graph:
                     self._bridge_graph.replay()
-            elif self._bridge is not None or not self.use_cuda_graph or \
+            elif self._bridge is not None or self._disc is not None or not self.use_cuda_graph or \
                     (self._world > 1 and not self._graph_collectives):
                 self._enqueue_step()
             else:  # one captured graph per batch set (they alternate)
@@ -1441,25 +1585,34 @@ class SAC_Base:
 
 
 class _AlphaAdam:
-    """Adam state of ``[log_d_alpha, log_c_alpha]`` (sac_base.py:472); only log_c_alpha ever gets a
-    gradient in continuous-only runs, so the torch state dict holds entry 1 alone."""
+    """Adam state of ``[log_d_alpha, log_c_alpha]`` (sac_base.py:472): entry 0 exists when discrete branches train
+    their alpha, entry 1 when continuous actions do (a parameter that never gets a gradient has no state)."""
 
-    def __init__(self, m_buf, v_buf, counters, lr):
+    def __init__(self, m_buf, v_buf, counters, lr, d_state=None, c_enabled=True):
         self._m, self._v, self._counters, self._lr = m_buf, v_buf, counters, lr
+        self._d, self._c = d_state, c_enabled
 
     def state_dict(self) -> dict:
         step = float(self._counters[3].item())
         state = {}
         if step > 0:
-            state[1] = {'step': torch.tensor(step), 'exp_avg': self._m[0].clone(), 'exp_avg_sq': self._v[0].clone()}
+            if self._d is not None:
+                state[0] = {'step': torch.tensor(step), 'exp_avg': self._d[0][0].clone(), 'exp_avg_sq': self._d[1][0].clone()}
+            if self._c:
+                state[1] = {'step': torch.tensor(step), 'exp_avg': self._m[0].clone(), 'exp_avg_sq': self._v[0].clone()}
         group = dict(lr=self._lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, maximize=False,
                      foreach=None, capturable=False, differentiable=False, fused=None, params=[0, 1])
         return {'state': state, 'param_groups': [group]}
 
     def load_state_dict(self, sd: dict) -> None:
-        st = sd['state'].get(1)
-        if st is None:
-            self._m.zero_(); self._v.zero_(); self._counters[3] = 0
-            return
-        self._m[0] = st['exp_avg']; self._v[0] = st['exp_avg_sq']
-        self._counters[3] = int(float(st['step']))
+        steps = []
+        for key, (m, v) in ((0, self._d if self._d is not None else (None, None)), (1, (self._m, self._v))):
+            if m is None:
+                continue
+            st = sd['state'].get(key)
+            if st is None:
+                m.zero_(); v.zero_()
+                continue
+            m[0] = st['exp_avg']; v[0] = st['exp_avg_sq']
+            steps.append(int(float(st['step'])))
+        self._counters[3] = max(steps) if steps else 0

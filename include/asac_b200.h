@@ -29,6 +29,7 @@ extern "C" {
 #define ASAC_EUNSUPPORTED (-2) /* configuration outside the fused path              */
 
 #define ASAC_MAX_COLUMNS 16
+#define ASAC_MAX_BRANCHES 8   /* discrete action branches */
 #define ASAC_MAX_NSTEP 16
 #define ASAC_MAX_DEPTH 4
 #define ASAC_MAX_ENSEMBLE 8
@@ -534,6 +535,63 @@ int asac_policy_act(const float *params, int state_size, int hidden, int depth, 
  * pass [0], critic backward [1] and policy backward [2] launch; out_host is int64[3][32], slot 31 is
  * the kernel's exit (tools/phase_breakdown.py prints the differences).  Synchronises. */
 int asac_debug_phase_clocks(int64_t *out_host);
+
+/* ------------------------------------------------------------------------------------
+ * Discrete (and the discrete half of hybrid) action branches — replaces the d_action_sizes paths of
+ * SAC_Base._get_y / _train_rep_q / _train_policy / _train_alpha / get_l_probs / _get_td_error
+ * (sac_base.py:1356-1421, 1543-1570, 1858-1880, 1924-1929, 1176-1178, 2226-2230) for the stock nets: one
+ * LinearLayers(state -> d_dense_n x d_dense_depth -> d_action_size_k) per branch in every ModelQ and in
+ * ModelPolicy (nn_models/q.py:60-64, policy.py:143-147).  Flat layout of one member: the K branch nets one
+ * after the other, each in the stock layout (W0 b0 ... Whead bhead) padded to a multiple of 4 floats.
+ * Actions and mu-probabilities are stored as [one-hot per branch ..., continuous ...] rows of D + A floats.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t branches;
+    int32_t sizes[ASAC_MAX_BRANCHES];   /* d_action_sizes                                                    */
+    int32_t hidden, depth;              /* d_dense_n, d_dense_depth                                          */
+    int32_t state_size;
+    float target_d_alpha;               /* ratio; the per-column target is ratio * -log(1 / size) (:463-466) */
+    float entropy_penalty;              /* d_policy_entropy_penalty                                          */
+} AsacDiscreteConfig;
+
+int64_t asac_dnets_member_floats(const AsacDiscreteConfig *d);   /* floats of one member's K branch nets          */
+int asac_dnets_tiles(int rows);                                  /* 16-row tiles = partial-gradient rows          */
+/* out[member, row, column] = branch nets of every member on row r = x + r * x_row_stride  (forward only) */
+int asac_dnets_forward(const AsacDiscreteConfig *d, const float *params, int64_t member_stride, int members,
+                       const float *x, int64_t x_row_stride, int rows, float *out, void *stream);
+/* the same walk with saved activations, then the backward pass from d_out[member, row, column] = d loss / d output;
+ * grad_part[tile, member, member_floats]: partial gradients per 16-row tile (summed by asac_flat_reduce_adam) */
+int asac_dnets_backward(const AsacDiscreteConfig *d, const float *params, int64_t member_stride, int members,
+                        const float *x, int64_t x_row_stride, int rows, const float *d_out, float *grad_part,
+                        void *stream);
+/* d_y[B]: expectation of mean-ensemble Q minus alpha log pi under the policy on rows b..b+n, V-trace with the
+ * discrete importance ratio (sac_base.py:1384-1412, 1244-1295).  pi_logits [B * L, D], tq [E, B * L, D];
+ * pi_probs_d != NULL: the td-error pass, whose mu probabilities are the policy's own (:2233). */
+int asac_d_target(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *pi_logits, const float *tq,
+                  const float *actions_full, const float *mu_full, const float *pi_probs_d, const float *rewards,
+                  const uint8_t *dones, const uint8_t *last_masks, const uint8_t *padding_masks,
+                  const float *log_d_alpha, float *d_y, void *stream);
+/* critic loss of the discrete part and its gradient w.r.t. the critics' outputs (:1543-1547, 1564-1570) */
+int asac_d_q_grad(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *q, const float *actions_full,
+                  const float *d_y, const float *weights, float scale, float *d_out, float *loss, float *q_single,
+                  void *stream);
+/* policy loss incl. the entropy penalty and its gradient w.r.t. the logits (:1858-1880); the logits of batch
+ * element e are row e * stride_rows + row_off of `logits` */
+int asac_d_pi_grad(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *logits, int stride_rows,
+                   int row_off, const float *q, const float *mu_full, const float *log_d_alpha, float *d_out,
+                   float *loss, float *entropy, void *stream);
+/* get_l_probs, discrete columns (:1176-1178): pi_probs_d [B, L - 1, D] (+ columns [0, D) of pi_probs_full) */
+int asac_d_probs(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *logits, float *pi_probs_d,
+                 float *pi_probs_full, void *stream);
+/* _train_alpha, discrete part (:1924-1929) + Adam on log_d_alpha; step[0] = steps taken so far, not advanced */
+int asac_d_alpha(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *logits, float *log_d_alpha,
+                 float *m, float *v, const int64_t *step, float grad_scale, float *grad_out, float *loss_out,
+                 void *stream);
+/* td_error[e] (+)= mean_i |sum(onehot * q_i) / branches - d_y|  (:2226-2230, 2238-2243) */
+int asac_d_td(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *q, const float *actions_full,
+              const float *d_y, float *td_error, int accumulate, void *stream);
+/* counters[i] += 1 for every bit i of mask (0 global step, 1 critics, 2 policy, 3 alpha, 4 representation) */
+int asac_bump_counters(int64_t *counters, int mask, void *stream);
 
 #ifdef __cplusplus
 }

@@ -158,8 +158,19 @@ def test_non_stock_networks_are_rejected(tmp_path):
         lowering.analyze_q(QWithState(6, [], 2, False))
     with pytest.raises(lowering.NotStockNetwork):
         lowering.analyze_q(QOverride(6, [], 2, False))
+    # discrete heads are lowered next to the continuous net (analyze_d_heads); unequal heads are not stock
+    shape, params = lowering.analyze_q(m.ModelQ(6, [3], 2, False))
+    assert shape == lowering.NetShape(8, 64, 3, 1) and len(params) == 8
+    d_shapes, d_params = lowering.analyze_d_heads(m.ModelQ(6, [3, 4], 2, False), 'ModelQ')
+    assert d_shapes == [lowering.NetShape(6, 64, 3, 3), lowering.NetShape(6, 64, 3, 4)] and len(d_params[1]) == 8
+    assert lowering.analyze_q(m.ModelQ(6, [3], 0, False)) == (None, [])
+
+    class QDeepHeads(m.ModelQ):
+        def _build_model(self):
+            super()._build_model(d_dense_depth=0)
+
     with pytest.raises(lowering.NotStockNetwork):
-        lowering.analyze_q(m.ModelQ(6, [3], 2, False))
+        lowering.analyze_d_heads(QDeepHeads(6, [3], 2, False), 'ModelQ')
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
