@@ -472,22 +472,33 @@ def measure(args, steps, warmup, clocks=None, detail=True):
     eps = [pin_episode(synth_episode(rng, T_in, S, A)) for _ in range(32)]
     h2d = sum(v.nbytes for k, v in eps[0].items() if not isinstance(v, list)) + sum(x.nbytes for x in eps[0]['ep_obses_list'])
     h2d += T_in  # the derived last_mask column
-    td_host = torch.empty(batch, dtype=torch.float32).pin_memory()
+    # Every step: put_episode() of pinned host transitions (H2D inside), train(), and a D2H copy of THAT step's
+    # td-errors into a pinned host buffer which the host then reads.  The read of step i is awaited after step i + 1
+    # has been enqueued (two host buffers, one CUDA event each) — the way an asynchronous learner consumes its
+    # results — so the host work of step i + 1 overlaps the device work of step i; every step's result is read.
+    td_hosts = [torch.empty(batch, dtype=torch.float32).pin_memory() for _ in range(2)]
+    td_events = [torch.cuda.Event() for _ in range(2)]
     for i in range(5):
-        sac.put_episode(**eps[i % 32]); sac.train(); td_host.copy_(sac._wk['td_error']); torch.cuda.synchronize()
+        sac.put_episode(**eps[i % 32]); sac.train(); td_hosts[0].copy_(sac._wk['td_error']); torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    acc = 0.0
     for i in range(steps):
         sac.put_episode(**eps[i % 32])
         sac.train()
-        td_host.copy_(sac._wk['td_error'], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        _ = float(td_host[0])
+        td_hosts[i & 1].copy_(sac._wk['td_error'], non_blocking=True)
+        td_events[i & 1].record()
+        if i > 0:
+            td_events[(i - 1) & 1].synchronize()
+            acc += float(td_hosts[(i - 1) & 1][0])
+    td_events[(steps - 1) & 1].synchronize()
+    acc += float(td_hosts[(steps - 1) & 1][0])
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    td_host = td_hosts[0]
     clock_info = clocks.snapshot() if clocks is not None else None
 
     # ---- max over ranks; replicas must hold bit-identical parameters after all those steps
@@ -523,7 +534,8 @@ def measure(args, steps, warmup, clocks=None, detail=True):
         'value_warm_l2': units_per_step * steps / (warm_ms * 1e-3),
         'e2e': {'value': units_per_step * steps / (e2e_ms * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(td_host.numel() * 4),
-                'what': f'put_episode({T_in} host transitions, pinned) + train() + D2H of td_error[{batch}], per step'},
+                'what': f'put_episode({T_in} host transitions, pinned) + train() + D2H of td_error[{batch}] per step; the host '
+                        'reads step i after enqueueing step i + 1 (double-buffered pinned results)'},
         'gpu_launches': launches_per_step * steps * world,
         'launches_per_step': launches_per_step,
         'clocks': clock_info,
