@@ -46,7 +46,7 @@ class AsacSacConfig(C.Structure):
                 ('v_c', C.c_float), ('clip_epsilon', C.c_float), ('target_c_alpha', C.c_float),
                 ('td_error_min', C.c_float), ('td_error_max', C.c_float), ('per_alpha', C.c_float),
                 ('gamma_ratio', C.c_float * MAX_NSTEP), ('lambda_ratio', C.c_float * MAX_NSTEP),
-                ('rep_kind', C.c_int32), ('rep_param_stride', C.c_int32)]
+                ('rep_kind', C.c_int32), ('rep_param_stride', C.c_int32), ('ensemble_sample', C.c_int32)]
 
 
 class AsacSacParams(C.Structure):
@@ -59,7 +59,7 @@ class AsacSacBatch(C.Structure):
     _fields_ = [('states', vp), ('actions', vp), ('rewards', vp), ('dones', vp), ('last_masks', vp),
                 ('padding_masks', vp), ('mu_probs', vp), ('priority_is', vp),
                 ('eps_y', vp), ('eps_pi', vp), ('eps_alpha', vp), ('eps_td', vp),
-                ('states_post', vp), ('target_states', vp)]
+                ('states_post', vp), ('target_states', vp), ('ensemble_perms', vp)]
 
 
 class AsacWriteColumn(C.Structure):
@@ -148,6 +148,7 @@ PROTOTYPES = {
     'asac_d_alpha': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, vp, f32, vp, vp, vp]),
     'asac_d_td': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, i32, vp]),
     'asac_bump_counters': (i32, [vp, i32, vp]),
+    'asac_ensemble_perms': (i32, [vp, i32, i32, u64, vp, vp]),
     'asac_sac_value_pass_on_tc': (i32, [P(AsacSacConfig), i32]),
     'asac_sac_polyak': (i32, [P(AsacSacConfig), P(AsacSacParams), f32, vp]),
     'asac_sac_target_y': (i32, [P(AsacSacConfig), P(AsacSacParams), P(AsacSacBatch), P(AsacSacWork), vp]),

@@ -107,11 +107,42 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
     return s;
 }
 
+// ensemble_q_sample < ensemble_q_num: the min over the critics runs over a random subset (sac_base.py:1434-1436, 1887)
+__host__ __device__ __forceinline__ bool ensemble_subset(const AsacSacConfig &c) {
+    return c.ensemble_sample > 0 && c.ensemble_sample < c.ensemble;
+}
+// Rank 0 of a value-pass cluster: min over the members of every value row.  All members, or — with a subset —
+// qmin[r] over the first Es entries of `perm_cur` (the rows used as V_k) and qmin2[r] over those of `perm_next`
+// (the rows used as V_{k+1}); the reference draws the two subsets independently.
+template <typename Cluster>
+__device__ __forceinline__ void combine_value_rows(Cluster &cluster, const AsacSacConfig &c, const int32_t *perms,
+                                                   int first_perm, float *qmin, float *qmin2, int RV) {
+    const int E = c.ensemble, tid = threadIdx.x;
+    if (!ensemble_subset(c) || perms == nullptr) {
+        for (int i = 1; i < E; ++i) {
+            const float *rmin = cluster.map_shared_rank(qmin, i);
+            for (int r = tid; r < RV; r += NT) qmin[r] = fminf(qmin[r], rmin[r]);  // sac_base.py:1439-1442
+        }
+        return;
+    }
+    const int Es = c.ensemble_sample;
+    const int32_t *pc = perms + first_perm * E, *pn = pc + E;
+    for (int r = tid; r < RV; r += NT) {
+        float m1 = INFINITY, m2 = INFINITY;
+        for (int j = 0; j < Es; ++j) {
+            m1 = fminf(m1, cluster.map_shared_rank(qmin, pc[j])[r]);
+            m2 = fminf(m2, cluster.map_shared_rank(qmin, pn[j])[r]);
+        }
+        qmin2[r] = m2;
+        qmin[r] = m1;  // (own row r is read above by this thread only)
+    }
+}
+
 // ------------------------------------------------------------------------------------ smem plans
 struct ValuePlan {
     int lda, wsz, rows_max;  // rows_max: multiple of 16
-    int off_xin, off_a, off_b, off_ho, off_xs, off_logp, off_qmin, off_ratio, off_qs, off_red, off_part, off_heads,
-        off_pipe, off_slots;
+    int off_xin, off_a, off_b, off_ho, off_xs, off_logp, off_qmin, off_qmin2, off_ratio, off_qs, off_red, off_part,
+        off_heads, off_pipe, off_slots;
     int n_jobs, n_slots;
     int total;  // floats
 };
@@ -136,6 +167,7 @@ __host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c,
     p.off_xs = o; o += round_up(TB * (n + 1) * A, 4);
     p.off_logp = o; o += round_up(TB * (n + 1), 4);
     p.off_qmin = o; o += round_up(p.rows_max, 4);
+    p.off_qmin2 = o; o += ensemble_subset(c) ? round_up(p.rows_max, 4) : 0;  // min over the "next rows" subset
     p.off_ratio = o; o += round_up(TB * (n > 0 ? n : 1), 4);
     p.off_qs = o; o += round_up(c.ensemble * TB, 4);
     p.off_red = o; o += 32;
@@ -431,15 +463,14 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     ASAC_PHASE(0, 6);
     // ---- ensemble combine on rank 0 over distributed shared memory, in member order
     cluster.sync();
+    float *qmin2 = ensemble_subset(c) && a.bat.ensemble_perms ? sm + pl.off_qmin2 : qmin;
     if (net == 0) {
-        for (int i = 1; i < E; ++i) {
-            const float *rmin = cluster.map_shared_rank(qmin, i);
-            for (int r = tid; r < RV; r += NT) qmin[r] = fminf(qmin[r], rmin[r]);  // sac_base.py:1439-1442
-            if (post) {
+        combine_value_rows(cluster, c, a.bat.ensemble_perms, post ? 3 : 0, qmin, qmin2, RV);
+        if (post)
+            for (int i = 1; i < E; ++i) {
                 const float *rqs = cluster.map_shared_rank(qs, i);
                 for (int e = tid; e < TBa; e += NT) qs[i * TB + e] = rqs[e];
             }
-        }
     }
     cluster.sync();  // remote shared memory stays alive until rank 0 has read it
     if (net != 0) return;
@@ -459,7 +490,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         float sum = 0.f, sum_q = 0.f, sum_l = 0.f, cprod = 1.f;
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
-            const float q_next = qmin[e * (n + 1) + k + 1], l_next = logp[e * (n + 1) + k + 1];
+            const float q_next = qmin2[e * (n + 1) + k + 1], l_next = logp[e * (n + 1) + k + 1];  // "next rows" subset
             const float v_next = q_next - alpha * l_next;
             const int64_t idx = (int64_t)eg * c.bn_stride + b + k;
             const float nd = a.bat.dones[idx] ? 0.f : 1.f;
@@ -485,7 +516,9 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
             sum += td * keep;
             sum_q += td_q * keep;
             sum_l += td_l * keep;
-            v_prev = v_next; q_prev = q_next; l_prev = l_next;
+            q_prev = qmin[e * (n + 1) + k + 1];  // the same row as V_k of the next term: the "current rows" subset
+            l_prev = l_next;
+            v_prev = qmin2 == qmin ? v_next : q_prev - alpha * l_prev;
         }
         if (!post) {
             a.wrk.y[eg] = v0 + sum;
@@ -738,9 +771,17 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     if (tid < R) {
         int best = 0;
         if (tid < TBa) {
-            float m = qv[tid];
-            for (int i = 1; i < E; ++i)
-                if (qv[i * R + tid] < m) { m = qv[i * R + tid]; best = i; }
+            if (ensemble_subset(c) && a.bat.ensemble_perms) {  // torch.min over stack[randperm[:Es]] (sac_base.py:1887-1894)
+                const int32_t *perm = a.bat.ensemble_perms + 2 * E;
+                best = perm[0];
+                float m = qv[best * R + tid];
+                for (int j = 1; j < c.ensemble_sample; ++j)
+                    if (qv[perm[j] * R + tid] < m) { m = qv[perm[j] * R + tid]; best = perm[j]; }
+            } else {
+                float m = qv[tid];
+                for (int i = 1; i < E; ++i)
+                    if (qv[i * R + tid] < m) { m = qv[i * R + tid]; best = i; }
+            }
         }
         amin[tid] = (float)best;
     }
@@ -1126,6 +1167,21 @@ __global__ void __launch_bounds__(1024) k_step_epilogue(const __grid_constant__ 
         return;
     }
     if (a.nodes) block_tree_apply(a.nodes, a.capacity, a.levels, slot, value, active, s_apply);  // else: deferred
+}
+
+// torch.randperm(E) x n_perms: Fisher-Yates, one thread per permutation
+__global__ void k_ensemble_perms(int32_t *out, int n_perms, int E, uint64_t seed, const int64_t *counter) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_perms) return;
+    int32_t v[ASAC_MAX_ENSEMBLE];
+    for (int i = 0; i < E; ++i) v[i] = i;
+    uint32_t r[4];
+    for (int i = E - 1; i > 0; --i) {
+        philox4(seed ^ 0xE5E3B1E5ull, (uint64_t)counter[0], ((uint64_t)p << 8) | (uint64_t)i, r);
+        const int j = (int)(u01_double(r[0], r[1]) * (double)(i + 1));
+        const int32_t t = v[i]; v[i] = v[j]; v[j] = t;
+    }
+    for (int i = 0; i < E; ++i) out[p * E + i] = v[i];
 }
 
 __global__ void k_bump(int64_t *counters, int mask) {
@@ -2087,6 +2143,15 @@ extern "C" int asac_d_td(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, 
               q, actions_full, d_y, td_error};
     k_d_td<<<(cfg->batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
     ASAC_LAUNCHED("k_d_td");
+    return ASAC_OK;
+}
+
+extern "C" int asac_ensemble_perms(int32_t *out, int n_perms, int ensemble, uint64_t seed, const int64_t *counter,
+                                   void *stream) {
+    ASAC_REQUIRE(out && counter && n_perms >= 1 && n_perms <= 64 && ensemble >= 1 && ensemble <= ASAC_MAX_ENSEMBLE,
+                 "asac_ensemble_perms: bad arguments");
+    k_ensemble_perms<<<1, 64, 0, (cudaStream_t)stream>>>(out, n_perms, ensemble, seed, counter);
+    ASAC_LAUNCHED("k_ensemble_perms");
     return ASAC_OK;
 }
 

@@ -13,7 +13,8 @@
 // ---------------------------------------------------------------- value pass
 struct ValueTcPlan {
     int RA;  // rows of the operand planes (multiple of 8)
-    int off_xhi, off_xlo, off_w, off_bias, off_ho, off_qo, off_xs, off_logp, off_qmin, off_ratio, off_qs, off_red, off_misc;
+    int off_xhi, off_xlo, off_w, off_bias, off_ho, off_qo, off_xs, off_logp, off_qmin, off_qmin2, off_ratio, off_qs, off_red,
+        off_misc;
     int total;  // floats
 };
 __host__ __device__ __forceinline__ ValueTcPlan value_tc_plan(const AsacSacConfig &c, int TB, int mode) {
@@ -35,6 +36,7 @@ __host__ __device__ __forceinline__ ValueTcPlan value_tc_plan(const AsacSacConfi
     p.off_xs = o; o += round_up(TB * (n + 1) * A, 4);
     p.off_logp = o; o += round_up(TB * (n + 1), 4);
     p.off_qmin = o; o += round_up(TB * (n + 1), 4);
+    p.off_qmin2 = o; o += ensemble_subset(c) ? round_up(TB * (n + 1), 4) : 0;
     p.off_ratio = o; o += round_up(TB * (n > 0 ? n : 1), 4);
     p.off_qs = o; o += round_up(c.ensemble * TB, 4);
     p.off_red = o; o += 32;
@@ -294,15 +296,14 @@ __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__
     ASAC_PHASE(0, 6);
     // ---- ensemble combine on rank 0 over distributed shared memory, in member order
     cluster.sync();
+    float *qmin2 = ensemble_subset(c) && a.bat.ensemble_perms ? sm + pl.off_qmin2 : qmin;
     if (net == 0) {
-        for (int i = 1; i < E; ++i) {
-            const float *rmin = cluster.map_shared_rank(qmin, i);
-            for (int r = tid; r < RV; r += NT) qmin[r] = fminf(qmin[r], rmin[r]);  // sac_base.py:1439-1442
-            if (post) {
+        combine_value_rows(cluster, c, a.bat.ensemble_perms, post ? 3 : 0, qmin, qmin2, RV);
+        if (post)
+            for (int i = 1; i < E; ++i) {
                 const float *rqs = cluster.map_shared_rank(qs, i);
                 for (int e = tid; e < TBa; e += NT) qs[i * TB + e] = rqs[e];
             }
-        }
     }
     cluster.sync();  // remote shared memory stays alive until rank 0 has read it
     ASAC_PHASE(0, 7);
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__
         float sum = 0.f, sum_q = 0.f, sum_l = 0.f, cprod = 1.f;
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
-            const float q_next = qmin[e * (n + 1) + k + 1], l_next = logp[e * (n + 1) + k + 1];
+            const float q_next = qmin2[e * (n + 1) + k + 1], l_next = logp[e * (n + 1) + k + 1];  // "next rows" subset
             const float v_next = q_next - alpha * l_next;
             const int64_t idx = (int64_t)eg * c.bn_stride + b + k;
             const float nd = a.bat.dones[idx] ? 0.f : 1.f;
@@ -346,7 +347,9 @@ __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__
             sum += td * keep;
             sum_q += td_q * keep;
             sum_l += td_l * keep;
-            v_prev = v_next; q_prev = q_next; l_prev = l_next;
+            q_prev = qmin[e * (n + 1) + k + 1];  // the same row as V_k of the next term: the "current rows" subset
+            l_prev = l_next;
+            v_prev = qmin2 == qmin ? v_next : q_prev - alpha * l_prev;
         }
         if (!post) {
             a.wrk.y[eg] = v0 + sum;

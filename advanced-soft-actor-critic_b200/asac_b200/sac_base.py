@@ -209,7 +209,9 @@ class SAC_Base:
             'use_rnd': use_rnd,
             'use_normalization': use_normalization,
             'offline_enabled': offline_enabled,
-            'ensemble_q_sample != ensemble_q_num': ensemble_q_sample != ensemble_q_num,
+            'ensemble_q_sample > ensemble_q_num': ensemble_q_sample > ensemble_q_num,
+            'ensemble_q_sample < ensemble_q_num with discrete action branches': bool(d_action_sizes) and
+            ensemble_q_sample != ensemble_q_num,
             'action_noise': action_noise is not None,
         }
         bad = [k for k, v in unsupported.items() if v]
@@ -422,6 +424,7 @@ class SAC_Base:
         cfg.update_target_per_step = int(self.update_target_per_step)
         cfg.bn_stride = cfg.seq_len
         cfg.rep_kind = 0 if (self._gru is None and self._bridge is None) else 1
+        cfg.ensemble_sample = self.ensemble_q_sample if 0 < self.ensemble_q_sample < E else 0
         cfg.rep_param_stride = 0 if self._gru is None else self._gru.stride
         cfg.tau, cfg.one_minus_tau = float(self.tau), float(np.float32(1. - self.tau))
         cfg.gamma, cfg.v_rho, cfg.v_c = float(self.gamma), float(self.v_rho), float(self.v_c)
@@ -584,6 +587,7 @@ class SAC_Base:
         # The sampled batch lives in a "batch set" (sample outputs, gathered windows, the C structs pointing
         # at them).  Two sets: while the networks train on one, the NEXT step's sample + gather fill the
         # other on a parallel branch (ASAC_SAMPLE_AHEAD=0: one set, sample and gather on the critical path).
+        self._ens_perms = torch.zeros(5, E, dtype=torch.int32, device=dev)  # ensemble_q_sample < ensemble_q_num
         self._sample_ahead = self.use_replay_buffer and os.environ.get('ASAC_SAMPLE_AHEAD', '1') != '0' \
             and self._bridge is None and self._disc is None  # (those steps run in program order on one stream)
         self._sets = [self._make_batch_set() for _ in range(2 if self._sample_ahead else 1)]
@@ -661,6 +665,8 @@ class SAC_Base:
         noise = torch.zeros(sum(sizes), **f32)
         offs = np.cumsum([0] + sizes)
         batch.eps_y, batch.eps_pi, batch.eps_alpha, batch.eps_td = [ptr(noise[offs[i]:offs[i + 1]]) for i in range(4)]
+        if self._cfg.ensemble_sample:  # the step's torch.randperm draws, refreshed on the device every step
+            batch.ensemble_perms = ptr(self._ens_perms)
         rep = None
         if self._gru is not None:
             g = self._gru
@@ -1083,6 +1089,14 @@ class SAC_Base:
                 raise ValueError(f'stored column {key} has {rb._row_bytes(key)} bytes per row, expected {nbytes}')
         return specs
 
+    def _enqueue_ensemble_perms(self) -> None:
+        """The five torch.randperm(E) draws of a step (sac_base.py:1434, 1436, 1887 and the two of _get_td_error's
+        _get_y), keyed by the global step; every rank of a data-parallel learner draws the same ones."""
+        if self._cfg.ensemble_sample:
+            check(self._lib.asac_ensemble_perms(ptr(self._ens_perms), 5, self.ensemble_q_num,
+                                                (int(self._seed) if self._seed is not None else 0) ^ 0x5EED,
+                                                ptr(self._counters), _lib.current_stream()), 'ensemble_perms')
+
     def _enqueue_noise(self, st: dict, stream_id: int) -> None:
         """The four Gaussian draws of a step (sac_base.py:1346, 1883, 1932, 2223) into batch set `st`:
         Philox keyed by (seed, global step at execution, stream_id)."""
@@ -1181,6 +1195,7 @@ class SAC_Base:
                                            cfg.one_minus_tau, 0, s2), 'flat_polyak')
             if nxt is None or not self._noise_ahead:  # this step's draws, next to the Polyak update
                 self._enqueue_noise(st, 0)
+            self._enqueue_ensemble_perms()
         stream = main.cuda_stream
         # 1 + 2. sample and gather: of the next step on its own branch, or (single batch set) of this one here
         defer = self._defer_active = self._defer_tree and fast_tail
@@ -1315,6 +1330,7 @@ class SAC_Base:
         b, L = self.burn_in_step, self._cfg.seq_len
         self._enqueue_sample(st)
         self._enqueue_noise(st, 0)
+        self._enqueue_ensemble_perms()
         hidden_post = self._bridge_step_networks(st)
         if self.use_priority:
             self._enqueue_tree_update(st)
@@ -1443,6 +1459,7 @@ class SAC_Base:
             lib, cfg, prm, work = self._lib, C.byref(self._cfg), C.byref(self._prm), C.byref(self._work)
             stream = _lib.current_stream()
             self._enqueue_noise(st, 0)
+            self._enqueue_ensemble_perms()
             if st['rep'] is not None:
                 check(lib.asac_flat_polyak(ptr(self._rept_flat), ptr(self._rep_flat), self._gru.count,
                                            ptr(self._counters), int(self.update_target_per_step), self._cfg.tau,

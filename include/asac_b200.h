@@ -215,7 +215,7 @@ typedef struct {
     int32_t n_step;         /* n  (<= ASAC_MAX_NSTEP)                        */
     int32_t state_size;     /* S                                             */
     int32_t action_size;    /* A  (continuous)                               */
-    int32_t ensemble;       /* E  (== ensemble_q_sample)                     */
+    int32_t ensemble;       /* E  = ensemble_q_num                           */
     int32_t q_hidden, q_depth;
     int32_t pi_hidden, pi_depth;
     int32_t use_n_step_is, use_priority, use_auto_alpha;
@@ -229,6 +229,9 @@ typedef struct {
                                the states of the online / re-encoded / target representation differ  */
     int32_t rep_param_stride; /* floats of the representation's flat gradient (0 without one): its slice of the
                                peer-exchange buffers (asac_peer_recv_words)                              */
+    int32_t ensemble_sample;  /* ensemble_q_sample: the min over the critics runs over the first `ensemble_sample`
+                               entries of a random permutation of the members (sac_base.py:1434-1436, 1887);
+                               0 or >= ensemble: over all of them                                        */
 } AsacSacConfig;
 
 typedef struct {
@@ -264,6 +267,10 @@ typedef struct {
     const float *states_post;     /* [B, L, S]  online representation re-evaluated after it (:2099-2105):
                                      policy / alpha losses, get_l_probs, Q_i(s_b, a_b) of _get_td_error   */
     const float *target_states;   /* [B, L, S]  target representation (:2073-2078): _get_y inside _get_td_error */
+    /* cfg.ensemble_sample < cfg.ensemble: int32[5, E] permutations of the members, one per torch.randperm call of a
+     * step in call order — _get_y current rows / next rows (:1434, :1436), _train_policy (:1887), _get_y of
+     * _get_td_error current / next rows (asac_ensemble_perms draws them on the device).  NULL: all members. */
+    const int32_t *ensemble_perms;
 } AsacSacBatch;
 
 typedef struct {
@@ -590,6 +597,9 @@ int asac_d_alpha(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const fl
 /* td_error[e] (+)= mean_i |sum(onehot * q_i) / branches - d_y|  (:2226-2230, 2238-2243) */
 int asac_d_td(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *q, const float *actions_full,
               const float *d_y, float *td_error, int accumulate, void *stream);
+/* out[n_perms, E] = independent uniform random permutations of 0..E-1 (Fisher-Yates on Philox4x32-10 keyed by
+ * seed, counter[0] and the permutation's index): the torch.randperm(E) draws of a step */
+int asac_ensemble_perms(int32_t *out, int n_perms, int ensemble, uint64_t seed, const int64_t *counter, void *stream);
 /* counters[i] += 1 for every bit i of mask (0 global step, 1 critics, 2 policy, 3 alpha, 4 representation) */
 int asac_bump_counters(int64_t *counters, int mask, void *stream);
 

@@ -239,8 +239,11 @@ def _write_custom_nn(tmpdir: Path, hidden: int, depth: int) -> Path:
     return p
 
 
-def gen_sac_case(name, *, S, A, E, hidden, depth, B, b, n, steps, seed, use_priority=True, nn_rel=None,
+def gen_sac_case(name, *, S, A, E, hidden, depth, B, b, n, steps, seed, use_priority=True, nn_rel=None, Es=None,
                  **hyper):
+    """``Es`` (ensemble_q_sample < E): the reference takes the min over a random SUBSET of the critics
+    (``torch.randperm(E)[:Es]``, sac_base.py:1434-1436, 1887) — the draws are recorded in call order under
+    ``s*.in.perms``: _get_y current rows, next rows; _train_policy; _get_y of _get_td_error current, next."""
     SAC_Base, _, _ = import_reference()
     import tempfile
     if nn_rel is not None:
@@ -256,7 +259,7 @@ def gen_sac_case(name, *, S, A, E, hidden, depth, B, b, n, steps, seed, use_prio
     with _NoThread():
         sac = SAC_Base(obs_names=['vector'], obs_shapes=[(S,)], d_action_sizes=[], c_action_size=A,
                        model_abs_dir=None, nn=nn, device='cpu', seed=seed, batch_size=B,
-                       burn_in_step=b, n_step=n, ensemble_q_num=E, ensemble_q_sample=E,
+                       burn_in_step=b, n_step=n, ensemble_q_num=E, ensemble_q_sample=E if Es is None else Es,
                        use_priority=use_priority, replay_config={'capacity': 1024}, **hyper)
     # make targets differ from the online nets (a fresh start hard-copies them, sac_base.py:629)
     with torch.no_grad():
@@ -356,6 +359,15 @@ def gen_sac_case(name, *, S, A, E, hidden, depth, B, b, n, steps, seed, use_prio
             out[f'{pre}.in.{k}'] = t.numpy().copy()
 
         ys.clear()
+        perms, real_randperm = [], torch.randperm
+
+        def tap_randperm(*a, **k):
+            pp = real_randperm(*a, **k)
+            perms.append(pp.numpy().copy())
+            return pp
+
+        if Es is not None:
+            torch.randperm = tap_randperm
         with _NoiseTap() as tap:
             tap.queue = [noise['eps_y'], noise['eps_pi']]
             if sac.use_auto_alpha:
@@ -395,8 +407,14 @@ def gen_sac_case(name, *, S, A, E, hidden, depth, B, b, n, steps, seed, use_prio
                 out[f'{pre}.out.td_error'] = td.numpy().copy()
                 out[f'{pre}.out.y_td'] = ys[1].numpy().copy()
             assert not tap.queue
+        torch.randperm = real_randperm
+        if Es is not None:
+            assert len(perms) == (5 if use_priority else 3), len(perms)
+            out[f'{pre}.in.perms'] = np.stack(perms).astype(np.int64)
         sac.increase_global_step()
         dump_params(f'{pre}.after')
+    if Es is not None:
+        out['ensemble_q_sample'] = np.int64(Es)
     sac.close()
     np.savez_compressed(GOLDEN / f'sac_{name}.npz', **out)
     print('wrote', f'sac_{name}.npz', sum(v.nbytes for v in out.values()), 'bytes raw')
@@ -960,6 +978,8 @@ CASES = {
                                     update_target_per_step=2, gamma=0.97),
     'sac_nois': lambda: gen_sac_case('nois', S=4, A=2, E=2, hidden=32, depth=2, B=10, b=0, n=2, steps=2, seed=13,
                                      use_n_step_is=False, use_auto_alpha=False),
+    # min over a random 2-of-3 subset of the critics (ensemble_q_sample < ensemble_q_num), recorded randperm draws
+    'sac_sub': lambda: gen_sac_case('sub', S=5, A=2, E=3, hidden=32, depth=2, B=12, b=1, n=3, steps=2, seed=19, Es=2),
     # config-4 shapes (envs/test/nn_rnn.py: GRU(6 + 2 -> 8, 2 layers)), shorter burn-in, 2 steps
     'sac_rnn': lambda: gen_sac_rnn_case('rnn', So=6, A=2, E=2, B=16, b=5, n=3, steps=2, seed=14, v_lambda=0.95),
     'sac_rnn_b0': lambda: gen_sac_rnn_case('rnn_b0', So=6, A=2, E=2, B=8, b=0, n=1, steps=2, seed=15,

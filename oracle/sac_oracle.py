@@ -167,6 +167,7 @@ class SacHyper:
     clip_epsilon: float = 0.2
     use_n_step_is: bool = True
     use_priority: bool = True
+    ensemble_q_sample: int = 0  # 0 = every critic; < ensemble_q_num: min over a random subset (sac_base.py:1434-1436, 1887)
 
 
 @dataclass
@@ -287,7 +288,9 @@ class SacOracle:
 
     # ---- sac_base.py:1297-1466 (continuous branch)
     @torch.no_grad()
-    def get_y(self, last_masks, padding_masks, nx_states, n_actions, rewards, dones, mu_probs, eps):
+    def get_y(self, last_masks, padding_masks, nx_states, n_actions, rewards, dones, mu_probs, eps, perms=None):
+        """``perms``: the two ``torch.randperm(E)`` draws of sac_base.py:1434 (current rows) and :1436 (next rows)
+        when ``ensemble_q_sample < ensemble_q_num``."""
         hp = self.hp
         alpha = torch.exp(self.log_c_alpha)
         nx_actions = torch.cat([n_actions, torch.zeros_like(n_actions[:, :1])], dim=1)
@@ -296,22 +299,26 @@ class SacOracle:
         squashed = torch.tanh(sampled)
         qs = [q_forward(q, hp.q_depth, nx_states, squashed) for q in self.q_target]
         logp = sum_log_prob(squash_log_prob(loc, scale, sampled))  # [B, n+1]
-        min_q = torch.stack(qs).min(dim=0)[0].squeeze(-1)          # [B, n+1]
-        v = min_q - alpha * logp
+        stacked = torch.stack(qs)
+        Es = hp.ensemble_q_sample if 0 < hp.ensemble_q_sample < hp.ensemble_q_num else hp.ensemble_q_num
+        sel_cur = torch.as_tensor(perms[0])[:Es] if perms is not None else slice(None)
+        sel_next = torch.as_tensor(perms[1])[:Es] if perms is not None else slice(None)
+        v_cur = stacked[sel_cur].min(dim=0)[0].squeeze(-1) - alpha * logp     # [B, n+1]; rows [:, :-1] are used
+        v_next = stacked[sel_next].min(dim=0)[0].squeeze(-1) - alpha * logp   # rows [:, 1:] are used
         pi = mu = None
         if hp.use_n_step_is:
             stored = torch.atanh(torch.clamp(nx_actions, -0.999, 0.999))
             pi = prod_prob(squash_prob(loc, scale, stored)[:, :-1])
             mu = prod_prob(mu_probs)
-        return self.v_trace(last_masks, padding_masks, rewards, dones, mu, pi, v[:, :-1], v[:, 1:])
+        return self.v_trace(last_masks, padding_masks, rewards, dones, mu, pi, v_cur[:, :-1], v_next[:, 1:])
 
     # ---- sac_base.py:1516-1603
-    def train_q(self, b: SacBatch, eps_y):
+    def train_q(self, b: SacBatch, eps_y, perms=None):
         hp = self.hp; s0 = hp.burn_in_step
         state, action = b.states[:, s0], b.actions[:, s0]
         q_vals = [q_forward(q, hp.q_depth, state, action) for q in self.q]
         y = self.get_y(b.last_masks[:, s0:], b.padding_masks[:, s0:], b.states[:, s0:], b.actions[:, s0:],
-                       b.rewards[:, s0:], b.dones[:, s0:], b.mu_probs[:, s0:], eps_y)
+                       b.rewards[:, s0:], b.dones[:, s0:], b.mu_probs[:, s0:], eps_y, perms)
         losses = []
         for i, q_val in enumerate(q_vals):
             if hp.clip_epsilon > 0:
@@ -333,7 +340,7 @@ class SacOracle:
         return dict(y=y, q=[v.detach() for v in q_vals], loss_q=[l.detach() for l in losses], grad_q=grads)
 
     # ---- sac_base.py:1882-1911
-    def train_policy(self, b: SacBatch, eps_pi):
+    def train_policy(self, b: SacBatch, eps_pi, perm=None):
         hp = self.hp; s0 = hp.burn_in_step
         state = b.states[:, s0]
         loc, scale = policy_forward(self.policy, hp.policy_depth, state)
@@ -342,7 +349,11 @@ class SacOracle:
         sampled = loc + eps_pi * scale
         qs = [q_forward(q, hp.q_depth, state, torch.tanh(sampled)) for q in self.q]
         logp = sum_log_prob(squash_log_prob(loc, scale, sampled), keepdim=True)
-        min_q = torch.stack(qs).min(dim=0)[0]
+        stacked = torch.stack(qs)
+        if perm is not None:  # sac_base.py:1887
+            Es = hp.ensemble_q_sample if 0 < hp.ensemble_q_sample < hp.ensemble_q_num else hp.ensemble_q_num
+            stacked = stacked[torch.as_tensor(perm)[:Es]]
+        min_q = stacked.min(dim=0)[0]
         loss = torch.mean(alpha * logp - min_q)
         self.opt_policy.zero_grad()
         loss.backward(inputs=list(self.policy.values()))
@@ -376,23 +387,25 @@ class SacOracle:
 
     # ---- sac_base.py:2182-2245
     @torch.no_grad()
-    def td_error(self, b: SacBatch, pi_probs, eps_td):
+    def td_error(self, b: SacBatch, pi_probs, eps_td, perms=None):
         hp = self.hp; s0 = hp.burn_in_step
         state, action = b.states[:, s0], b.actions[:, s0]
         q_vals = [q_forward(q, hp.q_depth, state, action) for q in self.q]
         y = self.get_y(b.last_masks[:, s0:], b.padding_masks[:, s0:], b.states[:, s0:], b.actions[:, s0:],
                        b.rewards[:, s0:], b.dones[:, s0:],
-                       pi_probs[:, s0:] if pi_probs is not None else None, eps_td)
+                       pi_probs[:, s0:] if pi_probs is not None else None, eps_td, perms)
         err = torch.cat([torch.abs(qv - y) for qv in q_vals], dim=-1)
         return torch.mean(err, dim=-1, keepdim=True), y
 
     # ---- sac_base.py:2057-2126 + 2558-2583
-    def step(self, b: SacBatch, noise: SacNoise) -> dict:
+    def step(self, b: SacBatch, noise: SacNoise, perms=None) -> dict:
+        """``perms`` [5, E] (ensemble_q_sample < ensemble_q_num): the reference's randperm draws in call order —
+        _get_y current / next rows, _train_policy, _get_y of _get_td_error current / next rows."""
         hp = self.hp
         if self.global_step % hp.update_target_per_step == 0:
             self.polyak(hp.tau)
-        out = self.train_q(b, noise.eps_y)
-        out.update(self.train_policy(b, noise.eps_pi))
+        out = self.train_q(b, noise.eps_y, None if perms is None else perms[0:2])
+        out.update(self.train_policy(b, noise.eps_pi, None if perms is None else perms[2]))
         if hp.use_auto_alpha:
             out.update(self.train_alpha(b, noise.eps_alpha))
         pi_probs = None
@@ -400,7 +413,7 @@ class SacOracle:
             pi_probs = self.l_probs(b.states[:, :-1], b.actions)
             out['pi_probs'] = pi_probs
         if hp.use_priority:
-            out['td_error'], out['y_td'] = self.td_error(b, pi_probs, noise.eps_td)
+            out['td_error'], out['y_td'] = self.td_error(b, pi_probs, noise.eps_td, None if perms is None else perms[3:5])
         self.global_step += 1
         return out
 

@@ -41,6 +41,7 @@ class SacCuda:
         cfg.clip_epsilon, cfg.target_c_alpha = float(hp.clip_epsilon), float(hp.target_c_alpha)
         cfg.td_error_min, cfg.td_error_max, cfg.per_alpha = 0.01, 1.0, 0.9
         cfg.rep_kind = rep_kind
+        cfg.ensemble_sample = int(getattr(hp, 'ensemble_q_sample', 0) or 0)
         gr = torch.logspace(0, n - 1, n, hp.gamma)
         lr = torch.logspace(0, n - 1, n, hp.v_lambda)
         for k in range(n):
@@ -158,8 +159,9 @@ class SacCuda:
                 lowering.state_dict_from_flat(self.pi_shape, self.wk['grad_pi'], True).items()}
 
     # ---- batch
-    def make_batch(self, b, noise) -> _lib.AsacSacBatch:
-        """b: oracle SacBatch (CPU tensors, [B, L-1, ...] layout), noise: SacNoise."""
+    def make_batch(self, b, noise, perms=None) -> _lib.AsacSacBatch:
+        """b: oracle SacBatch (CPU tensors, [B, L-1, ...] layout), noise: SacNoise; perms [5, E]: the reference's
+        randperm draws of the step (ensemble_q_sample < ensemble_q_num)."""
         dev = self.dev
         t = {
             'states': b.states.float(), 'actions': b.actions.float(), 'rewards': b.rewards.float(),
@@ -171,6 +173,8 @@ class SacCuda:
         t = {k: v.contiguous().to(dev) for k, v in t.items()}
         if b.priority_is is not None:
             t['priority_is'] = b.priority_is.float().contiguous().view(-1).to(dev)
+        if perms is not None:
+            t['ensemble_perms'] = torch.as_tensor(np.asarray(perms), dtype=torch.int32).contiguous().to(dev)
         self._keep = [t]
         batch = _lib.AsacSacBatch()
         for k, v in t.items():

@@ -34,7 +34,8 @@ def sac_hyper_from_golden(g: dict):
                     target_c_alpha=hp['target_c_alpha'], learning_rate=hp['learning_rate'],
                     gamma=hp['gamma'], v_lambda=hp['v_lambda'], v_rho=hp['v_rho'], v_c=hp['v_c'],
                     clip_epsilon=hp['clip_epsilon'], use_n_step_is=bool(hp['use_n_step_is']),
-                    use_priority=m['use_priority'])
+                    use_priority=m['use_priority'],
+                    ensemble_q_sample=int(g['ensemble_q_sample']) if 'ensemble_q_sample' in g else 0)
 
 
 def golden_params(g: dict, prefix: str, E: int):

@@ -51,8 +51,8 @@ def check_sac_steps(g: dict) -> None:
     tol = 2e-6  # two fp32 CPU evaluations of the same graph; the CUDA gate is 1e-5 (relative to scale)
     for s in range(m['steps']):
         batch, noise = golden_batch(g, s)
-        out = oracle.step(batch, noise)
         pre = f's{s}.'
+        out = oracle.step(batch, noise, g[pre + 'in.perms'] if pre + 'in.perms' in g else None)
         assert rel_err(out['y'], g[pre + 'out.y']) < tol
         assert rel_err(out['loss_q'][0], g[pre + 'out.loss_q0']) < tol
         assert rel_err(out['entropy'], g[pre + 'out.c_entropy']) < tol

@@ -284,6 +284,52 @@ def test_first_step_matches_golden_directly(name):
         assert rel_err(out['td_error'], g['s0.out.td_error'].reshape(-1)) < 1e-3
 
 
+def test_ensemble_subset_matches_reference():
+    """ensemble_q_sample < ensemble_q_num (sac_base.py:1434-1436, 1887): the min over the critics runs over the first
+    Es entries of a random permutation — drawn independently for the V_k rows, the V_{k+1} rows, the policy loss and
+    the two row sets of the td-error pass.  Fixture minted from the reference with its randperm draws recorded
+    (2 of 3 critics, burn-in 1, n = 3); the fused step with the same draws agrees with the staged one bit for bit."""
+    g, m, hp, oracle, cuda = _setup('sac_sub.npz')
+    assert hp.ensemble_q_sample == 2 and m['E'] == 3 and cuda.cfg.ensemble_sample == 2
+    for s in range(m['steps']):
+        prefix = 'init' if s == 0 else f's{s - 1}.after'
+        cuda.load_params(*golden_params(g, prefix, m['E']))
+        batch, noise = golden_batch(g, s)
+        pre = f's{s}.'
+        perms = g[pre + 'in.perms']
+        out = cuda.staged_step(cuda.make_batch(batch, noise, perms))
+        err = {'y': rel_err(out['y'], g[pre + 'out.y'].reshape(-1)),
+               'td_error': rel_err(out['td_error'], g[pre + 'out.td_error'].reshape(-1)),
+               'y_td': rel_err(out['y_td'], g[pre + 'out.y_td'].reshape(-1)),
+               'pi_probs': rel_err(out['pi_probs'], g[pre + 'out.pi_probs'])}
+        for i in range(m['E']):
+            for k, v in out['grad_q'][i].items():
+                err[f'grad.q{i}.{k}'] = rel_err(v, g[f'{pre}grad.q{i}.{k}'])
+        for k, v in out['grad_policy'].items():
+            err[f'grad.pi.{k}'] = rel_err(v, g[f'{pre}grad.pi.{k}'])
+        err['grad.log_c_alpha'] = rel_err(out['grad_log_alpha'], g[pre + 'grad.log_c_alpha'].reshape(-1))
+        print('ensemble subset, step', s, sorted(err.items(), key=lambda kv: -kv[1])[:5])
+        _dump(f'sac_sub_s{s}', err)
+        # policy gradient: TOL + 2 x the oracle's own fp32-vs-fp64 gap on this step (the rule of the stage test above)
+        from oracle.sac_oracle import SacOracle
+        grads = []
+        for dtype in (torch.float32, torch.float64):
+            o = SacOracle(hp, dtype=dtype)
+            o.load_params(*golden_params(g, prefix, m['E']))
+            b_, n_ = batch.to(dtype), noise.to(dtype)
+            o.polyak(hp.tau)
+            o.train_q(b_, n_.eps_y, perms[0:2])
+            grads.append(o.train_policy(b_, n_.eps_pi, perms[2])['grad_policy'])
+        gap = {f'grad.pi.{k}': rel_err(grads[0][k].numpy(), grads[1][k].numpy()) for k in grads[0]}
+        bad = {k: v for k, v in err.items() if not v < TOL + 2 * gap.get(k, 0.0) + (2 * TOL if k == 'pi_probs' else 0.0)}
+        assert not bad, (bad, {k: gap.get(k) for k in bad})
+    # the subsets matter: with all three critics the target differs from the reference's
+    g, m, hp, oracle, cuda = _setup('sac_sub.npz')
+    batch, noise = golden_batch(g, 0)
+    full = cuda.staged_step(cuda.make_batch(batch, noise, None))
+    assert rel_err(full['y'], g['s0.out.y'].reshape(-1)) > 1e-3
+
+
 def test_adam_kernel_on_identical_gradients():
     """asac_sac_adam fed the oracle's own gradients for 4 consecutive steps == torch.optim.Adam."""
     g, m, hp, oracle, cuda = _setup('sac_c2.npz')

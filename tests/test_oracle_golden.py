@@ -29,7 +29,7 @@ def test_padding_matches_reference(name):
     check_padding(load_golden(name))
 
 
-@pytest.mark.parametrize('name', ['sac_c2.npz', 'sac_c3.npz', 'sac_odd.npz', 'sac_nois.npz',
+@pytest.mark.parametrize('name', ['sac_c2.npz', 'sac_c3.npz', 'sac_odd.npz', 'sac_nois.npz', 'sac_sub.npz',
                                   'sac_c2_b256.npz', 'sac_c3_b1024.npz'])  # the last two: BASELINE's full shapes
 def test_sac_oracle_matches_reference(name):
     check_sac_steps(load_golden(name))
