@@ -142,6 +142,7 @@ PROTOTYPES = {
     'asac_dnets_forward': (i32, [P(AsacDiscreteConfig), vp, i64, i32, vp, i64, i32, vp, vp]),
     'asac_dnets_backward': (i32, [P(AsacDiscreteConfig), vp, i64, i32, vp, i64, i32, vp, vp, vp]),
     'asac_d_target': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'asac_d_target_dqn': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'asac_d_q_grad': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, f32, vp, vp, vp, vp]),
     'asac_d_pi_grad': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     'asac_d_probs': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp]),

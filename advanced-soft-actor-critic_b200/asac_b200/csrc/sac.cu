@@ -2072,6 +2072,24 @@ extern "C" int asac_d_target(const AsacSacConfig *cfg, const AsacDiscreteConfig 
     return ASAC_OK;
 }
 
+extern "C" int asac_d_target_dqn(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *eval_q, const float *tq,
+                                 const int32_t *perm_target, const int32_t *perm_online, const float *rewards,
+                                 const uint8_t *dones, const uint8_t *last_masks, const uint8_t *padding_masks,
+                                 float *d_y, void *stream) {
+    DDqnArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = d_sizes(d, a.sizes, a.D);
+    if (rc != ASAC_OK) return rc;
+    ASAC_REQUIRE(cfg && eval_q && tq && rewards && dones && last_masks && padding_masks && d_y, "asac_d_target_dqn: null pointer");
+    a.cfg = *cfg; a.branches = d->branches; a.eval_q = eval_q; a.tq = tq;
+    a.perm_target = perm_target; a.perm_online = perm_online;
+    a.Es = (cfg->ensemble_sample > 0 && cfg->ensemble_sample < cfg->ensemble) ? cfg->ensemble_sample : cfg->ensemble;
+    a.rewards = rewards; a.dones = dones; a.last_masks = last_masks; a.padding_masks = padding_masks; a.d_y = d_y;
+    k_d_target_dqn<<<(cfg->batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+    ASAC_LAUNCHED("k_d_target_dqn");
+    return ASAC_OK;
+}
+
 extern "C" int asac_d_q_grad(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *q, const float *actions_full,
                              const float *d_y, const float *weights, float scale, float *d_out, float *loss, float *q_single,
                              void *stream) {

@@ -284,6 +284,54 @@ __global__ void __launch_bounds__(256) k_d_target(const DTargetArgs a) {
     a.d_y[e] = v[0] + sum;
 }
 
+struct DDqnArgs {
+    AsacSacConfig cfg;
+    int branches, D;
+    int sizes[ASAC_MAX_BRANCHES];
+    const float *eval_q;            // [E, B * L, D] ONLINE critics on every row of the window
+    const float *tq;                // [E, B * L, D] target critics
+    const int32_t *perm_target, *perm_online;   // [E] each (the reference's two randperm draws), NULL: identity
+    int Es;                         // pairs taken: ensemble_q_sample
+    const float *rewards;
+    const uint8_t *dones, *last_masks, *padding_masks;
+    float *d_y;
+};
+// get_dqn_like_d_y (sac_base.py:1193-1242, 1363-1383): double DQN on the last solid step — per pair i of the two
+// shuffled stacks, the ONLINE member picks the arg-max action of every branch, the TARGET member is evaluated there;
+// min over the pairs; n-step discounted rewards in front.  One thread per batch element.
+__global__ void __launch_bounds__(256) k_d_target_dqn(const DDqnArgs a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const AsacSacConfig &c = a.cfg;
+    if (e >= c.batch) return;
+    const int L = c.seq_len, b = c.burn_in, n = c.n_step, D = a.D, K = a.branches;
+    int last = n - 1;  // get_last_false_indexes: n - 1 when every step is solid-masked (argmin of all ones is 0)
+    for (int k = n - 1; k >= 0; --k) {
+        const int64_t idx = (int64_t)e * c.bn_stride + b + k;
+        if (!(a.last_masks[idx] | a.padding_masks[idx])) { last = k; break; }
+    }
+    const int64_t row = (int64_t)e * L + b + last + 1;
+    float next_q = INFINITY;
+    for (int j = 0; j < a.Es; ++j) {
+        const int it = a.perm_target ? a.perm_target[j] : j, io = a.perm_online ? a.perm_online[j] : j;
+        const float *qe = a.eval_q + ((int64_t)io * c.batch * L + row) * D;
+        const float *qt = a.tq + ((int64_t)it * c.batch * L + row) * D;
+        float s = 0.f;
+        int cc = 0;
+        for (int k = 0; k < K; ++k) {
+            int best = 0;
+            for (int jj = 1; jj < a.sizes[k]; ++jj)
+                if (qe[cc + jj] > qe[cc + best]) best = jj;   // torch.argmax: first maximum
+            s += qt[cc + best];
+            cc += a.sizes[k];
+        }
+        next_q = fminf(next_q, s / (float)K);
+    }
+    float g = 0.f;
+    for (int k = 0; k < n; ++k) g += c.gamma_ratio[k] * a.rewards[(int64_t)e * c.bn_stride + b + k];
+    const float nd = a.dones[(int64_t)e * c.bn_stride + b + last] ? 0.f : 1.f;
+    a.d_y[e] = g + powf(c.gamma, (float)(last + 1)) * next_q * nd;
+}
+
 struct DQGradArgs {
     int B, L, b, E, branches, D, AF;
     const float *q;            // [E, B, D] online critics on (s_b)

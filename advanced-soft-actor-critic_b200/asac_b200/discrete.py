@@ -64,6 +64,7 @@ class DiscreteBranch:
         for k in range(self.K):
             o = int(self.branch_off[k])
             lowering.bind_parameters(pi_params[k], self.pi[o:o + shapes[k].stride])
+        self.dqn_like = bool(sac.discrete_dqn_like)
         self.log_alpha = torch.full((1,), float(sac._init_log_alpha), **f32)
         self.alpha_m, self.alpha_v = torch.zeros(1, **f32), torch.zeros(1, **f32)
         # per-step buffers
@@ -80,6 +81,8 @@ class DiscreteBranch:
             'pi_probs_d': torch.zeros(B, L - 1, self.D, **f32), 'grad_alpha': torch.zeros(1, **f32),
             'loss_alpha': torch.zeros(1, **f32),
         }
+        if self.dqn_like:
+            self.wk['eq'] = torch.zeros(E, R, self.D, **f32)  # online critics on every row (the arg-max side)
 
     # ------------------------------------------------------------------ helpers
     def _forward(self, params, member_stride, members, x, x_row_stride, rows, out):
@@ -116,7 +119,17 @@ class DiscreteBranch:
         sac, wk, bt = self.sac, self.wk, st['bt']
         B, L, S = sac.batch_size, sac._cfg.seq_len, sac.state_size
         E, P = sac.ensemble_q_num, self.P
-        if not post:  # (post: the logits of the policy after its step are already there, see stage_post)
+        if self.dqn_like:  # get_dqn_like_d_y: no policy in the target (sac_base.py:1193-1242, 1363-1383)
+            self._forward(self.qt, P, E, states_v, S, B * L, wk['tq'])
+            self._forward(self.q, P, E, states_v, S, B * L, wk['eq'])
+            perms = sac._ens_perms[7:9] if post else sac._ens_perms[5:7]   # (target, online) of this _get_y call
+            check(self.lib.asac_d_target_dqn(C.byref(sac._cfg_d), C.byref(self.cfg), ptr(wk['eq']), ptr(wk['tq']),
+                                             ptr(perms[0]), ptr(perms[1]), ptr(bt['rewards']), ptr(bt['dones']),
+                                             ptr(bt['last_masks']), ptr(bt['padding_masks']),
+                                             ptr(wk['d_y_td'] if post else wk['d_y']), _lib.current_stream()),
+                  'd_target_dqn')
+            return
+        if not post:  # (post: the logits of the policy after its step are already there, see stage_alpha)
             self._forward(self.pi, 0, 1, states_pi, S, B * L, wk['pi_logits'])
         self._forward(self.qt, P, E, states_v, S, B * L, wk['tq'])
         check(self.lib.asac_d_target(C.byref(sac._cfg_d), C.byref(self.cfg), ptr(wk['pi_logits']), ptr(wk['tq']),
@@ -167,7 +180,7 @@ class DiscreteBranch:
         sac, wk = self.sac, self.wk
         B, L, S = sac.batch_size, sac._cfg.seq_len, sac.state_size
         self._forward(self.pi, 0, 1, states_pi, S, B * L, wk['pi_logits'])
-        if sac.use_auto_alpha:
+        if sac.use_auto_alpha and not self.dqn_like:  # (DQN-like: no discrete alpha loss, sac_base.py:1924)
             check(self.lib.asac_d_alpha(C.byref(sac._cfg_d), C.byref(self.cfg), ptr(wk['pi_logits']), ptr(self.log_alpha),
                                         ptr(self.alpha_m), ptr(self.alpha_v), ptr(sac._counters[3:]), 1.0,
                                         ptr(wk['grad_alpha']), ptr(wk['loss_alpha']), _lib.current_stream()), 'd_alpha')

@@ -196,12 +196,12 @@ class SAC_Base:
         self.use_n_step_is = use_n_step_is
         self.action_noise = action_noise
         self.use_cuda_graph = use_cuda_graph
-        self.discrete_dqn_like = discrete_dqn_like
+        self.discrete_dqn_like = bool(discrete_dqn_like) and bool(d_action_sizes)
+        self.discrete_dqn_epsilon = discrete_dqn_epsilon
         self._init_log_alpha = init_log_alpha
 
         unsupported = {
             'neither discrete nor continuous actions': not d_action_sizes and not c_action_size,
-            'discrete_dqn_like': bool(d_action_sizes) and bool(discrete_dqn_like),
             'discrete action branches without a replay buffer': bool(d_action_sizes) and not use_replay_buffer,
             'siamese': siamese is not None,
             'use_prediction': use_prediction,
@@ -408,7 +408,7 @@ class SAC_Base:
         self.optimizer_alpha = None
         if self.use_auto_alpha:
             self.optimizer_alpha = _AlphaAdam(self._alpha_m, self._alpha_v, self._counters, lr,
-                                              d_state=(dq.alpha_m, dq.alpha_v) if dq is not None else None,
+                                              d_state=(dq.alpha_m, dq.alpha_v) if (dq is not None and not self.discrete_dqn_like) else None,
                                               c_enabled=self._c_enabled)
 
         # ---- C structs
@@ -587,7 +587,9 @@ class SAC_Base:
         # The sampled batch lives in a "batch set" (sample outputs, gathered windows, the C structs pointing
         # at them).  Two sets: while the networks train on one, the NEXT step's sample + gather fill the
         # other on a parallel branch (ASAC_SAMPLE_AHEAD=0: one set, sample and gather on the critical path).
-        self._ens_perms = torch.zeros(5, E, dtype=torch.int32, device=dev)  # ensemble_q_sample < ensemble_q_num
+        # the step's torch.randperm(E) draws (rows 0-4: ensemble_q_sample < ensemble_q_num, see AsacSacBatch;
+        # rows 5-8: (target, online) shuffles of the DQN-like target in _train_rep_q and in _get_td_error)
+        self._ens_perms = torch.zeros(9, E, dtype=torch.int32, device=dev)
         self._sample_ahead = self.use_replay_buffer and os.environ.get('ASAC_SAMPLE_AHEAD', '1') != '0' \
             and self._bridge is None and self._disc is None  # (those steps run in program order on one stream)
         self._sets = [self._make_batch_set() for _ in range(2 if self._sample_ahead else 1)]
@@ -989,12 +991,24 @@ class SAC_Base:
         if self.d_action_sizes:  # sac_base.py:901-936, 954-956 (policy branch; the DQN-like one is not supported)
             if offline is not None:
                 d_action = offline[..., :D]
+            elif self.discrete_dqn_like:  # arg-max of the first critic, epsilon-greedy while training (:903-925)
+                c_in = c_policy.sample() if self.c_action_size else None
+                d_qs, _ = self.model_q_list[0](state, c_in, obs)
+                d_action = torch.cat([torch.nn.functional.one_hot(q.argmax(dim=-1), k).float()
+                                      for q, k in zip(d_qs.split(self.d_action_sizes, dim=-1), self.d_action_sizes)], dim=-1)
+                if self.train_mode:
+                    batch = d_action.shape[0]
+                    mask = (torch.rand(batch) < self.discrete_dqn_epsilon).to(self.device)
+                    rnd = torch.cat([torch.nn.functional.one_hot(torch.randint(0, k, (batch,), device=self.device), k).float()
+                                     for k in self.d_action_sizes], dim=-1)
+                    d_action[mask] = rnd[mask]
             elif disable_sample:
                 d_action = d_policy.sample_deter().float()
             else:
                 d_action = d_policy.sample()
             actions.append(d_action)
-            probs.append(d_policy.probs)
+            # prob stays 1 for the discrete columns of a DQN-like run (sac_base.py:951-956)
+            probs.append(torch.ones_like(d_policy.probs) if self.discrete_dqn_like else d_policy.probs)
         if self.c_action_size:
             if offline is not None:
                 c_action = offline[..., D:]
@@ -1092,8 +1106,8 @@ class SAC_Base:
     def _enqueue_ensemble_perms(self) -> None:
         """The five torch.randperm(E) draws of a step (sac_base.py:1434, 1436, 1887 and the two of _get_td_error's
         _get_y), keyed by the global step; every rank of a data-parallel learner draws the same ones."""
-        if self._cfg.ensemble_sample:
-            check(self._lib.asac_ensemble_perms(ptr(self._ens_perms), 5, self.ensemble_q_num,
+        if self._cfg.ensemble_sample or self.discrete_dqn_like:
+            check(self._lib.asac_ensemble_perms(ptr(self._ens_perms), 9, self.ensemble_q_num,
                                                 (int(self._seed) if self._seed is not None else 0) ^ 0x5EED,
                                                 ptr(self._counters), _lib.current_stream()), 'ensemble_perms')
 
@@ -1262,6 +1276,7 @@ class SAC_Base:
         rb, st = self.replay_buffer, self._sets[self._cur]
         self._enqueue_sample(st)
         self._enqueue_noise(st, 0)
+        self._enqueue_ensemble_perms()
         self._discrete_step_networks(st)
         if self.use_priority:
             self._enqueue_tree_update(st)
@@ -1297,11 +1312,13 @@ class SAC_Base:
         if c:
             check(lib.asac_sac_policy_backward(cfg, prm, batch, work, stream), 'policy_backward')
             check(lib.asac_sac_reduce_grads(cfg, work, 1, stream), 'reduce_grads')
-        dq.stage_pi(st, states)
-        dq.adam_pi()
+        dqn = self.discrete_dqn_like  # no discrete policy / alpha loss (sac_base.py:1858, 1904-1907, 1924, 2115)
+        if not dqn:
+            dq.stage_pi(st, states)
+            dq.adam_pi()
         if c:
             check(lib.asac_sac_adam(cfg, prm, work, 1, 1.0, stream), 'adam')
-        else:
+        elif not dqn:
             bump(4)
         # _train_alpha, get_l_probs, _get_td_error
         need_post = self.use_auto_alpha or self.use_n_step_is or self.use_priority
@@ -1312,7 +1329,7 @@ class SAC_Base:
             if c:
                 check(lib.asac_sac_reduce_grads(cfg, work, 2, stream), 'reduce_grads')
                 check(lib.asac_sac_adam(cfg, prm, work, 2, 1.0, stream), 'adam')
-            else:
+            elif not dqn:
                 bump(8)
         if c and need_post:
             check(lib.asac_sac_td_error(cfg, prm, work, stream), 'td_error')

@@ -578,6 +578,14 @@ int asac_d_target(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const f
                   const float *actions_full, const float *mu_full, const float *pi_probs_d, const float *rewards,
                   const uint8_t *dones, const uint8_t *last_masks, const uint8_t *padding_masks,
                   const float *log_d_alpha, float *d_y, void *stream);
+/* discrete_dqn_like: d_y of get_dqn_like_d_y (sac_base.py:1193-1242, 1363-1383) — double DQN on the last solid step.
+ * eval_q / tq [E, B * L, D]: online / target critics on every row; perm_target / perm_online int32[E]: the
+ * reference's two torch.randperm draws (member j of one shuffled stack is paired with member j of the other), NULL:
+ * identity. */
+int asac_d_target_dqn(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *eval_q, const float *tq,
+                      const int32_t *perm_target, const int32_t *perm_online, const float *rewards,
+                      const uint8_t *dones, const uint8_t *last_masks, const uint8_t *padding_masks, float *d_y,
+                      void *stream);
 /* critic loss of the discrete part and its gradient w.r.t. the critics' outputs (:1543-1547, 1564-1570) */
 int asac_d_q_grad(const AsacSacConfig *cfg, const AsacDiscreteConfig *d, const float *q, const float *actions_full,
                   const float *d_y, const float *weights, float scale, float *d_out, float *loss, float *q_single,

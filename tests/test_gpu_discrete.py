@@ -40,6 +40,7 @@ def _learner(g, **extra):
                    target_c_alpha=float(hp['target_c_alpha']), target_d_alpha=ratio,
                    d_policy_entropy_penalty=float(hp['d_policy_entropy_penalty']),
                    init_log_alpha=float(hp['init_log_alpha']), use_auto_alpha=bool(hp['use_auto_alpha']),
+                   discrete_dqn_like=bool(float(hp.get('discrete_dqn_like', 0.0))),
                    replay_config={'capacity': 1024}, **extra)
     assert sac._disc is not None and sac._disc.D == sum(sizes)
     return sac
@@ -124,7 +125,7 @@ def _policy_gradient_gap(g, s):
     return {k: rel_err(grads[0][k].numpy(), grads[1][k].numpy()) for k in grads[0] if not k.startswith('d_dense_list')}
 
 
-@pytest.mark.parametrize('name', ['sac_disc.npz', 'sac_hybrid.npz'])
+@pytest.mark.parametrize('name', ['sac_disc.npz', 'sac_hybrid.npz', 'sac_dqn.npz'])
 def test_discrete_step_matches_reference(name):
     from asac_b200 import lowering
     g = load_golden(name)
@@ -137,6 +138,8 @@ def test_discrete_step_matches_reference(name):
         if s > 0:  # ... and its optimizer state is what the previous step left: keep ours (checked below)
             pass
         st = _fill(sac, g, s)
+        if f's{s}.in.perms' in g:  # DQN-like: the reference's (target, online) shuffles of _train_rep_q and _get_td_error
+            sac._ens_perms[5:5 + len(g[f's{s}.in.perms'])].copy_(torch.from_numpy(g[f's{s}.in.perms'].astype(np.int32)))
         sac._discrete_step_networks(st)
         torch.cuda.synchronize()
         pre = f's{s}.'
@@ -150,11 +153,13 @@ def test_discrete_step_matches_reference(name):
                 for k, v in lowering.state_dict_from_flat(sac._q_shape, sac._wk['grad_q'][i], policy=False).items():
                     err[f'grad.q{i}.{k}'] = rel_err(v.cpu().numpy(), g[f'{pre}grad.q{i}.{k}'])
         for k, v in _d_named(sac, dq.wk['grad_pi']).items():
-            err[f'grad.pi.{k}'] = rel_err(v.cpu().numpy(), g[f'{pre}grad.pi.{k}'])
+            if f'{pre}grad.pi.{k}' in g:  # (a DQN-like run leaves the policy's discrete heads without a gradient)
+                err[f'grad.pi.{k}'] = rel_err(v.cpu().numpy(), g[f'{pre}grad.pi.{k}'])
         if sac.c_action_size:
             for k, v in lowering.state_dict_from_flat(sac._pi_shape, sac._wk['grad_pi'], policy=True).items():
                 err[f'grad.pi.{k}'] = rel_err(v.cpu().numpy(), g[f'{pre}grad.pi.{k}'])
-        err['grad.log_d_alpha'] = rel_err(dq.wk['grad_alpha'].cpu().numpy(), g[pre + 'grad.log_d_alpha'].reshape(-1))
+        if pre + 'grad.log_d_alpha' in g:
+            err['grad.log_d_alpha'] = rel_err(dq.wk['grad_alpha'].cpu().numpy(), g[pre + 'grad.log_d_alpha'].reshape(-1))
         if pre + 'out.pi_probs' in g:
             err['pi_probs'] = rel_err(sac._wk['pi_probs_full'].cpu().numpy(), g[pre + 'out.pi_probs'])
         if pre + 'out.td_error' in g:
@@ -181,13 +186,14 @@ def test_discrete_step_matches_reference(name):
     sac.close()
 
 
-@pytest.mark.parametrize('sizes,A', [([3, 4], 0), ([3], 2)])
-def test_discrete_learner_trains_end_to_end(sizes, A):
+@pytest.mark.parametrize('sizes,A,dqn', [([3, 4], 0, False), ([3], 2, False), ([4, 2], 0, True), ([3], 2, True)])
+def test_discrete_learner_trains_end_to_end(sizes, A, dqn):
     """put_episode -> train() x 6 (CUDA graph from the second step on) -> choose_action, discrete-only and hybrid."""
     from algorithm.sac_base import SAC_Base
     D = sum(sizes)
     sac = SAC_Base(obs_names=['vector'], obs_shapes=[(6,)], d_action_sizes=sizes, c_action_size=A, model_abs_dir=None,
-                   nn=_plugin(), seed=5, batch_size=32, n_step=3, replay_config={'capacity': 2048})
+                   nn=_plugin(), seed=5, batch_size=32, n_step=3, discrete_dqn_like=dqn,
+                   replay_config={'capacity': 2048})
     rng = np.random.RandomState(1)
     for _ in range(6):
         T = 40
@@ -198,23 +204,27 @@ def test_discrete_learner_trains_end_to_end(sizes, A):
                         ep_dones=np.zeros((1, T), dtype=bool), ep_probs=rng.rand(1, T, D + A).astype(np.float32),
                         ep_pre_seq_hidden_states=np.zeros((1, T, 0), dtype=np.float32))
     before = [p.detach().clone() for p in sac.model_policy.parameters()]
+    before_q = [p.detach().clone() for p in sac.model_q_list[0].parameters()]
     mu0 = sac.replay_buffer._columns['mu_prob'].clone()
     for i in range(6):
         assert sac.train() == i + 1
     torch.cuda.synchronize()
-    assert all(not torch.equal(a, p) for a, p in zip(before, sac.model_policy.parameters()))
+    assert all(not torch.equal(a, p) for a, p in zip(before_q, sac.model_q_list[0].parameters()))
+    if not dqn:
+        assert all(not torch.equal(a, p) for a, p in zip(before, sac.model_policy.parameters()))
+        assert float(sac.log_d_alpha) != pytest.approx(-2.3, abs=1e-9)
     assert not torch.equal(mu0, sac.replay_buffer._columns['mu_prob'])
-    assert float(sac.log_d_alpha) != pytest.approx(-2.3, abs=1e-9)
     assert torch.isfinite(sac._wk['td_error']).all()
     act, prob, _ = sac.choose_action([rng.randn(5, 6).astype(np.float32)], np.zeros((5, D + A), dtype=np.float32),
                                      np.zeros((5, 0), dtype=np.float32))
     assert act.shape == (5, D + A) and prob.shape == (5, D + A)
     c = 0
-    for k in sizes:  # one-hot per branch, probabilities of a branch sum to one
-        assert np.all(act[:, c:c + k].sum(-1) == 1) and np.allclose(prob[:, c:c + k].sum(-1), 1, atol=1e-5)
+    for k in sizes:  # one-hot per branch; probabilities of a branch sum to one (DQN-like: they stay 1, :951-956)
+        assert np.all(act[:, c:c + k].sum(-1) == 1)
+        assert np.allclose(prob[:, c:c + k].sum(-1), k if dqn else 1, atol=1e-5)
         c += k
     # checkpoint state dicts carry both halves of every optimizer
     sd = sac.optimizer_q_list[0].state_dict()
     assert len(sd['state']) == len(list(sac.model_q_list[0].parameters()))
-    assert set(sac.optimizer_alpha.state_dict()['state']) == ({0, 1} if A else {0})
+    assert set(sac.optimizer_alpha.state_dict()['state']) == ({1} if dqn and A else set() if dqn else {0, 1} if A else {0})
     sac.close()

@@ -141,7 +141,7 @@ def test_unsupported_configurations_fail_loudly(tmp_path):
     nn = _plugin(tmp_path, PLUGIN_TEST, 'nn_plugin5')
     base = dict(obs_names=['v'], obs_shapes=[(6,)], c_action_size=2, model_abs_dir=None, nn=nn)
     with pytest.raises(NotImplementedError):
-        SAC_Base(d_action_sizes=[3], discrete_dqn_like=True, **base)  # (the policy-based discrete branch is supported)
+        SAC_Base(d_action_sizes=[3], ensemble_q_num=3, ensemble_q_sample=2, **base)  # (discrete branches: all critics only)
     with pytest.raises(NotImplementedError):
         SAC_Base(d_action_sizes=[], use_rnd=True, **base)
     with pytest.raises(Exception):
