@@ -140,7 +140,7 @@ PROTOTYPES = {
     'asac_dnets_member_floats': (i64, [P(AsacDiscreteConfig)]),
     'asac_dnets_tiles': (i32, [i32]),
     'asac_dnets_forward': (i32, [P(AsacDiscreteConfig), vp, i64, i32, vp, i64, i32, vp, vp]),
-    'asac_dnets_backward': (i32, [P(AsacDiscreteConfig), vp, i64, i32, vp, i64, i32, vp, vp, vp]),
+    'asac_dnets_backward': (i32, [P(AsacDiscreteConfig), vp, i64, i32, vp, i64, i32, vp, vp, vp, vp]),
     'asac_d_target': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'asac_d_target_dqn': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'asac_d_q_grad': (i32, [P(AsacSacConfig), P(AsacDiscreteConfig), vp, vp, vp, vp, f32, vp, vp, vp, vp]),

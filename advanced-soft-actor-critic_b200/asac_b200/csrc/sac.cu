@@ -2025,12 +2025,12 @@ extern "C" int asac_dnets_forward(const AsacDiscreteConfig *d, const float *para
 
 extern "C" int asac_dnets_backward(const AsacDiscreteConfig *d, const float *params, int64_t member_stride, int members,
                                    const float *x, int64_t x_row_stride, int rows, const float *d_out, float *grad_part,
-                                   void *stream) {
+                                   float *d_x, void *stream) {
     DBwdArgs a;
     int rc = fill_dnets(a.nets, d, params, member_stride, members);
     if (rc != ASAC_OK) return rc;
     ASAC_REQUIRE(x && d_out && grad_part && rows > 0 && x_row_stride >= d->state_size, "asac_dnets_backward: bad arguments");
-    a.x = x; a.x_row_stride = x_row_stride; a.rows = rows; a.d_out = d_out; a.grad_part = grad_part;
+    a.x = x; a.x_row_stride = x_row_stride; a.rows = rows; a.d_out = d_out; a.grad_part = grad_part; a.d_x = d_x;
     a.member_floats = asac_dnets_member_floats(d);
     const int bytes = dbwd_plan(a.nets.S, a.nets.H, a.nets.depth, D_MAX_COLS).total * 4;
     rc = set_smem(k_dnets_backward, bytes, "k_dnets_backward");

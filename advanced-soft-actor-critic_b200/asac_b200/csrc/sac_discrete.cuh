@@ -103,6 +103,7 @@ struct DBwdArgs {
     const float *d_out;    // [members, rows, D]  d loss / d output (already scaled: mean over the batch etc.)
     float *grad_part;      // [row tiles, members, member_floats]  partial gradients in the nets' flat layout
     int64_t member_floats;
+    float *d_x;            // optional [members, branches, rows, S]: d loss / d input row (trained representation)
 };
 
 struct DBwdPlan {
@@ -189,6 +190,18 @@ __global__ void __launch_bounds__(NT) k_dnets_backward(const DBwdArgs a) {
             layer_input_grad(H, dZ, lda, Ws, dY, dX, true, part, swz);  // ends with a CTA barrier
             pipe_release(pipe);
             cur = (cur + 2) % 3;
+        } else if (a.d_x) {
+            // first layer's input gradient (the critics' share of d loss / d state, sac_base.py:1573-1601)
+            const int S = s.in_dim;
+            const float *W0 = prm + net_w_off(s, 0);
+            float *dx = a.d_x + (((int64_t)member * n.branches + k) * a.rows + r0) * S;
+            for (int t = tid; t < rows * S; t += NT) {
+                const int r = t / S, kk = t - r * S;
+                float acc = 0.f;
+                for (int h = 0; h < H; ++h) acc = fmaf(dZ[r * lda + h], __ldg(W0 + (int64_t)h * S + kk), acc);
+                if (S == H) acc += dY[r * lda + kk];  // residual first block
+                dx[t] = acc;
+            }
         }
     }
 }

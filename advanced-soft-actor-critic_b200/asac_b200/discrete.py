@@ -90,9 +90,10 @@ class DiscreteBranch:
         check(self.lib.asac_dnets_forward(C.byref(self.cfg), ptr(params), member_stride, members, x.data_ptr(), x_row_stride,
                                           rows, ptr(out), _lib.current_stream()), 'dnets_forward')
 
-    def _backward(self, params, member_stride, members, x, x_row_stride, rows, d_out, grad_part):
+    def _backward(self, params, member_stride, members, x, x_row_stride, rows, d_out, grad_part, d_x=None):
         check(self.lib.asac_dnets_backward(C.byref(self.cfg), ptr(params), member_stride, members, x.data_ptr(), x_row_stride,
-                                           rows, ptr(d_out), ptr(grad_part), _lib.current_stream()), 'dnets_backward')
+                                           rows, ptr(d_out), ptr(grad_part), ptr(d_x), _lib.current_stream()),
+              'dnets_backward')
 
     def _adam(self, param, m, v, part, tiles, count, grad, counter_index):
         sac = self.sac
@@ -119,6 +120,15 @@ class DiscreteBranch:
         sac, wk, bt = self.sac, self.wk, st['bt']
         B, L, S = sac.batch_size, sac._cfg.seq_len, sac.state_size
         E, P = sac.ensemble_q_num, self.P
+        if post and states_v.data_ptr() != states_pi.data_ptr() and not self.dqn_like:
+            # trained representation: _get_td_error's _get_y runs the policy on the TARGET representation's states
+            # (sac_base.py:2226-2233), the probabilities of get_l_probs (the mu side) on the re-encoded ones
+            if 'pi_logits_v' not in wk:
+                wk['pi_logits_v'] = torch.zeros_like(wk['pi_logits'])
+            self._forward(self.pi, 0, 1, states_v, S, B * L, wk['pi_logits_v'])
+            logits_v = wk['pi_logits_v']
+        else:
+            logits_v = wk['pi_logits']
         if self.dqn_like:  # get_dqn_like_d_y: no policy in the target (sac_base.py:1193-1242, 1363-1383)
             self._forward(self.qt, P, E, states_v, S, B * L, wk['tq'])
             self._forward(self.q, P, E, states_v, S, B * L, wk['eq'])
@@ -132,14 +142,15 @@ class DiscreteBranch:
         if not post:  # (post: the logits of the policy after its step are already there, see stage_alpha)
             self._forward(self.pi, 0, 1, states_pi, S, B * L, wk['pi_logits'])
         self._forward(self.qt, P, E, states_v, S, B * L, wk['tq'])
-        check(self.lib.asac_d_target(C.byref(sac._cfg_d), C.byref(self.cfg), ptr(wk['pi_logits']), ptr(wk['tq']),
+        check(self.lib.asac_d_target(C.byref(sac._cfg_d), C.byref(self.cfg), ptr(logits_v), ptr(wk['tq']),
                                      ptr(bt['actions_full']), ptr(bt['mu_full']),
                                      ptr(wk['pi_probs_d']) if post else None, ptr(bt['rewards']), ptr(bt['dones']),
                                      ptr(bt['last_masks']), ptr(bt['padding_masks']), ptr(self.log_alpha),
                                      ptr(wk['d_y_td'] if post else wk['d_y']), _lib.current_stream()), 'd_target')
 
-    def stage_q(self, st, states, scale: float) -> None:
-        """Critic loss of the discrete part, backward, partial gradients (no Adam yet)."""
+    def stage_q(self, st, states, scale: float, want_dx: bool = False) -> None:
+        """Critic loss of the discrete part, backward, partial gradients (no Adam yet).  ``want_dx``: also
+        d loss_i / d state[:, b] of every member and branch into wk['d_x'] [E, K, B, S] (trained representation)."""
         sac, wk, bt = self.sac, self.wk, st['bt']
         B, L, S, b = sac.batch_size, sac._cfg.seq_len, sac.state_size, sac.burn_in_step
         E, P = sac.ensemble_q_num, self.P
@@ -149,7 +160,9 @@ class DiscreteBranch:
         check(self.lib.asac_d_q_grad(C.byref(sac._cfg_d), C.byref(self.cfg), ptr(wk['q_b']), ptr(bt['actions_full']),
                                      ptr(wk['d_y']), ptr(w), float(scale), ptr(wk['dq_out']), ptr(wk['loss_q']),
                                      ptr(wk['q_single']), _lib.current_stream()), 'd_q_grad')
-        self._backward(self.q, P, E, x, L * S, B, wk['dq_out'], wk['grad_q_part'])
+        if want_dx and 'd_x' not in wk:
+            wk['d_x'] = torch.zeros(E, self.K, B, S, dtype=torch.float32, device=sac.device)
+        self._backward(self.q, P, E, x, L * S, B, wk['dq_out'], wk['grad_q_part'], wk['d_x'] if want_dx else None)
 
     def adam_q(self) -> None:
         wk, E, P = self.wk, self.sac.ensemble_q_num, self.P

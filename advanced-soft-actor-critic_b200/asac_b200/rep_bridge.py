@@ -93,11 +93,12 @@ class TorchRepBridge:
                 p.grad = want
             off += p.numel()
 
-    def backward(self, states: torch.Tensor, grad_state: torch.Tensor) -> None:
+    def backward(self, states: torch.Tensor, grad_state_b: torch.Tensor) -> None:
         """d(sum_i mean loss_i) / d rep params: the critics only see state[:, burn_in] (sac_base.py:1516-1601),
-        ``grad_state`` [E, B, S] is what k_q_backward wrote for every member."""
+        ``grad_state_b`` [B, S] = the sum over the members (and over the discrete heads) of what the critic backward
+        kernels wrote."""
         g = torch.zeros_like(states)
-        g[:, self.b] = grad_state.sum(dim=0)
+        g[:, self.b] = grad_state_b
         self.zero_grad()
         with self._math():
             torch.autograd.backward([states], [g], inputs=self.params)

@@ -202,7 +202,6 @@ class SAC_Base:
 
         unsupported = {
             'neither discrete nor continuous actions': not d_action_sizes and not c_action_size,
-            'discrete action branches without a replay buffer': bool(d_action_sizes) and not use_replay_buffer,
             'siamese': siamese is not None,
             'use_prediction': use_prediction,
             'curiosity': curiosity is not None,
@@ -309,6 +308,8 @@ class SAC_Base:
             lowered = lowering.analyze_rep(self.model_rep, self.obs_shapes, A)
             if lowered is not None and os.environ.get('ASAC_REP_BRIDGE', '1') == '2':  # tests: stock GRU through torch
                 raise lowering.NotStockNetwork('ASAC_REP_BRIDGE=2')
+            if lowered is not None and self.d_action_sizes:  # the fused GRU step has no discrete stages
+                raise lowering.NotStockNetwork('stock GRU with discrete action branches')
         except lowering.NotStockNetwork as e:
             if os.environ.get('ASAC_REP_BRIDGE', '1') == '0':
                 raise
@@ -380,8 +381,8 @@ class SAC_Base:
         self._pi_m, self._pi_v = torch.zeros_like(self._pi_flat), torch.zeros_like(self._pi_flat)
         self._disc = None
         if self.d_action_sizes:
-            if self._gru is not None or self._bridge is not None:
-                raise NotImplementedError('discrete action branches together with a trained representation')
+            if self._gru is not None:
+                raise AssertionError('a representation with discrete branches runs as the torch module')
             if self._world > 1:
                 raise NotImplementedError('discrete action branches in the data-parallel learner')
             from .discrete import DiscreteBranch
@@ -517,8 +518,6 @@ class SAC_Base:
         if not self.use_replay_buffer:  # on-policy: every window once, in shuffled batches (sac_base.py:642-646)
             if self._world > 1:
                 raise NotImplementedError('data-parallel learner without a replay buffer')
-            if self._bridge is not None:
-                raise NotImplementedError('on-policy training (use_replay_buffer=False) with a torch-module representation')
             from .batch_buffer import BatchBuffer
             self.batch_buffer = BatchBuffer(burn_in_step=self.burn_in_step, n_step=self.n_step,
                                             padding_action=self._np_padding_action, batch_size=self.batch_size,
@@ -782,7 +781,7 @@ class SAC_Base:
     def get_initial_action(self, batch_size, get_numpy=True):
         if get_numpy:
             return np.repeat(self._np_padding_action[np.newaxis, :], batch_size, axis=0)
-        return self._padding_action.repeat(batch_size, 1)
+        return self._padding_action_full.repeat(batch_size, 1)
 
     def get_initial_seq_hidden_state(self, batch_size, get_numpy=True):
         if get_numpy:
@@ -924,6 +923,10 @@ class SAC_Base:
                                                   pre_seq_hidden_state=tail(ep_pre_attn_states),
                                                   is_prev_hidden_state=False, padding_mask=tail(ep_padding_masks))
             state = state.squeeze(1).contiguous()
+            if self.action_noise is not None or self._disc is not None:  # discrete heads: the plugin's modules
+                action, prob = self._act_from_state_torch(state, [o[:, -1] for o in obs], offline_action,
+                                                          disable_sample, eps)
+                return action.cpu().numpy(), prob.cpu().numpy(), attn_state.squeeze(1).cpu().numpy()
             rows, A = int(state.shape[0]), self.c_action_size
             f32 = dict(dtype=torch.float32, device=self.device)
             out, scratch = torch.empty(2, rows, A, **f32), torch.empty(rows, 2 * A, **f32)
@@ -984,6 +987,12 @@ class SAC_Base:
         else:
             state, hidden = self.model_rep([o.unsqueeze(1) for o in obs], None, None)
         state, hidden = state.squeeze(1), hidden.squeeze(1)
+        action, prob = self._act_from_state_torch(state, obs, offline_action, disable_sample, eps)
+        return action.cpu().numpy(), prob.cpu().numpy(), hidden.cpu().numpy()
+
+    def _act_from_state_torch(self, state, obs, offline_action=None, disable_sample: bool = False, eps=None):
+        """_choose_action (sac_base.py:882-966) from an encoded state with the plugin's policy / critic modules:
+        -> (action, prob) [batch, D + A] on the device."""
         d_policy, c_policy = self.model_policy(state, obs)
         D = self.d_action_summed_size
         offline = None if offline_action is None else torch.as_tensor(offline_action, dtype=torch.float32).to(self.device)
@@ -1027,8 +1036,7 @@ class SAC_Base:
             floor = torch.clamp_min(1 - torch.tanh(x) ** 2, 1e-2)
             actions.append(c_action)
             probs.append(torch.exp(c_policy.log_prob(x)) / floor.prod(-1, keepdim=True))  # operators.py:17-19
-        c_action, prob = torch.cat(actions, dim=-1), torch.cat(probs, dim=-1)
-        return c_action.cpu().numpy(), prob.cpu().numpy(), hidden.cpu().numpy()
+        return torch.cat(actions, dim=-1), torch.cat(probs, dim=-1)
 
     # ------------------------------------------------------------------ ingest
     def put_episode(self, ep_indexes, ep_obses_list, ep_actions, ep_rewards, ep_dones, ep_probs,
@@ -1160,10 +1168,8 @@ class SAC_Base:
 
     def _enqueue_step(self) -> None:
         """One train() on the device, eagerly: picks the batch sets, primes the first batch when needed."""
-        if self._bridge is not None:
-            return self._enqueue_step_bridge()
-        if self._disc is not None:
-            return self._enqueue_step_discrete()
+        if self._bridge is not None or self._disc is not None:
+            return self._enqueue_step_staged()
         cur = (1 - self._cur) if (self._sample_ahead and self._primed) else self._cur
         if self._sample_ahead and not self._primed:
             self._enqueue_sample(self._sets[cur])
@@ -1270,154 +1276,142 @@ class SAC_Base:
         if self.use_n_step_is or rep_c is not None:
             main.wait_stream(side)
 
-    def _enqueue_step_discrete(self) -> None:
-        """One train() with discrete (or hybrid) action branches: the discrete stages of asac_b200/discrete.py
-        interleaved with the staged continuous kernels in the reference's order (sac_base.py:2057-2116, 2556-2605)."""
-        rb, st = self.replay_buffer, self._sets[self._cur]
-        self._enqueue_sample(st)
-        self._enqueue_noise(st, 0)
-        self._enqueue_ensemble_perms()
-        self._discrete_step_networks(st)
-        if self.use_priority:
-            self._enqueue_tree_update(st)
-        if self.use_n_step_is:  # sac_base.py:2598-2605: [discrete probabilities, continuous densities] per row
-            rb.write_back(st['smp']['ids'], 'mu_prob', self._wk['pi_probs_full'], -self.burn_in_step,
-                          st['bt']['padding_masks'])
-
-    def _discrete_step_networks(self, st: dict) -> None:
-        lib, dq, wk, bt = self._lib, self._disc, self._wk, st['bt']
-        cfg, prm, batch, work = C.byref(self._cfg), C.byref(self._prm), C.byref(st['batch']), C.byref(self._work)
-        stream = _lib.current_stream()
-        c = self._c_enabled
-        states = bt['states']
-        bump = lambda mask: check(lib.asac_bump_counters(ptr(self._counters), mask, stream), 'bump_counters')
-        # _update_target_variables
-        if c:
-            check(lib.asac_sac_polyak(cfg, prm, -1.0, stream), 'polyak')
-        dq.polyak()
-        # _train_rep_q: y of both parts, ONE loss per critic, one Adam step per ModelQ
-        dq.stage_target(st, states, states, post=False)
-        if c:
-            check(lib.asac_sac_target_y(cfg, prm, batch, work, stream), 'target_y')
-            check(lib.asac_sac_q_backward(cfg, prm, batch, work, stream), 'q_backward')
-            check(lib.asac_sac_reduce_grads(cfg, work, 0, stream), 'reduce_grads')
-        # `loss += loss + mse` (sac_base.py:1562): without the clipped loss the reference counts the discrete part twice
-        dq.stage_q(st, states, 2.0 if (c and self.clip_epsilon <= 0) else 1.0)
-        dq.adam_q()  # same optimizer as the continuous part: reads the step counter before it advances
-        if c:
-            check(lib.asac_sac_adam(cfg, prm, work, 0, 1.0, stream), 'adam')
-        else:
-            bump(2)
-        # _train_policy
-        if c:
-            check(lib.asac_sac_policy_backward(cfg, prm, batch, work, stream), 'policy_backward')
-            check(lib.asac_sac_reduce_grads(cfg, work, 1, stream), 'reduce_grads')
-        dqn = self.discrete_dqn_like  # no discrete policy / alpha loss (sac_base.py:1858, 1904-1907, 1924, 2115)
-        if not dqn:
-            dq.stage_pi(st, states)
-            dq.adam_pi()
-        if c:
-            check(lib.asac_sac_adam(cfg, prm, work, 1, 1.0, stream), 'adam')
-        elif not dqn:
-            bump(4)
-        # _train_alpha, get_l_probs, _get_td_error
-        need_post = self.use_auto_alpha or self.use_n_step_is or self.use_priority
-        if c and need_post:
-            check(lib.asac_sac_post(cfg, prm, batch, work, stream), 'post')
-        dq.stage_alpha(st, states)
-        if self.use_auto_alpha:
-            if c:
-                check(lib.asac_sac_reduce_grads(cfg, work, 2, stream), 'reduce_grads')
-                check(lib.asac_sac_adam(cfg, prm, work, 2, 1.0, stream), 'adam')
-            elif not dqn:
-                bump(8)
-        if c and need_post:
-            check(lib.asac_sac_td_error(cfg, prm, work, stream), 'td_error')
-            if self.use_n_step_is:
-                wk['pi_probs_full'][..., dq.D:].copy_(wk['pi_probs'])
-        dq.stage_probs_td(st, states, states, states, accumulate_td=c)
-        check(lib.asac_sac_advance_step(prm, stream), 'advance_step')
-
-    def _enqueue_step_bridge(self) -> None:
-        """One train() with a representation that runs as the plugin's torch module (rep_bridge.py): the
-        kernels of the staged step with the three get_l_states passes, the representation's backward and its
-        Adam step in between, in the reference's order (sac_base.py:2057-2116, 2556-2605).  Eager, one stream."""
+    def _enqueue_step_staged(self) -> None:
+        """One train() of a learner whose step is not one of the fused graphs: a representation that runs as the
+        plugin's torch module (rep_bridge.py) and / or discrete action branches (discrete.py).  Sample + gather,
+        the staged networks step, priority update, write-backs (sac_base.py:2556-2605) — one stream, program order."""
         rb, st = self.replay_buffer, self._sets[self._cur]
         bt, smp = st['bt'], st['smp']
         b, L = self.burn_in_step, self._cfg.seq_len
         self._enqueue_sample(st)
         self._enqueue_noise(st, 0)
         self._enqueue_ensemble_perms()
-        hidden_post = self._bridge_step_networks(st)
+        hidden_post = self._staged_step_networks(st)
         if self.use_priority:
             self._enqueue_tree_update(st)
-        # write-backs (sac_base.py:2586-2605)
-        if int(np.prod(self.seq_hidden_state_shape)) != 0:
+        if hidden_post is not None and int(np.prod(self.seq_hidden_state_shape)) != 0:
             hp = hidden_post.reshape(self.batch_size, L, -1).contiguous()
             rb.write_back(smp['ids'], 'pre_seq_hidden_state', hp, 1 - b, bt['padding_masks'], n_rows=L - 1)
-        if self.use_n_step_is:
-            rb.write_back(smp['ids'], 'mu_prob', self._wk['pi_probs'], -b, bt['padding_masks'])
+        if self.use_n_step_is:  # [discrete probabilities, continuous densities] per row
+            rows = self._wk['pi_probs_full'] if self._disc is not None else self._wk['pi_probs']
+            rb.write_back(smp['ids'], 'mu_prob', rows, -b, bt['padding_masks'])
 
-    def _bridge_step_networks(self, st: dict) -> torch.Tensor:
-        """_train + get_l_probs + _get_td_error on the batch held by set `st` (sac_base.py:2057-2116, 2556-2583);
-        -> next_bnx_seq_hidden_states."""
-        lib, br = self._lib, self._bridge
+    _enqueue_step_bridge = _enqueue_step_discrete = _enqueue_step_staged
+
+    def _staged_step_networks(self, st: dict):
+        """_train + get_l_probs + _get_td_error on the batch held by set `st` (sac_base.py:2057-2116, 2556-2583) with
+        the staged kernels, in the reference's order:
+
+            _update_target_variables
+            [representation: states (autograd graph kept), target_states]
+            _train_rep_q:   y of the discrete and the continuous part, ONE loss per critic, one Adam step per ModelQ,
+                            [the representation's share of loss.backward() + its Adam step, re-encoded states]
+            _train_policy:  both parts, one Adam step        _train_alpha: both alphas, one Adam
+            get_l_probs, _get_td_error
+
+        -> next_bnx_seq_hidden_states (None without a torch-module representation)."""
+        lib, br, dq, c = self._lib, self._bridge, self._disc, self._c_enabled
         bt, wk = st['bt'], self._wk
         cfg, prm, batch, work = C.byref(self._cfg), C.byref(self._prm), C.byref(st['batch']), C.byref(self._work)
         stream = _lib.current_stream()
         scale = 1.0 / self._world
         b, L = self.burn_in_step, self._cfg.seq_len
-        check(lib.asac_sac_polyak(cfg, prm, -1.0, stream), 'sac_polyak')
-        check(lib.asac_flat_polyak(ptr(br.flat_target), ptr(br.flat), br.count, ptr(self._counters),
-                                   int(self.update_target_per_step), self._cfg.tau, self._cfg.one_minus_tau, 0,
-                                   stream), 'flat_polyak')
-        # get_bnx_data (sac_base.py:1090-1116) from the b + n stored rows
-        bn_index = bt['index'][:, :L - 1]
-        index = torch.cat([bn_index, bn_index[:, -1:] + (bn_index[:, -1:] != -1)], dim=1)
-        bn_pad = bt['padding_masks'][:, :L - 1].bool()
-        padding = torch.cat([bn_pad, bn_pad[:, -1:]], dim=1)
-        actions = bt['actions'][:, :L - 1]
-        pre_action = torch.cat([torch.zeros_like(actions[:, :1]), actions], dim=1)
-        obs_list = self._process_torch_obs_list(list(bt['obs_list']))
-        hidden = bt['hidden'].view(self.batch_size, L, *self.seq_hidden_state_shape)
-        states, _ = br.l_states(index, padding, obs_list, pre_action, hidden, target=False)
-        with torch.no_grad():
-            target_states, _ = br.l_states(index, padding, obs_list, pre_action, hidden, target=True)
-            bt['states'].copy_(states)
-            bt['target_states'].copy_(target_states)
-        check(lib.asac_sac_target_y(cfg, prm, batch, work, stream), 'target_y')
-        check(lib.asac_sac_q_backward(cfg, prm, batch, work, stream), 'q_backward')
-        check(lib.asac_sac_reduce_grads(cfg, work, 0, stream), 'reduce_grads')
-        adist.all_reduce_sum_(wk['grad_q'])
-        check(lib.asac_sac_adam(cfg, prm, work, 0, scale, stream), 'adam')
-        # the representation's share of loss.backward() and optimizer_rep.step() (sac_base.py:1573-1601)
-        br.backward(states, wk['grad_state'])
-        adist.all_reduce_sum_(br.grad)
-        if self._world > 1:
-            br.grad.mul_(scale)
-        check(lib.asac_flat_reduce_adam(ptr(br.flat), ptr(br.m), ptr(br.v), ptr(br.grad), 1, br.stride, br.count,
-                                        ptr(br.grad_out), ptr(self._counters[4:]), float(self.learning_rate), stream),
-              'flat_reduce_adam')
-        self._counters[4] += 1
-        with torch.no_grad():  # get_l_states with the new weights (sac_base.py:2099-2105)
-            states_post, hidden_post = br.l_states(index, padding, obs_list, pre_action, hidden, target=False)
-            bt['states_post'].copy_(states_post)
-        check(lib.asac_sac_policy_backward(cfg, prm, batch, work, stream), 'policy_backward')
-        check(lib.asac_sac_reduce_grads(cfg, work, 1, stream), 'reduce_grads')
-        adist.all_reduce_sum_(wk['grad_pi'])
-        check(lib.asac_sac_adam(cfg, prm, work, 1, scale, stream), 'adam')
+        bump = lambda mask: check(lib.asac_bump_counters(ptr(self._counters), mask, stream), 'bump_counters')
+        dqn = self.discrete_dqn_like
+        # ---- _update_target_variables
+        if c:
+            check(lib.asac_sac_polyak(cfg, prm, -1.0, stream), 'sac_polyak')
+        if dq is not None:
+            dq.polyak()
+        states_t = post_t = target_t = bt['states']
+        hidden_post = None
+        if br is not None:
+            check(lib.asac_flat_polyak(ptr(br.flat_target), ptr(br.flat), br.count, ptr(self._counters),
+                                       int(self.update_target_per_step), self._cfg.tau, self._cfg.one_minus_tau, 0,
+                                       stream), 'flat_polyak')
+            # get_bnx_data (sac_base.py:1090-1116) from the b + n stored rows
+            bn_index = bt['index'][:, :L - 1]
+            index = torch.cat([bn_index, bn_index[:, -1:] + (bn_index[:, -1:] != -1)], dim=1)
+            bn_pad = bt['padding_masks'][:, :L - 1].bool()
+            padding = torch.cat([bn_pad, bn_pad[:, -1:]], dim=1)
+            actions = (bt['actions_full'] if dq is not None else bt['actions'])[:, :L - 1]
+            pre_action = torch.cat([torch.zeros_like(actions[:, :1]), actions], dim=1)
+            obs_list = self._process_torch_obs_list(list(bt['obs_list']))
+            hidden = bt['hidden'].view(self.batch_size, L, *self.seq_hidden_state_shape)
+            states, _ = br.l_states(index, padding, obs_list, pre_action, hidden, target=False)
+            with torch.no_grad():
+                target_states, _ = br.l_states(index, padding, obs_list, pre_action, hidden, target=True)
+                bt['states'].copy_(states)
+                bt['target_states'].copy_(target_states)
+            post_t, target_t = bt['states_post'], bt['target_states']
+        # ---- _train_rep_q
+        if dq is not None:
+            dq.stage_target(st, states_t, states_t, post=False)
+        if c:
+            check(lib.asac_sac_target_y(cfg, prm, batch, work, stream), 'target_y')
+            check(lib.asac_sac_q_backward(cfg, prm, batch, work, stream), 'q_backward')
+            check(lib.asac_sac_reduce_grads(cfg, work, 0, stream), 'reduce_grads')
+            adist.all_reduce_sum_(wk['grad_q'])
+        if dq is not None:
+            # `loss += loss + mse` (sac_base.py:1562): without the clipped loss the reference counts the discrete part twice
+            dq.stage_q(st, states_t, 2.0 if (c and self.clip_epsilon <= 0) else 1.0, want_dx=br is not None)
+            dq.adam_q()  # same optimizer as the continuous part: reads the step counter before it advances
+        if c:
+            check(lib.asac_sac_adam(cfg, prm, work, 0, scale, stream), 'adam')
+        else:
+            bump(2)
+        if br is not None:
+            # the representation's share of loss.backward() and optimizer_rep.step() (sac_base.py:1573-1601)
+            g = wk['grad_state'].sum(dim=0) if c else torch.zeros_like(wk['grad_state'][0])
+            if dq is not None:
+                g = g + dq.wk['d_x'].sum(dim=(0, 1))
+            br.backward(states, g)
+            adist.all_reduce_sum_(br.grad)
+            if self._world > 1:
+                br.grad.mul_(scale)
+            check(lib.asac_flat_reduce_adam(ptr(br.flat), ptr(br.m), ptr(br.v), ptr(br.grad), 1, br.stride, br.count,
+                                            ptr(br.grad_out), ptr(self._counters[4:]), float(self.learning_rate), stream),
+                  'flat_reduce_adam')
+            bump(16)
+            with torch.no_grad():  # get_l_states with the new weights (sac_base.py:2099-2105)
+                states_post, hidden_post = br.l_states(index, padding, obs_list, pre_action, hidden, target=False)
+                bt['states_post'].copy_(states_post)
+            self._last_bridge = {'states': states.detach(), 'hidden_post': hidden_post}
+        # ---- _train_policy
+        if c:
+            check(lib.asac_sac_policy_backward(cfg, prm, batch, work, stream), 'policy_backward')
+            check(lib.asac_sac_reduce_grads(cfg, work, 1, stream), 'reduce_grads')
+            adist.all_reduce_sum_(wk['grad_pi'])
+        if dq is not None and not dqn:  # (DQN-like: no discrete policy / alpha loss, sac_base.py:1858, 1924)
+            dq.stage_pi(st, post_t)
+            dq.adam_pi()
+        if c:
+            check(lib.asac_sac_adam(cfg, prm, work, 1, scale, stream), 'adam')
+        elif not dqn:
+            bump(4)
+        # ---- _train_alpha, get_l_probs, _get_td_error
         need_post = self.use_auto_alpha or self.use_n_step_is or self.use_priority
-        if need_post:
+        if c and need_post:
             check(lib.asac_sac_post(cfg, prm, batch, work, stream), 'post')
+        if dq is not None:
+            dq.stage_alpha(st, post_t)
         if self.use_auto_alpha:
-            check(lib.asac_sac_reduce_grads(cfg, work, 2, stream), 'reduce_grads')
-            adist.all_reduce_sum_(wk['grad_alpha'])
-            check(lib.asac_sac_adam(cfg, prm, work, 2, scale, stream), 'adam')
-        if need_post:
+            if c:
+                check(lib.asac_sac_reduce_grads(cfg, work, 2, stream), 'reduce_grads')
+                adist.all_reduce_sum_(wk['grad_alpha'])
+                check(lib.asac_sac_adam(cfg, prm, work, 2, scale, stream), 'adam')
+            elif not dqn:
+                bump(8)
+        if c and need_post:
             check(lib.asac_sac_td_error(cfg, prm, work, stream), 'td_error')
+            if dq is not None and self.use_n_step_is:
+                wk['pi_probs_full'][..., dq.D:].copy_(wk['pi_probs'])
+        if dq is not None:
+            dq.stage_probs_td(st, post_t, target_t, post_t, accumulate_td=c)
         check(lib.asac_sac_advance_step(prm, stream), 'advance_step')
-        self._last_bridge = {'states': states.detach(), 'hidden_post': hidden_post}
         return hidden_post
+
+    _bridge_step_networks = _discrete_step_networks = _staged_step_networks
 
     def _enqueue_sac_step_data_parallel(self, stream, batch_struct) -> None:
         """asac_sac_step with a SUM all-reduce of each reduced gradient buffer between the backward
@@ -1460,11 +1454,19 @@ class SAC_Base:
             bt['index'][:, :bn].copy_(bn_indexes)
             bt['last_masks'][:, :bn].copy_(bn_last_masks)
             bt['padding_masks'][:, :bn].copy_(bn_padding_masks)
-            bt['actions'][:, :bn].copy_(bn_actions)
+            D = self.d_action_summed_size
+            if self._disc is not None:
+                bt['actions_full'][:, :bn].copy_(bn_actions)
+                bt['mu_full'][:, :bn].copy_(bn_mu_probs)
+            if self._c_enabled:
+                bt['actions'][:, :bn].copy_(bn_actions[..., D:])
+                bt['mu_probs'][:, :bn].copy_(bn_mu_probs[..., D:])
             bt['rewards'][:, :bn].copy_(bn_rewards)
             bt['dones'][:, :bn].copy_(bn_dones)
-            bt['mu_probs'][:, :bn].copy_(bn_mu_probs)
-            if self._gru is not None:
+            if self._bridge is not None:
+                bt['obs_list'] = [o.to(self.device) for o in bnx_obses_list]
+                bt['hidden'].copy_(bnx_hidden.reshape(bt['hidden'].shape))
+            elif self._gru is not None:
                 bt['obs'].copy_(bnx_obses_list[0])
                 bt['hidden'].copy_(bnx_hidden.reshape(bt['hidden'].shape))
             else:
@@ -1477,7 +1479,9 @@ class SAC_Base:
             stream = _lib.current_stream()
             self._enqueue_noise(st, 0)
             self._enqueue_ensemble_perms()
-            if st['rep'] is not None:
+            if self._bridge is not None or self._disc is not None:
+                self._staged_step_networks(st)
+            elif st['rep'] is not None:
                 check(lib.asac_flat_polyak(ptr(self._rept_flat), ptr(self._rep_flat), self._gru.count,
                                            ptr(self._counters), int(self.update_target_per_step), self._cfg.tau,
                                            self._cfg.one_minus_tau, 0, stream), 'flat_polyak')

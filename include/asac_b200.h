@@ -567,10 +567,11 @@ int asac_dnets_tiles(int rows);                                  /* 16-row tiles
 int asac_dnets_forward(const AsacDiscreteConfig *d, const float *params, int64_t member_stride, int members,
                        const float *x, int64_t x_row_stride, int rows, float *out, void *stream);
 /* the same walk with saved activations, then the backward pass from d_out[member, row, column] = d loss / d output;
- * grad_part[tile, member, member_floats]: partial gradients per 16-row tile (summed by asac_flat_reduce_adam) */
+ * grad_part[tile, member, member_floats]: partial gradients per 16-row tile (summed by asac_flat_reduce_adam);
+ * d_x (may be NULL) [member, branch, row, state_size]: d loss / d input row, for a trained representation */
 int asac_dnets_backward(const AsacDiscreteConfig *d, const float *params, int64_t member_stride, int members,
                         const float *x, int64_t x_row_stride, int rows, const float *d_out, float *grad_part,
-                        void *stream);
+                        float *d_x, void *stream);
 /* d_y[B]: expectation of mean-ensemble Q minus alpha log pi under the policy on rows b..b+n, V-trace with the
  * discrete importance ratio (sac_base.py:1384-1412, 1244-1295).  pi_logits [B * L, D], tq [E, B * L, D];
  * pi_probs_d != NULL: the td-error pass, whose mu probabilities are the policy's own (:2233). */
