@@ -175,8 +175,11 @@ static __device__ __noinline__ int pipe_fill_impl(float *slots, uint64_t *bars, 
         if (j.map) {
             // TMA: K / 32 tensor copies of [N][32] floats, 128-byte swizzle
             bs = Ws + j.N * j.K;
-            if (tid == 0) {
-                fence_proxy_async();  // generic-proxy reads of a recycled slot precede the async-proxy writes
+            // (issued by lane 0 of warp `issued mod 16`: the initial fill of ~10 jobs from thread 0 alone was 2.2 us of
+            // serial expect_tx + TMA issue in every kernel's setup)
+            if (tid == ((issued & (NT / 32 - 1)) << 5)) {
+                // generic-proxy reads of a RECYCLED slot precede the async-proxy writes (a slot's first use has none)
+                if (issued >= n_slots) fence_proxy_async();
                 mbar_expect_tx(bars + slot, (unsigned)(j.N * j.K * 4));
                 for (int seg = 0; seg < (j.K >> 5); ++seg)
                     tma_load_4d(Ws + seg * j.N * 32, j.map, seg * 32, 0, j.layer, j.net, bars + slot);
@@ -222,8 +225,8 @@ __device__ __forceinline__ void pipe_init(WeightPipe &p, float *slots, uint64_t 
     p.slots = slots; p.bars = bars; p.jobs = jobs;
     p.n_slots = n_slots < MAX_WEIGHT_SLOTS ? n_slots : MAX_WEIGHT_SLOTS;
     p.slot_floats = slot_floats; p.n_jobs = n_jobs; p.issued = 0; p.consumed = 0;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < p.n_slots; ++i) mbar_init(bars + i, NT);
+    if ((int)threadIdx.x < p.n_slots) {
+        mbar_init(bars + threadIdx.x, NT);
         fence_mbar_init();
     }
     __syncthreads();
@@ -346,6 +349,81 @@ __device__ __noinline__ void layer_forward_t(const float *X, int ldx, int K4, co
             g_layer_seg[3] += clock64() - c3;     // barrier
             g_layer_seg[4] += 1;
         }
+    }
+}
+
+// Hidden -> hidden pass (K4 == H) with a register tile of RT rows x CT columns per thread (RT * CT * KSPLIT * NT ==
+// 16 * H * KSPLIT ... i.e. RT * CT == 2 * H / 16).  A 128-bit shared load is served one quarter-warp (8 lanes, 128 bytes) per
+// wavefront: the mapping of layer_forward_t (2 x CM, 16 column groups per warp) spends 4 wavefronts on a weight
+// load that fetches 256 distinct bytes and the GEMM phase is bound by those wavefronts (1300 cycles for 512 FFMA
+// issue slots, measured).  With the column group = lane (CT = 2 at H = 64) every weight load fetches 512 distinct
+// bytes and the RT row loads are warp-uniform broadcasts.  Same arithmetic per output in the same order as
+// layer_forward_t (k ascending inside a K quarter, quarters added in order): results are bit-identical.
+template <int CM, bool SWZ, int RT>
+__device__ __noinline__ void layer_forward_hh(const float *X, int ldx, const float *Ws, const float *bs, float *Zs,
+                                              float *Ys, int ldy, int nrows, bool residual, float *part) {
+    ASAC_SMEM(X); ASAC_SMEM(Ws); ASAC_SMEM(bs); ASAC_SMEM(Ys); ASAC_SMEM(part);
+    constexpr int H = 16 * CM, K4 = H, ldw = K4 + 4, KQ = K4 / KSPLIT / 4;  // float4 steps per thread
+    constexpr int CT = 2 * CM / RT, NCG = H / CT, NRG = PASS_ROWS / RT;
+    static_assert(CT >= 1 && CT * RT == 2 * CM && NCG * NRG * KSPLIT == NT, "register tile");
+    const int tid = threadIdx.x, cg = tid % NCG, rg = (tid / NCG) % NRG, ks = tid / (NCG * NRG);
+    const int kb = ks * (K4 / KSPLIT);
+#pragma unroll 1
+    for (int r0 = 0; r0 < nrows; r0 += PASS_ROWS) {
+        const float *ap = X + (r0 + RT * rg) * ldx + kb, *wp = Ws + cg * ldw + kb;
+        const int x7 = cg & 7;
+        float acc[RT][CT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i)
+#pragma unroll
+            for (int c = 0; c < CT; ++c) acc[i][c] = 0.f;
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) {
+            const int k = kb + 4 * q;
+            float4 a[RT], w[CT];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) a[i] = *reinterpret_cast<const float4 *>(ap + i * ldx + 4 * q);
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                // rows cg + NCG c: (row & 7) == (cg & 7) since NCG is a multiple of 8
+                const int row = cg + NCG * c;
+                w[c] = SWZ ? *reinterpret_cast<const float4 *>(Ws + (k >> 5) * (H * 32) + row * 32 + ((((k >> 2) & 7) ^ x7) << 2))
+                           : *reinterpret_cast<const float4 *>(wp + NCG * c * ldw + 4 * q);
+            }
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    acc[i][c] = fmaf(a[i].x, w[c].x, acc[i][c]);
+                    acc[i][c] = fmaf(a[i].y, w[c].y, acc[i][c]);
+                    acc[i][c] = fmaf(a[i].z, w[c].z, acc[i][c]);
+                    acc[i][c] = fmaf(a[i].w, w[c].w, acc[i][c]);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < RT; ++i)
+#pragma unroll
+            for (int c = 0; c < CT; ++c) part[(ks * PASS_ROWS + RT * rg + i) * H + cg + NCG * c] = acc[i][c];
+        __syncthreads();
+        // epilogue: outputs tid, tid + NT, ... of the pass, their dependent chains (partials, erf) interleaved
+        constexpr int PER = PASS_ROWS * H / NT;  // 2 at H = 64
+        float z[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int o = tid + u * NT, j = o & (H - 1);
+            z[u] = bs[j];
+#pragma unroll
+            for (int s = 0; s < KSPLIT; ++s) z[u] += part[s * PASS_ROWS * H + o];
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int o = tid + u * NT, row = o / H, j = o & (H - 1);
+            if (Zs) Zs[(r0 + row) * ldy + j] = z[u];
+            float y = gelu_erf(z[u]);
+            if (residual) y = y + X[(r0 + row) * ldx + j];
+            Ys[(r0 + row) * ldy + j] = y;
+        }
+        __syncthreads();
     }
 }
 
@@ -602,21 +680,68 @@ __host__ __device__ __forceinline__ int head_floats(int hidden, int out_dim) { r
 __device__ __forceinline__ bool tma_layer(const NetShape &s, int l, const CUtensorMap *map) {
     return map != nullptr && l >= 1 && s.hidden >= 32;
 }
+// `lane` >= 0: called by a whole warp, lane n + l writes job n + l (thread 0 alone spent 1.9 us of every kernel's
+// setup building the table); lane < 0: the calling thread writes them all
 __device__ __forceinline__ int push_trunk_jobs(WeightJob *jobs, int n, const NetShape &s, const float *params,
-                                               const CUtensorMap *map = nullptr, int net = 0) {
-    for (int l = 0; l < s.depth; ++l)
-        jobs[n++] = WeightJob{params + net_w_off(s, l), params + net_b_off(s, l), s.hidden, net_k(s, l),
-                              tma_layer(s, l, map) ? map : nullptr, l - 1, net};
+                                               const CUtensorMap *map = nullptr, int net = 0, int lane = -1) {
+    for (int l = 0; l < s.depth; ++l, ++n)
+        if (lane < 0 || lane == n)
+            jobs[n] = WeightJob{params + net_w_off(s, l), params + net_b_off(s, l), s.hidden, net_k(s, l),
+                                tma_layer(s, l, map) ? map : nullptr, l - 1, net};
     return n;
 }
 // appends layers depth-1 .. 1 (the input-gradient passes of a backward walk; no bias needed)
 __device__ __forceinline__ int push_trunk_jobs_reverse(WeightJob *jobs, int n, const NetShape &s, const float *params,
-                                                       const CUtensorMap *map = nullptr, int net = 0) {
-    for (int l = s.depth - 1; l >= 1; --l)
-        jobs[n++] = WeightJob{params + net_w_off(s, l), nullptr, s.hidden, s.hidden,
-                              tma_layer(s, l, map) ? map : nullptr, l - 1, net};
+                                                       const CUtensorMap *map = nullptr, int net = 0, int lane = -1) {
+    for (int l = s.depth - 1; l >= 1; --l, ++n)
+        if (lane < 0 || lane == n)
+            jobs[n] = WeightJob{params + net_w_off(s, l), nullptr, s.hidden, s.hidden,
+                                tma_layer(s, l, map) ? map : nullptr, l - 1, net};
     return n;
 }
+// The same tables built by ONE WARP, lane j writing job j in closed form: a kernel's table is a sequence of up to
+// four segments (a net's trunk in forward order, or its layers depth-1 .. 1 for the input-gradient walk).
+struct JobSegment {
+    const float *params;
+    const CUtensorMap *map;
+    NetShape s;
+    int net;
+    int reverse;  // 0: layers 0 .. depth-1 with bias; 1: layers depth-1 .. 1 without
+};
+__device__ __forceinline__ int segment_jobs(const JobSegment &g) { return g.reverse ? g.s.depth - 1 : g.s.depth; }
+__device__ __forceinline__ void write_segment_job(WeightJob *jobs, int lane, int first, const JobSegment &g) {
+    const int i = lane - first;
+    if (i < 0 || i >= segment_jobs(g)) return;
+    const int l = g.reverse ? g.s.depth - 1 - i : i;
+    jobs[lane] = WeightJob{g.params + net_w_off(g.s, l), g.reverse ? nullptr : g.params + net_b_off(g.s, l), g.s.hidden,
+                           g.reverse ? g.s.hidden : net_k(g.s, l), tma_layer(g.s, l, g.map) ? g.map : nullptr, l - 1, g.net};
+}
+// lane < 32 of one warp; segments with params == nullptr are skipped
+__device__ __forceinline__ void write_job_table(WeightJob *jobs, int lane, const JobSegment &g0, const JobSegment &g1,
+                                                const JobSegment &g2, const JobSegment &g3) {
+    // pick the lane's segment first (a handful of compares), then build ONE job
+    const int n0 = g0.params ? segment_jobs(g0) : 0, n1 = g1.params ? segment_jobs(g1) : 0,
+              n2 = g2.params ? segment_jobs(g2) : 0, n3 = g3.params ? segment_jobs(g3) : 0;
+    const int f1 = n0, f2 = n0 + n1, f3 = n0 + n1 + n2;
+    if (lane < f1) write_segment_job(jobs, lane, 0, g0);
+    else if (lane < f2) write_segment_job(jobs, lane, f1, g1);
+    else if (lane < f3) write_segment_job(jobs, lane, f2, g2);
+    else if (lane < f3 + n3) write_segment_job(jobs, lane, f3, g3);
+}
+// descriptor fetch of a TMA tensor map ahead of its first copy (kernel entry, one thread)
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// Per-layer activation buffers of a saved forward pass: layer l at base + l * stride.  (Pointer arrays indexed by the
+// layer live in local memory: filling and reading them cost ~300 instructions of every backward kernel's setup.)
+struct LayerBufs {
+    float *base;
+    int stride;
+    __device__ LayerBufs(float *b, int s) : base(b), stride(s) {}
+    __device__ LayerBufs(decltype(nullptr)) : base(nullptr), stride(0) {}
+    __device__ __forceinline__ float *operator[](int l) const { return base + l * stride; }
+};
 
 // Runs the `depth` ResBlocks of a stock net over rows held in `x0` (nrows x lda, input columns
 // [0, in_dim) valid, pad columns up to round_up(in,4) zero); the pipe's next `depth` jobs must be
@@ -624,7 +749,7 @@ __device__ __forceinline__ int push_trunk_jobs_reverse(WeightJob *jobs, int n, c
 //   save == nullptr : ping-pongs between bufA and bufB, returns the buffer holding the output
 //   save != nullptr : layer l reads save_x[l] and writes z to save_z[l], y to save_x[l+1]
 __device__ __forceinline__ float *net_trunk_forward(const NetShape &s, WeightPipe &pipe, float *x0, float *bufA,
-                                                    float *bufB, float **save_x, float **save_z, int lda, int nrows,
+                                                    float *bufB, LayerBufs save_x, LayerBufs save_z, int lda, int nrows,
                                                     float *part) {
     const int H = s.hidden;
     float *x = x0;
@@ -634,8 +759,8 @@ __device__ __forceinline__ float *net_trunk_forward(const NetShape &s, WeightPip
         const bool swz = pipe_front_swizzled(pipe);
         pipe_acquire(pipe, Ws, bs);
         const int K = net_k(s, l);
-        float *y = save_x ? save_x[l + 1] : (x == bufA ? bufB : bufA);
-        layer_forward(H, x, lda, round_up(K, 4), Ws, bs, save_z ? save_z[l] : nullptr, y, lda, nrows, K == H, part,
+        float *y = save_x.base ? save_x[l + 1] : (x == bufA ? bufB : bufA);
+        layer_forward(H, x, lda, round_up(K, 4), Ws, bs, save_z.base ? save_z[l] : nullptr, y, lda, nrows, K == H, part,
                       swz);
         pipe_release(pipe);  // layer_forward ends with a CTA barrier
         x = y;

@@ -33,6 +33,8 @@ struct SacArgs {
     AsacSacWork wrk;
     int tile_batch;  // batch elements per CTA
     int mode;        // value pass: 0 = train (_get_y), 1 = post (alpha loss, l_probs, td error)
+    int plan[24];    // the launching kernel's shared-memory plan (ValuePlan / GradPlan), computed on the host: every
+                     // thread re-deriving it cost ~150 instructions with two integer divisions at kernel entry
 };
 
 __host__ __device__ __forceinline__ NetShape q_shape(const AsacSacConfig &c) {
@@ -77,6 +79,16 @@ __device__ long long g_phase_clock[3][32];
     do {                                                                              \
         if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_phase_clock[k][i] = clock64(); \
     } while (0)
+
+// Kernel parameters live in a constant bank that every SM faults in line by line on first use: the ~1.2 KB of
+// SacArgs read field after field by the setup code cost ~2 us of serial misses at the top of every kernel (measured
+// with the phase clocks).  Each warp touches a different 64-byte line first, so the misses overlap.
+__device__ __forceinline__ void warm_kernel_params(const SacArgs &a) {
+    const int *words = reinterpret_cast<const int *>(&a);
+    int acc = 0;
+    for (int off = (threadIdx.x >> 5) * 16; off < (int)(sizeof(SacArgs) / 4); off += (NT / 32) * 16) acc ^= words[off];
+    asm volatile("" ::"r"(acc));
+}
 
 constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
 
@@ -233,6 +245,7 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
 __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacArgs a) {
     pdl_wait();
     pdl_trigger();
+    warm_kernel_params(a);
     cg::cluster_group cluster = cg::this_cluster();
     const int net = (int)cluster.block_rank();
     extern __shared__ float4 smem4[];
@@ -257,7 +270,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     const float *st_v = post && a.bat.target_states ? a.bat.target_states : st_p;
     const bool split = post && c.rep_kind != 0;  // value rows run through the policy separately (rows RP ...)
     const int RPt = RP + (split ? RV : 0);
-    const ValuePlan pl = value_plan(c, TB, a.mode);
+    const ValuePlan &pl = *reinterpret_cast<const ValuePlan *>(a.plan);
     const int lda = pl.lda;
     float *xin = sm + pl.off_xin, *bufA = sm + pl.off_a, *bufB = sm + pl.off_b;
     float *ho = sm + pl.off_ho, *xs = sm + pl.off_xs, *logp = sm + pl.off_logp, *qmin = sm + pl.off_qmin;
@@ -270,12 +283,14 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     // ---- weight pipe: policy trunk, target critic `net`, (post) online critic `net`
     WeightJob *jobs = reinterpret_cast<WeightJob *>(sm + pl.off_pipe);
     uint64_t *bars = reinterpret_cast<uint64_t *>(jobs + MAX_WEIGHT_JOBS);
-    if (tid == 0) {
+    if (tid < 32) {  // one lane per job
         const CUtensorMap *mq = a.use_tma ? &a.maps[0] : nullptr, *mt = a.use_tma ? &a.maps[1] : nullptr,
                           *mp = a.use_tma ? &a.maps[2] : nullptr;
-        int nj = push_trunk_jobs(jobs, 0, ps, a.prm.pi, mp, 0);
-        nj = push_trunk_jobs(jobs, nj, qsh, a.prm.q_target + net * q_stride, mt, net);
-        if (post) nj = push_trunk_jobs(jobs, nj, qsh, a.prm.q + net * q_stride, mq, net);
+        if (a.use_tma && tid < 3 && (tid != 0 || post)) prefetch_tensormap(&a.maps[tid]);
+        write_job_table(jobs, tid, JobSegment{a.prm.pi, mp, ps, 0, 0},
+                        JobSegment{a.prm.q_target + net * q_stride, mt, qsh, net, 0},
+                        JobSegment{post ? a.prm.q + net * q_stride : nullptr, mq, qsh, net, 0},
+                        JobSegment{nullptr, nullptr, qsh, 0, 0});
     }
     float *head_pi = sm + pl.off_heads, *head_qt = head_pi + head_floats(ps.hidden, 2 * A),
           *head_q = head_qt + head_floats(qsh.hidden, 1);
@@ -549,6 +564,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
 __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacArgs a) {
     pdl_wait();
     pdl_trigger();
+    warm_kernel_params(a);
     ASAC_PHASE(1, 0);
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
@@ -556,7 +572,7 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
     const int tid = threadIdx.x;
     const int B = c.batch, L = c.seq_len, b = c.burn_in, S = c.state_size, A = c.action_size, E = c.ensemble;
     const int TB = a.tile_batch, e0 = blockIdx.x * TB, TBa = min(TB, B - e0), net = blockIdx.y;
-    const GradPlan pl = grad_plan(c, false);
+    const GradPlan &pl = *reinterpret_cast<const GradPlan *>(a.plan);
     const int lda = pl.lda, R = PASS_ROWS;
     const NetShape qsh = q_shape(c);
     const int d = qsh.depth, H = qsh.hidden;
@@ -564,23 +580,25 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
     const float *prm = a.prm.q + net * q_stride;
     float *gout = a.wrk.grad_q_part + ((int64_t)blockIdx.x * E + net) * q_stride;
 
-    float *px[ASAC_MAX_DEPTH + 1], *pz[ASAC_MAX_DEPTH];
-    for (int l = 0; l <= d; ++l) px[l] = sm + pl.off_px + l * R * lda;
-    for (int l = 0; l < d; ++l) pz[l] = sm + pl.off_pz + l * R * lda;
+    const LayerBufs px(sm + pl.off_px, R * lda), pz(sm + pl.off_pz, R * lda);
     float *g[3] = {sm + pl.off_g0, sm + pl.off_g1, sm + pl.off_g2};
     float *qout = sm + pl.off_small, *dq = qout + R, *red = sm + pl.off_red, *part = sm + pl.off_part;
     WeightJob *jobs = reinterpret_cast<WeightJob *>(sm + pl.off_pipe);
     uint64_t *bars = reinterpret_cast<uint64_t *>(jobs + MAX_WEIGHT_JOBS);
-    if (tid == 0) {
+    if (tid < 32) {  // one lane per job
         const CUtensorMap *mq = a.use_tma ? &a.maps[0] : nullptr;
-        const int nj = push_trunk_jobs(jobs, 0, qsh, prm, mq, net);
-        push_trunk_jobs_reverse(jobs, nj, qsh, prm, mq, net);
+        if (a.use_tma && tid == 0) prefetch_tensormap(&a.maps[0]);
+        write_job_table(jobs, tid, JobSegment{prm, mq, qsh, net, 0}, JobSegment{prm, mq, qsh, net, 1},
+                        JobSegment{nullptr, nullptr, qsh, 0, 0}, JobSegment{nullptr, nullptr, qsh, 0, 0});
     }
     float *head_q = sm + pl.off_heads + head_floats(c.pi_hidden, 2 * A);
+    ASAC_PHASE(1, 8);
     stage_head(head_q, qsh, prm);
     __syncthreads();
+    ASAC_PHASE(1, 9);
     WeightPipe pipe;
     pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
+    ASAC_PHASE(1, 10);
 
     const int K0 = S + A, K04 = round_up(K0, 4);
     for (int i = tid; i < R * K04; i += NT) {
@@ -673,6 +691,7 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
 __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ SacArgs a) {
     pdl_wait();
     pdl_trigger();
+    warm_kernel_params(a);
     ASAC_PHASE(2, 0);
     cg::cluster_group cluster = cg::this_cluster();
     const int net = (int)cluster.block_rank();
@@ -682,16 +701,14 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     const int tid = threadIdx.x;
     const int B = c.batch, L = c.seq_len, b = c.burn_in, S = c.state_size, A = c.action_size, E = c.ensemble;
     const int TB = a.tile_batch, e0 = blockIdx.x * TB, TBa = min(TB, B - e0);
-    const GradPlan pl = grad_plan(c, true);
+    const GradPlan &pl = *reinterpret_cast<const GradPlan *>(a.plan);
     const int lda = pl.lda, R = PASS_ROWS;
     const NetShape ps = pi_shape(c), qsh = q_shape(c);
     const int dp = ps.depth, Hp = ps.hidden, dqn = qsh.depth, Hq = qsh.hidden;
     const int64_t q_stride = net_stride(qsh), pi_stride = net_stride(ps);
     float *gout = a.wrk.grad_pi_part + (int64_t)blockIdx.x * pi_stride;
 
-    float *px[ASAC_MAX_DEPTH + 1], *pz[ASAC_MAX_DEPTH];
-    for (int l = 0; l <= dp; ++l) px[l] = sm + pl.off_px + l * R * lda;
-    for (int l = 0; l < dp; ++l) pz[l] = sm + pl.off_pz + l * R * lda;
+    const LayerBufs px(sm + pl.off_px, R * lda), pz(sm + pl.off_pz, R * lda);
     float *qin = sm + pl.off_qin;
     float *g[3] = {sm + pl.off_g0, sm + pl.off_g1, sm + pl.off_g2};
     // small: ho[R][2A] (m,s -> mu,sigma), xs[R][A], da[R][A], qv[E][R], dq[R], amin[R]
@@ -703,12 +720,11 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     const float *q_prm = a.prm.q + net * q_stride;
     // ranks != 0 leave before the policy backward: they must not have its weights in flight at exit
     const int n_jobs = pl.n_jobs - (net == 0 ? 0 : dp - 1);
-    if (tid == 0) {
+    if (tid < 32) {  // one lane per job
         const CUtensorMap *mq = a.use_tma ? &a.maps[0] : nullptr, *mp = a.use_tma ? &a.maps[2] : nullptr;
-        int nj = push_trunk_jobs(jobs, 0, ps, a.prm.pi, mp, 0);
-        nj = push_trunk_jobs(jobs, nj, qsh, q_prm, mq, net);
-        nj = push_trunk_jobs_reverse(jobs, nj, qsh, q_prm, mq, net);
-        if (net == 0) nj = push_trunk_jobs_reverse(jobs, nj, ps, a.prm.pi, mp, 0);
+        if (a.use_tma && (tid == 0 || tid == 2)) prefetch_tensormap(&a.maps[tid]);
+        write_job_table(jobs, tid, JobSegment{a.prm.pi, mp, ps, 0, 0}, JobSegment{q_prm, mq, qsh, net, 0},
+                        JobSegment{q_prm, mq, qsh, net, 1}, JobSegment{net == 0 ? a.prm.pi : nullptr, mp, ps, 0, 1});
     }
     float *head_pi = sm + pl.off_heads, *head_q = head_pi + head_floats(Hp, 2 * A);
     stage_head(head_pi, ps, a.prm.pi);
@@ -755,8 +771,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     ASAC_PHASE(2, 3);
     // ---- own critic forward (z saved), then the other members' values over DSMEM
     {
-        float *qz[ASAC_MAX_DEPTH];
-        for (int l = 0; l < dqn; ++l) qz[l] = sm + pl.off_qz + l * R * lda;
+        const LayerBufs qz(sm + pl.off_qz, R * lda);
         float *h = net_trunk_forward(qsh, pipe, qin, g[0], g[1], nullptr, qz, lda, R, part);
         head_forward(h, lda, Hq, head_q, head_q + Hq, 1, TBa, qv + net * R);
         __syncthreads();
@@ -1380,6 +1395,11 @@ extern "C" int asac_sac_tile_batch(const AsacSacConfig *c) {
     // >= 128 CTAs on the 148 SMs) over full 16-row tiles, then the largest tile that fits.
     int want = PASS_ROWS;
     while (want > 1 && c->batch / want < 64) want >>= 1;
+    static const int forced = [] {  // experiments: ASAC_TILE_BATCH=8 / 16
+        const char *e = getenv("ASAC_TILE_BATCH");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced > 0 && forced <= PASS_ROWS) want = forced;
     for (int tb = want; tb >= 1; tb >>= 1) {
         const int need0 = value_plan(*c, tb, 0).total * 4, need1 = value_plan(*c, tb, 1).total * 4;
         if (need0 <= kSmemLimit && need1 <= kSmemLimit) return tb;
@@ -1550,7 +1570,10 @@ static int launch_value_pass(SacArgs &a, int mode, void *stream) {
         ASAC_LAUNCHED("k_value_pass_tc");
         return ASAC_OK;
     }
-    const int bytes = value_plan(a.cfg, a.tile_batch, mode).total * 4;
+    const ValuePlan vp = value_plan(a.cfg, a.tile_batch, mode);
+    static_assert(sizeof(ValuePlan) <= sizeof(a.plan) && sizeof(GradPlan) <= sizeof(a.plan), "SacArgs::plan too small");
+    memcpy(a.plan, &vp, sizeof(vp));
+    const int bytes = vp.total * 4;
     int rc = set_smem(k_value_pass, bytes, "k_value_pass");
     if (rc != ASAC_OK) return rc;
     ASAC_CUDA(launch_ex(k_value_pass, dim3(a.wrk.n_tiles, a.cfg.ensemble), dim3(NT), (size_t)bytes, (cudaStream_t)stream,
@@ -1582,7 +1605,9 @@ extern "C" int asac_sac_q_backward(const AsacSacConfig *cfg, const AsacSacParams
     SacArgs a;
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
-    const int bytes = grad_plan(a.cfg, false).total * 4;
+    const GradPlan gp = grad_plan(a.cfg, false);
+    memcpy(a.plan, &gp, sizeof(gp));
+    const int bytes = gp.total * 4;
     rc = set_smem(k_q_backward, bytes, "k_q_backward");
     if (rc != ASAC_OK) return rc;
     ASAC_CUDA(launch_ex(k_q_backward, dim3(a.wrk.n_tiles, cfg->ensemble), dim3(NT), (size_t)bytes, (cudaStream_t)stream, 0,
@@ -1596,7 +1621,9 @@ extern "C" int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacP
     SacArgs a;
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
-    const int bytes = grad_plan(a.cfg, true).total * 4;
+    const GradPlan gp = grad_plan(a.cfg, true);
+    memcpy(a.plan, &gp, sizeof(gp));
+    const int bytes = gp.total * 4;
     rc = set_smem(k_policy_backward, bytes, "k_policy_backward");
     if (rc != ASAC_OK) return rc;
     ASAC_CUDA(launch_ex(k_policy_backward, dim3(a.wrk.n_tiles, cfg->ensemble), dim3(NT), (size_t)bytes,

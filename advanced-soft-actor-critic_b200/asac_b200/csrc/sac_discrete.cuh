@@ -146,9 +146,7 @@ __global__ void __launch_bounds__(NT) k_dnets_backward(const DBwdArgs a) {
     const int lda = pl.lda;
     const int r0 = blockIdx.x * R;
     const int rows = min(R, a.rows - r0);
-    float *px[ASAC_MAX_DEPTH + 1], *pz[ASAC_MAX_DEPTH];
-    for (int l = 0; l <= d; ++l) px[l] = sm + pl.off_px + l * R * lda;
-    for (int l = 0; l < d; ++l) pz[l] = sm + pl.off_pz + l * R * lda;
+    const LayerBufs px(sm + pl.off_px, R * lda), pz(sm + pl.off_pz, R * lda);
     float *g[3] = {sm + pl.off_g0, sm + pl.off_g1, sm + pl.off_g2};
     float *dO = sm + pl.off_dO, *part = sm + pl.off_part;
     WeightJob *jobs = reinterpret_cast<WeightJob *>(sm + pl.off_pipe);

@@ -47,6 +47,8 @@ def main():
           f'target-critic phase of the last value pass: before trunk {(clk[0, 10] - clk[0, 4]) / 1965.0:.2f}, '
           f'trunk {(clk[0, 11] - clk[0, 10]) / 1965.0:.2f}, head + barrier {(clk[0, 12] - clk[0, 11]) / 1965.0:.2f} us')
     mhz = 1965.0
+    print('k_q_backward setup detail (us): entry->jobs %.2f, stage_head %.2f, pipe_init %.2f, stage x %.2f' % tuple(
+        (clk[1, j] - clk[1, i]) / mhz for i, j in ((0, 8), (8, 9), (9, 10), (10, 1))))
     for k, title in ((0, 'k_value_pass (last launch = post pass)'), (1, 'k_q_backward'), (2, 'k_policy_backward')):
         print(title)
         idx = [i for i in sorted(NAMES[k]) if clk[k, i] != 0 and i in NAMES[k]]
