@@ -185,6 +185,7 @@ PROTOTYPES = {
     'asac_mlp_forward_tcf': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, i32, i32, vp]),
     'asac_mlp_forward_tcf_probe': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, i32, i32, vp, vp]),
     'asac_debug_phase_clocks': (i32, [vp]),
+    'asac_debug_global_stamps': (i32, [vp]),
     'asac_policy_act': (i32, [vp, i32, i32, i32, i32, vp, i64, vp, vp, i32, u64, vp, vp, vp, vp, i32, vp]),
 }
 

@@ -92,6 +92,14 @@ inline cudaError_t launch_ex(void (*kernel)(KP...), dim3 grid, dim3 block, size_
     return cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...);
 }
 
+// ---------------------------------------------------------------- Adam bias corrections
+// beta^t for torch.optim.Adam's float64 bias corrections 1 - beta^t.  exp(t ln beta) instead of pow(beta, t): the
+// double-precision pow sat on the critical path of every optimiser kernel (one thread, ~2 us each) and the result is
+// rounded to float32 anyway (relative error of this form <= 1e-15 |t ln beta|).
+constexpr double ADAM_LN_BETA1 = -0.10536051565782628;   // ln 0.9
+constexpr double ADAM_LN_BETA2 = -0.0010005003335835344;  // ln 0.999
+__device__ __forceinline__ double beta_pow(double ln_beta, double t) { return exp(t * ln_beta); }
+
 // ---------------------------------------------------------------- Philox4x32-10
 struct Philox {
     uint32_t c[4];

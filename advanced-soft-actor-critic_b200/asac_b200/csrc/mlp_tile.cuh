@@ -148,6 +148,8 @@ struct WeightPipe {
     uint64_t *bars;    // n_slots mbarriers (NT deferred arrivals each, one per thread, plus the TMA bytes)
     WeightJob *jobs;   // shared-memory job table
     int n_slots, slot_floats, n_jobs, issued, consumed;
+    int n_open;  // jobs [0, n_open) may be issued (a kernel that starts ahead of its predecessor under programmatic
+                 // dependent launch opens the jobs that read the predecessor's output after griddepcontrol.wait)
 };
 
 // Issues every job whose slot is free; returns the new `issued`.  Executed by ALL threads at
@@ -221,16 +223,22 @@ static __device__ __noinline__ int pipe_fill_impl(float *slots, uint64_t *bars, 
 
 // all threads; `jobs` must already be written (any thread) and published by a CTA barrier
 __device__ __forceinline__ void pipe_init(WeightPipe &p, float *slots, uint64_t *bars, WeightJob *jobs, int n_slots,
-                                          int slot_floats, int n_jobs) {
+                                          int slot_floats, int n_jobs, int n_open = -1) {
     p.slots = slots; p.bars = bars; p.jobs = jobs;
     p.n_slots = n_slots < MAX_WEIGHT_SLOTS ? n_slots : MAX_WEIGHT_SLOTS;
     p.slot_floats = slot_floats; p.n_jobs = n_jobs; p.issued = 0; p.consumed = 0;
+    p.n_open = n_open < 0 ? n_jobs : n_open;
     if ((int)threadIdx.x < p.n_slots) {
         mbar_init(bars + threadIdx.x, NT);
         fence_mbar_init();
     }
     __syncthreads();
-    p.issued = pipe_fill_impl(p.slots, p.bars, p.jobs, p.n_slots, p.slot_floats, p.n_jobs, p.issued, p.consumed);
+    p.issued = pipe_fill_impl(p.slots, p.bars, p.jobs, p.n_slots, p.slot_floats, p.n_open, p.issued, p.consumed);
+}
+// all threads, CTA-uniform: every job may be issued from here on
+__device__ __forceinline__ void pipe_open_all(WeightPipe &p) {
+    p.n_open = p.n_jobs;
+    p.issued = pipe_fill_impl(p.slots, p.bars, p.jobs, p.n_slots, p.slot_floats, p.n_open, p.issued, p.consumed);
 }
 
 // waits for the oldest unconsumed job; returns its staged weights / bias
@@ -263,8 +271,8 @@ __device__ __forceinline__ bool pipe_front_swizzled(const WeightPipe &p) { retur
 // call); refills the freed slot
 __device__ __forceinline__ void pipe_release(WeightPipe &p) {
     ++p.consumed;
-    if (p.issued < p.n_jobs)
-        p.issued = pipe_fill_impl(p.slots, p.bars, p.jobs, p.n_slots, p.slot_floats, p.n_jobs, p.issued, p.consumed);
+    if (p.issued < p.n_open)
+        p.issued = pipe_fill_impl(p.slots, p.bars, p.jobs, p.n_slots, p.slot_floats, p.n_open, p.issued, p.consumed);
 }
 
 // ---------------------------------------------------------------- activation

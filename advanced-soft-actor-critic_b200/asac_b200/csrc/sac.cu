@@ -33,6 +33,7 @@ struct SacArgs {
     AsacSacWork wrk;
     int tile_batch;  // batch elements per CTA
     int mode;        // value pass: 0 = train (_get_y), 1 = post (alpha loss, l_probs, td error)
+    int late_wait;   // experiments: ASAC_POST_LATE=0 keeps griddepcontrol.wait at the top of the post pass
     int plan[24];    // the launching kernel's shared-memory plan (ValuePlan / GradPlan), computed on the host: every
                      // thread re-deriving it cost ~150 instructions with two integer divisions at kernel entry
 };
@@ -88,6 +89,19 @@ __device__ __forceinline__ void warm_kernel_params(const SacArgs &a) {
     int acc = 0;
     for (int off = (threadIdx.x >> 5) * 16; off < (int)(sizeof(SacArgs) / 4); off += (NT / 32) * 16) acc ^= words[off];
     asm volatile("" ::"r"(acc));
+}
+
+// debug: %globaltimer stamps (ns) comparable across SMs — [0] critic backward exit (max over CTAs), [4] first / [5]
+// last policy-backward CTA start, [6] last return of its griddepcontrol.wait (tools/pdl_overlap_probe.py)
+__device__ unsigned long long g_gt[8];
+__device__ __forceinline__ void gt_stamp(int i, bool take_min) {
+#ifdef ASAC_PROBES
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (take_min) atomicMin(&g_gt[i], t); else atomicMax(&g_gt[i], t);
+    }
+#endif
 }
 
 constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
@@ -243,7 +257,12 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
 // policy (duplicated, it is the cheap part) and ONE ensemble member; the member outputs are
 // combined by cluster rank 0 through distributed shared memory (min over i, sac_base.py:1439-1442).
 __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacArgs a) {
-    pdl_wait();
+    // Programmatic dependent launch: the post pass follows the policy's Adam step, which only touches the policy's
+    // parameters — the job table, the critics' heads and the policy rows' states are staged while it drains and
+    // griddepcontrol.wait sits in front of the first read of the policy.  The train pass (and any pass of a run with
+    // a trained representation, whose states come from a kernel just ahead) waits first.
+    const bool late_wait = a.mode == 1 && a.cfg.rep_kind == 0 && a.late_wait;
+    if (!late_wait) pdl_wait();
     pdl_trigger();
     warm_kernel_params(a);
     cg::cluster_group cluster = cg::this_cluster();
@@ -294,14 +313,9 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     }
     float *head_pi = sm + pl.off_heads, *head_qt = head_pi + head_floats(ps.hidden, 2 * A),
           *head_q = head_qt + head_floats(qsh.hidden, 1);
-    stage_head(head_pi, ps, a.prm.pi);
     stage_head(head_qt, qsh, a.prm.q_target + net * q_stride);
     if (post) stage_head(head_q, qsh, a.prm.q + net * q_stride);
-    __syncthreads();
     WeightPipe pipe;
-    pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
-
-    ASAC_PHASE(0, 1);
     // ---- policy over the P rows
     {
         const int S4 = round_up(S, 4);
@@ -325,7 +339,11 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
             }
             xin[r * lda + col] = v;
         }
+        if (late_wait) pdl_wait();  // the policy's Adam step is complete and flushed from here on
+        stage_head(head_pi, ps, a.prm.pi);
         __syncthreads();
+        pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
+        ASAC_PHASE(0, 1);
         float *h = net_trunk_forward(ps, pipe, xin + p_lo * lda, bufA + p_lo * lda, bufB + p_lo * lda, nullptr, nullptr,
                                      lda, p_hi - p_lo, part);
         head_forward(h, lda, ps.hidden, head_pi, head_pi + 2 * A * ps.hidden, 2 * A, min(RPt, p_hi) - p_lo,
@@ -562,7 +580,10 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
 // (sac_base.py:1516, 1539-1570).  Partial gradients are sums over the tile's rows of
 // d(sum_i mean_B loss_i)/d theta_i.
 __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacArgs a) {
-    pdl_wait();
+    // Programmatic dependent launch: the forward pass reads nothing the value pass writes (parameters, batch), so it
+    // runs while the predecessor drains; griddepcontrol.wait sits in front of the first read of y / tq.  (With a
+    // trained representation the states themselves come from a kernel just ahead: wait first.)
+    if (a.cfg.rep_kind != 0) pdl_wait();
     pdl_trigger();
     warm_kernel_params(a);
     ASAC_PHASE(1, 0);
@@ -617,6 +638,7 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
     head_forward(px[d], lda, H, head_q, head_q + H, 1, TBa, qout);
     __syncthreads();
 
+    pdl_wait();  // y, tq: the value pass is complete and flushed from here on
     float loss = 0.f;
     if (tid < R) {
         float gq = 0.f;
@@ -682,6 +704,7 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
         }
     }
     ASAC_PHASE(1, 31);
+    gt_stamp(0, false);
 }
 
 // ------------------------------------------------------------------------------------ policy
@@ -689,8 +712,13 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
 // (s_b, tanh x), min over the cluster, backward through the own critic to the action, sum of
 // the action gradients on rank 0, which then runs the policy backward (sac_base.py:1882-1908).
 __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ SacArgs a) {
-    pdl_wait();
+    // Programmatic dependent launch: the policy forward reads the policy's parameters, the states and the noise —
+    // nothing the critics' Adam step writes — so it runs while that kernel drains; griddepcontrol.wait sits in front
+    // of the first read of the critics' parameters (their head and their weight jobs).  (With a trained
+    // representation the re-encoded states come from the kernel just ahead: wait first.)
+    if (a.cfg.rep_kind != 0) pdl_wait();
     pdl_trigger();
+    gt_stamp(4, true); gt_stamp(5, false);
     warm_kernel_params(a);
     ASAC_PHASE(2, 0);
     cg::cluster_group cluster = cg::this_cluster();
@@ -728,10 +756,9 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     }
     float *head_pi = sm + pl.off_heads, *head_q = head_pi + head_floats(Hp, 2 * A);
     stage_head(head_pi, ps, a.prm.pi);
-    stage_head(head_q, qsh, q_prm);
     __syncthreads();
     WeightPipe pipe;
-    pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, n_jobs);
+    pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, n_jobs, dp);  // policy trunk only
 
     ASAC_PHASE(2, 1);
     // ---- policy forward (saved); with a trained representation: on the re-encoded states (sac_base.py:2107-2113)
@@ -746,6 +773,10 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     head_forward(px[dp], lda, Hp, head_pi, head_pi + 2 * A * Hp, 2 * A, TBa, ho);
     __syncthreads();
 
+    pdl_wait();  // the critics' Adam step is complete and flushed from here on
+    gt_stamp(6, false);
+    stage_head(head_q, qsh, q_prm);
+    pipe_open_all(pipe);
     ASAC_PHASE(2, 2);
     // ---- sample, critic input
     const int K0 = S + A, K04 = round_up(K0, 4);
@@ -1020,7 +1051,7 @@ __global__ void __launch_bounds__(ADAM_PARAMS_PER_CTA *ADAM_TILE_GROUPS) k_reduc
     }
     if (tid == ADAM_PARAMS_PER_CTA * ADAM_TILE_GROUPS - 1 && a.do_adam) {  // a thread of the last warp
         const double t = (double)(a.step[0] + 1);
-        const double bc1 = 1.0 - pow(0.9, t), bc2 = 1.0 - pow(0.999, t);
+        const double bc1 = 1.0 - beta_pow(ADAM_LN_BETA1, t), bc2 = 1.0 - beta_pow(ADAM_LN_BETA2, t);
         s_bc[0] = (float)(-(a.lr / bc1));
         s_bc[1] = (float)sqrt(bc2);
     }
@@ -1092,7 +1123,7 @@ __device__ __forceinline__ void alpha_reduce_adam(const AsacSacParams &prm, cons
         if (do_adam) {
             gr = gr * grad_scale;
             const double t = (double)(prm.counters[3] + 1);
-            const double bc1 = 1.0 - pow(0.9, t), bc2 = 1.0 - pow(0.999, t);
+            const double bc1 = 1.0 - beta_pow(ADAM_LN_BETA1, t), bc2 = 1.0 - beta_pow(ADAM_LN_BETA2, t);
             const float step_size = (float)(-(lr / bc1));
             const float bc2_sqrt = (float)sqrt(bc2);
             const float w1 = (float)(1.0 - 0.9), w2 = (float)(1.0 - 0.999);
@@ -1489,6 +1520,11 @@ static int make_args(SacArgs &a, const AsacSacConfig *cfg, const AsacSacParams *
     a.tile_batch = asac_sac_tile_batch(cfg);
     if (a.tile_batch < 1) return a.tile_batch;
     a.mode = 0;
+    static const int post_late = [] {
+        const char *e = getenv("ASAC_POST_LATE");
+        return e ? atoi(e) : 1;
+    }();
+    a.late_wait = post_late;
     const int tiles = (cfg->batch + a.tile_batch - 1) / a.tile_batch;
     ASAC_REQUIRE(wrk->n_tiles == tiles, "work.n_tiles %d != ceil(B / tile_batch) = %d", wrk->n_tiles, tiles);
     ASAC_UNSUPPORTED(tiles > 1024, "batch %d needs %d tiles (> 1024)", cfg->batch, tiles);
@@ -1668,6 +1704,17 @@ extern "C" int asac_peer_timeouts(int reset) {
     return (int)n;
 }
 
+// (Measured and dropped, round 2: the same step on <= 20 fat CTAs launched as 2-CTA clusters, so that the 64 clusters
+// of the kernel behind it find 64 free TPCs and run their parameter-independent part during the optimiser step.  The
+// overlap worked — every policy-backward CTA started 1.4 us after the critic backward's exit — but 18 CTAs take 10.4 us
+// for what this grid does in 6.2, longer than the part it hides behind: 151.0 vs 149.6 us per step.)
+static int launch_adam_kernel(const AdamArgs &a, void *stream) {
+    ASAC_CUDA(launch_ex(k_reduce_adam, dim3((unsigned)((a.count + ADAM_PARAMS_PER_CTA - 1) / ADAM_PARAMS_PER_CTA)),
+                        dim3(ADAM_PARAMS_PER_CTA * ADAM_TILE_GROUPS), 0, (cudaStream_t)stream, 0, true, a));
+    ASAC_LAUNCHED("k_reduce_adam");
+    return ASAC_OK;
+}
+
 static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacWork *wrk, int which,
                               int do_reduce, int do_adam, float grad_scale, void *stream, int do_td = 0,
                               const AsacPeerTable *peers = nullptr) {
@@ -1707,10 +1754,7 @@ static int launch_reduce_adam(const AsacSacConfig *cfg, const AsacSacParams *prm
     a.do_adam = do_adam;
     a.grad_scale = grad_scale;
     a.lr = cfg->learning_rate;
-    ASAC_CUDA(launch_ex(k_reduce_adam, dim3((unsigned)((a.count + ADAM_PARAMS_PER_CTA - 1) / ADAM_PARAMS_PER_CTA)),
-                        dim3(ADAM_PARAMS_PER_CTA * ADAM_TILE_GROUPS), 0, (cudaStream_t)stream, 0, true, a));
-    ASAC_LAUNCHED("k_reduce_adam");
-    return ASAC_OK;
+    return launch_adam_kernel(a, stream);
 }
 
 static int bump(const AsacSacParams *prm, int mask, void *stream) {
@@ -1778,10 +1822,7 @@ static int flat_reduce_adam(float *param, float *m, float *v, const float *grad_
     a.param = param; a.m = m; a.v = v; a.part = grad_part; a.grad = grad; a.step = step_counter;
     a.count = count; a.tile_stride = tile_stride; a.n_tiles = n_tiles;
     a.write_grad = 1; a.do_adam = 1; a.grad_scale = grad_scale; a.lr = learning_rate;
-    ASAC_CUDA(launch_ex(k_reduce_adam, dim3((unsigned)((count + ADAM_PARAMS_PER_CTA - 1) / ADAM_PARAMS_PER_CTA)),
-                        dim3(ADAM_PARAMS_PER_CTA * ADAM_TILE_GROUPS), 0, (cudaStream_t)stream, 0, true, a));
-    ASAC_LAUNCHED("k_reduce_adam");
-    return ASAC_OK;
+    return launch_adam_kernel(a, stream);
 }
 
 extern "C" int asac_flat_reduce_adam(float *param, float *m, float *v, const float *grad_part, int n_tiles,
@@ -1981,6 +2022,14 @@ extern "C" int asac_policy_act(const float *params, int state_size, int hidden, 
 }
 
 // debug: phase clocks of CTA (0,0) of the last value pass / critic backward / policy backward launch
+// debug (-DASAC_PROBES): reads and resets the %globaltimer stamps (max slots to 0, min slots to ~0)
+extern "C" int asac_debug_global_stamps(uint64_t *out_host) {
+    ASAC_CUDA(cudaMemcpyFromSymbol(out_host, g_gt, sizeof(unsigned long long) * 8));
+    unsigned long long init[8] = {0, ~0ull, 0, 0, ~0ull, 0, 0, 0};
+    ASAC_CUDA(cudaMemcpyToSymbol(g_gt, init, sizeof(init)));
+    return ASAC_OK;
+}
+
 extern "C" int asac_debug_phase_clocks(int64_t *out_host) {
     ASAC_REQUIRE(out_host != nullptr, "asac_debug_phase_clocks: null pointer");
     ASAC_CUDA(cudaMemcpyFromSymbol(out_host, g_phase_clock, sizeof(long long) * 3 * 32));

@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(NT) k_d_alpha(const DAlphaArgs a) {  // NT thr
         const float m = 0.9f * a.m[0] + 0.1f * g;
         const float v = 0.999f * a.v[0] + 0.001f * (g * g);
         a.m[0] = m; a.v[0] = v;
-        const double bc1 = 1.0 - pow(0.9, t), bc2 = 1.0 - pow(0.999, t);
+        const double bc1 = 1.0 - beta_pow(ADAM_LN_BETA1, t), bc2 = 1.0 - beta_pow(ADAM_LN_BETA2, t);
         const float step_size = (float)(a.lr / bc1);
         const float denom = sqrtf(v) / (float)sqrt(bc2) + 1e-8f;
         a.log_d_alpha[0] = a.log_d_alpha[0] - step_size * (m / denom);

@@ -542,6 +542,8 @@ int asac_policy_act(const float *params, int state_size, int hidden, int depth, 
  * pass [0], critic backward [1] and policy backward [2] launch; out_host is int64[3][32], slot 31 is
  * the kernel's exit (tools/phase_breakdown.py prints the differences).  Synchronises. */
 int asac_debug_phase_clocks(int64_t *out_host);
+/* debug (library built with -DASAC_PROBES): 8 %globaltimer stamps (ns) around the critics' Adam step, then reset */
+int asac_debug_global_stamps(uint64_t *out_host);
 
 /* ------------------------------------------------------------------------------------
  * Discrete (and the discrete half of hybrid) action branches — replaces the d_action_sizes paths of
