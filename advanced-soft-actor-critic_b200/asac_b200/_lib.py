@@ -117,6 +117,7 @@ PROTOTYPES = {
     'asac_last_error': (C.c_char_p, []),
     'asac_version': (i32, []),
     'asac_launch_count': (i64, []),
+    'asac_set_pdl': (i32, [i32]),
     'asac_reset_launch_count': (None, []),
     'asac_tree_update': (i32, [vp, i64, vp, vp, i64, vp]),
     'asac_tree_rebuild': (i32, [vp, i64, vp]),

@@ -62,6 +62,7 @@ void count_launch(int n = 1);
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();
+int set_pdl(int on);
 
 // <<<>>> replacement carrying the launch attributes (cluster dimension along y, PDL)
 template <typename... KP, typename... Args>

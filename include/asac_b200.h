@@ -41,6 +41,11 @@ int asac_version(void);
  * (bench.py's gpu_launches) */
 int64_t asac_launch_count(void);
 void asac_reset_launch_count(void);
+/* Programmatic dependent launch of the step's kernels (default on; ASAC_PDL=0 in the environment turns it off):
+ * the critic backward, the policy backward and the post pass start their predecessor-independent part while the
+ * kernel ahead of them drains and wait (griddepcontrol.wait) in front of the first dependent read.  Takes effect
+ * at the next launch / graph capture; returns the previous setting.  Results do not depend on it. */
+int asac_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------
  * Sum tree  — replaces SumTree (algorithm/replay_buffer.py:145-242).

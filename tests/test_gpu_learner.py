@@ -72,6 +72,47 @@ def test_graph_replay_equals_eager(tmp_path, plugin, kw):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize('plugin,kw', [(PLUGIN_TEST, dict()),
+                                       (PLUGIN_PENDULUM, dict(n_step=5, v_lambda=1.0, use_n_step_is=True)),
+                                       (PLUGIN_RNN, dict(burn_in_step=4, n_step=3, seq_encoder='RNN'))])
+def test_programmatic_dependent_launch_does_not_change_results(tmp_path, plugin, kw):
+    """The step's kernels start ahead of their predecessor under programmatic dependent launch and wait
+    (griddepcontrol.wait) in front of their first dependent read: the same learner with the attribute off
+    (asac_set_pdl(0): plain stream order) must hold bit-identical parameters, tree and write-backs."""
+    from asac_b200 import _lib
+    lib = _lib.load()
+    nn = _plugin(tmp_path, plugin, 'nn_plugin')
+    kw = dict(kw)
+    extra = {}
+    if kw.get('seq_encoder') == 'RNN':
+        from algorithm.utils.enums import SEQ_ENCODER
+        kw['seq_encoder'] = SEQ_ENCODER.RNN
+        extra = dict(obs_shapes=((6,),), hidden_shape=(2, 8))
+    learners = []
+    before = lib.asac_set_pdl(1)
+    try:
+        for on in (1, 0):
+            lib.asac_set_pdl(on)
+            sac = _make(nn, graph=True, **extra, **kw)
+            for _ in range(8):
+                sac.train()
+            torch.cuda.synchronize()
+            learners.append(sac)
+    finally:
+        lib.asac_set_pdl(before)
+    a, b = learners
+    mods = lambda s: [s.model_rep, s.model_policy] + list(s.model_q_list) + list(s.model_target_q_list)
+    for ma, mb in zip(mods(a), mods(b)):
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            assert torch.equal(pa, pb)
+    assert torch.equal(a.log_c_alpha, b.log_c_alpha)
+    a.flush_priority_update(); b.flush_priority_update()
+    assert torch.equal(a.replay_buffer._nodes, b.replay_buffer._nodes)
+    assert torch.equal(a.replay_buffer._columns['mu_prob'], b.replay_buffer._columns['mu_prob'])
+    assert torch.equal(a._wk['td_error'], b._wk['td_error'])
+    a.close(); b.close()
+
+
 def test_train_returns_step_until_buffer_exceeds_batch(tmp_path):
     from algorithm.sac_base import SAC_Base
     nn = _plugin(tmp_path, PLUGIN_TEST, 'nn_plugin2')
