@@ -1598,7 +1598,10 @@ extern "C" int asac_sac_value_pass_on_tc(const AsacSacConfig *cfg, int mode) {
 static int launch_value_pass(SacArgs &a, int mode, void *stream) {
     a.mode = mode;
     if (value_pass_on_tc(a.cfg, a.tile_batch, mode)) {
-        const int bytes = value_tc_plan(a.cfg, a.tile_batch, mode).total * 4;
+        const ValueTcPlan tp = value_tc_plan(a.cfg, a.tile_batch, mode);
+        static_assert(sizeof(ValueTcPlan) <= sizeof(a.plan), "SacArgs::plan too small");
+        memcpy(a.plan, &tp, sizeof(tp));
+        const int bytes = tp.total * 4;
         int rc = set_smem(k_value_pass_tc, bytes, "k_value_pass_tc");
         if (rc != ASAC_OK) return rc;
         ASAC_CUDA(launch_ex(k_value_pass_tc, dim3(a.wrk.n_tiles, a.cfg.ensemble), dim3(NT), (size_t)bytes,

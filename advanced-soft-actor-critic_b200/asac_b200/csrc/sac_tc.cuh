@@ -49,8 +49,12 @@ __host__ __device__ __forceinline__ ValueTcPlan value_tc_plan(const AsacSacConfi
 // get_l_probs, y' parts and Q_i(s_b, a_b).  grid (n_tiles, E), cluster (1, E, 1): every rank runs the policy and
 // ONE ensemble member; rank 0 combines over distributed shared memory.
 __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__ SacArgs a) {
-    pdl_wait();
+    // programmatic dependent launch: as in k_value_pass, the post pass of a run without a trained representation
+    // stages its rows while the policy's Adam step drains and waits in front of the first read of the policy
+    const bool late_wait = a.mode == 1 && a.cfg.rep_kind == 0 && a.late_wait;
+    if (!late_wait) pdl_wait();
     pdl_trigger();
+    warm_kernel_params(a);
     cg::cluster_group cluster = cg::this_cluster();
     const int net = (int)cluster.block_rank();
     extern __shared__ float4 smem4[];
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__
     const float *st_v = post && a.bat.target_states ? a.bat.target_states : st_p;
     const bool split = post && c.rep_kind != 0;
     const int RPt = RP + (split ? RV : 0);
-    const ValueTcPlan pl = value_tc_plan(c, TB, a.mode);
+    const ValueTcPlan &pl = *reinterpret_cast<const ValueTcPlan *>(a.plan);  // computed on the host
     float *ho = sm + pl.off_ho, *qo = sm + pl.off_qo, *xs = sm + pl.off_xs, *logp = sm + pl.off_logp;
     float *qmin = sm + pl.off_qmin, *ratio = sm + pl.off_ratio, *qs = sm + pl.off_qs, *red = sm + pl.off_red;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + pl.off_misc + 2);
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__
     TcfJob job = tcf_trunk_job(ps, prm_pi, 0);
     {
         TcfWeights w0;
-        tcf_prefetch(w0, job);
+        if (!late_wait) tcf_prefetch(w0, job);
         const int Kp = job.Kp;
         for (int i = tid; i < (p_hi - p_lo) * Kp; i += NT) {
             const int rl = i / Kp, col = i - rl * Kp, r = p_lo + rl;
@@ -125,6 +129,10 @@ __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__
                 v = st_v[((int64_t)(e0 + e) * L + b + k) * S + col];
             }
             tcf_put(cx, rl, col, Kp, v);
+        }
+        if (late_wait) {
+            pdl_wait();  // the policy's Adam step is complete and flushed from here on
+            tcf_prefetch(w0, job);
         }
         tcf_store(w0, job, cx.w[0][0], cx.w[0][1], cx.bias);
     }
