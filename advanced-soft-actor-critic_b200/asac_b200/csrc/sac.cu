@@ -34,6 +34,9 @@ struct SacArgs {
     int tile_batch;  // batch elements per CTA
     int mode;        // value pass: 0 = train (_get_y), 1 = post (alpha loss, l_probs, td error)
     int late_wait;   // experiments: ASAC_POST_LATE=0 keeps griddepcontrol.wait at the top of the post pass
+    int q_sb_handoff;  // fused step: the policy backward also evaluates Q_i(s_b, a_b) (free rows of its critic pass,
+                       // the critics' weights no longer change within the step) and leaves it in wrk.tq; the post
+                       // pass reads it there instead of running the online critics itself (sac_base.py:2211-2216)
     int plan[24];    // the launching kernel's shared-memory plan (ValuePlan / GradPlan), computed on the host: every
                      // thread re-deriving it cost ~150 instructions with two integer divisions at kernel entry
 };
@@ -172,7 +175,7 @@ struct ValuePlan {
     int n_jobs, n_slots;
     int total;  // floats
 };
-__host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c, int TB, int mode) {
+__host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c, int TB, int mode, int q_sb_handoff = 0) {
     ValuePlan p;
     const int L = c.seq_len, n = c.n_step, A = c.action_size;
     const int t0 = (mode == 1 && c.use_n_step_is) ? 0 : c.burn_in;
@@ -202,7 +205,7 @@ __host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c,
     p.off_pipe = o; o += PIPE_HEADER_FLOATS;
     p.off_slots = o;
     o += 256;  // the slots start on the next 1024-byte boundary (TMA 128-byte swizzle)
-    p.n_jobs = c.pi_depth + c.q_depth + (mode == 1 ? c.q_depth : 0);
+    p.n_jobs = c.pi_depth + c.q_depth + ((mode == 1 && !q_sb_handoff) ? c.q_depth : 0);
     p.n_slots = slots_that_fit(o, p.wsz, p.n_jobs);
     o += p.n_slots * p.wsz;
     p.total = o;
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     const int Lp = L - t0;
     const int RP = TBa * Lp, RV = TBa * (n + 1), RS = TBa;
     const bool need_tq = !post && c.clip_epsilon > 0.f;
+    const bool online = post && !a.q_sb_handoff;  // the online critics' Q_i(s_b, a_b) is computed here
     // which representation's states feed what (sac_base.py:2066-2105, 2558-2582): the train pass sees the
     // online states before the representation's Adam step everywhere; the post pass evaluates the
     // probabilities, the alpha loss and Q_i(s_b, a_b) on the re-encoded online states (st_p) and
@@ -305,16 +309,16 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     if (tid < 32) {  // one lane per job
         const CUtensorMap *mq = a.use_tma ? &a.maps[0] : nullptr, *mt = a.use_tma ? &a.maps[1] : nullptr,
                           *mp = a.use_tma ? &a.maps[2] : nullptr;
-        if (a.use_tma && tid < 3 && (tid != 0 || post)) prefetch_tensormap(&a.maps[tid]);
+        if (a.use_tma && tid < 3 && (tid != 0 || online)) prefetch_tensormap(&a.maps[tid]);
         write_job_table(jobs, tid, JobSegment{a.prm.pi, mp, ps, 0, 0},
                         JobSegment{a.prm.q_target + net * q_stride, mt, qsh, net, 0},
-                        JobSegment{post ? a.prm.q + net * q_stride : nullptr, mq, qsh, net, 0},
+                        JobSegment{online ? a.prm.q + net * q_stride : nullptr, mq, qsh, net, 0},
                         JobSegment{nullptr, nullptr, qsh, 0, 0});
     }
     float *head_pi = sm + pl.off_heads, *head_qt = head_pi + head_floats(ps.hidden, 2 * A),
           *head_q = head_qt + head_floats(qsh.hidden, 1);
     stage_head(head_qt, qsh, a.prm.q_target + net * q_stride);
-    if (post) stage_head(head_q, qsh, a.prm.q + net * q_stride);
+    if (online) stage_head(head_q, qsh, a.prm.q + net * q_stride);
     WeightPipe pipe;
     // ---- policy over the P rows
     {
@@ -486,8 +490,8 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         __syncthreads();
     }
     ASAC_PHASE(0, 5);
-    // ---- post: online critic `net` over the S rows (sac_base.py:2211-2216)
-    if (post) {
+    // ---- post: online critic `net` over the S rows (sac_base.py:2211-2216) unless the policy backward left them
+    if (online) {
         float *h = net_trunk_forward(qsh, pipe, xin + s_row0 * lda, bufA, bufB, nullptr, nullptr, lda,
                                      round_up(RS, PASS_ROWS), part);
         head_forward(h, lda, qsh.hidden, head_q, head_q + qsh.hidden, 1, RS, qs);
@@ -499,10 +503,15 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     float *qmin2 = ensemble_subset(c) && a.bat.ensemble_perms ? sm + pl.off_qmin2 : qmin;
     if (net == 0) {
         combine_value_rows(cluster, c, a.bat.ensemble_perms, post ? 3 : 0, qmin, qmin2, RV);
-        if (post)
+        if (online)
             for (int i = 1; i < E; ++i) {
                 const float *rqs = cluster.map_shared_rank(qs, i);
                 for (int e = tid; e < TBa; e += NT) qs[i * TB + e] = rqs[e];
+            }
+        else if (post)
+            for (int i = tid; i < E * TBa; i += NT) {
+                const int m = i / TBa, e = i - m * TBa;
+                qs[m * TB + e] = __ldcg(a.wrk.tq + (int64_t)m * B + e0 + e);
             }
     }
     cluster.sync();  // remote shared memory stays alive until rank 0 has read it
@@ -780,6 +789,8 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     ASAC_PHASE(2, 2);
     // ---- sample, critic input
     const int K0 = S + A, K04 = round_up(K0, 4);
+    // rows [TBa, 2 TBa) of the same pass: (s_b, stored action) for the td error of the post pass (q_sb_handoff)
+    const bool handoff = a.q_sb_handoff && 2 * TBa <= R;
     for (int i = tid; i < R * K04; i += NT) {
         const int r = i / K04, col = i - r * K04;
         float v = 0.f;
@@ -793,6 +804,10 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
                 xs[r * A + j] = x;
                 v = tanhf(x);
             }
+        } else if (handoff && r < 2 * TBa) {
+            const int e = r - TBa;
+            if (col < S) v = px[0][e * lda + col];
+            else if (col < K0) v = a.bat.actions[((int64_t)(e0 + e) * c.bn_stride + b) * A + (col - S)];
         }
         qin[r * lda + col] = v;
     }
@@ -804,8 +819,9 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     {
         const LayerBufs qz(sm + pl.off_qz, R * lda);
         float *h = net_trunk_forward(qsh, pipe, qin, g[0], g[1], nullptr, qz, lda, R, part);
-        head_forward(h, lda, Hq, head_q, head_q + Hq, 1, TBa, qv + net * R);
+        head_forward(h, lda, Hq, head_q, head_q + Hq, 1, handoff ? 2 * TBa : TBa, qv + net * R);
         __syncthreads();
+        if (handoff && tid < TBa) a.wrk.tq[(int64_t)net * B + e0 + tid] = qv[net * R + TBa + tid];
     }
     cluster.sync();
     for (int i = 0; i < E; ++i) {
@@ -1525,6 +1541,7 @@ static int make_args(SacArgs &a, const AsacSacConfig *cfg, const AsacSacParams *
         return e ? atoi(e) : 1;
     }();
     a.late_wait = post_late;
+    a.q_sb_handoff = 0;
     const int tiles = (cfg->batch + a.tile_batch - 1) / a.tile_batch;
     ASAC_REQUIRE(wrk->n_tiles == tiles, "work.n_tiles %d != ceil(B / tile_batch) = %d", wrk->n_tiles, tiles);
     ASAC_UNSUPPORTED(tiles > 1024, "batch %d needs %d tiles (> 1024)", cfg->batch, tiles);
@@ -1609,7 +1626,7 @@ static int launch_value_pass(SacArgs &a, int mode, void *stream) {
         ASAC_LAUNCHED("k_value_pass_tc");
         return ASAC_OK;
     }
-    const ValuePlan vp = value_plan(a.cfg, a.tile_batch, mode);
+    const ValuePlan vp = value_plan(a.cfg, a.tile_batch, mode, a.q_sb_handoff);
     static_assert(sizeof(ValuePlan) <= sizeof(a.plan) && sizeof(GradPlan) <= sizeof(a.plan), "SacArgs::plan too small");
     memcpy(a.plan, &vp, sizeof(vp));
     const int bytes = vp.total * 4;
@@ -1655,20 +1672,34 @@ extern "C" int asac_sac_q_backward(const AsacSacConfig *cfg, const AsacSacParams
     return ASAC_OK;
 }
 
+static int launch_policy_backward(SacArgs &a, void *stream) {
+    const GradPlan gp = grad_plan(a.cfg, true);
+    memcpy(a.plan, &gp, sizeof(gp));
+    const int bytes = gp.total * 4;
+    int rc = set_smem(k_policy_backward, bytes, "k_policy_backward");
+    if (rc != ASAC_OK) return rc;
+    ASAC_CUDA(launch_ex(k_policy_backward, dim3(a.wrk.n_tiles, a.cfg.ensemble), dim3(NT), (size_t)bytes,
+                        (cudaStream_t)stream, a.cfg.ensemble, true, a));
+    ASAC_LAUNCHED("k_policy_backward");
+    return ASAC_OK;
+}
+
 extern "C" int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
                                         const AsacSacWork *wrk, void *stream) {
     SacArgs a;
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
-    const GradPlan gp = grad_plan(a.cfg, true);
-    memcpy(a.plan, &gp, sizeof(gp));
-    const int bytes = gp.total * 4;
-    rc = set_smem(k_policy_backward, bytes, "k_policy_backward");
-    if (rc != ASAC_OK) return rc;
-    ASAC_CUDA(launch_ex(k_policy_backward, dim3(a.wrk.n_tiles, cfg->ensemble), dim3(NT), (size_t)bytes,
-                        (cudaStream_t)stream, cfg->ensemble, true, a));
-    ASAC_LAUNCHED("k_policy_backward");
-    return ASAC_OK;
+    return launch_policy_backward(a, stream);
+}
+
+// The fused chains hand Q_i(s_b, a_b) from the policy backward to the post pass when a tile's rows leave room for it
+// in the critic pass (2 x tile_batch <= 16) and the post pass runs on the FFMA kernel.  ASAC_Q_HANDOFF=0 disables it.
+static bool q_sb_handoff(const SacArgs &a, bool need_post) {
+    static const int on = [] {
+        const char *e = getenv("ASAC_Q_HANDOFF");
+        return e ? atoi(e) : 1;
+    }();
+    return on && need_post && 2 * a.tile_batch <= PASS_ROWS && !value_pass_on_tc(a.cfg, a.tile_batch, 1);
 }
 
 // fills the kernel-side exchange descriptor for gradient kind `which` (0 critics, 1 policy, 2 alpha)
@@ -1805,9 +1836,10 @@ extern "C" int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacPar
     if ((rc = launch_value_pass(a, 0, stream)) != ASAC_OK) return rc;
     if ((rc = asac_sac_q_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
     if ((rc = launch_reduce_adam(cfg, prm, wrk, 0, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
-    if ((rc = asac_sac_policy_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
-    if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
     const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
+    a.q_sb_handoff = q_sb_handoff(a, need_post) ? 1 : 0;
+    if ((rc = launch_policy_backward(a, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
     if (need_post) {
         ASAC_REQUIRE(bat->eps_td && bat->eps_alpha, "asac_sac_step: missing eps_td / eps_alpha");
         if ((rc = launch_value_pass(a, 1, stream)) != ASAC_OK) return rc;
@@ -1893,9 +1925,10 @@ extern "C" int asac_sac_step_networks_rep(const AsacSacConfig *cfg, const AsacSa
     AsacGruNet again = {rep->params, rep->states_post, rep->hn_post, nullptr};
     if ((rc = asac_gru_forward(&rep->shape, &again, 1, rep->obs, bat->actions, cfg->bn_stride, nullptr, rep->h0,
                                rep->h0_b_stride, B, L, stream)) != ASAC_OK) return rc;
-    if ((rc = asac_sac_policy_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
-    if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
     const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
+    a.q_sb_handoff = q_sb_handoff(a, need_post) ? 1 : 0;
+    if ((rc = launch_policy_backward(a, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_reduce_adam(cfg, prm, wrk, 1, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
     if (need_post) {
         ASAC_REQUIRE(bat->eps_td && bat->eps_alpha, "asac_sac_step: missing eps_td / eps_alpha");
         if ((rc = launch_value_pass(a, 1, stream)) != ASAC_OK) return rc;
