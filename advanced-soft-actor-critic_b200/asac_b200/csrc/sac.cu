@@ -262,9 +262,10 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
 __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacArgs a) {
     // Programmatic dependent launch: the post pass follows the policy's Adam step, which only touches the policy's
     // parameters — the job table, the critics' heads and the policy rows' states are staged while it drains and
-    // griddepcontrol.wait sits in front of the first read of the policy.  The train pass (and any pass of a run with
-    // a trained representation, whose states come from a kernel just ahead) waits first.
-    const bool late_wait = a.mode == 1 && a.cfg.rep_kind == 0 && a.late_wait;
+    // griddepcontrol.wait sits in front of the first read of the policy.  (Also with a trained representation: the
+    // states of the post pass were written before the policy backward, two kernels ahead of that optimiser step.)
+    // The TRAIN pass waits first: with a representation its states come from the kernel just ahead.
+    const bool late_wait = a.mode == 1 && a.late_wait;
     if (!late_wait) pdl_wait();
     pdl_trigger();
     warm_kernel_params(a);
@@ -591,8 +592,8 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
 __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacArgs a) {
     // Programmatic dependent launch: the forward pass reads nothing the value pass writes (parameters, batch), so it
     // runs while the predecessor drains; griddepcontrol.wait sits in front of the first read of y / tq.  (With a
-    // trained representation the states themselves come from a kernel just ahead: wait first.)
-    if (a.cfg.rep_kind != 0) pdl_wait();
+    // trained representation the states come from the GRU forward TWO kernels ahead: the value pass in between waits
+    // for it before it triggers this launch, so they are complete and visible here too.)
     pdl_trigger();
     warm_kernel_params(a);
     ASAC_PHASE(1, 0);
@@ -724,8 +725,8 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     // Programmatic dependent launch: the policy forward reads the policy's parameters, the states and the noise —
     // nothing the critics' Adam step writes — so it runs while that kernel drains; griddepcontrol.wait sits in front
     // of the first read of the critics' parameters (their head and their weight jobs).  (With a trained
-    // representation the re-encoded states come from the kernel just ahead: wait first.)
-    if (a.cfg.rep_kind != 0) pdl_wait();
+    // representation the re-encoded states come from the kernel just ahead: only the job table, the policy's head and
+    // its weight jobs go before the wait.)
     pdl_trigger();
     gt_stamp(4, true); gt_stamp(5, false);
     warm_kernel_params(a);
@@ -773,6 +774,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     // ---- policy forward (saved); with a trained representation: on the re-encoded states (sac_base.py:2107-2113)
     const float *st = a.bat.states_post ? a.bat.states_post : a.bat.states;
     const int S4 = round_up(S, 4);
+    if (a.cfg.rep_kind != 0) pdl_wait();  // states_post: the GRU forward just ahead is complete from here on
     for (int i = tid; i < R * S4; i += NT) {
         const int r = i / S4, col = i - r * S4;
         px[0][r * lda + col] = (r < TBa && col < S) ? st[((int64_t)(e0 + r) * L + b) * S + col] : 0.f;

@@ -49,9 +49,9 @@ __host__ __device__ __forceinline__ ValueTcPlan value_tc_plan(const AsacSacConfi
 // get_l_probs, y' parts and Q_i(s_b, a_b).  grid (n_tiles, E), cluster (1, E, 1): every rank runs the policy and
 // ONE ensemble member; rank 0 combines over distributed shared memory.
 __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__ SacArgs a) {
-    // programmatic dependent launch: as in k_value_pass, the post pass of a run without a trained representation
-    // stages its rows while the policy's Adam step drains and waits in front of the first read of the policy
-    const bool late_wait = a.mode == 1 && a.cfg.rep_kind == 0 && a.late_wait;
+    // programmatic dependent launch: as in k_value_pass, the post pass stages its rows while the policy's Adam step
+    // drains and waits in front of the first read of the policy
+    const bool late_wait = a.mode == 1 && a.late_wait;
     if (!late_wait) pdl_wait();
     pdl_trigger();
     warm_kernel_params(a);
