@@ -33,7 +33,10 @@ struct SacArgs {
     AsacSacWork wrk;
     int tile_batch;  // batch elements per CTA
     int mode;        // value pass: 0 = train (_get_y), 1 = post (alpha loss, l_probs, td error)
-    int late_wait;   // experiments: ASAC_POST_LATE=0 keeps griddepcontrol.wait at the top of the post pass
+    int late_wait;   // 1 inside the fused step chains (asac_sac_step*): the kernels know what runs ahead of them and
+                     // put griddepcontrol.wait behind their predecessor-independent prologue; 0 for the stand-alone
+                     // entry points, whose predecessor is whatever the caller launched: wait first.  ASAC_LATE_WAIT=0
+                     // keeps every wait at the top (experiments)
     int q_sb_handoff;  // fused step: the policy backward also evaluates Q_i(s_b, a_b) (free rows of its critic pass,
                        // the critics' weights no longer change within the step) and leaves it in wrk.tq; the post
                        // pass reads it there instead of running the online critics itself (sac_base.py:2211-2216)
@@ -593,7 +596,9 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
     // Programmatic dependent launch: the forward pass reads nothing the value pass writes (parameters, batch), so it
     // runs while the predecessor drains; griddepcontrol.wait sits in front of the first read of y / tq.  (With a
     // trained representation the states come from the GRU forward TWO kernels ahead: the value pass in between waits
-    // for it before it triggers this launch, so they are complete and visible here too.)
+    // for it before it triggers this launch, so they are complete and visible here too.)  Stand-alone launches
+    // (asac_sac_q_backward after arbitrary work of the caller) wait first.
+    if (!a.late_wait) pdl_wait();
     pdl_trigger();
     warm_kernel_params(a);
     ASAC_PHASE(1, 0);
@@ -726,7 +731,8 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     // nothing the critics' Adam step writes — so it runs while that kernel drains; griddepcontrol.wait sits in front
     // of the first read of the critics' parameters (their head and their weight jobs).  (With a trained
     // representation the re-encoded states come from the kernel just ahead: only the job table, the policy's head and
-    // its weight jobs go before the wait.)
+    // its weight jobs go before the wait.)  Stand-alone launches wait first.
+    if (!a.late_wait) pdl_wait();
     pdl_trigger();
     gt_stamp(4, true); gt_stamp(5, false);
     warm_kernel_params(a);
@@ -1538,11 +1544,7 @@ static int make_args(SacArgs &a, const AsacSacConfig *cfg, const AsacSacParams *
     a.tile_batch = asac_sac_tile_batch(cfg);
     if (a.tile_batch < 1) return a.tile_batch;
     a.mode = 0;
-    static const int post_late = [] {
-        const char *e = getenv("ASAC_POST_LATE");
-        return e ? atoi(e) : 1;
-    }();
-    a.late_wait = post_late;
+    a.late_wait = 0;  // the chains switch it on (chain_late_wait)
     a.q_sb_handoff = 0;
     const int tiles = (cfg->batch + a.tile_batch - 1) / a.tile_batch;
     ASAC_REQUIRE(wrk->n_tiles == tiles, "work.n_tiles %d != ceil(B / tile_batch) = %d", wrk->n_tiles, tiles);
@@ -1658,20 +1660,24 @@ extern "C" int asac_sac_post(const AsacSacConfig *cfg, const AsacSacParams *prm,
     return launch_value_pass(a, 1, stream);
 }
 
+static int launch_q_backward(SacArgs &a, void *stream) {
+    const GradPlan gp = grad_plan(a.cfg, false);
+    memcpy(a.plan, &gp, sizeof(gp));
+    const int bytes = gp.total * 4;
+    int rc = set_smem(k_q_backward, bytes, "k_q_backward");
+    if (rc != ASAC_OK) return rc;
+    ASAC_CUDA(launch_ex(k_q_backward, dim3(a.wrk.n_tiles, a.cfg.ensemble), dim3(NT), (size_t)bytes, (cudaStream_t)stream,
+                        0, true, a));
+    ASAC_LAUNCHED("k_q_backward");
+    return ASAC_OK;
+}
+
 extern "C" int asac_sac_q_backward(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *bat,
                                    const AsacSacWork *wrk, void *stream) {
     SacArgs a;
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
-    const GradPlan gp = grad_plan(a.cfg, false);
-    memcpy(a.plan, &gp, sizeof(gp));
-    const int bytes = gp.total * 4;
-    rc = set_smem(k_q_backward, bytes, "k_q_backward");
-    if (rc != ASAC_OK) return rc;
-    ASAC_CUDA(launch_ex(k_q_backward, dim3(a.wrk.n_tiles, cfg->ensemble), dim3(NT), (size_t)bytes, (cudaStream_t)stream, 0,
-                        true, a));
-    ASAC_LAUNCHED("k_q_backward");
-    return ASAC_OK;
+    return launch_q_backward(a, stream);
 }
 
 static int launch_policy_backward(SacArgs &a, void *stream) {
@@ -1692,6 +1698,14 @@ extern "C" int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacP
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
     return launch_policy_backward(a, stream);
+}
+
+static int chain_late_wait() {
+    static const int on = [] {
+        const char *e = getenv("ASAC_LATE_WAIT");
+        return e ? atoi(e) : 1;
+    }();
+    return on;
 }
 
 // The fused chains hand Q_i(s_b, a_b) from the policy backward to the post pass when a tile's rows leave room for it
@@ -1833,10 +1847,11 @@ extern "C" int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacPar
     SacArgs a;
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
+    a.late_wait = chain_late_wait();  // this function launches the whole chain: the kernels know their predecessors
     ASAC_REQUIRE(bat && bat->states && bat->eps_y && bat->eps_pi, "asac_sac_step: missing batch tensors");
     if (with_polyak && (rc = asac_sac_polyak(cfg, prm, -1.f, stream)) != ASAC_OK) return rc;
     if ((rc = launch_value_pass(a, 0, stream)) != ASAC_OK) return rc;
-    if ((rc = asac_sac_q_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_q_backward(a, stream)) != ASAC_OK) return rc;
     if ((rc = launch_reduce_adam(cfg, prm, wrk, 0, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
     const bool need_post = cfg->use_auto_alpha || cfg->use_n_step_is || cfg->use_priority;
     a.q_sb_handoff = q_sb_handoff(a, need_post) ? 1 : 0;
@@ -1885,6 +1900,7 @@ extern "C" int asac_sac_step_networks_rep(const AsacSacConfig *cfg, const AsacSa
     SacArgs a;
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
+    a.late_wait = chain_late_wait();  // this function launches the whole chain: the kernels know their predecessors
     ASAC_REQUIRE(rep && cfg->rep_kind == 1, "asac_sac_step_networks_rep: cfg.rep_kind must be 1 (GRU)");
     ASAC_REQUIRE(rep->shape.hidden == cfg->state_size && rep->shape.action_size == cfg->action_size,
                  "asac_sac_step_networks_rep: GRU width %d / action %d vs state_size %d / action_size %d",
@@ -1915,7 +1931,7 @@ extern "C" int asac_sac_step_networks_rep(const AsacSacConfig *cfg, const AsacSa
     if ((rc = asac_gru_forward(&rep->shape, nets, 2, rep->obs, bat->actions, cfg->bn_stride, nullptr, rep->h0,
                                rep->h0_b_stride, B, L, stream)) != ASAC_OK) return rc;
     if ((rc = launch_value_pass(a, 0, stream)) != ASAC_OK) return rc;
-    if ((rc = asac_sac_q_backward(cfg, prm, bat, wrk, stream)) != ASAC_OK) return rc;
+    if ((rc = launch_q_backward(a, stream)) != ASAC_OK) return rc;
     if ((rc = launch_reduce_adam(cfg, prm, wrk, 0, 1, 1, gscale, stream, 0, peers)) != ASAC_OK) return rc;
     // the representation's share of loss.backward() and optimizer_rep.step() (sac_base.py:1573-1601)
     if ((rc = asac_gru_backward(&rep->shape, rep->params, rep->obs, bat->actions, cfg->bn_stride, nullptr, rep->h0,
