@@ -37,6 +37,11 @@ struct SacArgs {
                      // put griddepcontrol.wait behind their predecessor-independent prologue; 0 for the stand-alone
                      // entry points, whose predecessor is whatever the caller launched: wait first.  ASAC_LATE_WAIT=0
                      // keeps every wait at the top (experiments)
+    int pi_handoff;    // fused step, no trained representation, one policy pass per tile: the TRAIN value pass (rank 0)
+                       // leaves the policy's pre-activations of all its rows in the tile's slice of wrk.grad_pi_part
+                       // ([depth][16][lda]; the partial gradients are written there only at the end of the policy
+                       // backward) and the policy backward rebuilds its saved forward from the s_b rows instead of
+                       // running the trunk again — the policy does not change in between
     int q_sb_handoff;  // fused step: the policy backward also evaluates Q_i(s_b, a_b) (free rows of its critic pass,
                        // the critics' weights no longer change within the step) and leaves it in wrk.tq; the post
                        // pass reads it there instead of running the online critics itself (sac_base.py:2211-2216)
@@ -223,7 +228,7 @@ struct GradPlan {
     int total;
 };
 // critic: px/pz hold the critic's activations, qz unused.  policy: px/pz policy, qz critics' z.
-__host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, bool policy) {
+__host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, bool policy, int pi_handoff = 0) {
     GradPlan p;
     p.lda = sac_lda(c);
     p.wsz = sac_wsz(c);
@@ -246,7 +251,8 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
     // critic kernel: forward + reverse walk of one critic; policy kernel: policy forward, critic forward,
     // critic reverse, policy reverse (the last only on cluster rank 0, the plan reserves for it anyway)
     o += 256;  // the slots start on the next 1024-byte boundary (TMA 128-byte swizzle)
-    p.n_jobs = policy ? (c.pi_depth + c.q_depth + (c.q_depth - 1) + (c.pi_depth - 1)) : (c.q_depth + c.q_depth - 1);
+    p.n_jobs = policy ? ((pi_handoff ? 0 : c.pi_depth) + c.q_depth + (c.q_depth - 1) + (c.pi_depth - 1))
+                      : (c.q_depth + c.q_depth - 1);
     p.n_slots = slots_that_fit(o, p.wsz, p.n_jobs);
     o += p.n_slots * p.wsz;
     p.total = o;
@@ -352,7 +358,12 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         __syncthreads();
         pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, pl.n_jobs);
         ASAC_PHASE(0, 1);
-        float *h = net_trunk_forward(ps, pipe, xin + p_lo * lda, bufA + p_lo * lda, bufB + p_lo * lda, nullptr, nullptr,
+        // pi_handoff (host: train pass, one unshared policy pass): rank 0 leaves every layer's pre-activations of the
+        // pass in the tile's slice of grad_pi_part for the policy backward
+        const LayerBufs z_out = (!post && a.pi_handoff && net == 0)
+                                    ? LayerBufs(a.wrk.grad_pi_part + (int64_t)blockIdx.x * net_stride(ps), PASS_ROWS * lda)
+                                    : LayerBufs(nullptr);
+        float *h = net_trunk_forward(ps, pipe, xin + p_lo * lda, bufA + p_lo * lda, bufB + p_lo * lda, nullptr, z_out,
                                      lda, p_hi - p_lo, part);
         head_forward(h, lda, ps.hidden, head_pi, head_pi + 2 * A * ps.hidden, 2 * A, min(RPt, p_hi) - p_lo,
                      ho + p_lo * 2 * A);
@@ -767,14 +778,16 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     if (tid < 32) {  // one lane per job
         const CUtensorMap *mq = a.use_tma ? &a.maps[0] : nullptr, *mp = a.use_tma ? &a.maps[2] : nullptr;
         if (a.use_tma && (tid == 0 || tid == 2)) prefetch_tensormap(&a.maps[tid]);
-        write_job_table(jobs, tid, JobSegment{a.prm.pi, mp, ps, 0, 0}, JobSegment{q_prm, mq, qsh, net, 0},
-                        JobSegment{q_prm, mq, qsh, net, 1}, JobSegment{net == 0 ? a.prm.pi : nullptr, mp, ps, 0, 1});
+        write_job_table(jobs, tid, JobSegment{a.pi_handoff ? nullptr : a.prm.pi, mp, ps, 0, 0},
+                        JobSegment{q_prm, mq, qsh, net, 0}, JobSegment{q_prm, mq, qsh, net, 1},
+                        JobSegment{net == 0 ? a.prm.pi : nullptr, mp, ps, 0, 1});
     }
     float *head_pi = sm + pl.off_heads, *head_q = head_pi + head_floats(Hp, 2 * A);
     stage_head(head_pi, ps, a.prm.pi);
     __syncthreads();
     WeightPipe pipe;
-    pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, n_jobs, dp);  // policy trunk only
+    pipe_init(pipe, aligned_slots(sm, pl.off_slots), bars, jobs, pl.n_slots, pl.wsz, n_jobs,
+              a.pi_handoff ? 0 : dp);  // before the wait: the policy trunk only (nothing with the hand-off)
 
     ASAC_PHASE(2, 1);
     // ---- policy forward (saved); with a trained representation: on the re-encoded states (sac_base.py:2107-2113)
@@ -786,7 +799,29 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         px[0][r * lda + col] = (r < TBa && col < S) ? st[((int64_t)(e0 + r) * L + b) * S + col] : 0.f;
     }
     __syncthreads();
-    net_trunk_forward(ps, pipe, px[0], nullptr, nullptr, px, pz, lda, R, part);
+    if (a.pi_handoff) {
+        // the saved forward from the train value pass's pre-activations (row e * (L - b) of its pass is s_b of batch
+        // element e): y = gelu(z) (+ x), the expression of the layer routine, element by element — same bits
+        const float *zg = a.wrk.grad_pi_part + (int64_t)blockIdx.x * pi_stride;
+        const int Lv = L - b;
+        const bool res0 = net_k(ps, 0) == Hp;
+        for (int i = tid; i < R * Hp; i += NT) {
+            const int r = i / Hp, j = i - r * Hp;
+            float x = res0 ? px[0][r * lda + j] : 0.f;
+#pragma unroll 1
+            for (int l = 0; l < dp; ++l) {
+                const float z = r < TBa ? __ldcg(zg + ((int64_t)l * R + r * Lv) * lda + j) : 0.f;
+                float y = gelu_erf(z);
+                if (l > 0 || res0) y = y + x;
+                pz[l][r * lda + j] = z;
+                px[l + 1][r * lda + j] = y;
+                x = y;
+            }
+        }
+        __syncthreads();
+    } else {
+        net_trunk_forward(ps, pipe, px[0], nullptr, nullptr, px, pz, lda, R, part);
+    }
     head_forward(px[dp], lda, Hp, head_pi, head_pi + 2 * A * Hp, 2 * A, TBa, ho);
     __syncthreads();
 
@@ -1545,6 +1580,7 @@ static int make_args(SacArgs &a, const AsacSacConfig *cfg, const AsacSacParams *
     if (a.tile_batch < 1) return a.tile_batch;
     a.mode = 0;
     a.late_wait = 0;  // the chains switch it on (chain_late_wait)
+    a.pi_handoff = 0;
     a.q_sb_handoff = 0;
     const int tiles = (cfg->batch + a.tile_batch - 1) / a.tile_batch;
     ASAC_REQUIRE(wrk->n_tiles == tiles, "work.n_tiles %d != ceil(B / tile_batch) = %d", wrk->n_tiles, tiles);
@@ -1681,7 +1717,7 @@ extern "C" int asac_sac_q_backward(const AsacSacConfig *cfg, const AsacSacParams
 }
 
 static int launch_policy_backward(SacArgs &a, void *stream) {
-    const GradPlan gp = grad_plan(a.cfg, true);
+    const GradPlan gp = grad_plan(a.cfg, true, a.pi_handoff);
     memcpy(a.plan, &gp, sizeof(gp));
     const int bytes = gp.total * 4;
     int rc = set_smem(k_policy_backward, bytes, "k_policy_backward");
@@ -1698,6 +1734,19 @@ extern "C" int asac_sac_policy_backward(const AsacSacConfig *cfg, const AsacSacP
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
     return launch_policy_backward(a, stream);
+}
+
+// see SacArgs::pi_handoff.  ASAC_PI_HANDOFF=0 disables it.
+static bool pi_handoff(const SacArgs &a) {
+    static const int on = [] {
+        const char *e = getenv("ASAC_PI_HANDOFF");
+        return e ? atoi(e) : 1;
+    }();
+    const AsacSacConfig &c = a.cfg;
+    const NetShape ps = pi_shape(c);
+    const int rows = a.tile_batch * (c.seq_len - c.burn_in);  // policy rows of a tile in the train pass
+    return on && c.rep_kind == 0 && !value_pass_on_tc(c, a.tile_batch, 0) && rows <= PASS_ROWS &&
+           (int64_t)ps.depth * PASS_ROWS * sac_lda(c) <= net_stride(ps);
 }
 
 static int chain_late_wait() {
@@ -1848,6 +1897,7 @@ extern "C" int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacPar
     int rc = make_args(a, cfg, prm, bat, wrk);
     if (rc != ASAC_OK) return rc;
     a.late_wait = chain_late_wait();  // this function launches the whole chain: the kernels know their predecessors
+    a.pi_handoff = pi_handoff(a) ? 1 : 0;
     ASAC_REQUIRE(bat && bat->states && bat->eps_y && bat->eps_pi, "asac_sac_step: missing batch tensors");
     if (with_polyak && (rc = asac_sac_polyak(cfg, prm, -1.f, stream)) != ASAC_OK) return rc;
     if ((rc = launch_value_pass(a, 0, stream)) != ASAC_OK) return rc;
