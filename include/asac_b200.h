@@ -146,7 +146,9 @@ int asac_storage_write_table(const AsacWriteTable *table_host, int64_t capacity,
 /* PrioritizedReplayBuffer.add for a HOST-resident episode as one call (replay_buffer.py:293-315 +
  * DataStorage.add :30-56): packs the columns into a pinned staging buffer owned by the handle,
  * one cudaMemcpyAsync, then asac_tree_leaf_max (unless the buffer was empty: td_error_max is used,
- * :296-299), asac_storage_write_table and asac_per_add on `stream`.  The handle owns only its
+ * :296-299), asac_storage_write_table and asac_per_add on `stream` — for episodes of <= 1024 rows and <= 256 KB
+ * those three steps are ONE kernel (k_ingest_small: every CTA scans its share of the leaves and takes a ticket,
+ * the CTA with the last ticket copies the rows and inserts them; bit-identical tree and rings).  The handle owns only its
  * staging buffers/events; `rings` (one [capacity, row_bytes] device array per key, in the order
  * of `host_columns`), `nodes`, `store_ids`, `max_p_scratch` (device float) and `td_max_dev`
  * (device float holding td_error_max) stay the caller's and must outlive the handle.
