@@ -479,9 +479,13 @@ __device__ __forceinline__ void load_cm(const float *p, float (&w)[CM]) {
 // dX = dZ . W (+ dY when the block was residual) for a hidden -> hidden layer, 16 rows.
 // W is the forward staging (Ws[j * ldw + k], ldw = H + 4): thread (cg, rg, ks) owns the CM
 // consecutive columns k = CM*cg.. of rows {2rg, 2rg+1} over the ks-th quarter of j.
+// Zprev != nullptr: the epilogue also writes the NEXT backward step's dZ = dX * gelu'(Zprev) (rows >= valid_rows zero)
+// into dZprev — which may be the buffer dY lives in: every thread reads its dY element before it writes there.  That
+// is gelu_backward() of the layer below without its own pass over the tile and its two barriers; same expression.
 template <int CM, bool SWZ>
 __device__ __noinline__ void layer_input_grad_t(const float *dZ, int ld, const float *Ws, const float *dY, float *dX,
-                                                bool residual, float *part) {
+                                                bool residual, float *part, const float *Zprev, float *dZprev,
+                                                int valid_rows) {
     ASAC_SMEM(dZ); ASAC_SMEM(Ws); ASAC_SMEM(dY); ASAC_SMEM(dX); ASAC_SMEM(part);
     constexpr int H = 16 * CM;
     const int tid = threadIdx.x, cg = tid & 15, rg = (tid >> 4) & 7, ks = tid >> 7;
@@ -533,26 +537,28 @@ __device__ __noinline__ void layer_input_grad_t(const float *dZ, int ld, const f
         for (int s = 1; s < KSPLIT; ++s) v += part[s * PASS_ROWS * H + o];
         if (residual) v = v + dY[row * ld + k];
         dX[row * ld + k] = v;
+        if (Zprev) dZprev[row * ld + k] = row < valid_rows ? v * gelu_erf_grad(Zprev[row * ld + k]) : 0.f;
     }
     __syncthreads();
 }
 
 __device__ __forceinline__ void layer_input_grad(int hidden, const float *dZ, int ld, const float *Ws,
                                                  const float *dY, float *dX, bool residual, float *part,
-                                                 bool swizzled) {
+                                                 bool swizzled, const float *Zprev = nullptr, float *dZprev = nullptr,
+                                                 int valid_rows = 0) {
     if (swizzled) {
         switch (hidden >> 4) {
-            case 2: layer_input_grad_t<2, true>(dZ, ld, Ws, dY, dX, residual, part); break;
-            case 4: layer_input_grad_t<4, true>(dZ, ld, Ws, dY, dX, residual, part); break;
-            default: layer_input_grad_t<8, true>(dZ, ld, Ws, dY, dX, residual, part); break;
+            case 2: layer_input_grad_t<2, true>(dZ, ld, Ws, dY, dX, residual, part, Zprev, dZprev, valid_rows); break;
+            case 4: layer_input_grad_t<4, true>(dZ, ld, Ws, dY, dX, residual, part, Zprev, dZprev, valid_rows); break;
+            default: layer_input_grad_t<8, true>(dZ, ld, Ws, dY, dX, residual, part, Zprev, dZprev, valid_rows); break;
         }
         return;
     }
     switch (hidden >> 4) {
-        case 1: layer_input_grad_t<1, false>(dZ, ld, Ws, dY, dX, residual, part); break;
-        case 2: layer_input_grad_t<2, false>(dZ, ld, Ws, dY, dX, residual, part); break;
-        case 4: layer_input_grad_t<4, false>(dZ, ld, Ws, dY, dX, residual, part); break;
-        default: layer_input_grad_t<8, false>(dZ, ld, Ws, dY, dX, residual, part); break;
+        case 1: layer_input_grad_t<1, false>(dZ, ld, Ws, dY, dX, residual, part, Zprev, dZprev, valid_rows); break;
+        case 2: layer_input_grad_t<2, false>(dZ, ld, Ws, dY, dX, residual, part, Zprev, dZprev, valid_rows); break;
+        case 4: layer_input_grad_t<4, false>(dZ, ld, Ws, dY, dX, residual, part, Zprev, dZprev, valid_rows); break;
+        default: layer_input_grad_t<8, false>(dZ, ld, Ws, dY, dX, residual, part, Zprev, dZprev, valid_rows); break;
     }
 }
 

@@ -701,19 +701,20 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
     head_backward(dq, 1, px[d], lda, H, head_q, R, gout + net_w_off(qsh, d), gout + net_b_off(qsh, d), g[0], lda);
     ASAC_PHASE(1, 4);
     int cur = 0;
+    __syncthreads();
+    gelu_backward(g[0], pz[d - 1], g[1], lda, H, TBa);  // (the layers below get their dZ from the input-gradient epilogue)
+    __syncthreads();
 #pragma unroll 1
     for (int l = d - 1; l >= 0; --l) {
         const int K = net_k(qsh, l);
-        __syncthreads();
         float *dY = g[cur], *dZ = g[(cur + 1) % 3], *dX = g[(cur + 2) % 3];
-        gelu_backward(dY, pz[l], dZ, lda, H, TBa);
-        __syncthreads();
         layer_weight_grad(dZ, lda, px[l], lda, H, K, TBa, gout + net_w_off(qsh, l), gout + net_b_off(qsh, l));
         if (l > 0) {
             const float *Ws, *bs;
             const bool swz = pipe_front_swizzled(pipe);
             pipe_acquire(pipe, Ws, bs);
-            layer_input_grad(H, dZ, lda, Ws, dY, dX, true, part, swz);  // ends with a CTA barrier
+            // dX -> the next dY; the next dZ = dX * gelu'(z_{l-1}) lands where this dY was (the buffer rotation's slot)
+            layer_input_grad(H, dZ, lda, Ws, dY, dX, true, part, swz, pz[l - 1], dY, TBa);  // ends with a CTA barrier
             pipe_release(pipe);
             cur = (cur + 2) % 3;
         } else if (a.wrk.grad_state) {
@@ -901,17 +902,18 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         __syncthreads();
         head_backward(dq, 1, nullptr, lda, Hq, head_q, R, nullptr, nullptr, g[0], lda);
         int cur = 0;
+        __syncthreads();
+        gelu_backward(g[0], sm + pl.off_qz + (dqn - 1) * R * lda, g[1], lda, Hq, TBa);
+        __syncthreads();
 #pragma unroll 1
         for (int l = dqn - 1; l >= 0; --l) {
-            __syncthreads();
             float *dY = g[cur], *dZ = g[(cur + 1) % 3], *dX = g[(cur + 2) % 3];
-            gelu_backward(dY, sm + pl.off_qz + l * R * lda, dZ, lda, Hq, TBa);
-            __syncthreads();
             if (l > 0) {
                 const float *Ws, *bs;
                 const bool swz = pipe_front_swizzled(pipe);
                 pipe_acquire(pipe, Ws, bs);
-                layer_input_grad(Hq, dZ, lda, Ws, dY, dX, true, part, swz);  // ends with a CTA barrier
+                layer_input_grad(Hq, dZ, lda, Ws, dY, dX, true, part, swz, sm + pl.off_qz + (l - 1) * R * lda, dY,
+                                 TBa);  // ends with a CTA barrier
                 pipe_release(pipe);
                 cur = (cur + 2) % 3;
             } else {
@@ -986,19 +988,19 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     head_backward(dO, 2 * A, px[dp], lda, Hp, head_pi, R, gout + net_w_off(ps, dp), gout + net_b_off(ps, dp), g[0],
                   lda);
     int cur = 0;
+    __syncthreads();
+    gelu_backward(g[0], pz[dp - 1], g[1], lda, Hp, TBa);
+    __syncthreads();
 #pragma unroll 1
     for (int l = dp - 1; l >= 0; --l) {
         const int K = net_k(ps, l);
-        __syncthreads();
         float *dY = g[cur], *dZ = g[(cur + 1) % 3], *dX = g[(cur + 2) % 3];
-        gelu_backward(dY, pz[l], dZ, lda, Hp, TBa);
-        __syncthreads();
         layer_weight_grad(dZ, lda, px[l], lda, Hp, K, TBa, gout + net_w_off(ps, l), gout + net_b_off(ps, l));
         if (l > 0) {
             const float *Ws, *bs;
             const bool swz = pipe_front_swizzled(pipe);
             pipe_acquire(pipe, Ws, bs);
-            layer_input_grad(Hp, dZ, lda, Ws, dY, dX, true, part, swz);  // ends with a CTA barrier
+            layer_input_grad(Hp, dZ, lda, Ws, dY, dX, true, part, swz, pz[l - 1], dY, TBa);  // ends with a CTA barrier
             pipe_release(pipe);
             cur = (cur + 2) % 3;
         }
