@@ -646,8 +646,11 @@ static __device__ __noinline__ void head_forward(const float *X, int ldx, int H,
 
 // Head backward.  dO[r * O + o] (rows >= valid rows must be zero):
 //   gWh[o * H + j] = sum_r dO[r][o] X[r][j];  gbh[o] = sum_r dO[r][o];  dH[r][j] = sum_o dO[r][o] Wh[o][j]
+// Zlast != nullptr: also dZlast = dH * gelu'(Zlast) for the last ResBlock (rows >= valid_rows zero) — gelu_backward()
+// of that layer without its own pass and barriers; same expression.
 static __device__ __noinline__ void head_backward(const float *dO, int O, const float *X, int ldx, int H, const float *Wh,
-                                           int nrows, float *gWh, float *gbh, float *dH, int ldh) {
+                                           int nrows, float *gWh, float *gbh, float *dH, int ldh,
+                                           const float *Zlast = nullptr, float *dZlast = nullptr, int valid_rows = 0) {
     ASAC_SMEM(dO); ASAC_SMEM(dH);
     if (X) ASAC_SMEM(X);
     const int tid = threadIdx.x;
@@ -671,6 +674,7 @@ static __device__ __noinline__ void head_backward(const float *dO, int O, const 
         float s = 0.f;
         for (int o = 0; o < O; ++o) s = fmaf(dO[r * O + o], Wh[(int64_t)o * H + j], s);
         dH[r * ldh + j] = s;
+        if (Zlast) dZlast[r * ldh + j] = r < valid_rows ? s * gelu_erf_grad(Zlast[r * ldh + j]) : 0.f;
     }
 }
 

@@ -698,11 +698,11 @@ __global__ void __launch_bounds__(NT) k_q_backward(const __grid_constant__ SacAr
 
     // head backward, then the ResBlocks in reverse
     ASAC_PHASE(1, 3);
-    head_backward(dq, 1, px[d], lda, H, head_q, R, gout + net_w_off(qsh, d), gout + net_b_off(qsh, d), g[0], lda);
+    // (dZ of the last ResBlock comes out of the head backward, the layers below get theirs from the input-gradient epilogue)
+    head_backward(dq, 1, px[d], lda, H, head_q, R, gout + net_w_off(qsh, d), gout + net_b_off(qsh, d), g[0], lda,
+                  pz[d - 1], g[1], TBa);
     ASAC_PHASE(1, 4);
     int cur = 0;
-    __syncthreads();
-    gelu_backward(g[0], pz[d - 1], g[1], lda, H, TBa);  // (the layers below get their dZ from the input-gradient epilogue)
     __syncthreads();
 #pragma unroll 1
     for (int l = d - 1; l >= 0; --l) {
@@ -900,10 +900,9 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         const float *prm = a.prm.q + i * q_stride;
         if (tid < R) dq[tid] = (tid < TBa && (int)amin[tid] == i) ? -1.f / (float)B : 0.f;
         __syncthreads();
-        head_backward(dq, 1, nullptr, lda, Hq, head_q, R, nullptr, nullptr, g[0], lda);
+        head_backward(dq, 1, nullptr, lda, Hq, head_q, R, nullptr, nullptr, g[0], lda,
+                      sm + pl.off_qz + (dqn - 1) * R * lda, g[1], TBa);
         int cur = 0;
-        __syncthreads();
-        gelu_backward(g[0], sm + pl.off_qz + (dqn - 1) * R * lda, g[1], lda, Hq, TBa);
         __syncthreads();
 #pragma unroll 1
         for (int l = dqn - 1; l >= 0; --l) {
@@ -986,10 +985,8 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     ASAC_PHASE(2, 7);
     // ---- policy backward
     head_backward(dO, 2 * A, px[dp], lda, Hp, head_pi, R, gout + net_w_off(ps, dp), gout + net_b_off(ps, dp), g[0],
-                  lda);
+                  lda, pz[dp - 1], g[1], TBa);
     int cur = 0;
-    __syncthreads();
-    gelu_backward(g[0], pz[dp - 1], g[1], lda, Hp, TBa);
     __syncthreads();
 #pragma unroll 1
     for (int l = dp - 1; l >= 0; --l) {
