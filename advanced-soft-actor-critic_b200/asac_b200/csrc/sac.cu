@@ -242,7 +242,7 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
     p.off_g0 = o; o += rows * p.lda;
     p.off_g1 = o; o += rows * p.lda;
     p.off_g2 = o; o += rows * p.lda;
-    p.off_small = o; o += round_up(rows * (6 * c.action_size + c.ensemble + 4), 4);
+    p.off_small = o; o += round_up(rows * (9 * c.action_size + c.ensemble + 4), 4);  // (policy: + 3 A per row of loss terms)
     p.off_red = o; o += 32;
     p.off_part = o; o += sac_part(c);
     p.off_heads = o; o += head_floats(c.pi_hidden, 2 * c.action_size) + head_floats(c.q_hidden, 1);  // policy, critic
@@ -943,35 +943,50 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
 
     ASAC_PHASE(2, 6);
     // ---- d loss / d (mean, logstd) pre-activations; loss and entropy sums
+    // One thread per (row, action dimension) for everything that does not need the row's summed Jacobian term (the
+    // gradients of the head's outputs among them), then one thread per row for the two ordered sums: the same
+    // expressions in the same order as a single thread per row would evaluate them, with the ten transcendental
+    // calls of each dimension running side by side instead of in a row (3.4 -> 1.9 us at A = 2).
     float loss = 0.f, ent = 0.f;
     const float alpha = expf(a.prm.log_alpha[0]);
-    for (int i = tid; i < R * 2 * A; i += NT) dO[i] = 0.f;
+    float *lfs = dO + R * 2 * A, *lpn = lfs + R * A, *e1s = lpn + R * A;  // behind dO in the plan's `small` region
+    for (int i = tid; i < R * A; i += NT) {
+        const int r = i / A, j = i - r * A;
+        if (r >= TBa) {
+            dO[r * 2 * A + j] = 0.f;
+            dO[r * 2 * A + A + j] = 0.f;
+            continue;
+        }
+        const float m = ho[r * 2 * A + j], s = ho[r * 2 * A + A + j];
+        const float mu = policy_loc(m), sg = policy_scale(s);
+        const float x = xs[r * A + j], eps = a.bat.eps_pi[(int64_t)(e0 + r) * A + j];
+        lfs[i] = logf(squash_floor(x));
+        lpn[i] = normal_log_prob(x, mu, sg);
+        e1s[i] = 0.5f + LOG_SQRT_2PI + logf(sg);  // Normal.entropy
+        // d/dx of alpha * (-A * log max(1 - tanh^2 x, 1e-2)): every action dim carries the summed
+        // Jacobian term (operators.py:12-14), hence the factor A
+        const float t = tanhf(x), one_m = 1.f - t * t;
+        const float dcorr = one_m > 1e-2f ? 2.f * t : (one_m == 1e-2f ? t : 0.f);
+        const float dx = (alpha * (float)A * dcorr) / (float)B + da[r * A + j] * one_m;
+        // the Normal.log_prob(rsample) terms cancel analytically except -log(scale)
+        const float dsig = dx * eps - alpha / ((float)B * sg);
+        const float th = tanhf(m / 5.f);
+        dO[r * 2 * A + j] = dx * (1.f - th * th);
+        dO[r * 2 * A + A + j] = (s >= -20.f && s <= 0.5f) ? dsig * sg : 0.f;
+    }
     __syncthreads();
     if (tid < TBa) {
         const int r = tid;
-        float corr = 0.f, qm = qv[(int)amin[r] * R + r];
-        for (int j = 0; j < A; ++j) corr += logf(squash_floor(xs[r * A + j]));
+        float corr = 0.f;
+        const float qm = qv[(int)amin[r] * R + r];
+        for (int j = 0; j < A; ++j) corr += lfs[r * A + j];
         float lp_sum = 0.f;
         for (int j = 0; j < A; ++j) {
-            const float m = ho[r * 2 * A + j], s = ho[r * 2 * A + A + j];
-            const float mu = policy_loc(m), sg = policy_scale(s);
-            const float x = xs[r * A + j], eps = a.bat.eps_pi[(int64_t)(e0 + r) * A + j];
-            float lp = normal_log_prob(x, mu, sg) - corr;
-            const bool lp_inf = (lp == INFINITY);
-            if (lp_inf) lp = 0.f;
+            float lp = lpn[r * A + j] - corr;
+            if (lp == INFINITY) lp = 0.f;
             lp_sum += lp;
-            const float e1 = 0.5f + LOG_SQRT_2PI + logf(sg);  // Normal.entropy
+            const float e1 = e1s[r * A + j];
             ent += (e1 == INFINITY) ? 0.f : e1;
-            // d/dx of alpha * (-A * log max(1 - tanh^2 x, 1e-2)): every action dim carries the summed
-            // Jacobian term (operators.py:12-14), hence the factor A
-            const float t = tanhf(x), one_m = 1.f - t * t;
-            const float dcorr = one_m > 1e-2f ? 2.f * t : (one_m == 1e-2f ? t : 0.f);
-            const float dx = (alpha * (float)A * dcorr) / (float)B + da[r * A + j] * one_m;
-            // the Normal.log_prob(rsample) terms cancel analytically except -log(scale)
-            const float dsig = dx * eps - alpha / ((float)B * sg);
-            const float th = tanhf(m / 5.f);
-            dO[r * 2 * A + j] = dx * (1.f - th * th);
-            dO[r * 2 * A + A + j] = (s >= -20.f && s <= 0.5f) ? dsig * sg : 0.f;
         }
         loss = alpha * lp_sum - qm;
     }
