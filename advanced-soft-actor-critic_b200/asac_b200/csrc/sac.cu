@@ -37,6 +37,7 @@ struct SacArgs {
                      // put griddepcontrol.wait behind their predecessor-independent prologue; 0 for the stand-alone
                      // entry points, whose predecessor is whatever the caller launched: wait first.  ASAC_LATE_WAIT=0
                      // keeps every wait at the top (experiments)
+    int push_combine;  // value pass: ranks 1.. push their value rows to rank 0 (ASAC_PUSH_COMBINE=0: rank 0 pulls them)
     int pi_handoff;    // fused step, no trained representation, one policy pass per tile: the TRAIN value pass (rank 0)
                        // leaves the policy's pre-activations of all its rows in the tile's slice of wrk.grad_pi_part
                        // ([depth][16][lda]; the partial gradients are written there only at the end of the policy
@@ -178,7 +179,7 @@ __device__ __forceinline__ void combine_value_rows(Cluster &cluster, const AsacS
 // ------------------------------------------------------------------------------------ smem plans
 struct ValuePlan {
     int lda, wsz, rows_max;  // rows_max: multiple of 16
-    int off_xin, off_a, off_b, off_ho, off_xs, off_logp, off_qmin, off_qmin2, off_ratio, off_qs, off_red, off_part,
+    int off_xin, off_a, off_b, off_ho, off_xs, off_logp, off_qmin, off_qpush, off_qmin2, off_ratio, off_qs, off_red, off_part,
         off_heads, off_pipe, off_slots;
     int n_jobs, n_slots;
     int total;  // floats
@@ -204,6 +205,7 @@ __host__ __device__ __forceinline__ ValuePlan value_plan(const AsacSacConfig &c,
     p.off_xs = o; o += round_up(TB * (n + 1) * A, 4);
     p.off_logp = o; o += round_up(TB * (n + 1), 4);
     p.off_qmin = o; o += round_up(p.rows_max, 4);
+    p.off_qpush = o; o += (c.ensemble - 1) * round_up(p.rows_max, 4);  // ranks 1.. push their value rows to rank 0
     p.off_qmin2 = o; o += ensemble_subset(c) ? round_up(p.rows_max, 4) : 0;  // min over the "next rows" subset
     p.off_ratio = o; o += round_up(TB * (n > 0 ? n : 1), 4);
     p.off_qs = o; o += round_up(c.ensemble * TB, 4);
@@ -280,6 +282,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     warm_kernel_params(a);
     cg::cluster_group cluster = cg::this_cluster();
     const int net = (int)cluster.block_rank();
+    cluster.barrier_arrive();  // matched by barrier_wait() in front of the first remote access: every rank is running
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
     const AsacSacConfig &c = a.cfg;
@@ -368,8 +371,9 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
         head_forward(h, lda, ps.hidden, head_pi, head_pi + 2 * A * ps.hidden, 2 * A, min(RPt, p_hi) - p_lo,
                      ho + p_lo * 2 * A);
         __syncthreads();
+        cluster.barrier_wait();  // (arrived at kernel entry: long complete) every rank of the cluster is running
         if (share) {
-            cluster.sync();  // every rank of the cluster is running (remote shared memory may be written)
+            cluster.sync();
             const int lo = p_lo * 2 * A, hi = min(RPt, p_hi) * 2 * A;
             for (int q = 0; q < E; ++q) {
                 if (q == net) continue;
@@ -514,8 +518,30 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     }
     ASAC_PHASE(0, 6);
     // ---- ensemble combine on rank 0 over distributed shared memory, in member order
-    cluster.sync();
     float *qmin2 = ensemble_subset(c) && a.bat.ensemble_perms ? sm + pl.off_qmin2 : qmin;
+    if (qmin2 == qmin && !online && a.push_combine) {
+        // all members, nothing else to fetch: ranks 1.. PUSH their value rows into rank 0's shared memory and leave
+        // after ONE cluster barrier; rank 0 takes the minimum from its own memory (a pull costs a second barrier,
+        // to keep the remote memory alive, and a remote-load round trip: 1.3 us per pass)
+        const int stride = round_up(pl.rows_max, 4);
+        if (net != 0) {
+            float *dst = cluster.map_shared_rank(sm + pl.off_qpush, 0) + (net - 1) * stride;
+            for (int r = tid; r < RV; r += NT) dst[r] = qmin[r];
+        }
+        cluster.sync();
+        if (net != 0) return;
+        for (int i = 1; i < E; ++i) {
+            const float *src = sm + pl.off_qpush + (i - 1) * stride;
+            for (int r = tid; r < RV; r += NT) qmin[r] = fminf(qmin[r], src[r]);  // sac_base.py:1439-1442, member order
+        }
+        if (post)
+            for (int i = tid; i < E * TBa; i += NT) {
+                const int m = i / TBa, e = i - m * TBa;
+                qs[m * TB + e] = __ldcg(a.wrk.tq + (int64_t)m * B + e0 + e);
+            }
+        __syncthreads();
+    } else {
+    cluster.sync();
     if (net == 0) {
         combine_value_rows(cluster, c, a.bat.ensemble_perms, post ? 3 : 0, qmin, qmin2, RV);
         if (online)
@@ -531,6 +557,7 @@ __global__ void __launch_bounds__(NT) k_value_pass(const __grid_constant__ SacAr
     }
     cluster.sync();  // remote shared memory stays alive until rank 0 has read it
     if (net != 0) return;
+    }
 
     ASAC_PHASE(0, 7);
     // ---- per batch element: V, v-trace, y (sac_base.py:1244-1295, 1444-1464)
@@ -1606,6 +1633,11 @@ static int make_args(SacArgs &a, const AsacSacConfig *cfg, const AsacSacParams *
     if (a.tile_batch < 1) return a.tile_batch;
     a.mode = 0;
     a.late_wait = 0;  // the chains switch it on (chain_late_wait)
+    static const int push_combine = [] {
+        const char *e = getenv("ASAC_PUSH_COMBINE");
+        return e ? atoi(e) : 1;
+    }();
+    a.push_combine = push_combine;
     a.pi_handoff = 0;
     a.q_sb_handoff = 0;
     const int tiles = (cfg->batch + a.tile_batch - 1) / a.tile_batch;
