@@ -244,7 +244,8 @@ __host__ __device__ __forceinline__ GradPlan grad_plan(const AsacSacConfig &c, b
     p.off_g0 = o; o += rows * p.lda;
     p.off_g1 = o; o += rows * p.lda;
     p.off_g2 = o; o += rows * p.lda;
-    p.off_small = o; o += round_up(rows * (9 * c.action_size + c.ensemble + 4), 4);  // (policy: + 3 A per row of loss terms)
+    p.off_small = o;  // (policy: + 3 A per row of loss terms, + (E - 1) A per row of action gradients pushed by the other ranks)
+    o += round_up(rows * ((9 + c.ensemble - 1) * c.action_size + c.ensemble + 4), 4);
     p.off_red = o; o += 32;
     p.off_part = o; o += sac_part(c);
     p.off_heads = o; o += head_floats(c.pi_hidden, 2 * c.action_size) + head_floats(c.q_hidden, 1);  // policy, critic
@@ -778,6 +779,7 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
     ASAC_PHASE(2, 0);
     cg::cluster_group cluster = cg::this_cluster();
     const int net = (int)cluster.block_rank();
+    cluster.barrier_arrive();  // matched by barrier_wait() in front of the first remote store: every rank is running
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
     const AsacSacConfig &c = a.cfg;
@@ -894,13 +896,15 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         __syncthreads();
         if (handoff && tid < TBa) a.wrk.tq[(int64_t)net * B + e0 + tid] = qv[net * R + TBa + tid];
     }
-    cluster.sync();
+    // every rank PUSHES its member's values into the others' qv (remote stores, then one barrier: no remote-load
+    // round trip behind it)
+    cluster.barrier_wait();  // (arrived at kernel entry: long complete)
     for (int i = 0; i < E; ++i) {
         if (i == net) continue;
-        const float *rv = cluster.map_shared_rank(qv, i);
-        if (tid < TBa) qv[i * R + tid] = rv[i * R + tid];
+        float *rv = cluster.map_shared_rank(qv, i);
+        if (tid < TBa) rv[net * R + tid] = qv[net * R + tid];
     }
-    __syncthreads();
+    cluster.sync();
     if (tid < R) {
         int best = 0;
         if (tid < TBa) {
@@ -957,16 +961,16 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
         __syncthreads();
     }
     ASAC_PHASE(2, 5);
-    // ---- sum of the members' action gradients on rank 0, in member order
-    cluster.sync();
-    if (net == 0) {
-        for (int i = 1; i < E; ++i) {
-            const float *rda = cluster.map_shared_rank(da, i);
-            for (int t = tid; t < TBa * A; t += NT) da[t] += rda[t];
-        }
+    // ---- sum of the members' action gradients on rank 0, in member order: ranks 1.. push theirs and leave
+    float *da_push = dO + R * 2 * A + 3 * R * A;  // behind dO and the three loss-term arrays in the `small` region
+    if (net != 0) {
+        float *dst = cluster.map_shared_rank(da_push, 0) + (net - 1) * R * A;
+        for (int t = tid; t < TBa * A; t += NT) dst[t] = da[t];
     }
     cluster.sync();
     if (net != 0) return;
+    for (int i = 1; i < E; ++i)
+        for (int t = tid; t < TBa * A; t += NT) da[t] += da_push[(i - 1) * R * A + t];
 
     ASAC_PHASE(2, 6);
     // ---- d loss / d (mean, logstd) pre-activations; loss and entropy sums
