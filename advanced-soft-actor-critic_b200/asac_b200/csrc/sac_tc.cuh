@@ -13,8 +13,8 @@
 // ---------------------------------------------------------------- value pass
 struct ValueTcPlan {
     int RA;  // rows of the operand planes (multiple of 8)
-    int off_xhi, off_xlo, off_w, off_bias, off_ho, off_qo, off_xs, off_logp, off_qmin, off_qmin2, off_ratio, off_qs, off_red,
-        off_misc;
+    int off_xhi, off_xlo, off_w, off_bias, off_ho, off_qo, off_xs, off_logp, off_qmin, off_qpush, off_qmin2, off_ratio, off_qs,
+        off_red, off_misc;
     int total;  // floats
 };
 __host__ __device__ __forceinline__ ValueTcPlan value_tc_plan(const AsacSacConfig &c, int TB, int mode) {
@@ -36,6 +36,7 @@ __host__ __device__ __forceinline__ ValueTcPlan value_tc_plan(const AsacSacConfi
     p.off_xs = o; o += round_up(TB * (n + 1) * A, 4);
     p.off_logp = o; o += round_up(TB * (n + 1), 4);
     p.off_qmin = o; o += round_up(TB * (n + 1), 4);
+    p.off_qpush = o; o += (c.ensemble - 1) * round_up(TB * (n + 1), 4);  // ranks 1.. push their value rows to rank 0
     p.off_qmin2 = o; o += ensemble_subset(c) ? round_up(TB * (n + 1), 4) : 0;
     p.off_ratio = o; o += round_up(TB * (n > 0 ? n : 1), 4);
     p.off_qs = o; o += round_up(c.ensemble * TB, 4);
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__
     warm_kernel_params(a);
     cg::cluster_group cluster = cg::this_cluster();
     const int net = (int)cluster.block_rank();
+    cluster.barrier_arrive();  // matched by barrier_wait() in front of the first remote access: every rank is running
     extern __shared__ float4 smem4[];
     float *sm = reinterpret_cast<float *>(smem4);
     const AsacSacConfig &c = a.cfg;
@@ -154,8 +156,9 @@ __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__
         const TcfJob nxt = tcf_trunk_job(qsh, prm_qt, 0);
         tcf_layer<true>(cx, job, &nxt, R, false, ho + p_lo * 2 * A, 2 * A, min(RPt, p_hi) - p_lo);
         job = nxt;
+        cluster.barrier_wait();  // (arrived at kernel entry: long complete)
         if (share) {
-            cluster.sync();  // every rank of the cluster is running (remote shared memory may be written)
+            cluster.sync();
             const int lo = p_lo * 2 * A, hi = min(RPt, p_hi) * 2 * A;
             for (int q = 0; q < E; ++q) {
                 if (q == net) continue;
@@ -303,8 +306,24 @@ __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__
     }
     ASAC_PHASE(0, 6);
     // ---- ensemble combine on rank 0 over distributed shared memory, in member order
-    cluster.sync();
     float *qmin2 = ensemble_subset(c) && a.bat.ensemble_perms ? sm + pl.off_qmin2 : qmin;
+    if (!post && qmin2 == qmin && a.push_combine) {  // train pass, all members: push (see k_value_pass)
+        const int stride = round_up(TB * (n + 1), 4);
+        if (net != 0) {
+            float *dst = cluster.map_shared_rank(sm + pl.off_qpush, 0) + (net - 1) * stride;
+            for (int r = tid; r < RV; r += NT) dst[r] = qmin[r];
+        }
+        cluster.sync();
+        tc_fence_after();
+        if (tid < 32) tmem_dealloc(cx.tmem, tmem_cols);
+        if (net != 0) return;
+        for (int i = 1; i < E; ++i) {
+            const float *src = sm + pl.off_qpush + (i - 1) * stride;
+            for (int r = tid; r < RV; r += NT) qmin[r] = fminf(qmin[r], src[r]);
+        }
+        __syncthreads();
+    } else {
+    cluster.sync();
     if (net == 0) {
         combine_value_rows(cluster, c, a.bat.ensemble_perms, post ? 3 : 0, qmin, qmin2, RV);
         if (post)
@@ -318,6 +337,7 @@ __global__ void __launch_bounds__(NT, 1) k_value_pass_tc(const __grid_constant__
     tc_fence_after();
     if (tid < 32) tmem_dealloc(cx.tmem, tmem_cols);
     if (net != 0) return;
+    }
 
     // ---- per batch element: V, v-trace, y (sac_base.py:1244-1295, 1444-1464) — see k_value_pass
     if (tid < TBa) {
