@@ -857,8 +857,8 @@ __global__ void __launch_bounds__(NT) k_policy_backward(const __grid_constant__ 
 
     pdl_wait();  // the critics' Adam step is complete and flushed from here on
     gt_stamp(6, false);
+    pipe_open_all(pipe);  // (the weight copies are in flight while the head is loaded)
     stage_head(head_q, qsh, q_prm);
-    pipe_open_all(pipe);
     ASAC_PHASE(2, 2);
     // ---- sample, critic input
     const int K0 = S + A, K04 = round_up(K0, 4);
@@ -1217,9 +1217,11 @@ __global__ void __launch_bounds__(ADAM_PARAMS_PER_CTA *ADAM_TILE_GROUPS) k_reduc
 // `staged` (shared memory, n_tiles floats) holds wrk.grad_alpha_part[t * 2], loaded by the whole CTA:
 // one thread summing the tiles straight from global memory serialised n_tiles L2 round trips
 // Executed by ONE thread.  With a peer exchange the scalar gradient travels like a 1-float slice.
-__device__ __forceinline__ void alpha_reduce_adam(const AsacSacParams &prm, const AsacSacWork &wrk, int n_tiles,
-                                                  int batch, int do_reduce, int do_adam, float grad_scale,
-                                                  double lr, const float *staged, const PeerExchange *px = nullptr) {
+// -> log_alpha after the call
+__device__ __forceinline__ float alpha_reduce_adam(const AsacSacParams &prm, const AsacSacWork &wrk, int n_tiles,
+                                                   int batch, int do_reduce, int do_adam, float grad_scale,
+                                                   double lr, const float *staged, const PeerExchange *px = nullptr) {
+    float log_alpha = do_adam ? prm.log_alpha[0] : 0.f;  // (a reduce-only launch carries no parameters)
     {
         float gr;
         if (do_reduce) {
@@ -1249,9 +1251,11 @@ __device__ __forceinline__ void alpha_reduce_adam(const AsacSacParams &prm, cons
             const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
             prm.alpha_m[0] = m;
             prm.alpha_v[0] = v;
-            prm.log_alpha[0] = prm.log_alpha[0] + (step_size * m) / denom;
+            log_alpha = log_alpha + (step_size * m) / denom;
+            prm.log_alpha[0] = log_alpha;
         }
     }
+    return log_alpha;
 }
 
 __global__ void __launch_bounds__(1024) k_alpha_td(const AsacSacParams prm, const AsacSacWork wrk, int n_tiles,
@@ -1297,16 +1301,20 @@ struct EpilogueArgs {
 __global__ void __launch_bounds__(1024) k_step_epilogue(const __grid_constant__ EpilogueArgs a) {
     __shared__ TreeApplySmem s_apply;
     __shared__ float s_alpha[1024];
+    __shared__ float s_log_alpha;
     pdl_wait();
     pdl_trigger();
     const int t = threadIdx.x;
     if (a.use_auto_alpha) {
         for (int i = t; i < a.n_tiles; i += blockDim.x) s_alpha[i] = __ldcg(a.wrk.grad_alpha_part + i * 2);
         __syncthreads();
-        if (t == 0) alpha_reduce_adam(a.prm, a.wrk, a.n_tiles, a.batch, 1, 1, a.grad_scale, a.lr, s_alpha, &a.px);
+        if (t == 0)  // (the updated value goes to the other threads through shared memory, not a global round trip)
+            s_log_alpha = alpha_reduce_adam(a.prm, a.wrk, a.n_tiles, a.batch, 1, 1, a.grad_scale, a.lr, s_alpha, &a.px);
+    } else if (t == 0) {
+        s_log_alpha = __ldcg(a.prm.log_alpha);
     }
     __syncthreads();
-    const float alpha = expf(__ldcg(a.prm.log_alpha));
+    const float alpha = expf(s_log_alpha);
     bool active = t < a.batch;
     int slot = 0, bad = 0;
     float value = 0.f;
