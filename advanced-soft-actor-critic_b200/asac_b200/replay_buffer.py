@@ -20,6 +20,7 @@ import ctypes as C
 import functools
 import logging
 import math
+import os
 import threading
 from pathlib import Path
 
@@ -124,6 +125,13 @@ class PrioritizedReplayBuffer:
         # a learner that defers its priority update registers a hook here; everything that READS the tree
         # from outside the learner's own schedule (sample / save / copy) applies the pending update first
         self._flush_hook = None
+        # add() gives new rows the maximum leaf priority (replay_buffer.py:296-299).  With a deferred priority update
+        # pending, that maximum is the one BEFORE the last step's update (the update runs on the next step's parallel
+        # branch); ASAC_STRICT_ADD_ORDER=1 applies the pending update first — the reference's order when train() and
+        # put_episode() alternate in one thread — at the price of putting the 12 us tree update back on the stream
+        # in front of every add.  (The maximum saturates at td_error_max ** alpha in a running learner, so the two
+        # orders give the same priorities except while it is still being reached.)
+        self._strict_add_order = os.environ.get('ASAC_STRICT_ADD_ORDER', '0') == '1'
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -274,6 +282,8 @@ class PrioritizedReplayBuffer:
     @_locked
     def add(self, transitions: dict[str, np.ndarray], ignore_size=0) -> None:
         with torch.cuda.device(self.device):
+            if self._strict_add_order:
+                self._flush()
             if self._add_native(transitions, ignore_size):
                 return
             if self._size == 0:

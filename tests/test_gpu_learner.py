@@ -113,6 +113,38 @@ def test_programmatic_dependent_launch_does_not_change_results(tmp_path, plugin,
     a.close(); b.close()
 
 
+def test_strict_add_order_equals_the_undeferred_schedule(tmp_path, monkeypatch):
+    """add() gives new rows the maximum leaf priority.  With the priority update deferred to the next step's parallel
+    branch that maximum lags one update; ASAC_STRICT_ADD_ORDER=1 applies the pending update first.  Interleaving
+    put_episode() and train() it must then retrace the schedule that never defers (ASAC_DEFER_TREE=0) bit for bit."""
+    nn = _plugin(tmp_path, PLUGIN_TEST, 'nn_plugin')
+    runs = []
+    for env in ({'ASAC_DEFER_TREE': '0'}, {'ASAC_STRICT_ADD_ORDER': '1'}):
+        for k in ('ASAC_DEFER_TREE', 'ASAC_STRICT_ADD_ORDER'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        sac = _make(nn, graph=True)
+        rng = np.random.RandomState(3)
+        for i in range(10):
+            ep = _episode(rng, ((6,),), 2, 20)
+            ep['ep_rewards'] = ep['ep_rewards'] * (1.0 + i)  # growing td errors: the maximum priority keeps moving
+            sac.put_episode(**ep)
+            sac.train()
+        sac.flush_priority_update()
+        torch.cuda.synchronize()
+        runs.append(sac)
+    a, b = runs
+    assert b._defer_tree and not a._defer_tree and b.replay_buffer._strict_add_order
+    assert torch.equal(a.replay_buffer._nodes, b.replay_buffer._nodes)
+    for pa, pb in zip(a.model_policy.parameters(), b.model_policy.parameters()):
+        assert torch.equal(pa, pb)
+    for qa, qb in zip(a.model_q_list, b.model_q_list):
+        for pa, pb in zip(qa.parameters(), qb.parameters()):
+            assert torch.equal(pa, pb)
+    a.close(); b.close()
+
+
 def test_train_returns_step_until_buffer_exceeds_batch(tmp_path):
     from algorithm.sac_base import SAC_Base
     nn = _plugin(tmp_path, PLUGIN_TEST, 'nn_plugin2')
