@@ -1,5 +1,10 @@
 // 16-row layer passes on the warp-level tensor-core path (mma.sync.m16n8k8 tf32, 3xTF32), sm_100a.
 //
+// NOT part of libasac_b200.so: this is the variant the micro-benchmark tools/ubench/layer_chain.cu measures against the
+// FFMA routine (profiles/r02n_ubench_layer_chain.txt).  On B200 the legacy HMMA tf32 instruction issues about once per
+// 28 cycles per scheduler — 36 MAC/clk against FFMA's 32 — so a 16-row pass takes 1 537 cycles here against 2 116 for
+// the adopted FFMA tile, with four times the error: not worth the precision.  Kept as the record of that measurement.
+//
 // The update kernels of a replay-sized step hold ONE 16-row tile per CTA, so a layer is a 16 x H x K GEMM:
 // exactly one m16 tile tall.  The FFMA routine of mlp_tile.cuh needs 512 FFMA issue cycles per scheduler,
 // a K-split exchange through shared memory and two CTA barriers for it (~2 us per layer measured); tcgen05
