@@ -345,3 +345,22 @@ def test_flat_adam_state_dict_loads_into_torch_adam():
     assert int(counters[1]) == 8
     assert torch.equal(m_flat[16:24].view(2, 4), ref.state[clones[2]]['exp_avg'])
     assert torch.equal(v_flat[:12].view(4, 3), ref.state[clones[0]]['exp_avg_sq'])
+
+
+def test_every_environment_switch_is_documented():
+    """DESIGN.md §11 is the one list of A/B and debugging switches: every ASAC_* variable the product reads
+    (library sources, host package, bench.py) must appear there."""
+    import re
+    root = Path(__file__).resolve().parent.parent
+    pkg = root / 'advanced-soft-actor-critic_b200' / 'asac_b200'
+    files = list((pkg / 'csrc').glob('*.cu')) + list((pkg / 'csrc').glob('*.cuh')) + list(pkg.glob('*.py')) + [root / 'bench.py']
+    used = set()
+    for f in files:
+        text = f.read_text()
+        used |= set(re.findall(r'getenv\("(ASAC_[A-Z0-9_]+)"\)', text))
+        used |= set(re.findall(r"environ(?:\.get)?[\(\[]'(ASAC_[A-Z0-9_]+)'", text))
+    assert len(used) >= 15, used
+    design = (root / 'DESIGN.md').read_text()
+    section = design[design.index('## 11. Switches'):]
+    missing = sorted(v for v in used if v not in section)
+    assert not missing, f'switches not documented in DESIGN.md §11: {missing}'
