@@ -391,7 +391,12 @@ int asac_peer_timeouts(int reset);
 
 /* asac_sac_step without its tail: [polyak,] target_y, q_backward, reduce_adam(q), policy_backward,
  * reduce_adam(pi), post.  `with_polyak` = 0 when the caller has enqueued asac_sac_polyak itself
- * (e.g. on a parallel graph branch).  `peers` != NULL: gradients are averaged over the ranks. */
+ * (e.g. on a parallel graph branch).  `peers` != NULL: gradients are averaged over the ranks.
+ * Same results as the stand-alone calls in that order, bit for bit; what this entry point adds is knowledge of
+ * the sequence: each kernel runs its predecessor-independent prologue before griddepcontrol.wait, the train pass
+ * leaves the policy's pre-activations for the policy backward (scratch: the tile slices of work->grad_pi_part)
+ * and the policy backward leaves Q_i(s_b, a_b) for the post pass (scratch: work->tq, which therefore holds the
+ * ONLINE critics' values after the call). */
 int asac_sac_step_networks(const AsacSacConfig *cfg, const AsacSacParams *prm, const AsacSacBatch *batch,
                            const AsacSacWork *work, int with_polyak, const AsacPeerTable *peers,
                            void *stream);
